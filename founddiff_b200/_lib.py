@@ -1,0 +1,98 @@
+"""ctypes binding of the C-ABI CUDA library (include/founddiff_b200.h).
+
+There is NO CPU or PyTorch fallback: if the shared library is missing it is built in-tree with nvcc
+(founddiff_b200/build.py); if that fails, importing the ops raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_long, c_void_p
+
+from . import build as _build
+
+FD_F32, FD_BF16, FD_F16 = 0, 1, 2
+
+EXPORTS = [
+    "fd_version", "fd_selective_scan_fwd", "fd_conv2d_simt", "fd_conv2d_tc_supported", "fd_conv2d_tc_plan_create",
+    "fd_conv2d_tc_run", "fd_conv2d_tc_plan_destroy", "fd_init_conv7x7", "fd_ln_modulate", "fd_dwconv3x3_silu_scan",
+    "fd_xdt_proj", "fd_merge_ln_gate", "fd_dwconv3x3_qkv_gram", "fd_attn_weff", "fd_gn_stats", "fd_gn_silu_add",
+    "fd_linear_small", "fd_time_sinusoid", "fd_sampler_init", "fd_final_conv_update", "fd_unnormalize",
+]
+
+
+class ConvParams(Structure):
+    """Mirror of fd_conv_params."""
+    _fields_ = [
+        ("src0", c_void_p), ("src1", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("gate", c_void_p),
+        ("addend", c_void_p), ("out", c_void_p), ("gn_sums", c_void_p),
+        ("c0", c_int), ("c1", c_int), ("B", c_int), ("Hin", c_int), ("Win", c_int), ("Cout", c_int),
+        ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int), ("upsample", c_int),
+        ("silu_from", c_int), ("gate_stride", c_int), ("gn_groups", c_int), ("per_batch_weight", c_int),
+        ("dtype", c_int),
+    ]
+
+
+class FdError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building first if needed) the CUDA library.  Raises if it cannot be had — no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # stale-but-present library is still usable (e.g. no nvcc on this box)
+            if not os.path.exists(path):
+                raise FdError(f"founddiff_b200: CUDA library missing and nvcc build failed: {e}") from e
+    lib = ctypes.CDLL(path)
+    V, I, F, L = c_void_p, c_int, c_float, c_long
+    sig = {
+        "fd_selective_scan_fwd": [V] * 8 + [I] * 7 + [V],
+        "fd_conv2d_simt": [POINTER(ConvParams), V],
+        "fd_conv2d_tc_supported": [POINTER(ConvParams)],
+        "fd_conv2d_tc_plan_create": [POINTER(ConvParams), POINTER(c_void_p)],
+        "fd_conv2d_tc_run": [V, V],
+        "fd_init_conv7x7": [V] * 5 + [I] * 5 + [V],
+        "fd_ln_modulate": [V] * 6 + [I] * 4 + [F, I, V],
+        "fd_dwconv3x3_silu_scan": [V, I, V, V, V, I, I, I, I, I, V],
+        "fd_xdt_proj": [V] * 6 + [I] * 6 + [V],
+        "fd_merge_ln_gate": [V, V, I, I, V, V, V, V, V, I, I, I, I, F, I, V],
+        "fd_dwconv3x3_qkv_gram": [V] * 5 + [I] * 5 + [V],
+        "fd_attn_weff": [V] * 5 + [I] * 3 + [V],
+        "fd_gn_stats": [V, V, I, I, I, I, I, V],
+        "fd_gn_silu_add": [V] * 6 + [I] * 4 + [F, I, V],
+        "fd_linear_small": [V] * 5 + [I] * 5 + [V],
+        "fd_time_sinusoid": [V, V, I, I, V],
+        "fd_sampler_init": [V, V, F, V, V, V, L, V],
+        "fd_final_conv_update": [V] * 11 + [L, I, I, V],
+        "fd_unnormalize": [V, V, L, V],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    lib.fd_version.restype = c_char_p
+    lib.fd_version.argtypes = []
+    lib.fd_conv2d_tc_plan_destroy.argtypes = [c_void_p]
+    lib.fd_conv2d_tc_plan_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        kind = {-1: "bad argument", -2: "unsupported shape/dtype", -3: "CUDA driver entry point unavailable"}.get(
+            rc, f"CUDA error {rc}")
+        raise FdError(f"{what}: {kind}")

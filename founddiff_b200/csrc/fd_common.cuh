@@ -1,0 +1,98 @@
+// Shared device helpers for the founddiff_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/founddiff_b200.h"
+
+#define FD_DEVINL __device__ __forceinline__
+
+// Every extern "C" entry point returns 0 or a cudaError_t value; nothing throws across the ABI.
+#define FD_LAUNCH_CHECK()                        \
+    do {                                         \
+        cudaError_t e__ = cudaPeekAtLastError(); \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)
+
+template <typename T> struct fd_type;
+template <> struct fd_type<float> {
+    static FD_DEVINL float ld(const float* p) { return *p; }
+    static FD_DEVINL void st(float* p, float v) { *p = v; }
+};
+template <> struct fd_type<__nv_bfloat16> {
+    static FD_DEVINL float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    static FD_DEVINL void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <> struct fd_type<__half> {
+    static FD_DEVINL float ld(const __half* p) { return __half2float(*p); }
+    static FD_DEVINL void st(__half* p, float v) { *p = __float2half_rn(v); }
+};
+
+template <typename T> FD_DEVINL float fd_ld(const T* p) { return fd_type<T>::ld(p); }
+template <typename T> FD_DEVINL void fd_st(T* p, float v) { fd_type<T>::st(p, v); }
+
+// Vector of 8 (16-bit types) or 4 (float) elements = 16 bytes.
+template <typename T> struct fd_vec { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T, int N> FD_DEVINL void fd_ldv(const T* p, float (&v)[N]);
+template <> FD_DEVINL void fd_ldv<float, 4>(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> FD_DEVINL void fd_ldv<__nv_bfloat16, 8>(const __nv_bfloat16* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> FD_DEVINL void fd_ldv<__half, 8>(const __half* p, float (&v)[8]) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <typename T, int N> FD_DEVINL void fd_stv(T* p, const float (&v)[N]);
+template <> FD_DEVINL void fd_stv<float, 4>(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> FD_DEVINL void fd_stv<__nv_bfloat16, 8>(__nv_bfloat16* p, const float (&v)[8]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+}
+template <> FD_DEVINL void fd_stv<__half, 8>(__half* p, const float (&v)[8]) {
+    uint4 t;
+    __half2* h = reinterpret_cast<__half2*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+}
+
+FD_DEVINL float fd_silu(float x) { return x / (1.f + __expf(-x)); }
+FD_DEVINL float fd_softplus20(float x) { return x <= 20.f ? log1pf(__expf(x)) : x; }
+
+FD_DEVINL float fd_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+FD_DEVINL float fd_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// dtype dispatch for the extern "C" wrappers
+#define FD_DISPATCH_DTYPE(dtype, T, ...)                                           \
+    switch (dtype) {                                                               \
+        case FD_F32: { using T = float; __VA_ARGS__; break; }                      \
+        case FD_BF16: { using T = __nv_bfloat16; __VA_ARGS__; break; }             \
+        case FD_F16: { using T = __half; __VA_ARGS__; break; }                     \
+        default: return FD_ERR_BAD_ARGUMENT;                                       \
+    }
+
+static inline int fd_cdiv(long a, long b) { return (int)((a + b - 1) / b); }

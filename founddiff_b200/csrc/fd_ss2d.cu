@@ -1,0 +1,313 @@
+// SS2D producer / consumer kernels around the selective scan (src/emamba2.py:186-262, 295-367, 713-751).
+//
+//   fd_dwconv3x3_silu_scan : NHWC x-half of xz -> depthwise 3x3 + bias + SiLU -> 4-direction scan layout
+//   fd_xdt_proj            : x_proj / dt_proj on the scan layout
+//   fd_merge_ln_gate       : scan layout -> NHWC, LayerNorm(D), * z + local
+//
+// Scan layout: xs[b, k, d, l], L = (H/2)*(W/2); pixel (h, w) belongs to k = (h&1) | ((w&1)<<1);
+//   k in {0,2} (even h): l = (h/2)*(W/2) + (w/2)   (row-major sub-grid)
+//   k in {1,3} (odd  h): l = (w/2)*(H/2) + (h/2)   (column-major sub-grid)            emamba2.py:207-210
+// Both transposing kernels stage a 32x32-pixel x 16-channel tile in shared memory so that global reads are
+// 16-byte vectors along channels and global writes are 16-byte vectors along l (and vice versa).
+#include "fd_common.cuh"
+
+namespace {
+
+constexpr int TS = 32;        // spatial tile edge (pixels)
+constexpr int TH2 = TS / 2;   // sub-grid tile edge
+constexpr int CH = 16;        // channels per tile
+
+FD_DEVINL int scan_class(int py, int px) { return (py & 1) | ((px & 1) << 1); }
+// index inside the 16x16 sub-grid tile, in the direction's own scan order
+FD_DEVINL int scan_local(int k, int py, int px) { return (k & 1) ? (px >> 1) * TH2 + (py >> 1) : (py >> 1) * TH2 + (px >> 1); }
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_scan_kernel(const T* __restrict__ xz, int ld, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, T* __restrict__ xs, int H, int W,
+                                                          int D, int vec_ok) {
+    constexpr int VEC = fd_vec<T>::N;
+    constexpr int NVC = CH / VEC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_in = reinterpret_cast<T*>(smem_raw);                      // [(TS+2)*(TS+2)][CH]
+    T* s_out = s_in + (TS + 2) * (TS + 2) * CH;                    // [CH][4][TH2*TH2]
+    float* s_w = reinterpret_cast<float*>(s_out + CH * 4 * TH2 * TH2);  // [9][CH] + [CH]
+
+    const int c0 = blockIdx.x * CH;
+    const int tiles_w = (W + TS - 1) / TS;
+    const int ty0 = (blockIdx.y / tiles_w) * TS, tx0 = (blockIdx.y % tiles_w) * TS;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < 10 * CH; i += 256) {
+        const int c = i % CH, tap = i / CH;
+        s_w[i] = tap < 9 ? w[(long)(c0 + c) * 9 + tap] : (bias ? bias[c0 + c] : 0.f);
+    }
+    for (int i = tid; i < (TS + 2) * (TS + 2) * NVC; i += 256) {
+        const int pix = i / NVC, vc = i % NVC;
+        const int h = ty0 + pix / (TS + 2) - 1, ww = tx0 + pix % (TS + 2) - 1;
+        float v[VEC];
+        if (h >= 0 && h < H && ww >= 0 && ww < W) {
+            fd_ldv<T, VEC>(xz + (((long)b * H + h) * W + ww) * ld + c0 + vc * VEC, v);
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v[e] = 0.f;
+        }
+        fd_stv<T, VEC>(s_in + pix * CH + vc * VEC, v);
+    }
+    __syncthreads();
+    for (int i = tid; i < TS * TS * NVC; i += 256) {
+        const int pix = i / NVC, vc = i % NVC;
+        const int py = pix / TS, px = pix % TS;
+        float acc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = s_w[9 * CH + vc * VEC + e];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                float v[VEC];
+                fd_ldv<T, VEC>(s_in + ((py + dy) * (TS + 2) + px + dx) * CH + vc * VEC, v);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] = fmaf(v[e], s_w[(dy * 3 + dx) * CH + vc * VEC + e], acc[e]);
+            }
+        const int k = scan_class(py, px);
+        const int idx = scan_local(k, py, px);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) fd_st(s_out + ((vc * VEC + e) * 4 + k) * (TH2 * TH2) + idx, fd_silu(acc[e]));
+    }
+    __syncthreads();
+    // write runs of TH2 consecutive l
+    const int H2 = H / 2, W2 = W / 2, L = H2 * W2;
+    const int h2_0 = ty0 / 2, w2_0 = tx0 / 2;
+    constexpr int VPR = TH2 / VEC;  // vectors per run
+    for (int i = tid; i < CH * 4 * TH2 * VPR; i += 256) {
+        const int vv = i % VPR, r = (i / VPR) % TH2, k = (i / (VPR * TH2)) % 4, c = i / (VPR * TH2 * 4);
+        long l;
+        int nvalid;
+        bool run_ok;
+        if (k & 1) { run_ok = (w2_0 + r) < W2; l = (long)(w2_0 + r) * H2 + h2_0; nvalid = H2 - h2_0; }
+        else       { run_ok = (h2_0 + r) < H2; l = (long)(h2_0 + r) * W2 + w2_0; nvalid = W2 - w2_0; }
+        if (!run_ok) continue;
+        const T* sp = s_out + (c * 4 + k) * (TH2 * TH2) + r * TH2 + vv * VEC;
+        T* gp = xs + (((long)b * 4 + k) * D + c0 + c) * L + l + vv * VEC;
+        if (vec_ok && (vv + 1) * VEC <= nvalid) {
+            *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e)
+                if (vv * VEC + e < nvalid) gp[e] = sp[e];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// x_proj + dt_proj.  One thread per l (coalesced along l), CCP >= R+2N accumulators in registers.
+template <typename T, int CCP>
+__global__ void __launch_bounds__(128) xdt_proj_kernel(const T* __restrict__ xs, const float* __restrict__ x_proj_w,
+                                                       const float* __restrict__ dt_w, T* __restrict__ dts,
+                                                       float* __restrict__ Bs, float* __restrict__ Cs, int D, int L, int R,
+                                                       int N) {
+    constexpr int DT = 32;  // d-chunk of x_proj_w staged in shared memory
+    __shared__ float s_w[CCP][DT + 1];
+    const int CC = R + 2 * N;
+    const int bk = blockIdx.y;  // b*4 + k
+    const int k = bk & 3;
+    const int l = blockIdx.x * 128 + threadIdx.x;
+    const bool ok = l < L;
+    const T* xr = xs + (long)bk * D * L;
+    const float* wx = x_proj_w + (long)k * CC * D;
+    float acc[CCP];
+#pragma unroll
+    for (int c = 0; c < CCP; ++c) acc[c] = 0.f;
+    for (int d0 = 0; d0 < D; d0 += DT) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < CCP * DT; i += 128) {
+            const int c = i / DT, dd = i % DT;
+            s_w[c][dd] = (c < CC && d0 + dd < D) ? wx[(long)c * D + d0 + dd] : 0.f;
+        }
+        __syncthreads();
+        const int dn = min(DT, D - d0);
+        for (int dd = 0; dd < dn; ++dd) {
+            const float x = ok ? fd_ld(xr + (long)(d0 + dd) * L + l) : 0.f;
+#pragma unroll
+            for (int c = 0; c < CCP; ++c) acc[c] = fmaf(s_w[c][dd], x, acc[c]);
+        }
+    }
+    if (!ok) return;
+    float* Bo = Bs + (long)bk * N * L;
+    float* Co = Cs + (long)bk * N * L;
+#pragma unroll
+    for (int c = 0; c < CCP; ++c) {
+        if (c >= R && c < R + N) Bo[(long)(c - R) * L + l] = acc[c];
+        if (c >= R + N && c < CC) Co[(long)(c - R - N) * L + l] = acc[c];
+    }
+    const float* wd = dt_w + (long)k * D * R;
+    T* dr = dts + (long)bk * D * L;
+    for (int d = 0; d < D; ++d) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < CCP; ++r)
+            if (r < R) s = fmaf(__ldg(wd + (long)d * R + r), acc[r], s);
+        fd_st(dr + (long)d * L + l, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// merge, pass 1: per-pixel LayerNorm statistics straight from the scan layout (thread per l, loop over d).
+template <typename T>
+__global__ void __launch_bounds__(256) merge_stats_kernel(const T* __restrict__ ys, float* __restrict__ stats, int H, int W,
+                                                          int D, float eps) {
+    const int H2 = H / 2, W2 = W / 2, L = H2 * W2;
+    const int bk = blockIdx.y, b = bk >> 2, k = bk & 3;
+    const int l = blockIdx.x * 256 + threadIdx.x;
+    if (l >= L) return;
+    const T* yr = ys + (long)bk * D * L + l;
+    float s = 0.f, q = 0.f;
+    // two-pass-free: shifted sums around the first element keep the cancellation benign
+    const float x0 = fd_ld(yr);
+    for (int d = 0; d < D; ++d) {
+        const float v = fd_ld(yr + (long)d * L) - x0;
+        s += v;
+        q = fmaf(v, v, q);
+    }
+    const float m = s / (float)D;
+    const float var = fmaxf(q / (float)D - m * m, 0.f);
+    int h, w;
+    if (k & 1) { w = 2 * (l / H2) + (k >> 1); h = 2 * (l % H2) + 1; }
+    else       { h = 2 * (l / W2); w = 2 * (l % W2) + (k >> 1); }
+    float* o = stats + (((long)b * H + h) * W + w) * 2;
+    o[0] = m + x0;
+    o[1] = rsqrtf(var + eps);
+}
+
+// merge, pass 2: tile transpose + normalise + gate.
+template <typename T>
+__global__ void __launch_bounds__(256) merge_apply_kernel(const T* __restrict__ ys, const T* __restrict__ xz, int ld, int z_off,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ local, const float* __restrict__ stats,
+                                                          T* __restrict__ out, int H, int W, int D, int vec_ok) {
+    constexpr int VEC = fd_vec<T>::N;
+    constexpr int NVC = CH / VEC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_y = reinterpret_cast<T*>(smem_raw);  // [CH][4][TH2*TH2]
+    const int c0 = blockIdx.x * CH;
+    const int tiles_w = (W + TS - 1) / TS;
+    const int ty0 = (blockIdx.y / tiles_w) * TS, tx0 = (blockIdx.y % tiles_w) * TS;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int H2 = H / 2, W2 = W / 2, L = H2 * W2;
+    const int h2_0 = ty0 / 2, w2_0 = tx0 / 2;
+    constexpr int VPR = TH2 / VEC;
+    for (int i = tid; i < CH * 4 * TH2 * VPR; i += 256) {
+        const int vv = i % VPR, r = (i / VPR) % TH2, k = (i / (VPR * TH2)) % 4, c = i / (VPR * TH2 * 4);
+        long l;
+        int nvalid;
+        bool run_ok;
+        if (k & 1) { run_ok = (w2_0 + r) < W2; l = (long)(w2_0 + r) * H2 + h2_0; nvalid = H2 - h2_0; }
+        else       { run_ok = (h2_0 + r) < H2; l = (long)(h2_0 + r) * W2 + w2_0; nvalid = W2 - w2_0; }
+        T* sp = s_y + (c * 4 + k) * (TH2 * TH2) + r * TH2 + vv * VEC;
+        const T* gp = ys + (((long)b * 4 + k) * D + c0 + c) * L + l + vv * VEC;
+        if (run_ok && vec_ok && (vv + 1) * VEC <= nvalid) {
+            *reinterpret_cast<uint4*>(sp) = *reinterpret_cast<const uint4*>(gp);
+        } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) fd_st(sp + e, (run_ok && vv * VEC + e < nvalid) ? fd_ld(gp + e) : 0.f);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < TS * TS * NVC; i += 256) {
+        const int pix = i / NVC, vc = i % NVC;
+        const int py = pix / TS, px = pix % TS;
+        const int h = ty0 + py, w = tx0 + px;
+        if (h >= H || w >= W) continue;
+        const int k = scan_class(py, px);
+        const int idx = scan_local(k, py, px);
+        const long gpix = ((long)b * H + h) * W + w;
+        const float mean = stats[gpix * 2], rstd = stats[gpix * 2 + 1];
+        float z[VEC], o[VEC];
+        fd_ldv<T, VEC>(xz + gpix * ld + z_off + c0 + vc * VEC, z);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int c = vc * VEC + e;
+            const float y = fd_ld(s_y + (c * 4 + k) * (TH2 * TH2) + idx);
+            const float n = (y - mean) * rstd * __ldg(gamma + c0 + c) + __ldg(beta + c0 + c);
+            o[e] = n * z[e] + __ldg(local + (long)b * D + c0 + c);
+        }
+        fd_stv<T, VEC>(out + gpix * D + c0 + vc * VEC, o);
+    }
+}
+
+}  // namespace
+
+extern "C" int fd_dwconv3x3_silu_scan(const void* xz, int ld, const float* w, const float* bias, void* xs, int B, int H,
+                                      int W, int D, int dtype, cudaStream_t stream) {
+    if (!xz || !w || !xs || B <= 0 || H <= 0 || W <= 0 || D <= 0 || ld < D) return FD_ERR_BAD_ARGUMENT;
+    if ((H & 1) || (W & 1) || D % CH) return FD_ERR_UNSUPPORTED;
+    dim3 grid(D / CH, fd_cdiv(H, TS) * fd_cdiv(W, TS), B);
+    FD_DISPATCH_DTYPE(dtype, T, {
+        constexpr int VEC = fd_vec<T>::N;
+        if (ld % VEC) return FD_ERR_UNSUPPORTED;
+        const int vec_ok = ((H / 2) % VEC == 0) && ((W / 2) % VEC == 0);
+        const size_t smem = ((size_t)(TS + 2) * (TS + 2) * CH + (size_t)CH * 4 * TH2 * TH2) * sizeof(T) + 10 * CH * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(dwconv_scan_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        dwconv_scan_kernel<T><<<grid, 256, smem, stream>>>((const T*)xz, ld, w, bias, (T*)xs, H, W, D, vec_ok);
+    });
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T>
+static int xdt_launch(const void* xs, const float* x_proj_w, const float* dt_w, void* dts, float* Bs, float* Cs, int B, int D,
+                      int L, int R, int N, cudaStream_t stream) {
+    const int CC = R + 2 * N;
+    dim3 grid(fd_cdiv(L, 128), B * 4);
+#define XDT_CASE(P)                                                                                               \
+    if (CC <= P) {                                                                                                \
+        xdt_proj_kernel<T, P><<<grid, 128, 0, stream>>>((const T*)xs, x_proj_w, dt_w, (T*)dts, Bs, Cs, D, L, R, N); \
+        FD_LAUNCH_CHECK();                                                                                        \
+        return 0;                                                                                                 \
+    }
+    XDT_CASE(16) XDT_CASE(32) XDT_CASE(48) XDT_CASE(96)
+#undef XDT_CASE
+    return FD_ERR_UNSUPPORTED;
+}
+
+extern "C" int fd_xdt_proj(const void* xs, const float* x_proj_w, const float* dt_w, void* dts, float* Bs, float* Cs, int B,
+                           int D, int L, int R, int N, int dtype, cudaStream_t stream) {
+    if (!xs || !x_proj_w || !dt_w || !dts || !Bs || !Cs || B <= 0 || D <= 0 || L <= 0 || R <= 0 || N <= 0) return FD_ERR_BAD_ARGUMENT;
+    FD_DISPATCH_DTYPE(dtype, T, return xdt_launch<T>(xs, x_proj_w, dt_w, dts, Bs, Cs, B, D, L, R, N, stream));
+    return 0;
+}
+
+extern "C" int fd_merge_ln_gate(const void* ys, const void* xz, int ld, int z_off, const float* gamma, const float* beta,
+                                const float* local, float* stats_ws, void* out, int B, int H, int W, int D, float eps,
+                                int dtype, cudaStream_t stream) {
+    if (!ys || !xz || !gamma || !beta || !local || !stats_ws || !out || B <= 0 || H <= 0 || W <= 0 || D <= 0) return FD_ERR_BAD_ARGUMENT;
+    if ((H & 1) || (W & 1) || D % CH || ld < z_off + D) return FD_ERR_UNSUPPORTED;
+    const int L = (H / 2) * (W / 2);
+    FD_DISPATCH_DTYPE(dtype, T, {
+        constexpr int VEC = fd_vec<T>::N;
+        if (ld % VEC || z_off % VEC) return FD_ERR_UNSUPPORTED;
+        const int vec_ok = ((H / 2) % VEC == 0) && ((W / 2) % VEC == 0);
+        merge_stats_kernel<T><<<dim3(fd_cdiv(L, 256), B * 4), 256, 0, stream>>>((const T*)ys, stats_ws, H, W, D, eps);
+        FD_LAUNCH_CHECK();
+        const size_t smem = (size_t)CH * 4 * TH2 * TH2 * sizeof(T);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(merge_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        dim3 grid(D / CH, fd_cdiv(H, TS) * fd_cdiv(W, TS), B);
+        merge_apply_kernel<T><<<grid, 256, smem, stream>>>((const T*)ys, (const T*)xz, ld, z_off, gamma, beta, local,
+                                                           stats_ws, (T*)out, H, W, D, vec_ok);
+    });
+    FD_LAUNCH_CHECK();
+    return 0;
+}

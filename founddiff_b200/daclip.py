@@ -1,0 +1,99 @@
+"""DA-CLIP conditioning (dose / anatomy embeddings), computed ONCE per slice and cached across timesteps.
+
+The reference recomputes `CLIPIQA.forward` inside every `Unet.forward` (src/DADiff.py:692), including a 12-layer
+text transformer whose only consumer (`probs`) is discarded.  Both embeddings are pure functions of the low-dose
+input slice (channel 1 of the Unet input), so the sampler calls `embed()` once per `sample()` call and the
+per-step path never sees the encoder (SURVEY.md "Five facts" #4).
+
+This is off the per-step hot path; it runs the RN50 `ModifiedResNet` visual tower + `AttentionPool2d`
+(pos_embedding=False) + head1/head2 (src/DACLIP.py:168-349, 1180-1211) as fp32 library convolutions (cuDNN, TF32
+disabled) — the role SURVEY.md §7 step 7 assigns to it.
+"""
+from __future__ import annotations
+
+from typing import Dict, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+PREFIX = "dose_encoder."
+
+
+def _bn(sd, p, x):
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        training=False, eps=1e-5)
+
+
+class DAClipEncoder:
+    """Holds the frozen visual-tower weights on one device and maps (B,1,H,W) slices in [-1,1] to
+    (dose_embedding (B,1024), context_embedding (B,256))."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, layers: Sequence[int] = (3, 4, 6, 3), heads: int = 32):
+        self.sd = {k: v.detach().to(device=device, dtype=torch.float32 if v.is_floating_point() else v.dtype)
+                   for k, v in state_dict.items() if k.startswith(PREFIX)}
+        self.layers, self.heads = tuple(layers), heads
+        # BatchNorm (eval) folded into the preceding bias-free convolution once, at load time
+        self._folded = {}
+
+    def _conv_bn(self, x, conv, bn, stride=1, padding=0):
+        key = conv
+        if key not in self._folded:
+            sd = self.sd
+            w = sd[conv + ".weight"]
+            s = sd[bn + ".weight"] * torch.rsqrt(sd[bn + ".running_var"] + 1e-5)
+            self._folded[key] = ((w * s[:, None, None, None]).contiguous(), (sd[bn + ".bias"] - sd[bn + ".running_mean"] * s).contiguous())
+        w, b = self._folded[key]
+        return F.conv2d(x, w, b, stride=stride, padding=padding)
+
+    def _bottleneck(self, p, x, stride):
+        out = F.relu(self._conv_bn(x, p + "conv1", p + "bn1"))
+        out = F.relu(self._conv_bn(out, p + "conv2", p + "bn2", padding=1))
+        if stride > 1:
+            out = F.avg_pool2d(out, stride)
+        out = self._conv_bn(out, p + "conv3", p + "bn3")
+        if (p + "downsample.0.weight") in self.sd:
+            idt = F.avg_pool2d(x, stride) if stride > 1 else x
+            idt = self._conv_bn(idt, p + "downsample.0", p + "downsample.1")
+        else:
+            idt = x
+        return F.relu(out + idt)
+
+    @torch.no_grad()
+    def embed(self, x_input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        sd = self.sd
+        v = PREFIX + "clip_model.visual."
+        prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            x = x_input.to(torch.float32).repeat(1, 3, 1, 1)                       # src/DADiff.py:692
+            x = F.relu(self._conv_bn(x, v + "conv1", v + "bn1", stride=2, padding=1))
+            x = F.relu(self._conv_bn(x, v + "conv2", v + "bn2", padding=1))
+            x = F.relu(self._conv_bn(x, v + "conv3", v + "bn3", padding=1))
+            x = F.avg_pool2d(x, 2)
+            for li, blocks in enumerate(self.layers):
+                for bi in range(blocks):
+                    x = self._bottleneck(f"{v}layer{li + 1}.{bi}.", x, 2 if (li > 0 and bi == 0) else 1)
+            a = v + "attnpool."
+            B, C, H, W = x.shape
+            tok = x.reshape(B, C, H * W).permute(2, 0, 1)
+            tok = torch.cat([tok.mean(dim=0, keepdim=True), tok], dim=0)          # (HW+1, B, C)
+            q = F.linear(tok[:1], sd[a + "q_proj.weight"], sd[a + "q_proj.bias"])
+            k = F.linear(tok, sd[a + "k_proj.weight"], sd[a + "k_proj.bias"])
+            vv = F.linear(tok, sd[a + "v_proj.weight"], sd[a + "v_proj.bias"])
+            hd = C // self.heads
+            q = q.reshape(1, B, self.heads, hd) * (hd ** -0.5)
+            k = k.reshape(-1, B, self.heads, hd)
+            vv = vv.reshape(-1, B, self.heads, hd)
+            att = torch.einsum("qbhd,kbhd->bhqk", q, k).softmax(dim=-1)
+            o = torch.einsum("bhqk,kbhd->qbhd", att, vv).reshape(1, B, C)
+            feat = F.linear(o, sd[a + "c_proj.weight"], sd[a + "c_proj.bias"])[0]
+            h1 = F.linear(F.relu(F.linear(feat, sd[PREFIX + "head1.0.weight"], sd[PREFIX + "head1.0.bias"])),
+                          sd[PREFIX + "head1.2.weight"], sd[PREFIX + "head1.2.bias"])
+            h2 = F.linear(F.relu(F.linear(feat, sd[PREFIX + "head2.0.weight"], sd[PREFIX + "head2.0.bias"])),
+                          sd[PREFIX + "head2.2.weight"], sd[PREFIX + "head2.2.bias"])
+            dose = h1 / h1.norm(dim=-1, keepdim=True)                              # src/DACLIP.py:1210
+            ctx = F.normalize(h2, dim=1)                                           # src/DACLIP.py:1207
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        return dose.contiguous(), ctx.contiguous()

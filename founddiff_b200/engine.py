@@ -1,0 +1,367 @@
+"""The per-timestep denoiser engine: FoundDiff's `Unet.forward` (src/DADiff.py:685-740) as a fixed sequence of
+hand-written sm_100a kernels over pre-allocated channels-last buffers.
+
+One `UnetEngine` is built for a fixed (batch, H, W, dtype): weights are packed once (weight standardisation
+folded, conv weights in (Cout, KH, KW, Cin) order, -exp(A_logs) precomputed, the nine adaLN projections
+concatenated), every buffer is allocated once, every convolution call site is bound to its buffers once
+(`ops.Conv`) — so one timestep is pointer-stable and can be captured in a CUDA graph by the sampler.
+
+Data layout in HBM (B slices, level l has H_l x W_l pixels, C_l channels, D = 2C, L = H_l*W_l/4):
+    trunk / block-internal activations : (B, H_l, W_l, C)            channels-last, `dtype`
+    xz                                 : (B, H_l, W_l, 4C)           [x | silu(z)]
+    xs, dts, ys (scan layout)          : (B, 4, D, L)                emamba2.py:207-210 direction order
+    Bs, Cs                             : (B, 4, N, L)  fp32
+    conditioning                       : t (B,256), mods (B, sum 6C), locals (B, D) fp32
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .weights import UnetConfig
+
+GN_GROUPS = 8
+BASE_MID_STATE = 32            # int(base_d_state * 2 ** 3), src/DADiff.py:649
+
+
+def ws_fold(w: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """WeightStandardizedConv2d (src/DADiff.py:145-152) is a constant at inference: fold it once (fp32 eps)."""
+    w = w.float()
+    mean = w.mean(dim=(1, 2, 3), keepdim=True)
+    var = w.var(dim=(1, 2, 3), unbiased=False, keepdim=True)
+    return (w - mean) * (var + eps).rsqrt()
+
+
+def pack_conv(w: torch.Tensor, dtype, device) -> torch.Tensor:
+    """(Cout, Cin, KH, KW) -> (Cout, KH, KW, Cin) contiguous in the activation dtype."""
+    return w.float().permute(0, 2, 3, 1).contiguous().to(device=device, dtype=dtype)
+
+
+class UnetEngine:
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: UnetConfig, B: int, H: int, W: int,
+                 dtype: torch.dtype = torch.bfloat16, device="cuda", prefer_tc: bool = True):
+        self.cfg, self.B, self.H, self.W, self.dtype, self.device = cfg, B, H, W, dtype, torch.device(device)
+        self.prefer_tc = prefer_tc
+        self._bufs: Dict[str, torch.Tensor] = {}
+        f32 = lambda k: sd[k].detach().to(device=self.device, dtype=torch.float32).contiguous()  # noqa: E731
+        self.f32 = f32
+        self.sd = sd
+        d, td = cfg.dim, cfg.time_dim
+        dev = self.device
+
+        # ---- conditioning weights (fp32, tiny) --------------------------------------------------------
+        self.time_w1, self.time_b1 = f32("time_mlp.1.weight"), f32("time_mlp.1.bias")
+        self.time_w2, self.time_b2 = f32("time_mlp.3.weight"), f32("time_mlp.3.bias")
+        self.text_w0, self.text_b0 = f32("text_mlp.0.weight"), f32("text_mlp.0.bias")
+        self.text_w2, self.text_b2 = f32("text_mlp.2.weight"), f32("text_mlp.2.bias")
+        self.prompt = f32("prompt")
+        self.pm_w, self.pm_b = f32("prompt_mlp.weight"), f32("prompt_mlp.bias")
+        blocks = cfg.mamba_blocks()
+        self.mod_total = sum(6 * C for _, C, _ in blocks)
+        self.adaln_w = torch.cat([f32(f"{p}.adaLN_modulation.1.weight") for p, _, _ in blocks], dim=0).contiguous()
+        self.adaln_b = torch.cat([f32(f"{p}.adaLN_modulation.1.bias") for p, _, _ in blocks], dim=0).contiguous()
+        self.local_w = torch.cat([f32(f"{p}.mamba.attn.0.weight") for p, _, _ in blocks], dim=0).contiguous()
+        self.local_total = sum(2 * C for _, C, _ in blocks)
+
+        # ---- per-step conditioning buffers ---------------------------------------------------------------
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        self.time = z(B)                    # alphas_cumsum[t] * num_timesteps, written by the sampler
+        self.t_sin, self.t_hid, self.t_emb = z(B, d), z(B, td), z(B, td)
+        self.prompt_emb = z(B, td)
+        self.mods = z(B, self.mod_total)
+        self.locals = z(B, self.local_total)
+        self.txt_hid, self.txt_out = z(B, td), z(B, td)
+
+        # ---- accumulators zeroed once per forward ----------------------------------------------------------
+        self._acc_size = 0
+        self._acc_slices = []
+
+        def acc(n):
+            off = self._acc_size
+            self._acc_size += n
+            self._acc_slices.append((off, n))
+            return len(self._acc_slices) - 1
+        self._acc = acc
+
+        mod_off = loc_off = 0
+        self._mod_offsets, self._loc_offsets = {}, {}
+        for p, C, _N in blocks:
+            self._mod_offsets[p], self._loc_offsets[p] = mod_off, loc_off
+            mod_off += 6 * C
+            loc_off += 2 * C
+        self._local_views = []
+
+        # ---- build the layer list -----------------------------------------------------------------------
+        self.steps: List = []          # list of callables executed in order by forward()
+        self._acc_users = []
+        self._build(sd)
+        self.acc_buf = torch.zeros(max(self._acc_size, 1), device=dev, dtype=torch.float32)
+        for fn in self._acc_users:
+            fn()
+
+    # -------------------------------------------------------------------------------------------------------
+    def buf(self, name: str, *shape, dtype=None) -> torch.Tensor:
+        """Named arena: one allocation per name, grown to the largest request, returned as a view."""
+        dtype = dtype or self.dtype
+        n = int(math.prod(shape))
+        t = self._bufs.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            assert t is None, f"buffer {name} requested again with a larger size; allocate the maximum first"
+            t = torch.empty(n, device=self.device, dtype=dtype)
+            self._bufs[name] = t
+        return t[:n].view(*shape)
+
+    def _acc_view(self, idx, *shape):
+        off, n = self._acc_slices[idx]
+        return self.acc_buf[off:off + n].view(*shape)
+
+    # -------------------------------------------------------------------------------------------------------
+    def _build(self, sd):
+        cfg, B, H, W, dt, dev = self.cfg, self.B, self.H, self.W, self.dtype, self.device
+        if H % 16 or W % 16:
+            raise ValueError("H and W must be multiples of 16 (three 2x downsamplings + the stride-2 scan sub-grids)")
+        f32 = self.f32
+        d = cfg.dim
+        sizes = [(H >> i, W >> i) for i in range(4)]
+        up_c = [co for (_ci, co) in reversed(cfg.in_out)]          # Mamba width of ups.0..3 (512, 256, 128, 64)
+        # widest trunk at each level (SURVEY.md section 3.2 "Levels")
+        cmax = [max(cfg.in_out[0][0], up_c[3]), max(cfg.in_out[1][0], up_c[2]), max(cfg.in_out[2][0], up_c[1]),
+                max(cfg.in_out[3][0], cfg.mid_dim, up_c[0])]
+        nmax = [max(cfg.down_states[i], cfg.up_states[3 - i]) for i in range(4)]
+        nmax[3] = max(nmax[3], 8 * 4)
+        for l, ((h, w), C) in enumerate(zip(sizes, cmax)):
+            P = h * w
+            for name, ch in (("TA", C), ("TB", C), ("A", C), ("XZ", 4 * C), ("XS", 2 * C), ("DTS", 2 * C), ("YS", 2 * C),
+                             ("G", 2 * C), ("QKV", 3 * C), ("V", C), ("Y", C), ("SK", C)):
+                self.buf(f"{name}{l}", B, P, ch)
+            self.buf(f"H{l}", B, P, cfg.in_out[l][0])
+            self.buf(f"WEFF{l}", B, C, C)
+            self.buf(f"STAT{l}", B, P, 2, dtype=torch.float32)
+            self.buf(f"BS{l}", B, 4, nmax[l], P // 4, dtype=torch.float32)
+            self.buf(f"CS{l}", B, 4, nmax[l], P // 4, dtype=torch.float32)
+
+        # init conv (fp32 images -> level-0 trunk); `r = x.clone()` (src/DADiff.py:701) lives in its own buffer R
+        self.init_w, self.init_b = f32("init_conv.weight"), f32("init_conv.bias")
+        self.x_t = torch.zeros(B, H * W, device=dev, dtype=torch.float32)
+        self.x_input = torch.zeros(B, H * W, device=dev, dtype=torch.float32)
+        R = self.buf("R", B, H * W, d)
+        self.steps.append(lambda: ops.init_conv7x7(self.x_t, self.x_input, self.init_w, self.init_b, R, B, H, W))
+
+        def conv_plain(key_w, key_b, src, dst, h, w, k, stride=1, upsample=False):
+            c = ops.Conv(src, pack_conv(sd[key_w], dt, dev), dst, B=B, Hin=h, Win=w, KH=k, KW=k, stride=stride,
+                         pad=1, upsample=upsample, bias=f32(key_b), prefer_tc=self.prefer_tc)
+            self.steps.append(c.run)
+
+        cur = R
+        for i, (ci, co) in enumerate(cfg.in_out):                                   # src/DADiff.py:712-719
+            h, w = sizes[i]
+            P = h * w
+            ta = self.buf(f"TA{i}", B, P, ci)
+            self._mamba(f"downs.{i}.1", i, cur, ta, ci, cfg.down_states[i], h, w)
+            hs = self.buf(f"H{i}", B, P, ci)
+            self._resblock(f"downs.{i}.0", i, [ta], hs, ci, h, w)
+            if i < 3:
+                nh, nw = sizes[i + 1]
+                cur = self.buf(f"TA{i + 1}", B, nh * nw, co)
+                conv_plain(f"downs.{i}.2.weight", f"downs.{i}.2.bias", hs, cur, h, w, 4, stride=2)
+            else:
+                cur = self.buf(f"TB{i}", B, P, co)
+                conv_plain(f"downs.{i}.2.weight", f"downs.{i}.2.bias", hs, cur, h, w, 3)
+        h, w = sizes[3]
+        md = cfg.mid_dim
+        x = self.buf("TA3", B, h * w, md)
+        self._resblock("mid_block", 3, [cur], x, md, h, w)                         # :721
+        self._mamba("mid_attn", 3, x, x, md, BASE_MID_STATE, h, w)                 # :722
+        cur = x
+        for i, (ci, co) in enumerate(reversed(cfg.in_out)):                         # :725-731
+            l = 3 - i
+            h, w = sizes[l]
+            P = h * w
+            hs = self.buf(f"H{l}", B, P, ci)
+            tb = self.buf(f"TB{l}", B, P, co)
+            self._resblock(f"ups.{i}.0", l, [cur, hs], tb, co, h, w)
+            self._mamba(f"ups.{i}.1", l, tb, tb, co, cfg.up_states[i], h, w)
+            if i < 3:
+                nh, nw = sizes[l - 1]
+                cur = self.buf(f"TA{l - 1}", B, nh * nw, ci)
+                conv_plain(f"ups.{i}.2.1.weight", f"ups.{i}.2.1.bias", tb, cur, h, w, 3, upsample=True)
+            else:
+                cur = self.buf(f"TA{l}", B, P, ci)
+                conv_plain(f"ups.{i}.2.weight", f"ups.{i}.2.bias", tb, cur, h, w, 3)
+        h, w = sizes[0]
+        self.feat = self.buf("TB0", B, h * w, d)
+        self._resblock("final_res_block", 0, [cur, R], self.feat, d, h, w)         # :733-735
+        self.final_w = f32("final_conv.weight").reshape(-1).contiguous()
+        self.final_b = f32("final_conv.bias")
+
+    # -------------------------------------------------------------------------------------------------------
+    def _resblock(self, p, l, srcs, out, cout, h, w):
+        """SiLU(GN8(WSConv3x3(x))) + res_conv(x)  (src/DADiff.py:213-229, 397-430); x = cat(srcs)."""
+        sd, B, dt, dev = self.sd, self.B, self.dtype, self.device
+        f32 = self.f32
+        P = h * w
+        cin = sum(s.shape[-1] for s in srcs)
+        wc = pack_conv(ws_fold(sd[p + ".block1.proj.weight"]), dt, dev)
+        bc = f32(p + ".block1.proj.bias")
+        gamma, beta = f32(p + ".block1.norm.weight"), f32(p + ".block1.norm.bias")
+        y = self.buf(f"Y{l}", B, P, cout)
+        src1 = srcs[1] if len(srcs) > 1 else None
+        acc = self._acc(B * GN_GROUPS * 2)
+        has_res = (p + ".res_conv.weight") in sd
+        if has_res:
+            sk = self.buf(f"SK{l}", B, P, cout)
+            wr, br = pack_conv(sd[p + ".res_conv.weight"], dt, dev), f32(p + ".res_conv.bias")
+        else:
+            assert len(srcs) == 1 and cin == cout
+            sk = srcs[0]
+        for t in srcs:
+            assert t.data_ptr() not in (y.data_ptr(), out.data_ptr()) and (not has_res or t.data_ptr() != sk.data_ptr())
+        holder = {}
+
+        def bind():
+            sums = self._acc_view(acc, B, GN_GROUPS, 2)
+            holder["sums"] = sums
+            holder["conv"] = ops.Conv(srcs[0], wc, y, B=B, Hin=h, Win=w, KH=3, KW=3, pad=1, src1=src1, bias=bc,
+                                      gn_sums=sums, gn_groups=GN_GROUPS, prefer_tc=self.prefer_tc)
+            if has_res:
+                holder["rconv"] = ops.Conv(srcs[0], wr, sk, B=B, Hin=h, Win=w, src1=src1, bias=br, prefer_tc=self.prefer_tc)
+        self._acc_users.append(bind)
+
+        def run():
+            holder["conv"].run()
+            if has_res:
+                holder["rconv"].run()
+            ops.gn_silu_add(y, holder["sums"], gamma, beta, sk, out, B, P, cout, GN_GROUPS)
+        self.steps.append(run)
+
+    # -------------------------------------------------------------------------------------------------------
+    def _mamba(self, p, l, x_in, x, C, N, h, w):
+        """Mamba_block (src/DADiff.py:477-488).  Reads trunk `x_in`, leaves the result in trunk `x` (may alias)."""
+        sd, B, dt, dev = self.sd, self.B, self.dtype, self.device
+        f32 = self.f32
+        P, D, L = h * w, 2 * C, h * w // 4
+        R = math.ceil(C / 16)
+        heads = C // 32
+        mo, lo = self._mod_offsets[p], self._loc_offsets[p]
+        MS = self.mod_total
+        mods = self.mods
+        sh1, sc1, g1, sh2, sc2, g2 = (_view_ptr(mods[:, mo + j * C:mo + (j + 1) * C]) for j in range(6))
+        n1w, n1b = f32(p + ".norm1.weight"), f32(p + ".norm1.bias")
+        a = self.buf(f"A{l}", B, P, C)
+        xz = self.buf(f"XZ{l}", B, P, 4 * C)
+        xs, dts, ys = (self.buf(f"{n}{l}", B, 4, D, L) for n in ("XS", "DTS", "YS"))
+        Bs, Cs = self.buf(f"BS{l}", B, 4, N, L, dtype=torch.float32), self.buf(f"CS{l}", B, 4, N, L, dtype=torch.float32)
+        g = self.buf(f"G{l}", B, P, D)
+        stat = self.buf(f"STAT{l}", B, P, 2, dtype=torch.float32)
+        qkv = self.buf(f"QKV{l}", B, P, 3 * C)
+        v = self.buf(f"V{l}", B, P, C)
+        weff = self.buf(f"WEFF{l}", B, C, C)
+        to_dt = lambda t: t.detach().to(device=dev, dtype=dt).contiguous()  # noqa: E731
+        in_w = to_dt(sd[p + ".mamba.in_proj.weight"])                                                  # (4C, C)
+        out_w = to_dt(sd[p + ".mamba.out_proj.weight"])                                                # (C, 2C)
+        dw_w, dw_b = f32(p + ".mamba.conv2d.weight").reshape(D, 9).contiguous(), f32(p + ".mamba.conv2d.bias")
+        xp_w, dtp_w = f32(p + ".mamba.x_proj_weight"), f32(p + ".mamba.dt_projs_weight")
+        dt_bias = f32(p + ".mamba.dt_projs_bias").reshape(-1).contiguous()
+        A_neg = (-torch.exp(f32(p + ".mamba.A_logs"))).contiguous()                                   # emamba2.py:344
+        Ds = f32(p + ".mamba.Ds")
+        on_w, on_b = f32(p + ".mamba.out_norm.weight"), f32(p + ".mamba.out_norm.bias")
+        qkv_w = to_dt(sd[p + ".attn_blk.qkv.weight"].reshape(3 * C, C))
+        qdw_w = f32(p + ".attn_blk.qkv_dwconv.weight").reshape(3 * C, 9).contiguous()
+        proj_w = f32(p + ".attn_blk.project_out.weight").reshape(C, C).contiguous()
+        temp = f32(p + ".attn_blk.temperature").reshape(-1).contiguous()
+        acc_g = self._acc(B * heads * 32 * 32)
+        acc_q = self._acc(B * 2 * C)
+        tc = self.prefer_tc
+        holder = {}
+        c_in = ops.Conv(a, in_w, xz, B=B, Hin=h, Win=w, silu_from=2 * C, prefer_tc=tc)
+        c_out = ops.Conv(g, out_w, x, B=B, Hin=h, Win=w, gate=g1, gate_stride=MS, addend=x_in, prefer_tc=tc)
+        c_qkv = ops.Conv(a, qkv_w, qkv, B=B, Hin=h, Win=w, prefer_tc=tc)
+        c_att = ops.Conv(v, weff, x, B=B, Hin=h, Win=w, gate=g2, gate_stride=MS, addend=x, per_batch_weight=True,
+                         prefer_tc=tc)
+        local_c = _LocalView(self.locals, lo, D)
+        self._local_views.append(local_c)
+
+        def bind():
+            holder["gram"] = self._acc_view(acc_g, B, heads, 32, 32)
+            holder["qk"] = self._acc_view(acc_q, B, 2, C)
+        self._acc_users.append(bind)
+
+        def run():
+            ops.ln_modulate(x_in, a, n1w, n1b, sh1, sc1, MS, B, P, C, 1e-5)
+            c_in.run()
+            ops.dwconv3x3_silu_scan(xz, 4 * C, dw_w, dw_b, xs, B, h, w, D)
+            ops.xdt_proj(xs, xp_w, dtp_w, dts, Bs, Cs, B, D, L, R, N)
+            ops.selective_scan_fwd(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs, Cs, Ds, dt_bias, True,
+                                   out=ys.view(B, 4 * D, L))
+            ops.merge_ln_gate(ys, xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), stat, g, B, h, w, D)
+            c_out.run()
+            ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
+            c_qkv.run()
+            ops.dwconv3x3_qkv_gram(qkv, qdw_w, v, holder["gram"], holder["qk"], B, h, w, C)
+            ops.attn_weff(holder["gram"], holder["qk"], temp, proj_w, weff, B, C)
+            c_att.run()
+        self.steps.append(run)
+        return x
+
+    # -------------------------------------------------------------------------------------------------------
+    def set_condition(self, dose_emb: torch.Tensor, ctx_emb: torch.Tensor):
+        """Per-slice constants (computed once per sample() call, never per step): the prompt embedding
+        prompt_mlp(softmax(text_mlp(dose)) * prompt) (src/DADiff.py:706-707) and every SS2D `local` vector
+        SiLU(Linear(256 -> 2C)(ctx)) (src/emamba2.py:522-525, 715)."""
+        B = self.B
+        ops.linear_small(dose_emb.float().contiguous(), self.text_w0, self.text_b0, self.txt_hid, act_out=1)
+        ops.linear_small(self.txt_hid, self.text_w2, self.text_b2, self.txt_out)
+        sm = torch.softmax(self.txt_out, dim=1) * self.prompt
+        ops.linear_small(sm.contiguous(), self.pm_w, self.pm_b, self.prompt_emb)
+        ops.linear_small(ctx_emb.float().contiguous(), self.local_w, None, self.locals, act_out=1)
+        for lv in self._local_views:
+            lv.refresh()
+
+    def conditioning(self):
+        """Per-step: time embedding (+ prompt) and the 9 adaLN modulation vectors (src/DADiff.py:703-709, 484)."""
+        ops.time_sinusoid(self.time, self.t_sin)
+        ops.linear_small(self.t_sin, self.time_w1, self.time_b1, self.t_hid, act_out=2)
+        ops.linear_small(self.t_hid, self.time_w2, self.time_b2, self.t_emb, add=self.prompt_emb)
+        ops.linear_small(self.t_emb, self.adaln_w, self.adaln_b, self.mods, act_in=1)
+
+    def forward(self):
+        """One Unet evaluation on (self.x_t, self.x_input, self.time); the result is `self.feat`, the input of
+        final_conv, which the sampler fuses with the update (ops.final_conv_update)."""
+        self.acc_buf.zero_()
+        self.conditioning()
+        for fn in self.steps:
+            fn()
+        return self.feat
+
+
+class _LocalView:
+    """Dense (B, D) copy of one block's slice of the concatenated `locals` tensor (the kernel wants row stride D)."""
+
+    def __init__(self, full, off, D):
+        self.full, self.off, self.D = full, off, D
+        self._dense = torch.zeros(full.shape[0], D, device=full.device, dtype=torch.float32)
+
+    def refresh(self):
+        self._dense.copy_(self.full[:, self.off:self.off + self.D])
+
+    def dense(self):
+        return self._dense
+
+
+class _view_ptr:
+    """Marks a strided fp32 view whose base pointer is handed to a kernel together with an explicit row stride."""
+
+    def __init__(self, t: torch.Tensor):
+        assert t.dtype == torch.float32 and t.is_cuda
+        self.t = t
+        self.dtype = torch.float32
+        self.is_cuda = True
+
+    def is_contiguous(self):
+        return True
+
+    def data_ptr(self):
+        return self.t.data_ptr()

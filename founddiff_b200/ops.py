@@ -1,0 +1,180 @@
+"""Thin tensor-level wrappers over the C ABI (include/founddiff_b200.h).  PyTorch here is only the owner of device
+memory and streams: every function passes raw pointers + the current CUDA stream to a hand-written kernel.
+No function in this file has a PyTorch/CPU fallback; a non-CUDA tensor raises."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_void_p
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import FD_BF16, FD_F16, FD_F32, ConvParams, check
+
+_DT = {torch.float32: FD_F32, torch.bfloat16: FD_BF16, torch.float16: FD_F16}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise TypeError(f"unsupported activation dtype {dt}") from None
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.FdError("founddiff_b200 ops need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return c_void_p(t.data_ptr())
+
+
+def _f32(t: Optional[torch.Tensor]):
+    if t is not None and t.dtype != torch.float32:
+        raise TypeError("expected a float32 tensor")
+    return _p(t)
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def version() -> str:
+    return _lib.load().fd_version().decode()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def selective_scan_fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=True, out=None):
+    """u, delta: (b, KD, L) [fp32/bf16/fp16]; A: (KD, N) fp32; B, C: (b, K, N, L) fp32; D, delta_bias: (KD,) fp32."""
+    lib = _lib.load()
+    b, kd, L = u.shape
+    n, g = A.shape[1], B.shape[1]
+    assert delta.shape == u.shape and delta.dtype == u.dtype and A.shape[0] == kd
+    assert B.shape == (b, g, n, L) and C.shape == B.shape
+    y = torch.empty_like(u) if out is None else out
+    check(lib.fd_selective_scan_fwd(_p(u), _p(delta), _f32(A), _f32(B), _f32(C), _f32(D), _f32(delta_bias), _p(y),
+                                    b, kd, L, n, g, int(bool(delta_softplus)), dtype_code(u.dtype), _stream()),
+          "fd_selective_scan_fwd")
+    return y
+
+
+class Conv:
+    """One convolution / 1x1 GEMM call site (fd_conv_params).  `run()` launches it; buffers are bound at
+    construction so that the call is CUDA-graph friendly (and so that the tcgen05 path can bake TMA descriptors)."""
+
+    def __init__(self, src0, weight, out, *, B, Hin, Win, KH=1, KW=1, stride=1, pad=0, upsample=False, src1=None,
+                 bias=None, gate=None, gate_stride=0, addend=None, silu_from=None, gn_sums=None, gn_groups=0,
+                 per_batch_weight=False, prefer_tc=True):
+        lib = _lib.load()
+        c0 = src0.shape[-1]
+        c1 = src1.shape[-1] if src1 is not None else 0
+        cout = out.shape[-1]
+        p = ConvParams()
+        p.src0, p.src1, p.weight, p.out = _p(src0), _p(src1), _p(weight), _p(out)
+        p.bias, p.gate, p.addend, p.gn_sums = _f32(bias), _f32(gate), _p(addend), _f32(gn_sums)
+        p.c0, p.c1, p.B, p.Hin, p.Win, p.Cout = c0, c1, B, Hin, Win, cout
+        p.KH, p.KW, p.stride, p.pad, p.upsample = KH, KW, stride, pad, int(upsample)
+        p.silu_from = cout if silu_from is None else silu_from
+        p.gate_stride, p.gn_groups, p.per_batch_weight = gate_stride, gn_groups, int(per_batch_weight)
+        p.dtype = dtype_code(out.dtype)
+        assert src0.dtype == out.dtype == weight.dtype and (src1 is None or src1.dtype == out.dtype)
+        assert weight.numel() == (B if per_batch_weight else 1) * cout * KH * KW * (c0 + c1), (weight.shape, cout, KH, KW, c0, c1)
+        self.params = p
+        self._keep = (src0, src1, weight, out, bias, gate, addend, gn_sums)
+        self._lib = lib
+        self._plan = c_void_p()
+        self.uses_tc = False
+        if prefer_tc and lib.fd_conv2d_tc_supported(byref(p)):
+            check(lib.fd_conv2d_tc_plan_create(byref(p), byref(self._plan)), "fd_conv2d_tc_plan_create")
+            self.uses_tc = True
+
+    def run(self):
+        if self.uses_tc:
+            check(self._lib.fd_conv2d_tc_run(self._plan, _stream()), "fd_conv2d_tc_run")
+        else:
+            check(self._lib.fd_conv2d_simt(byref(self.params), _stream()), "fd_conv2d_simt")
+
+    def __del__(self):
+        try:
+            if self._plan:
+                self._lib.fd_conv2d_tc_plan_destroy(self._plan)
+        except Exception:
+            pass
+
+
+def init_conv7x7(x_t, x_input, weight, bias, out, B, H, W):
+    check(_lib.load().fd_init_conv7x7(_f32(x_t), _f32(x_input), _f32(weight), _f32(bias), _p(out), B, H, W,
+                                      out.shape[-1], dtype_code(out.dtype), _stream()), "fd_init_conv7x7")
+
+
+def ln_modulate(x, out, gamma, beta, shift, scale, mod_stride, B, P, C, eps):
+    check(_lib.load().fd_ln_modulate(_p(x), _p(out), _f32(gamma), _f32(beta), _f32(shift), _f32(scale), mod_stride,
+                                     B, P, C, float(eps), dtype_code(x.dtype), _stream()), "fd_ln_modulate")
+
+
+def dwconv3x3_silu_scan(xz, ld, w, bias, xs, B, H, W, D):
+    check(_lib.load().fd_dwconv3x3_silu_scan(_p(xz), ld, _f32(w), _f32(bias), _p(xs), B, H, W, D,
+                                             dtype_code(xz.dtype), _stream()), "fd_dwconv3x3_silu_scan")
+
+
+def xdt_proj(xs, x_proj_w, dt_w, dts, Bs, Cs, B, D, L, R, N):
+    check(_lib.load().fd_xdt_proj(_p(xs), _f32(x_proj_w), _f32(dt_w), _p(dts), _f32(Bs), _f32(Cs), B, D, L, R, N,
+                                  dtype_code(xs.dtype), _stream()), "fd_xdt_proj")
+
+
+def merge_ln_gate(ys, xz, ld, z_off, gamma, beta, local, stats_ws, out, B, H, W, D, eps=1e-5):
+    check(_lib.load().fd_merge_ln_gate(_p(ys), _p(xz), ld, z_off, _f32(gamma), _f32(beta), _f32(local), _f32(stats_ws),
+                                       _p(out), B, H, W, D, float(eps), dtype_code(ys.dtype), _stream()),
+          "fd_merge_ln_gate")
+
+
+def dwconv3x3_qkv_gram(qkv, w, v, gram, qk_sq, B, H, W, C):
+    check(_lib.load().fd_dwconv3x3_qkv_gram(_p(qkv), _f32(w), _p(v), _f32(gram), _f32(qk_sq), B, H, W, C,
+                                            dtype_code(qkv.dtype), _stream()), "fd_dwconv3x3_qkv_gram")
+
+
+def attn_weff(gram, qk_sq, temperature, proj_w, weff, B, C):
+    check(_lib.load().fd_attn_weff(_f32(gram), _f32(qk_sq), _f32(temperature), _f32(proj_w), _p(weff), B, C,
+                                   dtype_code(weff.dtype), _stream()), "fd_attn_weff")
+
+
+def gn_stats(y, sums, B, P, C, G):
+    check(_lib.load().fd_gn_stats(_p(y), _f32(sums), B, P, C, G, dtype_code(y.dtype), _stream()), "fd_gn_stats")
+
+
+def gn_silu_add(y, sums, gamma, beta, skip, out, B, P, C, G, eps=1e-5):
+    check(_lib.load().fd_gn_silu_add(_p(y), _f32(sums), _f32(gamma), _f32(beta), _p(skip), _p(out), B, P, C, G,
+                                     float(eps), dtype_code(y.dtype), _stream()), "fd_gn_silu_add")
+
+
+def linear_small(x, W, bias, out, *, add=None, act_in=0, act_out=0):
+    B, K = x.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and out.shape == (B, N)
+    check(_lib.load().fd_linear_small(_f32(x), _f32(W), _f32(bias), _f32(add), _f32(out), B, K, N, act_in, act_out,
+                                      _stream()), "fd_linear_small")
+
+
+def time_sinusoid(time, out):
+    B, dim = out.shape
+    check(_lib.load().fd_time_sinusoid(_f32(time), _f32(out), B, dim, _stream()), "fd_time_sinusoid")
+
+
+def sampler_init(ldct, noise, noise_scale, x_input, x_t, first):
+    check(_lib.load().fd_sampler_init(_f32(ldct), _f32(noise), float(noise_scale), _f32(x_input), _f32(x_t), _f32(first),
+                                      ldct.numel(), _stream()), "fd_sampler_init")
+
+
+def final_conv_update(feat, w, bias, x_input, x_t, noise, coef, x_next, pred_res=None, pred_noise=None, x_start=None):
+    npix = x_input.numel()
+    C = feat.shape[-1]
+    check(_lib.load().fd_final_conv_update(_p(feat), _f32(w), _f32(bias), _f32(x_input), _f32(x_t), _f32(noise), _f32(coef),
+                                           _f32(x_next), _f32(pred_res), _f32(pred_noise), _f32(x_start), npix, C,
+                                           dtype_code(feat.dtype), _stream()), "fd_final_conv_update")
+
+
+def unnormalize(x, out):
+    check(_lib.load().fd_unnormalize(_f32(x), _f32(out), x.numel(), _stream()), "fd_unnormalize")

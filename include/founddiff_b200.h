@@ -1,0 +1,189 @@
+/*
+ * founddiff_b200 — C ABI of the B200-native FoundDiff reverse-diffusion sampling path.
+ *
+ * Every entry point:
+ *   - takes raw DEVICE pointers, sizes and a cudaStream_t; the caller (PyTorch host code) owns all memory;
+ *   - never allocates, never synchronises, never reads device memory from the host -> stream-ordered and
+ *     CUDA-graph capturable (the tcgen05 GEMM additionally needs fd_gemm_plan objects built on the host
+ *     beforehand, they hold TMA descriptors only);
+ *   - returns 0 on success, a cudaError_t value (>0) for a CUDA failure, or FD_ERR_* (<0) for a bad argument;
+ *     nothing throws across the ABI.
+ *
+ * Activation layout everywhere: channels-last ("NHWC"), i.e. a (B, H, W, C) tensor is B*H*W rows of C contiguous
+ * elements.  `dtype` selects the activation storage type (fd_dtype); accumulation is always fp32.
+ *
+ * Each declaration cites the reference interface (file:line under the reference repo) that it replaces.
+ */
+#ifndef FOUNDDIFF_B200_H
+#define FOUNDDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+typedef enum { FD_F32 = 0, FD_BF16 = 1, FD_F16 = 2 } fd_dtype;
+
+#define FD_ERR_BAD_ARGUMENT (-1)
+#define FD_ERR_UNSUPPORTED (-2)
+#define FD_ERR_DRIVER (-3)
+
+/* Library / build identification ("founddiff_b200 <version> sm_100a"). */
+const char* fd_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Selective scan forward — replaces the third-party native op the reference calls:
+ *   selective_scan_cuda_core.fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, nrows)  src/emamba2.py:154
+ *   selective_scan_cuda.fwd(u, delta, A, B, C, D, None, delta_bias, delta_softplus)        src/emamba2.py:152
+ * u, delta, y: (batch, dim, seqlen) in `io_dtype`; A: (dim, dstate) fp32; Bm, Cm: (batch, ngroups, dstate,
+ * seqlen) fp32; D, delta_bias: (dim) fp32 or NULL.  Channel d uses group d / (dim / ngroups).
+ *   dt = delta + delta_bias; if delta_softplus: dt = dt <= 20 ? log1p(exp(dt)) : dt
+ *   h_n <- exp(dt*A[d,n]) * h_n + dt * B[n,l] * u[l];   y[l] = sum_n h_n * C[n,l] + D[d] * u[l]
+ * --------------------------------------------------------------------------------------------------------- */
+int fd_selective_scan_fwd(const void* u, const void* delta, const float* A, const float* Bm, const float* Cm,
+                          const float* D, const float* delta_bias, void* y, int batch, int dim, int seqlen,
+                          int dstate, int ngroups, int delta_softplus, int io_dtype, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / 1x1 GEMM with fused epilogue — replaces F.conv2d / nn.Linear call sites:
+ *   WeightStandardizedConv2d 3x3 (src/DADiff.py:139-154; standardisation folded into `weight` by the host),
+ *   Downsample 4x4 s2 (:135-136), Upsample nearest x2 + 3x3 (:128-133, `upsample`=1), plain 3x3 (:643, 675),
+ *   res_conv 1x1 (:407-408), SS2D in_proj/out_proj (src/emamba2.py:474, 519, 717, 748),
+ *   TransposedAttention qkv / project_out 1x1 (src/DADiff.py:258, 260), torch.cat inputs (:727, 733).
+ *
+ *   acc[m, n]  = sum_{kh,kw,ci} in[b, ho*stride-pad+kh, wo*stride-pad+kw, ci] * weight[(b,) n, kh, kw, ci]
+ *   v          = acc + bias[n];  if (n >= silu_from) v = silu(v)
+ *   out[m, n]  = (addend ? addend[m, n] : 0) + (gate ? gate[b*gate_stride + n] : 1) * v
+ *   gn_sums[b, n / (Cout/gn_groups), 0:2] += (sum v, sum v^2)          (optional GroupNorm partial statistics)
+ * `in` is the channel concatenation of src0 (c0 channels) and src1 (c1 channels, may be NULL/0).
+ * weight: (Cout, KH, KW, c0+c1) in `dtype`, or (B, Cout, KH, KW, c0+c1) when per_batch_weight.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* src0;
+    const void* src1;
+    const void* weight;
+    const float* bias;
+    const float* gate;
+    const void* addend;
+    void* out;
+    float* gn_sums;
+    int c0, c1;
+    int B, Hin, Win, Cout;
+    int KH, KW, stride, pad, upsample;
+    int silu_from;        /* >= Cout: no activation */
+    int gate_stride;      /* row stride (floats) of gate, e.g. 6*C for the adaLN modulation tensor */
+    int gn_groups;        /* used when gn_sums != NULL */
+    int per_batch_weight;
+    int dtype;
+} fd_conv_params;
+
+/* CUDA-core fp32-accumulate path (any dtype; the fp32 validation path and the fallback for odd shapes). */
+int fd_conv2d_simt(const fd_conv_params* p, cudaStream_t stream);
+
+/* tcgen05 / TMEM / TMA path (dtype bf16 or fp16, c0 and c1 multiples of 64 for k>1, ...).  A plan owns the TMA
+ * descriptors of one call site (pointers and shapes are baked in); create once, run many times. */
+typedef struct fd_gemm_plan fd_gemm_plan;
+int fd_conv2d_tc_supported(const fd_conv_params* p);
+int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** plan);
+int fd_conv2d_tc_run(const fd_gemm_plan* plan, cudaStream_t stream);
+void fd_conv2d_tc_plan_destroy(fd_gemm_plan* plan);
+
+/* init_conv: 7x7, pad 3, over cat(x_t, x_input) (two fp32 single-channel images) -> (B,H,W,Cout) in `dtype`.
+ * Replaces Unet.init_conv (src/DADiff.py:558, 700) + torch.cat (:1160).  weight: (Cout, 2, 7, 7) fp32. */
+int fd_init_conv7x7(const float* x_t, const float* x_input, const float* weight, const float* bias, void* out,
+                    int B, int H, int W, int Cout, int dtype, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * LayerNorm over C + adaLN modulate:  out = (LN(x) * gamma + beta) * (1 + scale[b]) + shift[b]
+ * Replaces nn.LayerNorm + modulate() (src/DADiff.py:450-451, 459, 461, 486-487).  gamma/beta may be NULL
+ * (norm2: elementwise_affine=False, eps=1e-6).  shift/scale: fp32, element (b, c) at [b*mod_stride + c].
+ * --------------------------------------------------------------------------------------------------------- */
+int fd_ln_modulate(const void* x, void* out, const float* gamma, const float* beta, const float* shift,
+                   const float* scale, int mod_stride, int B, int P, int C, float eps, int dtype,
+                   cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * SS2D producer: depthwise 3x3 (+bias) + SiLU over the x half of `xz`, written in the 4-direction scan layout.
+ * Replaces SS2D.conv2d + act (src/emamba2.py:480-488, 722) + EfficientScan.forward (:186-213).
+ * xz: (B,H,W,ld) rows, the D conv channels are columns [0, D).  w: (D,3,3) fp32.  xs: (B,4,D,L), L = H/2*W/2:
+ *   k=0: (even h, even w) row-major; k=1: (odd h, even w) column-major; k=2: (even h, odd w) row-major;
+ *   k=3: (odd h, odd w) column-major.                                   H and W must be even.
+ * --------------------------------------------------------------------------------------------------------- */
+int fd_dwconv3x3_silu_scan(const void* xz, int ld, const float* w, const float* bias, void* xs, int B, int H,
+                           int W, int D, int dtype, cudaStream_t stream);
+
+/* x_proj + dt_proj (src/emamba2.py:335-340): per direction k,
+ *   x_dbl = x_proj_w[k] (R+2N, D) @ xs[b,k] (D, L);  dts = dt_w[k] (D, R) @ x_dbl[:R];  Bs = x_dbl[R:R+N];  Cs = rest.
+ * dts: (B,4,D,L) in `dtype`; Bs, Cs: (B,4,N,L) fp32.  Weights fp32. */
+int fd_xdt_proj(const void* xs, const float* x_proj_w, const float* dt_w, void* dts, float* Bs, float* Cs, int B,
+                int D, int L, int R, int N, int dtype, cudaStream_t stream);
+
+/* SS2D consumer: EfficientMerge (src/emamba2.py:238-262) + out_norm LayerNorm(D) (:365) + y*z + local (:747-748).
+ * ys: (B,4,D,L); z = columns [z_off, z_off+D) of xz rows (already SiLU'd); local: (B, D) fp32; out: (B,H,W,D).
+ * stats_ws: caller-provided workspace of B*H*W*2 floats (per-pixel mean / rstd). */
+int fd_merge_ln_gate(const void* ys, const void* xz, int ld, int z_off, const float* gamma, const float* beta,
+                     const float* local, float* stats_ws, void* out, int B, int H, int W, int D, float eps, int dtype,
+                     cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * TransposedAttention (src/DADiff.py:263-285), C/32 heads of 32 channels.
+ * fd_dwconv3x3_qkv_gram: depthwise 3x3 over qkv (B,H,W,3C); writes v (B,H,W,C) and ACCUMULATES (atomics; zero
+ *   the buffers first) gram[b, head, i, j] = sum_p q_i k_j  and  qk_sq[b, 0:2, c] = sum_p q_c^2, k_c^2.
+ * fd_attn_weff: attn = softmax(gram / (max(|q_i|,1e-12) max(|k_j|,1e-12)) * temperature[head]) and folds it
+ *   into the output projection: weff[b, o, h*32+j] = sum_i proj_w[o, h*32+i] * attn[b,h,i,j]   (dtype),
+ *   so that project_out(attn @ v) == v @ weff[b]^T, a per-sample 1x1 GEMM (fd_conv2d_*, per_batch_weight).
+ * --------------------------------------------------------------------------------------------------------- */
+int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, float* gram, float* qk_sq, int B, int H,
+                          int W, int C, int dtype, cudaStream_t stream);
+int fd_attn_weff(const float* gram, const float* qk_sq, const float* temperature, const float* proj_w,
+                 void* weff, int B, int C, int dtype, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * GroupNorm(G) + SiLU + skip add (src/DADiff.py:213-229, 426-430):
+ *   fd_gn_stats:     sums[b, g, 0:2] += (sum, sum of squares) over the group (zero the buffer first)
+ *   fd_gn_silu_add:  out = silu((y - mean) * rstd * gamma + beta) + (skip ? skip : 0)
+ * --------------------------------------------------------------------------------------------------------- */
+int fd_gn_stats(const void* y, float* sums, int B, int P, int C, int G, int dtype, cudaStream_t stream);
+int fd_gn_silu_add(const void* y, const float* sums, const float* gamma, const float* beta, const void* skip,
+                   void* out, int B, int P, int C, int G, float eps, int dtype, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Small dense layers on (B, K) fp32 vectors: time_mlp, adaLN_modulation (src/DADiff.py:173-185, 463-466,
+ * 580-585).  out[b, n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] ) + add[b,n]
+ * act: 0 none, 1 SiLU, 2 GELU(erf), 3 ReLU.
+ * --------------------------------------------------------------------------------------------------------- */
+int fd_linear_small(const float* x, const float* W, const float* bias, const float* add, float* out, int B, int K,
+                    int N, int act_in, int act_out, cudaStream_t stream);
+/* SinusoidalPosEmb (src/DADiff.py:173-185): out[b] = cat(sin(t_b f_k), cos(t_b f_k)), f_k = exp(-k ln(1e4)/(dim/2-1)) */
+int fd_time_sinusoid(const float* time, float* out, int B, int dim, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Sampler (src/DADiff.py:1153-1209 model_predictions 'pred_res'; :1221-1230 p_sample; :1142-1151 q_posterior;
+ * :1317-1344 ddim update).  Images are fp32 (B, H*W).
+ * fd_sampler_init:  x_input = 2*ldct - 1;  x_t = x_input + noise_scale * noise;  first = (x_t + 1)/2
+ * fd_final_conv_update: final_conv 1x1 (C -> 1, src/DADiff.py:683, 740) fused with the whole update:
+ *   pred_res  = clamp(feat . w + bias, -1, 1)
+ *   x_start   = clamp(x_input - pred_res, -1, 1)
+ *   pred_noise= (x_t - x_input - (acs - 1) * pred_res) / bcs                       (written if non-NULL)
+ *   x_next    = c_xt * x_t + c_res * pred_res + c_x0 * x_start + c_noise * noise     (noise may be NULL)
+ *   with coef (DEVICE, fp32[6]) = {c_xt, c_res, c_x0, c_noise, acs = alphas_cumsum[t], bcs = betas_cumsum[t]}.
+ *   DDIM (eta=0): {1, -(acs_t - acs_next), 0, 0} and {0, 0, 1, 0} for the last pair;  ancestral:
+ *   {coef1[t], coef2[t], coef3[t], exp(0.5*logvar[t]) or 0 at t=0}.
+ * fd_unnormalize: out = (x + 1) / 2.
+ * --------------------------------------------------------------------------------------------------------- */
+int fd_sampler_init(const float* ldct, const float* noise, float noise_scale, float* x_input, float* x_t,
+                    float* first, long n, cudaStream_t stream);
+int fd_final_conv_update(const void* feat, const float* w, const float* bias, const float* x_input,
+                         const float* x_t, const float* noise, const float* coef, float* x_next, float* pred_res,
+                         float* pred_noise, float* x_start, long npix, int C, int dtype, cudaStream_t stream);
+int fd_unnormalize(const float* x, float* out, long n, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOUNDDIFF_B200_H */

@@ -12,8 +12,9 @@ extension, un-vendored and un-pinned; see oracle/selective_scan_ref.c): parity f
 "unpinned" — it is anchored on the published recurrence and an independent fp64 evaluation.
 
 The reference's floating-point arithmetic is fp32 throughout (train.py:141 amp=False), so is this.
-`rt` ("round-trip") is an optional hook applied wherever the CUDA path stores an activation to HBM; tests use it
-to model bf16 storage rounding.  Default: identity.
+`rt(tensor, kind)` ("round-trip") is an optional hook applied wherever the CUDA path stores an activation to
+HBM (kind "trunk" = the residual/skip stream, "inner" = block-internal tensors); tests use it to model bf16
+storage rounding.  Default: identity.
 """
 from __future__ import annotations
 
@@ -26,7 +27,7 @@ import torch.nn.functional as F
 from . import scan_cpu
 
 Tensor = torch.Tensor
-_ID = lambda t: t  # noqa: E731
+_ID = lambda t, kind="inner": t  # noqa: E731
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -145,7 +146,7 @@ def resnet_block(sd, p: str, x: Tensor, groups: int = 8, rt: Callable = _ID) -> 
         skip = F.conv2d(x, sd[p + ".res_conv.weight"], sd[p + ".res_conv.bias"])
     else:
         skip = x
-    return rt(h + skip)
+    return rt(h + skip, "trunk")
 
 
 def efficient_scan(x: Tensor) -> Tensor:
@@ -227,10 +228,10 @@ def mamba_block(sd, p: str, x: Tensor, c: Tensor, t: Tensor, rt: Callable = _ID,
     sh1, sc1, g1, sh2, sc2, g2 = [m[:, None, None, :] for m in mod.chunk(6, dim=1)]
     a = F.layer_norm(x, (C,), sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], eps=1e-5)
     a = rt(a * (1 + sc1) + sh1)
-    x = rt(x + g1 * ss2d(sd, p + ".mamba", a, c, rt, taps))                         # :486
+    x = rt(x + g1 * ss2d(sd, p + ".mamba", a, c, rt, taps), "trunk")                         # :486
     a = rt(F.layer_norm(x, (C,), None, None, eps=1e-6) * (1 + sc2) + sh2)
     att = transposed_attention(sd, p + ".attn_blk", a.permute(0, 3, 1, 2), C // 32, rt)
-    x = rt(x + g2 * att.permute(0, 2, 3, 1))                                        # :487
+    x = rt(x + g2 * att.permute(0, 2, 3, 1), "trunk")                                        # :487
     return x.permute(0, 3, 1, 2)
 
 
@@ -261,7 +262,7 @@ def unet_forward(sd, x: Tensor, time: Tensor, dose_emb: Optional[Tensor] = None,
     c = ctx_emb.unsqueeze(1)
     tap = (lambda k, v: taps.__setitem__(k, v.clone())) if taps is not None else (lambda k, v: None)
     tap("dose_emb", dose_emb), tap("ctx_emb", ctx_emb)
-    x = rt(F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=3))     # :700
+    x = rt(F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=3), "trunk")     # :700
     r = x
     t = time_embedding(sd, time, dim) + prompt_embedding(sd, dose_emb)              # :703-709
     tap("t_emb", t), tap("init_conv", x)
@@ -273,7 +274,7 @@ def unet_forward(sd, x: Tensor, time: Tensor, dose_emb: Optional[Tensor] = None,
         tap(f"downs.{i}.res", x)
         h.append(x)
         w, b = sd[f"downs.{i}.2.weight"], sd[f"downs.{i}.2.bias"]
-        x = rt(F.conv2d(x, w, b, stride=2, padding=1) if w.shape[-1] == 4 else F.conv2d(x, w, b, padding=1))
+        x = rt(F.conv2d(x, w, b, stride=2, padding=1) if w.shape[-1] == 4 else F.conv2d(x, w, b, padding=1), "trunk")
         tap(f"downs.{i}.down", x)
     x = resnet_block(sd, "mid_block", x, rt=rt)                                     # :721-722
     x = mamba_block(sd, "mid_attn", x, c, t, rt)
@@ -286,9 +287,9 @@ def unet_forward(sd, x: Tensor, time: Tensor, dose_emb: Optional[Tensor] = None,
         tap(f"ups.{i}.mamba", x)
         if i < 3:
             x = F.interpolate(x, scale_factor=2, mode="nearest")
-            x = rt(F.conv2d(x, sd[f"ups.{i}.2.1.weight"], sd[f"ups.{i}.2.1.bias"], padding=1))
+            x = rt(F.conv2d(x, sd[f"ups.{i}.2.1.weight"], sd[f"ups.{i}.2.1.bias"], padding=1), "trunk")
         else:
-            x = rt(F.conv2d(x, sd[f"ups.{i}.2.weight"], sd[f"ups.{i}.2.bias"], padding=1))
+            x = rt(F.conv2d(x, sd[f"ups.{i}.2.weight"], sd[f"ups.{i}.2.bias"], padding=1), "trunk")
         tap(f"ups.{i}.up", x)
     x = torch.cat((x, r), dim=1)                                                    # :733
     x = resnet_block(sd, "final_res_block", x, rt=rt)

@@ -1,0 +1,329 @@
+"""Per-kernel parity tests (GPU): every C-ABI entry point against the CPU oracle / a plain torch fp32 restatement of
+the same op, on seeded inputs.  Tolerances: fp32 storage 2e-5 rel-L2 (re-association only), bf16 storage 1e-2,
+fp16 3e-3 (the storage rounding of the OUTPUT alone is 2^-9 / 2^-11)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+from oracle import founddiff_oracle as O
+from oracle import scan_cpu
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [torch.float32, torch.bfloat16, torch.float16]
+TOL = {torch.float32: 2e-5, torch.bfloat16: 1e-2, torch.float16: 3e-3}
+
+
+def rel(a, b):
+    return O.rel_l2(a.detach().float().cpu(), b.detach().float().cpu())
+
+
+def nhwc(x, dt):          # (B,C,H,W) cpu -> (B,H*W,C) cuda
+    B, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B, H * W, C).contiguous().to("cuda", dt)
+
+
+def nchw(x, H, W):        # (B,P,C) cuda -> (B,C,H,W) cpu fp32
+    B, P, C = x.shape
+    return x.float().cpu().reshape(B, H, W, C).permute(0, 3, 1, 2)
+
+
+def q(x, dt):             # storage rounding of an input
+    return x.to(dt).float()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from founddiff_b200 import ops as _ops
+    assert "sm_100a" in _ops.version()
+    return _ops
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 4, 8, 4, 300), (1, 4, 16, 16, 65), (2, 1, 4, 32, 1), (2, 4, 32, 8, 1024),
+                                   (1, 4, 8, 32, 2048), (1, 2, 6, 5, 77)])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_selective_scan(ops, shape, dt):
+    b, K, Dk, N, L = shape
+    g = torch.Generator().manual_seed(L + N)
+    u = q(torch.randn(b, K * Dk, L, generator=g), dt)
+    delta = q(torch.randn(b, K * Dk, L, generator=g) * 2, dt)
+    if L >= 5:
+        delta[0, 0, :5] = 25.0
+    A = -torch.exp(torch.randn(K * Dk, N, generator=g) * 0.5)
+    Bm, Cm = torch.randn(b, K, N, L, generator=g), torch.randn(b, K, N, L, generator=g)
+    D, bias = torch.randn(K * Dk, generator=g), torch.randn(K * Dk, generator=g)
+    ref = scan_cpu.selective_scan_fwd(u, delta, A, Bm, Cm, D, bias, True)
+    c = lambda t: t.cuda()
+    y = ops.selective_scan_fwd(c(u).to(dt), c(delta).to(dt), c(A), c(Bm), c(Cm), c(D), c(bias), True)
+    assert rel(y, ref) < TOL[dt]
+    y2 = ops.selective_scan_fwd(c(u).to(dt), c(delta).to(dt), c(A), c(Bm), c(Cm), None, None, False)
+    ref2 = scan_cpu.selective_scan_fwd(u, delta, A, Bm, Cm, None, None, False)
+    assert rel(y2, ref2) < TOL[dt]
+
+
+def test_selective_scan_golden(ops):
+    g = load_golden("scan.npz")
+    for tag in "abc":
+        c = lambda k: g[f"{tag}.{k}"].cuda()
+        y = ops.selective_scan_fwd(c("u"), c("delta"), c("A"), c("B"), c("C"), c("D"), c("bias"), True)
+        assert rel(y, g[f"{tag}.y64"]) < 2e-6
+
+
+def test_selective_scan_module_is_dropin(ops):
+    """The reference-facing signatures of src/emamba2.py:152,154."""
+    from founddiff_b200 import selective_scan as S
+    g = load_golden("scan.npz")
+    c = lambda k: g[f"a.{k}"].cuda()
+    out, x = S.selective_scan_cuda_core.fwd(c("u"), c("delta"), c("A"), c("B"), c("C"), c("D"), c("bias"), True, 1)
+    assert x is None and rel(out, g["a.y64"]) < 2e-6
+    out2, _ = S.fwd(c("u"), c("delta"), c("A"), c("B"), c("C"), c("D"), None, c("bias"), True)
+    assert torch.equal(out, out2)
+    with pytest.raises(RuntimeError):
+        S.fwd(g["a.u"], g["a.delta"], g["a.A"], g["a.B"], g["a.C"], g["a.D"], None, g["a.bias"], True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # c0, c1, cout, k, stride, pad, upsample, H, W
+    (64, 0, 64, 3, 1, 1, False, 16, 24),
+    (64, 64, 64, 3, 1, 1, False, 8, 16),
+    (128, 64, 128, 1, 1, 0, False, 8, 12),
+    (64, 0, 128, 4, 2, 1, False, 16, 24),
+    (128, 0, 64, 3, 1, 1, True, 8, 12),
+    (64, 0, 256, 1, 1, 0, False, 16, 16),
+    (32, 0, 48, 3, 1, 1, False, 6, 10),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("dt", DTYPES)
+def test_conv2d_simt(ops, case, dt):
+    c0, c1, cout, k, stride, pad, up, H, W = case
+    B = 2
+    g = torch.Generator().manual_seed(c0 + cout + k)
+    x0 = q(torch.randn(B, c0, H, W, generator=g), dt)
+    x1 = q(torch.randn(B, c1, H, W, generator=g), dt) if c1 else None
+    w = q(torch.randn(cout, c0 + c1, k, k, generator=g) / math.sqrt((c0 + c1) * k * k), dt)
+    bias = torch.randn(cout, generator=g)
+    xin = torch.cat([x0, x1], dim=1) if c1 else x0
+    if up:
+        xin = F.interpolate(xin, scale_factor=2, mode="nearest")
+    ref = F.conv2d(xin, w, bias, stride=stride, padding=pad)
+    Ho, Wo = ref.shape[-2:]
+    out = torch.empty(B, Ho * Wo, cout, device="cuda", dtype=dt)
+    wp = w.permute(0, 2, 3, 1).contiguous().to("cuda", dt)
+    conv = ops.Conv(nhwc(x0, dt), wp, out, B=B, Hin=H, Win=W, KH=k, KW=k, stride=stride, pad=pad, upsample=up,
+                    src1=nhwc(x1, dt) if c1 else None, bias=bias.cuda(), prefer_tc=False)
+    conv.run()
+    assert rel(nchw(out, Ho, Wo), ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_conv2d_simt_epilogues(ops, dt):
+    B, C, H, W, cout = 2, 64, 8, 12, 128
+    g = torch.Generator().manual_seed(3)
+    x = q(torch.randn(B, C, H, W, generator=g), dt)
+    w = q(torch.randn(cout, C, 1, 1, generator=g) / 8, dt)
+    # (a) SiLU on the upper half (SS2D in_proj: x | silu(z))
+    ref = F.conv2d(x, w)
+    ref = torch.cat([ref[:, :cout // 2], F.silu(ref[:, cout // 2:])], dim=1)
+    out = torch.empty(B, H * W, cout, device="cuda", dtype=dt)
+    ops.Conv(nhwc(x, dt), w.reshape(cout, C).to("cuda", dt), out, B=B, Hin=H, Win=W, silu_from=cout // 2, prefer_tc=False).run()
+    assert rel(nchw(out, H, W), ref) < TOL[dt]
+    # (b) gate * acc + addend with a strided gate tensor, in place on the addend; per-batch weights; GN partial sums
+    mods = torch.randn(B, 3 * cout, generator=g)
+    add = q(torch.randn(B, cout, H, W, generator=g), dt)
+    wb = q(torch.randn(B, cout, C, generator=g) / 8, dt)
+    bias = torch.randn(cout, generator=g)
+    v = torch.stack([F.conv2d(x[b:b + 1], wb[b].reshape(cout, C, 1, 1), bias)[0] for b in range(B)])
+    ref = add + mods[:, cout:2 * cout, None, None] * v
+    buf = nhwc(add, dt)
+    sums = torch.zeros(B, 8, 2, device="cuda")
+    from founddiff_b200.engine import _view_ptr
+    mods_d = mods.cuda()
+    ops.Conv(nhwc(x, dt), wb.to("cuda", dt).contiguous(), buf, B=B, Hin=H, Win=W, bias=bias.cuda(),
+             gate=_view_ptr(mods_d[:, cout:2 * cout]), gate_stride=3 * cout, addend=buf, per_batch_weight=True,
+             gn_sums=sums, gn_groups=8, prefer_tc=False).run()
+    assert rel(nchw(buf, H, W), ref) < TOL[dt]
+    vg = v.reshape(B, 8, -1)
+    ref_sums = torch.stack([vg.sum(-1), (vg * vg).sum(-1)], dim=-1)
+    assert rel(sums, ref_sums) < 1e-4
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_init_conv7x7(ops, dt):
+    B, H, W = 2, 20, 36
+    g = torch.Generator().manual_seed(1)
+    xt, xi = torch.randn(B, 1, H, W, generator=g), torch.randn(B, 1, H, W, generator=g)
+    w, b = torch.randn(64, 2, 7, 7, generator=g) / 10, torch.randn(64, generator=g)
+    ref = F.conv2d(torch.cat([xt, xi], 1), w, b, padding=3)
+    out = torch.empty(B, H * W, 64, device="cuda", dtype=dt)
+    ops.init_conv7x7(xt.reshape(B, -1).cuda(), xi.reshape(B, -1).cuda(), w.cuda(), b.cuda(), out, B, H, W)
+    assert rel(nchw(out, H, W), ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 512, 1024])
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("affine", [True, False])
+def test_ln_modulate(ops, C, dt, affine):
+    from founddiff_b200.engine import _view_ptr
+    B, P = 2, 50
+    g = torch.Generator().manual_seed(C)
+    x = q(torch.randn(B, P, C, generator=g) * 2 + 0.5, dt)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    mods = torch.randn(B, 6 * C, generator=g)
+    eps = 1e-5 if affine else 1e-6
+    ref = F.layer_norm(x, (C,), gamma if affine else None, beta if affine else None, eps=eps)
+    ref = ref * (1 + mods[:, None, C:2 * C]) + mods[:, None, :C]
+    out = torch.empty(B, P, C, device="cuda", dtype=dt)
+    md = mods.cuda()
+    ops.ln_modulate(x.to("cuda", dt), out, gamma.cuda() if affine else None, beta.cuda() if affine else None,
+                    _view_ptr(md[:, :C]), _view_ptr(md[:, C:2 * C]), 6 * C, B, P, C, eps)
+    assert rel(out, ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("C", [64, 128, 512])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_groupnorm_silu_add(ops, C, dt):
+    B, H, W = 2, 12, 20
+    P = H * W
+    g = torch.Generator().manual_seed(C)
+    y = q(torch.randn(B, C, H, W, generator=g) * 3 + 1, dt)
+    skip = q(torch.randn(B, C, H, W, generator=g), dt)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = F.silu(F.group_norm(y, 8, gamma, beta, eps=1e-5)) + skip
+    sums = torch.zeros(B, 8, 2, device="cuda")
+    yd = nhwc(y, dt)
+    ops.gn_stats(yd, sums, B, P, C, 8)
+    out = torch.empty_like(yd)
+    ops.gn_silu_add(yd, sums, gamma.cuda(), beta.cuda(), nhwc(skip, dt), out, B, P, C, 8)
+    assert rel(nchw(out, H, W), ref) < TOL[dt]
+    ops.gn_silu_add(yd, sums, gamma.cuda(), beta.cuda(), None, out, B, P, C, 8)
+    assert rel(nchw(out, H, W), ref - skip) < TOL[dt]
+
+
+@pytest.mark.parametrize("hw", [(16, 24), (32, 32), (8, 12), (64, 32)])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_dwconv_scan_and_merge(ops, hw, dt):
+    """dwconv+SiLU+EfficientScan and EfficientMerge+LN+gate against the oracle's restatement of
+    src/emamba2.py:186-262."""
+    H, W = hw
+    B, C = 2, 32
+    D, L = 2 * C, H * W // 4
+    g = torch.Generator().manual_seed(H * W)
+    xz = q(torch.randn(B, H, W, 4 * C, generator=g), dt)
+    w, b = torch.randn(D, 1, 3, 3, generator=g) / 3, torch.randn(D, generator=g)
+    x = xz[..., :D].permute(0, 3, 1, 2)
+    ref_xs = O.efficient_scan(F.silu(F.conv2d(x, w, b, padding=1, groups=D)))
+    xs = torch.empty(B, 4, D, L, device="cuda", dtype=dt)
+    xzd = xz.reshape(B, H * W, 4 * C).to("cuda", dt)
+    ops.dwconv3x3_silu_scan(xzd, 4 * C, w.reshape(D, 9).cuda(), b.cuda(), xs, B, H, W, D)
+    assert rel(xs, ref_xs) < TOL[dt]
+    # merge
+    ys = q(torch.randn(B, 4, D, L, generator=g), dt)
+    gamma, beta, local = torch.randn(D, generator=g), torch.randn(D, generator=g), torch.randn(B, D, generator=g)
+    y = O.efficient_merge(ys, H, W).permute(0, 2, 3, 1)
+    ref = F.layer_norm(y, (D,), gamma, beta, eps=1e-5) * xz[..., D:2 * D] + local[:, None, None, :]
+    out = torch.empty(B, H * W, D, device="cuda", dtype=dt)
+    stat = torch.empty(B, H * W, 2, device="cuda")
+    ops.merge_ln_gate(ys.to("cuda", dt), xzd, 4 * C, D, gamma.cuda(), beta.cuda(), local.cuda(), stat, out, B, H, W, D)
+    assert rel(out.reshape(B, H, W, D), ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("cfg", [(128, 4, 4, 100), (128, 4, 8, 384), (256, 8, 16, 64), (1024, 32, 32, 40)])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_xdt_proj(ops, cfg, dt):
+    D, R, N, L = cfg
+    B = 2
+    g = torch.Generator().manual_seed(D + L)
+    xs = q(torch.randn(B, 4, D, L, generator=g), dt)
+    Wx = torch.randn(4, R + 2 * N, D, generator=g) / math.sqrt(D)
+    Wdt = torch.randn(4, D, R, generator=g) / math.sqrt(R)
+    x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, Wx)
+    dts_r, Bs_r, Cs_r = torch.split(x_dbl, [R, N, N], dim=2)
+    dts_r = torch.einsum("bkrl,kdr->bkdl", dts_r, Wdt)
+    dts = torch.empty(B, 4, D, L, device="cuda", dtype=dt)
+    Bs, Cs = torch.empty(B, 4, N, L, device="cuda"), torch.empty(B, 4, N, L, device="cuda")
+    ops.xdt_proj(xs.to("cuda", dt), Wx.cuda(), Wdt.cuda(), dts, Bs, Cs, B, D, L, R, N)
+    assert rel(dts, dts_r) < TOL[dt] and rel(Bs, Bs_r) < 2e-5 and rel(Cs, Cs_r) < 2e-5
+
+
+@pytest.mark.parametrize("C", [64, 128])
+@pytest.mark.parametrize("hw", [(16, 24), (8, 40)])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_transposed_attention(ops, C, hw, dt):
+    """dwconv+Gram, softmax/W_eff fold and the per-sample 1x1 GEMM together == TransposedAttention after the qkv
+    1x1 (src/DADiff.py:266-283)."""
+    H, W = hw
+    B, heads = 2, C // 32
+    g = torch.Generator().manual_seed(C + H)
+    qkv = q(torch.randn(B, 3 * C, H, W, generator=g), dt)
+    wdw = torch.randn(3 * C, 1, 3, 3, generator=g) / 3
+    wproj = torch.randn(C, C, 1, 1, generator=g) / math.sqrt(C)
+    temp = torch.rand(heads, 1, 1, generator=g) + 0.5
+    t = F.conv2d(qkv, wdw, padding=1, groups=3 * C)
+    qq, kk, vv = t.chunk(3, dim=1)
+    qn = F.normalize(qq.reshape(B, heads, 32, H * W), dim=-1)
+    kn = F.normalize(kk.reshape(B, heads, 32, H * W), dim=-1)
+    attn = ((qn @ kn.transpose(-2, -1)) * temp).softmax(dim=-1)
+    ref = F.conv2d((attn @ vv.reshape(B, heads, 32, H * W)).reshape(B, C, H, W), wproj)
+    v = torch.empty(B, H * W, C, device="cuda", dtype=dt)
+    gram = torch.zeros(B, heads, 32, 32, device="cuda")
+    qk = torch.zeros(B, 2, C, device="cuda")
+    ops.dwconv3x3_qkv_gram(nhwc(qkv, dt), wdw.reshape(3 * C, 9).cuda(), v, gram, qk, B, H, W, C)
+    assert rel(nchw(v, H, W), vv) < TOL[dt]
+    assert rel(gram, qq.reshape(B, heads, 32, -1) @ kk.reshape(B, heads, 32, -1).transpose(-2, -1)) < 1e-4
+    weff = torch.empty(B, C, C, device="cuda", dtype=dt)
+    ops.attn_weff(gram, qk, temp.reshape(-1).cuda(), wproj.reshape(C, C).cuda(), weff, B, C)
+    out = torch.empty(B, H * W, C, device="cuda", dtype=dt)
+    ops.Conv(v, weff, out, B=B, Hin=H, Win=W, per_batch_weight=True, prefer_tc=False).run()
+    assert rel(nchw(out, H, W), ref) < 2 * TOL[dt]
+
+
+def test_small_linear_and_time_embedding(ops):
+    g = torch.Generator().manual_seed(0)
+    B, K, N = 3, 256, 777
+    x, Wm, b, add = torch.randn(B, K, generator=g), torch.randn(N, K, generator=g) / 16, torch.randn(N, generator=g), torch.randn(B, N, generator=g)
+    out = torch.empty(B, N, device="cuda")
+    ops.linear_small(x.cuda(), Wm.cuda(), b.cuda(), out, add=add.cuda(), act_in=1, act_out=2)
+    assert rel(out, F.gelu(F.linear(F.silu(x), Wm, b)) + add) < 1e-5
+    ops.linear_small(x.cuda(), Wm.cuda(), None, out, act_out=3)
+    assert rel(out, F.relu(F.linear(x, Wm))) < 1e-5
+    time = torch.tensor([993.647, 719.666, 0.05001])
+    dim = 64
+    half = dim // 2
+    freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+    ref = torch.cat(((time[:, None] * freq).sin(), (time[:, None] * freq).cos()), dim=-1)
+    out = torch.empty(3, dim, device="cuda")
+    ops.time_sinusoid(time.cuda(), out)
+    assert (out.cpu() - ref).abs().max() < 2e-4
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_sampler_kernels(ops, dt):
+    g = torch.Generator().manual_seed(9)
+    B, P, C = 2, 300, 64
+    ldct, noise = torch.rand(B, P, generator=g), torch.randn(B, P, generator=g)
+    xi, xt, first = (torch.empty(B, P, device="cuda") for _ in range(3))
+    ops.sampler_init(ldct.cuda(), noise.cuda(), 0.1, xi, xt, first)
+    assert torch.allclose(xi.cpu(), ldct * 2 - 1, atol=1e-6) and torch.allclose(xt.cpu(), ldct * 2 - 1 + 0.1 * noise, atol=1e-6)
+    assert torch.allclose(first.cpu(), (ldct * 2 - 1 + 0.1 * noise + 1) / 2, atol=1e-6)
+    feat = q(torch.randn(B, P, C, generator=g), dt)
+    w, b = torch.randn(C, generator=g) / 4, torch.randn(1, generator=g)
+    coef = torch.tensor([0.7, -0.3, 0.2, 0.05, 0.72, 0.96, 0, 0])
+    n2 = torch.randn(B, P, generator=g)
+    pr = (feat @ w + b).clamp(-1, 1)
+    x0 = (xi.cpu() - pr).clamp(-1, 1)
+    pn = (xt.cpu() - xi.cpu() - (coef[4] - 1) * pr) / coef[5]
+    xn = coef[0] * xt.cpu() + coef[1] * pr + coef[2] * x0 + coef[3] * n2
+    o = [torch.empty(B, P, device="cuda") for _ in range(4)]
+    ops.final_conv_update(feat.to("cuda", dt), w.cuda(), b.cuda(), xi, xt, n2.cuda(), coef.cuda(), o[0], o[1], o[2], o[3])
+    for mine, ref in zip(o, (xn, pr, pn, x0)):
+        assert rel(mine, ref) < 1e-5
+    un = torch.empty(B, P, device="cuda")
+    ops.unnormalize(xt, un)
+    assert torch.allclose(un, (xt + 1) / 2)
