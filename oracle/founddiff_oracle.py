@@ -140,7 +140,7 @@ def ws_weight(w: Tensor, eps: float = 1e-5) -> Tensor:
 def resnet_block(sd, p: str, x: Tensor, groups: int = 8, rt: Callable = _ID) -> Tensor:
     """SiLU(GroupNorm8(WSConv3x3(x))) + res_conv(x)   (src/DADiff.py:213-229, 397-430)."""
     h = F.conv2d(x, ws_weight(sd[p + ".block1.proj.weight"]), sd[p + ".block1.proj.bias"], padding=1)
-    h = rt(h)
+    h = rt(h, "conv_out")
     h = F.silu(F.group_norm(h, groups, sd[p + ".block1.norm.weight"], sd[p + ".block1.norm.bias"], eps=1e-5))
     if (p + ".res_conv.weight") in sd:
         skip = F.conv2d(x, sd[p + ".res_conv.weight"], sd[p + ".res_conv.bias"])
@@ -180,10 +180,10 @@ def ss2d(sd, p: str, x: Tensor, c: Tensor, rt: Callable = _ID, taps: Optional[di
     local = F.silu(F.linear(c, sd[p + ".attn.0.weight"]))                           # (B,1,2C)  :522-525, 715
     xz = F.linear(x, sd[p + ".in_proj.weight"])                                     # :717
     xx, z = xz.chunk(2, dim=-1)
-    z = rt(F.silu(z))                                                               # :720
-    xx = rt(xx).permute(0, 3, 1, 2)
+    z = rt(F.silu(z), "z")                                                               # :720
+    xx = rt(xx, "xz_x").permute(0, 3, 1, 2)
     xx = F.silu(F.conv2d(xx, sd[p + ".conv2d.weight"], sd[p + ".conv2d.bias"], padding=1, groups=xx.shape[1]))  # :722
-    xx = rt(xx)
+    xx = rt(xx, "xs")
     D = xx.shape[1]
     Wx, Wdt = sd[p + ".x_proj_weight"], sd[p + ".dt_projs_weight"]
     K, _, R = Wdt.shape
@@ -191,27 +191,27 @@ def ss2d(sd, p: str, x: Tensor, c: Tensor, rt: Callable = _ID, taps: Optional[di
     xs = efficient_scan(xx)                                                         # (B,4,D,L)
     x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, Wx)                                  # :335
     dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-    dts = rt(torch.einsum("bkrl,kdr->bkdl", dts, Wdt))                              # :340
+    dts = rt(torch.einsum("bkrl,kdr->bkdl", dts, Wdt), "dts")                              # :340
     L = xs.shape[-1]
     As = -torch.exp(sd[p + ".A_logs"].float())                                      # :344
     ys = scan_cpu.selective_scan_fwd(xs.reshape(B, K * D, L), dts.reshape(B, K * D, L), As, Bs.contiguous(),
                                      Cs.contiguous(), sd[p + ".Ds"], sd[p + ".dt_projs_bias"].reshape(-1), True)
     if taps is not None:
         taps.update(xs=xs, dts=dts, Bs=Bs, Cs=Cs, ys=ys)
-    ys = rt(ys).reshape(B, K, D, L)
+    ys = rt(ys, "ys").reshape(B, K, D, L)
     y = efficient_merge(ys, H, W).permute(0, 2, 3, 1)                               # (B,H,W,D)  :358-365
     y = F.layer_norm(y, (D,), sd[p + ".out_norm.weight"], sd[p + ".out_norm.bias"], eps=1e-5)
-    y = rt(y * z + local.unsqueeze(1))                                              # :747-748
+    y = rt(y * z + local.unsqueeze(1), "gated")                                              # :747-748
     return F.linear(y, sd[p + ".out_proj.weight"])
 
 
 def transposed_attention(sd, p: str, x: Tensor, heads: int, rt: Callable = _ID) -> Tensor:
     """TransposedAttention.forward (src/DADiff.py:263-285). x: (B,C,H,W)."""
     B, C, H, W = x.shape
-    qkv = rt(F.conv2d(x, sd[p + ".qkv.weight"]))
+    qkv = rt(F.conv2d(x, sd[p + ".qkv.weight"]), "qkv")
     qkv = F.conv2d(qkv, sd[p + ".qkv_dwconv.weight"], padding=1, groups=3 * C)
     q, k, v = qkv.chunk(3, dim=1)
-    v = rt(v)
+    v = rt(v, "v")
     q = F.normalize(q.reshape(B, heads, C // heads, H * W), dim=-1)                 # :273
     k = F.normalize(k.reshape(B, heads, C // heads, H * W), dim=-1)
     v = v.reshape(B, heads, C // heads, H * W)
@@ -227,9 +227,9 @@ def mamba_block(sd, p: str, x: Tensor, c: Tensor, t: Tensor, rt: Callable = _ID,
     mod = F.linear(F.silu(t), sd[p + ".adaLN_modulation.1.weight"], sd[p + ".adaLN_modulation.1.bias"])
     sh1, sc1, g1, sh2, sc2, g2 = [m[:, None, None, :] for m in mod.chunk(6, dim=1)]
     a = F.layer_norm(x, (C,), sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], eps=1e-5)
-    a = rt(a * (1 + sc1) + sh1)
+    a = rt(a * (1 + sc1) + sh1, "ln1")
     x = rt(x + g1 * ss2d(sd, p + ".mamba", a, c, rt, taps), "trunk")                         # :486
-    a = rt(F.layer_norm(x, (C,), None, None, eps=1e-6) * (1 + sc2) + sh2)
+    a = rt(F.layer_norm(x, (C,), None, None, eps=1e-6) * (1 + sc2) + sh2, "ln2")
     att = transposed_attention(sd, p + ".attn_blk", a.permute(0, 3, 1, 2), C // 32, rt)
     x = rt(x + g2 * att.permute(0, 2, 3, 1), "trunk")                                        # :487
     return x.permute(0, 3, 1, 2)
