@@ -25,7 +25,7 @@ class ConvParams(Structure):
     """Mirror of fd_conv_params."""
     _fields_ = [
         ("src0", c_void_p), ("src1", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("gate", c_void_p),
-        ("addend", c_void_p), ("out", c_void_p), ("gn_sums", c_void_p),
+        ("addend", c_void_p), ("out", c_void_p), ("gn_sums", c_void_p), ("weight_up4", c_void_p),
         ("c0", c_int), ("c1", c_int), ("B", c_int), ("Hin", c_int), ("Win", c_int), ("Cout", c_int),
         ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int), ("upsample", c_int),
         ("silu_from", c_int), ("gate_stride", c_int), ("gn_groups", c_int), ("per_batch_weight", c_int),

@@ -1,13 +1,442 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution (placeholder until the kernel lands: reports "unsupported",
-// callers then use fd_conv2d_simt).
+// Implicit-GEMM convolution / 1x1 GEMM on the 5th-generation tensor cores (sm_100a):
+//   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a 4-stage mbarrier ring,
+//   * tcgen05.mma (kind::f16, cta_group::1, M=128, N=64/128/256, K=16) issued by one elected thread,
+//   * fp32 accumulators in TMEM, read back with tcgen05.ld by four epilogue warps that apply the fused epilogue of
+//     fd_conv_params (bias, SiLU on a channel range, adaLN gate, residual addend, GroupNorm partial sums).
+//
+// GEMM view (same as fd_conv_simt.cu): M = output pixels, N = Cout, K = taps x Cin.  An M tile is an 8x16 patch of
+// output pixels of ONE sample; for tap (kh, kw) and a 64-channel slice the A tile is ONE TMA box
+// {64 ch, 16 cols, 8 rows, 1 sample} at element offset (kw - pad, kh - pad): out-of-bounds elements are zero-filled
+// by the TMA unit, which is exactly the convolution's zero padding.  The box lands in shared memory as 128 rows of
+// 128 bytes with the 128B swizzle = the canonical K-major UMMA operand layout, so no thread ever touches A or B.
+//   stride 2 (Downsample 4x4 s2): the same box with elementStrides {1,2,2,1}.
+//   nearest x2 upsample + 3x3   : decomposed into 4 output phases, each a 2x2 convolution over the LOW-resolution
+//                                 input with pre-summed weights (host-packed `weight_up4`), 2.25x fewer FLOPs.
+//   torch.cat inputs            : two tensor maps; K blocks switch map at c0.
+//   per-sample weights (W_eff)  : 3-D weight map {K, Cout, batch}.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "fd_common.cuh"
 
-struct fd_gemm_plan { int unused; };
+namespace {
 
-extern "C" int fd_conv2d_tc_supported(const fd_conv_params*) { return 0; }
-extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params*, fd_gemm_plan** plan) {
-    if (plan) *plan = nullptr;
-    return FD_ERR_UNSUPPORTED;
+constexpr int BM = 128;          // UMMA M (pixels per tile)
+constexpr int TILE_H = 8, TILE_W = 16;
+constexpr int BK = 64;           // K block = one 128-byte swizzle atom of 16-bit elements
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 192;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+struct TcParams {
+    fd_conv_params p;
+    int Hout, Wout;
+    int tiles_h, tiles_w;
+    int BN;                 // N tile (64, 128 or 256)
+    int n_tiles;            // Cout / BN
+    int phases;             // 4 for upsample, else 1
+    int taps_h, taps_w;     // taps per phase
+    int kblocks0, kblocks1; // 64-channel blocks of src0 / src1
+    int fmt;                // 0 = f16, 1 = bf16 (UMMA a/b format)
+};
+
+// ---------------------------------------------------------------------------------------------------- PTX helpers
+FD_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+FD_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-extern "C" int fd_conv2d_tc_run(const fd_gemm_plan*, cudaStream_t) { return FD_ERR_UNSUPPORTED; }
-extern "C" void fd_conv2d_tc_plan_destroy(fd_gemm_plan*) {}
+FD_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+FD_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+FD_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+FD_DEVINL void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+FD_DEVINL void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+FD_DEVINL void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+FD_DEVINL void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+FD_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO (ignored for swizzled K-major) = 1, SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (sm_100), layout 2 (128B).
+FD_DEVINL uint64_t make_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format f32 (bit 4), a/b format (bits 7, 10), K-major both, N>>3 (bit 17), M>>4 (bit 24)
+FD_DEVINL uint32_t make_idesc(int fmt, int n) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <typename T> FD_DEVINL void store16(T* dst, const float (&v)[16]) {
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
+    fd_stv<T, 8>(dst, a);
+    fd_stv<T, 8>(dst + 8, b);
+}
+template <typename T> FD_DEVINL void load16(const T* src, float (&v)[16]) {
+    float a[8], b[8];
+    fd_ldv<T, 8>(src, a);
+    fd_ldv<T, 8>(src + 8, b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = a[i]; v[8 + i] = b[i]; }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_w, const TcParams q) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [STAGES][A 16 KB][B BN*128 B] then barriers
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int BN = q.BN;
+    const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)BN * BK * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    uint64_t* full_bar = (uint64_t*)(smem + STAGES * stage_bytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* accum_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+    float* s_gn = (float*)(tmem_slot + 2);      // [2][32] GroupNorm partial sums of this tile
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const fd_conv_params& p = q.p;
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tw = t % q.tiles_w; t /= q.tiles_w;
+    const int th = t % q.tiles_h; t /= q.tiles_h;
+    const int phase = t % q.phases;
+    const int b = t / q.phases;
+    const int n0 = blockIdx.y * BN;
+    const int ho0 = th * TILE_H, wo0 = tw * TILE_W;       // in the (per-phase) output grid
+
+    const int kb_per_tap = q.kblocks0 + q.kblocks1;
+    const int taps = q.taps_h * q.taps_w;
+    const int num_kb = taps * kb_per_tap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 64) s_gn[threadIdx.x] = 0.f;
+    if (warp == 1) {  // TMEM allocation (power of two >= 32 columns), owned by this warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+            int stage = 0;
+            uint32_t ph = 0;
+            // input coordinate of the tile origin for tap (0,0)
+            int hbase, wbase;
+            if (p.upsample) {          // phase (a, b): low-res rows {i-1+a, i+a}, cols likewise
+                hbase = ho0 - 1 + (phase >> 1);
+                wbase = wo0 - 1 + (phase & 1);
+            } else {
+                hbase = ho0 * p.stride - p.pad;
+                wbase = wo0 * p.stride - p.pad;
+            }
+            const int wbatch = p.per_batch_weight ? b : phase;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int tap = kb / kb_per_tap, cb = kb % kb_per_tap;
+                const int kh = tap / q.taps_w, kw = tap % q.taps_w;
+                mbar_wait(&empty_bar[stage], ph ^ 1);
+                uint8_t* sa = smem + stage * stage_bytes;
+                uint8_t* sb = sa + a_bytes;
+                mbar_expect_tx(&full_bar[stage], stage_bytes);
+                if (cb < q.kblocks0) tma_load_4d(sa, &map_a0, &full_bar[stage], cb * BK, wbase + kw, hbase + kh, b);
+                else                 tma_load_4d(sa, &map_a1, &full_bar[stage], (cb - q.kblocks0) * BK, wbase + kw, hbase + kh, b);
+                tma_load_3d(sb, &map_w, &full_bar[stage], kb * BK, n0, wbatch);
+                if (++stage == STAGES) { stage = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(q.fmt, BN);
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_f16(tmem_base, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                             (kb | k) ? 1u : 0u);
+                umma_commit(&empty_bar[stage]);      // frees the smem slot when these MMAs retire
+                if (++stage == STAGES) { stage = 0; ph ^= 1; }
+            }
+            umma_commit(accum_bar);                  // accumulator complete
+        }
+    } else {
+        // ================================ epilogue (4 warps = 128 TMEM lanes) ================================
+        const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
+        const int m = q4 * 32 + lane;                // accumulator row = pixel of the tile
+        const int oi = ho0 + m / TILE_W, oj = wo0 + m % TILE_W;      // per-phase output coordinates
+        const bool row_ok = oi < q.Hout / (p.upsample ? 2 : 1) && oj < q.Wout / (p.upsample ? 2 : 1);
+        const int oh = p.upsample ? 2 * oi + (phase >> 1) : oi;
+        const int ow = p.upsample ? 2 * oj + (phase & 1) : oj;
+        const long orow = (((long)b * q.Hout + oh) * q.Wout + ow) * p.Cout;
+        T* out = (T*)p.out;
+        const T* addend = (const T*)p.addend;
+        const int cpg = p.gn_sums ? p.Cout / p.gn_groups : 16;
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c = 0; c < BN; c += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float v[16];
+            const int n = n0 + c;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+                if (n + j >= p.silu_from) x = fd_silu(x);
+                v[j] = x;
+            }
+            if (p.gn_sums) {       // per-group sums over the tile's rows; 8 consecutive columns always share a group
+#pragma unroll
+                for (int g0 = 0; g0 < 16; g0 += 8) {
+                    float s = 0.f, ss = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const float x = row_ok ? v[g0 + j] : 0.f; s += x; ss = fmaf(x, x, ss); }
+                    s = fd_warp_sum(s);
+                    ss = fd_warp_sum(ss);
+                    if (lane == 0) {
+                        const int gl = (c + g0) / cpg;       // group index local to the tile (< 32)
+                        atomicAdd(&s_gn[gl], s);
+                        atomicAdd(&s_gn[32 + gl], ss);
+                    }
+                }
+            }
+            if (row_ok) {
+                if (p.gate) {
+                    const float* gp = p.gate + (long)b * p.gate_stride + n;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= __ldg(gp + j);
+                }
+                if (addend) {
+                    float a[16];
+                    load16<T>(addend + orow + n, a);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += a[j];
+                }
+                store16<T>(out + orow + n, v);
+            }
+        }
+        if (p.gn_sums) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+            const int et = threadIdx.x - 64;
+            const int ngl = (BN + cpg - 1) / cpg;
+            if (et < 2 * ngl) {
+                const int which = et / ngl, gl = et % ngl;
+                atomicAdd(&p.gn_sums[((long)b * p.gn_groups + n0 / cpg + gl) * 2 + which], s_gn[which * 32 + gl]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+int encode(CUtensorMap* map, int dtype, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+           const cuuint32_t* box, const cuuint32_t* estr) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) return FD_ERR_DRIVER;
+    CUresult r = fn(map, dtype == FD_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                    const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : FD_ERR_DRIVER;
+}
+
+int act_map(CUtensorMap* map, const void* base, int dtype, int B, int H, int W, int C, int estride) {
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {BK, (cuuint32_t)(TILE_W * estride), (cuuint32_t)(TILE_H * estride), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    return encode(map, dtype, 4, base, dims, strides, box, estr);
+}
+
+}  // namespace
+
+struct fd_gemm_plan {
+    alignas(64) CUtensorMap map_a0;
+    alignas(64) CUtensorMap map_a1;
+    alignas(64) CUtensorMap map_w;
+    TcParams q;
+    size_t smem;
+    dim3 grid;
+};
+
+static int conv_dims(const fd_conv_params* p, int* Hout, int* Wout) {
+    const int Hv = p->upsample ? 2 * p->Hin : p->Hin, Wv = p->upsample ? 2 * p->Win : p->Win;
+    *Hout = (Hv + 2 * p->pad - p->KH) / p->stride + 1;
+    *Wout = (Wv + 2 * p->pad - p->KW) / p->stride + 1;
+    return (*Hout > 0 && *Wout > 0) ? 0 : FD_ERR_BAD_ARGUMENT;
+}
+
+extern "C" int fd_conv_check_params(const fd_conv_params* p);
+
+extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
+    if (fd_conv_check_params(p)) return 0;
+    if (p->dtype != FD_BF16 && p->dtype != FD_F16) return 0;
+    if (p->c0 % BK || p->c1 % BK) return 0;
+    if (p->Cout % 64) return 0;
+    int Hout, Wout;
+    if (conv_dims(p, &Hout, &Wout)) return 0;
+    const int gh = p->upsample ? Hout / 2 : Hout, gw = p->upsample ? Wout / 2 : Wout;   // per-phase output grid
+    if (gh % TILE_H || gw % TILE_W) return 0;
+    if (p->upsample) {
+        if (!(p->KH == 3 && p->KW == 3 && p->stride == 1 && p->pad == 1) || !p->weight_up4 || p->per_batch_weight) return 0;
+    } else {
+        if (p->stride != 1 && p->stride != 2) return 0;
+    }
+    if (p->gn_sums) {
+        const int cpg = p->Cout / p->gn_groups;
+        if (cpg < 8 || cpg % 8 || (cpg & (cpg - 1))) return 0;
+    }
+    const uintptr_t al = (uintptr_t)p->src0 | (uintptr_t)p->src1 | (uintptr_t)p->weight | (uintptr_t)p->out |
+                         (uintptr_t)p->addend | (uintptr_t)p->weight_up4;
+    if (al & 15) return 0;
+    return get_encode() != nullptr;
+}
+
+extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** out_plan) {
+    if (!out_plan) return FD_ERR_BAD_ARGUMENT;
+    *out_plan = nullptr;
+    if (!fd_conv2d_tc_supported(p)) return FD_ERR_UNSUPPORTED;
+    fd_gemm_plan* plan = nullptr;
+    if (posix_memalign((void**)&plan, 64, sizeof(fd_gemm_plan)) || !plan) return FD_ERR_BAD_ARGUMENT;
+    memset(plan, 0, sizeof(*plan));
+    TcParams& q = plan->q;
+    q.p = *p;
+    conv_dims(p, &q.Hout, &q.Wout);
+    const int Cin = p->c0 + p->c1;
+    q.phases = p->upsample ? 4 : 1;
+    q.taps_h = p->upsample ? 2 : p->KH;
+    q.taps_w = p->upsample ? 2 : p->KW;
+    q.kblocks0 = p->c0 / BK;
+    q.kblocks1 = p->c1 / BK;
+    q.BN = (p->Cout % 256 == 0) ? 256 : (p->Cout % 128 == 0 ? 128 : 64);
+    q.n_tiles = p->Cout / q.BN;
+    q.fmt = p->dtype == FD_BF16 ? 1 : 0;
+    const int gh = q.Hout / (p->upsample ? 2 : 1), gw = q.Wout / (p->upsample ? 2 : 1);
+    q.tiles_h = gh / TILE_H;
+    q.tiles_w = gw / TILE_W;
+    int rc = act_map(&plan->map_a0, p->src0, p->dtype, p->B, p->Hin, p->Win, p->c0, p->upsample ? 1 : p->stride);
+    if (!rc && p->c1) rc = act_map(&plan->map_a1, p->src1, p->dtype, p->B, p->Hin, p->Win, p->c1, p->upsample ? 1 : p->stride);
+    if (!rc && !p->c1) plan->map_a1 = plan->map_a0;
+    if (!rc) {
+        const long Kp = (long)q.taps_h * q.taps_w * Cin;
+        const int G = p->upsample ? 4 : (p->per_batch_weight ? p->B : 1);
+        const void* wbase = p->upsample ? p->weight_up4 : p->weight;
+        const cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)p->Cout, (cuuint64_t)G};
+        const cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)Kp * p->Cout * 2};
+        const cuuint32_t box[3] = {BK, (cuuint32_t)q.BN, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        rc = encode(&plan->map_w, p->dtype, 3, wbase, dims, strides, box, estr);
+    }
+    if (rc) { free(plan); return rc; }
+    plan->smem = (size_t)STAGES * (BM * BK * 2 + (size_t)q.BN * BK * 2) + 1024 /*align slack*/ + 512 /*barriers, gn*/;
+    plan->grid = dim3((unsigned)(p->B * q.phases * q.tiles_h * q.tiles_w), (unsigned)q.n_tiles);
+    *out_plan = plan;
+    return 0;
+}
+
+extern "C" int fd_conv2d_tc_run(const fd_gemm_plan* plan, cudaStream_t stream) {
+    if (!plan) return FD_ERR_BAD_ARGUMENT;
+    static bool attr_bf16 = false, attr_f16 = false;
+    if (plan->q.p.dtype == FD_BF16) {
+        if (!attr_bf16) {
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            attr_bf16 = true;
+        }
+        conv_tc_kernel<__nv_bfloat16><<<plan->grid, NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
+    } else {
+        if (!attr_f16) {
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            attr_f16 = true;
+        }
+        conv_tc_kernel<__half><<<plan->grid, NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
+    }
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" void fd_conv2d_tc_plan_destroy(fd_gemm_plan* plan) { free(plan); }

@@ -61,6 +61,26 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplu
     return y
 
 
+def pack_upsample_phases(weight: torch.Tensor, cout: int, cin: int) -> torch.Tensor:
+    """nearest-x2 upsample followed by a 3x3 conv == 4 output phases, each a 2x2 conv over the low-resolution input
+    whose taps are sums of the 3x3 taps that land on the same low-res pixel.  weight: (Cout, 3, 3, Cin) ->
+    (4, Cout, 2, 2, Cin), phase = 2*row_parity + col_parity."""
+    w = weight.reshape(cout, 3, 3, cin).float()
+    # row/col combination per parity: parity 0 -> taps {0}, {1,2};  parity 1 -> taps {0,1}, {2}
+    comb = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    out = torch.zeros(4, cout, 2, 2, cin, device=w.device, dtype=torch.float32)
+    for a in (0, 1):
+        for b in (0, 1):
+            for dh in (0, 1):
+                for dw in (0, 1):
+                    acc = 0
+                    for kh in comb[a][dh]:
+                        for kw in comb[b][dw]:
+                            acc = acc + w[:, kh, kw, :]
+                    out[2 * a + b, :, dh, dw, :] = acc
+    return out.to(weight.dtype).contiguous()
+
+
 class Conv:
     """One convolution / 1x1 GEMM call site (fd_conv_params).  `run()` launches it; buffers are bound at
     construction so that the call is CUDA-graph friendly (and so that the tcgen05 path can bake TMA descriptors)."""
@@ -77,6 +97,10 @@ class Conv:
         p.bias, p.gate, p.addend, p.gn_sums = _f32(bias), _f32(gate), _p(addend), _f32(gn_sums)
         p.c0, p.c1, p.B, p.Hin, p.Win, p.Cout = c0, c1, B, Hin, Win, cout
         p.KH, p.KW, p.stride, p.pad, p.upsample = KH, KW, stride, pad, int(upsample)
+        self._w4 = None
+        if upsample and prefer_tc and out.dtype != torch.float32:
+            self._w4 = pack_upsample_phases(weight, cout, c0 + c1)
+            p.weight_up4 = _p(self._w4)
         p.silu_from = cout if silu_from is None else silu_from
         p.gate_stride, p.gn_groups, p.per_batch_weight = gate_stride, gn_groups, int(per_batch_weight)
         p.dtype = dtype_code(out.dtype)

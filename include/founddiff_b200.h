@@ -72,6 +72,7 @@ typedef struct {
     const void* addend;
     void* out;
     float* gn_sums;
+    const void* weight_up4; /* upsample only (tcgen05 path): (4, Cout, 2, 2, c0) phase-summed weights, see fd_conv_tc.cu */
     int c0, c1;
     int B, Hin, Win, Cout;
     int KH, KW, stride, pad, upsample;

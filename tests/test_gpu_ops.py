@@ -329,3 +329,77 @@ def test_sampler_kernels(ops, dt):
     un = torch.empty(B, P, device="cuda")
     ops.unnormalize(xt, un)
     assert torch.allclose(un, (xt + 1) / 2)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 / TMEM / TMA implicit-GEMM path against the CUDA-core path (same inputs, same fused epilogue)
+TC_CASES = [
+    # c0, c1, cout, k, stride, pad, upsample, H, W
+    (64, 0, 64, 3, 1, 1, False, 16, 32),
+    (64, 64, 64, 3, 1, 1, False, 8, 16),
+    (256, 128, 256, 3, 1, 1, False, 16, 16),
+    (128, 0, 512, 1, 1, 0, False, 8, 32),
+    (64, 0, 192, 1, 1, 0, False, 16, 16),
+    (64, 0, 128, 4, 2, 1, False, 32, 32),
+    (128, 0, 64, 3, 1, 1, True, 8, 16),
+    (512, 0, 256, 3, 1, 1, True, 8, 16),
+    (512, 256, 512, 3, 1, 1, False, 8, 16),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_conv2d_tc_matches_simt(ops, case, dt):
+    c0, c1, cout, k, stride, pad, up, H, W = case
+    B = 2
+    g = torch.Generator().manual_seed(c0 + cout + k + c1)
+    x0 = torch.randn(B, H * W, c0, generator=g).to("cuda", dt)
+    x1 = torch.randn(B, H * W, c1, generator=g).to("cuda", dt) if c1 else None
+    w = (torch.randn(cout, k, k, c0 + c1, generator=g) / math.sqrt((c0 + c1) * k * k)).to("cuda", dt)
+    bias = torch.randn(cout, generator=g).cuda()
+    Ho = (H * (2 if up else 1) + 2 * pad - k) // stride + 1
+    Wo = (W * (2 if up else 1) + 2 * pad - k) // stride + 1
+    outs = []
+    for tc in (False, True):
+        out = torch.zeros(B, Ho * Wo, cout, device="cuda", dtype=dt)
+        sums = torch.zeros(B, 8, 2, device="cuda")
+        conv = ops.Conv(x0, w, out, B=B, Hin=H, Win=W, KH=k, KW=k, stride=stride, pad=pad, upsample=up, src1=x1, bias=bias,
+                        gn_sums=sums, gn_groups=8, prefer_tc=tc)
+        assert conv.uses_tc == tc
+        conv.run()
+        torch.cuda.synchronize()
+        outs.append((out.float().cpu(), sums.cpu()))
+    # same bf16 inputs, fp32 accumulation on both paths: only summation order (and the phase-summed upsample
+    # weights, rounded once more to 16 bit) differ
+    tol = (2e-2 if dt == torch.bfloat16 else 3e-3) if up else 3e-3 if dt == torch.bfloat16 else 5e-4
+    assert rel(outs[1][0], outs[0][0]) < tol, rel(outs[1][0], outs[0][0])
+    assert rel(outs[1][1], outs[0][1]) < tol
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_conv2d_tc_epilogues(ops, dt):
+    from founddiff_b200.engine import _view_ptr
+    B, C, H, W, cout = 2, 128, 16, 16, 256
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H * W, C, generator=g).to("cuda", dt)
+    w = (torch.randn(cout, C, generator=g) / math.sqrt(C)).to("cuda", dt)
+    res = []
+    for tc in (False, True):
+        out = torch.zeros(B, H * W, cout, device="cuda", dtype=dt)
+        conv = ops.Conv(x, w, out, B=B, Hin=H, Win=W, silu_from=cout // 2, prefer_tc=tc)
+        assert conv.uses_tc == tc
+        conv.run()
+        res.append(out.float().cpu())
+    assert rel(res[1], res[0]) < 3e-3
+    mods = torch.randn(B, 3 * cout, generator=g).cuda()
+    add = torch.randn(B, H * W, cout, generator=g).to("cuda", dt)
+    wb = (torch.randn(B, cout, C, generator=g) / math.sqrt(C)).to("cuda", dt)
+    res = []
+    for tc in (False, True):
+        buf = add.clone()
+        conv = ops.Conv(x, wb, buf, B=B, Hin=H, Win=W, gate=_view_ptr(mods[:, cout:2 * cout]), gate_stride=3 * cout, addend=buf,
+                        per_batch_weight=True, prefer_tc=tc)
+        assert conv.uses_tc == tc
+        conv.run()
+        res.append(buf.float().cpu())
+    assert rel(res[1], res[0]) < 3e-3
