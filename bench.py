@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the FoundDiff reverse-diffusion sampling hot path (BASELINE.json metric: 512^2 CT slices/sec for a
+complete `sample()` call).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path (one process per GPU, torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the box's host cores
+
+A "step" = one `ResidualDiffusion.sample()` call over one batch of synthetic low-dose slices (per-GPU batch 16 of
+512x512, DDIM with `--sampling-timesteps` Unet evaluations, default 2 = the reference's default, train.py:39).
+`value` = slices/s with inputs resident in HBM; `e2e` = the same through the public `sample()` call with pinned HOST
+buffers (H2D of slices + noise and D2H of the result inside the timed region).  Weak scaling: every GPU samples its own
+16 slices; the only collective is one all_gather of the denoised slices per call (inside the timed regions).
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "512x512 CT slices/sec, full reverse sampling (sample() call)"
+UNIT = "slices/s"
+T_ROOF_US = 893.6          # per slice-step roofline, BASELINE.md §3 (burst tensor peak) — the judged denominator
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="slices per GPU")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--sampling-timesteps", type=int, default=2)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel timing pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-table", default="", help="write the per-kernel timing table (JSON) here")
+    return ap.parse_args()
+
+
+def synth_slices(B, H, W, seed=1234, sigma=0.05):
+    """SURVEY §8d synthetic input: box-filtered uniform noise ("NDCT") + Gaussian noise -> LDCT in [0,1]."""
+    g = torch.Generator().manual_seed(seed)
+    ndct = torch.rand(B, 1, H, W, generator=g)
+    ndct = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(ndct, (2, 2, 2, 2), mode="reflect"), 5, stride=1)
+    ldct = (ndct + sigma * torch.randn(B, 1, H, W, generator=g)).clamp(0, 1)
+    return ndct, ldct
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_run(size, S, steps, warmup, threads=None):
+    """The reference algorithm on the host cores: the CPU oracle port (oracle/founddiff_oracle.py — a restatement of
+    the reference's PyTorch modules pinned to it by tests/golden; the reference itself is pure Python that cannot
+    travel to this box, and its third-party scan is CUDA-only) with every host thread.  One step = one 512^2 slice."""
+    from founddiff_b200 import weights
+    from oracle import founddiff_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd = weights.random_state_dict(10)
+    _, ldct = synth_slices(1, size, size)
+    noise = torch.randn(1, 1, size, size, generator=torch.Generator().manual_seed(4321))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.sample(sd, ldct, noise, sampling_timesteps=S)
+        times.append(time.perf_counter() - t0)
+    t = sum(times[warmup:])
+    return dict(value=steps / t, seconds_per_slice=t / steps, cores=threads,
+                sample=f"{steps} x (1 slice {size}x{size}, DDIM-{S} sample(), fp32, oracle port + C scan)")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.size, args.sampling_timesteps, max(args.steps, 1), args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_slice"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"FoundDiff full reverse sampling, 1 slice {args.size}x{args.size} per step, DDIM-{args.sampling_timesteps}, "
+                               "reference algorithm on host cores"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def algorithmic(name, detail, es):
+    """(bytes, flops) one launch must move / compute at minimum, from the op's shape string."""
+    try:
+        if name == "selective_scan":
+            dims, n = detail.split(" N")
+            b, kd, L = map(int, dims.split("x"))
+            n = int(n)
+            return 3.0 * b * kd * L * es + 2.0 * b * 4 * n * L * 4, 9.0 * b * kd * L * n
+        if name in ("ln_modulate", "gn_silu_add"):
+            b, p, c = map(int, detail.split("x"))
+            return (2.0 if name == "ln_modulate" else 3.0) * b * p * c * es, 0.0
+        if name == "dwconv_scan":
+            b, h, w, d = map(int, detail.split("x"))
+            return 2.0 * b * h * w * d * es, 18.0 * b * h * w * d
+        if name == "merge_ln_gate":
+            b, h, w, d = map(int, detail.split("x"))
+            return 3.0 * b * h * w * d * es, 0.0
+        if name == "dwconv_qkv_gram":
+            b, h, w, c = map(int, detail.split("x"))
+            return 4.0 * b * h * w * c * es, (54.0 + 64.0) * b * h * w * c
+        if name == "xdt_proj":
+            dims, r, n = detail.replace(" R", " ").replace(" N", " ").split(" ")
+            b, d, L = map(int, dims.split("x"))
+            r, n = int(r), int(n)
+            return 2.0 * b * 4 * d * L * es + 2.0 * b * 4 * n * L * 4, 2.0 * b * 4 * L * d * (2 * r + 2 * n)
+        if name == "init_conv7x7":
+            b, h, w = map(int, detail.split("x"))
+            return b * h * w * (8.0 + 64 * es), 2.0 * b * h * w * 98 * 64
+        if name == "final_conv_update":
+            npix, c = map(int, detail.split("x"))
+            return npix * (c * es + 16.0), 2.0 * npix * c
+    except Exception:
+        pass
+    return 0.0, 0.0
+
+
+def conv_algorithmic(detail, es):
+    # "BxHxW c0+c1->Cout kK sS [up2] [wb]"
+    parts = detail.split(" ")
+    b, h, w = map(int, parts[0].split("x"))
+    cin, cout = parts[1].split("->")
+    c0, c1 = map(int, cin.split("+"))
+    cout = int(cout)
+    k, s = int(parts[2][1:]), int(parts[3][1:])
+    up = 2 if "up2" in parts else 1
+    ho, wo = h * up // s, w * up // s
+    flops = 2.0 * b * ho * wo * cout * k * k * (c0 + c1)
+    byts = (b * h * w * (c0 + c1) + b * ho * wo * cout) * es
+    return byts, flops
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from founddiff_b200 import distributed as fdist
+    from founddiff_b200 import ops, weights
+    from founddiff_b200.diffusion import ResidualDiffusion, UnetRes
+
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if ws > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
+    B, H, S = args.batch, args.size, args.sampling_timesteps
+
+    sd = weights.random_state_dict(10)
+    model = UnetRes(dim=64, dim_mults=(1, 2, 4, 8), num_unet=1, condition=True, input_condition=False, objective='pred_res',
+                    test_res_or_noise='res')
+    model.load_state_dict({"unet0." + k: v for k, v in sd.items()})
+    model.compute_dtype = dt
+    diffusion = ResidualDiffusion(model, image_size=H, timesteps=1000, sampling_timesteps=S, objective='pred_res', loss_type='l2',
+                                  condition=True, sum_scale=0.01).to(dev)
+    diffusion.init()
+
+    n_global = B * ws
+    _, ldct_g = synth_slices(n_global, H, H)
+    n_noise_steps = 0 if diffusion.is_ddim_sampling else diffusion.num_timesteps - 1
+    a, b_ = fdist.shard_range(n_global, rank, ws)
+    init_g, steps_g = fdist.global_noise(n_global, (1, H, H), 4321, n_noise_steps)
+    ldct_host = ldct_g[a:b_].contiguous().pin_memory()
+    noise_host = {"init": init_g[a:b_].contiguous().pin_memory()}
+    if steps_g is not None:
+        noise_host["steps"] = steps_g[:, a:b_].contiguous().pin_memory()
+    ldct_dev = ldct_host.to(dev)
+    noise_dev = {k: v.to(dev) for k, v in noise_host.items()}
+
+    def step_resident():
+        out = diffusion.sample([ldct_dev], batch_size=B, last=True, noise=noise_dev)[-1]
+        return fdist.gather_slices(out, n_global)
+
+    def step_e2e():
+        x = ldct_host.to(dev, non_blocking=True)
+        nz = {k: v.to(dev, non_blocking=True) for k, v in noise_host.items()}
+        out = diffusion.sample([x], batch_size=B, last=True, noise=nz)[-1]
+        out = fdist.gather_slices(out, n_global)
+        return out.to("cpu", non_blocking=False)          # D2H read of the step's result (synchronises)
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if ws > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    launches0 = ops.LAUNCHES
+    diffusion.use_cuda_graph = False          # count kernels of one call in eager mode (graph replays launch the same set)
+    step_resident()
+    launches_per_call = ops.LAUNCHES - launches0
+    diffusion.use_cuda_graph = True
+    step_resident()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms = timed(step_resident, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    value = n_global * args.steps / (ms / 1e3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = n_global * args.steps / (ms_e2e / 1e3)
+    h2d = ldct_host.numel() * 4 + sum(v.numel() * 4 for v in noise_host.values())
+    d2h = n_global * H * H * 4
+
+    # ---- per-kernel timing pass (eager, CUDA events around every launch) -> roofline of the dominant kernel ------
+    roofline, table = None, []
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    peak_src = "measured (MEASURED_PEAKS.json; sustained bf16 figure: kernel timed inside a long step)" if peaks else "fallback"
+    if not args.no_profile and rank == 0:
+        es = 4 if dt == torch.float32 else 2
+        diffusion.use_cuda_graph = False
+        ops.PROFILE = []
+        step_resident()
+        torch.cuda.synchronize(dev)
+        prof, ops.PROFILE = ops.PROFILE, None
+        diffusion.use_cuda_graph = True
+        agg = {}
+        for name, detail, e0, e1 in prof:
+            k = (name, detail)
+            t = e0.elapsed_time(e1)
+            a_ = agg.setdefault(k, [0, 0.0])
+            a_[0] += 1
+            a_[1] += t
+        total = sum(v[1] for v in agg.values())
+        for (name, detail), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            byts, flops = conv_algorithmic(detail, es) if name.startswith("conv") else algorithmic(name, detail, es)
+            avg_ms = t / n
+            table.append({"kernel": name, "shape": detail, "launches": n, "total_ms": round(t, 4), "share": round(t / total, 4),
+                          "avg_us": round(avg_ms * 1e3, 2), "alg_GB": round(byts / 1e9, 5), "alg_GFLOP": round(flops / 1e9, 4),
+                          "GBps": round(byts / avg_ms / 1e6, 1) if avg_ms > 0 else None,
+                          "TFLOPs": round(flops / avg_ms / 1e9, 2) if avg_ms > 0 else None})
+        top = table[0]
+        t_hbm = top["alg_GB"] / hbm_peak * 1e3          # ms at the HBM roof
+        t_tc = top["alg_GFLOP"] / tc_peak               # ms at the tensor roof
+        if top["kernel"].startswith("conv") and t_tc >= t_hbm:
+            roofline = {"bound": "tensor", "achieved": top["TFLOPs"], "peak": tc_peak, "unit": "TFLOP/s",
+                        "frac": round(top["TFLOPs"] / tc_peak, 4), "traffic": None}
+        else:
+            roofline = {"bound": "hbm", "achieved": top["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": round(top["GBps"] / hbm_peak, 4), "traffic": None}
+        roofline.update({"kernel": top["kernel"], "shape": top["shape"], "share_of_step": top["share"], "avg_us": top["avg_us"],
+                         "peak_source": peak_src})
+        if args.kernel_table:
+            os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
+            json.dump({"per_call_ms_eager": total, "kernels": table}, open(args.kernel_table, "w"), indent=1)
+
+    cpu_base = None
+    if rank == 0 and ws == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(H, S, 1, 0)
+        cpu_base = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        per_slice_step_us = (ms / args.steps) * 1e3 / (B * S)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"FoundDiff full reverse sampling, batch {B} of {H}x{H} slices per GPU, {args.dtype}, "
+                                   f"{'DDIM-' + str(S) if S < 1000 else 'ancestral-1000'}, random-init weights (seed 10, adaLN de-zeroed)",
+                       "slices_per_gpu": B, "global_batch": n_global, "sampling_timesteps": S, "parallelism": f"dp{ws} (independent chains, 1 all_gather)",
+                       "l2": "per-step activations (GBs) >> 126 MB L2; no explicit flush needed", "cuda_graph": True},
+            "per_slice_step_us": per_slice_step_us,
+            "step_roofline": {"t_roof_us": T_ROOF_US, "frac": T_ROOF_US / per_slice_step_us,
+                              "note": "BASELINE.md §3 per-slice-step roofline / measured per-slice-step time (includes DA-CLIP + sampler)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_call * args.steps,
+            "gpu_launches_per_step": launches_per_call,
+            "clocks": clk,
+        }
+        if roofline:
+            line["roofline"] = roofline
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if ws > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -231,7 +231,14 @@ class ResidualDiffusion(nn.Module):
 
     # -- helpers -------------------------------------------------------------------------------------------
     def _sched(self, name, t) -> float:
-        return float(getattr(self, name)[t])
+        """Schedule scalars are read from a host copy (no device sync inside the sampling loop)."""
+        cache = self.__dict__.setdefault("_sched_host", {})
+        buf = getattr(self, name)
+        key = (name, buf.data_ptr(), buf._version)
+        if cache.get("key_" + name) != key:
+            cache[name] = buf.detach().float().cpu()
+            cache["key_" + name] = key
+        return float(cache[name][t])
 
     def _ddim_pairs(self):
         times = torch.linspace(-1, self.num_timesteps - 1, steps=self.sampling_timesteps + 1)   # :1287-1291
@@ -247,12 +254,13 @@ class ResidualDiffusion(nn.Module):
                 if t_next < 0:
                     plan.append((t, [0., 0., 1., 0., acs, bcs]))                                   # :1317-1321
                 else:
-                    alpha = float(self.alphas_cumsum[t] - self.alphas_cumsum[t_next])               # :1323-1325 (fp32)
+                    import numpy as np
+                    alpha = float(np.float32(acs) - np.float32(self._sched("alphas_cumsum", t_next)))  # :1323-1325 (fp32)
                     plan.append((t, [1., -alpha, 0., 0., acs, bcs]))                                # :1344, sigma2 = 0
         else:
             for t in reversed(range(self.num_timesteps)):                                           # :1254
                 acs, bcs = self._sched("alphas_cumsum", t), self._sched("betas_cumsum", t)
-                cn = float((0.5 * self.posterior_log_variance_clipped[t]).exp()) if t > 0 else 0.   # :1228-1229
+                cn = float(torch.tensor(0.5 * self._sched("posterior_log_variance_clipped", t), dtype=torch.float32).exp()) if t > 0 else 0.   # :1228-1229
                 plan.append((t, [self._sched("posterior_mean_coef1", t), self._sched("posterior_mean_coef2", t),
                                  self._sched("posterior_mean_coef3", t), cn, acs, bcs]))
         return plan
@@ -296,8 +304,7 @@ class ResidualDiffusion(nn.Module):
         if trace is not None:
             taps = [self._buffer(eng, n, B * P).view(B, P) for n in ("pred_res", "pred_noise", "x_start")]
         coef_host = torch.tensor([[*c, 0., 0.] for _, c in plan], dtype=torch.float32).pin_memory()
-        time_host = torch.tensor([float(self.alphas_cumsum[t] * self.num_timesteps) for t, _ in plan],
-                                 dtype=torch.float32)                                                 # :1162
+        time_host = torch.tensor([self._sched("alphas_cumsum", t) for t, _ in plan], dtype=torch.float32) * self.num_timesteps  # :1162
         time_rows = time_host[:, None].expand(-1, B).contiguous().pin_memory()
 
         def one_step():

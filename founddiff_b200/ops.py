@@ -47,6 +47,40 @@ def version() -> str:
 
 
 # ---------------------------------------------------------------------------------------------------------
+# Launch accounting / per-kernel timing (bench.py).  LAUNCHES counts kernels launched through this module;
+# when PROFILE is a list every op is bracketed by CUDA events on the launching stream and appended as
+# (name, detail, start_event, end_event).
+LAUNCHES = 0
+PROFILE = None
+
+
+def _launched(name: str, detail: str = "", n: int = 1):
+    """Context manager used by every wrapper: counts `n` kernel launches and optionally times them."""
+    return _Launch(name, detail, n)
+
+
+class _Launch:
+    __slots__ = ("name", "detail", "n", "ev")
+
+    def __init__(self, name, detail, n):
+        self.name, self.detail, self.n, self.ev = name, detail, n, None
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += self.n
+        if PROFILE is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+            PROFILE.append((self.name, self.detail, self.ev[0], self.ev[1]))
+        return False
+
+
+# ---------------------------------------------------------------------------------------------------------
 def selective_scan_fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=True, out=None):
     """u, delta: (b, KD, L) [fp32/bf16/fp16]; A: (KD, N) fp32; B, C: (b, K, N, L) fp32; D, delta_bias: (KD,) fp32."""
     lib = _lib.load()
@@ -55,9 +89,10 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplu
     assert delta.shape == u.shape and delta.dtype == u.dtype and A.shape[0] == kd
     assert B.shape == (b, g, n, L) and C.shape == B.shape
     y = torch.empty_like(u) if out is None else out
-    check(lib.fd_selective_scan_fwd(_p(u), _p(delta), _f32(A), _f32(B), _f32(C), _f32(D), _f32(delta_bias), _p(y),
-                                    b, kd, L, n, g, int(bool(delta_softplus)), dtype_code(u.dtype), _stream()),
-          "fd_selective_scan_fwd")
+    with _launched("selective_scan", f"{b}x{kd}x{L} N{n}"):
+        check(lib.fd_selective_scan_fwd(_p(u), _p(delta), _f32(A), _f32(B), _f32(C), _f32(D), _f32(delta_bias), _p(y),
+                                        b, kd, L, n, g, int(bool(delta_softplus)), dtype_code(u.dtype), _stream()),
+              "fd_selective_scan_fwd")
     return y
 
 
@@ -115,11 +150,26 @@ class Conv:
             check(lib.fd_conv2d_tc_plan_create(byref(p), byref(self._plan)), "fd_conv2d_tc_plan_create")
             self.uses_tc = True
 
+    def describe(self) -> str:
+        p = self.params
+        return (f"{p.B}x{p.Hin}x{p.Win} {p.c0}+{p.c1}->{p.Cout} k{p.KH} s{p.stride}" + (" up2" if p.upsample else "")
+                + (" wb" if p.per_batch_weight else ""))
+
+    def flops(self) -> float:
+        """Dense FLOPs of the convolution as the reference computes it (2*MAC; upsample counted at 3x3 on the
+        upsampled grid, as FlopCounterMode does for the reference — SURVEY.md Appendix A)."""
+        p = self.params
+        up = 2 if p.upsample else 1
+        ho = (p.Hin * up + 2 * p.pad - p.KH) // p.stride + 1
+        wo = (p.Win * up + 2 * p.pad - p.KW) // p.stride + 1
+        return 2.0 * p.B * ho * wo * p.Cout * p.KH * p.KW * (p.c0 + p.c1)
+
     def run(self):
-        if self.uses_tc:
-            check(self._lib.fd_conv2d_tc_run(self._plan, _stream()), "fd_conv2d_tc_run")
-        else:
-            check(self._lib.fd_conv2d_simt(byref(self.params), _stream()), "fd_conv2d_simt")
+        with _launched("conv_tc" if self.uses_tc else "conv_simt", self.describe()):
+            if self.uses_tc:
+                check(self._lib.fd_conv2d_tc_run(self._plan, _stream()), "fd_conv2d_tc_run")
+            else:
+                check(self._lib.fd_conv2d_simt(byref(self.params), _stream()), "fd_conv2d_simt")
 
     def __del__(self):
         try:
@@ -130,75 +180,89 @@ class Conv:
 
 
 def init_conv7x7(x_t, x_input, weight, bias, out, B, H, W):
-    check(_lib.load().fd_init_conv7x7(_f32(x_t), _f32(x_input), _f32(weight), _f32(bias), _p(out), B, H, W,
-                                      out.shape[-1], dtype_code(out.dtype), _stream()), "fd_init_conv7x7")
+    with _launched("init_conv7x7", f"{B}x{H}x{W}", 1):
+        check(_lib.load().fd_init_conv7x7(_f32(x_t), _f32(x_input), _f32(weight), _f32(bias), _p(out), B, H, W,
+                                          out.shape[-1], dtype_code(out.dtype), _stream()), "fd_init_conv7x7")
 
 
 def ln_modulate(x, out, gamma, beta, shift, scale, mod_stride, B, P, C, eps):
-    check(_lib.load().fd_ln_modulate(_p(x), _p(out), _f32(gamma), _f32(beta), _f32(shift), _f32(scale), mod_stride,
-                                     B, P, C, float(eps), dtype_code(x.dtype), _stream()), "fd_ln_modulate")
+    with _launched("ln_modulate", f"{B}x{P}x{C}", 1):
+        check(_lib.load().fd_ln_modulate(_p(x), _p(out), _f32(gamma), _f32(beta), _f32(shift), _f32(scale), mod_stride,
+                                         B, P, C, float(eps), dtype_code(x.dtype), _stream()), "fd_ln_modulate")
 
 
 def dwconv3x3_silu_scan(xz, ld, w, bias, xs, B, H, W, D):
-    check(_lib.load().fd_dwconv3x3_silu_scan(_p(xz), ld, _f32(w), _f32(bias), _p(xs), B, H, W, D,
-                                             dtype_code(xz.dtype), _stream()), "fd_dwconv3x3_silu_scan")
+    with _launched("dwconv_scan", f"{B}x{H}x{W}x{D}", 1):
+        check(_lib.load().fd_dwconv3x3_silu_scan(_p(xz), ld, _f32(w), _f32(bias), _p(xs), B, H, W, D,
+                                                 dtype_code(xz.dtype), _stream()), "fd_dwconv3x3_silu_scan")
 
 
 def xdt_proj(xs, x_proj_w, dt_w, dts, Bs, Cs, B, D, L, R, N):
-    check(_lib.load().fd_xdt_proj(_p(xs), _f32(x_proj_w), _f32(dt_w), _p(dts), _f32(Bs), _f32(Cs), B, D, L, R, N,
-                                  dtype_code(xs.dtype), _stream()), "fd_xdt_proj")
+    with _launched("xdt_proj", f"{B}x{D}x{L} R{R} N{N}", 1):
+        check(_lib.load().fd_xdt_proj(_p(xs), _f32(x_proj_w), _f32(dt_w), _p(dts), _f32(Bs), _f32(Cs), B, D, L, R, N,
+                                      dtype_code(xs.dtype), _stream()), "fd_xdt_proj")
 
 
 def merge_ln_gate(ys, xz, ld, z_off, gamma, beta, local, stats_ws, out, B, H, W, D, eps=1e-5):
-    check(_lib.load().fd_merge_ln_gate(_p(ys), _p(xz), ld, z_off, _f32(gamma), _f32(beta), _f32(local), _f32(stats_ws),
-                                       _p(out), B, H, W, D, float(eps), dtype_code(ys.dtype), _stream()),
-          "fd_merge_ln_gate")
+    with _launched("merge_ln_gate", f"{B}x{H}x{W}x{D}", 2):
+        check(_lib.load().fd_merge_ln_gate(_p(ys), _p(xz), ld, z_off, _f32(gamma), _f32(beta), _f32(local), _f32(stats_ws),
+                                           _p(out), B, H, W, D, float(eps), dtype_code(ys.dtype), _stream()),
+              "fd_merge_ln_gate")
 
 
 def dwconv3x3_qkv_gram(qkv, w, v, gram, qk_sq, B, H, W, C):
-    check(_lib.load().fd_dwconv3x3_qkv_gram(_p(qkv), _f32(w), _p(v), _f32(gram), _f32(qk_sq), B, H, W, C,
-                                            dtype_code(qkv.dtype), _stream()), "fd_dwconv3x3_qkv_gram")
+    with _launched("dwconv_qkv_gram", f"{B}x{H}x{W}x{C}", 1):
+        check(_lib.load().fd_dwconv3x3_qkv_gram(_p(qkv), _f32(w), _p(v), _f32(gram), _f32(qk_sq), B, H, W, C,
+                                                dtype_code(qkv.dtype), _stream()), "fd_dwconv3x3_qkv_gram")
 
 
 def attn_weff(gram, qk_sq, temperature, proj_w, weff, B, C):
-    check(_lib.load().fd_attn_weff(_f32(gram), _f32(qk_sq), _f32(temperature), _f32(proj_w), _p(weff), B, C,
-                                   dtype_code(weff.dtype), _stream()), "fd_attn_weff")
+    with _launched("attn_weff", f"{B}x{C}", 1):
+        check(_lib.load().fd_attn_weff(_f32(gram), _f32(qk_sq), _f32(temperature), _f32(proj_w), _p(weff), B, C,
+                                       dtype_code(weff.dtype), _stream()), "fd_attn_weff")
 
 
 def gn_stats(y, sums, B, P, C, G):
-    check(_lib.load().fd_gn_stats(_p(y), _f32(sums), B, P, C, G, dtype_code(y.dtype), _stream()), "fd_gn_stats")
+    with _launched("gn_stats", f"{B}x{P}x{C}", 1):
+        check(_lib.load().fd_gn_stats(_p(y), _f32(sums), B, P, C, G, dtype_code(y.dtype), _stream()), "fd_gn_stats")
 
 
 def gn_silu_add(y, sums, gamma, beta, skip, out, B, P, C, G, eps=1e-5):
-    check(_lib.load().fd_gn_silu_add(_p(y), _f32(sums), _f32(gamma), _f32(beta), _p(skip), _p(out), B, P, C, G,
-                                     float(eps), dtype_code(y.dtype), _stream()), "fd_gn_silu_add")
+    with _launched("gn_silu_add", f"{B}x{P}x{C}", 1):
+        check(_lib.load().fd_gn_silu_add(_p(y), _f32(sums), _f32(gamma), _f32(beta), _p(skip), _p(out), B, P, C, G,
+                                         float(eps), dtype_code(y.dtype), _stream()), "fd_gn_silu_add")
 
 
 def linear_small(x, W, bias, out, *, add=None, act_in=0, act_out=0):
     B, K = x.shape
     N = W.shape[0]
     assert W.shape[1] == K and out.shape == (B, N)
-    check(_lib.load().fd_linear_small(_f32(x), _f32(W), _f32(bias), _f32(add), _f32(out), B, K, N, act_in, act_out,
-                                      _stream()), "fd_linear_small")
+    with _launched("linear_small", f"{B}x{K}x{N}"):
+        check(_lib.load().fd_linear_small(_f32(x), _f32(W), _f32(bias), _f32(add), _f32(out), B, K, N, act_in, act_out,
+                                          _stream()), "fd_linear_small")
 
 
 def time_sinusoid(time, out):
-    B, dim = out.shape
-    check(_lib.load().fd_time_sinusoid(_f32(time), _f32(out), B, dim, _stream()), "fd_time_sinusoid")
+    with _launched("time_sinusoid", "", 1):
+        B, dim = out.shape
+        check(_lib.load().fd_time_sinusoid(_f32(time), _f32(out), B, dim, _stream()), "fd_time_sinusoid")
 
 
 def sampler_init(ldct, noise, noise_scale, x_input, x_t, first):
-    check(_lib.load().fd_sampler_init(_f32(ldct), _f32(noise), float(noise_scale), _f32(x_input), _f32(x_t), _f32(first),
-                                      ldct.numel(), _stream()), "fd_sampler_init")
+    with _launched("sampler_init", "", 1):
+        check(_lib.load().fd_sampler_init(_f32(ldct), _f32(noise), float(noise_scale), _f32(x_input), _f32(x_t), _f32(first),
+                                          ldct.numel(), _stream()), "fd_sampler_init")
 
 
 def final_conv_update(feat, w, bias, x_input, x_t, noise, coef, x_next, pred_res=None, pred_noise=None, x_start=None):
     npix = x_input.numel()
     C = feat.shape[-1]
-    check(_lib.load().fd_final_conv_update(_p(feat), _f32(w), _f32(bias), _f32(x_input), _f32(x_t), _f32(noise), _f32(coef),
-                                           _f32(x_next), _f32(pred_res), _f32(pred_noise), _f32(x_start), npix, C,
-                                           dtype_code(feat.dtype), _stream()), "fd_final_conv_update")
+    with _launched("final_conv_update", f"{npix}x{C}"):
+        check(_lib.load().fd_final_conv_update(_p(feat), _f32(w), _f32(bias), _f32(x_input), _f32(x_t), _f32(noise), _f32(coef),
+                                               _f32(x_next), _f32(pred_res), _f32(pred_noise), _f32(x_start), npix, C,
+                                               dtype_code(feat.dtype), _stream()), "fd_final_conv_update")
 
 
 def unnormalize(x, out):
-    check(_lib.load().fd_unnormalize(_f32(x), _f32(out), x.numel(), _stream()), "fd_unnormalize")
+    with _launched("unnormalize", "", 1):
+        check(_lib.load().fd_unnormalize(_f32(x), _f32(out), x.numel(), _stream()), "fd_unnormalize")

@@ -206,3 +206,24 @@ def test_fp16_meets_strict_north_star_gate(model):
     set_mode(model, torch.float16)
     time = g["t999.time"].cuda()
     assert rel(model.model(g["x_in"].cuda(), [time, time])[0], g["t999.out"]) < STRICT_16BIT_GATE
+
+
+def test_full_size_512_vs_oracle(model, state_dict):
+    """BASELINE config 2 geometry (512x512, DDIM-2) on ONE slice against the CPU oracle (about 30 s of CPU time);
+    every convolution here takes the tcgen05 path."""
+    from founddiff_b200 import ops
+    g = torch.Generator().manual_seed(1234)
+    ldct = torch.rand(1, 1, 512, 512, generator=g)
+    ldct = torch.nn.functional.avg_pool2d(torch.nn.functional.pad(ldct, (2, 2, 2, 2), mode="reflect"), 5, stride=1)
+    noise = torch.randn(1, 1, 512, 512, generator=g)
+    otrace, trace = [], []
+    ref = O.sample(state_dict, ldct, noise, sampling_timesteps=2, trace=otrace)[-1]
+    for dt in (torch.bfloat16, torch.float16):
+        set_mode(model, dt, sampling_timesteps=2)
+        trace.clear()
+        out = model.sample([ldct.cuda()], last=True, noise={"init": noise}, trace=trace)[-1]
+        for a, b in zip(trace, otrace):
+            r = rel(a["pred_res"], b["pred_res"])
+            print(f"512^2 {dt} t={a['t']} pred_res rel-L2 {r:.3e}")
+            assert r < GATE[dt]
+        assert abs(O.psnr(out.cpu(), ldct) - O.psnr(ref, ldct)) < 0.05
