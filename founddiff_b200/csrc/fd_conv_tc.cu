@@ -15,6 +15,7 @@
 //   torch.cat inputs            : two tensor maps; K blocks switch map at c0.
 //   per-sample weights (W_eff)  : 3-D weight map {K, Cout, batch}.
 #include <cuda.h>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -26,8 +27,9 @@ constexpr int BM = 128;          // UMMA M (pixels per tile)
 constexpr int TILE_H = 8, TILE_W = 16;
 constexpr int BK = 64;           // K block = one 128-byte swizzle atom of 16-bit elements
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int NTHREADS = 192;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_EPI_WARPS = 16;
+constexpr int NTHREADS = (2 + NUM_EPI_WARPS) * 32;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, 16 epilogue warps
 
 struct TcParams {
     fd_conv_params p;
@@ -39,6 +41,8 @@ struct TcParams {
     int taps_h, taps_w;     // taps per phase
     int kblocks0, kblocks1; // 64-channel blocks of src0 / src1
     int fmt;                // 0 = f16, 1 = bf16 (UMMA a/b format)
+    int stages;             // depth of the smem ring
+    int total_tiles;
 };
 
 // ---------------------------------------------------------------------------------------------------- PTX helpers
@@ -108,62 +112,75 @@ FD_DEVINL uint32_t make_idesc(int fmt, int n) {
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// 32-byte (16 x 16-bit) vector global access: one full sector per thread per instruction (LDG/STG.E.ENL2.256)
 template <typename T> FD_DEVINL void store16(T* dst, const float (&v)[16]) {
-    float a[8], b[8];
+    uint32_t w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a[i] = v[i]; b[i] = v[8 + i]; }
-    fd_stv<T, 8>(dst, a);
-    fd_stv<T, 8>(dst + 8, b);
+    for (int i = 0; i < 8; ++i) {
+        if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        } else {
+            __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
 }
 template <typename T> FD_DEVINL void load16(const T* src, float (&v)[16]) {
-    float a[8], b[8];
-    fd_ldv<T, 8>(src, a);
-    fd_ldv<T, 8>(src + 8, b);
+    uint32_t w[8];
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(src));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] = a[i]; v[8 + i] = b[i]; }
+    for (int i = 0; i < 8; ++i) {
+        float2 f;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[i]));
+        else f = __half22float2(*reinterpret_cast<__half2*>(&w[i]));
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
 }
+FD_DEVINL float fast_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
-// ------------------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised kernel.  Roles: warp 0 = TMA producer, warp 1 = MMA issuer (owns TMEM), warps 2..17 =
+// epilogue (lane quarter = warp % 4, column group = (warp - 2) / 4).  Two TMEM accumulator buffers let the epilogue of
+// tile i overlap the loads + MMAs of tile i+1; every role walks the same static tile sequence
+// tile = blockIdx.x + i * gridDim.x (N tile fastest, so neighbouring CTAs share the A tile in L2).
 template <typename T>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [STAGES][A 16 KB][B BN*128 B] then barriers
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int BN = q.BN;
     const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)BN * BK * 2;
     const uint32_t stage_bytes = a_bytes + b_bytes;
-    uint64_t* full_bar = (uint64_t*)(smem + STAGES * stage_bytes);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* accum_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
-    float* s_gn = (float*)(tmem_slot + 2);      // [2][32] GroupNorm partial sums of this tile
+    const int stages = q.stages;
+    uint64_t* full_bar = (uint64_t*)(smem + stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + MAX_STAGES;     // [2] accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    float* s_gn = (float*)(tmem_slot + 2);            // [2][8] GroupNorm partial sums of the current sample
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fd_conv_params& p = q.p;
-
-    // tile coordinates
-    int t = blockIdx.x;
-    const int tw = t % q.tiles_w; t /= q.tiles_w;
-    const int th = t % q.tiles_h; t /= q.tiles_h;
-    const int phase = t % q.phases;
-    const int b = t / q.phases;
-    const int n0 = blockIdx.y * BN;
-    const int ho0 = th * TILE_H, wo0 = tw * TILE_W;       // in the (per-phase) output grid
-
     const int kb_per_tap = q.kblocks0 + q.kblocks1;
-    const int taps = q.taps_h * q.taps_w;
-    const int num_kb = taps * kb_per_tap;
+    const int num_kb = q.taps_h * q.taps_w * kb_per_tap;
+    const int total_tiles = q.total_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(accum_bar, 1);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 64) s_gn[threadIdx.x] = 0.f;
-    if (warp == 1) {  // TMEM allocation (power of two >= 32 columns), owned by this warp
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN));
+    if (threadIdx.x < 16) s_gn[threadIdx.x] = 0.f;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -178,27 +195,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
             int stage = 0;
             uint32_t ph = 0;
-            // input coordinate of the tile origin for tap (0,0)
-            int hbase, wbase;
-            if (p.upsample) {          // phase (a, b): low-res rows {i-1+a, i+a}, cols likewise
-                hbase = ho0 - 1 + (phase >> 1);
-                wbase = wo0 - 1 + (phase & 1);
-            } else {
-                hbase = ho0 * p.stride - p.pad;
-                wbase = wo0 * p.stride - p.pad;
-            }
-            const int wbatch = p.per_batch_weight ? b : phase;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int tap = kb / kb_per_tap, cb = kb % kb_per_tap;
-                const int kh = tap / q.taps_w, kw = tap % q.taps_w;
-                mbar_wait(&empty_bar[stage], ph ^ 1);
-                uint8_t* sa = smem + stage * stage_bytes;
-                uint8_t* sb = sa + a_bytes;
-                mbar_expect_tx(&full_bar[stage], stage_bytes);
-                if (cb < q.kblocks0) tma_load_4d(sa, &map_a0, &full_bar[stage], cb * BK, wbase + kw, hbase + kh, b);
-                else                 tma_load_4d(sa, &map_a1, &full_bar[stage], (cb - q.kblocks0) * BK, wbase + kw, hbase + kh, b);
-                tma_load_3d(sb, &map_w, &full_bar[stage], kb * BK, n0, wbatch);
-                if (++stage == STAGES) { stage = 0; ph ^= 1; }
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int nt = t % q.n_tiles; t /= q.n_tiles;
+                const int tw = t % q.tiles_w; t /= q.tiles_w;
+                const int th = t % q.tiles_h; t /= q.tiles_h;
+                const int phase = t % q.phases;
+                const int b = t / q.phases;
+                const int ho0 = th * TILE_H, wo0 = tw * TILE_W, n0 = nt * BN;
+                int hbase, wbase;
+                if (p.upsample) { hbase = ho0 - 1 + (phase >> 1); wbase = wo0 - 1 + (phase & 1); }
+                else { hbase = ho0 * p.stride - p.pad; wbase = wo0 * p.stride - p.pad; }
+                const int wbatch = p.per_batch_weight ? b : phase;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int tap = kb / kb_per_tap, cb = kb % kb_per_tap;
+                    const int kh = tap / q.taps_w, kw = tap % q.taps_w;
+                    mbar_wait(&empty_bar[stage], ph ^ 1);
+                    uint8_t* sa = smem + stage * stage_bytes;
+                    mbar_expect_tx(&full_bar[stage], stage_bytes);
+                    if (cb < q.kblocks0) tma_load_4d(sa, &map_a0, &full_bar[stage], cb * BK, wbase + kw, hbase + kh, b);
+                    else                 tma_load_4d(sa, &map_a1, &full_bar[stage], (cb - q.kblocks0) * BK, wbase + kw, hbase + kh, b);
+                    tma_load_3d(sa + a_bytes, &map_w, &full_bar[stage], kb * BK, n0, wbatch);
+                    if (++stage == stages) { stage = 0; ph ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -207,90 +226,129 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const uint32_t idesc = make_idesc(q.fmt, BN);
             int stage = 0;
             uint32_t ph = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full_bar[stage], ph);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                    umma_f16(tmem_base, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
-                             (kb | k) ? 1u : 0u);
-                umma_commit(&empty_bar[stage]);      // frees the smem slot when these MMAs retire
-                if (++stage == STAGES) { stage = 0; ph ^= 1; }
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_f16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
+                                 (kb | k) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == stages) { stage = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull_bar[buf]);
             }
-            umma_commit(accum_bar);                  // accumulator complete
         }
     } else {
-        // ================================ epilogue (4 warps = 128 TMEM lanes) ================================
-        const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
-        const int m = q4 * 32 + lane;                // accumulator row = pixel of the tile
-        const int oi = ho0 + m / TILE_W, oj = wo0 + m % TILE_W;      // per-phase output coordinates
-        const bool row_ok = oi < q.Hout / (p.upsample ? 2 : 1) && oj < q.Wout / (p.upsample ? 2 : 1);
-        const int oh = p.upsample ? 2 * oi + (phase >> 1) : oi;
-        const int ow = p.upsample ? 2 * oj + (phase & 1) : oj;
-        const long orow = (((long)b * q.Hout + oh) * q.Wout + ow) * p.Cout;
+        // ================================ epilogue: 16 warps ================================
+        const int q4 = warp & 3;                       // TMEM lane quarter this warp may access
+        const int cg = (warp - 2) >> 2;                // column group 0..3
+        const int cols_per_warp = BN / 4;
+        const int m = q4 * 32 + lane;                  // accumulator row = pixel of the tile
+        const int gh = q.Hout / (p.upsample ? 2 : 1), gw = q.Wout / (p.upsample ? 2 : 1);
         T* out = (T*)p.out;
         const T* addend = (const T*)p.addend;
-        const int cpg = p.gn_sums ? p.Cout / p.gn_groups : 16;
-        mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int c = 0; c < BN; c += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)c, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            float v[16];
-            const int n = n0 + c;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-                if (n + j >= p.silu_from) x = fd_silu(x);
-                v[j] = x;
+        const int cpg = p.gn_sums ? p.Cout / p.gn_groups : 8;
+        int cur_b = -1;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            int t = tile;
+            const int nt = t % q.n_tiles; t /= q.n_tiles;
+            const int tw = t % q.tiles_w; t /= q.tiles_w;
+            const int th = t % q.tiles_h; t /= q.tiles_h;
+            const int phase = t % q.phases;
+            const int b = t / q.phases;
+            const int n0 = nt * BN;
+            const int oi = th * TILE_H + m / TILE_W, oj = tw * TILE_W + m % TILE_W;
+            const bool row_ok = oi < gh && oj < gw;
+            const int oh = p.upsample ? 2 * oi + (phase >> 1) : oi;
+            const int ow = p.upsample ? 2 * oj + (phase & 1) : oj;
+            const long orow = (((long)b * q.Hout + oh) * q.Wout + ow) * p.Cout;
+            if (p.gn_sums && b != cur_b) {             // flush the previous sample's partial sums (uniform over the 16 warps)
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                const int et = threadIdx.x - 64;
+                if (cur_b >= 0 && et < 2 * p.gn_groups) {
+                    const int which = et / p.gn_groups, g = et % p.gn_groups;
+                    atomicAdd(&p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which], s_gn[which * 8 + g]);
+                    s_gn[which * 8 + g] = 0.f;
+                }
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                cur_b = b;
             }
-            if (p.gn_sums) {       // per-group sums over the tile's rows; 8 consecutive columns always share a group
+            const int buf = it & 1;
+            mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q4 * 32) << 16);
+            for (int cc = 0; cc < cols_per_warp; cc += 16) {
+                const int c = cg * cols_per_warp + cc;
+                uint32_t r[16];
+                tmem_ld16(tacc + (uint32_t)c, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cc + 16 >= cols_per_warp) {        // last TMEM read of this tile: hand the accumulator back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[buf])) : "memory");
+                }
+                float v[16];
+                const int n = n0 + c;
 #pragma unroll
-                for (int g0 = 0; g0 < 16; g0 += 8) {
-                    float s = 0.f, ss = 0.f;
+                for (int j = 0; j < 16; ++j) {
+                    float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
+                    if (n + j >= p.silu_from) x = fast_silu(x);
+                    v[j] = x;
+                }
+                if (p.gn_sums) {                       // 8 consecutive columns always share a group (cpg >= 8)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { const float x = row_ok ? v[g0 + j] : 0.f; s += x; ss = fmaf(x, x, ss); }
-                    s = fd_warp_sum(s);
-                    ss = fd_warp_sum(ss);
-                    if (lane == 0) {
-                        const int gl = (c + g0) / cpg;       // group index local to the tile (< 32)
-                        atomicAdd(&s_gn[gl], s);
-                        atomicAdd(&s_gn[32 + gl], ss);
+                    for (int g0 = 0; g0 < 16; g0 += 8) {
+                        float s = 0.f, ss = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { const float x = row_ok ? v[g0 + j] : 0.f; s += x; ss = fmaf(x, x, ss); }
+                        s = fd_warp_sum(s);
+                        ss = fd_warp_sum(ss);
+                        if (lane == 0) {
+                            const int g = (n + g0) / cpg;
+                            atomicAdd(&s_gn[g], s);
+                            atomicAdd(&s_gn[8 + g], ss);
+                        }
                     }
                 }
-            }
-            if (row_ok) {
-                if (p.gate) {
-                    const float* gp = p.gate + (long)b * p.gate_stride + n;
+                if (row_ok) {
+                    if (p.gate) {
+                        const float* gp = p.gate + (long)b * p.gate_stride + n;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] *= __ldg(gp + j);
-                }
-                if (addend) {
-                    float a[16];
-                    load16<T>(addend + orow + n, a);
+                        for (int j = 0; j < 16; ++j) v[j] *= __ldg(gp + j);
+                    }
+                    if (addend) {
+                        float a[16];
+                        load16<T>(addend + orow + n, a);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += a[j];
+                        for (int j = 0; j < 16; ++j) v[j] += a[j];
+                    }
+                    store16<T>(out + orow + n, v);
                 }
-                store16<T>(out + orow + n, v);
             }
         }
         if (p.gn_sums) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             const int et = threadIdx.x - 64;
-            const int ngl = (BN + cpg - 1) / cpg;
-            if (et < 2 * ngl) {
-                const int which = et / ngl, gl = et % ngl;
-                atomicAdd(&p.gn_sums[((long)b * p.gn_groups + n0 / cpg + gl) * 2 + which], s_gn[which * 32 + gl]);
+            if (cur_b >= 0 && et < 2 * p.gn_groups) {
+                const int which = et / p.gn_groups, g = et % p.gn_groups;
+                atomicAdd(&p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which], s_gn[which * 8 + g]);
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
     }
 }
 
@@ -367,7 +425,7 @@ extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
     }
     if (p->gn_sums) {
         const int cpg = p->Cout / p->gn_groups;
-        if (cpg < 8 || cpg % 8 || (cpg & (cpg - 1))) return 0;
+        if (cpg < 8 || cpg % 8 || (cpg & (cpg - 1)) || p->gn_groups > 8) return 0;
     }
     const uintptr_t al = (uintptr_t)p->src0 | (uintptr_t)p->src1 | (uintptr_t)p->weight | (uintptr_t)p->out |
                          (uintptr_t)p->addend | (uintptr_t)p->weight_up4;
@@ -411,8 +469,17 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
         rc = encode(&plan->map_w, p->dtype, 3, wbase, dims, strides, box, estr);
     }
     if (rc) { free(plan); return rc; }
-    plan->smem = (size_t)STAGES * (BM * BK * 2 + (size_t)q.BN * BK * 2) + 1024 /*align slack*/ + 512 /*barriers, gn*/;
-    plan->grid = dim3((unsigned)(p->B * q.phases * q.tiles_h * q.tiles_w), (unsigned)q.n_tiles);
+    const size_t stage_bytes = BM * BK * 2 + (size_t)q.BN * BK * 2;
+    const int num_kb = q.taps_h * q.taps_w * (q.kblocks0 + q.kblocks1);
+    q.stages = (int)((190 * 1024) / stage_bytes);
+    if (q.stages > MAX_STAGES) q.stages = MAX_STAGES;
+    if (q.stages > 2 * num_kb) q.stages = 2 * num_kb < 2 ? 2 : 2 * num_kb;     // enough to prefetch the next tile
+    q.total_tiles = p->B * q.phases * q.tiles_h * q.tiles_w * q.n_tiles;
+    plan->smem = (size_t)q.stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers, gn*/;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    plan->grid = dim3((unsigned)(q.total_tiles < sms ? q.total_tiles : sms));
     *out_plan = plan;
     return 0;
 }
@@ -422,14 +489,14 @@ extern "C" int fd_conv2d_tc_run(const fd_gemm_plan* plan, cudaStream_t stream) {
     static bool attr_bf16 = false, attr_f16 = false;
     if (plan->q.p.dtype == FD_BF16) {
         if (!attr_bf16) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr_bf16 = true;
         }
         conv_tc_kernel<__nv_bfloat16><<<plan->grid, NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
     } else {
         if (!attr_f16) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr_f16 = true;
         }
