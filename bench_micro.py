@@ -1,0 +1,132 @@
+#!/usr/bin/env python
+"""Micro-benchmarks of single hot-path kernels (BASELINE.json config 5: emamba2 selective scan + attention at 256^2 and
+512^2 feature maps vs the HBM roofline).  Each kernel is timed alone with CUDA events (3 warm-ups, then `--iters`
+launches; inputs are larger than L2 at batch 16), and reported as algorithmic GB/s and fraction of the measured HBM peak
+(MEASURED_PEAKS.json burst figure — kernels timed in isolation).
+
+    python bench_micro.py [--batch 16] [--iters 10] [--only scan|attn|xdt|ss2d|norm|conv] [--json out.json]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# (KD, L, N) of the nine selective-scan calls of one Unet evaluation at 512^2
+SCAN_SHAPES = [(512, 65536, 4), (512, 16384, 8), (1024, 4096, 16), (2048, 1024, 32), (4096, 1024, 32),
+               (2048, 4096, 16), (1024, 16384, 8)]
+LEVELS = [(64, 512, 4), (64, 256, 8), (128, 128, 16), (256, 64, 32), (512, 64, 32), (256, 128, 16), (128, 256, 8)]  # (C, H, N)
+
+
+def timeit(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--json", default="")
+    ap.add_argument("--pick", default="", help="comma-separated indices into the shape list of the selected kernel")
+    args = ap.parse_args()
+    from founddiff_b200 import ops
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
+    es = 4 if dt == torch.float32 else 2
+    B = args.batch
+    pick = [int(i) for i in args.pick.split(",")] if args.pick else None
+    sel = lambda lst: [x for i, x in enumerate(lst) if pick is None or i in pick]  # noqa: E731
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    rows = []
+
+    def report(kernel, shape, ms, byts, flops=0.0):
+        r = dict(kernel=kernel, shape=shape, us=round(ms * 1e3, 1), GBps=round(byts / ms / 1e6, 1), frac_hbm=round(byts / ms / 1e6 / hbm, 3),
+                 GFLOP=round(flops / 1e9, 2), TFLOPs=round(flops / ms / 1e9, 2))
+        rows.append(r)
+        print(f"{kernel:18s} {shape:34s} {r['us']:10.1f} us {r['GBps']:9.1f} GB/s ({r['frac_hbm']:.3f} of {hbm:.0f})  {r['TFLOPs']:8.2f} TFLOP/s", flush=True)
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rn = lambda *s, d=dt: torch.randn(*s, device="cuda", generator=g).to(d)  # noqa: E731
+
+    if args.only in ("", "scan"):
+        for KD, L, N in sel(SCAN_SHAPES):
+            u, delta = rn(B, KD, L), rn(B, KD, L) * 0.5
+            A = -torch.exp(torch.randn(KD, N, device="cuda", generator=g) * 0.3)
+            Bm, Cm = rn(B, 4, N, L, d=torch.float32), rn(B, 4, N, L, d=torch.float32)
+            D, bias = rn(KD, d=torch.float32), rn(KD, d=torch.float32)
+            y = torch.empty_like(u)
+            ms = timeit(lambda: ops.selective_scan_fwd(u, delta, A, Bm, Cm, D, bias, True, out=y), args.iters)
+            report("selective_scan", f"{B}x{KD}x{L} N{N}", ms, 3.0 * B * KD * L * es + 2.0 * B * 4 * N * L * 4, 9.0 * B * KD * L * N)
+            del u, delta, Bm, Cm, y
+    if args.only in ("", "attn"):
+        for C, H, _N in sel(LEVELS):
+            qkv = rn(B, H * H, 3 * C)
+            w = rn(3 * C, 9, d=torch.float32)
+            v = torch.empty(B, H * H, C, device="cuda", dtype=dt)
+            gram = torch.zeros(B, C // 32, 32, 32, device="cuda")
+            qk = torch.zeros(B, 2, C, device="cuda")
+            ms = timeit(lambda: ops.dwconv3x3_qkv_gram(qkv, w, v, gram, qk, B, H, H, C), args.iters)
+            report("dwconv_qkv_gram", f"{B}x{H}x{H}x{C}", ms, 4.0 * B * H * H * C * es, (54.0 + 64.0) * B * H * H * C)
+            del qkv, v
+    if args.only in ("", "xdt"):
+        for C, H, N in sel(LEVELS):
+            D, L, R = 2 * C, H * H // 4, math.ceil(C / 16)
+            xs = rn(B, 4, D, L)
+            Wx, Wd = rn(4, R + 2 * N, D, d=torch.float32), rn(4, D, R, d=torch.float32)
+            dts = torch.empty_like(xs)
+            Bs, Cs = torch.empty(B, 4, N, L, device="cuda"), torch.empty(B, 4, N, L, device="cuda")
+            ms = timeit(lambda: ops.xdt_proj(xs, Wx, Wd, dts, Bs, Cs, B, D, L, R, N), args.iters)
+            report("xdt_proj", f"{B}x{D}x{L} R{R} N{N}", ms, 2.0 * B * 4 * D * L * es + 2.0 * B * 4 * N * L * 4, 2.0 * B * 4 * L * D * (2 * R + 2 * N))
+            del xs, dts, Bs, Cs
+    if args.only in ("", "ss2d"):
+        for C, H, N in LEVELS[:3]:
+            D, L = 2 * C, H * H // 4
+            xz = rn(B, H * H, 4 * C)
+            w, b = rn(D, 9, d=torch.float32), rn(D, d=torch.float32)
+            xs = torch.empty(B, 4, D, L, device="cuda", dtype=dt)
+            ms = timeit(lambda: ops.dwconv3x3_silu_scan(xz, 4 * C, w, b, xs, B, H, H, D), args.iters)
+            report("dwconv_scan", f"{B}x{H}x{H}x{D}", ms, 2.0 * B * H * H * D * es)
+            gm, bt, loc = rn(D, d=torch.float32), rn(D, d=torch.float32), rn(B, D, d=torch.float32)
+            stat = torch.empty(B, H * H, 2, device="cuda")
+            out = torch.empty(B, H * H, D, device="cuda", dtype=dt)
+            ms = timeit(lambda: ops.merge_ln_gate(xs, xz, 4 * C, D, gm, bt, loc, stat, out, B, H, H, D), args.iters)
+            report("merge_ln_gate", f"{B}x{H}x{H}x{D}", ms, 3.0 * B * H * H * D * es)
+            del xz, xs, out
+    if args.only in ("", "norm"):
+        from founddiff_b200.engine import _view_ptr
+        for C, H, _ in LEVELS[:3]:
+            P = H * H
+            x, out = rn(B, P, C), torch.empty(B, P, C, device="cuda", dtype=dt)
+            mods = rn(B, 6 * C, d=torch.float32)
+            gm, bt = rn(C, d=torch.float32), rn(C, d=torch.float32)
+            ms = timeit(lambda: ops.ln_modulate(x, out, gm, bt, _view_ptr(mods[:, :C]), _view_ptr(mods[:, C:2 * C]), 6 * C, B, P, C, 1e-5), args.iters)
+            report("ln_modulate", f"{B}x{P}x{C}", ms, 2.0 * B * P * C * es)
+            sums = torch.zeros(B, 8, 2, device="cuda")
+            ops.gn_stats(x, sums, B, P, C, 8)
+            ms = timeit(lambda: ops.gn_silu_add(x, sums, gm, bt, x, out, B, P, C, 8), args.iters)
+            report("gn_silu_add", f"{B}x{P}x{C}", ms, 3.0 * B * P * C * es)
+    if args.json:
+        os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
+        json.dump(dict(batch=B, dtype=args.dtype, hbm_peak_gbs=hbm, rows=rows), open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

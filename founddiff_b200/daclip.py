@@ -28,7 +28,12 @@ class DAClipEncoder:
     """Holds the frozen visual-tower weights on one device and maps (B,1,H,W) slices in [-1,1] to
     (dose_embedding (B,1024), context_embedding (B,256))."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device, layers: Sequence[int] = (3, 4, 6, 3), heads: int = 32):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, layers: Sequence[int] = (3, 4, 6, 3), heads: int = 32,
+                 conv_dtype: torch.dtype = torch.float32):
+        # conv_dtype: storage/compute type of the RN50 convolutions.  bf16 (tensor-core cuDNN, channels_last) is used
+        # by the 16-bit sampling modes: it perturbs the embeddings by ~6e-3 and the Unet output by ~1.6e-4 rel-L2
+        # (measured with the oracle, DESIGN.md "Precision"), far below the 16-bit path's own rounding.
+        self.conv_dtype = conv_dtype
         self.sd = {k: v.detach().to(device=device, dtype=torch.float32 if v.is_floating_point() else v.dtype)
                    for k, v in state_dict.items() if k.startswith(PREFIX)}
         self.layers, self.heads = tuple(layers), heads
@@ -41,7 +46,8 @@ class DAClipEncoder:
             sd = self.sd
             w = sd[conv + ".weight"]
             s = sd[bn + ".weight"] * torch.rsqrt(sd[bn + ".running_var"] + 1e-5)
-            self._folded[key] = ((w * s[:, None, None, None]).contiguous(), (sd[bn + ".bias"] - sd[bn + ".running_mean"] * s).contiguous())
+            wf = (w * s[:, None, None, None]).to(self.conv_dtype).contiguous(memory_format=torch.channels_last)
+            self._folded[key] = (wf, (sd[bn + ".bias"] - sd[bn + ".running_mean"] * s).to(self.conv_dtype).contiguous())
         w, b = self._folded[key]
         return F.conv2d(x, w, b, stride=stride, padding=padding)
 
@@ -66,7 +72,7 @@ class DAClipEncoder:
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
         try:
-            x = x_input.to(torch.float32).repeat(1, 3, 1, 1)                       # src/DADiff.py:692
+            x = x_input.to(self.conv_dtype).repeat(1, 3, 1, 1).contiguous(memory_format=torch.channels_last)   # src/DADiff.py:692
             x = F.relu(self._conv_bn(x, v + "conv1", v + "bn1", stride=2, padding=1))
             x = F.relu(self._conv_bn(x, v + "conv2", v + "bn2", padding=1))
             x = F.relu(self._conv_bn(x, v + "conv3", v + "bn3", padding=1))
@@ -75,6 +81,7 @@ class DAClipEncoder:
                 for bi in range(blocks):
                     x = self._bottleneck(f"{v}layer{li + 1}.{bi}.", x, 2 if (li > 0 and bi == 0) else 1)
             a = v + "attnpool."
+            x = x.float()
             B, C, H, W = x.shape
             tok = x.reshape(B, C, H * W).permute(2, 0, 1)
             tok = torch.cat([tok.mean(dim=0, keepdim=True), tok], dim=0)          # (HW+1, B, C)

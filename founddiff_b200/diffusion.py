@@ -133,8 +133,9 @@ class UnetRes(nn.Module):
         return eng
 
     def daclip(self, device) -> DAClipEncoder:
-        if self._daclip is None or str(self._daclip_dev) != str(device):
-            self._daclip = DAClipEncoder(self._live_sd(), device)
+        cdt = torch.float32 if self.compute_dtype == torch.float32 else torch.bfloat16
+        if self._daclip is None or str(self._daclip_dev) != str(device) or self._daclip.conv_dtype != cdt:
+            self._daclip = DAClipEncoder(self._live_sd(), device, conv_dtype=cdt)
             self._daclip_dev = device
         return self._daclip
 

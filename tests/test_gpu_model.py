@@ -119,7 +119,8 @@ def test_unet_forward_vs_reference(model, dt):
         assert r < GATE[dt], (dt, t, r)
     # DA-CLIP embeddings (computed once per slice) match the reference's
     dose, ctx = model.model.daclip(x.device).embed(x[:, 1:2])
-    assert rel(dose, g["dose_emb"]) < 1e-4 and rel(ctx, g["ctx_emb"]) < 1e-4
+    etol = 1e-4 if dt == torch.float32 else 2e-2          # 16-bit modes run the RN50 tower in bf16 (DESIGN.md "Precision")
+    assert rel(dose, g["dose_emb"]) < etol and rel(ctx, g["ctx_emb"]) < etol
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
