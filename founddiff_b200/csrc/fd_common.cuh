@@ -86,6 +86,26 @@ FD_DEVINL float fd_warp_max(float v) {
     return v;
 }
 
+// ---- warp-level tensor-core helpers (mma.sync m16n8k16, fp32 accumulate) for the small, memory-bound GEMMs that sit
+// inside fused kernels (Gram matrices, x_proj/dt_proj); the large convolutions / projections use tcgen05 (fd_conv_tc.cu).
+FD_DEVINL void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+FD_DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_ptr);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+template <typename T> FD_DEVINL void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <> FD_DEVINL void mma_16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <> FD_DEVINL void mma_16816<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // dtype dispatch for the extern "C" wrappers
 #define FD_DISPATCH_DTYPE(dtype, T, ...)                                           \
     switch (dtype) {                                                               \

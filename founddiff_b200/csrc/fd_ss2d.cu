@@ -9,6 +9,8 @@
 //   k in {1,3} (odd  h): l = (w/2)*(H/2) + (h/2)   (column-major sub-grid)            emamba2.py:207-210
 // Both transposing kernels stage a 32x32-pixel x 16-channel tile in shared memory so that global reads are
 // 16-byte vectors along channels and global writes are 16-byte vectors along l (and vice versa).
+#include <type_traits>
+
 #include "fd_common.cuh"
 
 namespace {
@@ -154,6 +156,163 @@ __global__ void __launch_bounds__(128) xdt_proj_kernel(const T* __restrict__ xs,
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// x_proj + dt_proj on the tensor cores (16-bit storage types).  Per (sample, direction) and 128 consecutive l:
+//   stage 1:  X_dbl[c, l] = sum_d Wx[c, d] xs[d, l]        M = c (<= 96, padded to 16), N = l (128), K = d
+//   stage 2:  dts[d, l]   = sum_r Wdt[d, r] X_dbl[r, l]     M = d, N = l, K = r (padded to 16 / 32)
+// mma.sync m16n8k16 with fp32 accumulation; xs chunks are staged in shared memory (ldmatrix.trans, since the scan
+// layout is l-contiguous), weights arrive pre-converted / zero-padded from the host (xw16: (4, CCp, D), dw16: (4, D, Rp)).
+// The kernel is bound by the xs read + dts write (2 x 2PC elements); the matmuls are ~2 % of the tensor peak.
+constexpr int XT_L = 128;          // l tile
+constexpr int XT_KC = 32;          // d chunk of stage 1
+constexpr int XT_XLD = XT_L + 8;   // padded row of the xs / X_dbl / output tiles (conflict-free ldmatrix)
+constexpr int XT_WLD = XT_KC + 8;
+
+template <typename T, int MT>      // MT = CCp / 16 (1..6)
+__global__ void __launch_bounds__(256) xdt_proj_mma_kernel(const T* __restrict__ xs, const T* __restrict__ xw16,
+                                                           const T* __restrict__ dw16, T* __restrict__ dts,
+                                                           float* __restrict__ Bs, float* __restrict__ Cs, int D, int L, int R,
+                                                           int N, int Rp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_x = reinterpret_cast<T*>(smem_raw);                 // [XT_KC][XT_XLD]
+    T* s_w = s_x + XT_KC * XT_XLD;                           // [MT*16][XT_WLD]
+    T* s_xd = s_w + MT * 16 * XT_WLD;                        // [32][XT_XLD]   first Rp rows of X_dbl
+    T* s_o = s_xd + 32 * XT_XLD;                             // [8 warps][16][XT_XLD] output staging
+    const int CC = R + 2 * N, CCp = MT * 16;
+    const int bk = blockIdx.y, k = bk & 3;
+    const int l0 = blockIdx.x * XT_L;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const T* xr = xs + (long)bk * D * L;
+    const T* wx = xw16 + (long)k * CCp * D;
+    const bool full = (l0 + XT_L <= L) && (L % 8 == 0);
+
+    float acc[MT][2][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+
+    for (int d0 = 0; d0 < D; d0 += XT_KC) {
+        __syncthreads();
+        // xs chunk: 32 rows x 128 l  (16 vectors of 8 per row)
+        for (int i = tid; i < XT_KC * (XT_L / 8); i += 256) {
+            const int r = i / (XT_L / 8), v = i % (XT_L / 8);
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (d0 + r < D) {
+                const T* src = xr + (long)(d0 + r) * L + l0 + v * 8;
+                if (full) val = *reinterpret_cast<const uint4*>(src);
+                else {
+                    T tmp[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) tmp[e] = (l0 + v * 8 + e < L) ? src[e] : T(0.f);
+                    val = *reinterpret_cast<uint4*>(tmp);
+                }
+            }
+            *reinterpret_cast<uint4*>(s_x + r * XT_XLD + v * 8) = val;
+        }
+        // Wx chunk: CCp rows x 32 d (4 vectors per row)
+        for (int i = tid; i < CCp * (XT_KC / 8); i += 256) {
+            const int r = i / (XT_KC / 8), v = i % (XT_KC / 8);
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (d0 + v * 8 < D) val = *reinterpret_cast<const uint4*>(wx + (long)r * D + d0 + v * 8);
+            *reinterpret_cast<uint4*>(s_w + r * XT_WLD + v * 8) = val;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < XT_KC / 16; ++ks) {
+            uint32_t bfr[4];
+            ldmatrix_x4_trans(bfr, s_x + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * XT_XLD + warp * 16 + 8 * (lane >> 4));
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                uint32_t afr[4];
+                ldmatrix_x4(afr, s_w + (mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * XT_WLD + ks * 16 + 8 * (lane >> 4));
+                mma_16816<T>(acc[mt][0], afr, bfr[0], bfr[1]);
+                mma_16816<T>(acc[mt][1], afr, bfr[2], bfr[3]);
+            }
+        }
+    }
+    // stage-1 epilogue: Bs / Cs (fp32, global) and the dt rows (16-bit, shared)
+    for (int i = tid; i < 32 * XT_XLD / 8; i += 256) *reinterpret_cast<uint4*>(s_xd + i * 8) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int c = mt * 16 + g + 8 * hh;
+                const int col = warp * 16 + nt * 8 + 2 * t4;
+                const float v0 = acc[mt][nt][2 * hh], v1 = acc[mt][nt][2 * hh + 1];
+                if (c < R) {
+                    fd_st(s_xd + c * XT_XLD + col, v0);
+                    fd_st(s_xd + c * XT_XLD + col + 1, v1);
+                } else if (c < CC) {
+                    float* dst = (c < R + N ? Bs + ((long)bk * N + (c - R)) * L : Cs + ((long)bk * N + (c - R - N)) * L) + l0 + col;
+                    if (l0 + col + 1 < L) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+                    else if (l0 + col < L) dst[0] = v0;
+                }
+            }
+    __syncthreads();
+    // stage 2: each warp takes m-tiles (16 channels d) round-robin, all 128 l
+    const T* wd = dw16 + (long)k * D * Rp;
+    T* so = s_o + warp * 16 * XT_XLD;
+    T* dr = dts + (long)bk * D * L;
+    for (int mtile = warp; mtile * 16 < D; mtile += 8) {
+        const int dbase = mtile * 16;
+        float o[16][4];
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+        for (int ks = 0; ks < Rp / 16; ++ks) {
+            uint32_t afr[4];
+            const T* w0 = wd + (long)(dbase + g) * Rp + ks * 16 + 2 * t4;
+            const T* w1 = wd + (long)(dbase + g + 8) * Rp + ks * 16 + 2 * t4;
+            afr[0] = *reinterpret_cast<const uint32_t*>(w0);
+            afr[1] = *reinterpret_cast<const uint32_t*>(w1);
+            afr[2] = *reinterpret_cast<const uint32_t*>(w0 + 8);
+            afr[3] = *reinterpret_cast<const uint32_t*>(w1 + 8);
+#pragma unroll
+            for (int np = 0; np < 8; ++np) {
+                uint32_t bfr[4];
+                ldmatrix_x4_trans(bfr, s_xd + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * XT_XLD + np * 16 + 8 * (lane >> 4));
+                mma_16816<T>(o[2 * np], afr, bfr[0], bfr[1]);
+                mma_16816<T>(o[2 * np + 1], afr, bfr[2], bfr[3]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) {
+            const int col = nt * 8 + 2 * t4;
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                *reinterpret_cast<__nv_bfloat162*>(so + g * XT_XLD + col) = __floats2bfloat162_rn(o[nt][0], o[nt][1]);
+                *reinterpret_cast<__nv_bfloat162*>(so + (g + 8) * XT_XLD + col) = __floats2bfloat162_rn(o[nt][2], o[nt][3]);
+            } else {
+                *reinterpret_cast<__half2*>(so + g * XT_XLD + col) = __floats2half2_rn(o[nt][0], o[nt][1]);
+                *reinterpret_cast<__half2*>(so + (g + 8) * XT_XLD + col) = __floats2half2_rn(o[nt][2], o[nt][3]);
+            }
+        }
+        __syncwarp();
+        // 16 rows x 256 B: lanes write 16-byte chunks, two rows per instruction
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 2 + (lane >> 4), v = lane & 15;
+            if (dbase + r < D) {
+                T* dst = dr + (long)(dbase + r) * L + l0 + v * 8;
+                if (full) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(so + r * XT_XLD + v * 8);
+                else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (l0 + v * 8 + e < L) dst[e] = so[r * XT_XLD + v * 8 + e];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // merge, pass 1: per-pixel LayerNorm statistics straight from the scan layout (thread per l, loop over d).
 template <typename T>
 __global__ void __launch_bounds__(256) merge_stats_kernel(const T* __restrict__ ys, float* __restrict__ stats, int H, int W,
@@ -283,6 +442,40 @@ extern "C" int fd_xdt_proj(const void* xs, const float* x_proj_w, const float* d
     if (!xs || !x_proj_w || !dt_w || !dts || !Bs || !Cs || B <= 0 || D <= 0 || L <= 0 || R <= 0 || N <= 0) return FD_ERR_BAD_ARGUMENT;
     FD_DISPATCH_DTYPE(dtype, T, return xdt_launch<T>(xs, x_proj_w, dt_w, dts, Bs, Cs, B, D, L, R, N, stream));
     return 0;
+}
+
+template <typename T>
+static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, void* dts, float* Bs, float* Cs, int B, int D, int L,
+                          int R, int N, int Rp, cudaStream_t stream) {
+    const int CC = R + 2 * N;
+    const int MT = (CC + 15) / 16;
+    dim3 grid(fd_cdiv(L, XT_L), B * 4);
+#define XDT_MMA_CASE(M)                                                                                                        \
+    if (MT == M) {                                                                                                             \
+        const size_t smem = ((size_t)XT_KC * XT_XLD + (size_t)M * 16 * XT_WLD + 32 * XT_XLD + 8 * 16 * XT_XLD) * sizeof(T);     \
+        static bool attr_set = false;                                                                                          \
+        if (!attr_set) {                                                                                                       \
+            cudaError_t e = cudaFuncSetAttribute(xdt_proj_mma_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                                                               \
+            attr_set = true;                                                                                                   \
+        }                                                                                                                      \
+        xdt_proj_mma_kernel<T, M><<<grid, 256, smem, stream>>>((const T*)xs, (const T*)xw16, (const T*)dw16, (T*)dts, Bs, Cs, D, L, \
+                                                                R, N, Rp);                                                      \
+        FD_LAUNCH_CHECK();                                                                                                     \
+        return 0;                                                                                                              \
+    }
+    XDT_MMA_CASE(1) XDT_MMA_CASE(2) XDT_MMA_CASE(3) XDT_MMA_CASE(4) XDT_MMA_CASE(5) XDT_MMA_CASE(6)
+#undef XDT_MMA_CASE
+    return FD_ERR_UNSUPPORTED;
+}
+
+extern "C" int fd_xdt_proj_tc(const void* xs, const void* xw16, const void* dw16, void* dts, float* Bs, float* Cs, int B, int D,
+                              int L, int R, int N, int Rp, int dtype, cudaStream_t stream) {
+    if (!xs || !xw16 || !dw16 || !dts || !Bs || !Cs || B <= 0 || D <= 0 || L <= 0 || R <= 0 || N <= 0) return FD_ERR_BAD_ARGUMENT;
+    if ((Rp != 16 && Rp != 32) || R > Rp || D % 16 || R + 2 * N > 96) return FD_ERR_UNSUPPORTED;
+    if (dtype == FD_BF16) return xdt_mma_launch<__nv_bfloat16>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, stream);
+    if (dtype == FD_F16) return xdt_mma_launch<__half>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, stream);
+    return FD_ERR_UNSUPPORTED;
 }
 
 extern "C" int fd_merge_ln_gate(const void* ys, const void* xz, int ld, int z_off, const float* gamma, const float* beta,

@@ -264,6 +264,9 @@ class UnetEngine:
         out_w = to_dt(sd[p + ".mamba.out_proj.weight"])                                                # (C, 2C)
         dw_w, dw_b = f32(p + ".mamba.conv2d.weight").reshape(D, 9).contiguous(), f32(p + ".mamba.conv2d.bias")
         xp_w, dtp_w = f32(p + ".mamba.x_proj_weight"), f32(p + ".mamba.dt_projs_weight")
+        use_xdt_tc = dt != torch.float32 and R <= 32 and R + 2 * N <= 96
+        if use_xdt_tc:
+            xw16, dw16, Rp = ops.pack_xdt_weights(xp_w, dtp_w, dt)
         dt_bias = f32(p + ".mamba.dt_projs_bias").reshape(-1).contiguous()
         A_neg = (-torch.exp(f32(p + ".mamba.A_logs"))).contiguous()                                   # emamba2.py:344
         Ds = f32(p + ".mamba.Ds")
@@ -293,7 +296,10 @@ class UnetEngine:
             ops.ln_modulate(x_in, a, n1w, n1b, sh1, sc1, MS, B, P, C, 1e-5)
             c_in.run()
             ops.dwconv3x3_silu_scan(xz, 4 * C, dw_w, dw_b, xs, B, h, w, D)
-            ops.xdt_proj(xs, xp_w, dtp_w, dts, Bs, Cs, B, D, L, R, N)
+            if use_xdt_tc:
+                ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N)
+            else:
+                ops.xdt_proj(xs, xp_w, dtp_w, dts, Bs, Cs, B, D, L, R, N)
             ops.selective_scan_fwd(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs, Cs, Ds, dt_bias, True,
                                    out=ys.view(B, 4 * D, L))
             ops.merge_ln_gate(ys, xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), stat, g, B, h, w, D)

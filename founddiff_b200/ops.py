@@ -203,6 +203,25 @@ def xdt_proj(xs, x_proj_w, dt_w, dts, Bs, Cs, B, D, L, R, N):
                                       dtype_code(xs.dtype), _stream()), "fd_xdt_proj")
 
 
+def pack_xdt_weights(x_proj_w: torch.Tensor, dt_w: torch.Tensor, dtype: torch.dtype):
+    """(4, R+2N, D) / (4, D, R) fp32 -> zero-padded 16-bit copies for fd_xdt_proj_tc: (4, CCp, D), (4, D, Rp), Rp."""
+    K, CC, D = x_proj_w.shape
+    R = dt_w.shape[-1]
+    CCp = (CC + 15) // 16 * 16
+    Rp = 16 if R <= 16 else 32
+    xw = torch.zeros(K, CCp, D, device=x_proj_w.device, dtype=dtype)
+    xw[:, :CC] = x_proj_w.to(dtype)
+    dw = torch.zeros(K, D, Rp, device=dt_w.device, dtype=dtype)
+    dw[:, :, :R] = dt_w.to(dtype)
+    return xw.contiguous(), dw.contiguous(), Rp
+
+
+def xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N):
+    with _launched("xdt_proj_tc", f"{B}x{D}x{L} R{R} N{N}", 1):
+        check(_lib.load().fd_xdt_proj_tc(_p(xs), _p(xw16), _p(dw16), _p(dts), _f32(Bs), _f32(Cs), B, D, L, R, N, Rp,
+                                         dtype_code(xs.dtype), _stream()), "fd_xdt_proj_tc")
+
+
 def merge_ln_gate(ys, xz, ld, z_off, gamma, beta, local, stats_ws, out, B, H, W, D, eps=1e-5):
     with _launched("merge_ln_gate", f"{B}x{H}x{W}x{D}", 2):
         check(_lib.load().fd_merge_ln_gate(_p(ys), _p(xz), ld, z_off, _f32(gamma), _f32(beta), _f32(local), _f32(stats_ws),

@@ -124,6 +124,11 @@ int fd_dwconv3x3_silu_scan(const void* xz, int ld, const float* w, const float* 
 int fd_xdt_proj(const void* xs, const float* x_proj_w, const float* dt_w, void* dts, float* Bs, float* Cs, int B,
                 int D, int L, int R, int N, int dtype, cudaStream_t stream);
 
+/* Tensor-core variant (dtype bf16 / fp16): xw16 = x_proj_w in `dtype`, rows zero-padded to a multiple of 16:
+ * (4, CCp, D); dw16 = dt_w in `dtype`, columns zero-padded to Rp in {16, 32}: (4, D, Rp).  Same outputs. */
+int fd_xdt_proj_tc(const void* xs, const void* xw16, const void* dw16, void* dts, float* Bs, float* Cs, int B, int D,
+                   int L, int R, int N, int Rp, int dtype, cudaStream_t stream);
+
 /* SS2D consumer: EfficientMerge (src/emamba2.py:238-262) + out_norm LayerNorm(D) (:365) + y*z + local (:747-748).
  * ys: (B,4,D,L); z = columns [z_off, z_off+D) of xz rows (already SiLU'd); local: (B, D) fp32; out: (B,H,W,D).
  * stats_ws: caller-provided workspace of B*H*W*2 floats (per-pixel mean / rstd). */

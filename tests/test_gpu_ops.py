@@ -236,7 +236,8 @@ def test_dwconv_scan_and_merge(ops, hw, dt):
     assert rel(out.reshape(B, H, W, D), ref) < TOL[dt]
 
 
-@pytest.mark.parametrize("cfg", [(128, 4, 4, 100), (128, 4, 8, 384), (256, 8, 16, 64), (1024, 32, 32, 40)])
+@pytest.mark.parametrize("cfg", [(128, 4, 4, 100), (128, 4, 8, 384), (256, 8, 16, 64), (1024, 32, 32, 40), (512, 16, 32, 1024),
+                                 (128, 4, 4, 4096)])
 @pytest.mark.parametrize("dt", DTYPES)
 def test_xdt_proj(ops, cfg, dt):
     D, R, N, L = cfg
@@ -252,6 +253,13 @@ def test_xdt_proj(ops, cfg, dt):
     Bs, Cs = torch.empty(B, 4, N, L, device="cuda"), torch.empty(B, 4, N, L, device="cuda")
     ops.xdt_proj(xs.to("cuda", dt), Wx.cuda(), Wdt.cuda(), dts, Bs, Cs, B, D, L, R, N)
     assert rel(dts, dts_r) < TOL[dt] and rel(Bs, Bs_r) < 2e-5 and rel(Cs, Cs_r) < 2e-5
+    if dt != torch.float32:       # tensor-core variant: 16-bit weights, fp32 accumulation
+        xw16, dw16, Rp = ops.pack_xdt_weights(Wx.cuda(), Wdt.cuda(), dt)
+        dts2 = torch.zeros_like(dts)
+        Bs2, Cs2 = torch.zeros_like(Bs), torch.zeros_like(Cs)
+        ops.xdt_proj_tc(xs.to("cuda", dt), xw16, dw16, Rp, dts2, Bs2, Cs2, B, D, L, R, N)
+        wt = 1e-2 if dt == torch.bfloat16 else 2e-3
+        assert rel(dts2, dts_r) < 2 * wt and rel(Bs2, Bs_r) < wt and rel(Cs2, Cs_r) < wt
 
 
 @pytest.mark.parametrize("C", [64, 128])
@@ -278,7 +286,10 @@ def test_transposed_attention(ops, C, hw, dt):
     qk = torch.zeros(B, 2, C, device="cuda")
     ops.dwconv3x3_qkv_gram(nhwc(qkv, dt), wdw.reshape(3 * C, 9).cuda(), v, gram, qk, B, H, W, C)
     assert rel(nchw(v, H, W), vv) < TOL[dt]
-    assert rel(gram, qq.reshape(B, heads, 32, -1) @ kk.reshape(B, heads, 32, -1).transpose(-2, -1)) < 1e-4
+    # 16-bit modes form the Gram matrix on the tensor cores from q, k rounded once to the storage type
+    gtol = {torch.float32: 1e-4, torch.bfloat16: 1e-2, torch.float16: 2e-3}[dt]
+    assert rel(gram, qq.reshape(B, heads, 32, -1) @ kk.reshape(B, heads, 32, -1).transpose(-2, -1)) < gtol
+    assert rel(qk[:, 0], (qq * qq).sum(dim=(2, 3))) < gtol and rel(qk[:, 1], (kk * kk).sum(dim=(2, 3))) < gtol
     weff = torch.empty(B, C, C, device="cuda", dtype=dt)
     ops.attn_weff(gram, qk, temp.reshape(-1).cuda(), wproj.reshape(C, C).cuda(), weff, B, C)
     out = torch.empty(B, H * W, C, device="cuda", dtype=dt)
