@@ -44,7 +44,7 @@ def ops():
 
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(2, 4, 8, 4, 300), (1, 4, 16, 16, 65), (2, 1, 4, 32, 1), (2, 4, 32, 8, 1024),
-                                   (1, 4, 8, 32, 2048), (1, 2, 6, 5, 77)])
+                                   (1, 4, 8, 32, 2048), (1, 2, 6, 5, 77), (2, 4, 16, 4, 512), (1, 4, 8, 16, 776), (2, 2, 24, 8, 264)])
 @pytest.mark.parametrize("dt", DTYPES)
 def test_selective_scan(ops, shape, dt):
     b, K, Dk, N, L = shape
