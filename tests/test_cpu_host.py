@@ -1,0 +1,156 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares (no compute without a GPU), host
+logic (schedule / step plan / weight schema / key layout), the no-CPU-fallback rule, and the N>1 sharding path on 2 gloo ranks."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+
+def test_library_exports_every_declared_symbol():
+    from founddiff_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "founddiff_b200.h")).read()
+    declared = set(re.findall(r"\b(fd_[a-z0-9_]+)\s*\(", header)) - {"fd_dtype"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/founddiff_b200.h but not exported"
+    assert set(_lib.EXPORTS) <= declared
+    assert b"sm_100a" in lib.fd_version()
+    # the library must not depend on a GPU driver being present (symbol test runs on CPU boxes)
+    out = subprocess.run(["ldd", _lib.lib_path()], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out and "libtorch" not in out
+
+
+def test_no_cpu_fallback():
+    from founddiff_b200 import ops
+    from founddiff_b200._lib import FdError
+    with pytest.raises(FdError):
+        ops.unnormalize(torch.zeros(4), torch.zeros(4))
+    from founddiff_b200.diffusion import ResidualDiffusion, UnetRes
+    m = UnetRes(dim=64, dim_mults=(1, 2, 4, 8), num_unet=1, condition=True, objective='pred_res', test_res_or_noise='res')
+    d = ResidualDiffusion(m, image_size=64, timesteps=1000, sampling_timesteps=2, objective='pred_res', condition=True, sum_scale=0.01)
+    with pytest.raises(RuntimeError):
+        d.sample([torch.rand(1, 1, 64, 64)], last=True)
+    with pytest.raises(RuntimeError):
+        m(torch.rand(1, 2, 64, 64), [torch.zeros(1), torch.zeros(1)])
+    with pytest.raises(NotImplementedError):
+        UnetRes(dim=64, num_unet=2, objective='pred_res_noise')
+    # product code never imports the oracle
+    for root, _, files in os.walk(os.path.join(ROOT, "founddiff_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_schedule_and_step_plan_match_reference():
+    from founddiff_b200.diffusion import ResidualDiffusion, UnetRes, make_schedule
+    g = load_golden("schedule.npz")
+    for variant in ("ctor", "init"):
+        for k, v in make_schedule(1000, variant).items():
+            assert torch.allclose(v, g[f"{variant}.{k}"], rtol=1e-6, atol=1e-9), (variant, k)
+    m = UnetRes(dim=64, dim_mults=(1, 2, 4, 8), num_unet=1, condition=True, objective='pred_res', test_res_or_noise='res')
+    d = ResidualDiffusion(m, image_size=512, timesteps=1000, sampling_timesteps=2, objective='pred_res', condition=True, sum_scale=0.01)
+    assert torch.allclose(d.alphas, g["ctor.alphas"])
+    d.init()
+    assert torch.allclose(d.alphas, g["init.alphas"]) and d.is_ddim_sampling and d.ddim_sampling_eta == 0.
+    plan = d._step_plan()
+    assert [t for t, _ in plan] == [999, 499]                       # src/DADiff.py:1287-1291 with S = 2
+    acs = g["init.alphas_cumsum"]
+    assert abs(plan[0][1][1] + float(acs[999] - acs[499])) < 1e-7 and plan[0][1][0] == 1.0
+    assert plan[1][1][:4] == [0., 0., 1., 0.]                       # last pair: img = x_start (:1317-1321)
+    d.sampling_timesteps, d.is_ddim_sampling = 1000, False
+    plan = d._step_plan()
+    assert len(plan) == 1000 and plan[0][0] == 999 and plan[-1][0] == 0 and plan[-1][1][3] == 0.0
+    t = 500
+    assert abs(plan[999 - t][1][0] - float(g["init.posterior_mean_coef1"][t])) < 1e-7
+    assert abs(plan[999 - t][1][3] - float((0.5 * g["init.posterior_log_variance_clipped"][t]).exp())) < 1e-7
+
+
+def test_weight_schema_and_checkpoint_ingestion():
+    from founddiff_b200 import weights
+    from founddiff_b200.diffusion import UnetRes
+    sd = weights.random_state_dict(10)
+    sd2 = weights.random_state_dict(10)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)              # deterministic: fixtures depend on it
+    blk = sd["downs.0.1.adaLN_modulation.1.weight"]
+    assert blk.abs().max() > 0                                       # de-zeroed (SURVEY "Five facts" #1)
+    # a reference-style checkpoint: EMA prefix + dead members; live keys are picked, dead ones dropped
+    ckpt = {"ema_model.model.unet0." + k: v for k, v in sd.items()}
+    ckpt["ema_model.model.unet0.clip_model.visual.conv1.weight"] = torch.zeros(1)
+    live = weights.extract_live_weights(ckpt)
+    assert set(live) == set(sd)
+    m = UnetRes(dim=64, dim_mults=(1, 2, 4, 8), num_unet=1, condition=True, objective='pred_res', test_res_or_noise='res', seed=3)
+    state = {"unet0." + k: v for k, v in sd.items()}
+    state["unet0.clip_model.visual.conv1.weight"] = torch.zeros(1)
+    state["unet0.dose_encoder.prompt_learner.ctx"] = torch.zeros(2, 16, 512)
+    m.load_state_dict(state)
+    assert torch.equal(m.unet0.state_dict()["init_conv.weight"], sd["init_conv.weight"])
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({**state, "unet0.bogus": torch.zeros(1)})
+
+
+def test_upsample_phase_weights_are_exact():
+    """nearest-x2 + conv3x3 == 4 phase-wise 2x2 convolutions over the low-res input (fd_conv_tc.cu)."""
+    import torch.nn.functional as F
+    from founddiff_b200.ops import pack_upsample_phases
+    g = torch.Generator().manual_seed(0)
+    cin, cout, H, W = 5, 7, 6, 9
+    x = torch.randn(2, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    w4 = pack_upsample_phases(w.permute(0, 2, 3, 1).contiguous(), cout, cin)       # (4, Cout, 2, 2, Cin)
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for a in (0, 1):
+        for b in (0, 1):
+            k = w4[2 * a + b].permute(0, 3, 1, 2)                                   # (Cout, Cin, 2, 2)
+            y = F.conv2d(xp[:, :, a:a + H + 1, b:b + W + 1], k)                     # rows {i-1+a, i+a}, cols likewise
+            out[:, :, a::2, b::2] = y
+    assert torch.allclose(out, ref, atol=1e-5)
+
+
+def test_shard_ranges_cover_batch():
+    from founddiff_b200.distributed import shard_range
+    for n in (1, 7, 16, 128):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from founddiff_b200 import distributed as fdist
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank, ws = fdist.world()
+n = 5                                   # ragged: shards of 3 and 2
+full = torch.arange(n * 6, dtype=torch.float32).reshape(n, 1, 2, 3)
+mine = fdist.shard(full)
+assert mine.shape[0] == (3 if rank == 0 else 2)
+init, steps = fdist.global_noise(n, (1, 2, 3), seed=4321, steps=2)
+init2, _ = fdist.global_noise(n, (1, 2, 3), seed=4321, steps=2)
+assert torch.equal(init, init2) and steps.shape == (2, n, 1, 2, 3)
+out = fdist.gather_slices(mine * 2, n)
+assert torch.equal(out, full * 2), out
+even = fdist.gather_slices(torch.full((2, 1, 2, 3), float(rank)))
+assert even.shape[0] == 4 and even[:2].eq(0).all() and even[2:].eq(1).all()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_two_rank_gloo_shard_and_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 1000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
