@@ -16,7 +16,7 @@ FD_F32, FD_BF16, FD_F16 = 0, 1, 2
 EXPORTS = [
     "fd_version", "fd_selective_scan_fwd", "fd_conv2d_simt", "fd_conv2d_tc_supported", "fd_conv2d_tc_plan_create",
     "fd_conv2d_tc_run", "fd_conv2d_tc_plan_destroy", "fd_init_conv7x7", "fd_ln_modulate", "fd_dwconv3x3_silu_scan",
-    "fd_xdt_proj", "fd_xdt_proj_tc", "fd_merge_ln_gate", "fd_dwconv3x3_qkv_gram", "fd_attn_weff", "fd_gn_stats", "fd_gn_silu_add",
+    "fd_xdt_proj", "fd_xdt_proj_tc", "fd_merge_ln_gate", "fd_dwconv3x3_qkv_gram", "fd_dwconv3x3_nhwc", "fd_gram_qk", "fd_attn_weff", "fd_gn_stats", "fd_gn_silu_add",
     "fd_linear_small", "fd_time_sinusoid", "fd_sampler_init", "fd_final_conv_update", "fd_unnormalize",
 ]
 
@@ -26,7 +26,7 @@ class ConvParams(Structure):
     _fields_ = [
         ("src0", c_void_p), ("src1", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("gate", c_void_p),
         ("addend", c_void_p), ("out", c_void_p), ("gn_sums", c_void_p), ("weight_up4", c_void_p),
-        ("c0", c_int), ("c1", c_int), ("B", c_int), ("Hin", c_int), ("Win", c_int), ("Cout", c_int),
+        ("c0", c_int), ("c1", c_int), ("ld0", c_int), ("B", c_int), ("Hin", c_int), ("Win", c_int), ("Cout", c_int),
         ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int), ("upsample", c_int),
         ("silu_from", c_int), ("gate_stride", c_int), ("gn_groups", c_int), ("per_batch_weight", c_int),
         ("dtype", c_int),
@@ -72,6 +72,8 @@ def load():
         "fd_merge_ln_gate": [V, V, I, I, V, V, V, V, V, I, I, I, I, F, I, V],
         "fd_dwconv3x3_qkv_gram": [V] * 5 + [I] * 5 + [V],
         "fd_attn_weff": [V] * 5 + [I] * 3 + [V],
+        "fd_dwconv3x3_nhwc": [V] * 4 + [I] * 6 + [V],
+        "fd_gram_qk": [V, I, V, V, I, I, I, I, V],
         "fd_gn_stats": [V, V, I, I, I, I, I, V],
         "fd_gn_silu_add": [V] * 6 + [I] * 4 + [F, I, V],
         "fd_linear_small": [V] * 5 + [I] * 5 + [V],

@@ -1,6 +1,8 @@
 // TransposedAttention (channel attention, src/DADiff.py:252-285): depthwise 3x3 over qkv fused with the per-head
 // 32x32 Gram matrix q.k^T and the squared norms, then softmax + folding of the attention matrix into the output
 // projection (W_eff = W_proj . blockdiag(attn)), so the attn@v + project_out pair becomes one per-sample 1x1 GEMM.
+#include <type_traits>
+
 #include "fd_common.cuh"
 
 namespace {
@@ -97,38 +99,125 @@ __global__ void __launch_bounds__(256) dwconv_qkv_gram_kernel(const T* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// 16-bit storage types: same fusion, but the Gram matrix and the squared norms run on the tensor cores
-// (mma.sync m16n8k16, fp32 accumulate): G = Q^T K, |q|^2 = diag(Q^T Q), |k|^2 = diag(K^T K) with q, k rounded once
-// to the storage type (cosine similarities stay consistent).  A block walks TPB consecutive 8x32 tiles of one
-// (sample, head) and keeps the accumulators in registers, so global atomics are issued once per block instead of
-// once per tile.
+// 16-bit storage types: two streaming kernels instead of the fused CUDA-core one.
+//
+// (1) dwconv3x3_nhwc_kernel — depthwise 3x3 over a channels-last tensor with a REGISTER sliding window: a thread owns
+//     one (column, 8-channel vector) and walks down the rows; per input row it loads the three horizontally adjacent
+//     vectors (coalesced: an NHWC row is contiguous over (x, c)), feeds the three output rows they contribute to
+//     (72 FMAs against weights held in registers) and emits one finished output vector.  No shared memory, no
+//     barrier; ~115 instructions per output vector instead of ~250 for the tile/halo formulation.
+// (2) gram_mma_kernel — streams q, k (the first 2C channels of the dwconv output) once: 256-pixel tiles staged with
+//     cp.async, G = Q^T K and the diagonals of Q^T Q, K^T K on the tensor cores (mma.sync m16n8k16, fp32 accumulate),
+//     accumulators kept in registers across the block's pixel range, one global atomic per entry per block.
+constexpr int DW_RY = 32;      // output rows per block segment (2 halo rows are recomputed: 6 %)
+
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(256) dwconv3x3_nhwc_kernel(const T* __restrict__ in, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, T* __restrict__ out, int H, int W,
+                                                             int C) {
+    const int NV = C / 8;                               // vectors per pixel
+    const long rowv = (long)W * NV;                     // vectors per image row
+    const long f = (long)blockIdx.x * 256 + threadIdx.x;
+    if (f >= rowv) return;
+    const int cv = (int)(f % NV), x = (int)(f / NV);
+    const int b = blockIdx.z;
+    const int y0 = blockIdx.y * DW_RY, y1 = min(H, y0 + DW_RY);
+    float wr[9][8], bs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        bs[e] = bias ? bias[cv * 8 + e] : 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wr[t][e] = w[(long)(cv * 8 + e) * 9 + t];
+    }
+    const bool has_l = x > 0, has_r = x + 1 < W;
+    const T* base = in + (long)b * H * rowv * 8;
+    T* obase = out + (long)b * H * rowv * 8;
+    float acc[3][8];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[r][e] = bs[e];
+
+    // input row `yi` contributes to output rows yi+1 (tap row 0), yi (1), yi-1 (2); accumulator slot = output row mod 3
+    auto step = [&](int yi, auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;      // == yi mod 3 (compile-time so that acc[] stays in registers)
+        if (yi >= 0 && yi < H) {
+            const T* rp = base + ((long)yi * rowv + f) * 8;
+            float v[3][8];
+            if (has_l) fd_ldv<T, 8>(rp - (long)NV * 8, v[0]);
+            fd_ldv<T, 8>(rp, v[1]);
+            if (has_r) fd_ldv<T, 8>(rp + (long)NV * 8, v[2]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (!has_l) v[0][e] = 0.f;
+                if (!has_r) v[2][e] = 0.f;
+            }
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    acc[(S + 1) % 3][e] = fmaf(v[dx][e], wr[0 * 3 + dx][e], acc[(S + 1) % 3][e]);   // output row yi+1
+                    acc[S][e] = fmaf(v[dx][e], wr[1 * 3 + dx][e], acc[S][e]);                       // output row yi
+                    acc[(S + 2) % 3][e] = fmaf(v[dx][e], wr[2 * 3 + dx][e], acc[(S + 2) % 3][e]);   // output row yi-1
+                }
+        }
+        // output row yi-1 is complete (slot (S+2)%3)
+        const int yo = yi - 1;
+        if (yo >= y0 && yo < y1) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = SILU ? fd_silu(acc[(S + 2) % 3][e]) : acc[(S + 2) % 3][e];
+            fd_stv<T, 8>(obase + ((long)yo * rowv + f) * 8, o);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[(S + 2) % 3][e] = bs[e];
+    };
+    // rows y0-1 .. y1 (inclusive); start aligned to a multiple of 3 so that the slot index is compile-time
+    const int ystart = y0 - 1;
+    const int ybase = ((ystart % 3) + 3) % 3;           // slot of the first row
+    int yi = ystart;
+    // peel until yi mod 3 == 0
+    if (ybase == 1) { step(yi, std::integral_constant<int, 1>{}); ++yi; step(yi, std::integral_constant<int, 2>{}); ++yi; }
+    else if (ybase == 2) { step(yi, std::integral_constant<int, 2>{}); ++yi; }
+    for (; yi <= y1; yi += 3) {
+        step(yi, std::integral_constant<int, 0>{});
+        if (yi + 1 <= y1) step(yi + 1, std::integral_constant<int, 1>{});
+        if (yi + 2 <= y1) step(yi + 2, std::integral_constant<int, 2>{});
+    }
+}
+
 constexpr int QK_LD = 40;      // padded row (elements) of the q / k tiles: conflict-free ldmatrix
-constexpr int TPB = 8;         // tiles per block
+constexpr int GR_TILE = 256;   // pixels per staged tile
+constexpr int GR_PIX = 4096;   // pixels per block
 
 template <typename T>
-__global__ void __launch_bounds__(256) dwconv_qkv_gram_mma_kernel(const T* __restrict__ qkv, const float* __restrict__ w,
-                                                                  T* __restrict__ v_out, float* __restrict__ gram,
-                                                                  float* __restrict__ qk_sq, int H, int W, int C, int ntiles) {
-    constexpr int VEC = 8, NVH = HD / VEC;
-    constexpr int HP = (TPH + 2) * (TPW + 2);
+__global__ void __launch_bounds__(256) gram_mma_kernel(const T* __restrict__ qkv, int ld, float* __restrict__ gram,
+                                                       float* __restrict__ qk_sq, int P, int C) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_in = reinterpret_cast<T*>(smem_raw);                 // [HP][3*HD]
-    T* s_q = s_in + HP * 3 * HD;                              // [256][QK_LD]
-    T* s_k = s_q + TPH * TPW * QK_LD;                         // [256][QK_LD]
-    float* s_w = reinterpret_cast<float*>(s_k + TPH * TPW * QK_LD);   // [9][3*HD]
-    float* s_red = s_w + 9 * 3 * HD;                          // [3][32][32] cross-warp reduction
-
+    T* s_qk = reinterpret_cast<T*>(smem_raw);                      // [2 buffers][2 (q,k)][256][QK_LD]
+    float* s_red = reinterpret_cast<float*>(s_qk + 2 * 2 * GR_TILE * QK_LD);   // [32*32 + 2*32]
     const int head = blockIdx.x, b = blockIdx.z;
-    const int tiles_w = (W + TPW - 1) / TPW;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < 9 * 3 * HD; i += 256) {
-        const int tap = i / (3 * HD), sc = i % (3 * HD);
-        s_w[i] = w[(long)((sc / HD) * C + head * HD + sc % HD) * 9 + tap];
-    }
-    for (int i = tid; i < 3 * HD * HD; i += 256) s_red[i] = 0.f;
+    const long p_begin = (long)blockIdx.y * GR_PIX;
+    const long p_end = min((long)P, p_begin + GR_PIX);
+    const int ntiles = (int)((p_end - p_begin + GR_TILE - 1) / GR_TILE);
+    for (int i = tid; i < HD * HD + 2 * HD; i += 256) s_red[i] = 0.f;
 
-    float acc[2][4][4];        // Q^T K            [m tile][n tile][frag]
-    float accd[2][2][2][4];    // Q^T Q, K^T K diagonal 16x16 blocks  [which][m tile][n sub-tile][frag]
+    auto stage = [&](int tile, int buf) {   // 256 pixels x (q 4 vectors + k 4 vectors), zero-filled past p_end
+        T* dst = s_qk + (size_t)buf * 2 * GR_TILE * QK_LD;
+        for (int i = tid; i < GR_TILE * 8; i += 256) {
+            const int pix = i >> 3, sv = i & 7, sec = sv >> 2, vc = sv & 3;
+            const long p = p_begin + (long)tile * GR_TILE + pix;
+            const bool ok = p < p_end;
+            const T* src = qkv + ((long)b * P + (ok ? p : p_begin)) * ld + sec * C + head * HD + vc * 8;
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + (sec * GR_TILE + pix) * QK_LD + vc * 8);
+            const int sz = ok ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    float acc[2][4][4], accd[2][2][2][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
@@ -142,63 +231,24 @@ __global__ void __launch_bounds__(256) dwconv_qkv_gram_mma_kernel(const T* __res
 #pragma unroll
                 for (int e = 0; e < 4; ++e) accd[a][mt][ns][e] = 0.f;
     }
-
-    const int t_begin = blockIdx.y * TPB, t_end = min(ntiles, t_begin + TPB);
-    for (int tile = t_begin; tile < t_end; ++tile) {
-        const int ty0 = (tile / tiles_w) * TPH, tx0 = (tile % tiles_w) * TPW;
-        __syncthreads();       // previous tile's mma reads of s_q/s_k and conv reads of s_in are done
-        for (int i = tid; i < HP * 3 * NVH; i += 256) {
-            const int pix = i / (3 * NVH), sv = i % (3 * NVH);
-            const int sec = sv / NVH, vc = sv % NVH;
-            const int h = ty0 + pix / (TPW + 2) - 1, ww = tx0 + pix % (TPW + 2) - 1;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (h >= 0 && h < H && ww >= 0 && ww < W)
-                val = *reinterpret_cast<const uint4*>(qkv + (((long)b * H + h) * W + ww) * (3 * C) + sec * C + head * HD + vc * VEC);
-            *reinterpret_cast<uint4*>(s_in + pix * 3 * HD + sec * HD + vc * VEC) = val;
-        }
+    stage(0, 0);
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int buf = tile & 1;
+        if (tile + 1 < ntiles) { stage(tile + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        for (int i = tid; i < TPH * TPW * 3 * NVH; i += 256) {
-            const int pix = i / (3 * NVH), sv = i % (3 * NVH);
-            const int sec = sv / NVH, vc = sv % NVH;
-            const int py = pix / TPW, px = pix % TPW;
-            const bool inside = (ty0 + py < H) && (tx0 + px < W);
-            float a8[VEC];
+        const T* s_q = s_qk + (size_t)buf * 2 * GR_TILE * QK_LD;
+        const T* s_k = s_q + GR_TILE * QK_LD;
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) a8[e] = 0.f;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    float v[VEC];
-                    fd_ldv<T, VEC>(s_in + ((py + dy) * (TPW + 2) + px + dx) * 3 * HD + sec * HD + vc * VEC, v);
-                    const float* wp = s_w + (dy * 3 + dx) * 3 * HD + sec * HD + vc * VEC;
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) a8[e] = fmaf(v[e], wp[e], a8[e]);
-                }
-            if (sec == 2) {
-                if (inside) fd_stv<T, VEC>(v_out + (((long)b * H + ty0 + py) * W + tx0 + px) * C + head * HD + vc * VEC, a8);
-            } else {
-                if (!inside) {
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) a8[e] = 0.f;
-                }
-                fd_stv<T, VEC>((sec == 0 ? s_q : s_k) + pix * QK_LD + vc * VEC, a8);
-            }
-        }
-        __syncthreads();
-        // each warp owns 32 pixels (2 k-steps of 16) of the tile
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
+        for (int ks = 0; ks < 2; ++ks) {                 // each warp owns 32 pixels of the tile
             const int p0 = warp * 32 + ks * 16;
             uint32_t aq[2][4], ak[2][4], bq[2][4], bk[2][4];
-            // A fragments (operand stored [k = pixel][m = channel]) : ldmatrix.trans
             const int ar = p0 + (lane & 7) + 8 * (lane >> 4), ac = 8 * ((lane >> 3) & 1);
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
                 ldmatrix_x4_trans(aq[mt], s_q + ar * QK_LD + mt * 16 + ac);
                 ldmatrix_x4_trans(ak[mt], s_k + ar * QK_LD + mt * 16 + ac);
             }
-            // B fragments (operand stored [k = pixel][n = channel]) : ldmatrix.trans, two n-tiles per x4
             const int br = p0 + (lane & 7) + 8 * ((lane >> 3) & 1), bc = 8 * (lane >> 4);
 #pragma unroll
             for (int np = 0; np < 2; ++np) {
@@ -211,14 +261,14 @@ __global__ void __launch_bounds__(256) dwconv_qkv_gram_mma_kernel(const T* __res
                 for (int nt = 0; nt < 4; ++nt)
                     mma_16816<T>(acc[mt][nt], aq[mt], bk[nt >> 1][(nt & 1) * 2], bk[nt >> 1][(nt & 1) * 2 + 1]);
 #pragma unroll
-                for (int ns = 0; ns < 2; ++ns) {   // the norms only need the diagonal 16x16 blocks
+                for (int ns = 0; ns < 2; ++ns) {         // the norms only need the diagonal 16x16 blocks
                     mma_16816<T>(accd[0][mt][ns], aq[mt], bq[mt][ns * 2], bq[mt][ns * 2 + 1]);
                     mma_16816<T>(accd[1][mt][ns], ak[mt], bk[mt][ns * 2], bk[mt][ns * 2 + 1]);
                 }
             }
         }
+        __syncthreads();                                 // buffer `buf` may be refilled by the next-but-one stage
     }
-    // cross-warp reduction in shared memory, then one global atomic per entry
     {
         const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll
@@ -235,7 +285,7 @@ __global__ void __launch_bounds__(256) dwconv_qkv_gram_mma_kernel(const T* __res
             for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int ns = 0; ns < 2; ++ns) {
-                    float* r = s_red + (1 + a) * HD * HD;
+                    float* r = s_red + HD * HD + a * HD;
                     const int row = mt * 16 + g, col = mt * 16 + ns * 8 + 2 * t4;
                     if (row == col) atomicAdd(&r[row], accd[a][mt][ns][0]);
                     if (row == col + 1) atomicAdd(&r[row], accd[a][mt][ns][1]);
@@ -247,10 +297,7 @@ __global__ void __launch_bounds__(256) dwconv_qkv_gram_mma_kernel(const T* __res
     __syncthreads();
     float* gg = gram + ((long)b * (C / HD) + head) * HD * HD;
     for (int i = tid; i < HD * HD; i += 256) atomicAdd(gg + i, s_red[i]);
-    if (tid < 2 * HD) {
-        const int which = tid / HD, c = tid % HD;
-        atomicAdd(qk_sq + ((long)b * 2 + which) * C + head * HD + c, s_red[(1 + which) * HD * HD + c]);
-    }
+    if (tid < 2 * HD) atomicAdd(qk_sq + ((long)b * 2 + tid / HD) * C + head * HD + tid % HD, s_red[HD * HD + tid]);
 }
 
 // grid: (heads, B); block 256.  attn in shared memory, then weff rows.
@@ -311,30 +358,51 @@ extern "C" int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, f
         FD_LAUNCH_CHECK();
         return 0;
     }
-    dim3 grid(C / HD, fd_cdiv(ntiles, TPB), B);
-    const size_t smem = ((size_t)(TPH + 2) * (TPW + 2) * 3 * HD + 2 * (size_t)TPH * TPW * QK_LD) * 2 +
-                        (size_t)(9 * 3 * HD + 3 * HD * HD) * sizeof(float);
-    if (dtype == FD_BF16) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(dwconv_qkv_gram_mma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            attr_set = true;
-        }
-        dwconv_qkv_gram_mma_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>((const __nv_bfloat16*)qkv, w, (__nv_bfloat16*)v, gram, qk_sq, H, W, C, ntiles);
-    } else if (dtype == FD_F16) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(dwconv_qkv_gram_mma_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            attr_set = true;
-        }
-        dwconv_qkv_gram_mma_kernel<__half><<<grid, 256, smem, stream>>>((const __half*)qkv, w, (__half*)v, gram, qk_sq, H, W, C, ntiles);
-    } else {
-        return FD_ERR_BAD_ARGUMENT;
-    }
+    return FD_ERR_UNSUPPORTED;   // 16-bit types: use fd_dwconv3x3_nhwc + fd_gram_qk
+}
+
+template <typename T>
+static int dwconv_nhwc_launch(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int C, int silu,
+                              cudaStream_t stream) {
+    const long rowv = (long)W * (C / 8);
+    dim3 grid((unsigned)fd_cdiv(rowv, 256), (unsigned)fd_cdiv(H, DW_RY), (unsigned)B);
+    if (silu) dwconv3x3_nhwc_kernel<T, true><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
+    else dwconv3x3_nhwc_kernel<T, false><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
     FD_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int fd_dwconv3x3_nhwc(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int C,
+                                 int silu, int dtype, cudaStream_t stream) {
+    if (!in || !w || !out || in == out || B <= 0 || H <= 0 || W <= 0 || C <= 0) return FD_ERR_BAD_ARGUMENT;
+    if (C % 8) return FD_ERR_UNSUPPORTED;
+    if (dtype == FD_BF16) return dwconv_nhwc_launch<__nv_bfloat16>(in, w, bias, out, B, H, W, C, silu, stream);
+    if (dtype == FD_F16) return dwconv_nhwc_launch<__half>(in, w, bias, out, B, H, W, C, silu, stream);
+    return FD_ERR_UNSUPPORTED;
+}
+
+template <typename T>
+static int gram_launch(const void* qkv, int ld, float* gram, float* qk_sq, int B, int P, int C, cudaStream_t stream) {
+    const size_t smem = (size_t)2 * 2 * GR_TILE * QK_LD * sizeof(T) + (size_t)(HD * HD + 2 * HD) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gram_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(C / HD), (unsigned)fd_cdiv(P, GR_PIX), (unsigned)B);
+    gram_mma_kernel<T><<<grid, 256, smem, stream>>>((const T*)qkv, ld, gram, qk_sq, P, C);
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fd_gram_qk(const void* qkv, int ld, float* gram, float* qk_sq, int B, int P, int C, int dtype,
+                          cudaStream_t stream) {
+    if (!qkv || !gram || !qk_sq || B <= 0 || P <= 0 || C <= 0 || ld < 2 * C) return FD_ERR_BAD_ARGUMENT;
+    if (C % HD || ld % 8) return FD_ERR_UNSUPPORTED;
+    if (dtype == FD_BF16) return gram_launch<__nv_bfloat16>(qkv, ld, gram, qk_sq, B, P, C, stream);
+    if (dtype == FD_F16) return gram_launch<__half>(qkv, ld, gram, qk_sq, B, P, C, stream);
+    return FD_ERR_UNSUPPORTED;
 }
 
 extern "C" int fd_attn_weff(const float* gram, const float* qk_sq, const float* temperature, const float* proj_w, void* weff,

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(fd_conv_params p, int Ho
     const int m0 = (blockIdx.x % tiles_per_sample) * TM;
     const int n0 = blockIdx.y * TN;
     const int Cin = p.c0 + p.c1;
+    const int ld0 = p.ld0 > 0 ? p.ld0 : p.c0;
     const int K = p.KH * p.KW * Cin;
     const int P = Hout * Wout;
     const int Hin = p.Hin, Win = p.Win;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(fd_conv_params p, int Ho
                     if (hi >= 0 && hi < Hv && wi >= 0 && wi < Wv) {
                         if (p.upsample) { hi >>= 1; wi >>= 1; }
                         const long pix = ((long)b * Hin + hi) * Win + wi;
-                        av = ci < p.c0 ? fd_ld(src0 + pix * p.c0 + ci) : fd_ld(src1 + pix * p.c1 + (ci - p.c0));
+                        av = ci < p.c0 ? fd_ld(src0 + pix * ld0 + ci) : fd_ld(src1 + pix * p.c1 + (ci - p.c0));
                     }
                 }
                 if (brow_ok) bv = fd_ld(wgt + (long)bn * K + k);
@@ -137,6 +138,7 @@ extern "C" int fd_conv_check_params(const fd_conv_params* p) {
     if (p->B <= 0 || p->Hin <= 0 || p->Win <= 0 || p->Cout <= 0 || p->KH <= 0 || p->KW <= 0 || p->stride <= 0 || p->pad < 0)
         return FD_ERR_BAD_ARGUMENT;
     if (p->gate && p->gate_stride < p->Cout) return FD_ERR_BAD_ARGUMENT;
+    if (p->ld0 != 0 && p->ld0 < p->c0) return FD_ERR_BAD_ARGUMENT;
     if (p->gn_sums) {
         if (p->gn_groups <= 0 || p->Cout % p->gn_groups) return FD_ERR_BAD_ARGUMENT;
         const int cpg = p->Cout / p->gn_groups;

@@ -381,9 +381,9 @@ int encode(CUtensorMap* map, int dtype, int rank, const void* base, const cuuint
     return r == CUDA_SUCCESS ? 0 : FD_ERR_DRIVER;
 }
 
-int act_map(CUtensorMap* map, const void* base, int dtype, int B, int H, int W, int C, int estride) {
+int act_map(CUtensorMap* map, const void* base, int dtype, int B, int H, int W, int C, int ld, int estride) {
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
     const cuuint32_t box[4] = {BK, (cuuint32_t)(TILE_W * estride), (cuuint32_t)(TILE_H * estride), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     return encode(map, dtype, 4, base, dims, strides, box, estr);
@@ -412,7 +412,7 @@ extern "C" int fd_conv_check_params(const fd_conv_params* p);
 extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
     if (fd_conv_check_params(p)) return 0;
     if (p->dtype != FD_BF16 && p->dtype != FD_F16) return 0;
-    if (p->c0 % BK || p->c1 % BK) return 0;
+    if (p->c0 % BK || p->c1 % BK || p->ld0 % 8) return 0;
     if (p->Cout % 64) return 0;
     int Hout, Wout;
     if (conv_dims(p, &Hout, &Wout)) return 0;
@@ -455,8 +455,9 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     const int gh = q.Hout / (p->upsample ? 2 : 1), gw = q.Wout / (p->upsample ? 2 : 1);
     q.tiles_h = gh / TILE_H;
     q.tiles_w = gw / TILE_W;
-    int rc = act_map(&plan->map_a0, p->src0, p->dtype, p->B, p->Hin, p->Win, p->c0, p->upsample ? 1 : p->stride);
-    if (!rc && p->c1) rc = act_map(&plan->map_a1, p->src1, p->dtype, p->B, p->Hin, p->Win, p->c1, p->upsample ? 1 : p->stride);
+    int rc = act_map(&plan->map_a0, p->src0, p->dtype, p->B, p->Hin, p->Win, p->c0, p->ld0 > 0 ? p->ld0 : p->c0,
+                     p->upsample ? 1 : p->stride);
+    if (!rc && p->c1) rc = act_map(&plan->map_a1, p->src1, p->dtype, p->B, p->Hin, p->Win, p->c1, p->c1, p->upsample ? 1 : p->stride);
     if (!rc && !p->c1) plan->map_a1 = plan->map_a0;
     if (!rc) {
         const long Kp = (long)q.taps_h * q.taps_w * Cin;

@@ -135,7 +135,7 @@ class UnetEngine:
         for l, ((h, w), C) in enumerate(zip(sizes, cmax)):
             P = h * w
             for name, ch in (("TA", C), ("TB", C), ("A", C), ("XZ", 4 * C), ("XS", 2 * C), ("DTS", 2 * C), ("YS", 2 * C),
-                             ("G", 2 * C), ("QKV", 3 * C), ("V", C), ("Y", C), ("SK", C)):
+                             ("G", 2 * C), ("QKV", 3 * C), ("QKV2", 3 * C), ("V", C), ("Y", C), ("SK", C)):
                 self.buf(f"{name}{l}", B, P, ch)
             self.buf(f"H{l}", B, P, cfg.in_out[l][0])
             self.buf(f"WEFF{l}", B, C, C)
@@ -282,8 +282,15 @@ class UnetEngine:
         c_in = ops.Conv(a, in_w, xz, B=B, Hin=h, Win=w, silu_from=2 * C, prefer_tc=tc)
         c_out = ops.Conv(g, out_w, x, B=B, Hin=h, Win=w, gate=g1, gate_stride=MS, addend=x_in, prefer_tc=tc)
         c_qkv = ops.Conv(a, qkv_w, qkv, B=B, Hin=h, Win=w, prefer_tc=tc)
-        c_att = ops.Conv(v, weff, x, B=B, Hin=h, Win=w, gate=g2, gate_stride=MS, addend=x, per_batch_weight=True,
-                         prefer_tc=tc)
+        split_attn = dt != torch.float32            # 16-bit modes: streaming dwconv + tensor-core Gram, v read in place
+        if split_attn:
+            qkv2 = self.buf(f"QKV2{l}", B, P, 3 * C)
+            v_view = qkv2[:, :, 2 * C:]
+            c_att = ops.Conv(v_view, weff, x, B=B, Hin=h, Win=w, gate=g2, gate_stride=MS, addend=x, per_batch_weight=True,
+                             prefer_tc=tc, c0=C, ld0=3 * C)
+        else:
+            c_att = ops.Conv(v, weff, x, B=B, Hin=h, Win=w, gate=g2, gate_stride=MS, addend=x, per_batch_weight=True,
+                             prefer_tc=tc)
         local_c = _LocalView(self.locals, lo, D)
         self._local_views.append(local_c)
 
@@ -306,7 +313,11 @@ class UnetEngine:
             c_out.run()
             ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
             c_qkv.run()
-            ops.dwconv3x3_qkv_gram(qkv, qdw_w, v, holder["gram"], holder["qk"], B, h, w, C)
+            if split_attn:
+                ops.dwconv3x3_nhwc(qkv, qdw_w, None, qkv2, B, h, w, 3 * C)
+                ops.gram_qk(qkv2, 3 * C, holder["gram"], holder["qk"], B, P, C)
+            else:
+                ops.dwconv3x3_qkv_gram(qkv, qdw_w, v, holder["gram"], holder["qk"], B, h, w, C)
             ops.attn_weff(holder["gram"], holder["qk"], temp, proj_w, weff, B, C)
             c_att.run()
         self.steps.append(run)

@@ -122,15 +122,19 @@ class Conv:
 
     def __init__(self, src0, weight, out, *, B, Hin, Win, KH=1, KW=1, stride=1, pad=0, upsample=False, src1=None,
                  bias=None, gate=None, gate_stride=0, addend=None, silu_from=None, gn_sums=None, gn_groups=0,
-                 per_batch_weight=False, prefer_tc=True):
+                 per_batch_weight=False, prefer_tc=True, c0=None, ld0=0):
+        """`c0` / `ld0`: read only the first c0 channels of rows of pitch ld0 starting at src0's data pointer (src0 may
+        be a strided channel-slice view)."""
         lib = _lib.load()
-        c0 = src0.shape[-1]
+        c0 = src0.shape[-1] if c0 is None else c0
         c1 = src1.shape[-1] if src1 is not None else 0
         cout = out.shape[-1]
         p = ConvParams()
-        p.src0, p.src1, p.weight, p.out = _p(src0), _p(src1), _p(weight), _p(out)
+        p.src0 = c_void_p(src0.data_ptr()) if ld0 else _p(src0)
+        p.src1, p.weight, p.out = _p(src1), _p(weight), _p(out)
         p.bias, p.gate, p.addend, p.gn_sums = _f32(bias), _f32(gate), _p(addend), _f32(gn_sums)
         p.c0, p.c1, p.B, p.Hin, p.Win, p.Cout = c0, c1, B, Hin, Win, cout
+        p.ld0 = ld0
         p.KH, p.KW, p.stride, p.pad, p.upsample = KH, KW, stride, pad, int(upsample)
         self._w4 = None
         if upsample and prefer_tc and out.dtype != torch.float32:
@@ -233,6 +237,18 @@ def dwconv3x3_qkv_gram(qkv, w, v, gram, qk_sq, B, H, W, C):
     with _launched("dwconv_qkv_gram", f"{B}x{H}x{W}x{C}", 1):
         check(_lib.load().fd_dwconv3x3_qkv_gram(_p(qkv), _f32(w), _p(v), _f32(gram), _f32(qk_sq), B, H, W, C,
                                                 dtype_code(qkv.dtype), _stream()), "fd_dwconv3x3_qkv_gram")
+
+
+def dwconv3x3_nhwc(x, w, bias, out, B, H, W, C, silu=False):
+    with _launched("dwconv3x3_nhwc", f"{B}x{H}x{W}x{C}", 1):
+        check(_lib.load().fd_dwconv3x3_nhwc(_p(x), _f32(w), _f32(bias), _p(out), B, H, W, C, int(silu), dtype_code(x.dtype),
+                                            _stream()), "fd_dwconv3x3_nhwc")
+
+
+def gram_qk(qkv, ld, gram, qk_sq, B, P, C):
+    with _launched("gram_qk", f"{B}x{P}x{C}", 1):
+        check(_lib.load().fd_gram_qk(_p(qkv), ld, _f32(gram), _f32(qk_sq), B, P, C, dtype_code(qkv.dtype), _stream()),
+              "fd_gram_qk")
 
 
 def attn_weff(gram, qk_sq, temperature, proj_w, weff, B, C):

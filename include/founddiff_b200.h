@@ -74,6 +74,7 @@ typedef struct {
     float* gn_sums;
     const void* weight_up4; /* upsample only (tcgen05 path): (4, Cout, 2, 2, c0) phase-summed weights, see fd_conv_tc.cu */
     int c0, c1;
+    int ld0;              /* row pitch (elements) of src0; 0 = dense (c0).  Lets a GEMM read a channel slice of a wider tensor */
     int B, Hin, Win, Cout;
     int KH, KW, stride, pad, upsample;
     int silu_from;        /* >= Cout: no activation */
@@ -146,6 +147,14 @@ int fd_merge_ln_gate(const void* ys, const void* xz, int ld, int z_off, const fl
  * --------------------------------------------------------------------------------------------------------- */
 int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, float* gram, float* qk_sq, int B, int H,
                           int W, int C, int dtype, cudaStream_t stream);
+/* 16-bit storage types (bf16 / fp16) split the first step into two streaming kernels:
+ *   fd_dwconv3x3_nhwc: depthwise 3x3 (+bias, +SiLU) over a channels-last (B,H,W,C) tensor, register sliding window;
+ *   fd_gram_qk:        gram / qk_sq (same meaning as above, ACCUMULATED) from q = columns [0,C), k = columns [C,2C) of
+ *                      rows of pitch `ld` — q.k^T and the norms run on the tensor cores (mma.sync, fp32 accumulate).
+ * v is then read in place (columns [2C,3C), ld0 = 3C) by the per-sample W_eff GEMM. */
+int fd_dwconv3x3_nhwc(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int C, int silu,
+                      int dtype, cudaStream_t stream);
+int fd_gram_qk(const void* qkv, int ld, float* gram, float* qk_sq, int B, int P, int C, int dtype, cudaStream_t stream);
 int fd_attn_weff(const float* gram, const float* qk_sq, const float* temperature, const float* proj_w,
                  void* weff, int B, int C, int dtype, cudaStream_t stream);
 

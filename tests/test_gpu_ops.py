@@ -263,7 +263,7 @@ def test_xdt_proj(ops, cfg, dt):
 
 
 @pytest.mark.parametrize("C", [64, 128])
-@pytest.mark.parametrize("hw", [(16, 24), (8, 40)])
+@pytest.mark.parametrize("hw", [(16, 24), (8, 40), (16, 32), (72, 64)])
 @pytest.mark.parametrize("dt", DTYPES)
 def test_transposed_attention(ops, C, hw, dt):
     """dwconv+Gram, softmax/W_eff fold and the per-sample 1x1 GEMM together == TransposedAttention after the qkv
@@ -281,11 +281,20 @@ def test_transposed_attention(ops, C, hw, dt):
     kn = F.normalize(kk.reshape(B, heads, 32, H * W), dim=-1)
     attn = ((qn @ kn.transpose(-2, -1)) * temp).softmax(dim=-1)
     ref = F.conv2d((attn @ vv.reshape(B, heads, 32, H * W)).reshape(B, C, H, W), wproj)
-    v = torch.empty(B, H * W, C, device="cuda", dtype=dt)
     gram = torch.zeros(B, heads, 32, 32, device="cuda")
     qk = torch.zeros(B, 2, C, device="cuda")
-    ops.dwconv3x3_qkv_gram(nhwc(qkv, dt), wdw.reshape(3 * C, 9).cuda(), v, gram, qk, B, H, W, C)
-    assert rel(nchw(v, H, W), vv) < TOL[dt]
+    if dt == torch.float32:
+        v = torch.empty(B, H * W, C, device="cuda", dtype=dt)
+        ops.dwconv3x3_qkv_gram(nhwc(qkv, dt), wdw.reshape(3 * C, 9).cuda(), v, gram, qk, B, H, W, C)
+        v_src, kw = v, {}
+    else:       # streaming dwconv (register sliding window) + tensor-core Gram; v is read in place by the GEMM
+        qkv2 = torch.empty(B, H * W, 3 * C, device="cuda", dtype=dt)
+        ops.dwconv3x3_nhwc(nhwc(qkv, dt), wdw.reshape(3 * C, 9).cuda(), None, qkv2, B, H, W, 3 * C)
+        assert rel(nchw(qkv2, H, W), t) < TOL[dt]
+        ops.gram_qk(qkv2, 3 * C, gram, qk, B, H * W, C)
+        v = qkv2[:, :, 2 * C:]
+        v_src, kw = v, dict(c0=C, ld0=3 * C)
+    assert rel(nchw(v.contiguous(), H, W), vv) < TOL[dt]
     # 16-bit modes form the Gram matrix on the tensor cores from q, k rounded once to the storage type
     gtol = {torch.float32: 1e-4, torch.bfloat16: 1e-2, torch.float16: 2e-3}[dt]
     assert rel(gram, qq.reshape(B, heads, 32, -1) @ kk.reshape(B, heads, 32, -1).transpose(-2, -1)) < gtol
@@ -293,8 +302,28 @@ def test_transposed_attention(ops, C, hw, dt):
     weff = torch.empty(B, C, C, device="cuda", dtype=dt)
     ops.attn_weff(gram, qk, temp.reshape(-1).cuda(), wproj.reshape(C, C).cuda(), weff, B, C)
     out = torch.empty(B, H * W, C, device="cuda", dtype=dt)
-    ops.Conv(v, weff, out, B=B, Hin=H, Win=W, per_batch_weight=True, prefer_tc=False).run()
+    ops.Conv(v_src, weff, out, B=B, Hin=H, Win=W, per_batch_weight=True, prefer_tc=False, **kw).run()
     assert rel(nchw(out, H, W), ref) < 2 * TOL[dt]
+    if dt != torch.float32 and H % 8 == 0 and W % 16 == 0:
+        out2 = torch.empty_like(out)
+        c = ops.Conv(v_src, weff, out2, B=B, Hin=H, Win=W, per_batch_weight=True, prefer_tc=True, **kw)
+        assert c.uses_tc
+        c.run()
+        assert rel(out2, out) < 3e-3
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 40, 24, 64, True), (1, 33, 17, 24, False), (2, 64, 64, 192, False)])
+def test_dwconv3x3_nhwc(ops, dt, shape):
+    B, H, W, C, silu = shape
+    g = torch.Generator().manual_seed(H * W + C)
+    x = q(torch.randn(B, C, H, W, generator=g), dt)
+    w, b = torch.randn(C, 1, 3, 3, generator=g) / 3, torch.randn(C, generator=g)
+    ref = F.conv2d(x, w, b if silu else None, padding=1, groups=C)
+    ref = F.silu(ref) if silu else ref
+    out = torch.empty(B, H * W, C, device="cuda", dtype=dt)
+    ops.dwconv3x3_nhwc(nhwc(x, dt), w.reshape(C, 9).cuda(), b.cuda() if silu else None, out, B, H, W, C, silu=silu)
+    assert rel(nchw(out, H, W), ref) < TOL[dt]
 
 
 def test_small_linear_and_time_embedding(ops):
