@@ -80,12 +80,20 @@ def main():
         for C, H, _N in sel(LEVELS):
             qkv = rn(B, H * H, 3 * C)
             w = rn(3 * C, 9, d=torch.float32)
-            v = torch.empty(B, H * H, C, device="cuda", dtype=dt)
             gram = torch.zeros(B, C // 32, 32, 32, device="cuda")
             qk = torch.zeros(B, 2, C, device="cuda")
-            ms = timeit(lambda: ops.dwconv3x3_qkv_gram(qkv, w, v, gram, qk, B, H, H, C), args.iters)
-            report("dwconv_qkv_gram", f"{B}x{H}x{H}x{C}", ms, 4.0 * B * H * H * C * es, (54.0 + 64.0) * B * H * H * C)
-            del qkv, v
+            if dt == torch.float32:
+                v = torch.empty(B, H * H, C, device="cuda", dtype=dt)
+                ms = timeit(lambda: ops.dwconv3x3_qkv_gram(qkv, w, v, gram, qk, B, H, H, C), args.iters)
+                report("dwconv_qkv_gram", f"{B}x{H}x{H}x{C}", ms, 4.0 * B * H * H * C * es, (54.0 + 64.0) * B * H * H * C)
+            else:
+                qkv2 = torch.empty_like(qkv)
+                ms = timeit(lambda: ops.dwconv3x3_nhwc(qkv, w, None, qkv2, B, H, H, 3 * C), args.iters)
+                report("dwconv3x3_nhwc", f"{B}x{H}x{H}x{3 * C}", ms, 6.0 * B * H * H * C * es, 54.0 * B * H * H * C)
+                ms = timeit(lambda: ops.gram_qk(qkv2, 3 * C, gram, qk, B, H * H, C), args.iters)
+                report("gram_qk", f"{B}x{H * H}x{C}", ms, 2.0 * B * H * H * C * es, 64.0 * 3 * B * H * H * C)
+                del qkv2
+            del qkv
     if args.only in ("", "xdt"):
         for C, H, N in sel(LEVELS):
             D, L, R = 2 * C, H * H // 4, math.ceil(C / 16)

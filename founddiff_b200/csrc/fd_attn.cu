@@ -110,73 +110,98 @@ __global__ void __launch_bounds__(256) dwconv_qkv_gram_kernel(const T* __restric
 //     cp.async, G = Q^T K and the diagonals of Q^T Q, K^T K on the tensor cores (mma.sync m16n8k16, fp32 accumulate),
 //     accumulators kept in registers across the block's pixel range, one global atomic per entry per block.
 constexpr int DW_RY = 32;      // output rows per block segment (2 halo rows are recomputed: 6 %)
+constexpr int DW_V = 4;        // channels per thread (8-byte accesses; keeps the register window at ~80 registers)
+
+template <typename T> FD_DEVINL uint2 dw_ld_raw(const T* p) { return *reinterpret_cast<const uint2*>(p); }
+template <typename T> FD_DEVINL void dw_cvt(uint2 r, float (&v)[4]) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+        const float2 a = __half22float2(*reinterpret_cast<__half2*>(&r.x));
+        const float2 b = __half22float2(*reinterpret_cast<__half2*>(&r.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+}
+template <typename T> FD_DEVINL void dw_st(T* p, const float (&v)[4]) {
+    uint2 r;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+    } else {
+        __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+        r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint2*>(p) = r;
+}
 
 template <typename T, bool SILU>
-__global__ void __launch_bounds__(256) dwconv3x3_nhwc_kernel(const T* __restrict__ in, const float* __restrict__ w,
-                                                             const float* __restrict__ bias, T* __restrict__ out, int H, int W,
-                                                             int C) {
-    const int NV = C / 8;                               // vectors per pixel
+__global__ void __launch_bounds__(256, 3) dwconv3x3_nhwc_kernel(const T* __restrict__ in, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, T* __restrict__ out, int H,
+                                                                int W, int C) {
+    const int NV = C / DW_V;                            // vectors per pixel
     const long rowv = (long)W * NV;                     // vectors per image row
     const long f = (long)blockIdx.x * 256 + threadIdx.x;
     if (f >= rowv) return;
     const int cv = (int)(f % NV), x = (int)(f / NV);
     const int b = blockIdx.z;
     const int y0 = blockIdx.y * DW_RY, y1 = min(H, y0 + DW_RY);
-    float wr[9][8], bs[8];
+    float wr[9][DW_V], bs[DW_V];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        bs[e] = bias ? bias[cv * 8 + e] : 0.f;
+    for (int e = 0; e < DW_V; ++e) {
+        bs[e] = bias ? bias[cv * DW_V + e] : 0.f;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) wr[t][e] = w[(long)(cv * 8 + e) * 9 + t];
+        for (int t = 0; t < 9; ++t) wr[t][e] = w[(long)(cv * DW_V + e) * 9 + t];
     }
     const bool has_l = x > 0, has_r = x + 1 < W;
-    const T* base = in + (long)b * H * rowv * 8;
-    T* obase = out + (long)b * H * rowv * 8;
-    float acc[3][8];
+    const T* base = in + (long)b * H * rowv * DW_V;
+    T* obase = out + (long)b * H * rowv * DW_V;
+    float acc[3][DW_V];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[r][e] = bs[e];
+        for (int e = 0; e < DW_V; ++e) acc[r][e] = bs[e];
 
+    uint2 nxt[3];                                        // raw vectors of the NEXT input row (software pipelining)
+    auto fetch = [&](int yi) {
+        nxt[0] = nxt[1] = nxt[2] = make_uint2(0u, 0u);
+        if (yi >= 0 && yi < H) {
+            const T* rp = base + ((long)yi * rowv + f) * DW_V;
+            if (has_l) nxt[0] = dw_ld_raw<T>(rp - (long)NV * DW_V);
+            nxt[1] = dw_ld_raw<T>(rp);
+            if (has_r) nxt[2] = dw_ld_raw<T>(rp + (long)NV * DW_V);
+        }
+    };
     // input row `yi` contributes to output rows yi+1 (tap row 0), yi (1), yi-1 (2); accumulator slot = output row mod 3
     auto step = [&](int yi, auto slot_c) {
         constexpr int S = decltype(slot_c)::value;      // == yi mod 3 (compile-time so that acc[] stays in registers)
-        if (yi >= 0 && yi < H) {
-            const T* rp = base + ((long)yi * rowv + f) * 8;
-            float v[3][8];
-            if (has_l) fd_ldv<T, 8>(rp - (long)NV * 8, v[0]);
-            fd_ldv<T, 8>(rp, v[1]);
-            if (has_r) fd_ldv<T, 8>(rp + (long)NV * 8, v[2]);
+        float v[3][DW_V];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                if (!has_l) v[0][e] = 0.f;
-                if (!has_r) v[2][e] = 0.f;
+        for (int dx = 0; dx < 3; ++dx) dw_cvt<T>(nxt[dx], v[dx]);
+        fetch(yi + 1);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int e = 0; e < DW_V; ++e) {
+                acc[(S + 1) % 3][e] = fmaf(v[dx][e], wr[0 * 3 + dx][e], acc[(S + 1) % 3][e]);   // output row yi+1
+                acc[S][e] = fmaf(v[dx][e], wr[1 * 3 + dx][e], acc[S][e]);                       // output row yi
+                acc[(S + 2) % 3][e] = fmaf(v[dx][e], wr[2 * 3 + dx][e], acc[(S + 2) % 3][e]);   // output row yi-1
             }
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    acc[(S + 1) % 3][e] = fmaf(v[dx][e], wr[0 * 3 + dx][e], acc[(S + 1) % 3][e]);   // output row yi+1
-                    acc[S][e] = fmaf(v[dx][e], wr[1 * 3 + dx][e], acc[S][e]);                       // output row yi
-                    acc[(S + 2) % 3][e] = fmaf(v[dx][e], wr[2 * 3 + dx][e], acc[(S + 2) % 3][e]);   // output row yi-1
-                }
-        }
-        // output row yi-1 is complete (slot (S+2)%3)
-        const int yo = yi - 1;
+        const int yo = yi - 1;                          // output row yi-1 is complete (slot (S+2)%3)
         if (yo >= y0 && yo < y1) {
-            float o[8];
+            float o[DW_V];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = SILU ? fd_silu(acc[(S + 2) % 3][e]) : acc[(S + 2) % 3][e];
-            fd_stv<T, 8>(obase + ((long)yo * rowv + f) * 8, o);
+            for (int e = 0; e < DW_V; ++e) o[e] = SILU ? fd_silu(acc[(S + 2) % 3][e]) : acc[(S + 2) % 3][e];
+            dw_st<T>(obase + ((long)yo * rowv + f) * DW_V, o);
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[(S + 2) % 3][e] = bs[e];
+        for (int e = 0; e < DW_V; ++e) acc[(S + 2) % 3][e] = bs[e];
     };
-    // rows y0-1 .. y1 (inclusive); start aligned to a multiple of 3 so that the slot index is compile-time
-    const int ystart = y0 - 1;
-    const int ybase = ((ystart % 3) + 3) % 3;           // slot of the first row
-    int yi = ystart;
-    // peel until yi mod 3 == 0
+    // rows y0-1 .. y1 (inclusive); peel so that the slot index (row mod 3) is a compile-time constant
+    int yi = y0 - 1;
+    fetch(yi);
+    const int ybase = ((yi % 3) + 3) % 3;
     if (ybase == 1) { step(yi, std::integral_constant<int, 1>{}); ++yi; step(yi, std::integral_constant<int, 2>{}); ++yi; }
     else if (ybase == 2) { step(yi, std::integral_constant<int, 2>{}); ++yi; }
     for (; yi <= y1; yi += 3) {
@@ -364,7 +389,7 @@ extern "C" int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, f
 template <typename T>
 static int dwconv_nhwc_launch(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int C, int silu,
                               cudaStream_t stream) {
-    const long rowv = (long)W * (C / 8);
+    const long rowv = (long)W * (C / DW_V);
     dim3 grid((unsigned)fd_cdiv(rowv, 256), (unsigned)fd_cdiv(H, DW_RY), (unsigned)B);
     if (silu) dwconv3x3_nhwc_kernel<T, true><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
     else dwconv3x3_nhwc_kernel<T, false><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
