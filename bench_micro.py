@@ -131,6 +131,33 @@ def main():
             ops.gn_stats(x, sums, B, P, C, 8)
             ms = timeit(lambda: ops.gn_silu_add(x, sums, gm, bt, x, out, B, P, C, 8), args.iters)
             report("gn_silu_add", f"{B}x{P}x{C}", ms, 3.0 * B * P * C * es)
+    if args.only in ("", "conv"):
+        # (c0, c1, cout, k, stride, up, H, epilogue) of representative call sites of one Unet evaluation
+        CONVS = [(64, 0, 256, 1, 1, False, 512, "silu_half"), (64, 0, 192, 1, 1, False, 512, "plain"),
+                 (128, 0, 64, 1, 1, False, 512, "gate_res"), (64, 64, 64, 3, 1, False, 512, "gn"),
+                 (64, 0, 64, 3, 1, False, 512, "gn"), (256, 128, 256, 3, 1, False, 128, "gn"),
+                 (512, 0, 256, 3, 1, True, 64, "plain"), (64, 0, 64, 4, 2, False, 512, "plain")]
+        for c0, c1, cout, k, stride, up, H, epi in sel(CONVS):
+            x0 = rn(B, H * H, c0)
+            x1 = rn(B, H * H, c1) if c1 else None
+            w = rn(cout, k, k, c0 + c1) * 0.05
+            Ho = H * (2 if up else 1) // stride
+            out = torch.empty(B, Ho * Ho, cout, device="cuda", dtype=dt)
+            kw = {}
+            if epi == "silu_half":
+                kw = dict(silu_from=cout // 2)
+            elif epi == "gate_res":
+                gate = rn(B, cout, d=torch.float32)
+                kw = dict(gate=gate, gate_stride=cout, addend=out)
+            elif epi == "gn":
+                kw = dict(bias=rn(cout, d=torch.float32), gn_sums=torch.zeros(B, 8, 2, device="cuda"), gn_groups=8)
+            conv = ops.Conv(x0, w, out, B=B, Hin=H, Win=H, KH=k, KW=k, stride=stride, pad=(k - 1) // 2 if k != 4 else 1, upsample=up,
+                            src1=x1, **kw)
+            ms = timeit(conv.run, args.iters)
+            flops = conv.flops()
+            byts = (B * H * H * (c0 + c1) + B * Ho * Ho * cout * (2 if epi == "gate_res" else 1)) * es
+            report("conv_tc" if conv.uses_tc else "conv_simt", conv.describe() + " " + epi, ms, byts, flops)
+            del x0, x1, out, conv
     if args.json:
         os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
         json.dump(dict(batch=B, dtype=args.dtype, hbm_peak_gbs=hbm, rows=rows), open(args.json, "w"), indent=1)
