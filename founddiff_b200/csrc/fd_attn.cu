@@ -137,7 +137,7 @@ template <typename T> FD_DEVINL void dw_st(T* p, const float (&v)[4]) {
 }
 
 template <typename T, bool SILU>
-__global__ void __launch_bounds__(256, 3) dwconv3x3_nhwc_kernel(const T* __restrict__ in, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) dwconv3x3_nhwc_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, T* __restrict__ out, int H,
                                                                 int W, int C) {
     const int NV = C / DW_V;                            // vectors per pixel
@@ -163,23 +163,25 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_nhwc_kernel(const T* __restr
 #pragma unroll
         for (int e = 0; e < DW_V; ++e) acc[r][e] = bs[e];
 
-    uint2 nxt[3];                                        // raw vectors of the NEXT input row (software pipelining)
-    auto fetch = [&](int yi) {
-        nxt[0] = nxt[1] = nxt[2] = make_uint2(0u, 0u);
-        if (yi >= 0 && yi < H) {
-            const T* rp = base + ((long)yi * rowv + f) * DW_V;
-            if (has_l) nxt[0] = dw_ld_raw<T>(rp - (long)NV * DW_V);
-            nxt[1] = dw_ld_raw<T>(rp);
-            if (has_r) nxt[2] = dw_ld_raw<T>(rp + (long)NV * DW_V);
+    // software pipeline: raw vectors of input rows yi, yi+1, yi+2 are in flight (ring slot = row mod 3)
+    uint2 ring[3][3];
+    auto fetch = [&](int yr, auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;
+        ring[S][0] = ring[S][1] = ring[S][2] = make_uint2(0u, 0u);
+        if (yr >= 0 && yr < H && yr <= y1) {
+            const T* rp = base + ((long)yr * rowv + f) * DW_V;
+            if (has_l) ring[S][0] = dw_ld_raw<T>(rp - (long)NV * DW_V);
+            ring[S][1] = dw_ld_raw<T>(rp);
+            if (has_r) ring[S][2] = dw_ld_raw<T>(rp + (long)NV * DW_V);
         }
     };
     // input row `yi` contributes to output rows yi+1 (tap row 0), yi (1), yi-1 (2); accumulator slot = output row mod 3
     auto step = [&](int yi, auto slot_c) {
-        constexpr int S = decltype(slot_c)::value;      // == yi mod 3 (compile-time so that acc[] stays in registers)
+        constexpr int S = decltype(slot_c)::value;      // == yi mod 3 (compile-time so that acc[] / ring[] stay in registers)
         float v[3][DW_V];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) dw_cvt<T>(nxt[dx], v[dx]);
-        fetch(yi + 1);
+        for (int dx = 0; dx < 3; ++dx) dw_cvt<T>(ring[S][dx], v[dx]);
+        fetch(yi + 3, slot_c);
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
@@ -198,12 +200,14 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_nhwc_kernel(const T* __restr
 #pragma unroll
         for (int e = 0; e < DW_V; ++e) acc[(S + 2) % 3][e] = bs[e];
     };
-    // rows y0-1 .. y1 (inclusive); peel so that the slot index (row mod 3) is a compile-time constant
+    // rows ya .. y1 (inclusive) with ya = the multiple of 3 at or below y0-1: rows before y0-1 are never fetched into
+    // the window as real data?  They are: so start exactly at a multiple of 3 and let the (cheap) extra rows run —
+    // their contributions land in accumulators that are reset before the first real output row is emitted.
     int yi = y0 - 1;
-    fetch(yi);
-    const int ybase = ((yi % 3) + 3) % 3;
-    if (ybase == 1) { step(yi, std::integral_constant<int, 1>{}); ++yi; step(yi, std::integral_constant<int, 2>{}); ++yi; }
-    else if (ybase == 2) { step(yi, std::integral_constant<int, 2>{}); ++yi; }
+    yi -= ((yi % 3) + 3) % 3;                            // round down to a multiple of 3 (may be < y0-1, even < 0)
+    fetch(yi, std::integral_constant<int, 0>{});
+    fetch(yi + 1, std::integral_constant<int, 1>{});
+    fetch(yi + 2, std::integral_constant<int, 2>{});
     for (; yi <= y1; yi += 3) {
         step(yi, std::integral_constant<int, 0>{});
         if (yi + 1 <= y1) step(yi + 1, std::integral_constant<int, 1>{});

@@ -69,6 +69,11 @@ FD_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Waits that are expected to be long (producer on a full ring, epilogue on the next accumulator): back off so that the
+// spinning warps do not take issue slots from the working ones.
+FD_DEVINL void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 FD_DEVINL void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
@@ -210,7 +215,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int tap = kb / kb_per_tap, cb = kb % kb_per_tap;
                     const int kh = tap / q.taps_w, kw = tap % q.taps_w;
-                    mbar_wait(&empty_bar[stage], ph ^ 1);
+                    mbar_wait_backoff(&empty_bar[stage], ph ^ 1);
                     uint8_t* sa = smem + stage * stage_bytes;
                     mbar_expect_tx(&full_bar[stage], stage_bytes);
                     if (cb < q.kblocks0) tma_load_4d(sa, &map_a0, &full_bar[stage], cb * BK, wbase + kw, hbase + kh, b);
@@ -284,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 cur_b = b;
             }
             const int buf = it & 1;
-            mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+            mbar_wait_backoff(&tfull_bar[buf], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q4 * 32) << 16);
             for (int cc = 0; cc < cols_per_warp; cc += 16) {
@@ -300,10 +305,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 float v[16];
                 const int n = n0 + c;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float x = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n + j) : 0.f);
-                    if (n + j >= p.silu_from) x = fast_silu(x);
-                    v[j] = x;
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (p.bias) {                          // warp-uniform branches, 16-byte parameter loads
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                    }
+                }
+                if (n >= p.silu_from) {                // silu_from is a multiple of 16 (checked on the host)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fast_silu(v[j]);
                 }
                 if (p.gn_sums) {                       // 8 consecutive columns always share a group (cpg >= 8)
 #pragma unroll
@@ -413,6 +425,8 @@ extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
     if (fd_conv_check_params(p)) return 0;
     if (p->dtype != FD_BF16 && p->dtype != FD_F16) return 0;
     if (p->c0 % BK || p->c1 % BK || p->ld0 % 8) return 0;
+    if (p->silu_from < p->Cout && p->silu_from % 16) return 0;
+    if (((uintptr_t)p->bias | (uintptr_t)p->gate) & 15 || (p->gate && p->gate_stride % 4)) return 0;
     if (p->Cout % 64) return 0;
     int Hout, Wout;
     if (conv_dims(p, &Hout, &Wout)) return 0;
