@@ -88,7 +88,8 @@ def main():
                 report("dwconv_qkv_gram", f"{B}x{H}x{H}x{C}", ms, 4.0 * B * H * H * C * es, (54.0 + 64.0) * B * H * H * C)
             else:
                 qkv2 = torch.empty_like(qkv)
-                ms = timeit(lambda: ops.dwconv3x3_nhwc(qkv, w, None, qkv2, B, H, H, 3 * C), args.iters)
+                wt = w.t().contiguous()
+                ms = timeit(lambda: ops.dwconv3x3_nhwc(qkv, wt, None, qkv2, B, H, H, 3 * C), args.iters)
                 report("dwconv3x3_nhwc", f"{B}x{H}x{H}x{3 * C}", ms, 6.0 * B * H * H * C * es, 54.0 * B * H * H * C)
                 ms = timeit(lambda: ops.gram_qk(qkv2, 3 * C, gram, qk, B, H * H, C), args.iters)
                 report("gram_qk", f"{B}x{H * H}x{C}", ms, 2.0 * B * H * H * C * es, 64.0 * 3 * B * H * H * C)

@@ -147,12 +147,19 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_nhwc_kernel(const T* __restr
     const int cv = (int)(f % NV), x = (int)(f / NV);
     const int b = blockIdx.z;
     const int y0 = blockIdx.y * DW_RY, y1 = min(H, y0 + DW_RY);
+    // weights are tap-major (9, C) so that a warp's loads are contiguous 16-byte vectors (the (C, 9) layout made the
+    // 36 scalar weight loads cost as many L2 sectors as the whole data stream of the block)
     float wr[9][DW_V], bs[DW_V];
 #pragma unroll
-    for (int e = 0; e < DW_V; ++e) {
-        bs[e] = bias ? bias[cv * DW_V + e] : 0.f;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) wr[t][e] = w[(long)(cv * DW_V + e) * 9 + t];
+    for (int t = 0; t < 9; ++t) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long)t * C + cv * DW_V));
+        wr[t][0] = wv.x; wr[t][1] = wv.y; wr[t][2] = wv.z; wr[t][3] = wv.w;
+    }
+    if (bias) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + cv * DW_V));
+        bs[0] = bv.x; bs[1] = bv.y; bs[2] = bv.z; bs[3] = bv.w;
+    } else {
+        bs[0] = bs[1] = bs[2] = bs[3] = 0.f;
     }
     const bool has_l = x > 0, has_r = x + 1 < W;
     const T* base = in + (long)b * H * rowv * DW_V;

@@ -273,6 +273,7 @@ class UnetEngine:
         on_w, on_b = f32(p + ".mamba.out_norm.weight"), f32(p + ".mamba.out_norm.bias")
         qkv_w = to_dt(sd[p + ".attn_blk.qkv.weight"].reshape(3 * C, C))
         qdw_w = f32(p + ".attn_blk.qkv_dwconv.weight").reshape(3 * C, 9).contiguous()
+        qdw_wt = qdw_w.t().contiguous()                      # tap-major copy for the streaming dwconv kernel
         proj_w = f32(p + ".attn_blk.project_out.weight").reshape(C, C).contiguous()
         temp = f32(p + ".attn_blk.temperature").reshape(-1).contiguous()
         acc_g = self._acc(B * heads * 32 * 32)
@@ -314,7 +315,7 @@ class UnetEngine:
             ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
             c_qkv.run()
             if split_attn:
-                ops.dwconv3x3_nhwc(qkv, qdw_w, None, qkv2, B, h, w, 3 * C)
+                ops.dwconv3x3_nhwc(qkv, qdw_wt, None, qkv2, B, h, w, 3 * C)
                 ops.gram_qk(qkv2, 3 * C, holder["gram"], holder["qk"], B, P, C)
             else:
                 ops.dwconv3x3_qkv_gram(qkv, qdw_w, v, holder["gram"], holder["qk"], B, h, w, C)

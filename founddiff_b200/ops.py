@@ -240,6 +240,8 @@ def dwconv3x3_qkv_gram(qkv, w, v, gram, qk_sq, B, H, W, C):
 
 
 def dwconv3x3_nhwc(x, w, bias, out, B, H, W, C, silu=False):
+    """w: TAP-MAJOR (9, C) fp32 (use `w.reshape(C, 9).t().contiguous()` on a (C,1,3,3) PyTorch weight)."""
+    assert tuple(w.shape) == (9, C), w.shape
     with _launched("dwconv3x3_nhwc", f"{B}x{H}x{W}x{C}", 1):
         check(_lib.load().fd_dwconv3x3_nhwc(_p(x), _f32(w), _f32(bias), _p(out), B, H, W, C, int(silu), dtype_code(x.dtype),
                                             _stream()), "fd_dwconv3x3_nhwc")

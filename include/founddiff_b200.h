@@ -149,6 +149,7 @@ int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, float* gram,
                           int W, int C, int dtype, cudaStream_t stream);
 /* 16-bit storage types (bf16 / fp16) split the first step into two streaming kernels:
  *   fd_dwconv3x3_nhwc: depthwise 3x3 (+bias, +SiLU) over a channels-last (B,H,W,C) tensor, register sliding window;
+ *                      NB its weights are TAP-MAJOR: w is (9, C) fp32 (the other dwconv entry points take (C, 9));
  *   fd_gram_qk:        gram / qk_sq (same meaning as above, ACCUMULATED) from q = columns [0,C), k = columns [C,2C) of
  *                      rows of pitch `ld` — q.k^T and the norms run on the tensor cores (mma.sync, fp32 accumulate).
  * v is then read in place (columns [2C,3C), ld0 = 3C) by the per-sample W_eff GEMM. */

@@ -289,7 +289,7 @@ def test_transposed_attention(ops, C, hw, dt):
         v_src, kw = v, {}
     else:       # streaming dwconv (register sliding window) + tensor-core Gram; v is read in place by the GEMM
         qkv2 = torch.empty(B, H * W, 3 * C, device="cuda", dtype=dt)
-        ops.dwconv3x3_nhwc(nhwc(qkv, dt), wdw.reshape(3 * C, 9).cuda(), None, qkv2, B, H, W, 3 * C)
+        ops.dwconv3x3_nhwc(nhwc(qkv, dt), wdw.reshape(3 * C, 9).t().contiguous().cuda(), None, qkv2, B, H, W, 3 * C)
         assert rel(nchw(qkv2, H, W), t) < TOL[dt]
         ops.gram_qk(qkv2, 3 * C, gram, qk, B, H * W, C)
         v = qkv2[:, :, 2 * C:]
@@ -322,7 +322,7 @@ def test_dwconv3x3_nhwc(ops, dt, shape):
     ref = F.conv2d(x, w, b if silu else None, padding=1, groups=C)
     ref = F.silu(ref) if silu else ref
     out = torch.empty(B, H * W, C, device="cuda", dtype=dt)
-    ops.dwconv3x3_nhwc(nhwc(x, dt), w.reshape(C, 9).cuda(), b.cuda() if silu else None, out, B, H, W, C, silu=silu)
+    ops.dwconv3x3_nhwc(nhwc(x, dt), w.reshape(C, 9).t().contiguous().cuda(), b.cuda() if silu else None, out, B, H, W, C, silu=silu)
     assert rel(nchw(out, H, W), ref) < TOL[dt]
 
 
