@@ -159,11 +159,13 @@ FD_DEVINL float fast_softplus(float x) {
 }
 
 template <typename T, int NS, int NBUF>
-__global__ void __launch_bounds__(kRowsPerBlock * 32) selective_scan_smem_kernel(
+__global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selective_scan_smem_kernel(
     const T* __restrict__ u, const T* __restrict__ delta, const float* __restrict__ A, const float* __restrict__ Bm,
     const float* __restrict__ Cm, const float* __restrict__ D, const float* __restrict__ delta_bias, T* __restrict__ y,
     int dim, int L, int G, int softplus) {
-    extern __shared__ __align__(16) float s_bc[];          // [NBUF][2][NS][kPadChunk]
+    extern __shared__ __align__(16) float s_bc[];          // [NBUF][2][NS][kPadChunk] (+ [8 rows][NS] of A*log2e for NS >= 16)
+    constexpr bool kA2InSmem = NS >= 16;                   // keeps the register count at two blocks per SM for large d_state
+    float* s_a2 = s_bc + (size_t)NBUF * 2 * NS * kPadChunk;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per_group = dim / G;
     const int blocks_per_group = per_group / kRowsPerBlock;
@@ -179,9 +181,16 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32) selective_scan_smem_kernel
     const float bias = delta_bias ? delta_bias[d] : 0.f;
     const float Dd = D ? D[d] : 0.f;
 
-    float A2[NS], h[NS];
+    float A2[kA2InSmem ? 1 : NS], h[NS];
 #pragma unroll
-    for (int n = 0; n < NS; ++n) { A2[n] = A[(long)d * NS + n] * 1.4426950408889634f; h[n] = 0.f; }
+    for (int n = 0; n < NS; ++n) {
+        if constexpr (!kA2InSmem) A2[n] = A[(long)d * NS + n] * 1.4426950408889634f;
+        h[n] = 0.f;
+    }
+    if constexpr (kA2InSmem) {
+        for (int n = lane; n < NS; n += 32) s_a2[warp * NS + n] = A[(long)d * NS + n] * 1.4426950408889634f;
+        __syncwarp();
+    }
 
     auto stage = [&](int c0, int buf) {   // cooperative cp.async of B/C[:, c0 : c0+256] (zero-filled past L)
         float* dst = s_bc + (size_t)buf * 2 * NS * kPadChunk;
@@ -234,10 +243,11 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32) selective_scan_smem_kernel
             const float4 c1v = *reinterpret_cast<const float4*>(sC + n * kPadChunk + 4);
             float Bn[kItems] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             const float Cn[kItems] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+            const float a2n = kA2InSmem ? s_a2[warp * NS + n] : A2[kA2InSmem ? 0 : n];
             float a[kItems], ap = 1.f, bp = 0.f;
 #pragma unroll
             for (int i = 0; i < kItems; ++i) {
-                a[i] = ex2_approx(dt[i] * A2[n]);
+                a[i] = ex2_approx(dt[i] * a2n);
                 Bn[i] = dtu[i] * Bn[i];
                 ap *= a[i];
                 bp = fmaf(a[i], bp, Bn[i]);
@@ -279,7 +289,7 @@ int scan_launch(const void* u, const void* delta, const float* A, const float* B
         const unsigned grid2 = (unsigned)(rows / kRowsPerBlock);
 #define SCAN2_CASE(NSV, NB)                                                                                         \
     if (N == NSV) {                                                                                                 \
-        const size_t smem = (size_t)NB * 2 * NSV * kPadChunk * sizeof(float);                                       \
+        const size_t smem = ((size_t)NB * 2 * NSV * kPadChunk + (NSV >= 16 ? kRowsPerBlock * NSV : 0)) * sizeof(float); \
         static bool attr_set = false;                                                                               \
         if (!attr_set) {                                                                                            \
             cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB>,                            \
