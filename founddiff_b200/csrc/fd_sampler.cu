@@ -91,57 +91,77 @@ extern "C" int fd_final_conv_update(const void* feat, const float* w, const floa
 
 // ------------------------------------------------------------------------------------------------------
 // init_conv 7x7 pad 3 over two fp32 single-channel images (Unet.init_conv, src/DADiff.py:558, 700 + cat :1160).
-// Block: 16x16 output pixels; the 22x22x2 input patch and the (Cout,2,7,7) weights live in shared memory;
-// each thread produces all Cout channels of one pixel, 16 channels per pass.
+// fp32 CUDA-core kernel (the two input images are fp32 and K = 98 is tiny): block = 16 rows x 64 cols of output pixels,
+// 256 threads; a thread owns 4 horizontally adjacent pixels x 16 output channels per pass, so every weight vector read
+// from shared memory feeds 4 pixels and every input value feeds 16 channels (64 FMAs per 4 + 10 shared loads).
 // ------------------------------------------------------------------------------------------------------
+constexpr int IC_TH = 16, IC_TW = 64;
+constexpr int IC_PH = IC_TH + 6, IC_PW = IC_TW + 6 + 2;     // patch with halo (+2: row pitch 72 keeps 16-byte alignment)
+
 template <typename T>
 __global__ void __launch_bounds__(256) init_conv7x7_kernel(const float* __restrict__ x_t, const float* __restrict__ x_in,
                                                            const float* __restrict__ weight,
                                                            const float* __restrict__ bias, T* __restrict__ out, int H,
                                                            int W, int Cout) {
-    extern __shared__ float sm[];
-    float* sw = sm;                      // [98][Cout]  (tap-major so that a pass reads 16 consecutive floats)
-    float* sb = sw + 98 * Cout;          // [Cout]
-    float* sp = sb + Cout;               // [2][22][23]
-    const int b = blockIdx.z, ty0 = blockIdx.y * 16, tx0 = blockIdx.x * 16;
+    extern __shared__ __align__(16) float sm[];
+    float* sw = sm;                                  // [98][Cout]  tap-major
+    float* sb = sw + 98 * Cout;                      // [Cout]
+    float* sp = sb + Cout;                           // [2][IC_PH][IC_PW]
+    const int b = blockIdx.z, ty0 = blockIdx.y * IC_TH, tx0 = blockIdx.x * IC_TW;
     for (int i = threadIdx.x; i < 98 * Cout; i += 256) {
-        const int co = i / 98, tap = i % 98;             // weight memory order: (co, ci, kh, kw)
+        const int co = i / 98, tap = i % 98;         // weight memory order: (co, ci, kh, kw)
         sw[tap * Cout + co] = weight[i];
     }
     for (int i = threadIdx.x; i < Cout; i += 256) sb[i] = bias[i];
     const long img = (long)b * H * W;
-    for (int i = threadIdx.x; i < 2 * 22 * 22; i += 256) {
-        const int ci = i / 484, r = (i % 484) / 22, c = i % 22;
+    for (int i = threadIdx.x; i < 2 * IC_PH * IC_PW; i += 256) {
+        const int ci = i / (IC_PH * IC_PW), r = (i % (IC_PH * IC_PW)) / IC_PW, c = i % IC_PW;
         const int h = ty0 + r - 3, w = tx0 + c - 3;
         float v = 0.f;
         if (h >= 0 && h < H && w >= 0 && w < W) v = (ci == 0 ? x_t : x_in)[img + (long)h * W + w];
-        sp[(ci * 22 + r) * 23 + c] = v;
+        sp[i] = v;
     }
     __syncthreads();
-    const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
-    const int h = ty0 + ty, w = tx0 + tx;
-    if (h >= H || w >= W) return;
-    T* orow = out + (img + (long)h * W + w) * Cout;
+    const int ty = threadIdx.x / 16, tx4 = (threadIdx.x % 16) * 4;      // 16 rows x 16 groups of 4 pixels
+    const int h = ty0 + ty;
     for (int c0 = 0; c0 < Cout; c0 += 16) {
-        float acc[16];
+        float acc[4][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = sb[c0 + j];
+        for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[px][j] = sb[c0 + j];
         for (int ci = 0; ci < 2; ++ci)
-            for (int kh = 0; kh < 7; ++kh)
+            for (int kh = 0; kh < 7; ++kh) {
+                const float* prow = sp + (ci * IC_PH + ty + kh) * IC_PW + tx4;
+                float in[10];
+#pragma unroll
+                for (int j = 0; j < 10; ++j) in[j] = prow[j];
 #pragma unroll
                 for (int kw = 0; kw < 7; ++kw) {
-                    const float v = sp[(ci * 22 + ty + kh) * 23 + tx + kw];
-                    const float* wp = sw + ((ci * 7 + kh) * 7 + kw) * Cout + c0;
+                    const float4* wp = reinterpret_cast<const float4*>(sw + ((ci * 7 + kh) * 7 + kw) * Cout + c0);
+                    const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+                    const float wv[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+                    for (int px = 0; px < 4; ++px)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[px][j] = fmaf(in[px + kw], wv[j], acc[px][j]);
                 }
-        constexpr int VEC = fd_vec<T>::N;
+            }
+        if (h < H) {
+            constexpr int VEC = fd_vec<T>::N;
 #pragma unroll
-        for (int j = 0; j < 16; j += VEC) {
-            float t[VEC];
+            for (int px = 0; px < 4; ++px) {
+                const int w = tx0 + tx4 + px;
+                if (w >= W) continue;
+                T* orow = out + (img + (long)h * W + w) * Cout + c0;
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) t[e] = acc[j + e];
-            fd_stv<T, VEC>(orow + c0 + j, t);
+                for (int j = 0; j < 16; j += VEC) {
+                    float t[VEC];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) t[e] = acc[px][j + e];
+                    fd_stv<T, VEC>(orow + j, t);
+                }
+            }
         }
     }
 }
@@ -150,12 +170,16 @@ extern "C" int fd_init_conv7x7(const float* x_t, const float* x_input, const flo
                                void* out, int B, int H, int W, int Cout, int dtype, cudaStream_t stream) {
     if (!x_t || !x_input || !weight || !bias || !out || B <= 0 || H <= 0 || W <= 0 || Cout <= 0 || Cout % 16)
         return FD_ERR_BAD_ARGUMENT;
-    const size_t smem = (size_t)(98 * Cout + Cout + 2 * 22 * 23) * sizeof(float);
+    const size_t smem = (size_t)(98 * Cout + Cout + 2 * IC_PH * IC_PW) * sizeof(float);
     if (smem > 200 * 1024) return FD_ERR_UNSUPPORTED;
-    dim3 grid(fd_cdiv(W, 16), fd_cdiv(H, 16), B);
+    dim3 grid(fd_cdiv(W, IC_TW), fd_cdiv(H, IC_TH), B);
     FD_DISPATCH_DTYPE(dtype, T, {
-        cudaError_t e = cudaFuncSetAttribute(init_conv7x7_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(init_conv7x7_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
         init_conv7x7_kernel<T><<<grid, 256, smem, stream>>>(x_t, x_input, weight, bias, (T*)out, H, W, Cout);
     });
     FD_LAUNCH_CHECK();
