@@ -95,6 +95,91 @@ extern "C" int fd_ln_modulate(const void* x, void* out, const float* gamma, cons
 }
 
 // ------------------------------------------------------------------------------------------------------
+// SS2D tail on channels-last data (src/emamba2.py:365, 747-748): out = (LN(y) * gamma + beta) * z + local[b]
+// with z = columns [z_off, z_off + C) of rows of pitch `ld` (the silu(z) half of xz).  Same row mapping as above.
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int LPR, int NV>
+__global__ void __launch_bounds__(256) ln_gate_kernel(const T* __restrict__ y, const T* __restrict__ xz, int ld, int z_off,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ local, T* __restrict__ out, long rows, int P,
+                                                      int C, float eps) {
+    constexpr int VEC = fd_vec<T>::N;
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % LPR;
+    const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long row = warp * RPW + lane / LPR;
+    const bool active = row < rows;
+    float v[NV][VEC];
+    float s = 0.f;
+    const T* yr = y + (active ? row : 0) * (long)C;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        fd_ldv<T, VEC>(yr + (sub + j * LPR) * VEC, v[j]);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s += v[j][e];
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { float d = v[j][e] - mean; q += d * d; }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    if (!active) return;
+    const int b = (int)(row / P);
+    const T* zr = xz + row * (long)ld + z_off;
+    const float* lc = local + (long)b * C;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c0 = (sub + j * LPR) * VEC;
+        float z[VEC];
+        fd_ldv<T, VEC>(zr + c0, z);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float n = (v[j][e] - mean) * rstd * __ldg(gamma + c0 + e) + __ldg(beta + c0 + e);
+            v[j][e] = n * z[e] + __ldg(lc + c0 + e);
+        }
+        fd_stv<T, VEC>(out + row * (long)C + c0, v[j]);
+    }
+}
+
+template <typename T>
+static int ln_gate_launch(const void* y, const void* xz, int ld, int z_off, const float* gamma, const float* beta,
+                          const float* local, void* out, int B, int P, int C, float eps, cudaStream_t st) {
+    constexpr int VEC = fd_vec<T>::N;
+    if (C % VEC || ld % VEC || z_off % VEC) return FD_ERR_UNSUPPORTED;
+    const int vr = C / VEC;
+    const long rows = (long)B * P;
+    const int lpr = vr >= 32 ? 32 : vr;
+    const int nv = vr / lpr;
+    if (lpr * nv != vr || (lpr & (lpr - 1))) return FD_ERR_UNSUPPORTED;
+    const int rpw = 32 / lpr, warps = 8;
+    const int grid = fd_cdiv(rows, (long)rpw * warps);
+#define LG_CASE(L, N)                                                                                              \
+    if (lpr == L && nv == N) {                                                                                     \
+        ln_gate_kernel<T, L, N><<<grid, warps * 32, 0, st>>>((const T*)y, (const T*)xz, ld, z_off, gamma, beta, local, \
+                                                             (T*)out, rows, P, C, eps);                            \
+        FD_LAUNCH_CHECK();                                                                                         \
+        return 0;                                                                                                  \
+    }
+    LG_CASE(8, 1) LG_CASE(16, 1) LG_CASE(32, 1) LG_CASE(32, 2) LG_CASE(32, 4) LG_CASE(32, 8)
+#undef LG_CASE
+    return FD_ERR_UNSUPPORTED;
+}
+
+extern "C" int fd_ln_gate(const void* y, const void* xz, int ld, int z_off, const float* gamma, const float* beta,
+                          const float* local, void* out, int B, int P, int C, float eps, int dtype, cudaStream_t stream) {
+    if (!y || !xz || !gamma || !beta || !local || !out || B <= 0 || P <= 0 || C <= 0 || ld < z_off + C) return FD_ERR_BAD_ARGUMENT;
+    FD_DISPATCH_DTYPE(dtype, T, return ln_gate_launch<T>(y, xz, ld, z_off, gamma, beta, local, out, B, P, C, eps, stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // GroupNorm statistics: sums[b, g, 0:2] += (sum, sumsq).  One block = 256 threads over a slab of pixels of one
 // sample; thread t owns vector column (t % VR) so its group is fixed; smem + atomics finish the reduction.
 // ------------------------------------------------------------------------------------------------------

@@ -158,14 +158,18 @@ FD_DEVINL float fast_softplus(float x) {
     return (w == 1.f) ? y : __logf(w) * __fdividef(y, w - 1.f);
 }
 
-template <typename T, int NS, int NBUF>
+// MERGE = true fuses EfficientMerge (src/emamba2.py:238-262) into the scan: instead of the (b, KD, L) scan layout the
+// block transposes each 256-step chunk of its 8 channels through shared memory and writes 16-byte channel groups
+// straight into the channels-last tensor y_nhwc (B, H, W, dim/4) at the pixel each (direction, l) stands for.
+template <typename T, int NS, int NBUF, bool MERGE>
 __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selective_scan_smem_kernel(
     const T* __restrict__ u, const T* __restrict__ delta, const float* __restrict__ A, const float* __restrict__ Bm,
     const float* __restrict__ Cm, const float* __restrict__ D, const float* __restrict__ delta_bias, T* __restrict__ y,
-    int dim, int L, int G, int softplus) {
+    int dim, int L, int G, int softplus, int H, int W) {
     extern __shared__ __align__(16) float s_bc[];          // [NBUF][2][NS][kPadChunk] (+ [8 rows][NS] of A*log2e for NS >= 16)
     constexpr bool kA2InSmem = NS >= 16;                   // keeps the register count at two blocks per SM for large d_state
     float* s_a2 = s_bc + (size_t)NBUF * 2 * NS * kPadChunk;
+    T* s_y = reinterpret_cast<T*>(s_a2 + (kA2InSmem ? kRowsPerBlock * NS : 0));     // [8 rows][kChunk] (MERGE only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per_group = dim / G;
     const int blocks_per_group = per_group / kRowsPerBlock;
@@ -271,16 +275,38 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selecti
                 yacc[i] = fmaf(hh, Cn[i], yacc[i]);
             }
         }
-        store_items<T>(yr, l0, L, true, yacc);
-        __syncthreads();            // everyone is done with `buf` before it is refilled
-        if (NBUF == 1 && c + 1 < nchunks) stage(c0 + kChunk, 0);
+        if constexpr (!MERGE) {
+            store_items<T>(yr, l0, L, true, yacc);
+            __syncthreads();        // everyone is done with `buf` before it is refilled
+            if (NBUF == 1 && c + 1 < nchunks) stage(c0 + kChunk, 0);
+        } else {
+            fd_stv<T, 8>(s_y + warp * kChunk + lane * kItems, yacc);
+            __syncthreads();        // chunk of all 8 channels is in s_y; `buf` may be refilled
+            if (NBUF == 1 && c + 1 < nchunks) stage(c0 + kChunk, 0);
+            const int l = c0 + (int)threadIdx.x;            // one pixel per thread
+            if (l < L) {
+                const int k = bg % G;                       // direction of this block's channel group
+                const int H2 = H >> 1, W2 = W >> 1;
+                int hh, ww;
+                if (k & 1) { ww = 2 * (l / H2) + (k >> 1); hh = 2 * (l % H2) + 1; }     // column-major sub-grids
+                else       { hh = 2 * (l / W2); ww = 2 * (l % W2) + (k >> 1); }
+                uint4 pk;
+                unsigned short* ps = reinterpret_cast<unsigned short*>(&pk);
+                const unsigned short* src = reinterpret_cast<const unsigned short*>(s_y) + threadIdx.x;
+#pragma unroll
+                for (int r = 0; r < kRowsPerBlock; ++r) ps[r] = src[r * kChunk];
+                const int dloc0 = (blockIdx.x % blocks_per_group) * kRowsPerBlock;
+                *reinterpret_cast<uint4*>(y + (((long)b * H + hh) * W + ww) * per_group + dloc0) = pk;
+            }
+            // the next iteration's top-of-loop barrier orders these reads before s_y is overwritten
+        }
     }
 }
 
 template <typename T>
 int scan_launch(const void* u, const void* delta, const float* A, const float* Bm, const float* Cm, const float* D,
                 const float* delta_bias, void* y, int batch, int dim, int L, int N, int G, int softplus,
-                cudaStream_t st) {
+                cudaStream_t st, int mergeH = 0, int mergeW = 0) {
     const long rows = (long)batch * dim;
     const int vec_ok = (L % kItems == 0) && ((((uintptr_t)u | (uintptr_t)delta | (uintptr_t)y) & 31) == 0) &&
                        ((((uintptr_t)Bm | (uintptr_t)Cm) & 31) == 0);
@@ -292,19 +318,34 @@ int scan_launch(const void* u, const void* delta, const float* A, const float* B
         const size_t smem = ((size_t)NB * 2 * NSV * kPadChunk + (NSV >= 16 ? kRowsPerBlock * NSV : 0)) * sizeof(float); \
         static bool attr_set = false;                                                                               \
         if (!attr_set) {                                                                                            \
-            cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB>,                            \
+            cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, false>,                     \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
             if (e != cudaSuccess) return (int)e;                                                                    \
             attr_set = true;                                                                                        \
         }                                                                                                           \
-        selective_scan_smem_kernel<T, NSV, NB><<<grid2, kRowsPerBlock * 32, smem, st>>>(                            \
-            (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus);                    \
+        if (mergeH) {                                                                                               \
+            if (sizeof(T) != 2) return FD_ERR_UNSUPPORTED;                                                          \
+            static bool attr_m = false;                                                                             \
+            const size_t smem_m = smem + (size_t)kRowsPerBlock * kChunk * sizeof(T);                                \
+            if (!attr_m) {                                                                                          \
+                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, true>,                  \
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);     \
+                if (e != cudaSuccess) return (int)e;                                                                \
+                attr_m = true;                                                                                      \
+            }                                                                                                       \
+            selective_scan_smem_kernel<T, NSV, NB, true><<<grid2, kRowsPerBlock * 32, smem_m, st>>>(                \
+                (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus, mergeH, mergeW); \
+        } else {                                                                                                    \
+            selective_scan_smem_kernel<T, NSV, NB, false><<<grid2, kRowsPerBlock * 32, smem, st>>>(                 \
+                (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus, 0, 0);          \
+        }                                                                                                           \
         FD_LAUNCH_CHECK();                                                                                          \
         return 0;                                                                                                   \
     }
         SCAN2_CASE(4, 2) SCAN2_CASE(8, 2) SCAN2_CASE(16, 2) SCAN2_CASE(32, 1)
 #undef SCAN2_CASE
     }
+    if (mergeH) return FD_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)((rows + kWarpsPerBlock - 1) / kWarpsPerBlock);
 #define SCAN_CASE(NSV)                                                                                              \
     if (N <= NSV) {                                                                                                 \
@@ -331,4 +372,19 @@ extern "C" int fd_selective_scan_fwd(const void* u, const void* delta, const flo
                       return scan_launch<T>(u, delta, A, Bm, Cm, D, delta_bias, y, batch, dim, seqlen, dstate, ngroups,
                                             delta_softplus, stream));
     return 0;
+}
+
+// Scan + EfficientMerge: same inputs as fd_selective_scan_fwd (4 direction groups, L = H/2 * W/2), output written
+// channels-last: y_nhwc (batch, H, W, dim/4), pixel of (direction k, step l) per src/emamba2.py:207-210, 253-256.
+extern "C" int fd_selective_scan_fwd_merge(const void* u, const void* delta, const float* A, const float* Bm, const float* Cm,
+                                           const float* D, const float* delta_bias, void* y_nhwc, int batch, int dim, int H,
+                                           int W, int dstate, int delta_softplus, int io_dtype, cudaStream_t stream) {
+    if (!u || !delta || !A || !Bm || !Cm || !y_nhwc) return FD_ERR_BAD_ARGUMENT;
+    if (batch <= 0 || dim <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || dstate <= 0 || dim % 4) return FD_ERR_BAD_ARGUMENT;
+    const int L = (H / 2) * (W / 2);
+    if (io_dtype == FD_BF16)
+        return scan_launch<__nv_bfloat16>(u, delta, A, Bm, Cm, D, delta_bias, y_nhwc, batch, dim, L, dstate, 4, delta_softplus, stream, H, W);
+    if (io_dtype == FD_F16)
+        return scan_launch<__half>(u, delta, A, Bm, Cm, D, delta_bias, y_nhwc, batch, dim, L, dstate, 4, delta_softplus, stream, H, W);
+    return FD_ERR_UNSUPPORTED;
 }

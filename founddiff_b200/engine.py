@@ -283,6 +283,8 @@ class UnetEngine:
         c_in = ops.Conv(a, in_w, xz, B=B, Hin=h, Win=w, silu_from=2 * C, prefer_tc=tc)
         c_out = ops.Conv(g, out_w, x, B=B, Hin=h, Win=w, gate=g1, gate_stride=MS, addend=x_in, prefer_tc=tc)
         c_qkv = ops.Conv(a, qkv_w, qkv, B=B, Hin=h, Win=w, prefer_tc=tc)
+        # fused scan+merge needs 16-bit io, 16/32-byte aligned rows (L % 8 == 0) and d_state in {4, 8, 16, 32}
+        fuse_merge = dt != torch.float32 and L % 8 == 0 and N in (4, 8, 16, 32) and D % 8 == 0
         split_attn = dt != torch.float32            # 16-bit modes: streaming dwconv + tensor-core Gram, v read in place
         if split_attn:
             qkv2 = self.buf(f"QKV2{l}", B, P, 3 * C)
@@ -308,9 +310,14 @@ class UnetEngine:
                 ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N)
             else:
                 ops.xdt_proj(xs, xp_w, dtp_w, dts, Bs, Cs, B, D, L, R, N)
-            ops.selective_scan_fwd(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs, Cs, Ds, dt_bias, True,
-                                   out=ys.view(B, 4 * D, L))
-            ops.merge_ln_gate(ys, xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), stat, g, B, h, w, D)
+            if fuse_merge:      # scan writes channels-last directly (EfficientMerge fused), then a row-wise LN + gate
+                ops.selective_scan_fwd_merge(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs, Cs, Ds, dt_bias, True,
+                                             ys.view(B, P, D), h, w)
+                ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
+            else:
+                ops.selective_scan_fwd(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs, Cs, Ds, dt_bias, True,
+                                       out=ys.view(B, 4 * D, L))
+                ops.merge_ln_gate(ys, xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), stat, g, B, h, w, D)
             c_out.run()
             ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
             c_qkv.run()

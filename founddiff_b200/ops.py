@@ -96,6 +96,24 @@ def selective_scan_fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplu
     return y
 
 
+def selective_scan_fwd_merge(u, delta, A, B, C, D, delta_bias, delta_softplus, y_nhwc, H, W):
+    """Scan + EfficientMerge: u, delta (b, 4*Dg, L); y_nhwc (b, H*W, Dg) channels-last."""
+    b, kd, L = u.shape
+    n = A.shape[1]
+    assert L == (H // 2) * (W // 2) and B.shape == (b, 4, n, L)
+    with _launched("selective_scan_merge", f"{b}x{kd}x{L} N{n}"):
+        check(_lib.load().fd_selective_scan_fwd_merge(_p(u), _p(delta), _f32(A), _f32(B), _f32(C), _f32(D), _f32(delta_bias),
+                                                      _p(y_nhwc), b, kd, H, W, n, int(bool(delta_softplus)), dtype_code(u.dtype),
+                                                      _stream()), "fd_selective_scan_fwd_merge")
+    return y_nhwc
+
+
+def ln_gate(y, xz, ld, z_off, gamma, beta, local, out, B, P, C, eps=1e-5):
+    with _launched("ln_gate", f"{B}x{P}x{C}"):
+        check(_lib.load().fd_ln_gate(_p(y), _p(xz), ld, z_off, _f32(gamma), _f32(beta), _f32(local), _p(out), B, P, C,
+                                     float(eps), dtype_code(y.dtype), _stream()), "fd_ln_gate")
+
+
 def pack_upsample_phases(weight: torch.Tensor, cout: int, cin: int) -> torch.Tensor:
     """nearest-x2 upsample followed by a 3x3 conv == 4 output phases, each a 2x2 conv over the low-resolution input
     whose taps are sums of the 3x3 taps that land on the same low-res pixel.  weight: (Cout, 3, 3, Cin) ->

@@ -49,6 +49,13 @@ int fd_selective_scan_fwd(const void* u, const void* delta, const float* A, cons
                           const float* D, const float* delta_bias, void* y, int batch, int dim, int seqlen,
                           int dstate, int ngroups, int delta_softplus, int io_dtype, cudaStream_t stream);
 
+/* Scan fused with EfficientMerge (src/emamba2.py:238-262): same inputs with ngroups = 4 and seqlen = (H/2)*(W/2); the
+ * output is written channels-last, y_nhwc (batch, H, W, dim/4), at the pixel each (direction, step) stands for
+ * (16-bit io types only).  Followed by fd_ln_gate it replaces fd_merge_ln_gate. */
+int fd_selective_scan_fwd_merge(const void* u, const void* delta, const float* A, const float* Bm, const float* Cm,
+                                const float* D, const float* delta_bias, void* y_nhwc, int batch, int dim, int H, int W,
+                                int dstate, int delta_softplus, int io_dtype, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution / 1x1 GEMM with fused epilogue — replaces F.conv2d / nn.Linear call sites:
  *   WeightStandardizedConv2d 3x3 (src/DADiff.py:139-154; standardisation folded into `weight` by the host),
@@ -136,6 +143,11 @@ int fd_xdt_proj_tc(const void* xs, const void* xw16, const void* dw16, void* dts
 int fd_merge_ln_gate(const void* ys, const void* xz, int ld, int z_off, const float* gamma, const float* beta,
                      const float* local, float* stats_ws, void* out, int B, int H, int W, int D, float eps, int dtype,
                      cudaStream_t stream);
+
+/* Row-wise tail of SS2D on channels-last data: out = (LN_C(y) * gamma + beta) * z + local[b]  (src/emamba2.py:365,
+ * 747-748); z = columns [z_off, z_off+C) of xz rows of pitch ld; local: (B, C) fp32. */
+int fd_ln_gate(const void* y, const void* xz, int ld, int z_off, const float* gamma, const float* beta, const float* local,
+               void* out, int B, int P, int C, float eps, int dtype, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * TransposedAttention (src/DADiff.py:263-285), C/32 heads of 32 channels.

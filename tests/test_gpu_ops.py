@@ -444,3 +444,30 @@ def test_conv2d_tc_epilogues(ops, dt):
         conv.run()
         res.append(buf.float().cpu())
     assert rel(res[1], res[0]) < 3e-3
+
+
+@pytest.mark.parametrize("cfg", [(16, 32, 64, 4), (32, 16, 32, 8), (16, 16, 128, 16), (8, 16, 256, 32), (64, 64, 16, 4)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_scan_merge_fused_and_ln_gate(ops, cfg, dt):
+    """Scan with EfficientMerge fused (channels-last output) + row-wise LN/gate == scan -> EfficientMerge -> LayerNorm ->
+    y*z + local of the oracle (src/emamba2.py:353-367, 747-748)."""
+    H, W, Dg, N = cfg
+    B, L = 2, (H // 2) * (W // 2)
+    g = torch.Generator().manual_seed(H * W + N)
+    u = q(torch.randn(B, 4 * Dg, L, generator=g), dt)
+    delta = q(torch.randn(B, 4 * Dg, L, generator=g), dt)
+    A = -torch.exp(torch.randn(4 * Dg, N, generator=g) * 0.3)
+    Bm, Cm = torch.randn(B, 4, N, L, generator=g), torch.randn(B, 4, N, L, generator=g)
+    D, bias = torch.randn(4 * Dg, generator=g), torch.randn(4 * Dg, generator=g)
+    ys = scan_cpu.selective_scan_fwd(u, delta, A, Bm, Cm, D, bias, True).reshape(B, 4, Dg, L)
+    y_ref = O.efficient_merge(ys, H, W).permute(0, 2, 3, 1)                       # (B,H,W,Dg)
+    c = lambda t: t.cuda()
+    y = torch.zeros(B, H * W, Dg, device="cuda", dtype=dt)
+    ops.selective_scan_fwd_merge(c(u).to(dt), c(delta).to(dt), c(A), c(Bm), c(Cm), c(D), c(bias), True, y, H, W)
+    assert rel(y.reshape(B, H, W, Dg), y_ref) < TOL[dt]
+    xz = q(torch.randn(B, H, W, 2 * Dg, generator=g), dt)
+    gamma, beta, local = torch.randn(Dg, generator=g), torch.randn(Dg, generator=g), torch.randn(B, Dg, generator=g)
+    ref = F.layer_norm(y.float().cpu().reshape(B, H, W, Dg), (Dg,), gamma, beta, eps=1e-5) * xz[..., Dg:] + local[:, None, None, :]
+    out = torch.empty(B, H * W, Dg, device="cuda", dtype=dt)
+    ops.ln_gate(y, xz.reshape(B, H * W, 2 * Dg).to("cuda", dt), 2 * Dg, Dg, gamma.cuda(), beta.cuda(), local.cuda(), out, B, H * W, Dg)
+    assert rel(out.reshape(B, H, W, Dg), ref) < TOL[dt]
