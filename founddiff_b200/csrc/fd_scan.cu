@@ -324,7 +324,7 @@ int scan_launch(const void* u, const void* delta, const float* A, const float* B
             attr_set = true;                                                                                        \
         }                                                                                                           \
         if (mergeH) {                                                                                               \
-            if (sizeof(T) != 2) return FD_ERR_UNSUPPORTED;                                                          \
+          if constexpr (sizeof(T) != 2) { return FD_ERR_UNSUPPORTED; } else {                                       \
             static bool attr_m = false;                                                                             \
             const size_t smem_m = smem + (size_t)kRowsPerBlock * kChunk * sizeof(T);                                \
             if (!attr_m) {                                                                                          \
@@ -335,6 +335,7 @@ int scan_launch(const void* u, const void* delta, const float* A, const float* B
             }                                                                                                       \
             selective_scan_smem_kernel<T, NSV, NB, true><<<grid2, kRowsPerBlock * 32, smem_m, st>>>(                \
                 (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus, mergeH, mergeW); \
+          }                                                                                                         \
         } else {                                                                                                    \
             selective_scan_smem_kernel<T, NSV, NB, false><<<grid2, kRowsPerBlock * 32, smem, st>>>(                 \
                 (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus, 0, 0);          \
