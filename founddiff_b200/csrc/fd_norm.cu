@@ -167,7 +167,7 @@ static int ln_gate_launch(const void* y, const void* xz, int ld, int z_off, cons
         FD_LAUNCH_CHECK();                                                                                         \
         return 0;                                                                                                  \
     }
-    LG_CASE(8, 1) LG_CASE(16, 1) LG_CASE(32, 1) LG_CASE(32, 2) LG_CASE(32, 4) LG_CASE(32, 8)
+    LG_CASE(2, 1) LG_CASE(4, 1) LG_CASE(8, 1) LG_CASE(16, 1) LG_CASE(32, 1) LG_CASE(32, 2) LG_CASE(32, 4) LG_CASE(32, 8)
 #undef LG_CASE
     return FD_ERR_UNSUPPORTED;
 }

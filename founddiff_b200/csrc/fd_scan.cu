@@ -159,42 +159,53 @@ FD_DEVINL float fast_softplus(float x) {
 }
 
 // MERGE = true fuses EfficientMerge (src/emamba2.py:238-262) into the scan: instead of the (b, KD, L) scan layout the
-// block transposes each 256-step chunk of its 8 channels through shared memory and writes 16-byte channel groups
+// block transposes each 256-step chunk of its channels through shared memory and writes whole 32-byte channel groups
 // straight into the channels-last tensor y_nhwc (B, H, W, dim/4) at the pixel each (direction, l) stands for.
-template <typename T, int NS, int NBUF, bool MERGE>
-__global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selective_scan_smem_kernel(
+// RPW = rows (channels) per warp: 2 for small d_state, where the per-chunk overhead (staging, barriers) would otherwise
+// dominate and so that a block owns 16 channels = one full sector per pixel.
+template <typename T, int NS, int NBUF, bool MERGE, int RPW>
+__global__ void __launch_bounds__(kRowsPerBlock * 32, ((NS <= 8 && RPW == 1) ? 3 : 2)) selective_scan_smem_kernel(
     const T* __restrict__ u, const T* __restrict__ delta, const float* __restrict__ A, const float* __restrict__ Bm,
     const float* __restrict__ Cm, const float* __restrict__ D, const float* __restrict__ delta_bias, T* __restrict__ y,
     int dim, int L, int G, int softplus, int H, int W) {
-    extern __shared__ __align__(16) float s_bc[];          // [NBUF][2][NS][kPadChunk] (+ [8 rows][NS] of A*log2e for NS >= 16)
+    extern __shared__ __align__(16) float s_bc[];          // [NBUF][2][NS][kPadChunk] (+ A*log2e for NS >= 16) (+ s_y)
     constexpr bool kA2InSmem = NS >= 16;                   // keeps the register count at two blocks per SM for large d_state
+    constexpr int kCh = kRowsPerBlock * RPW;               // channels per block
     float* s_a2 = s_bc + (size_t)NBUF * 2 * NS * kPadChunk;
-    T* s_y = reinterpret_cast<T*>(s_a2 + (kA2InSmem ? kRowsPerBlock * NS : 0));     // [8 rows][kChunk] (MERGE only)
+    T* s_y = reinterpret_cast<T*>(s_a2 + (kA2InSmem ? kCh * NS : 0));     // [kCh][kChunk] (MERGE only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per_group = dim / G;
-    const int blocks_per_group = per_group / kRowsPerBlock;
+    const int blocks_per_group = per_group / kCh;
     const int bg = blockIdx.x / blocks_per_group;          // b * G + g
-    const int d = (bg % G) * per_group + (blockIdx.x % blocks_per_group) * kRowsPerBlock + warp;
+    const int dloc0 = (blockIdx.x % blocks_per_group) * kCh;
     const int b = bg / G;
-    const long row = (long)b * dim + d;
-    const T* ur = u + row * (long)L;
-    const T* dr = delta + row * (long)L;
-    T* yr = y + row * (long)L;
     const float* Bg = Bm + (long)bg * NS * L;
     const float* Cg = Cm + (long)bg * NS * L;
-    const float bias = delta_bias ? delta_bias[d] : 0.f;
-    const float Dd = D ? D[d] : 0.f;
 
-    float A2[kA2InSmem ? 1 : NS], h[NS];
+    const T* ur[RPW];
+    const T* dr[RPW];
+    T* yr[RPW];
+    float bias[RPW], Dd[RPW];
+    float A2[RPW][kA2InSmem ? 1 : NS], h[RPW][NS];
 #pragma unroll
-    for (int n = 0; n < NS; ++n) {
-        if constexpr (!kA2InSmem) A2[n] = A[(long)d * NS + n] * 1.4426950408889634f;
-        h[n] = 0.f;
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int d = (bg % G) * per_group + dloc0 + warp * RPW + rr;
+        const long row = (long)b * dim + d;
+        ur[rr] = u + row * (long)L;
+        dr[rr] = delta + row * (long)L;
+        yr[rr] = y + row * (long)L;
+        bias[rr] = delta_bias ? delta_bias[d] : 0.f;
+        Dd[rr] = D ? D[d] : 0.f;
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            if constexpr (!kA2InSmem) A2[rr][n] = A[(long)d * NS + n] * 1.4426950408889634f;
+            h[rr][n] = 0.f;
+        }
+        if constexpr (kA2InSmem) {
+            for (int n = lane; n < NS; n += 32) s_a2[(warp * RPW + rr) * NS + n] = A[(long)d * NS + n] * 1.4426950408889634f;
+        }
     }
-    if constexpr (kA2InSmem) {
-        for (int n = lane; n < NS; n += 32) s_a2[warp * NS + n] = A[(long)d * NS + n] * 1.4426950408889634f;
-        __syncwarp();
-    }
+    if constexpr (kA2InSmem) __syncwarp();
 
     auto stage = [&](int c0, int buf) {   // cooperative cp.async of B/C[:, c0 : c0+256] (zero-filled past L)
         float* dst = s_bc + (size_t)buf * 2 * NS * kPadChunk;
@@ -209,9 +220,12 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selecti
 
     const int nchunks = (L + kChunk - 1) / kChunk;
     stage(0, 0);
-    float dt_n[kItems], u_n[kItems];
-    load_items<T>(dr, lane * kItems, L, true, dt_n);
-    load_items<T>(ur, lane * kItems, L, true, u_n);
+    float dt_n[RPW][kItems], u_n[RPW][kItems];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+        load_items<T>(dr[rr], lane * kItems, L, true, dt_n[rr]);
+        load_items<T>(ur[rr], lane * kItems, L, true, u_n[rr]);
+    }
 
     for (int c = 0; c < nchunks; ++c) {
         const int c0 = c * kChunk, l0 = c0 + lane * kItems;
@@ -223,66 +237,67 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selecti
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        float dt[kItems], dtu[kItems], yacc[kItems];
-#pragma unroll
-        for (int i = 0; i < kItems; ++i) {
-            float t = dt_n[i] + bias;
-            if (softplus) t = fast_softplus(t);
-            if (l0 + i >= L) t = 0.f;
-            yacc[i] = Dd * u_n[i];
-            dtu[i] = t * u_n[i];
-            dt[i] = t;
-        }
-        if (c + 1 < nchunks) {      // prefetch the next chunk's u / delta
-            load_items<T>(dr, l0 + kChunk, L, true, dt_n);
-            load_items<T>(ur, l0 + kChunk, L, true, u_n);
-        }
         const float* sB = s_bc + (size_t)buf * 2 * NS * kPadChunk + pad_idx(lane * kItems);
         const float* sC = sB + NS * kPadChunk;
+        const bool tail = c0 + kChunk > L;
 #pragma unroll
-        for (int n = 0; n < NS; ++n) {
-            const float4 b0 = *reinterpret_cast<const float4*>(sB + n * kPadChunk);
-            const float4 b1 = *reinterpret_cast<const float4*>(sB + n * kPadChunk + 4);
-            const float4 c0v = *reinterpret_cast<const float4*>(sC + n * kPadChunk);
-            const float4 c1v = *reinterpret_cast<const float4*>(sC + n * kPadChunk + 4);
-            float Bn[kItems] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            const float Cn[kItems] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
-            const float a2n = kA2InSmem ? s_a2[warp * NS + n] : A2[kA2InSmem ? 0 : n];
-            float a[kItems], ap = 1.f, bp = 0.f;
+        for (int rr = 0; rr < RPW; ++rr) {
+            float dt[kItems], dtu[kItems], yacc[kItems];
 #pragma unroll
             for (int i = 0; i < kItems; ++i) {
-                a[i] = ex2_approx(dt[i] * a2n);
-                Bn[i] = dtu[i] * Bn[i];
-                ap *= a[i];
-                bp = fmaf(a[i], bp, Bn[i]);
+                float t = dt_n[rr][i] + bias[rr];
+                if (softplus) t = fast_softplus(t);
+                if (tail && l0 + i >= L) t = 0.f;
+                yacc[i] = Dd[rr] * u_n[rr][i];
+                dtu[i] = t * u_n[rr][i];
+                dt[i] = t;
+            }
+            if (c + 1 < nchunks) {      // prefetch the next chunk's u / delta
+                load_items<T>(dr[rr], l0 + kChunk, L, true, dt_n[rr]);
+                load_items<T>(ur[rr], l0 + kChunk, L, true, u_n[rr]);
             }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float au = __shfl_up_sync(0xffffffffu, ap, o);
-                const float bu = __shfl_up_sync(0xffffffffu, bp, o);
-                if (lane >= o) { bp = fmaf(ap, bu, bp); ap *= au; }
-            }
-            float ae = __shfl_up_sync(0xffffffffu, ap, 1);
-            float be = __shfl_up_sync(0xffffffffu, bp, 1);
-            if (lane == 0) { ae = 1.f; be = 0.f; }
-            float hh = fmaf(ae, h[n], be);
-            const float at = __shfl_sync(0xffffffffu, ap, 31);
-            const float bt = __shfl_sync(0xffffffffu, bp, 31);
-            h[n] = fmaf(at, h[n], bt);
+            for (int n = 0; n < NS; ++n) {
+                const float4 b0 = *reinterpret_cast<const float4*>(sB + n * kPadChunk);
+                const float4 b1 = *reinterpret_cast<const float4*>(sB + n * kPadChunk + 4);
+                const float4 c0v = *reinterpret_cast<const float4*>(sC + n * kPadChunk);
+                const float4 c1v = *reinterpret_cast<const float4*>(sC + n * kPadChunk + 4);
+                float Bn[kItems] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float Cn[kItems] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+                const float a2n = kA2InSmem ? s_a2[(warp * RPW + rr) * NS + n] : A2[rr][kA2InSmem ? 0 : n];
+                float a[kItems], ap = 1.f, bp = 0.f;
 #pragma unroll
-            for (int i = 0; i < kItems; ++i) {
-                hh = fmaf(a[i], hh, Bn[i]);
-                yacc[i] = fmaf(hh, Cn[i], yacc[i]);
+                for (int i = 0; i < kItems; ++i) {
+                    a[i] = ex2_approx(dt[i] * a2n);
+                    Bn[i] = dtu[i] * Bn[i];
+                    ap *= a[i];
+                    bp = fmaf(a[i], bp, Bn[i]);
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float au = __shfl_up_sync(0xffffffffu, ap, o);
+                    const float bu = __shfl_up_sync(0xffffffffu, bp, o);
+                    if (lane >= o) { bp = fmaf(ap, bu, bp); ap *= au; }
+                }
+                float ae = __shfl_up_sync(0xffffffffu, ap, 1);
+                float be = __shfl_up_sync(0xffffffffu, bp, 1);
+                if (lane == 0) { ae = 1.f; be = 0.f; }
+                float hh = fmaf(ae, h[rr][n], be);
+                const float at = __shfl_sync(0xffffffffu, ap, 31);
+                const float bt = __shfl_sync(0xffffffffu, bp, 31);
+                h[rr][n] = fmaf(at, h[rr][n], bt);
+#pragma unroll
+                for (int i = 0; i < kItems; ++i) {
+                    hh = fmaf(a[i], hh, Bn[i]);
+                    yacc[i] = fmaf(hh, Cn[i], yacc[i]);
+                }
             }
+            if constexpr (!MERGE) store_items<T>(yr[rr], l0, L, true, yacc);
+            else fd_stv<T, 8>(s_y + (warp * RPW + rr) * kChunk + lane * kItems, yacc);
         }
-        if constexpr (!MERGE) {
-            store_items<T>(yr, l0, L, true, yacc);
-            __syncthreads();        // everyone is done with `buf` before it is refilled
-            if (NBUF == 1 && c + 1 < nchunks) stage(c0 + kChunk, 0);
-        } else {
-            fd_stv<T, 8>(s_y + warp * kChunk + lane * kItems, yacc);
-            __syncthreads();        // chunk of all 8 channels is in s_y; `buf` may be refilled
-            if (NBUF == 1 && c + 1 < nchunks) stage(c0 + kChunk, 0);
+        __syncthreads();                // everyone is done with `buf` (and, MERGE, the chunk of all channels is in s_y)
+        if (NBUF == 1 && c + 1 < nchunks) stage(c0 + kChunk, 0);
+        if constexpr (MERGE) {
             const int l = c0 + (int)threadIdx.x;            // one pixel per thread
             if (l < L) {
                 const int k = bg % G;                       // direction of this block's channel group
@@ -290,13 +305,16 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selecti
                 int hh, ww;
                 if (k & 1) { ww = 2 * (l / H2) + (k >> 1); hh = 2 * (l % H2) + 1; }     // column-major sub-grids
                 else       { hh = 2 * (l / W2); ww = 2 * (l % W2) + (k >> 1); }
-                uint4 pk;
-                unsigned short* ps = reinterpret_cast<unsigned short*>(&pk);
                 const unsigned short* src = reinterpret_cast<const unsigned short*>(s_y) + threadIdx.x;
+                T* dst = y + (((long)b * H + hh) * W + ww) * per_group + dloc0;
 #pragma unroll
-                for (int r = 0; r < kRowsPerBlock; ++r) ps[r] = src[r * kChunk];
-                const int dloc0 = (blockIdx.x % blocks_per_group) * kRowsPerBlock;
-                *reinterpret_cast<uint4*>(y + (((long)b * H + hh) * W + ww) * per_group + dloc0) = pk;
+                for (int v = 0; v < kCh / 8; ++v) {
+                    uint4 pk;
+                    unsigned short* ps = reinterpret_cast<unsigned short*>(&pk);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) ps[r] = src[(v * 8 + r) * kChunk];
+                    *reinterpret_cast<uint4*>(dst + v * 8) = pk;
+                }
             }
             // the next iteration's top-of-loop barrier orders these reads before s_y is overwritten
         }
@@ -311,39 +329,39 @@ int scan_launch(const void* u, const void* delta, const float* A, const float* B
     const int vec_ok = (L % kItems == 0) && ((((uintptr_t)u | (uintptr_t)delta | (uintptr_t)y) & 31) == 0) &&
                        ((((uintptr_t)Bm | (uintptr_t)Cm) & 31) == 0);
     // v2: rows of a block share one direction group and every access is 16/32-byte aligned
-    if (vec_ok && (dim / G) % kRowsPerBlock == 0 && (N == 4 || N == 8 || N == 16 || N == 32)) {
-        const unsigned grid2 = (unsigned)(rows / kRowsPerBlock);
-#define SCAN2_CASE(NSV, NB)                                                                                         \
-    if (N == NSV) {                                                                                                 \
-        const size_t smem = ((size_t)NB * 2 * NSV * kPadChunk + (NSV >= 16 ? kRowsPerBlock * NSV : 0)) * sizeof(float); \
-        static bool attr_set = false;                                                                               \
-        if (!attr_set) {                                                                                            \
-            cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, false>,                     \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-            if (e != cudaSuccess) return (int)e;                                                                    \
-            attr_set = true;                                                                                        \
-        }                                                                                                           \
+    if (vec_ok && (N == 4 || N == 8 || N == 16 || N == 32)) {
+#define SCAN2_CASE(NSV, NB, RPWV)                                                                                   \
+    if (N == NSV && (dim / G) % (kRowsPerBlock * RPWV) == 0) {                                                      \
+        const unsigned grid2 = (unsigned)(rows / (kRowsPerBlock * RPWV));                                           \
+        const size_t smem = ((size_t)NB * 2 * NSV * kPadChunk + (NSV >= 16 ? kRowsPerBlock * RPWV * NSV : 0)) * sizeof(float); \
         if (mergeH) {                                                                                               \
           if constexpr (sizeof(T) != 2) { return FD_ERR_UNSUPPORTED; } else {                                       \
             static bool attr_m = false;                                                                             \
-            const size_t smem_m = smem + (size_t)kRowsPerBlock * kChunk * sizeof(T);                                \
+            const size_t smem_m = smem + (size_t)kRowsPerBlock * RPWV * kChunk * sizeof(T);                         \
             if (!attr_m) {                                                                                          \
-                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, true>,                  \
+                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, true, RPWV>,            \
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);     \
                 if (e != cudaSuccess) return (int)e;                                                                \
                 attr_m = true;                                                                                      \
             }                                                                                                       \
-            selective_scan_smem_kernel<T, NSV, NB, true><<<grid2, kRowsPerBlock * 32, smem_m, st>>>(                \
+            selective_scan_smem_kernel<T, NSV, NB, true, RPWV><<<grid2, kRowsPerBlock * 32, smem_m, st>>>(          \
                 (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus, mergeH, mergeW); \
           }                                                                                                         \
         } else {                                                                                                    \
-            selective_scan_smem_kernel<T, NSV, NB, false><<<grid2, kRowsPerBlock * 32, smem, st>>>(                 \
+            static bool attr_set = false;                                                                           \
+            if (!attr_set) {                                                                                        \
+                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, false, RPWV>,           \
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+                if (e != cudaSuccess) return (int)e;                                                                \
+                attr_set = true;                                                                                    \
+            }                                                                                                       \
+            selective_scan_smem_kernel<T, NSV, NB, false, RPWV><<<grid2, kRowsPerBlock * 32, smem, st>>>(           \
                 (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus, 0, 0);          \
         }                                                                                                           \
         FD_LAUNCH_CHECK();                                                                                          \
         return 0;                                                                                                   \
     }
-        SCAN2_CASE(4, 2) SCAN2_CASE(8, 2) SCAN2_CASE(16, 2) SCAN2_CASE(32, 1)
+        SCAN2_CASE(4, 2, 2) SCAN2_CASE(8, 2, 2) SCAN2_CASE(4, 2, 1) SCAN2_CASE(8, 2, 1) SCAN2_CASE(16, 2, 1) SCAN2_CASE(32, 1, 1)
 #undef SCAN2_CASE
     }
     if (mergeH) return FD_ERR_UNSUPPORTED;
