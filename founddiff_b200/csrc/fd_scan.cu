@@ -361,7 +361,8 @@ int scan_launch(const void* u, const void* delta, const float* A, const float* B
         FD_LAUNCH_CHECK();                                                                                          \
         return 0;                                                                                                   \
     }
-        SCAN2_CASE(4, 2, 2) SCAN2_CASE(8, 2, 2) SCAN2_CASE(4, 2, 1) SCAN2_CASE(8, 2, 1) SCAN2_CASE(16, 2, 1) SCAN2_CASE(32, 1, 1)
+        // RPW = 2 (16 channels per block, full-sector writes) was measured SLOWER (register spills, occupancy): not used
+        SCAN2_CASE(4, 2, 1) SCAN2_CASE(8, 2, 1) SCAN2_CASE(16, 2, 1) SCAN2_CASE(32, 1, 1)
 #undef SCAN2_CASE
     }
     if (mergeH) return FD_ERR_UNSUPPORTED;
