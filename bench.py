@@ -139,14 +139,20 @@ def run_reference(args):
 def algorithmic(name, detail, es):
     """(bytes, flops) one launch must move / compute at minimum, from the op's shape string."""
     try:
-        if name == "selective_scan":
+        if name in ("selective_scan", "selective_scan_merge"):
             dims, n = detail.split(" N")
             b, kd, L = map(int, dims.split("x"))
             n = int(n)
             return 3.0 * b * kd * L * es + 2.0 * b * 4 * n * L * 4, 9.0 * b * kd * L * n
-        if name in ("ln_modulate", "gn_silu_add"):
+        if name in ("ln_modulate", "gn_silu_add", "ln_gate"):
             b, p, c = map(int, detail.split("x"))
             return (2.0 if name == "ln_modulate" else 3.0) * b * p * c * es, 0.0
+        if name == "dwconv3x3_nhwc":
+            b, h, w, c = map(int, detail.split("x"))
+            return 2.0 * b * h * w * c * es, 18.0 * b * h * w * c
+        if name == "gram_qk":
+            b, p, c = map(int, detail.split("x"))
+            return 2.0 * b * p * c * es, 64.0 * 3 * b * p * c
         if name == "dwconv_scan":
             b, h, w, d = map(int, detail.split("x"))
             return 2.0 * b * h * w * d * es, 18.0 * b * h * w * d
@@ -156,7 +162,7 @@ def algorithmic(name, detail, es):
         if name == "dwconv_qkv_gram":
             b, h, w, c = map(int, detail.split("x"))
             return 4.0 * b * h * w * c * es, (54.0 + 64.0) * b * h * w * c
-        if name == "xdt_proj":
+        if name in ("xdt_proj", "xdt_proj_tc"):
             dims, r, n = detail.replace(" R", " ").replace(" N", " ").split(" ")
             b, d, L = map(int, dims.split("x"))
             r, n = int(r), int(n)
@@ -319,6 +325,14 @@ def run_b200(args):
                         "frac": round(top["GBps"] / hbm_peak, 4), "traffic": None}
         roofline.update({"kernel": top["kernel"], "shape": top["shape"], "share_of_step": top["share"], "avg_us": top["avg_us"],
                          "peak_source": peak_src})
+        # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r1_ncu_traffic.json), if this
+        # kernel/shape was captured
+        tf = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+        if os.path.exists(tf):
+            ent = json.load(open(tf)).get(f"{top['kernel']}|{top['shape']}")
+            if ent:
+                roofline["traffic"] = ent["dram_bytes"]
+                roofline["traffic_source"] = ent["source"]
         if args.kernel_table:
             os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
             json.dump({"per_call_ms_eager": total, "kernels": table}, open(args.kernel_table, "w"), indent=1)
