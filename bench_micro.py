@@ -159,6 +159,13 @@ def main():
             byts = (B * H * H * (c0 + c1) + B * Ho * Ho * cout * (2 if epi == "gate_res" else 1)) * es
             report("conv_tc" if conv.uses_tc else "conv_simt", conv.describe() + " " + epi, ms, byts, flops)
             del x0, x1, out, conv
+    if args.only in ("", "flash"):
+        # lucidrains bottleneck Attention: 4 heads x 32 over (H/8)^2 tokens for 256^2 and 512^2 inputs
+        for N in sel([1024, 4096]):
+            qkv = rn(B, N, 3 * 128)
+            out = torch.empty(B, N, 128, device="cuda", dtype=dt)
+            ms = timeit(lambda: ops.flash_attn_d32(qkv, out, B, N, 4, 32 ** -0.5), args.iters)
+            report("flash_attn_d32", f"{B}x{N}x4x32", ms, 4.0 * B * N * 128 * es, 4.0 * B * 4 * N * N * 32)
     if args.json:
         os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
         json.dump(dict(batch=B, dtype=args.dtype, hbm_peak_gbs=hbm, rows=rows), open(args.json, "w"), indent=1)

@@ -230,7 +230,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) gn_silu_add_kernel(const T* __restrict__ y, const float* __restrict__ sums,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta,
-                                                          const T* __restrict__ skip, T* __restrict__ out, int P,
+                                                          const float* __restrict__ scale, const float* __restrict__ shift,
+                                                          int ss_stride, const T* __restrict__ skip, T* __restrict__ out, int P,
                                                           int C, int G, float eps, long nvec_per_sample) {
     constexpr int VEC = fd_vec<T>::N;
     const int b = blockIdx.y;
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(256) gn_silu_add_kernel(const T* __restrict__ 
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             float t = (v[e] - mean) * rstd * __ldg(gamma + c0 + e) + __ldg(beta + c0 + e);
+            if (scale) t = t * (__ldg(scale + (long)b * ss_stride + c0 + e) + 1.f) + __ldg(shift + (long)b * ss_stride + c0 + e);
             t = fd_silu(t);
             v[e] = skip ? t + s[e] : t;
         }
@@ -265,8 +267,27 @@ extern "C" int fd_gn_silu_add(const void* y, const float* sums, const float* gam
         if ((C / G) % VEC) return FD_ERR_UNSUPPORTED;
         const long nvec = (long)P * C / VEC;
         dim3 grid((unsigned)min((long)fd_cdiv(nvec, 256), 148L * 16), B);
-        gn_silu_add_kernel<T><<<grid, 256, 0, stream>>>((const T*)y, sums, gamma, beta, (const T*)skip, (T*)out, P, C,
-                                                        G, eps, nvec);
+        gn_silu_add_kernel<T><<<grid, 256, 0, stream>>>((const T*)y, sums, gamma, beta, nullptr, nullptr, 0, (const T*)skip,
+                                                        (T*)out, P, C, G, eps, nvec);
+    });
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
+// lucidrains Block with the time-embedding scale/shift (src/denoising_diffusion_pytorch.py:183-199):
+//   out = silu( GN(y) * (scale[b] + 1) + shift[b] ) + skip        scale/shift: fp32, element (b, c) at [b*ss_stride + c]
+extern "C" int fd_gn_scale_shift_silu(const void* y, const float* sums, const float* gamma, const float* beta,
+                                      const float* scale, const float* shift, int ss_stride, const void* skip, void* out, int B,
+                                      int P, int C, int G, float eps, int dtype, cudaStream_t stream) {
+    if (!y || !sums || !gamma || !beta || !scale || !shift || !out || B <= 0 || P <= 0 || C <= 0 || G <= 0 || C % G || ss_stride < C)
+        return FD_ERR_BAD_ARGUMENT;
+    FD_DISPATCH_DTYPE(dtype, T, {
+        constexpr int VEC = fd_vec<T>::N;
+        if ((C / G) % VEC) return FD_ERR_UNSUPPORTED;
+        const long nvec = (long)P * C / VEC;
+        dim3 grid((unsigned)min((long)fd_cdiv(nvec, 256), 148L * 16), B);
+        gn_silu_add_kernel<T><<<grid, 256, 0, stream>>>((const T*)y, sums, gamma, beta, scale, shift, ss_stride, (const T*)skip,
+                                                        (T*)out, P, C, G, eps, nvec);
     });
     FD_LAUNCH_CHECK();
     return 0;

@@ -288,6 +288,21 @@ def gn_silu_add(y, sums, gamma, beta, skip, out, B, P, C, G, eps=1e-5):
                                          float(eps), dtype_code(y.dtype), _stream()), "fd_gn_silu_add")
 
 
+def gn_scale_shift_silu(y, sums, gamma, beta, scale, shift, ss_stride, skip, out, B, P, C, G, eps=1e-5):
+    """lucidrains Block with time scale/shift (src/denoising_diffusion_pytorch.py:183-199)."""
+    with _launched("gn_scale_shift_silu", f"{B}x{P}x{C}"):
+        check(_lib.load().fd_gn_scale_shift_silu(_p(y), _f32(sums), _f32(gamma), _f32(beta), _f32(scale), _f32(shift), ss_stride,
+                                                 _p(skip), _p(out), B, P, C, G, float(eps), dtype_code(y.dtype), _stream()),
+              "fd_gn_scale_shift_silu")
+
+
+def flash_attn_d32(qkv, out, B, N, heads, scale):
+    """lucidrains bottleneck Attention (src/denoising_diffusion_pytorch.py:257-279); qkv (B,N,3*heads*32), out (B,N,heads*32)."""
+    with _launched("flash_attn_d32", f"{B}x{N}x{heads}"):
+        check(_lib.load().fd_flash_attn_d32(_p(qkv), _p(out), B, N, heads, float(scale), dtype_code(qkv.dtype), _stream()),
+              "fd_flash_attn_d32")
+
+
 def linear_small(x, W, bias, out, *, add=None, act_in=0, act_out=0):
     B, K = x.shape
     N = W.shape[0]

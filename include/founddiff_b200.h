@@ -180,6 +180,16 @@ int fd_gn_stats(const void* y, float* sums, int B, int P, int C, int G, int dtyp
 int fd_gn_silu_add(const void* y, const float* sums, const float* gamma, const float* beta, const void* skip,
                    void* out, int B, int P, int C, int G, float eps, int dtype, cudaStream_t stream);
 
+/* Secondary path (lucidrains Unet, src/denoising_diffusion_pytorch.py): Block with the time-embedding scale/shift
+ * (:183-199, 201-225): out = silu(GN(y) * (scale[b]+1) + shift[b]) + skip; scale/shift fp32 at [b*ss_stride + c]. */
+int fd_gn_scale_shift_silu(const void* y, const float* sums, const float* gamma, const float* beta, const float* scale,
+                           const float* shift, int ss_stride, const void* skip, void* out, int B, int P, int C, int G,
+                           float eps, int dtype, cudaStream_t stream);
+/* Secondary path: bottleneck Attention (:257-279), heads of 32 channels over N = H*W tokens, flash-style:
+ * out[b, i, h*32 + d] = sum_j softmax_j(scale * q_i . k_j) v_j[d];  qkv (B, N, 3*heads*32) = [q | k | v] channels-last
+ * ('b (h c)' order, as produced by the to_qkv 1x1 GEMM); out (B, N, heads*32).  dtype bf16 / fp16. */
+int fd_flash_attn_d32(const void* qkv, void* out, int B, int N, int heads, float scale, int dtype, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Small dense layers on (B, K) fp32 vectors: time_mlp, adaLN_modulation (src/DADiff.py:173-185, 463-466,
  * 580-585).  out[b, n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] ) + add[b,n]

@@ -471,3 +471,45 @@ def test_scan_merge_fused_and_ln_gate(ops, cfg, dt):
     out = torch.empty(B, H * W, Dg, device="cuda", dtype=dt)
     ops.ln_gate(y, xz.reshape(B, H * W, 2 * Dg).to("cuda", dt), 2 * Dg, Dg, gamma.cuda(), beta.cuda(), local.cuda(), out, B, H * W, Dg)
     assert rel(out.reshape(B, H, W, Dg), ref) < TOL[dt]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Secondary path kernels (lucidrains Unet, src/denoising_diffusion_pytorch.py)
+@pytest.mark.parametrize("dt", DTYPES)
+def test_gn_scale_shift_silu(ops, dt):
+    """Block.forward with scale_shift (:183-199) + the ResnetBlock skip (:225)."""
+    B, C, H, W = 2, 128, 12, 20
+    P = H * W
+    g = torch.Generator().manual_seed(7)
+    y = q(torch.randn(B, C, H, W, generator=g) * 2 + 0.3, dt)
+    skip = q(torch.randn(B, C, H, W, generator=g), dt)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ss = torch.randn(B, 2 * C, generator=g)                       # mlp(time_emb).chunk(2): scale | shift
+    scale, shift = ss[:, :C], ss[:, C:]
+    ref = F.silu(F.group_norm(y, 8, gamma, beta, eps=1e-5) * (scale[:, :, None, None] + 1) + shift[:, :, None, None]) + skip
+    sums = torch.zeros(B, 8, 2, device="cuda")
+    yd = nhwc(y, dt)
+    ops.gn_stats(yd, sums, B, P, C, 8)
+    out = torch.empty_like(yd)
+    from founddiff_b200.engine import _view_ptr
+    ssd = ss.cuda()
+    ops.gn_scale_shift_silu(yd, sums, gamma.cuda(), beta.cuda(), _view_ptr(ssd[:, :C]), _view_ptr(ssd[:, C:]), 2 * C, nhwc(skip, dt),
+                            out, B, P, C, 8)
+    assert rel(nchw(out, H, W), ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("cfg", [(2, 4, 1024), (1, 4, 4096), (2, 2, 200), (1, 1, 64)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_flash_attention_d32(ops, cfg, dt):
+    """Attention.forward between to_qkv and to_out (:266-277): softmax(q^T k * 32^-0.5) v per head."""
+    B, heads, N = cfg
+    HC = heads * 32
+    g = torch.Generator().manual_seed(N + heads)
+    qkv = q(torch.randn(B, N, 3 * HC, generator=g), dt)
+    qq, kk, vv = [t.reshape(B, N, heads, 32).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=-1)]      # (B, h, N, d)
+    attn = ((qq * 32 ** -0.5) @ kk.transpose(-2, -1)).softmax(dim=-1)
+    ref = (attn @ vv).permute(0, 2, 1, 3).reshape(B, N, HC)
+    out = torch.zeros(B, N, HC, device="cuda", dtype=dt)
+    ops.flash_attn_d32(qkv.to("cuda", dt), out, B, N, heads, 32 ** -0.5)
+    # P is rounded to the storage type before the P.V tensor-core product
+    assert rel(out, ref) < (1e-2 if dt == torch.bfloat16 else 2e-3)
