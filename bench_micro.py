@@ -166,6 +166,16 @@ def main():
             out = torch.empty(B, N, 128, device="cuda", dtype=dt)
             ms = timeit(lambda: ops.flash_attn_d32(qkv, out, B, N, 4, 32 ** -0.5), args.iters)
             report("flash_attn_d32", f"{B}x{N}x4x32", ms, 4.0 * B * N * 128 * es, 4.0 * B * 4 * N * N * 32)
+    if args.only in ("", "linattn"):
+        # lucidrains LinearAttention (4 heads x 32) at the 256^2 and 512^2 feature maps of the first level (dim 64)
+        for H in sel([256, 512]):
+            qkv = rn(B, H * H, 3 * 128)
+            wout, bias, gam = rn(64, 128, d=torch.float32) * 0.1, rn(64, d=torch.float32), rn(64, d=torch.float32)
+            out = torch.empty(B, H * H, 64, device="cuda", dtype=dt)
+            ms = timeit(lambda: ops.linear_attention(qkv, wout, bias, gam, out, B, H, H, 4, 64), max(2, args.iters // 3))
+            report("linear_attention", f"{B}x{H}x{H} 4x32->64", ms, B * H * H * (2 * 256 + 128 + 128 + 2 * 64 + 2 * 64 + 128) * es / 1.0,
+                   2.0 * B * H * H * (128 * 32 + 128 * 64))
+            del qkv, out
     if args.json:
         os.makedirs(os.path.dirname(os.path.abspath(args.json)), exist_ok=True)
         json.dump(dict(batch=B, dtype=args.dtype, hbm_peak_gbs=hbm, rows=rows), open(args.json, "w"), indent=1)

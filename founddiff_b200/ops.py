@@ -303,6 +303,30 @@ def flash_attn_d32(qkv, out, B, N, heads, scale):
               "fd_flash_attn_d32")
 
 
+def linear_attention(qkv, wout, bias, g, out, B, H, W, heads, dim, scale=32 ** -0.5, prefer_tc=True):
+    """lucidrains LinearAttention between to_qkv and the end of to_out (src/denoising_diffusion_pytorch.py:238-255):
+    qkv (B, H*W, 3*heads*32) -> out (B, H*W, dim) = LayerNorm_c(Conv1x1(linear-attention(q, k, v)) + bias) * g."""
+    lib = _lib.load()
+    N, HC, dev, dt = H * W, heads * 32, qkv.device, qkv.dtype
+    kmax = torch.full((B, HC), float("-inf"), device=dev)
+    ksum = torch.zeros(B, HC, device=dev)
+    ctx = torch.zeros(B, heads, 32, 32, device=dev)
+    with _launched("linattn_context", f"{B}x{N}x{heads}", 2):
+        check(lib.fd_linattn_context(_p(qkv), _f32(kmax), _f32(ksum), _f32(ctx), B, N, heads, dtype_code(dt), _stream()), "fd_linattn_context")
+    weff = torch.empty(B, dim, HC, device=dev, dtype=dt)
+    with _launched("linattn_weff", f"{B}x{dim}"):
+        check(lib.fd_linattn_weff(_f32(ctx), _f32(ksum), _f32(wout), _p(weff), B, N, heads, dim, float(scale), dtype_code(dt), _stream()),
+              "fd_linattn_weff")
+    qhat = torch.empty(B, N, HC, device=dev, dtype=dt)
+    with _launched("softmax_d32", f"{B}x{N}x{heads}"):
+        check(lib.fd_softmax_d32(_p(qkv), _p(qhat), B, N, heads, dtype_code(dt), _stream()), "fd_softmax_d32")
+    y = torch.empty(B, N, dim, device=dev, dtype=dt)
+    Conv(qhat, weff, y, B=B, Hin=H, Win=W, bias=bias, per_batch_weight=True, prefer_tc=prefer_tc).run()
+    zeros = torch.zeros(B, dim, device=dev)
+    ln_modulate(y, out, g, torch.zeros_like(g), zeros, zeros, dim, B, N, dim, 1e-5)
+    return out
+
+
 def linear_small(x, W, bias, out, *, add=None, act_in=0, act_out=0):
     B, K = x.shape
     N = W.shape[0]

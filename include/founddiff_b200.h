@@ -190,6 +190,20 @@ int fd_gn_scale_shift_silu(const void* y, const float* sums, const float* gamma,
  * ('b (h c)' order, as produced by the to_qkv 1x1 GEMM); out (B, N, heads*32).  dtype bf16 / fp16. */
 int fd_flash_attn_d32(const void* qkv, void* out, int B, int N, int heads, float scale, int dtype, cudaStream_t stream);
 
+/* Secondary path: LinearAttention (:227-255) between to_qkv and to_out, same qkv layout as above.
+ *   fd_linattn_context: ctx_raw[b,h,d,e] += sum_n exp(k[n,d] - kmax[d]) v[n,e];  ksum[b,hd] += sum_n exp(k - kmax)
+ *                       (kmax pre-filled with -inf and ksum / ctx_raw with 0 by the caller; two launches: column max, then
+ *                       the tensor-core accumulation);
+ *   fd_linattn_weff:    weff[b,o,h*32+d] = scale/(N*ksum[d]) * sum_e wout[o,h*32+e] ctx_raw[b,h,d,e], so that
+ *                       to_out.0(out) == softmax_d(q) @ weff[b]^T + bias (a per-sample 1x1 GEMM, fd_conv2d_*);
+ *   fd_softmax_d32:     qhat (B,N,heads*32) = softmax over each head's 32 channels of q.
+ * The channel LayerNorm of to_out.1 is fd_ln_modulate with zero shift/scale. */
+int fd_linattn_context(const void* qkv, float* kmax, float* ksum, float* ctx_raw, int B, int N, int heads, int dtype,
+                       cudaStream_t stream);
+int fd_linattn_weff(const float* ctx_raw, const float* ksum, const float* wout, void* weff, int B, int N, int heads, int dim,
+                    float scale, int dtype, cudaStream_t stream);
+int fd_softmax_d32(const void* qkv, void* qhat, int B, int N, int heads, int dtype, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Small dense layers on (B, K) fp32 vectors: time_mlp, adaLN_modulation (src/DADiff.py:173-185, 463-466,
  * 580-585).  out[b, n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] ) + add[b,n]

@@ -513,3 +513,26 @@ def test_flash_attention_d32(ops, cfg, dt):
     ops.flash_attn_d32(qkv.to("cuda", dt), out, B, N, heads, 32 ** -0.5)
     # P is rounded to the storage type before the P.V tensor-core product
     assert rel(out, ref) < (1e-2 if dt == torch.bfloat16 else 2e-3)
+
+
+@pytest.mark.parametrize("cfg", [(2, 64, 32, 32), (1, 128, 64, 48), (2, 64, 16, 16)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_linear_attention(ops, cfg, dt):
+    """LinearAttention.forward after to_qkv (:238-255): softmax_d(q)*scale, softmax_n(k), v/N, context, out, to_out conv + LayerNorm."""
+    B, dim, H, W = cfg
+    heads, HC, N = 4, 128, H * W
+    g = torch.Generator().manual_seed(dim + H)
+    qkv = q(torch.randn(B, 3 * HC, H, W, generator=g), dt)
+    wout = torch.randn(dim, HC, generator=g) / math.sqrt(HC)
+    bias, gam = torch.randn(dim, generator=g), torch.randn(dim, generator=g)
+    qq, kk, vv = [t.reshape(B, heads, 32, N) for t in qkv.chunk(3, dim=1)]
+    qs = qq.softmax(dim=-2) * 32 ** -0.5
+    ks = kk.softmax(dim=-1)
+    ctx = torch.einsum("bhdn,bhen->bhde", ks, vv / N)
+    o = torch.einsum("bhde,bhdn->bhen", ctx, qs).reshape(B, HC, H, W)
+    y = F.conv2d(o, wout.reshape(dim, HC, 1, 1), bias)
+    var, mean = torch.var(y, dim=1, unbiased=False, keepdim=True), torch.mean(y, dim=1, keepdim=True)
+    ref = (y - mean) * (var + 1e-5).rsqrt() * gam.reshape(1, dim, 1, 1)
+    out = torch.empty(B, N, dim, device="cuda", dtype=dt)
+    ops.linear_attention(nhwc(qkv, dt), wout.cuda(), bias.cuda(), gam.cuda(), out, B, H, W, heads, dim)
+    assert rel(nchw(out, H, W), ref) < (2e-2 if dt == torch.bfloat16 else 4e-3)
