@@ -35,6 +35,35 @@ extern "C" int fd_unnormalize(const float* x, float* out, long n, cudaStream_t s
     return 0;
 }
 
+// Secondary path: epsilon-prediction GaussianDiffusion update (src/denoising_diffusion_pytorch.py:556-576 model_predictions,
+// :547-554 q_posterior, :588-595 p_sample, :612-646 ddim_sample) as one fused elementwise kernel:
+//   x0     = sr * x_t - srm1 * eps            (predict_start_from_noise);  clipped to [-1, 1] when coef[6] != 0
+//   x_next = a0 * x0 + a1 * x_t + a2 * eps + a3 * noise
+// coef (DEVICE fp32[8]) = {sr, srm1, a0, a1, a2, a3, clip, 0}:  ancestral {.., c1[t], c2[t], 0, exp(.5 logvar[t]) | 0};
+// DDIM {.., sqrt(abar_next), 0, c, sigma};  last DDIM pair {.., 1, 0, 0, 0}.
+__global__ void ddpm_update_kernel(const float* __restrict__ x_t, const float* __restrict__ eps, const float* __restrict__ noise,
+                                   const float* __restrict__ coef, float* __restrict__ x_next, float* __restrict__ x_start, long n) {
+    const float sr = coef[0], srm1 = coef[1], a0 = coef[2], a1 = coef[3], a2 = coef[4], a3 = coef[5];
+    const bool clip = coef[6] != 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float xt = x_t[i], e = eps[i];
+        float x0 = sr * xt - srm1 * e;
+        if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+        if (x_start) x_start[i] = x0;
+        float xn = a0 * x0 + a1 * xt + a2 * e;
+        if (noise) xn += a3 * noise[i];
+        x_next[i] = xn;
+    }
+}
+
+extern "C" int fd_ddpm_update(const float* x_t, const float* eps, const float* noise, const float* coef, float* x_next,
+                              float* x_start, long n, cudaStream_t stream) {
+    if (!x_t || !eps || !coef || !x_next || n <= 0) return FD_ERR_BAD_ARGUMENT;
+    ddpm_update_kernel<<<(unsigned)min((long)fd_cdiv(n, 256), 148L * 8), 256, 0, stream>>>(x_t, eps, noise, coef, x_next, x_start, n);
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
 // One pixel per LPP lanes; each lane reads one 16-byte vector of the C-channel feature row.
 template <typename T>
 __global__ void __launch_bounds__(256) final_conv_update_kernel(

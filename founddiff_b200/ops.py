@@ -360,3 +360,10 @@ def final_conv_update(feat, w, bias, x_input, x_t, noise, coef, x_next, pred_res
 def unnormalize(x, out):
     with _launched("unnormalize", "", 1):
         check(_lib.load().fd_unnormalize(_f32(x), _f32(out), x.numel(), _stream()), "fd_unnormalize")
+
+
+def ddpm_update(x_t, eps, noise, coef, x_next, x_start=None):
+    """lucidrains GaussianDiffusion p_sample / ddim_sample update (src/denoising_diffusion_pytorch.py:588-595, 612-646)."""
+    with _launched("ddpm_update", ""):
+        check(_lib.load().fd_ddpm_update(_f32(x_t), _f32(eps), _f32(noise), _f32(coef), _f32(x_next), _f32(x_start), x_t.numel(),
+                                         _stream()), "fd_ddpm_update")

@@ -234,6 +234,11 @@ int fd_final_conv_update(const void* feat, const float* w, const float* bias, co
                          const float* x_t, const float* noise, const float* coef, float* x_next, float* pred_res,
                          float* pred_noise, float* x_start, long npix, int C, int dtype, cudaStream_t stream);
 int fd_unnormalize(const float* x, float* out, long n, cudaStream_t stream);
+/* Secondary path: epsilon-prediction GaussianDiffusion update (src/denoising_diffusion_pytorch.py:547-576, 588-595,
+ * 612-646), fused: x0 = sr*x_t - srm1*eps (clipped to [-1,1] if coef[6]); x_next = a0*x0 + a1*x_t + a2*eps + a3*noise;
+ * coef (DEVICE fp32[8]) = {sr, srm1, a0, a1, a2, a3, clip, 0}. */
+int fd_ddpm_update(const float* x_t, const float* eps, const float* noise, const float* coef, float* x_next, float* x_start,
+                   long n, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

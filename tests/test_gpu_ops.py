@@ -536,3 +536,33 @@ def test_linear_attention(ops, cfg, dt):
     out = torch.empty(B, N, dim, device="cuda", dtype=dt)
     ops.linear_attention(nhwc(qkv, dt), wout.cuda(), bias.cuda(), gam.cuda(), out, B, H, W, heads, dim)
     assert rel(nchw(out, H, W), ref) < (2e-2 if dt == torch.bfloat16 else 4e-3)
+
+
+def test_ddpm_update_matches_gaussian_diffusion_formulas(ops):
+    """p_sample (:588-595) and one DDIM step (:629-642) of the epsilon-prediction GaussianDiffusion, cosine schedule."""
+    T = 1000
+    steps = T + 1
+    x = torch.linspace(0, T, steps, dtype=torch.float64)
+    ac = torch.cos(((x / T) + 0.008) / 1.008 * math.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
+    alphas = 1. - betas
+    abar = torch.cumprod(alphas, dim=0)
+    abar_prev = F.pad(abar[:-1], (1, 0), value=1.)
+    pv = betas * (1. - abar_prev) / (1. - abar)
+    c1 = betas * torch.sqrt(abar_prev) / (1. - abar)
+    c2 = (1. - abar_prev) * torch.sqrt(alphas) / (1. - abar)
+    g = torch.Generator().manual_seed(3)
+    xt, eps, nz = (torch.randn(2, 4096, generator=g) for _ in range(3))
+    t, tn = 700, 500
+    sr, srm1 = float(torch.sqrt(1. / abar[t])), float(torch.sqrt(1. / abar[t] - 1))
+    x0 = (sr * xt - srm1 * eps).clamp(-1, 1)
+    ref_anc = float(c1[t]) * x0 + float(c2[t]) * xt + float((0.5 * torch.log(pv[t].clamp(min=1e-20))).exp()) * nz
+    ref_ddim = x0 * float(abar[tn].sqrt()) + float((1 - abar[tn]).sqrt()) * eps       # eta = 0
+    out, xs = torch.empty(2, 4096, device="cuda"), torch.empty(2, 4096, device="cuda")
+    coef = torch.tensor([sr, srm1, float(c1[t]), float(c2[t]), 0., float((0.5 * torch.log(pv[t].clamp(min=1e-20))).exp()), 1., 0.])
+    ops.ddpm_update(xt.cuda(), eps.cuda(), nz.cuda(), coef.cuda(), out, xs)
+    assert rel(out, ref_anc) < 1e-6 and rel(xs, x0) < 1e-6
+    coef = torch.tensor([sr, srm1, float(abar[tn].sqrt()), 0., float((1 - abar[tn]).sqrt()), 0., 1., 0.])
+    ops.ddpm_update(xt.cuda(), eps.cuda(), None, coef.cuda(), out)
+    assert rel(out, ref_ddim) < 1e-6
