@@ -136,19 +136,21 @@ template <typename T> FD_DEVINL void dw_st(T* p, const float (&v)[4]) {
     *reinterpret_cast<uint2*>(p) = r;
 }
 
+// A thread owns TWO horizontally adjacent pixels x 4 channels: the 4 input vectors x-1 .. x+2 of a row feed both
+// (2 loads + 2 conversions per output instead of 3), weights in registers, 3-row software-pipelined ring.
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(256, 2) dwconv3x3_nhwc_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, T* __restrict__ out, int H,
                                                                 int W, int C) {
     const int NV = C / DW_V;                            // vectors per pixel
     const long rowv = (long)W * NV;                     // vectors per image row
-    const long f = (long)blockIdx.x * 256 + threadIdx.x;
-    if (f >= rowv) return;
-    const int cv = (int)(f % NV), x = (int)(f / NV);
+    const int W2 = (W + 1) / 2;
+    const long f2 = (long)blockIdx.x * 256 + threadIdx.x;   // index over (pixel pair, vector)
+    if (f2 >= (long)W2 * NV) return;
+    const int cv = (int)(f2 % NV), x = 2 * (int)(f2 / NV);
+    const long f = (long)x * NV + cv;                   // vector index of the left pixel within a row
     const int b = blockIdx.z;
     const int y0 = blockIdx.y * DW_RY, y1 = min(H, y0 + DW_RY);
-    // weights are tap-major (9, C) so that a warp's loads are contiguous 16-byte vectors (the (C, 9) layout made the
-    // 36 scalar weight loads cost as many L2 sectors as the whole data stream of the block)
     float wr[9][DW_V], bs[DW_V];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
@@ -161,57 +163,75 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_nhwc_kernel(const T* __restr
     } else {
         bs[0] = bs[1] = bs[2] = bs[3] = 0.f;
     }
-    const bool has_l = x > 0, has_r = x + 1 < W;
+    const bool has_l = x > 0, has_1 = x + 1 < W, has_2 = x + 2 < W;
     const T* base = in + (long)b * H * rowv * DW_V;
     T* obase = out + (long)b * H * rowv * DW_V;
-    float acc[3][DW_V];
+    float acc[3][2][DW_V];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int e = 0; e < DW_V; ++e) acc[r][e] = bs[e];
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int e = 0; e < DW_V; ++e) acc[r][px][e] = bs[e];
 
-    // software pipeline: raw vectors of input rows yi, yi+1, yi+2 are in flight (ring slot = row mod 3)
-    uint2 ring[3][3];
+    // Loads are UNCONDITIONAL (clamped addresses) and masked when consumed three rows later: a predicated load followed by
+    // a select makes ptxas wait for the load right away, which serialises the whole prefetch ring on DRAM latency.
+    const long offl = has_l ? (long)NV * DW_V : 0, off1 = has_1 ? (long)NV * DW_V : 0, off2 = has_2 ? 2L * NV * DW_V : 0;
+    const int ymax = min(H - 1, y1);
+    uint2 ring[3][4];                                   // raw vectors x-1, x, x+1, x+2 of input rows yi, yi+1, yi+2
     auto fetch = [&](int yr, auto slot_c) {
         constexpr int S = decltype(slot_c)::value;
-        ring[S][0] = ring[S][1] = ring[S][2] = make_uint2(0u, 0u);
-        if (yr >= 0 && yr < H && yr <= y1) {
-            const T* rp = base + ((long)yr * rowv + f) * DW_V;
-            if (has_l) ring[S][0] = dw_ld_raw<T>(rp - (long)NV * DW_V);
-            ring[S][1] = dw_ld_raw<T>(rp);
-            if (has_r) ring[S][2] = dw_ld_raw<T>(rp + (long)NV * DW_V);
-        }
+        const T* rp = base + ((long)min(max(yr, 0), ymax) * rowv + f) * DW_V;
+        ring[S][0] = dw_ld_raw<T>(rp - offl);
+        ring[S][1] = dw_ld_raw<T>(rp);
+        ring[S][2] = dw_ld_raw<T>(rp + off1);
+        ring[S][3] = dw_ld_raw<T>(rp + off2);
     };
     // input row `yi` contributes to output rows yi+1 (tap row 0), yi (1), yi-1 (2); accumulator slot = output row mod 3
     auto step = [&](int yi, auto slot_c) {
         constexpr int S = decltype(slot_c)::value;      // == yi mod 3 (compile-time so that acc[] / ring[] stay in registers)
-        float v[3][DW_V];
+        float v[4][DW_V];
+        {
+            const bool rv = yi >= 0 && yi < H;
+            const bool ok[4] = {rv && has_l, rv, rv && has_1, rv && has_2};
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) dw_cvt<T>(ring[S][dx], v[dx]);
+            for (int j = 0; j < 4; ++j) {
+                uint2 r = ring[S][j];
+                r.x = ok[j] ? r.x : 0u;
+                r.y = ok[j] ? r.y : 0u;
+                dw_cvt<T>(r, v[j]);
+            }
+        }
         fetch(yi + 3, slot_c);
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
+        for (int px = 0; px < 2; ++px)
 #pragma unroll
-            for (int e = 0; e < DW_V; ++e) {
-                acc[(S + 1) % 3][e] = fmaf(v[dx][e], wr[0 * 3 + dx][e], acc[(S + 1) % 3][e]);   // output row yi+1
-                acc[S][e] = fmaf(v[dx][e], wr[1 * 3 + dx][e], acc[S][e]);                       // output row yi
-                acc[(S + 2) % 3][e] = fmaf(v[dx][e], wr[2 * 3 + dx][e], acc[(S + 2) % 3][e]);   // output row yi-1
-            }
+            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int e = 0; e < DW_V; ++e) {
+                    const float xv = v[px + dx][e];
+                    acc[(S + 1) % 3][px][e] = fmaf(xv, wr[0 * 3 + dx][e], acc[(S + 1) % 3][px][e]);   // output row yi+1
+                    acc[S][px][e] = fmaf(xv, wr[1 * 3 + dx][e], acc[S][px][e]);                       // output row yi
+                    acc[(S + 2) % 3][px][e] = fmaf(xv, wr[2 * 3 + dx][e], acc[(S + 2) % 3][px][e]);   // output row yi-1
+                }
         const int yo = yi - 1;                          // output row yi-1 is complete (slot (S+2)%3)
         if (yo >= y0 && yo < y1) {
-            float o[DW_V];
 #pragma unroll
-            for (int e = 0; e < DW_V; ++e) o[e] = SILU ? fd_silu(acc[(S + 2) % 3][e]) : acc[(S + 2) % 3][e];
-            dw_st<T>(obase + ((long)yo * rowv + f) * DW_V, o);
+            for (int px = 0; px < 2; ++px) {
+                if (px == 1 && !has_1) continue;
+                float o[DW_V];
+#pragma unroll
+                for (int e = 0; e < DW_V; ++e) o[e] = SILU ? fd_silu(acc[(S + 2) % 3][px][e]) : acc[(S + 2) % 3][px][e];
+                dw_st<T>(obase + ((long)yo * rowv + f + (long)px * NV) * DW_V, o);
+            }
         }
 #pragma unroll
-        for (int e = 0; e < DW_V; ++e) acc[(S + 2) % 3][e] = bs[e];
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int e = 0; e < DW_V; ++e) acc[(S + 2) % 3][px][e] = bs[e];
     };
-    // rows ya .. y1 (inclusive) with ya = the multiple of 3 at or below y0-1: rows before y0-1 are never fetched into
-    // the window as real data?  They are: so start exactly at a multiple of 3 and let the (cheap) extra rows run —
-    // their contributions land in accumulators that are reset before the first real output row is emitted.
     int yi = y0 - 1;
-    yi -= ((yi % 3) + 3) % 3;                            // round down to a multiple of 3 (may be < y0-1, even < 0)
+    yi -= ((yi % 3) + 3) % 3;                            // round down to a multiple of 3 (extra rows only touch accumulators that are reset)
     fetch(yi, std::integral_constant<int, 0>{});
     fetch(yi + 1, std::integral_constant<int, 1>{});
     fetch(yi + 2, std::integral_constant<int, 2>{});
@@ -400,8 +420,8 @@ extern "C" int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, f
 template <typename T>
 static int dwconv_nhwc_launch(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int C, int silu,
                               cudaStream_t stream) {
-    const long rowv = (long)W * (C / DW_V);
-    dim3 grid((unsigned)fd_cdiv(rowv, 256), (unsigned)fd_cdiv(H, DW_RY), (unsigned)B);
+    const long pairs = (long)((W + 1) / 2) * (C / DW_V);
+    dim3 grid((unsigned)fd_cdiv(pairs, 256), (unsigned)fd_cdiv(H, DW_RY), (unsigned)B);
     if (silu) dwconv3x3_nhwc_kernel<T, true><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
     else dwconv3x3_nhwc_kernel<T, false><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
     FD_LAUNCH_CHECK();
