@@ -72,7 +72,8 @@ template <> FD_DEVINL void fd_stv<__half, 8>(__half* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = t;
 }
 
-FD_DEVINL float fd_silu(float x) { return x / (1.f + __expf(-x)); }
+// MUFU.EX2 + MUFU.RCP, no IEEE-division slow path (FCHK + branch): the full-precision divide cost ~2x the instructions
+FD_DEVINL float fd_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 FD_DEVINL float fd_softplus20(float x) { return x <= 20.f ? log1pf(__expf(x)) : x; }
 
 FD_DEVINL float fd_warp_sum(float v) {

@@ -104,6 +104,166 @@ __global__ void __launch_bounds__(256) dwconv_scan_kernel(const T* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// 16-bit storage types: register sliding-window formulation of the same op.  A block owns a 32x32-pixel x 32-channel
+// tile; a thread owns a horizontal pixel PAIR x 4 channels and walks down the rows with a 3-row prefetch ring of raw
+// 8-byte vectors (loads are unconditional on clamped addresses and masked when consumed, so they stay in flight),
+// weights in registers.  Finished SiLU outputs go to a shared-memory tile already in scan order
+// [channel][k][run][16 l] (run stride 9 words, channel stride 577 words: bank-conflict-free for both the row-major
+// and the column-major directions); the tile is then written as 32-byte runs along l.
+constexpr int RW_TS = 32, RW_CH = 32, RW_V = 4;
+constexpr int RW_RUN = 18;                      // elements per padded run (16 + 2)
+constexpr int RW_KST = 16 * RW_RUN;             // elements per direction k
+constexpr int RW_CST = 4 * RW_KST + 2;          // elements per channel (577 words)
+
+template <typename T> FD_DEVINL uint2 rw_ld_raw(const T* p) { return *reinterpret_cast<const uint2*>(p); }
+template <typename T> FD_DEVINL void rw_cvt(uint2 r, float (&v)[4]) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+        const float2 a = __half22float2(*reinterpret_cast<__half2*>(&r.x));
+        const float2 b = __half22float2(*reinterpret_cast<__half2*>(&r.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128, 3) dwconv_scan_rw_kernel(const T* __restrict__ xz, int ld, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, T* __restrict__ xs, int H,
+                                                                int W, int D, int word_ok) {
+    static_assert(sizeof(T) == 2, "16-bit storage only");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_out = reinterpret_cast<T*>(smem_raw);                              // [RW_CH][RW_CST]
+    float* s_w = reinterpret_cast<float*>(s_out + RW_CH * RW_CST);          // [RW_CH*9] + [RW_CH]
+
+    const int c0 = blockIdx.x * RW_CH;
+    const int tiles_w = (W + RW_TS - 1) / RW_TS;
+    const int ty0 = (blockIdx.y / tiles_w) * RW_TS, tx0 = (blockIdx.y % tiles_w) * RW_TS;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int cv = tid % (RW_CH / RW_V), pr = tid / (RW_CH / RW_V);         // channel vector, pixel pair
+    const int x = tx0 + 2 * pr;
+
+    for (int i = tid; i < RW_CH * 10; i += 128)
+        s_w[i] = i < RW_CH * 9 ? w[(long)c0 * 9 + i] : (bias ? bias[c0 + i - RW_CH * 9] : 0.f);
+    __syncthreads();
+    float wr[9][RW_V], bs[RW_V];
+#pragma unroll
+    for (int e = 0; e < RW_V; ++e) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wr[t][e] = s_w[(cv * RW_V + e) * 9 + t];
+        bs[e] = s_w[RW_CH * 9 + cv * RW_V + e];
+    }
+
+    const int y0 = ty0, y1 = min(H, ty0 + RW_TS);
+    const bool has_0 = x < W, has_l = has_0 && x > 0, has_1 = x + 1 < W, has_2 = x + 2 < W;
+    const int xc = min(x, W - 1);
+    const T* base = xz + (long)b * H * W * ld + c0 + cv * RW_V;
+    const long offl = has_l ? (long)ld : 0, off1 = has_1 ? (long)ld : 0, off2 = has_2 ? 2L * ld : 0;
+    const int ymax = min(H - 1, y1);
+    float acc[3][2][RW_V];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int e = 0; e < RW_V; ++e) acc[r][px][e] = bs[e];
+    uint2 ring[3][4];
+    auto fetch = [&](int yr, auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;
+        const T* rp = base + ((long)min(max(yr, 0), ymax) * W + xc) * ld;
+        ring[S][0] = rw_ld_raw<T>(rp - offl);
+        ring[S][1] = rw_ld_raw<T>(rp);
+        ring[S][2] = rw_ld_raw<T>(rp + off1);
+        ring[S][3] = rw_ld_raw<T>(rp + off2);
+    };
+    T* s_thr = s_out + cv * RW_V * RW_CST;
+    auto step = [&](int yi, auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;
+        float v[4][RW_V];
+        {
+            const bool rv = yi >= 0 && yi < H;
+            const bool ok[4] = {rv && has_l, rv && has_0, rv && has_1, rv && has_2};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint2 r = ring[S][j];
+                r.x = ok[j] ? r.x : 0u;
+                r.y = ok[j] ? r.y : 0u;
+                rw_cvt<T>(r, v[j]);
+            }
+        }
+        fetch(yi + 3, slot_c);
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int e = 0; e < RW_V; ++e) {
+                    const float xv = v[px + dx][e];
+                    acc[(S + 1) % 3][px][e] = fmaf(xv, wr[0 * 3 + dx][e], acc[(S + 1) % 3][px][e]);
+                    acc[S][px][e] = fmaf(xv, wr[1 * 3 + dx][e], acc[S][px][e]);
+                    acc[(S + 2) % 3][px][e] = fmaf(xv, wr[2 * 3 + dx][e], acc[(S + 2) % 3][px][e]);
+                }
+        const int yo = yi - 1;
+        if (yo >= y0 && yo < y1) {
+            const int py = yo - y0;
+            // even rows: run = py/2, position = pair; odd rows (column-major directions): run = pair, position = py/2
+            const int off = (py & 1) ? (RW_KST + pr * RW_RUN + (py >> 1)) : ((py >> 1) * RW_RUN + pr);
+#pragma unroll
+            for (int px = 0; px < 2; ++px)
+#pragma unroll
+                for (int e = 0; e < RW_V; ++e)
+                    fd_st(s_thr + e * RW_CST + px * 2 * RW_KST + off, fd_silu(acc[(S + 2) % 3][px][e]));
+        }
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int e = 0; e < RW_V; ++e) acc[(S + 2) % 3][px][e] = bs[e];
+    };
+    int yi = y0 - 1;
+    yi -= ((yi % 3) + 3) % 3;
+    fetch(yi, std::integral_constant<int, 0>{});
+    fetch(yi + 1, std::integral_constant<int, 1>{});
+    fetch(yi + 2, std::integral_constant<int, 2>{});
+    for (; yi <= y1; yi += 3) {
+        step(yi, std::integral_constant<int, 0>{});
+        if (yi + 1 <= y1) step(yi + 1, std::integral_constant<int, 1>{});
+        if (yi + 2 <= y1) step(yi + 2, std::integral_constant<int, 2>{});
+    }
+    __syncthreads();
+
+    // write phase: 8 lanes x 4 bytes per 16-element run; iteration `it` covers the 16 runs of one (channel, k)
+    const int H2 = H / 2, W2 = W / 2;
+    const long L = (long)H2 * W2;
+    const int h2_0 = ty0 / 2, w2_0 = tx0 / 2;
+    const int j = tid % 8, r = tid / 8;
+    const uint32_t* s_words = reinterpret_cast<const uint32_t*>(s_out) + r * (RW_RUN / 2) + j;
+    T* gbase = xs + ((long)b * 4 * D + c0) * L + 2 * j;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        long l;
+        int nvalid;
+        bool run_ok;
+        if (k & 1) { run_ok = (w2_0 + r) < W2; l = (long)(w2_0 + r) * H2 + h2_0; nvalid = H2 - h2_0; }
+        else       { run_ok = (h2_0 + r) < H2; l = (long)(h2_0 + r) * W2 + w2_0; nvalid = W2 - w2_0; }
+        if (!run_ok) continue;
+        T* gp = gbase + (long)k * D * L + l;
+        const uint32_t* sp = s_words + k * (RW_KST / 2);
+        if (word_ok && 2 * j + 1 < nvalid) {
+#pragma unroll 8
+            for (int c = 0; c < RW_CH; ++c) *reinterpret_cast<uint32_t*>(gp + c * L) = sp[c * (RW_CST / 2)];
+        } else {
+            for (int c = 0; c < RW_CH; ++c) {
+                const uint32_t wv = sp[c * (RW_CST / 2)];
+                if (2 * j < nvalid) *reinterpret_cast<unsigned short*>(gp + c * L) = (unsigned short)(wv & 0xffffu);
+                if (2 * j + 1 < nvalid) *reinterpret_cast<unsigned short*>(gp + c * L + 1) = (unsigned short)(wv >> 16);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // x_proj + dt_proj.  One thread per l (coalesced along l), CCP >= R+2N accumulators in registers.
 template <typename T, int CCP>
 __global__ void __launch_bounds__(128) xdt_proj_kernel(const T* __restrict__ xs, const float* __restrict__ x_proj_w,
@@ -403,6 +563,30 @@ extern "C" int fd_dwconv3x3_silu_scan(const void* xz, int ld, const float* w, co
                                       int W, int D, int dtype, cudaStream_t stream) {
     if (!xz || !w || !xs || B <= 0 || H <= 0 || W <= 0 || D <= 0 || ld < D) return FD_ERR_BAD_ARGUMENT;
     if ((H & 1) || (W & 1) || D % CH) return FD_ERR_UNSUPPORTED;
+    if (dtype != FD_F32 && D % RW_CH == 0 && ld % RW_V == 0 && ((uintptr_t)xz % 8) == 0 && ((uintptr_t)xs % 4) == 0) {
+        dim3 grid(D / RW_CH, fd_cdiv(H, RW_TS) * fd_cdiv(W, RW_TS), B);
+        const int word_ok = ((H / 2) % 2 == 0) && ((W / 2) % 2 == 0);
+        const size_t smem = (size_t)RW_CH * RW_CST * 2 + RW_CH * 10 * sizeof(float);
+        if (dtype == FD_BF16) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaError_t e = cudaFuncSetAttribute(dwconv_scan_rw_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return (int)e;
+                attr_set = true;
+            }
+            dwconv_scan_rw_kernel<__nv_bfloat16><<<grid, 128, smem, stream>>>((const __nv_bfloat16*)xz, ld, w, bias, (__nv_bfloat16*)xs, H, W, D, word_ok);
+        } else {
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaError_t e = cudaFuncSetAttribute(dwconv_scan_rw_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return (int)e;
+                attr_set = true;
+            }
+            dwconv_scan_rw_kernel<__half><<<grid, 128, smem, stream>>>((const __half*)xz, ld, w, bias, (__half*)xs, H, W, D, word_ok);
+        }
+        FD_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid(D / CH, fd_cdiv(H, TS) * fd_cdiv(W, TS), B);
     FD_DISPATCH_DTYPE(dtype, T, {
         constexpr int VEC = fd_vec<T>::N;

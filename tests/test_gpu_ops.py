@@ -208,7 +208,7 @@ def test_groupnorm_silu_add(ops, C, dt):
     assert rel(nchw(out, H, W), ref - skip) < TOL[dt]
 
 
-@pytest.mark.parametrize("hw", [(16, 24), (32, 32), (8, 12), (64, 32)])
+@pytest.mark.parametrize("hw", [(16, 24), (32, 32), (8, 12), (64, 32), (6, 10), (36, 70)])
 @pytest.mark.parametrize("dt", DTYPES)
 def test_dwconv_scan_and_merge(ops, hw, dt):
     """dwconv+SiLU+EfficientScan and EfficientMerge+LN+gate against the oracle's restatement of
