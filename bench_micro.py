@@ -118,6 +118,10 @@ def main():
             out = torch.empty(B, H * H, D, device="cuda", dtype=dt)
             ms = timeit(lambda: ops.merge_ln_gate(xs, xz, 4 * C, D, gm, bt, loc, stat, out, B, H, H, D), args.iters)
             report("merge_ln_gate", f"{B}x{H}x{H}x{D}", ms, 3.0 * B * H * H * D * es)
+            ynhwc = rn(B, H * H, D)
+            ms = timeit(lambda: ops.ln_gate(ynhwc, xz, 4 * C, 2 * C, gm, bt, loc, out, B, H * H, D), args.iters)
+            report("ln_gate", f"{B}x{H * H}x{D}", ms, 3.0 * B * H * H * D * es)
+            del ynhwc
             del xz, xs, out
     if args.only in ("", "norm"):
         from founddiff_b200.engine import _view_ptr

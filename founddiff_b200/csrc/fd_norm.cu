@@ -1,60 +1,157 @@
 // LayerNorm+modulate, GroupNorm statistics / apply, small dense layers, sinusoidal embedding.
 // All HBM-bound row kernels: 16-byte vector accesses, sub-warp shuffles for the per-row reductions.
+#include <type_traits>
+
 #include "fd_common.cuh"
 
 // ------------------------------------------------------------------------------------------------------
-// LayerNorm over C + adaLN modulate (src/DADiff.py:450-451, 459, 461, 486-487).
-// LPR lanes cooperate on one row; each lane owns NV 16-byte vectors (interleaved: vector j of lane i is
-// vector i + j*LPR of the row) so that a warp's loads are fully coalesced.
+// Row kernels over channels-last data.  LPR lanes cooperate on one row; each lane owns NV 16-byte vectors
+// (interleaved: vector j of lane i is vector i + j*LPR of the row) so that a warp's accesses are fully coalesced.
+// A warp handles U consecutive groups of 32/LPR rows: all U*NV raw vectors are requested before anything is
+// consumed (bytes in flight, not occupancy, carry these kernels), and the per-channel parameters of the lane's
+// columns are fetched once and reused for the U rows while they belong to the same sample.
 // ------------------------------------------------------------------------------------------------------
-template <typename T, int LPR, int NV>
+template <typename T> FD_DEVINL void fd_raw_to_f(const uint4& r, float (&v)[16 / sizeof(T)]) {
+    if constexpr (sizeof(T) == 4) {
+        v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+    } else {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f;
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            else f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+}
+template <typename T> FD_DEVINL uint4 fd_f_to_raw(const float (&v)[16 / sizeof(T)]) {
+    uint4 r;
+    if constexpr (sizeof(T) == 4) {
+        r.x = __float_as_uint(v[0]); r.y = __float_as_uint(v[1]); r.z = __float_as_uint(v[2]); r.w = __float_as_uint(v[3]);
+    } else {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+                __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+        }
+        r.x = w[0]; r.y = w[1]; r.z = w[2]; r.w = w[3];
+    }
+    return r;
+}
+FD_DEVINL void fd_ld_f32v(const float* p, float* v, int n) {   // n is 4 or 8, p 16-byte aligned
+    for (int i = 0; i < n; i += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+}
+
+// mean / rstd of one row held as NV vectors per lane across LPR lanes (two-pass in registers)
+template <int LPR, int NV, int VEC>
+FD_DEVINL void fd_row_stats(const float (&v)[NV][VEC], int C, float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) s += v[j][e];
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { const float d = v[j][e] - mean; q += d * d; }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    rstd = rsqrtf(q / (float)C + eps);
+}
+
+// LayerNorm over C + adaLN modulate (src/DADiff.py:450-451, 459, 461, 486-487).
+template <typename T, int LPR, int NV, int U>
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const T* __restrict__ x, T* __restrict__ out,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta,
                                                           const float* __restrict__ shift,
                                                           const float* __restrict__ scale, int mod_stride,
-                                                          long rows, int P, int C, float eps) {
+                                                          unsigned rows, unsigned P, int C, float eps) {
     constexpr int VEC = fd_vec<T>::N;
-    constexpr int RPW = 32 / LPR;  // rows per warp
+    constexpr int RPW = 32 / LPR;  // rows per warp per group
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
-    const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long row = warp * RPW + lane / LPR;
-    const bool active = row < rows;
-    float v[NV][VEC];
-    float s = 0.f;
-    const T* xr = x + (active ? row : 0) * (long)C;
+    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned row0 = warp * (RPW * U) + lane / LPR;
+    uint4 raw[U][NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        fd_ldv<T, VEC>(xr + (sub + j * LPR) * VEC, v[j]);
+    for (int u = 0; u < U; ++u) {
+        const unsigned row = row0 + u * RPW;
+        const T* xr = x + (long)(row < rows ? row : 0) * C;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) s += v[j][e];
+        for (int j = 0; j < NV; ++j) raw[u][j] = *reinterpret_cast<const uint4*>(xr + (sub + j * LPR) * VEC);
     }
+    // per-channel parameters folded to y = xhat * a + c with a = gamma*(1+scale), c = beta*(1+scale) + shift
+    constexpr bool HOIST = NV <= 2;   // wider rows would spill; they read the (L1-resident) parameters per use instead
+    float pa[HOIST ? NV : 1][VEC], pc[HOIST ? NV : 1][VEC];
+    unsigned bcur = 0xffffffffu;
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / (float)C;
-    float q = 0.f;
+    for (int u = 0; u < U; ++u) {
+        const unsigned row = row0 + u * RPW;
+        const bool active = row < rows;
+        const unsigned b = (active ? row : 0) / P;
+        if (HOIST && b != bcur) {
+            bcur = b;
+            const float* sh = shift + (long)b * mod_stride;
+            const float* sc = scale + (long)b * mod_stride;
 #pragma unroll
-    for (int j = 0; j < NV; ++j)
+            for (int j = 0; j < (HOIST ? NV : 0); ++j) {
+                const int c0 = (sub + j * LPR) * VEC;
+                float tsc[VEC], tsh[VEC];
+                fd_ld_f32v(sc + c0, tsc, VEC);
+                fd_ld_f32v(sh + c0, tsh, VEC);
+                if (gamma) {
+                    float tg[VEC], tb[VEC];
+                    fd_ld_f32v(gamma + c0, tg, VEC);
+                    fd_ld_f32v(beta + c0, tb, VEC);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) { float d = v[j][e] - mean; q += d * d; }
+                    for (int e = 0; e < VEC; ++e) { pa[j][e] = tg[e] * (1.f + tsc[e]); pc[j][e] = fmaf(tb[e], 1.f + tsc[e], tsh[e]); }
+                } else {
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / (float)C + eps);
-    if (!active) return;
-    const int b = (int)(row / P);
-    const float* sh = shift + (long)b * mod_stride;
-    const float* sc = scale + (long)b * mod_stride;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const int c0 = (sub + j * LPR) * VEC;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            float y = (v[j][e] - mean) * rstd;
-            if (gamma) y = y * __ldg(gamma + c0 + e) + __ldg(beta + c0 + e);
-            v[j][e] = y * (1.f + __ldg(sc + c0 + e)) + __ldg(sh + c0 + e);
+                    for (int e = 0; e < VEC; ++e) { pa[j][e] = 1.f + tsc[e]; pc[j][e] = tsh[e]; }
+                }
+            }
         }
-        fd_stv<T, VEC>(out + row * (long)C + c0, v[j]);
+        float v[NV][VEC];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) fd_raw_to_f<T>(raw[u][j], v[j]);
+        float mean, rstd;
+        fd_row_stats<LPR, NV, VEC>(v, C, eps, mean, rstd);
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                if constexpr (HOIST) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) v[j][e] = fmaf((v[j][e] - mean) * rstd, pa[j][e], pc[j][e]);
+                } else {
+                    const int c0 = (sub + j * LPR) * VEC;
+                    float tsc[VEC], tsh[VEC];
+                    fd_ld_f32v(scale + (long)b * mod_stride + c0, tsc, VEC);
+                    fd_ld_f32v(shift + (long)b * mod_stride + c0, tsh, VEC);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        float t = (v[j][e] - mean) * rstd;
+                        if (gamma) t = fmaf(t, __ldg(gamma + c0 + e), __ldg(beta + c0 + e));
+                        v[j][e] = fmaf(t, 1.f + tsc[e], tsh[e]);
+                    }
+                }
+                *reinterpret_cast<uint4*>(out + (long)row * C + (sub + j * LPR) * VEC) = fd_f_to_raw<T>(v[j]);
+            }
+        }
     }
 }
 
@@ -63,23 +160,25 @@ static int ln_modulate_launch(const void* x, void* out, const float* gamma, cons
                               const float* shift, const float* scale, int mod_stride, int B, int P, int C,
                               float eps, cudaStream_t st) {
     constexpr int VEC = fd_vec<T>::N;
-    if (C % VEC) return FD_ERR_UNSUPPORTED;
+    if (C % VEC || mod_stride % 4 || ((uintptr_t)shift | (uintptr_t)scale | (uintptr_t)gamma | (uintptr_t)beta) % 16)
+        return FD_ERR_UNSUPPORTED;
     const int vr = C / VEC;  // vectors per row
     const long rows = (long)B * P;
+    if (rows >= (1L << 31)) return FD_ERR_UNSUPPORTED;
     const int lpr = vr >= 32 ? 32 : vr;
     const int nv = vr / lpr;
     if (lpr * nv != vr || (lpr & (lpr - 1))) return FD_ERR_UNSUPPORTED;
     const int rpw = 32 / lpr;
     const int warps = 8;
-    const int grid = fd_cdiv(rows, (long)rpw * warps);
-#define LN_CASE(L, N)                                                                                        \
+#define LN_CASE(L, N, UU)                                                                                    \
     if (lpr == L && nv == N) {                                                                               \
-        ln_modulate_kernel<T, L, N><<<grid, warps * 32, 0, st>>>((const T*)x, (T*)out, gamma, beta, shift,   \
-                                                                 scale, mod_stride, rows, P, C, eps);        \
+        const int grid = fd_cdiv(rows, (long)rpw * warps * UU);                                              \
+        ln_modulate_kernel<T, L, N, UU><<<grid, warps * 32, 0, st>>>((const T*)x, (T*)out, gamma, beta, shift, scale, \
+                                                                     mod_stride, (unsigned)rows, (unsigned)P, C, eps); \
         FD_LAUNCH_CHECK();                                                                                   \
         return 0;                                                                                            \
     }
-    LN_CASE(4, 1) LN_CASE(8, 1) LN_CASE(16, 1) LN_CASE(32, 1) LN_CASE(32, 2) LN_CASE(32, 4) LN_CASE(32, 8)
+    LN_CASE(4, 1, 4) LN_CASE(8, 1, 4) LN_CASE(16, 1, 4) LN_CASE(32, 1, 4) LN_CASE(32, 2, 2) LN_CASE(32, 4, 1) LN_CASE(32, 8, 1)
 #undef LN_CASE
     return FD_ERR_UNSUPPORTED;
 }
@@ -98,53 +197,80 @@ extern "C" int fd_ln_modulate(const void* x, void* out, const float* gamma, cons
 // SS2D tail on channels-last data (src/emamba2.py:365, 747-748): out = (LN(y) * gamma + beta) * z + local[b]
 // with z = columns [z_off, z_off + C) of rows of pitch `ld` (the silu(z) half of xz).  Same row mapping as above.
 // ------------------------------------------------------------------------------------------------------
-template <typename T, int LPR, int NV>
+template <typename T, int LPR, int NV, int U>
 __global__ void __launch_bounds__(256) ln_gate_kernel(const T* __restrict__ y, const T* __restrict__ xz, int ld, int z_off,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                      const float* __restrict__ local, T* __restrict__ out, long rows, int P,
-                                                      int C, float eps) {
+                                                      const float* __restrict__ local, T* __restrict__ out, unsigned rows,
+                                                      unsigned P, int C, float eps) {
     constexpr int VEC = fd_vec<T>::N;
     constexpr int RPW = 32 / LPR;
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR;
-    const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long row = warp * RPW + lane / LPR;
-    const bool active = row < rows;
-    float v[NV][VEC];
-    float s = 0.f;
-    const T* yr = y + (active ? row : 0) * (long)C;
+    const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned row0 = warp * (RPW * U) + lane / LPR;
+    uint4 raw[U][NV], rawz[U][NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        fd_ldv<T, VEC>(yr + (sub + j * LPR) * VEC, v[j]);
+    for (int u = 0; u < U; ++u) {
+        const unsigned row = row0 + u * RPW;
+        const long rr = row < rows ? row : 0;
+        const T* yr = y + rr * C;
+        const T* zr = xz + rr * ld + z_off;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) s += v[j][e];
-    }
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / (float)C;
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < NV; ++j)
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) { float d = v[j][e] - mean; q += d * d; }
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / (float)C + eps);
-    if (!active) return;
-    const int b = (int)(row / P);
-    const T* zr = xz + row * (long)ld + z_off;
-    const float* lc = local + (long)b * C;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const int c0 = (sub + j * LPR) * VEC;
-        float z[VEC];
-        fd_ldv<T, VEC>(zr + c0, z);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const float n = (v[j][e] - mean) * rstd * __ldg(gamma + c0 + e) + __ldg(beta + c0 + e);
-            v[j][e] = n * z[e] + __ldg(lc + c0 + e);
+        for (int j = 0; j < NV; ++j) {
+            raw[u][j] = *reinterpret_cast<const uint4*>(yr + (sub + j * LPR) * VEC);
+            rawz[u][j] = *reinterpret_cast<const uint4*>(zr + (sub + j * LPR) * VEC);
         }
-        fd_stv<T, VEC>(out + row * (long)C + c0, v[j]);
+    }
+    constexpr bool HOIST = NV <= 2;
+    constexpr int NH = HOIST ? NV : 1;
+    float pg[NH][VEC], pb[NH][VEC], pl[NH][VEC];
+#pragma unroll
+    for (int j = 0; j < (HOIST ? NV : 0); ++j) {
+        fd_ld_f32v(gamma + (sub + j * LPR) * VEC, pg[j], VEC);
+        fd_ld_f32v(beta + (sub + j * LPR) * VEC, pb[j], VEC);
+    }
+    unsigned bcur = 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const unsigned row = row0 + u * RPW;
+        const bool active = row < rows;
+        const unsigned b = (active ? row : 0) / P;
+        if (HOIST && b != bcur) {
+            bcur = b;
+#pragma unroll
+            for (int j = 0; j < (HOIST ? NV : 0); ++j) fd_ld_f32v(local + (long)b * C + (sub + j * LPR) * VEC, pl[j], VEC);
+        }
+        float v[NV][VEC];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) fd_raw_to_f<T>(raw[u][j], v[j]);
+        float mean, rstd;
+        fd_row_stats<LPR, NV, VEC>(v, C, eps, mean, rstd);
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                float z[VEC];
+                fd_raw_to_f<T>(rawz[u][j], z);
+                if constexpr (HOIST) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        const float n = fmaf((v[j][e] - mean) * rstd, pg[j][e], pb[j][e]);
+                        v[j][e] = fmaf(n, z[e], pl[j][e]);
+                    }
+                } else {
+                    const int c0 = (sub + j * LPR) * VEC;
+                    float tg[VEC], tb[VEC], tl[VEC];
+                    fd_ld_f32v(gamma + c0, tg, VEC);
+                    fd_ld_f32v(beta + c0, tb, VEC);
+                    fd_ld_f32v(local + (long)b * C + c0, tl, VEC);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        const float n = fmaf((v[j][e] - mean) * rstd, tg[e], tb[e]);
+                        v[j][e] = fmaf(n, z[e], tl[e]);
+                    }
+                }
+                *reinterpret_cast<uint4*>(out + (long)row * C + (sub + j * LPR) * VEC) = fd_f_to_raw<T>(v[j]);
+            }
+        }
     }
 }
 
@@ -152,22 +278,24 @@ template <typename T>
 static int ln_gate_launch(const void* y, const void* xz, int ld, int z_off, const float* gamma, const float* beta,
                           const float* local, void* out, int B, int P, int C, float eps, cudaStream_t st) {
     constexpr int VEC = fd_vec<T>::N;
-    if (C % VEC || ld % VEC || z_off % VEC) return FD_ERR_UNSUPPORTED;
+    if (C % VEC || ld % VEC || z_off % VEC || ((uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)local) % 16) return FD_ERR_UNSUPPORTED;
     const int vr = C / VEC;
     const long rows = (long)B * P;
+    if (rows >= (1L << 31)) return FD_ERR_UNSUPPORTED;
     const int lpr = vr >= 32 ? 32 : vr;
     const int nv = vr / lpr;
     if (lpr * nv != vr || (lpr & (lpr - 1))) return FD_ERR_UNSUPPORTED;
     const int rpw = 32 / lpr, warps = 8;
-    const int grid = fd_cdiv(rows, (long)rpw * warps);
-#define LG_CASE(L, N)                                                                                              \
+#define LG_CASE(L, N, UU)                                                                                          \
     if (lpr == L && nv == N) {                                                                                     \
-        ln_gate_kernel<T, L, N><<<grid, warps * 32, 0, st>>>((const T*)y, (const T*)xz, ld, z_off, gamma, beta, local, \
-                                                             (T*)out, rows, P, C, eps);                            \
+        const int grid = fd_cdiv(rows, (long)rpw * warps * UU);                                                    \
+        ln_gate_kernel<T, L, N, UU><<<grid, warps * 32, 0, st>>>((const T*)y, (const T*)xz, ld, z_off, gamma, beta, local, \
+                                                                 (T*)out, (unsigned)rows, (unsigned)P, C, eps);    \
         FD_LAUNCH_CHECK();                                                                                         \
         return 0;                                                                                                  \
     }
-    LG_CASE(2, 1) LG_CASE(4, 1) LG_CASE(8, 1) LG_CASE(16, 1) LG_CASE(32, 1) LG_CASE(32, 2) LG_CASE(32, 4) LG_CASE(32, 8)
+    LG_CASE(2, 1, 4) LG_CASE(4, 1, 4) LG_CASE(8, 1, 4) LG_CASE(16, 1, 4) LG_CASE(32, 1, 2) LG_CASE(32, 2, 1) LG_CASE(32, 4, 1)
+    LG_CASE(32, 8, 1)
 #undef LG_CASE
     return FD_ERR_UNSUPPORTED;
 }
