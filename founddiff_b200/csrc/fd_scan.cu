@@ -6,6 +6,8 @@
 // chunked warp-shuffle scan with no shared memory and no block barrier.  Loads/stores are 16-byte vectors,
 // consecutive lanes touching consecutive addresses.  exp(dt*A) is one MUFU.EX2 per (step, state): the kernel
 // is bound by the SFU/FMA pipes rather than by HBM for dstate >= 4 ("selective scan").
+#include <type_traits>
+
 #include "fd_common.cuh"
 
 namespace {
@@ -150,65 +152,121 @@ FD_DEVINL void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
     const int sz = valid ? 16 : 0;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
+FD_DEVINL float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// log1p(exp(x)), branch-free, 2 MUFU ops.  w = 1 + y rounds; for y < 1 the lost part (y - (w - 1)) is exact and
+// log1p(y) = log(w) + log1p((y - (w-1)) / w) ~ log(w) + (y - (w-1)) * (1 - y)   (the factor only has to be right to
+// O(1) because the term itself is <= half an ulp of w); for y >= 1 the rounding of w is below 1e-7 relative already.
 FD_DEVINL float fast_softplus(float x) {
-    // log1p(exp(x)) with the classic compensation log(w) * y / (w - 1), w = 1 + y: ~1e-6 relative, 3 MUFU ops
-    if (x > 20.f) return x;
-    const float y = __expf(x);
+    const float y = ex2_approx(x * 1.4426950408889634f);
     const float w = 1.f + y;
-    return (w == 1.f) ? y : __logf(w) * __fdividef(y, w - 1.f);
+    const float corr = (y < 1.f) ? (y - (w - 1.f)) * (1.f - y) : 0.f;
+    const float r = fmaf(lg2_approx(w), 0.6931471805599453f, corr);
+    return x > 20.f ? x : r;
+}
+
+// One Kogge-Stone round of the (a, b) composition across lanes: lanes whose source lane exists (the shuffle's own
+// predicate) fold it in, with predicated FMA/MUL instead of compare + select.
+FD_DEVINL void scan_round(float& ap, float& bp, int o) {
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .f32 au, bu;\n"
+        "shfl.sync.up.b32 au|p, %0, %2, 0, 0xffffffff;\n"
+        "shfl.sync.up.b32 bu, %1, %2, 0, 0xffffffff;\n"
+        "@p fma.rn.f32 %1, %0, bu, %1;\n"
+        "@p mul.f32 %0, %0, au;\n"
+        "}\n"
+        : "+f"(ap), "+f"(bp)
+        : "r"(o));
+}
+// exclusive prefix of the lane aggregates: (ae, be) = aggregate of lane-1, identity for lane 0
+FD_DEVINL void scan_exclusive(float ap, float bp, float& ae, float& be) {
+    asm("{\n"
+        ".reg .pred p;\n"
+        "shfl.sync.up.b32 %0|p, %2, 1, 0, 0xffffffff;\n"
+        "shfl.sync.up.b32 %1, %3, 1, 0, 0xffffffff;\n"
+        "@!p mov.f32 %0, 0f3F800000;\n"
+        "@!p mov.f32 %1, 0f00000000;\n"
+        "}\n"
+        : "=&f"(ae), "=&f"(be)
+        : "f"(ap), "f"(bp));
+}
+
+// raw (unconverted) 8-item vectors: the prefetch for the next chunk is held in this form so that nothing consumes the
+// load before the chunk boundary (a float conversion right behind the load made every warp sit out the DRAM latency)
+template <typename T> struct RawItems { uint4 v[sizeof(T) * kItems / 16]; };
+template <typename T> FD_DEVINL RawItems<T> load_raw(const T* p) {
+    RawItems<T> r;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) * kItems / 16); ++i) r.v[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
+    return r;
+}
+template <typename T> FD_DEVINL void raw_to_float(const RawItems<T>& r, float (&v)[kItems]) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            v[4 * i] = __uint_as_float(r.v[i].x); v[4 * i + 1] = __uint_as_float(r.v[i].y);
+            v[4 * i + 2] = __uint_as_float(r.v[i].z); v[4 * i + 3] = __uint_as_float(r.v[i].w);
+        }
+    } else {
+        const uint32_t w[4] = {r.v[0].x, r.v[0].y, r.v[0].z, r.v[0].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f;
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+            else f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
 }
 
 // MERGE = true fuses EfficientMerge (src/emamba2.py:238-262) into the scan: instead of the (b, KD, L) scan layout the
-// block transposes each 256-step chunk of its channels through shared memory and writes whole 32-byte channel groups
+// block transposes each 256-step chunk of its 8 channels through shared memory and writes 16-byte channel groups
 // straight into the channels-last tensor y_nhwc (B, H, W, dim/4) at the pixel each (direction, l) stands for.
-// RPW = rows (channels) per warp: 2 for small d_state, where the per-chunk overhead (staging, barriers) would otherwise
-// dominate and so that a block owns 16 channels = one full sector per pixel.
-template <typename T, int NS, int NBUF, bool MERGE, int RPW>
-__global__ void __launch_bounds__(kRowsPerBlock * 32, ((NS <= 8 && RPW == 1) ? 3 : 2)) selective_scan_smem_kernel(
+// One block barrier per chunk: the barrier that publishes chunk c's B/C also retires chunk c-1 (its staging buffer may
+// be refilled, its transposed outputs may be written out while the warps already work on chunk c).
+template <typename T, int NS, int NBUF, bool MERGE>
+__global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selective_scan_smem_kernel(
     const T* __restrict__ u, const T* __restrict__ delta, const float* __restrict__ A, const float* __restrict__ Bm,
     const float* __restrict__ Cm, const float* __restrict__ D, const float* __restrict__ delta_bias, T* __restrict__ y,
     int dim, int L, int G, int softplus, int H, int W) {
     extern __shared__ __align__(16) float s_bc[];          // [NBUF][2][NS][kPadChunk] (+ A*log2e for NS >= 16) (+ s_y)
     constexpr bool kA2InSmem = NS >= 16;                   // keeps the register count at two blocks per SM for large d_state
-    constexpr int kCh = kRowsPerBlock * RPW;               // channels per block
     float* s_a2 = s_bc + (size_t)NBUF * 2 * NS * kPadChunk;
-    T* s_y = reinterpret_cast<T*>(s_a2 + (kA2InSmem ? kCh * NS : 0));     // [kCh][kChunk] (MERGE only)
+    T* s_y = reinterpret_cast<T*>(s_a2 + (kA2InSmem ? kRowsPerBlock * NS : 0));     // [2][8][kChunk] (MERGE only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per_group = dim / G;
-    const int blocks_per_group = per_group / kCh;
+    const int blocks_per_group = per_group / kRowsPerBlock;
     const int bg = blockIdx.x / blocks_per_group;          // b * G + g
-    const int dloc0 = (blockIdx.x % blocks_per_group) * kCh;
+    const int dloc0 = (blockIdx.x % blocks_per_group) * kRowsPerBlock;
     const int b = bg / G;
     const float* Bg = Bm + (long)bg * NS * L;
     const float* Cg = Cm + (long)bg * NS * L;
 
-    const T* ur[RPW];
-    const T* dr[RPW];
-    T* yr[RPW];
-    float bias[RPW], Dd[RPW];
-    float A2[RPW][kA2InSmem ? 1 : NS], h[RPW][NS];
+    const int d = (bg % G) * per_group + dloc0 + warp;
+    const long row = (long)b * dim + d;
+    const T* ur = u + row * (long)L;
+    const T* dr = delta + row * (long)L;
+    T* yr = y + row * (long)L;
+    const float bias = delta_bias ? delta_bias[d] : 0.f;
+    const float Dd = D ? D[d] : 0.f;
+    float A2[kA2InSmem ? 1 : NS], h[NS];
 #pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-        const int d = (bg % G) * per_group + dloc0 + warp * RPW + rr;
-        const long row = (long)b * dim + d;
-        ur[rr] = u + row * (long)L;
-        dr[rr] = delta + row * (long)L;
-        yr[rr] = y + row * (long)L;
-        bias[rr] = delta_bias ? delta_bias[d] : 0.f;
-        Dd[rr] = D ? D[d] : 0.f;
-#pragma unroll
-        for (int n = 0; n < NS; ++n) {
-            if constexpr (!kA2InSmem) A2[rr][n] = A[(long)d * NS + n] * 1.4426950408889634f;
-            h[rr][n] = 0.f;
-        }
-        if constexpr (kA2InSmem) {
-            for (int n = lane; n < NS; n += 32) s_a2[(warp * RPW + rr) * NS + n] = A[(long)d * NS + n] * 1.4426950408889634f;
-        }
+    for (int n = 0; n < NS; ++n) {
+        if constexpr (!kA2InSmem) A2[n] = A[(long)d * NS + n] * 1.4426950408889634f;
+        h[n] = 0.f;
     }
-    if constexpr (kA2InSmem) __syncwarp();
+    if constexpr (kA2InSmem) {
+        for (int n = lane; n < NS; n += 32) s_a2[warp * NS + n] = A[(long)d * NS + n] * 1.4426950408889634f;
+        __syncwarp();
+    }
 
     auto stage = [&](int c0, int buf) {   // cooperative cp.async of B/C[:, c0 : c0+256] (zero-filled past L)
         float* dst = s_bc + (size_t)buf * 2 * NS * kPadChunk;
+#pragma unroll
         for (int i = threadIdx.x; i < 2 * NS * (kChunk / 4); i += kRowsPerBlock * 32) {
             const int v = i % (kChunk / 4), rn = i / (kChunk / 4);     // rn: 0..NS-1 = B rows, NS..2NS-1 = C rows
             const int l = c0 + v * 4;
@@ -218,106 +276,112 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, ((NS <= 8 && RPW == 1) ? 3
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    // EfficientMerge scatter of one finished chunk: one pixel per thread, 8 channels = 16 bytes
+    const int mk = bg % G;                                  // direction of this block's channel group
+    const int mdiv = (mk & 1) ? (H >> 1) : (W >> 1);        // sub-grid extent along the direction's fast axis
+    const int msh = (mdiv & (mdiv - 1)) ? -1 : (__ffs(mdiv) - 1);
+    auto merge_store = [&](int c) {
+        if constexpr (MERGE) {
+            const int l = c * kChunk + (int)threadIdx.x;
+            if (l < L) {
+                const int qd = msh >= 0 ? (l >> msh) : (l / mdiv);
+                const int rm = l - qd * mdiv;
+                int hh, ww;
+                if (mk & 1) { ww = 2 * qd + (mk >> 1); hh = 2 * rm + 1; }     // column-major sub-grids
+                else        { hh = 2 * qd; ww = 2 * rm + (mk >> 1); }
+                const unsigned short* src = reinterpret_cast<const unsigned short*>(s_y) + (c & 1) * kRowsPerBlock * kChunk + threadIdx.x;
+                uint32_t pk[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) pk[r] = (uint32_t)src[(2 * r) * kChunk] | ((uint32_t)src[(2 * r + 1) * kChunk] << 16);
+                *reinterpret_cast<uint4*>(y + (((long)b * H + hh) * W + ww) * per_group + dloc0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+    };
+
     const int nchunks = (L + kChunk - 1) / kChunk;
     stage(0, 0);
-    float dt_n[RPW][kItems], u_n[RPW][kItems];
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-        load_items<T>(dr[rr], lane * kItems, L, true, dt_n[rr]);
-        load_items<T>(ur[rr], lane * kItems, L, true, u_n[rr]);
-    }
+    // rows are kItems-aligned (launcher), so a lane's 8 steps are all inside or all outside the row; outside lanes read a
+    // clamped (valid) address and are masked through dt = 0
+    RawItems<T> dt_raw = load_raw<T>(dr + min(lane * kItems, L - kItems));
+    RawItems<T> u_raw = load_raw<T>(ur + min(lane * kItems, L - kItems));
 
     for (int c = 0; c < nchunks; ++c) {
         const int c0 = c * kChunk, l0 = c0 + lane * kItems;
         const int buf = (NBUF == 2) ? (c & 1) : 0;
-        if (NBUF == 2) {
-            if (c + 1 < nchunks) { stage(c0 + kChunk, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                  // chunk c's B/C visible to all; every warp is past chunk c-1
+        if (NBUF == 2 && c + 1 < nchunks) stage(c0 + kChunk, buf ^ 1);
+        if (c > 0) merge_store(c - 1);
         const float* sB = s_bc + (size_t)buf * 2 * NS * kPadChunk + pad_idx(lane * kItems);
         const float* sC = sB + NS * kPadChunk;
-        const bool tail = c0 + kChunk > L;
-#pragma unroll
-        for (int rr = 0; rr < RPW; ++rr) {
-            float dt[kItems], dtu[kItems], yacc[kItems];
+        float dt[kItems], dtu[kItems], yacc[kItems];
+        {
+            float dtv[kItems], uv[kItems];
+            raw_to_float<T>(dt_raw, dtv);
+            raw_to_float<T>(u_raw, uv);
+            const bool live = l0 < L;
 #pragma unroll
             for (int i = 0; i < kItems; ++i) {
-                float t = dt_n[rr][i] + bias[rr];
+                float t = dtv[i] + bias;
                 if (softplus) t = fast_softplus(t);
-                if (tail && l0 + i >= L) t = 0.f;
-                yacc[i] = Dd[rr] * u_n[rr][i];
-                dtu[i] = t * u_n[rr][i];
+                t = live ? t : 0.f;
+                yacc[i] = Dd * uv[i];
+                dtu[i] = t * uv[i];
                 dt[i] = t;
             }
-            if (c + 1 < nchunks) {      // prefetch the next chunk's u / delta
-                load_items<T>(dr[rr], l0 + kChunk, L, true, dt_n[rr]);
-                load_items<T>(ur[rr], l0 + kChunk, L, true, u_n[rr]);
-            }
-#pragma unroll
-            for (int n = 0; n < NS; ++n) {
-                const float4 b0 = *reinterpret_cast<const float4*>(sB + n * kPadChunk);
-                const float4 b1 = *reinterpret_cast<const float4*>(sB + n * kPadChunk + 4);
-                const float4 c0v = *reinterpret_cast<const float4*>(sC + n * kPadChunk);
-                const float4 c1v = *reinterpret_cast<const float4*>(sC + n * kPadChunk + 4);
-                float Bn[kItems] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                const float Cn[kItems] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
-                const float a2n = kA2InSmem ? s_a2[(warp * RPW + rr) * NS + n] : A2[rr][kA2InSmem ? 0 : n];
-                float a[kItems], ap = 1.f, bp = 0.f;
-#pragma unroll
-                for (int i = 0; i < kItems; ++i) {
-                    a[i] = ex2_approx(dt[i] * a2n);
-                    Bn[i] = dtu[i] * Bn[i];
-                    ap *= a[i];
-                    bp = fmaf(a[i], bp, Bn[i]);
-                }
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const float au = __shfl_up_sync(0xffffffffu, ap, o);
-                    const float bu = __shfl_up_sync(0xffffffffu, bp, o);
-                    if (lane >= o) { bp = fmaf(ap, bu, bp); ap *= au; }
-                }
-                float ae = __shfl_up_sync(0xffffffffu, ap, 1);
-                float be = __shfl_up_sync(0xffffffffu, bp, 1);
-                if (lane == 0) { ae = 1.f; be = 0.f; }
-                float hh = fmaf(ae, h[rr][n], be);
-                const float at = __shfl_sync(0xffffffffu, ap, 31);
-                const float bt = __shfl_sync(0xffffffffu, bp, 31);
-                h[rr][n] = fmaf(at, h[rr][n], bt);
-#pragma unroll
-                for (int i = 0; i < kItems; ++i) {
-                    hh = fmaf(a[i], hh, Bn[i]);
-                    yacc[i] = fmaf(hh, Cn[i], yacc[i]);
-                }
-            }
-            if constexpr (!MERGE) store_items<T>(yr[rr], l0, L, true, yacc);
-            else fd_stv<T, 8>(s_y + (warp * RPW + rr) * kChunk + lane * kItems, yacc);
         }
-        __syncthreads();                // everyone is done with `buf` (and, MERGE, the chunk of all channels is in s_y)
-        if (NBUF == 1 && c + 1 < nchunks) stage(c0 + kChunk, 0);
-        if constexpr (MERGE) {
-            const int l = c0 + (int)threadIdx.x;            // one pixel per thread
-            if (l < L) {
-                const int k = bg % G;                       // direction of this block's channel group
-                const int H2 = H >> 1, W2 = W >> 1;
-                int hh, ww;
-                if (k & 1) { ww = 2 * (l / H2) + (k >> 1); hh = 2 * (l % H2) + 1; }     // column-major sub-grids
-                else       { hh = 2 * (l / W2); ww = 2 * (l % W2) + (k >> 1); }
-                const unsigned short* src = reinterpret_cast<const unsigned short*>(s_y) + threadIdx.x;
-                T* dst = y + (((long)b * H + hh) * W + ww) * per_group + dloc0;
-#pragma unroll
-                for (int v = 0; v < kCh / 8; ++v) {
-                    uint4 pk;
-                    unsigned short* ps = reinterpret_cast<unsigned short*>(&pk);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) ps[r] = src[(v * 8 + r) * kChunk];
-                    *reinterpret_cast<uint4*>(dst + v * 8) = pk;
-                }
-            }
-            // the next iteration's top-of-loop barrier orders these reads before s_y is overwritten
+        if (c + 1 < nchunks) {          // prefetch the next chunk's u / delta (raw: consumed after the next barrier)
+            const int ln = min(l0 + kChunk, L - kItems);
+            dt_raw = load_raw<T>(dr + ln);
+            u_raw = load_raw<T>(ur + ln);
         }
+        float sdt = 0.f;
+#pragma unroll
+        for (int i = 0; i < kItems; ++i) sdt += dt[i];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            const float4 b0 = *reinterpret_cast<const float4*>(sB + n * kPadChunk);
+            const float4 b1 = *reinterpret_cast<const float4*>(sB + n * kPadChunk + 4);
+            const float4 c0v = *reinterpret_cast<const float4*>(sC + n * kPadChunk);
+            const float4 c1v = *reinterpret_cast<const float4*>(sC + n * kPadChunk + 4);
+            float Bn[kItems] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            const float Cn[kItems] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+            const float a2n = kA2InSmem ? s_a2[warp * NS + n] : A2[kA2InSmem ? 0 : n];
+            float a[kItems], bp = 0.f;
+            float ap = ex2_approx(sdt * a2n);      // product of the lane's 8 decay factors
+#pragma unroll
+            for (int i = 0; i < kItems; ++i) {
+                a[i] = ex2_approx(dt[i] * a2n);
+                Bn[i] = dtu[i] * Bn[i];
+                bp = fmaf(a[i], bp, Bn[i]);
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) scan_round(ap, bp, o);
+            float ae, be;
+            scan_exclusive(ap, bp, ae, be);
+            float hh = fmaf(ae, h[n], be);
+            const float at = __shfl_sync(0xffffffffu, ap, 31);
+            const float bt = __shfl_sync(0xffffffffu, bp, 31);
+            h[n] = fmaf(at, h[n], bt);
+#pragma unroll
+            for (int i = 0; i < kItems; ++i) {
+                hh = fmaf(a[i], hh, Bn[i]);
+                yacc[i] = fmaf(hh, Cn[i], yacc[i]);
+            }
+        }
+        if constexpr (!MERGE) {
+            if (l0 < L) store_items<T>(yr, l0, L, true, yacc);
+        } else {
+            fd_stv<T, 8>(s_y + ((c & 1) * kRowsPerBlock + warp) * kChunk + lane * kItems, yacc);
+        }
+        if (NBUF == 1) {
+            __syncthreads();            // single staging buffer: everyone is done with it before it is refilled
+            if (c + 1 < nchunks) stage(c0 + kChunk, 0);
+        }
+    }
+    if constexpr (MERGE) {
+        __syncthreads();
+        merge_store(nchunks - 1);
     }
 }
 
@@ -329,7 +393,7 @@ int scan_launch(const void* u, const void* delta, const float* A, const float* B
     const int vec_ok = (L % kItems == 0) && ((((uintptr_t)u | (uintptr_t)delta | (uintptr_t)y) & 31) == 0) &&
                        ((((uintptr_t)Bm | (uintptr_t)Cm) & 31) == 0);
     // v2: rows of a block share one direction group and every access is 16/32-byte aligned
-    if (vec_ok && (N == 4 || N == 8 || N == 16 || N == 32)) {
+    if (vec_ok && L >= kItems && (N == 4 || N == 8 || N == 16 || N == 32)) {
 #define SCAN2_CASE(NSV, NB, RPWV)                                                                                   \
     if (N == NSV && (dim / G) % (kRowsPerBlock * RPWV) == 0) {                                                      \
         const unsigned grid2 = (unsigned)(rows / (kRowsPerBlock * RPWV));                                           \
@@ -337,25 +401,25 @@ int scan_launch(const void* u, const void* delta, const float* A, const float* B
         if (mergeH) {                                                                                               \
           if constexpr (sizeof(T) != 2) { return FD_ERR_UNSUPPORTED; } else {                                       \
             static bool attr_m = false;                                                                             \
-            const size_t smem_m = smem + (size_t)kRowsPerBlock * RPWV * kChunk * sizeof(T);                         \
+            const size_t smem_m = smem + (size_t)2 * kRowsPerBlock * RPWV * kChunk * sizeof(T);                         \
             if (!attr_m) {                                                                                          \
-                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, true, RPWV>,            \
+                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, true>,            \
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);     \
                 if (e != cudaSuccess) return (int)e;                                                                \
                 attr_m = true;                                                                                      \
             }                                                                                                       \
-            selective_scan_smem_kernel<T, NSV, NB, true, RPWV><<<grid2, kRowsPerBlock * 32, smem_m, st>>>(          \
+            selective_scan_smem_kernel<T, NSV, NB, true><<<grid2, kRowsPerBlock * 32, smem_m, st>>>(          \
                 (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus, mergeH, mergeW); \
           }                                                                                                         \
         } else {                                                                                                    \
             static bool attr_set = false;                                                                           \
             if (!attr_set) {                                                                                        \
-                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, false, RPWV>,           \
+                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, false>,           \
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
                 if (e != cudaSuccess) return (int)e;                                                                \
                 attr_set = true;                                                                                    \
             }                                                                                                       \
-            selective_scan_smem_kernel<T, NSV, NB, false, RPWV><<<grid2, kRowsPerBlock * 32, smem, st>>>(           \
+            selective_scan_smem_kernel<T, NSV, NB, false><<<grid2, kRowsPerBlock * 32, smem, st>>>(           \
                 (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus, 0, 0);          \
         }                                                                                                           \
         FD_LAUNCH_CHECK();                                                                                          \
