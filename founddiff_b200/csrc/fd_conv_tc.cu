@@ -14,6 +14,16 @@
 //                                 input with pre-summed weights (host-packed `weight_up4`), 2.25x fewer FLOPs.
 //   torch.cat inputs            : two tensor maps; K blocks switch map at c0.
 //   per-sample weights (W_eff)  : 3-D weight map {K, Cout, batch}.
+//
+// HALO mode (stride-1 convolutions with more than one tap): re-fetching the shifted A box for every tap made the
+// full-resolution 3x3 convolutions L2-bandwidth bound (9 x 16 KB per 64-channel slice and tile).  Instead the M tile
+// becomes 16 rows x 8 pixels and ONE TMA box {64 ch, 8+KW-1, 16+KH-1} (the halo tile, 23 KB for 3x3) is loaded per
+// 64-channel slice; every tap's A operand is a *shifted window* of it, expressed purely in the UMMA descriptor:
+// start = halo + ((kh*HT_W + kw) * 128 B), SBO = HT_W * 128 B (pitch of a halo row), base_offset 0 — the 128B swizzle
+// is a function of the absolute shared-memory address, so the XOR phase TMA wrote matches what the MMA unit reads
+// (tools/probes/umma_halo_probe.cu verifies this on the device for all nine shifts).  Weights go through their own
+// ring, or stay resident in shared memory for the whole persistent CTA when they fit (full-resolution 64-channel
+// convolutions: 72-144 KB), which removes the second largest L2 stream.
 #include <cuda.h>
 #include <type_traits>
 #include <stdlib.h>
@@ -41,8 +51,14 @@ struct TcParams {
     int taps_h, taps_w;     // taps per phase
     int kblocks0, kblocks1; // 64-channel blocks of src0 / src1
     int fmt;                // 0 = f16, 1 = bf16 (UMMA a/b format)
-    int stages;             // depth of the smem ring
+    int stages;             // depth of the smem ring (box mode: A+B stages; halo mode: A halo stages)
     int total_tiles;
+    int tile_h, tile_w;     // M tile = tile_h x tile_w output pixels (8x16 box mode, 16x8 halo mode)
+    int halo;               // 1: halo mode
+    int ht_h, ht_w;         // halo tile extent (pixels)
+    int a_stage_bytes;      // halo mode: bytes per A stage (1024-aligned)
+    int stages_b;           // halo mode: weight ring depth (ignored when b_stationary)
+    int b_stationary;       // halo mode: all weight tiles resident in shared memory
 };
 
 // ---------------------------------------------------------------------------------------------------- PTX helpers
@@ -95,6 +111,11 @@ FD_DEVINL void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint3
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+FD_DEVINL bool elect_one() {      // one lane of the (converged) warp; the same lane every time
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 FD_DEVINL void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -108,8 +129,8 @@ FD_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
 // LBO (ignored for swizzled K-major) = 1, SBO = 1024 B (8 rows x 128 B) >> 4, version 1 (sm_100), layout 2 (128B).
-FD_DEVINL uint64_t make_smem_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
+FD_DEVINL uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes = 1024) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
 // cute::UMMA::InstrDescriptor: c_format f32 (bit 4), a/b format (bits 7, 10), K-major both, N>>3 (bit 17), M>>4 (bit 24)
@@ -165,21 +186,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)BN * BK * 2;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     const int stages = q.stages;
-    uint64_t* full_bar = (uint64_t*)(smem + stages * stage_bytes);
+    const int kb_per_tap = q.kblocks0 + q.kblocks1;
+    const int num_kb = q.taps_h * q.taps_w * kb_per_tap;
+    // halo mode: [weight slots][A halo stages]; box mode: [stages x (A, B)]
+    const int b_slots = q.b_stationary ? num_kb : q.stages_b;
+    uint8_t* sB_halo = smem;
+    uint8_t* sA_halo = smem + (size_t)b_slots * b_bytes;
+    const size_t data_bytes = q.halo ? (size_t)b_slots * b_bytes + (size_t)stages * q.a_stage_bytes : (size_t)stages * stage_bytes;
+    uint64_t* full_bar = (uint64_t*)(smem + data_bytes);
     uint64_t* empty_bar = full_bar + MAX_STAGES;
-    uint64_t* tfull_bar = empty_bar + MAX_STAGES;     // [2] accumulator ready
+    uint64_t* bfull_bar = empty_bar + MAX_STAGES;     // halo mode: weight ring
+    uint64_t* bempty_bar = bfull_bar + MAX_STAGES;
+    uint64_t* wfull_bar = bempty_bar + MAX_STAGES;    // halo mode, stationary weights: all tiles landed
+    uint64_t* tfull_bar = wfull_bar + 1;              // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
     float* s_gn = (float*)(tmem_slot + 2);            // [2][8] GroupNorm partial sums of the current sample
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fd_conv_params& p = q.p;
-    const int kb_per_tap = q.kblocks0 + q.kblocks1;
-    const int num_kb = q.taps_h * q.taps_w * kb_per_tap;
     const int total_tiles = q.total_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
+        mbar_init(wfull_bar, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -198,8 +229,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-            int stage = 0;
-            uint32_t ph = 0;
+            int stage = 0, bstage = 0;
+            uint32_t ph = 0, bph = 0;
+            if (q.halo && q.b_stationary) {            // weights are tile-invariant: load every K block once
+                mbar_expect_tx(wfull_bar, (uint32_t)num_kb * b_bytes);
+                for (int kb = 0; kb < num_kb; ++kb) tma_load_3d(sB_halo + (size_t)kb * b_bytes, &map_w, wfull_bar, kb * BK, 0, 0);
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int t = tile;
                 const int nt = t % q.n_tiles; t /= q.n_tiles;
@@ -207,11 +242,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 const int th = t % q.tiles_h; t /= q.tiles_h;
                 const int phase = t % q.phases;
                 const int b = t / q.phases;
-                const int ho0 = th * TILE_H, wo0 = tw * TILE_W, n0 = nt * BN;
+                const int ho0 = th * q.tile_h, wo0 = tw * q.tile_w, n0 = nt * BN;
                 int hbase, wbase;
                 if (p.upsample) { hbase = ho0 - 1 + (phase >> 1); wbase = wo0 - 1 + (phase & 1); }
                 else { hbase = ho0 * p.stride - p.pad; wbase = wo0 * p.stride - p.pad; }
                 const int wbatch = p.per_batch_weight ? b : phase;
+                if (q.halo) {
+                    const uint32_t halo_bytes = (uint32_t)(q.ht_h * q.ht_w) * 128u;
+                    for (int cb = 0; cb < kb_per_tap; ++cb) {
+                        mbar_wait_backoff(&empty_bar[stage], ph ^ 1);
+                        mbar_expect_tx(&full_bar[stage], halo_bytes);
+                        uint8_t* sa = sA_halo + (size_t)stage * q.a_stage_bytes;
+                        if (cb < q.kblocks0) tma_load_4d(sa, &map_a0, &full_bar[stage], cb * BK, wbase, hbase, b);
+                        else                 tma_load_4d(sa, &map_a1, &full_bar[stage], (cb - q.kblocks0) * BK, wbase, hbase, b);
+                        if (++stage == stages) { stage = 0; ph ^= 1; }
+                        if (!q.b_stationary) {
+                            for (int tap = 0; tap < q.taps_h * q.taps_w; ++tap) {
+                                mbar_wait_backoff(&bempty_bar[bstage], bph ^ 1);
+                                mbar_expect_tx(&bfull_bar[bstage], b_bytes);
+                                tma_load_3d(sB_halo + (size_t)bstage * b_bytes, &map_w, &bfull_bar[bstage], (tap * kb_per_tap + cb) * BK, n0, wbatch);
+                                if (++bstage == q.stages_b) { bstage = 0; bph ^= 1; }
+                            }
+                        }
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int tap = kb / kb_per_tap, cb = kb % kb_per_tap;
                     const int kh = tap / q.taps_w, kw = tap % q.taps_w;
@@ -227,29 +282,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
+        // The whole warp walks the (warp-uniform) loop and polls the barriers; one elected lane issues the MMAs and
+        // commits.  Keeping the control flow converged lets the compiler hold descriptors in uniform registers — as a
+        // single divergent thread the issue loop cost ~25 instructions per MMA and, for N = 64 tiles, was the
+        // critical path of the kernel.
+        {
             const uint32_t idesc = make_idesc(q.fmt, BN);
-            int stage = 0;
-            uint32_t ph = 0;
+            int stage = 0, bstage = 0;
+            uint32_t ph = 0, bph = 0;
             int it = 0;
+            if (q.halo && q.b_stationary) mbar_wait(wfull_bar, 0);
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+                uint32_t acc = 0;
+                if (q.halo) {
+                    const uint32_t sbo_a = (uint32_t)q.ht_w * 128u;
+                    const uint32_t sB0 = smem_u32(sB_halo);
+                    for (int cb = 0; cb < kb_per_tap; ++cb) {
+                        mbar_wait(&full_bar[stage], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t da0 = make_smem_desc(smem_u32(sA_halo) + (uint32_t)stage * (uint32_t)q.a_stage_bytes, sbo_a);
+                        uint32_t b_res = sB0 + (uint32_t)cb * b_bytes;                 // resident weights: slot of (tap 0, cb)
+                        for (int kh = 0; kh < q.taps_h; ++kh) {
+                            for (int kw = 0; kw < q.taps_w; ++kw) {
+                                uint32_t b_base = b_res;
+                                if (!q.b_stationary) {
+                                    mbar_wait(&bfull_bar[bstage], bph);
+                                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                    b_base = sB0 + (uint32_t)bstage * b_bytes;
+                                }
+                                const uint64_t da = da0 + (uint64_t)((kh * q.ht_w + kw) * 8);   // 128 B per halo pixel, >> 4
+                                const uint64_t db = make_smem_desc(b_base);
+                                if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_f16(tacc, da + (uint64_t)(k * UMMA_K * 2 / 16), db + (uint64_t)(k * UMMA_K * 2 / 16), idesc,
-                                 (kb | k) ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);
-                    if (++stage == stages) { stage = 0; ph ^= 1; }
+                                    for (int k = 0; k < BK / UMMA_K; ++k)
+                                        umma_f16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc | (uint32_t)k);
+                                    if (!q.b_stationary) umma_commit(&bempty_bar[bstage]);
+                                }
+                                __syncwarp();
+                                acc = 1u;
+                                b_res += (uint32_t)kb_per_tap * b_bytes;
+                                if (!q.b_stationary && ++bstage == q.stages_b) { bstage = 0; bph ^= 1; }
+                            }
+                        }
+                        if (elect_one()) umma_commit(&empty_bar[stage]);
+                        __syncwarp();
+                        if (++stage == stages) { stage = 0; ph ^= 1; }
+                    }
+                } else {
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(&full_bar[stage], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t sa = smem_u32(smem) + (uint32_t)stage * stage_bytes;
+                        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + a_bytes);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k)
+                                umma_f16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc | (uint32_t)k);
+                            umma_commit(&empty_bar[stage]);
+                        }
+                        __syncwarp();
+                        acc = 1u;
+                        if (++stage == stages) { stage = 0; ph ^= 1; }
+                    }
                 }
-                umma_commit(&tfull_bar[buf]);
+                if (elect_one()) umma_commit(&tfull_bar[buf]);
+                __syncwarp();
             }
         }
     } else {
@@ -272,7 +373,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const int phase = t % q.phases;
             const int b = t / q.phases;
             const int n0 = nt * BN;
-            const int oi = th * TILE_H + m / TILE_W, oj = tw * TILE_W + m % TILE_W;
+            const int oi = th * q.tile_h + m / q.tile_w, oj = tw * q.tile_w + m % q.tile_w;
             const bool row_ok = oi < gh && oj < gw;
             const int oh = p.upsample ? 2 * oi + (phase >> 1) : oi;
             const int ow = p.upsample ? 2 * oj + (phase & 1) : oj;
@@ -393,10 +494,10 @@ int encode(CUtensorMap* map, int dtype, int rank, const void* base, const cuuint
     return r == CUDA_SUCCESS ? 0 : FD_ERR_DRIVER;
 }
 
-int act_map(CUtensorMap* map, const void* base, int dtype, int B, int H, int W, int C, int ld, int estride) {
+int act_map(CUtensorMap* map, const void* base, int dtype, int B, int H, int W, int C, int ld, int estride, int box_w, int box_h) {
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-    const cuuint32_t box[4] = {BK, (cuuint32_t)(TILE_W * estride), (cuuint32_t)(TILE_H * estride), 1};
+    const cuuint32_t box[4] = {BK, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     return encode(map, dtype, 4, base, dims, strides, box, estr);
 }
@@ -431,7 +532,8 @@ extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
     int Hout, Wout;
     if (conv_dims(p, &Hout, &Wout)) return 0;
     const int gh = p->upsample ? Hout / 2 : Hout, gw = p->upsample ? Wout / 2 : Wout;   // per-phase output grid
-    if (gh % TILE_H || gw % TILE_W) return 0;
+    const bool box_ok = gh % TILE_H == 0 && gw % TILE_W == 0, halo_ok = gh % 16 == 0 && gw % 8 == 0;
+    if (!box_ok && !(halo_ok && p->stride == 1 && (p->upsample || p->KH * p->KW > 1))) return 0;
     if (p->upsample) {
         if (!(p->KH == 3 && p->KW == 3 && p->stride == 1 && p->pad == 1) || !p->weight_up4 || p->per_batch_weight) return 0;
     } else {
@@ -467,11 +569,40 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     q.n_tiles = p->Cout / q.BN;
     q.fmt = p->dtype == FD_BF16 ? 1 : 0;
     const int gh = q.Hout / (p->upsample ? 2 : 1), gw = q.Wout / (p->upsample ? 2 : 1);
-    q.tiles_h = gh / TILE_H;
-    q.tiles_w = gw / TILE_W;
+    const int num_kb = q.taps_h * q.taps_w * (q.kblocks0 + q.kblocks1);
+    const size_t b_tile = (size_t)q.BN * BK * 2;
+    const size_t kSmemBudget = 212 * 1024;      // data region; + 1 KB alignment slack + 512 B barriers <= the 220 KB opt-in
+    q.halo = (p->stride == 1 && q.taps_h * q.taps_w > 1 && gh % 16 == 0 && gw % 8 == 0 && !getenv("FD_CONV_NO_HALO")) ? 1 : 0;
+    if (q.halo) {
+        q.tile_h = 16; q.tile_w = 8;
+        q.ht_h = q.tile_h + q.taps_h - 1; q.ht_w = q.tile_w + q.taps_w - 1;
+        q.a_stage_bytes = (q.ht_h * q.ht_w * 128 + 1023) & ~1023;
+        q.b_stationary = (q.phases == 1 && !p->per_batch_weight && q.BN == p->Cout &&
+                          num_kb * b_tile + 3 * (size_t)q.a_stage_bytes <= kSmemBudget + 6 * 1024) ? 1 : 0;
+        if (q.b_stationary) {
+            q.stages = (int)((kSmemBudget + 6 * 1024 - num_kb * b_tile) / q.a_stage_bytes);
+            q.stages_b = 0;
+        } else {
+            q.stages = 3;
+            q.stages_b = (int)((kSmemBudget - 3 * (size_t)q.a_stage_bytes) / b_tile);
+            if (q.stages_b > MAX_STAGES) q.stages_b = MAX_STAGES;
+            if (q.stages_b < 2) q.halo = 0;
+            // spend what is left on deeper A prefetch
+            while (q.halo && q.stages < MAX_STAGES &&
+                   (size_t)(q.stages + 1) * q.a_stage_bytes + q.stages_b * b_tile <= kSmemBudget) ++q.stages;
+        }
+        if (q.stages > MAX_STAGES) q.stages = MAX_STAGES;
+    }
+    if (!q.halo) {
+        q.tile_h = TILE_H; q.tile_w = TILE_W; q.ht_h = q.ht_w = q.a_stage_bytes = q.stages_b = q.b_stationary = 0;
+        if (gh % TILE_H || gw % TILE_W) { free(plan); return FD_ERR_UNSUPPORTED; }
+    }
+    q.tiles_h = gh / q.tile_h;
+    q.tiles_w = gw / q.tile_w;
+    const int box_w = q.halo ? q.ht_w : TILE_W, box_h = q.halo ? q.ht_h : TILE_H;
     int rc = act_map(&plan->map_a0, p->src0, p->dtype, p->B, p->Hin, p->Win, p->c0, p->ld0 > 0 ? p->ld0 : p->c0,
-                     p->upsample ? 1 : p->stride);
-    if (!rc && p->c1) rc = act_map(&plan->map_a1, p->src1, p->dtype, p->B, p->Hin, p->Win, p->c1, p->c1, p->upsample ? 1 : p->stride);
+                     p->upsample ? 1 : p->stride, box_w, box_h);
+    if (!rc && p->c1) rc = act_map(&plan->map_a1, p->src1, p->dtype, p->B, p->Hin, p->Win, p->c1, p->c1, p->upsample ? 1 : p->stride, box_w, box_h);
     if (!rc && !p->c1) plan->map_a1 = plan->map_a0;
     if (!rc) {
         const long Kp = (long)q.taps_h * q.taps_w * Cin;
@@ -485,12 +616,16 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     }
     if (rc) { free(plan); return rc; }
     const size_t stage_bytes = BM * BK * 2 + (size_t)q.BN * BK * 2;
-    const int num_kb = q.taps_h * q.taps_w * (q.kblocks0 + q.kblocks1);
-    q.stages = (int)((190 * 1024) / stage_bytes);
-    if (q.stages > MAX_STAGES) q.stages = MAX_STAGES;
-    if (q.stages > 2 * num_kb) q.stages = 2 * num_kb < 2 ? 2 : 2 * num_kb;     // enough to prefetch the next tile
+    if (!q.halo) {
+        q.stages = (int)((190 * 1024) / stage_bytes);
+        if (q.stages > MAX_STAGES) q.stages = MAX_STAGES;
+        if (q.stages > 2 * num_kb) q.stages = 2 * num_kb < 2 ? 2 : 2 * num_kb;     // enough to prefetch the next tile
+    }
     q.total_tiles = p->B * q.phases * q.tiles_h * q.tiles_w * q.n_tiles;
-    plan->smem = (size_t)q.stages * stage_bytes + 1024 /*align slack*/ + 512 /*barriers, gn*/;
+    const size_t data_bytes = q.halo ? (size_t)(q.b_stationary ? num_kb : q.stages_b) * b_tile + (size_t)q.stages * q.a_stage_bytes
+                                     : (size_t)q.stages * stage_bytes;
+    plan->smem = data_bytes + 1024 /*align slack*/ + 512 /*barriers, gn*/;
+    if (plan->smem > 220 * 1024) { free(plan); return FD_ERR_UNSUPPORTED; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

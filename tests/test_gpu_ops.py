@@ -384,6 +384,15 @@ TC_CASES = [
     (128, 0, 64, 3, 1, 1, True, 8, 16),
     (512, 0, 256, 3, 1, 1, True, 8, 16),
     (512, 256, 512, 3, 1, 1, False, 8, 16),
+    # halo mode (16x8 tiles, shifted-window UMMA descriptors): resident weights, weight ring, concat, upsample phases,
+    # and enough tiles that every persistent CTA walks several of them
+    (64, 64, 64, 3, 1, 1, False, 32, 32),
+    (64, 0, 64, 3, 1, 1, False, 128, 128),
+    (64, 64, 64, 3, 1, 1, False, 144, 136),
+    (128, 64, 128, 3, 1, 1, False, 32, 16),
+    (128, 0, 64, 3, 1, 1, True, 16, 16),
+    (128, 0, 64, 3, 1, 1, True, 96, 64),
+    (256, 256, 256, 3, 1, 1, False, 64, 64),
 ]
 
 
