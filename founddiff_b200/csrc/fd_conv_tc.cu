@@ -41,6 +41,12 @@ constexpr int MAX_STAGES = 8;
 constexpr int NUM_EPI_WARPS = 16;
 constexpr int NTHREADS = (2 + NUM_EPI_WARPS) * 32;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, 16 epilogue warps
 
+// n / d for 0 <= n with n * d < 2^32 as one multiply-high (host-precomputed ceil(2^32 / d); d == 1 handled apart)
+struct FastDiv {
+    uint32_t mul, d;
+};
+FD_DEVINL uint32_t fdiv(uint32_t n, const FastDiv& f) { return f.d == 1 ? n : __umulhi(n, f.mul); }
+
 struct TcParams {
     fd_conv_params p;
     int Hout, Wout;
@@ -59,7 +65,23 @@ struct TcParams {
     int a_stage_bytes;      // halo mode: bytes per A stage (1024-aligned)
     int stages_b;           // halo mode: weight ring depth (ignored when b_stationary)
     int b_stationary;       // halo mode: all weight tiles resident in shared memory
+    FastDiv dv_n, dv_w, dv_h, dv_p;   // tile index -> (n tile, tile column, tile row, phase, sample)
+    int tile_w_shift, cpg_shift;
 };
+
+struct TileCoord {
+    int nt, tw, th, phase, b;
+};
+FD_DEVINL TileCoord decode_tile(const TcParams& q, int tile) {
+    TileCoord c;
+    uint32_t t = (uint32_t)tile, u;
+    u = fdiv(t, q.dv_n); c.nt = (int)(t - u * q.dv_n.d); t = u;
+    u = fdiv(t, q.dv_w); c.tw = (int)(t - u * q.dv_w.d); t = u;
+    u = fdiv(t, q.dv_h); c.th = (int)(t - u * q.dv_h.d); t = u;
+    u = fdiv(t, q.dv_p); c.phase = (int)(t - u * q.dv_p.d);
+    c.b = (int)u;
+    return c;
+}
 
 // ---------------------------------------------------------------------------------------------------- PTX helpers
 FD_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,7 +110,11 @@ FD_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Waits that are expected to be long (producer on a full ring, epilogue on the next accumulator): back off so that the
 // spinning warps do not take issue slots from the working ones.
 FD_DEVINL void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+    while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+}
+// epilogue warps waiting for the next accumulator: 16 warps, long waits, and they share schedulers with the MMA warp
+FD_DEVINL void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(200);
 }
 FD_DEVINL void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
@@ -110,6 +136,32 @@ FD_DEVINL void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint3
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// the four K = 16 steps of one 64-channel K block: descriptors advance by 32 B (2 descriptor units) per step
+FD_DEVINL void umma_f16_x4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+        "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"
+        "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all taps of one 64-channel slice against resident weights, fully unrolled: the A window offsets are immediates and the
+// issue stream is nothing but descriptor adds and MMAs (the issuing thread is the critical path for N = 64 tiles)
+template <int TAPS_H, int TAPS_W, int HT_W>
+FD_DEVINL void umma_taps_resident(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t tap_stride, uint32_t idesc, uint32_t accumulate) {
+#pragma unroll
+    for (int kh = 0; kh < TAPS_H; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < TAPS_W; ++kw) {
+            umma_f16_x4(tmem_d, da + (uint64_t)((kh * HT_W + kw) * 8), db, idesc, (kh | kw) ? 1u : accumulate);
+            db += tap_stride;
+        }
 }
 FD_DEVINL bool elect_one() {      // one lane of the (converged) warp; the same lane every time
     uint32_t pred;
@@ -236,13 +288,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 for (int kb = 0; kb < num_kb; ++kb) tma_load_3d(sB_halo + (size_t)kb * b_bytes, &map_w, wfull_bar, kb * BK, 0, 0);
             }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int t = tile;
-                const int nt = t % q.n_tiles; t /= q.n_tiles;
-                const int tw = t % q.tiles_w; t /= q.tiles_w;
-                const int th = t % q.tiles_h; t /= q.tiles_h;
-                const int phase = t % q.phases;
-                const int b = t / q.phases;
-                const int ho0 = th * q.tile_h, wo0 = tw * q.tile_w, n0 = nt * BN;
+                const TileCoord tc = decode_tile(q, tile);
+                const int phase = tc.phase, b = tc.b;
+                const int ho0 = tc.th * q.tile_h, wo0 = tc.tw * q.tile_w, n0 = tc.nt * BN;
                 int hbase, wbase;
                 if (p.upsample) { hbase = ho0 - 1 + (phase >> 1); wbase = wo0 - 1 + (phase & 1); }
                 else { hbase = ho0 * p.stride - p.pad; wbase = wo0 * p.stride - p.pad; }
@@ -301,35 +349,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 if (q.halo) {
                     const uint32_t sbo_a = (uint32_t)q.ht_w * 128u;
                     const uint32_t sB0 = smem_u32(sB_halo);
+                    const uint32_t tap_stride = (uint32_t)kb_per_tap * (b_bytes >> 4);        // resident weights: descriptor units
+                    const uint32_t row_skip = (uint32_t)(q.ht_w - q.taps_w) * 8u;
                     for (int cb = 0; cb < kb_per_tap; ++cb) {
                         mbar_wait(&full_bar[stage], ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint64_t da0 = make_smem_desc(smem_u32(sA_halo) + (uint32_t)stage * (uint32_t)q.a_stage_bytes, sbo_a);
-                        uint32_t b_res = sB0 + (uint32_t)cb * b_bytes;                 // resident weights: slot of (tap 0, cb)
-                        for (int kh = 0; kh < q.taps_h; ++kh) {
-                            for (int kw = 0; kw < q.taps_w; ++kw) {
-                                uint32_t b_base = b_res;
-                                if (!q.b_stationary) {
-                                    mbar_wait(&bfull_bar[bstage], bph);
-                                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                                    b_base = sB0 + (uint32_t)bstage * b_bytes;
+                        const int bstage_in = bstage;
+                        const uint32_t bph_in = bph;
+                        if (elect_one()) {      // one thread runs the whole tap loop of this 64-channel slice
+                            uint64_t da = make_smem_desc(smem_u32(sA_halo) + (uint32_t)stage * (uint32_t)q.a_stage_bytes, sbo_a);
+                            uint64_t db = make_smem_desc(sB0 + (uint32_t)cb * b_bytes);       // resident: slot of (tap 0, cb)
+                            if (q.b_stationary && q.taps_h == 3 && q.taps_w == 3) {
+                                umma_taps_resident<3, 3, 10>(tacc, da, db, tap_stride, idesc, acc);
+                            } else
+                            for (int kh = 0; kh < q.taps_h; ++kh) {
+                                for (int kw = 0; kw < q.taps_w; ++kw) {
+                                    if (!q.b_stationary) {
+                                        mbar_wait(&bfull_bar[bstage], bph);
+                                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                        db = make_smem_desc(sB0 + (uint32_t)bstage * b_bytes);
+                                    }
+                                    umma_f16_x4(tacc, da, db, idesc, acc);
+                                    acc = 1u;
+                                    if (!q.b_stationary) {
+                                        umma_commit(&bempty_bar[bstage]);
+                                        if (++bstage == q.stages_b) { bstage = 0; bph ^= 1; }
+                                    }
+                                    da += 8u;                    // next halo pixel (128 B >> 4)
+                                    db += tap_stride;
                                 }
-                                const uint64_t da = da0 + (uint64_t)((kh * q.ht_w + kw) * 8);   // 128 B per halo pixel, >> 4
-                                const uint64_t db = make_smem_desc(b_base);
-                                if (elect_one()) {
-#pragma unroll
-                                    for (int k = 0; k < BK / UMMA_K; ++k)
-                                        umma_f16(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, acc | (uint32_t)k);
-                                    if (!q.b_stationary) umma_commit(&bempty_bar[bstage]);
-                                }
-                                __syncwarp();
-                                acc = 1u;
-                                b_res += (uint32_t)kb_per_tap * b_bytes;
-                                if (!q.b_stationary && ++bstage == q.stages_b) { bstage = 0; bph ^= 1; }
+                                da += row_skip;
                             }
+                            umma_commit(&empty_bar[stage]);
                         }
-                        if (elect_one()) umma_commit(&empty_bar[stage]);
                         __syncwarp();
+                        // the ring position is warp-uniform state: every lane advances it the same way
+                        if (!q.b_stationary) {
+                            const int adv = bstage_in + q.taps_h * q.taps_w;
+                            bph = bph_in ^ (uint32_t)((adv / q.stages_b) & 1);
+                            bstage = adv % q.stages_b;
+                        }
+                        acc = 1u;
                         if (++stage == stages) { stage = 0; ph ^= 1; }
                     }
                 } else {
@@ -362,38 +422,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int gh = q.Hout / (p.upsample ? 2 : 1), gw = q.Wout / (p.upsample ? 2 : 1);
         T* out = (T*)p.out;
         const T* addend = (const T*)p.addend;
-        const int cpg = p.gn_sums ? p.Cout / p.gn_groups : 8;
-        int cur_b = -1;
+        // GroupNorm partial sums: every lane accumulates its own pixel's contribution per 8-column half (8 consecutive
+        // columns always share a group, cpg >= 8) across tiles; lanes are only reduced when the sample (or, with several
+        // N tiles, the column set) changes.
+        float gacc_s[4][2], gacc_q[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { gacc_s[i][0] = gacc_s[i][1] = gacc_q[i][0] = gacc_q[i][1] = 0.f; }
+        int cur_b = -1, cur_n0 = 0;
+        auto gn_reduce_to_smem = [&]() {               // warp-reduce the lane accumulators into the block's s_gn
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+                if (ci * 16 < cols_per_warp) {
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const float sv = fd_warp_sum(gacc_s[ci][hf]), qv = fd_warp_sum(gacc_q[ci][hf]);
+                        if (lane == 0) {
+                            const int g = (cur_n0 + cg * cols_per_warp + ci * 16 + hf * 8) >> q.cpg_shift;
+                            atomicAdd(&s_gn[g], sv);
+                            atomicAdd(&s_gn[8 + g], qv);
+                        }
+                        gacc_s[ci][hf] = gacc_q[ci][hf] = 0.f;
+                    }
+                }
+            }
+        };
+        auto gn_flush_sample = [&]() {                 // all 16 epilogue warps: block sums of sample cur_b -> global
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            const int et = threadIdx.x - 64;
+            if (cur_b >= 0 && et < 2 * p.gn_groups) {
+                const int which = et / p.gn_groups, g = et % p.gn_groups;
+                atomicAdd(&p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which], s_gn[which * 8 + g]);
+                s_gn[which * 8 + g] = 0.f;
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+        };
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            int t = tile;
-            const int nt = t % q.n_tiles; t /= q.n_tiles;
-            const int tw = t % q.tiles_w; t /= q.tiles_w;
-            const int th = t % q.tiles_h; t /= q.tiles_h;
-            const int phase = t % q.phases;
-            const int b = t / q.phases;
-            const int n0 = nt * BN;
-            const int oi = th * q.tile_h + m / q.tile_w, oj = tw * q.tile_w + m % q.tile_w;
+            const TileCoord tc = decode_tile(q, tile);
+            const int phase = tc.phase, b = tc.b;
+            const int n0 = tc.nt * BN;
+            const int oi = tc.th * q.tile_h + (m >> q.tile_w_shift), oj = tc.tw * q.tile_w + (m & (q.tile_w - 1));
             const bool row_ok = oi < gh && oj < gw;
             const int oh = p.upsample ? 2 * oi + (phase >> 1) : oi;
             const int ow = p.upsample ? 2 * oj + (phase & 1) : oj;
             const long orow = (((long)b * q.Hout + oh) * q.Wout + ow) * p.Cout;
-            if (p.gn_sums && b != cur_b) {             // flush the previous sample's partial sums (uniform over the 16 warps)
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                const int et = threadIdx.x - 64;
-                if (cur_b >= 0 && et < 2 * p.gn_groups) {
-                    const int which = et / p.gn_groups, g = et % p.gn_groups;
-                    atomicAdd(&p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which], s_gn[which * 8 + g]);
-                    s_gn[which * 8 + g] = 0.f;
-                }
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                cur_b = b;
+            if (p.gn_sums && (b != cur_b || n0 != cur_n0)) {       // uniform over the 16 warps
+                if (cur_b >= 0) gn_reduce_to_smem();
+                if (b != cur_b) { gn_flush_sample(); cur_b = b; }
+                cur_n0 = n0;
             }
             const int buf = it & 1;
-            mbar_wait_backoff(&tfull_bar[buf], (it >> 1) & 1);
+            mbar_wait_long(&tfull_bar[buf], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q4 * 32) << 16);
-            for (int cc = 0; cc < cols_per_warp; cc += 16) {
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+                const int cc = ci * 16;
+                if (cc >= cols_per_warp) break;
                 const int c = cg * cols_per_warp + cc;
                 uint32_t r[16];
                 tmem_ld16(tacc + (uint32_t)c, r);
@@ -418,26 +503,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fast_silu(v[j]);
                 }
-                if (p.gn_sums) {                       // 8 consecutive columns always share a group (cpg >= 8)
+                if (p.gn_sums && row_ok) {
 #pragma unroll
-                    for (int g0 = 0; g0 < 16; g0 += 8) {
-                        float s = 0.f, ss = 0.f;
+                    for (int hf = 0; hf < 2; ++hf) {
+                        float sv = 0.f, qv = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float x = row_ok ? v[g0 + j] : 0.f; s += x; ss = fmaf(x, x, ss); }
-                        s = fd_warp_sum(s);
-                        ss = fd_warp_sum(ss);
-                        if (lane == 0) {
-                            const int g = (n + g0) / cpg;
-                            atomicAdd(&s_gn[g], s);
-                            atomicAdd(&s_gn[8 + g], ss);
-                        }
+                        for (int j = 0; j < 8; ++j) { const float x = v[hf * 8 + j]; sv += x; qv = fmaf(x, x, qv); }
+                        gacc_s[ci][hf] += sv;
+                        gacc_q[ci][hf] += qv;
                     }
                 }
                 if (row_ok) {
                     if (p.gate) {
                         const float* gp = p.gate + (long)b * p.gate_stride + n;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] *= __ldg(gp + j);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 gv = __ldg(reinterpret_cast<const float4*>(gp + j));
+                            v[j] *= gv.x; v[j + 1] *= gv.y; v[j + 2] *= gv.z; v[j + 3] *= gv.w;
+                        }
                     }
                     if (addend) {
                         float a[16];
@@ -450,12 +533,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
         }
         if (p.gn_sums) {
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            const int et = threadIdx.x - 64;
-            if (cur_b >= 0 && et < 2 * p.gn_groups) {
-                const int which = et / p.gn_groups, g = et % p.gn_groups;
-                atomicAdd(&p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which], s_gn[which * 8 + g]);
-            }
+            if (cur_b >= 0) gn_reduce_to_smem();
+            gn_flush_sample();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -622,6 +701,17 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
         if (q.stages > 2 * num_kb) q.stages = 2 * num_kb < 2 ? 2 : 2 * num_kb;     // enough to prefetch the next tile
     }
     q.total_tiles = p->B * q.phases * q.tiles_h * q.tiles_w * q.n_tiles;
+    {
+        auto mk = [](int d) { FastDiv f; f.d = (uint32_t)d; f.mul = d > 1 ? (uint32_t)((((uint64_t)1 << 32) + d - 1) / d) : 0u; return f; };
+        q.dv_n = mk(q.n_tiles); q.dv_w = mk(q.tiles_w); q.dv_h = mk(q.tiles_h); q.dv_p = mk(q.phases);
+        int dmax = q.n_tiles;
+        if (q.tiles_w > dmax) dmax = q.tiles_w;
+        if (q.tiles_h > dmax) dmax = q.tiles_h;
+        if ((uint64_t)q.total_tiles * (uint64_t)dmax >= ((uint64_t)1 << 32)) { free(plan); return FD_ERR_UNSUPPORTED; }
+        q.tile_w_shift = q.tile_w == 8 ? 3 : 4;
+        q.cpg_shift = 3;
+        if (p->gn_sums) { int cpg = p->Cout / p->gn_groups; q.cpg_shift = 0; while ((1 << q.cpg_shift) < cpg) ++q.cpg_shift; }
+    }
     const size_t data_bytes = q.halo ? (size_t)(q.b_stationary ? num_kb : q.stages_b) * b_tile + (size_t)q.stages * q.a_stage_bytes
                                      : (size_t)q.stages * stage_bytes;
     plan->smem = data_bytes + 1024 /*align slack*/ + 512 /*barriers, gn*/;
