@@ -140,9 +140,12 @@ def algorithmic(name, detail, es):
     """(bytes, flops) one launch must move / compute at minimum, from the op's shape string."""
     try:
         if name in ("selective_scan", "selective_scan_merge"):
-            dims, n = detail.split(" N")
+            fused = detail.endswith(" dt-fused")       # delta formed in-kernel from the rank-R rows of x_dbl (R == N here)
+            dims, n = detail.replace(" dt-fused", "").split(" N")
             b, kd, L = map(int, dims.split("x"))
             n = int(n)
+            if fused:
+                return 2.0 * b * kd * L * es + 3.0 * b * 4 * n * L * 4, (9.0 * n + 2.0 * n) * b * kd * L
             return 3.0 * b * kd * L * es + 2.0 * b * 4 * n * L * 4, 9.0 * b * kd * L * n
         if name in ("ln_modulate", "gn_silu_add", "ln_gate"):
             b, p, c = map(int, detail.split("x"))
@@ -167,6 +170,11 @@ def algorithmic(name, detail, es):
             b, d, L = map(int, dims.split("x"))
             r, n = int(r), int(n)
             return 2.0 * b * 4 * d * L * es + 2.0 * b * 4 * n * L * 4, 2.0 * b * 4 * L * d * (2 * r + 2 * n)
+        if name == "x_proj_tc":
+            dims, r, n = detail.replace(" R", " ").replace(" N", " ").split(" ")
+            b, d, L = map(int, dims.split("x"))
+            r, n = int(r), int(n)
+            return b * 4.0 * d * L * es + b * 4.0 * (r + 2 * n) * L * 4, 2.0 * b * 4 * L * d * (r + 2 * n)
         if name == "init_conv7x7":
             b, h, w = map(int, detail.split("x"))
             return b * h * w * (8.0 + 64 * es), 2.0 * b * h * w * 98 * 64

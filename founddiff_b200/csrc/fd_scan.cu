@@ -228,14 +228,18 @@ template <typename T> FD_DEVINL void raw_to_float(const RawItems<T>& r, float (&
 // straight into the channels-last tensor y_nhwc (B, H, W, dim/4) at the pixel each (direction, l) stands for.
 // One block barrier per chunk: the barrier that publishes chunk c's B/C also retires chunk c-1 (its staging buffer may
 // be refilled, its transposed outputs may be written out while the warps already work on chunk c).
-template <typename T, int NS, int NBUF, bool MERGE>
+// RDT > 0 fuses dt_proj: `dtr` holds the rank-RDT dt input rows (fp32, same group layout as B / C with `gstride` floats
+// between direction groups), dt_w the (dim, RDT) projection; delta is formed per step in registers and `delta` is unused.
+template <typename T, int NS, int NBUF, bool MERGE, int RDT = 0>
 __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selective_scan_smem_kernel(
     const T* __restrict__ u, const T* __restrict__ delta, const float* __restrict__ A, const float* __restrict__ Bm,
     const float* __restrict__ Cm, const float* __restrict__ D, const float* __restrict__ delta_bias, T* __restrict__ y,
-    int dim, int L, int G, int softplus, int H, int W) {
-    extern __shared__ __align__(16) float s_bc[];          // [NBUF][2][NS][kPadChunk] (+ A*log2e for NS >= 16) (+ s_y)
+    int dim, int L, int G, int softplus, int H, int W, const float* __restrict__ dtr = nullptr,
+    const float* __restrict__ dt_w = nullptr, long gstride = 0) {
+    extern __shared__ __align__(16) float s_bc[];          // [NBUF][2*NS + RDT][kPadChunk] (+ A*log2e for NS >= 16) (+ s_y)
     constexpr bool kA2InSmem = NS >= 16;                   // keeps the register count at two blocks per SM for large d_state
-    float* s_a2 = s_bc + (size_t)NBUF * 2 * NS * kPadChunk;
+    constexpr int kRows = 2 * NS + RDT;                    // staged rows per chunk: B, C, (dt input)
+    float* s_a2 = s_bc + (size_t)NBUF * kRows * kPadChunk;
     T* s_y = reinterpret_cast<T*>(s_a2 + (kA2InSmem ? kRowsPerBlock * NS : 0));     // [2][8][kChunk] (MERGE only)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per_group = dim / G;
@@ -243,8 +247,10 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selecti
     const int bg = blockIdx.x / blocks_per_group;          // b * G + g
     const int dloc0 = (blockIdx.x % blocks_per_group) * kRowsPerBlock;
     const int b = bg / G;
-    const float* Bg = Bm + (long)bg * NS * L;
-    const float* Cg = Cm + (long)bg * NS * L;
+    const long gs = RDT > 0 ? gstride : (long)NS * L;
+    const float* Bg = Bm + (long)bg * gs;
+    const float* Cg = Cm + (long)bg * gs;
+    const float* Tg = RDT > 0 ? dtr + (long)bg * gs : nullptr;
 
     const int d = (bg % G) * per_group + dloc0 + warp;
     const long row = (long)b * dim + d;
@@ -259,18 +265,23 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selecti
         if constexpr (!kA2InSmem) A2[n] = A[(long)d * NS + n] * 1.4426950408889634f;
         h[n] = 0.f;
     }
+    float wdt[RDT > 0 ? RDT : 1];
+    if constexpr (RDT > 0) {
+#pragma unroll
+        for (int r = 0; r < RDT; ++r) wdt[r] = dt_w[(long)d * RDT + r];
+    }
     if constexpr (kA2InSmem) {
         for (int n = lane; n < NS; n += 32) s_a2[warp * NS + n] = A[(long)d * NS + n] * 1.4426950408889634f;
         __syncwarp();
     }
 
     auto stage = [&](int c0, int buf) {   // cooperative cp.async of B/C[:, c0 : c0+256] (zero-filled past L)
-        float* dst = s_bc + (size_t)buf * 2 * NS * kPadChunk;
+        float* dst = s_bc + (size_t)buf * kRows * kPadChunk;
 #pragma unroll
-        for (int i = threadIdx.x; i < 2 * NS * (kChunk / 4); i += kRowsPerBlock * 32) {
-            const int v = i % (kChunk / 4), rn = i / (kChunk / 4);     // rn: 0..NS-1 = B rows, NS..2NS-1 = C rows
+        for (int i = threadIdx.x; i < kRows * (kChunk / 4); i += kRowsPerBlock * 32) {
+            const int v = i % (kChunk / 4), rn = i / (kChunk / 4);     // rn: 0..NS-1 = B rows, NS..2NS-1 = C rows, then dt rows
             const int l = c0 + v * 4;
-            const float* src = (rn < NS ? Bg + (long)rn * L : Cg + (long)(rn - NS) * L) + l;
+            const float* src = (rn < NS ? Bg + (long)rn * L : rn < 2 * NS ? Cg + (long)(rn - NS) * L : Tg + (long)(rn - 2 * NS) * L) + l;
             cp_async16(dst + rn * kPadChunk + pad_idx(v * 4), l < L ? src : Bg, l < L);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -302,7 +313,8 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selecti
     stage(0, 0);
     // rows are kItems-aligned (launcher), so a lane's 8 steps are all inside or all outside the row; outside lanes read a
     // clamped (valid) address and are masked through dt = 0
-    RawItems<T> dt_raw = load_raw<T>(dr + min(lane * kItems, L - kItems));
+    RawItems<T> dt_raw;
+    if constexpr (RDT == 0) dt_raw = load_raw<T>(dr + min(lane * kItems, L - kItems));
     RawItems<T> u_raw = load_raw<T>(ur + min(lane * kItems, L - kItems));
 
     for (int c = 0; c < nchunks; ++c) {
@@ -312,12 +324,27 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selecti
         __syncthreads();                  // chunk c's B/C visible to all; every warp is past chunk c-1
         if (NBUF == 2 && c + 1 < nchunks) stage(c0 + kChunk, buf ^ 1);
         if (c > 0) merge_store(c - 1);
-        const float* sB = s_bc + (size_t)buf * 2 * NS * kPadChunk + pad_idx(lane * kItems);
+        const float* sB = s_bc + (size_t)buf * kRows * kPadChunk + pad_idx(lane * kItems);
         const float* sC = sB + NS * kPadChunk;
         float dt[kItems], dtu[kItems], yacc[kItems];
         {
             float dtv[kItems], uv[kItems];
-            raw_to_float<T>(dt_raw, dtv);
+            if constexpr (RDT == 0) {
+                raw_to_float<T>(dt_raw, dtv);
+            } else {                                  // dt_proj: delta = dt_w[d, :] . x_dbl[:R, l]
+#pragma unroll
+                for (int i = 0; i < kItems; ++i) dtv[i] = 0.f;
+                const float* sT = sB + 2 * NS * kPadChunk;
+#pragma unroll
+                for (int r = 0; r < RDT; ++r) {
+                    const float4 t0 = *reinterpret_cast<const float4*>(sT + r * kPadChunk);
+                    const float4 t1 = *reinterpret_cast<const float4*>(sT + r * kPadChunk + 4);
+                    dtv[0] = fmaf(wdt[r], t0.x, dtv[0]); dtv[1] = fmaf(wdt[r], t0.y, dtv[1]);
+                    dtv[2] = fmaf(wdt[r], t0.z, dtv[2]); dtv[3] = fmaf(wdt[r], t0.w, dtv[3]);
+                    dtv[4] = fmaf(wdt[r], t1.x, dtv[4]); dtv[5] = fmaf(wdt[r], t1.y, dtv[5]);
+                    dtv[6] = fmaf(wdt[r], t1.z, dtv[6]); dtv[7] = fmaf(wdt[r], t1.w, dtv[7]);
+                }
+            }
             raw_to_float<T>(u_raw, uv);
             const bool live = l0 < L;
 #pragma unroll
@@ -332,7 +359,7 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selecti
         }
         if (c + 1 < nchunks) {          // prefetch the next chunk's u / delta (raw: consumed after the next barrier)
             const int ln = min(l0 + kChunk, L - kItems);
-            dt_raw = load_raw<T>(dr + ln);
+            if constexpr (RDT == 0) dt_raw = load_raw<T>(dr + ln);
             u_raw = load_raw<T>(ur + ln);
         }
         float sdt = 0.f;
@@ -456,6 +483,47 @@ extern "C" int fd_selective_scan_fwd(const void* u, const void* delta, const flo
                       return scan_launch<T>(u, delta, A, Bm, Cm, D, delta_bias, y, batch, dim, seqlen, dstate, ngroups,
                                             delta_softplus, stream));
     return 0;
+}
+
+// Scan + EfficientMerge + fused dt_proj (see include/founddiff_b200.h)
+template <typename T, int NS, int RDT>
+static int scan_xdbl_launch(const void* u, const float* x_dbl, const float* dt_w, const float* A, const float* D,
+                            const float* delta_bias, void* y, int batch, int dim, int H, int W, int softplus, cudaStream_t st) {
+    const int L = (H / 2) * (W / 2);
+    constexpr int kRows = 2 * NS + RDT;
+    const size_t smem = (size_t)2 * kRows * kPadChunk * sizeof(float) + (size_t)2 * kRowsPerBlock * kChunk * sizeof(T);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NS, 2, true, RDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    const long rows = (long)batch * dim;
+    selective_scan_smem_kernel<T, NS, 2, true, RDT><<<(unsigned)(rows / kRowsPerBlock), kRowsPerBlock * 32, smem, st>>>(
+        (const T*)u, nullptr, A, x_dbl + (long)RDT * L, x_dbl + (long)(RDT + NS) * L, D, delta_bias, (T*)y, dim, L, 4, softplus, H, W,
+        x_dbl, dt_w, (long)kRows * L);
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fd_selective_scan_fwd_merge_xdbl(const void* u, const float* x_dbl, const float* dt_w, const float* A, const float* D,
+                                                const float* delta_bias, void* y_nhwc, int batch, int dim, int H, int W, int dstate,
+                                                int dt_rank, int delta_softplus, int io_dtype, cudaStream_t stream) {
+    if (!u || !x_dbl || !dt_w || !A || !y_nhwc) return FD_ERR_BAD_ARGUMENT;
+    if (batch <= 0 || dim <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || dim % 4) return FD_ERR_BAD_ARGUMENT;
+    const int L = (H / 2) * (W / 2);
+    if (L % kItems || L < kItems || (dim / 4) % kRowsPerBlock || (((uintptr_t)u | (uintptr_t)y_nhwc | (uintptr_t)x_dbl) & 15))
+        return FD_ERR_UNSUPPORTED;
+#define XDBL_CASE(NSV, RV)                                                                                              \
+    if (dstate == NSV && dt_rank == RV) {                                                                               \
+        if (io_dtype == FD_BF16)                                                                                        \
+            return scan_xdbl_launch<__nv_bfloat16, NSV, RV>(u, x_dbl, dt_w, A, D, delta_bias, y_nhwc, batch, dim, H, W, delta_softplus, stream); \
+        if (io_dtype == FD_F16)                                                                                         \
+            return scan_xdbl_launch<__half, NSV, RV>(u, x_dbl, dt_w, A, D, delta_bias, y_nhwc, batch, dim, H, W, delta_softplus, stream); \
+    }
+    XDBL_CASE(4, 4) XDBL_CASE(8, 8)
+#undef XDBL_CASE
+    return FD_ERR_UNSUPPORTED;
 }
 
 // Scan + EfficientMerge: same inputs as fd_selective_scan_fwd (4 direction groups, L = H/2 * W/2), output written

@@ -9,6 +9,7 @@
 //   k in {1,3} (odd  h): l = (w/2)*(H/2) + (h/2)   (column-major sub-grid)            emamba2.py:207-210
 // Both transposing kernels stage a 32x32-pixel x 16-channel tile in shared memory so that global reads are
 // 16-byte vectors along channels and global writes are 16-byte vectors along l (and vice versa).
+#include <stdlib.h>
 #include <type_traits>
 
 #include "fd_common.cuh"
@@ -473,6 +474,173 @@ __global__ void __launch_bounds__(256) xdt_proj_mma_kernel(const T* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// x_proj only (dt_rank <= 8 levels): X_dbl[b, k, c, l] = sum_d Wx[k, c, d] * xs[b, k, d, l], all R + 2N rows written in
+// fp32 to ONE tensor (B, 4, R+2N, L).  The scan kernel reads its B / C rows from it and applies the rank-R dt_proj
+// itself (R FMAs per step), so the (B, 4, D, L) delta tensor is never written or read: the op becomes a single
+// streaming pass over xs.  128-step tiles, 8 warps x 16 columns, 32-channel chunks through a 3-stage cp.async ring.
+constexpr int XP_STAGES = 3;
+FD_DEVINL void xp_cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+// WITH_DT = true is the pipelined form of xdt_proj_mma_kernel: B / C rows go to Bs / Cs, the R dt rows stay in shared
+// memory (16-bit) and the second GEMM (dt_proj, K = Rp) produces the (B, 4, D, L) delta tensor.
+template <typename T, int MT, bool WITH_DT>
+__global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ xs, const T* __restrict__ xw16,
+                                                         float* __restrict__ xdbl, int D, int L, int CC,
+                                                         const T* __restrict__ dw16 = nullptr, T* __restrict__ dts = nullptr,
+                                                         float* __restrict__ Bs = nullptr, float* __restrict__ Cs = nullptr,
+                                                         int R = 0, int N = 0, int Rp = 0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_x = reinterpret_cast<T*>(smem_raw);                     // [XP_STAGES][XT_KC][XT_XLD]
+    T* s_w = s_x + XP_STAGES * XT_KC * XT_XLD;                   // [XP_STAGES][MT*16][XT_WLD]
+    T* s_xd = s_w + XP_STAGES * MT * 16 * XT_WLD;                // WITH_DT: [32][XT_XLD] first Rp rows of X_dbl
+    T* s_o = s_xd + 32 * XT_XLD;                                 // WITH_DT: [8 warps][16][XT_XLD] output staging
+    constexpr int CCp = MT * 16;
+    const int bk = blockIdx.y, k = bk & 3;
+    const int l0 = blockIdx.x * XT_L;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const T* xr = xs + (long)bk * D * L;
+    const T* wx = xw16 + (long)k * CCp * D;
+    const int nchunks = D / XT_KC;
+
+    auto stage = [&](int ch, int buf) {
+        const int d0 = ch * XT_KC;
+        T* sx = s_x + buf * XT_KC * XT_XLD;
+        T* sw = s_w + buf * CCp * XT_WLD;
+        for (int i = tid; i < XT_KC * (XT_L / 8); i += 256) {
+            const int r = i / (XT_L / 8), v = i % (XT_L / 8);
+            const bool ok = l0 + v * 8 < L;                       // L % 8 == 0: vectors are all-in or all-out
+            xp_cp_async16(sx + r * XT_XLD + v * 8, ok ? xr + (long)(d0 + r) * L + l0 + v * 8 : xr, ok);
+        }
+        for (int i = tid; i < CCp * (XT_KC / 8); i += 256) {
+            const int r = i / (XT_KC / 8), v = i % (XT_KC / 8);
+            xp_cp_async16(sw + r * XT_WLD + v * 8, wx + (long)r * D + d0 + v * 8, true);
+        }
+    };
+
+    float acc[MT][2][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < XP_STAGES - 1; ++s) {
+        if (s < nchunks) stage(s, s);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(XP_STAGES - 2) : "memory");
+        __syncthreads();                                          // chunk ch landed; everyone is done with chunk ch-1's buffer
+        if (ch + XP_STAGES - 1 < nchunks) stage(ch + XP_STAGES - 1, (ch + XP_STAGES - 1) % XP_STAGES);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const T* sx = s_x + (ch % XP_STAGES) * XT_KC * XT_XLD;
+        const T* sw = s_w + (ch % XP_STAGES) * CCp * XT_WLD;
+#pragma unroll
+        for (int ks = 0; ks < XT_KC / 16; ++ks) {
+            uint32_t bfr[4];
+            ldmatrix_x4_trans(bfr, sx + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * XT_XLD + warp * 16 + 8 * (lane >> 4));
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                uint32_t afr[4];
+                ldmatrix_x4(afr, sw + (mt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * XT_WLD + ks * 16 + 8 * (lane >> 4));
+                mma_16816<T>(acc[mt][0], afr, bfr[0], bfr[1]);
+                mma_16816<T>(acc[mt][1], afr, bfr[2], bfr[3]);
+            }
+        }
+    }
+    if constexpr (!WITH_DT) {
+        float* orow = xdbl + (long)bk * CC * L + l0;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int c = mt * 16 + g + 8 * hh;
+                    const int col = warp * 16 + nt * 8 + 2 * t4;
+                    if (c < CC && l0 + col < L)
+                        *reinterpret_cast<float2*>(orow + (long)c * L + col) = make_float2(acc[mt][nt][2 * hh], acc[mt][nt][2 * hh + 1]);
+                }
+    } else {
+        // stage-1 epilogue: Bs / Cs (fp32, global) and the dt rows (16-bit, shared)
+        for (int i = tid; i < 32 * XT_XLD / 8; i += 256) *reinterpret_cast<uint4*>(s_xd + i * 8) = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int c = mt * 16 + g + 8 * hh;
+                    const int col = warp * 16 + nt * 8 + 2 * t4;
+                    const float v0 = acc[mt][nt][2 * hh], v1 = acc[mt][nt][2 * hh + 1];
+                    if (c < R) {
+                        fd_st(s_xd + c * XT_XLD + col, v0);
+                        fd_st(s_xd + c * XT_XLD + col + 1, v1);
+                    } else if (c < CC && l0 + col < L) {
+                        float* dst = (c < R + N ? Bs + ((long)bk * N + (c - R)) * L : Cs + ((long)bk * N + (c - R - N)) * L) + l0 + col;
+                        *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+                    }
+                }
+        __syncthreads();
+        // stage 2: each warp takes m-tiles (16 channels d) round-robin, all 128 l
+        const T* wd = dw16 + (long)k * D * Rp;
+        T* so = s_o + warp * 16 * XT_XLD;
+        T* dr = dts + (long)bk * D * L;
+        for (int mtile = warp; mtile * 16 < D; mtile += 8) {
+            const int dbase = mtile * 16;
+            float o[16][4];
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+            for (int ks = 0; ks < Rp / 16; ++ks) {
+                uint32_t afr[4];
+                const T* w0 = wd + (long)(dbase + g) * Rp + ks * 16 + 2 * t4;
+                const T* w1 = wd + (long)(dbase + g + 8) * Rp + ks * 16 + 2 * t4;
+                afr[0] = *reinterpret_cast<const uint32_t*>(w0);
+                afr[1] = *reinterpret_cast<const uint32_t*>(w1);
+                afr[2] = *reinterpret_cast<const uint32_t*>(w0 + 8);
+                afr[3] = *reinterpret_cast<const uint32_t*>(w1 + 8);
+#pragma unroll
+                for (int np = 0; np < 8; ++np) {
+                    uint32_t bfr[4];
+                    ldmatrix_x4_trans(bfr, s_xd + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * XT_XLD + np * 16 + 8 * (lane >> 4));
+                    mma_16816<T>(o[2 * np], afr, bfr[0], bfr[1]);
+                    mma_16816<T>(o[2 * np + 1], afr, bfr[2], bfr[3]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+                const int col = nt * 8 + 2 * t4;
+                if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                    *reinterpret_cast<__nv_bfloat162*>(so + g * XT_XLD + col) = __floats2bfloat162_rn(o[nt][0], o[nt][1]);
+                    *reinterpret_cast<__nv_bfloat162*>(so + (g + 8) * XT_XLD + col) = __floats2bfloat162_rn(o[nt][2], o[nt][3]);
+                } else {
+                    *reinterpret_cast<__half2*>(so + g * XT_XLD + col) = __floats2half2_rn(o[nt][0], o[nt][1]);
+                    *reinterpret_cast<__half2*>(so + (g + 8) * XT_XLD + col) = __floats2half2_rn(o[nt][2], o[nt][3]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {       // 16 rows x 256 B: lanes write 16-byte chunks, two rows per instruction
+                const int r = it * 2 + (lane >> 4), v = lane & 15;
+                if (dbase + r < D && l0 + v * 8 < L)
+                    *reinterpret_cast<uint4*>(dr + (long)(dbase + r) * L + l0 + v * 8) = *reinterpret_cast<const uint4*>(so + r * XT_XLD + v * 8);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // merge, pass 1: per-pixel LayerNorm statistics straight from the scan layout (thread per l, loop over d).
 template <typename T>
 __global__ void __launch_bounds__(256) merge_stats_kernel(const T* __restrict__ ys, float* __restrict__ stats, int H, int W,
@@ -634,6 +802,24 @@ static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, vo
     const int CC = R + 2 * N;
     const int MT = (CC + 15) / 16;
     dim3 grid(fd_cdiv(L, XT_L), B * 4);
+    if (D % XT_KC == 0 && L % 8 == 0 && !getenv("FD_XDT_NO_PIPE")) {       // pipelined stage 1 (cp.async ring)
+#define XDT_PIPE_CASE(M)                                                                                                       \
+    if (MT == M) {                                                                                                             \
+        const size_t smem = ((size_t)XP_STAGES * ((size_t)XT_KC * XT_XLD + (size_t)M * 16 * XT_WLD) + 32 * XT_XLD + 8 * 16 * XT_XLD) * sizeof(T); \
+        static bool attr_set = false;                                                                                          \
+        if (!attr_set) {                                                                                                       \
+            cudaError_t e = cudaFuncSetAttribute(x_proj_mma_kernel<T, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                                                               \
+            attr_set = true;                                                                                                   \
+        }                                                                                                                      \
+        x_proj_mma_kernel<T, M, true><<<grid, 256, smem, stream>>>((const T*)xs, (const T*)xw16, nullptr, D, L, CC, (const T*)dw16, \
+                                                                   (T*)dts, Bs, Cs, R, N, Rp);                                  \
+        FD_LAUNCH_CHECK();                                                                                                     \
+        return 0;                                                                                                              \
+    }
+        XDT_PIPE_CASE(1) XDT_PIPE_CASE(2) XDT_PIPE_CASE(3) XDT_PIPE_CASE(4) XDT_PIPE_CASE(5) XDT_PIPE_CASE(6)
+#undef XDT_PIPE_CASE
+    }
 #define XDT_MMA_CASE(M)                                                                                                        \
     if (MT == M) {                                                                                                             \
         const size_t smem = ((size_t)XT_KC * XT_XLD + (size_t)M * 16 * XT_WLD + 32 * XT_XLD + 8 * 16 * XT_XLD) * sizeof(T);     \
@@ -659,6 +845,37 @@ extern "C" int fd_xdt_proj_tc(const void* xs, const void* xw16, const void* dw16
     if ((Rp != 16 && Rp != 32) || R > Rp || D % 16 || R + 2 * N > 96) return FD_ERR_UNSUPPORTED;
     if (dtype == FD_BF16) return xdt_mma_launch<__nv_bfloat16>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, stream);
     if (dtype == FD_F16) return xdt_mma_launch<__half>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, stream);
+    return FD_ERR_UNSUPPORTED;
+}
+
+template <typename T>
+static int x_proj_launch(const void* xs, const void* xw16, float* xdbl, int B, int D, int L, int CC, cudaStream_t stream) {
+    const int MT = (CC + 15) / 16;
+    dim3 grid(fd_cdiv(L, XT_L), B * 4);
+#define XP_CASE(M)                                                                                                            \
+    if (MT == M) {                                                                                                            \
+        const size_t smem = (size_t)XP_STAGES * ((size_t)XT_KC * XT_XLD + (size_t)M * 16 * XT_WLD) * sizeof(T);               \
+        static bool attr_set = false;                                                                                         \
+        if (!attr_set) {                                                                                                      \
+            cudaError_t e = cudaFuncSetAttribute(x_proj_mma_kernel<T, M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                                                              \
+            attr_set = true;                                                                                                  \
+        }                                                                                                                     \
+        x_proj_mma_kernel<T, M, false><<<grid, 256, smem, stream>>>((const T*)xs, (const T*)xw16, xdbl, D, L, CC);                    \
+        FD_LAUNCH_CHECK();                                                                                                    \
+        return 0;                                                                                                             \
+    }
+    XP_CASE(1) XP_CASE(2) XP_CASE(3) XP_CASE(4) XP_CASE(5) XP_CASE(6)
+#undef XP_CASE
+    return FD_ERR_UNSUPPORTED;
+}
+
+extern "C" int fd_x_proj_tc(const void* xs, const void* xw16, float* x_dbl, int B, int D, int L, int R, int N, int dtype,
+                            cudaStream_t stream) {
+    if (!xs || !xw16 || !x_dbl || B <= 0 || D <= 0 || L <= 0 || R <= 0 || N <= 0) return FD_ERR_BAD_ARGUMENT;
+    if (D % XT_KC || L % 8 || R + 2 * N > 96 || (((uintptr_t)xs | (uintptr_t)xw16) & 15) || ((uintptr_t)x_dbl & 7)) return FD_ERR_UNSUPPORTED;
+    if (dtype == FD_BF16) return x_proj_launch<__nv_bfloat16>(xs, xw16, x_dbl, B, D, L, R + 2 * N, stream);
+    if (dtype == FD_F16) return x_proj_launch<__half>(xs, xw16, x_dbl, B, D, L, R + 2 * N, stream);
     return FD_ERR_UNSUPPORTED;
 }
 

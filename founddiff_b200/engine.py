@@ -18,6 +18,8 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Optional
 
+import os
+
 import torch
 
 from . import ops
@@ -285,6 +287,12 @@ class UnetEngine:
         c_qkv = ops.Conv(a, qkv_w, qkv, B=B, Hin=h, Win=w, prefer_tc=tc)
         # fused scan+merge needs 16-bit io, 16/32-byte aligned rows (L % 8 == 0) and d_state in {4, 8, 16, 32}
         fuse_merge = dt != torch.float32 and L % 8 == 0 and N in (4, 8, 16, 32) and D % 8 == 0
+        # levels with a small dt_rank: x_proj alone, dt_proj applied inside the scan (no (B, 4D, L) delta tensor at all)
+        fuse_dt = (fuse_merge and use_xdt_tc and (N, R) in ((4, 4), (8, 8)) and D % 32 == 0
+                   and os.environ.get("FD_FUSE_DT", "0") == "1")
+        if fuse_dt:
+            xdbl = self.buf(f"XDBL{l}", B, 4, R + 2 * N, L, dtype=torch.float32)
+            dtw_flat = dtp_w.reshape(4 * D, R).contiguous()
         split_attn = dt != torch.float32            # 16-bit modes: streaming dwconv + tensor-core Gram, v read in place
         if split_attn:
             qkv2 = self.buf(f"QKV2{l}", B, P, 3 * C)
@@ -306,11 +314,17 @@ class UnetEngine:
             ops.ln_modulate(x_in, a, n1w, n1b, sh1, sc1, MS, B, P, C, 1e-5)
             c_in.run()
             ops.dwconv3x3_silu_scan(xz, 4 * C, dw_w, dw_b, xs, B, h, w, D)
-            if use_xdt_tc:
+            if fuse_dt:
+                ops.x_proj_tc(xs, xw16, xdbl, B, D, L, R, N)
+                ops.selective_scan_fwd_merge_xdbl(xs.view(B, 4 * D, L), xdbl, dtw_flat, A_neg, Ds, dt_bias, True, ys.view(B, P, D), h, w)
+                ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
+            elif use_xdt_tc:
                 ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N)
             else:
                 ops.xdt_proj(xs, xp_w, dtp_w, dts, Bs, Cs, B, D, L, R, N)
-            if fuse_merge:      # scan writes channels-last directly (EfficientMerge fused), then a row-wise LN + gate
+            if fuse_dt:
+                pass
+            elif fuse_merge:      # scan writes channels-last directly (EfficientMerge fused), then a row-wise LN + gate
                 ops.selective_scan_fwd_merge(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs, Cs, Ds, dt_bias, True,
                                              ys.view(B, P, D), h, w)
                 ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)

@@ -244,6 +244,25 @@ def xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N):
                                          dtype_code(xs.dtype), _stream()), "fd_xdt_proj_tc")
 
 
+def x_proj_tc(xs, xw16, x_dbl, B, D, L, R, N):
+    """x_dbl (B, 4, R+2N, L) fp32 = x_proj(xs) on the tensor cores; consumed by selective_scan_fwd_merge_xdbl."""
+    assert x_dbl.dtype == torch.float32 and x_dbl.shape == (B, 4, R + 2 * N, L)
+    with _launched("x_proj_tc", f"{B}x{D}x{L} R{R} N{N}", 1):
+        check(_lib.load().fd_x_proj_tc(_p(xs), _p(xw16), _f32(x_dbl), B, D, L, R, N, dtype_code(xs.dtype), _stream()), "fd_x_proj_tc")
+
+
+def selective_scan_fwd_merge_xdbl(u, x_dbl, dt_w, A, D, delta_bias, delta_softplus, y_nhwc, H, W):
+    """Scan + EfficientMerge with dt_proj fused: u (b, 4*Dg, L) 16-bit, x_dbl (b, 4, R+2N, L) fp32, dt_w (4*Dg, R) fp32."""
+    b, kd, L = u.shape
+    n, r = A.shape[1], dt_w.shape[1]
+    assert L == (H // 2) * (W // 2) and x_dbl.shape == (b, 4, r + 2 * n, L) and dt_w.shape[0] == kd
+    with _launched("selective_scan_merge", f"{b}x{kd}x{L} N{n} dt-fused"):
+        check(_lib.load().fd_selective_scan_fwd_merge_xdbl(_p(u), _f32(x_dbl), _f32(dt_w), _f32(A), _f32(D), _f32(delta_bias),
+                                                           _p(y_nhwc), b, kd, H, W, n, r, int(bool(delta_softplus)),
+                                                           dtype_code(u.dtype), _stream()), "fd_selective_scan_fwd_merge_xdbl")
+    return y_nhwc
+
+
 def merge_ln_gate(ys, xz, ld, z_off, gamma, beta, local, stats_ws, out, B, H, W, D, eps=1e-5):
     with _launched("merge_ln_gate", f"{B}x{H}x{W}x{D}", 2):
         check(_lib.load().fd_merge_ln_gate(_p(ys), _p(xz), ld, z_off, _f32(gamma), _f32(beta), _f32(local), _f32(stats_ws),

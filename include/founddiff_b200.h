@@ -56,6 +56,14 @@ int fd_selective_scan_fwd_merge(const void* u, const void* delta, const float* A
                                 const float* D, const float* delta_bias, void* y_nhwc, int batch, int dim, int H, int W,
                                 int dstate, int delta_softplus, int io_dtype, cudaStream_t stream);
 
+/* Same as fd_selective_scan_fwd_merge with dt_proj fused (src/emamba2.py:337-338, 353-359): delta[b, d, l] =
+ * sum_r dt_w[d, r] * x_dbl[b, k(d), r, l] is formed inside the scan (fp32) instead of being read from a (B, 4D, L) tensor;
+ * B / C are rows [R, R+N) / [R+N, R+2N) of the same x_dbl.  dt_w: (dim, R) fp32 = dt_projs_weight flattened over (k, d).
+ * dt_rank in {4, 8}; 16-bit io only. */
+int fd_selective_scan_fwd_merge_xdbl(const void* u, const float* x_dbl, const float* dt_w, const float* A, const float* D,
+                                     const float* delta_bias, void* y_nhwc, int batch, int dim, int H, int W, int dstate,
+                                     int dt_rank, int delta_softplus, int io_dtype, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution / 1x1 GEMM with fused epilogue — replaces F.conv2d / nn.Linear call sites:
  *   WeightStandardizedConv2d 3x3 (src/DADiff.py:139-154; standardisation folded into `weight` by the host),
@@ -136,6 +144,13 @@ int fd_xdt_proj(const void* xs, const float* x_proj_w, const float* dt_w, void* 
  * (4, CCp, D); dw16 = dt_w in `dtype`, columns zero-padded to Rp in {16, 32}: (4, D, Rp).  Same outputs. */
 int fd_xdt_proj_tc(const void* xs, const void* xw16, const void* dw16, void* dts, float* Bs, float* Cs, int B, int D,
                    int L, int R, int N, int Rp, int dtype, cudaStream_t stream);
+
+/* x_proj alone on the tensor cores (levels with dt_rank <= 8): x_dbl (B, 4, R+2N, L) fp32 = einsum(xs, x_proj_weight)
+ * (src/emamba2.py:334-336).  Rows [0,R) are the low-rank dt input, [R,R+N) B, [R+N,R+2N) C; fd_selective_scan_fwd_merge_xdbl
+ * consumes the tensor as is.  xw16: the zero-padded 16-bit (4, ceil16(R+2N), D) copy made by the host.  Needs D % 32 == 0,
+ * L % 8 == 0. */
+int fd_x_proj_tc(const void* xs, const void* xw16, float* x_dbl, int B, int D, int L, int R, int N, int dtype,
+                 cudaStream_t stream);
 
 /* SS2D consumer: EfficientMerge (src/emamba2.py:238-262) + out_norm LayerNorm(D) (:365) + y*z + local (:747-748).
  * ys: (B,4,D,L); z = columns [z_off, z_off+D) of xz rows (already SiLU'd); local: (B, D) fp32; out: (B,H,W,D).

@@ -575,3 +575,33 @@ def test_ddpm_update_matches_gaussian_diffusion_formulas(ops):
     coef = torch.tensor([sr, srm1, float(abar[tn].sqrt()), 0., float((1 - abar[tn]).sqrt()), 0., 1., 0.])
     ops.ddpm_update(xt.cuda(), eps.cuda(), None, coef.cuda(), out)
     assert rel(out, ref_ddim) < 1e-6
+
+
+@pytest.mark.parametrize("cfg", [(32, 64, 128, 4, 4), (16, 48, 64, 8, 8), (64, 64, 32, 4, 4), (24, 40, 96, 8, 8)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_x_proj_and_scan_with_fused_dt_proj(ops, cfg, dt):
+    """x_proj alone (tensor cores, fp32 x_dbl) + scan with dt_proj and EfficientMerge fused == the oracle's x_proj ->
+    dt_proj -> selective scan -> EfficientMerge (src/emamba2.py:334-367)."""
+    H, W, D, N, R = cfg
+    B, L = 2, (H // 2) * (W // 2)
+    g = torch.Generator().manual_seed(H * W + D)
+    xs = q(torch.randn(B, 4, D, L, generator=g), dt)
+    Wx = torch.randn(4, R + 2 * N, D, generator=g) / math.sqrt(D)
+    Wdt = torch.randn(4, D, R, generator=g) / math.sqrt(R)
+    A = -torch.exp(torch.randn(4 * D, N, generator=g) * 0.3)
+    Dp, bias = torch.randn(4 * D, generator=g), torch.randn(4 * D, generator=g) * 0.5
+    # reference (fp32 on the 16-bit-rounded xs / x_proj weights, as the kernel sees them)
+    x_dbl_ref = torch.einsum("bkdl,kcd->bkcl", xs, q(Wx, dt))
+    dts_r, Bs_r, Cs_r = torch.split(x_dbl_ref, [R, N, N], dim=2)
+    delta = torch.einsum("bkrl,kdr->bkdl", dts_r, Wdt).reshape(B, 4 * D, L)
+    y_ref = scan_cpu.selective_scan_fwd(xs.reshape(B, 4 * D, L).contiguous(), delta.contiguous(), A, Bs_r.contiguous(), Cs_r.contiguous(),
+                                        Dp, bias, True)
+    y_ref = O.efficient_merge(y_ref.view(B, 4, D, L), H, W).permute(0, 2, 3, 1)          # (B, H, W, D)
+    xw16, _dw16, _Rp = ops.pack_xdt_weights(Wx.cuda(), Wdt.cuda(), dt)
+    x_dbl = torch.zeros(B, 4, R + 2 * N, L, device="cuda")
+    ops.x_proj_tc(xs.to("cuda", dt), xw16, x_dbl, B, D, L, R, N)
+    assert rel(x_dbl, x_dbl_ref) < 2e-5
+    y = torch.empty(B, H * W, D, device="cuda", dtype=dt)
+    ops.selective_scan_fwd_merge_xdbl(xs.reshape(B, 4 * D, L).to("cuda", dt), x_dbl, Wdt.reshape(4 * D, R).cuda(), A.cuda(), Dp.cuda(),
+                                      bias.cuda(), True, y, H, W)
+    assert rel(y.reshape(B, H, W, D), y_ref) < TOL[dt]
