@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(fd_conv_params p, int Ho
             gq[j] += v * v;
             float o = p.gate ? p.gate[(long)b * p.gate_stride + n] * v : v;
             if (addend) o += fd_ld(addend + orow + n);
+            if (p.relu_out) o = fmaxf(o, 0.f);
             fd_st(out + orow + n, o);
         }
     }

@@ -533,6 +533,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] += a[j];
                     }
+                    if (p.relu_out) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
                     store16<T>(out + orow + n, v);
                 }
             }

@@ -481,3 +481,47 @@ extern "C" int fd_time_sinusoid(const float* time, float* out, int B, int dim, c
     FD_LAUNCH_CHECK();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------
+// 2x2 / stride-2 average pooling over channels-last data: one thread per (output pixel, 16-byte channel vector).
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool2x2_nhwc_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C,
+                                                              long total) {
+    constexpr int VEC = fd_vec<T>::N;
+    const long i = (long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int vr = C / VEC;
+    const int cv = (int)(i % vr);
+    long pix = i / vr;
+    const int Wo = W / 2, Ho = H / 2;
+    const int xo = (int)(pix % Wo); pix /= Wo;
+    const int yo = (int)(pix % Ho);
+    const long b = pix / Ho;
+    const T* p00 = in + (((b * H + 2 * yo) * W + 2 * xo) * (long)C) + cv * VEC;
+    float a[VEC], t[VEC];
+    fd_raw_to_f<T>(*reinterpret_cast<const uint4*>(p00), a);
+    fd_raw_to_f<T>(*reinterpret_cast<const uint4*>(p00 + C), t);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) a[e] += t[e];
+    fd_raw_to_f<T>(*reinterpret_cast<const uint4*>(p00 + (long)W * C), t);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) a[e] += t[e];
+    fd_raw_to_f<T>(*reinterpret_cast<const uint4*>(p00 + (long)W * C + C), t);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) a[e] = (a[e] + t[e]) * 0.25f;
+    *reinterpret_cast<uint4*>(out + (((b * Ho + yo) * Wo + xo) * (long)C) + cv * VEC) = fd_f_to_raw<T>(a);
+}
+
+extern "C" int fd_avgpool2x2_nhwc(const void* in, void* out, int B, int H, int W, int C, int dtype, cudaStream_t stream) {
+    if (!in || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0) return FD_ERR_BAD_ARGUMENT;
+    if ((H & 1) || (W & 1)) return FD_ERR_UNSUPPORTED;
+    FD_DISPATCH_DTYPE(dtype, T, {
+        constexpr int VEC = fd_vec<T>::N;
+        if (C % VEC || (((uintptr_t)in | (uintptr_t)out) & 15)) return FD_ERR_UNSUPPORTED;
+        const long total = (long)B * (H / 2) * (W / 2) * (C / VEC);
+        avgpool2x2_nhwc_kernel<T><<<(unsigned)fd_cdiv(total, 256), 256, 0, stream>>>((const T*)in, (T*)out, H, W, C, total);
+    });
+    FD_LAUNCH_CHECK();
+    return 0;
+}

@@ -6,8 +6,14 @@ input slice (channel 1 of the Unet input), so the sampler calls `embed()` once p
 per-step path never sees the encoder (SURVEY.md "Five facts" #4).
 
 This is off the per-step hot path; it runs the RN50 `ModifiedResNet` visual tower + `AttentionPool2d`
-(pos_embedding=False) + head1/head2 (src/DACLIP.py:168-349, 1180-1211) as fp32 library convolutions (cuDNN, TF32
-disabled) — the role SURVEY.md §7 step 7 assigns to it.
+(pos_embedding=False) + head1/head2 (src/DACLIP.py:168-349, 1180-1211).
+
+* fp32 mode: library convolutions (cuDNN, TF32 disabled) — the validation path.
+* 16-bit modes: the 16 bottleneck blocks (94 % of the tower's FLOPs: 1x1 / 3x3 convolutions over 64..2048 channels) run
+  on this repo's tcgen05 implicit-GEMM kernel (fd_conv2d_tc) with BatchNorm folded into weights + bias, ReLU and the
+  residual add fused into the epilogue and channels-last activations; only the 3-convolution stem (3 / 32 input
+  channels, below the 64-channel K block) and the attention pool stay on the library path.  At 16 x 512^2 this takes the
+  embedding from 7.9 ms (cuDNN bf16) to the figure in DESIGN.md.
 """
 from __future__ import annotations
 
@@ -15,6 +21,8 @@ from typing import Dict, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
+
+from . import ops
 
 PREFIX = "dose_encoder."
 
@@ -39,6 +47,8 @@ class DAClipEncoder:
         self.layers, self.heads = tuple(layers), heads
         # BatchNorm (eval) folded into the preceding bias-free convolution once, at load time
         self._folded = {}
+        self._towers = {}
+        self.use_tc = conv_dtype != torch.float32      # tcgen05 bottleneck tower (16-bit storage only)
 
     def _conv_bn(self, x, conv, bn, stride=1, padding=0):
         key = conv
@@ -64,6 +74,87 @@ class DAClipEncoder:
             idt = x
         return F.relu(out + idt)
 
+    # ---------------------------------------------------------------------------------------------------
+    # tensor-core tower (16-bit modes)
+    def _folded_nhwc(self, conv, bn):
+        """BN-folded weight as (Cout, KH, KW, Cin) 16-bit + fp32 bias, the layout fd_conv_params takes."""
+        key = "nhwc:" + conv
+        if key not in self._folded:
+            sd = self.sd
+            w = sd[conv + ".weight"]
+            s = sd[bn + ".weight"] * torch.rsqrt(sd[bn + ".running_var"] + 1e-5)
+            wf = (w * s[:, None, None, None]).permute(0, 2, 3, 1).to(self.conv_dtype).contiguous()
+            self._folded[key] = (wf, (sd[bn + ".bias"] - sd[bn + ".running_mean"] * s).float().contiguous())
+        return self._folded[key]
+
+    def _build_tower(self, B: int, H: int, W: int, dev):
+        """Buffers + convolution plans of layer1..layer4 for a (B, 64, H, W) stem output (H, W = input / 4)."""
+        v = PREFIX + "clip_model.visual."
+        dt = self.conv_dtype
+        steps, keep = [], []
+        x = torch.empty(B, H * W, 64, device=dev, dtype=dt)
+        tower_in = x
+        cin, h, w = 64, H, W
+        for li, blocks in enumerate(self.layers):
+            planes = 64 * 2 ** li
+            for bi in range(blocks):
+                p = f"{v}layer{li + 1}.{bi}."
+                stride = 2 if (li > 0 and bi == 0) else 1
+                ho, wo = h // stride, w // stride
+                new = lambda hh, ww, c: torch.empty(B, hh * ww, c, device=dev, dtype=dt)  # noqa: E731
+                t1, t2 = new(h, w, planes), new(h, w, planes)
+                out = new(ho, wo, planes * 4)
+                w1, b1 = self._folded_nhwc(p + "conv1", p + "bn1")
+                w2, b2 = self._folded_nhwc(p + "conv2", p + "bn2")
+                w3, b3 = self._folded_nhwc(p + "conv3", p + "bn3")
+                c1 = ops.Conv(x, w1, t1, B=B, Hin=h, Win=w, bias=b1, relu_out=True)
+                c2 = ops.Conv(t1, w2, t2, B=B, Hin=h, Win=w, KH=3, KW=3, pad=1, bias=b2, relu_out=True)
+                seq = [c1.run, c2.run]
+                t2p = t2
+                if stride > 1:
+                    t2p = new(ho, wo, planes)
+                    seq.append(lambda a=t2, o=t2p, hh=h, ww=w, c=planes: ops.avgpool2x2_nhwc(a, o, B, hh, ww, c))
+                idt = x
+                if (p + "downsample.0.weight") in self.sd:
+                    wd, bd = self._folded_nhwc(p + "downsample.0", p + "downsample.1")
+                    src = x
+                    if stride > 1:
+                        src = new(ho, wo, cin)
+                        seq.append(lambda a=x, o=src, hh=h, ww=w, c=cin: ops.avgpool2x2_nhwc(a, o, B, hh, ww, c))
+                    idt = new(ho, wo, planes * 4)
+                    cd = ops.Conv(src, wd, idt, B=B, Hin=ho, Win=wo, bias=bd)
+                    seq.append(cd.run)
+                    keep.append(cd)
+                c3 = ops.Conv(t2p, w3, out, B=B, Hin=ho, Win=wo, bias=b3, addend=idt, relu_out=True)
+                seq.append(c3.run)
+                keep += [c1, c2, c3]
+                for c in (c1, c2, c3):
+                    if not c.uses_tc:
+                        raise RuntimeError("DA-CLIP tower: convolution not eligible for the tcgen05 path: " + c.describe())
+                steps += seq
+                x, cin, h, w = out, planes * 4, ho, wo
+        return dict(inp=tower_in, out=x, steps=steps, keep=keep, h=h, w=w, c=cin)
+
+    def _tower_tc(self, x: torch.Tensor):
+        """x: stem output (B, 64, H, W), any memory format -> layer4 output as (B, C, h, w) view of channels-last data,
+        or None when the size does not tile for the tensor-core kernel."""
+        B, C, H, W = x.shape
+        key = (B, H, W, str(x.device))
+        tw = self._towers.get(key)
+        if tw is None:
+            self._towers.clear()
+            try:
+                tw = self._build_tower(B, H, W, x.device)
+            except RuntimeError:
+                tw = False                                 # some level does not tile (small / odd sizes): library path
+            self._towers[key] = tw
+        if tw is False:
+            return None
+        tw["inp"].view(B, H, W, C).copy_(x.permute(0, 2, 3, 1))
+        for fn in tw["steps"]:
+            fn()
+        return tw["out"].view(B, tw["h"], tw["w"], tw["c"]).permute(0, 3, 1, 2)
+
     @torch.no_grad()
     def embed(self, x_input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         sd = self.sd
@@ -77,9 +168,13 @@ class DAClipEncoder:
             x = F.relu(self._conv_bn(x, v + "conv2", v + "bn2", padding=1))
             x = F.relu(self._conv_bn(x, v + "conv3", v + "bn3", padding=1))
             x = F.avg_pool2d(x, 2)
-            for li, blocks in enumerate(self.layers):
-                for bi in range(blocks):
-                    x = self._bottleneck(f"{v}layer{li + 1}.{bi}.", x, 2 if (li > 0 and bi == 0) else 1)
+            y = self._tower_tc(x) if (self.use_tc and x.shape[2] % 8 == 0 and x.shape[3] % 8 == 0) else None
+            if y is not None:
+                x = y
+            else:
+                for li, blocks in enumerate(self.layers):
+                    for bi in range(blocks):
+                        x = self._bottleneck(f"{v}layer{li + 1}.{bi}.", x, 2 if (li > 0 and bi == 0) else 1)
             a = v + "attnpool."
             x = x.float()
             B, C, H, W = x.shape

@@ -140,7 +140,7 @@ class Conv:
 
     def __init__(self, src0, weight, out, *, B, Hin, Win, KH=1, KW=1, stride=1, pad=0, upsample=False, src1=None,
                  bias=None, gate=None, gate_stride=0, addend=None, silu_from=None, gn_sums=None, gn_groups=0,
-                 per_batch_weight=False, prefer_tc=True, c0=None, ld0=0):
+                 per_batch_weight=False, prefer_tc=True, c0=None, ld0=0, relu_out=False):
         """`c0` / `ld0`: read only the first c0 channels of rows of pitch ld0 starting at src0's data pointer (src0 may
         be a strided channel-slice view)."""
         lib = _lib.load()
@@ -161,6 +161,7 @@ class Conv:
         p.silu_from = cout if silu_from is None else silu_from
         p.gate_stride, p.gn_groups, p.per_batch_weight = gate_stride, gn_groups, int(per_batch_weight)
         p.dtype = dtype_code(out.dtype)
+        p.relu_out = int(bool(relu_out))
         assert src0.dtype == out.dtype == weight.dtype and (src1 is None or src1.dtype == out.dtype)
         assert weight.numel() == (B if per_batch_weight else 1) * cout * KH * KW * (c0 + c1), (weight.shape, cout, KH, KW, c0, c1)
         self.params = p
@@ -199,6 +200,11 @@ class Conv:
                 self._lib.fd_conv2d_tc_plan_destroy(self._plan)
         except Exception:
             pass
+
+
+def avgpool2x2_nhwc(x, out, B, H, W, C):
+    with _launched("avgpool2x2_nhwc", f"{B}x{H}x{W}x{C}", 1):
+        check(_lib.load().fd_avgpool2x2_nhwc(_p(x), _p(out), B, H, W, C, dtype_code(x.dtype), _stream()), "fd_avgpool2x2_nhwc")
 
 
 def init_conv7x7(x_t, x_input, weight, bias, out, B, H, W):

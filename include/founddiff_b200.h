@@ -97,6 +97,7 @@ typedef struct {
     int gn_groups;        /* used when gn_sums != NULL */
     int per_batch_weight;
     int dtype;
+    int relu_out;         /* 1: out = max(out, 0) after bias / gate / addend (the DA-CLIP ResNet blocks, src/DACLIP.py) */
 } fd_conv_params;
 
 /* CUDA-core fp32-accumulate path (any dtype; the fp32 validation path and the fallback for odd shapes). */
@@ -109,6 +110,10 @@ int fd_conv2d_tc_supported(const fd_conv_params* p);
 int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** plan);
 int fd_conv2d_tc_run(const fd_gemm_plan* plan, cudaStream_t stream);
 void fd_conv2d_tc_plan_destroy(fd_gemm_plan* plan);
+
+/* 2x2 average pooling, stride 2, channels-last (B,H,W,C) -> (B,H/2,W/2,C); H, W even, C % 8 == 0 for 16-bit types.
+ * nn.AvgPool2d(2) of the DA-CLIP ModifiedResNet (stem, strided bottlenecks, their downsample branch). */
+int fd_avgpool2x2_nhwc(const void* in, void* out, int B, int H, int W, int C, int dtype, cudaStream_t stream);
 
 /* init_conv: 7x7, pad 3, over cat(x_t, x_input) (two fp32 single-channel images) -> (B,H,W,Cout) in `dtype`.
  * Replaces Unet.init_conv (src/DADiff.py:558, 700) + torch.cat (:1160).  weight: (Cout, 2, 7, 7) fp32. */

@@ -228,3 +228,24 @@ def test_full_size_512_vs_oracle(model, state_dict):
             print(f"512^2 {dt} t={a['t']} pred_res rel-L2 {r:.3e}")
             assert r < GATE[dt]
         assert abs(O.psnr(out.cpu(), ldct) - O.psnr(ref, ldct)) < 0.05
+
+
+@pytest.mark.gpu
+def test_daclip_tensor_core_tower_matches_library_path(state_dict):
+    """16-bit DA-CLIP embedding with the bottleneck tower on fd_conv2d_tc == the same embedding through cuDNN bf16 (both
+    against the fp32 library path within the 16-bit budget DESIGN.md allots to the conditioning)."""
+    import torch
+    from founddiff_b200.daclip import DAClipEncoder
+    dev = torch.device("cuda")
+    x = torch.rand(2, 1, 512, 512, generator=torch.Generator().manual_seed(3)).to(dev) * 2 - 1
+    ref = DAClipEncoder(state_dict, dev, conv_dtype=torch.float32).embed(x)
+    tc = DAClipEncoder(state_dict, dev, conv_dtype=torch.bfloat16)
+    got = tc.embed(x)
+    assert tc._towers and all(v is not False for v in tc._towers.values()), "tensor-core tower was not used"
+    lib = DAClipEncoder(state_dict, dev, conv_dtype=torch.bfloat16)
+    lib.use_tc = False
+    got_lib = lib.embed(x)
+    for a, b, c in zip(got, got_lib, ref):
+        e_tc = float((a - c).norm() / c.norm())
+        e_lib = float((b - c).norm() / c.norm())
+        assert e_tc < 2e-2 and e_tc < 3 * e_lib + 2e-3, (e_tc, e_lib)
