@@ -73,7 +73,11 @@ template <> FD_DEVINL void fd_stv<__half, 8>(__half* p, const float (&v)[8]) {
 }
 
 // MUFU.EX2 + MUFU.RCP, no IEEE-division slow path (FCHK + branch): the full-precision divide cost ~2x the instructions
-FD_DEVINL float fd_silu(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+FD_DEVINL float fd_silu(float x) {      // FMUL, MUFU.EX2 (ftz: no denormal rescaling code), FADD, MUFU.RCP, FMUL
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    return __fdividef(x, 1.f + e);
+}
 FD_DEVINL float fd_softplus20(float x) { return x <= 20.f ? log1pf(__expf(x)) : x; }
 
 FD_DEVINL float fd_warp_sum(float v) {

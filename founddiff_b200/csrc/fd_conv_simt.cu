@@ -10,7 +10,7 @@ namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16;
 
-template <typename T>
+template <typename TA, typename T>       // TA: src0 / src1 / weight storage, T: out / addend storage
 __global__ void __launch_bounds__(256) conv_simt_kernel(fd_conv_params p, int Hout, int Wout, int tiles_per_sample) {
     __shared__ float As[TK][TM + 4];
     __shared__ float Bs[TK][TN + 4];
@@ -25,9 +25,9 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(fd_conv_params p, int Ho
     const int P = Hout * Wout;
     const int Hin = p.Hin, Win = p.Win;
     const int Hv = p.upsample ? 2 * Hin : Hin, Wv = p.upsample ? 2 * Win : Win;  // virtual (upsampled) input size
-    const T* src0 = (const T*)p.src0;
-    const T* src1 = (const T*)p.src1;
-    const T* wgt = (const T*)p.weight + (p.per_batch_weight ? (long)b * p.Cout * K : 0);
+    const TA* src0 = (const TA*)p.src0;
+    const TA* src1 = (const TA*)p.src1;
+    const TA* wgt = (const TA*)p.weight + (p.per_batch_weight ? (long)b * p.Cout * K : 0);
 
     const int tid = threadIdx.x;
     // loader mapping: 4 consecutive k for one row
@@ -146,6 +146,11 @@ extern "C" int fd_conv_check_params(const fd_conv_params* p) {
         if (cpg < 4 || cpg % 4 || (64 % cpg && cpg % 64)) return FD_ERR_UNSUPPORTED;
     }
     if (p->dtype != FD_F32 && p->dtype != FD_BF16 && p->dtype != FD_F16) return FD_ERR_BAD_ARGUMENT;
+    if (p->ab_dtype_p1) {
+        const int ab = p->ab_dtype_p1 - 1;
+        if (ab != FD_F32 && ab != FD_BF16 && ab != FD_F16) return FD_ERR_BAD_ARGUMENT;
+        if ((ab == FD_F32) != (p->dtype == FD_F32)) return FD_ERR_UNSUPPORTED;       // fp32 does not mix with 16-bit storage
+    }
     return 0;
 }
 
@@ -157,7 +162,16 @@ extern "C" int fd_conv2d_simt(const fd_conv_params* p, cudaStream_t stream) {
     if (p->gn_sums && (p->Cout / p->gn_groups) > 64) return FD_ERR_UNSUPPORTED;
     const int tiles = fd_cdiv((long)Hout * Wout, TM);
     dim3 grid((unsigned)(tiles * p->B), fd_cdiv(p->Cout, TN));
-    FD_DISPATCH_DTYPE(p->dtype, T, (conv_simt_kernel<T><<<grid, 256, 0, stream>>>(*p, Hout, Wout, tiles)));
+    const int ab = p->ab_dtype_p1 ? p->ab_dtype_p1 - 1 : p->dtype;
+    if (ab == p->dtype) {
+        FD_DISPATCH_DTYPE(p->dtype, T, (conv_simt_kernel<T, T><<<grid, 256, 0, stream>>>(*p, Hout, Wout, tiles)));
+    } else if (ab == FD_BF16 && p->dtype == FD_F16) {
+        conv_simt_kernel<__nv_bfloat16, __half><<<grid, 256, 0, stream>>>(*p, Hout, Wout, tiles);
+    } else if (ab == FD_F16 && p->dtype == FD_BF16) {
+        conv_simt_kernel<__half, __nv_bfloat16><<<grid, 256, 0, stream>>>(*p, Hout, Wout, tiles);
+    } else {
+        return FD_ERR_UNSUPPORTED;
+    }
     FD_LAUNCH_CHECK();
     return 0;
 }

@@ -613,6 +613,7 @@ extern "C" int fd_conv_check_params(const fd_conv_params* p);
 extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
     if (fd_conv_check_params(p)) return 0;
     if (p->dtype != FD_BF16 && p->dtype != FD_F16) return 0;
+    if (p->ab_dtype_p1 && p->ab_dtype_p1 - 1 != FD_BF16 && p->ab_dtype_p1 - 1 != FD_F16) return 0;
     if (p->c0 % BK || p->c1 % BK || p->ld0 % 8) return 0;
     if (p->silu_from < p->Cout && p->silu_from % 16) return 0;
     if (((uintptr_t)p->bias | (uintptr_t)p->gate) & 15 || (p->gate && p->gate_stride % 4)) return 0;
@@ -655,7 +656,8 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     q.kblocks1 = p->c1 / BK;
     q.BN = (p->Cout % 256 == 0) ? 256 : (p->Cout % 128 == 0 ? 128 : 64);
     q.n_tiles = p->Cout / q.BN;
-    q.fmt = p->dtype == FD_BF16 ? 1 : 0;
+    const int ab_dtype = p->ab_dtype_p1 ? p->ab_dtype_p1 - 1 : p->dtype;      // operand storage (both A and B); T = output storage
+    q.fmt = ab_dtype == FD_BF16 ? 1 : 0;
     const int gh = q.Hout / (p->upsample ? 2 : 1), gw = q.Wout / (p->upsample ? 2 : 1);
     const int num_kb = q.taps_h * q.taps_w * (q.kblocks0 + q.kblocks1);
     const size_t b_tile = (size_t)q.BN * BK * 2;
@@ -688,9 +690,9 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     q.tiles_h = gh / q.tile_h;
     q.tiles_w = gw / q.tile_w;
     const int box_w = q.halo ? q.ht_w : TILE_W, box_h = q.halo ? q.ht_h : TILE_H;
-    int rc = act_map(&plan->map_a0, p->src0, p->dtype, p->B, p->Hin, p->Win, p->c0, p->ld0 > 0 ? p->ld0 : p->c0,
+    int rc = act_map(&plan->map_a0, p->src0, ab_dtype, p->B, p->Hin, p->Win, p->c0, p->ld0 > 0 ? p->ld0 : p->c0,
                      p->upsample ? 1 : p->stride, box_w, box_h);
-    if (!rc && p->c1) rc = act_map(&plan->map_a1, p->src1, p->dtype, p->B, p->Hin, p->Win, p->c1, p->c1, p->upsample ? 1 : p->stride, box_w, box_h);
+    if (!rc && p->c1) rc = act_map(&plan->map_a1, p->src1, ab_dtype, p->B, p->Hin, p->Win, p->c1, p->c1, p->upsample ? 1 : p->stride, box_w, box_h);
     if (!rc && !p->c1) plan->map_a1 = plan->map_a0;
     if (!rc) {
         const long Kp = (long)q.taps_h * q.taps_w * Cin;
@@ -700,7 +702,7 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
         const cuuint64_t strides[2] = {(cuuint64_t)Kp * 2, (cuuint64_t)Kp * p->Cout * 2};
         const cuuint32_t box[3] = {BK, (cuuint32_t)q.BN, 1};
         const cuuint32_t estr[3] = {1, 1, 1};
-        rc = encode(&plan->map_w, p->dtype, 3, wbase, dims, strides, box, estr);
+        rc = encode(&plan->map_w, ab_dtype, 3, wbase, dims, strides, box, estr);
     }
     if (rc) { free(plan); return rc; }
     const size_t stage_bytes = BM * BK * 2 + (size_t)q.BN * BK * 2;

@@ -74,8 +74,8 @@ FD_DEVINL void fd_row_stats(const float (&v)[NV][VEC], int C, float eps, float& 
 }
 
 // LayerNorm over C + adaLN modulate (src/DADiff.py:450-451, 459, 461, 486-487).
-template <typename T, int LPR, int NV, int U>
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const T* __restrict__ x, T* __restrict__ out,
+template <typename T, typename TO, int LPR, int NV, int U>      // T: storage of x, TO: storage of out (same width)
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const T* __restrict__ x, TO* __restrict__ out,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta,
                                                           const float* __restrict__ shift,
@@ -149,13 +149,13 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const T* __restrict__ 
                         v[j][e] = fmaf(t, 1.f + tsc[e], tsh[e]);
                     }
                 }
-                *reinterpret_cast<uint4*>(out + (long)row * C + (sub + j * LPR) * VEC) = fd_f_to_raw<T>(v[j]);
+                *reinterpret_cast<uint4*>(out + (long)row * C + (sub + j * LPR) * VEC) = fd_f_to_raw<TO>(v[j]);
             }
         }
     }
 }
 
-template <typename T>
+template <typename T, typename TO>
 static int ln_modulate_launch(const void* x, void* out, const float* gamma, const float* beta,
                               const float* shift, const float* scale, int mod_stride, int B, int P, int C,
                               float eps, cudaStream_t st) {
@@ -173,7 +173,7 @@ static int ln_modulate_launch(const void* x, void* out, const float* gamma, cons
 #define LN_CASE(L, N, UU)                                                                                    \
     if (lpr == L && nv == N) {                                                                               \
         const int grid = fd_cdiv(rows, (long)rpw * warps * UU);                                              \
-        ln_modulate_kernel<T, L, N, UU><<<grid, warps * 32, 0, st>>>((const T*)x, (T*)out, gamma, beta, shift, scale, \
+        ln_modulate_kernel<T, TO, L, N, UU><<<grid, warps * 32, 0, st>>>((const T*)x, (TO*)out, gamma, beta, shift, scale, \
                                                                      mod_stride, (unsigned)rows, (unsigned)P, C, eps); \
         FD_LAUNCH_CHECK();                                                                                   \
         return 0;                                                                                            \
@@ -189,8 +189,22 @@ extern "C" int fd_ln_modulate(const void* x, void* out, const float* gamma, cons
     if (!x || !out || !shift || !scale || B <= 0 || P <= 0 || C <= 0) return FD_ERR_BAD_ARGUMENT;
     if ((gamma == nullptr) != (beta == nullptr)) return FD_ERR_BAD_ARGUMENT;
     FD_DISPATCH_DTYPE(dtype, T,
-                      return ln_modulate_launch<T>(x, out, gamma, beta, shift, scale, mod_stride, B, P, C, eps, stream));
+                      return (ln_modulate_launch<T, T>(x, out, gamma, beta, shift, scale, mod_stride, B, P, C, eps, stream)));
     return 0;
+}
+
+extern "C" int fd_ln_modulate_io(const void* x, void* out, const float* gamma, const float* beta, const float* shift,
+                                 const float* scale, int mod_stride, int B, int P, int C, float eps, int in_dtype, int out_dtype,
+                                 cudaStream_t stream) {
+    if (in_dtype == out_dtype)
+        return fd_ln_modulate(x, out, gamma, beta, shift, scale, mod_stride, B, P, C, eps, in_dtype, stream);
+    if (!x || !out || !shift || !scale || B <= 0 || P <= 0 || C <= 0) return FD_ERR_BAD_ARGUMENT;
+    if ((gamma == nullptr) != (beta == nullptr)) return FD_ERR_BAD_ARGUMENT;
+    if (in_dtype == FD_F16 && out_dtype == FD_BF16)
+        return ln_modulate_launch<__half, __nv_bfloat16>(x, out, gamma, beta, shift, scale, mod_stride, B, P, C, eps, stream);
+    if (in_dtype == FD_BF16 && out_dtype == FD_F16)
+        return ln_modulate_launch<__nv_bfloat16, __half>(x, out, gamma, beta, shift, scale, mod_stride, B, P, C, eps, stream);
+    return FD_ERR_UNSUPPORTED;
 }
 
 // ------------------------------------------------------------------------------------------------------

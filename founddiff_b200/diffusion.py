@@ -97,6 +97,10 @@ class UnetRes(nn.Module):
                           random_fourier_features=random_fourier_features, learned_sinusoidal_dim=learned_sinusoidal_dim,
                           condition=condition, input_condition=input_condition, seed=seed)
         self.compute_dtype = torch.bfloat16
+        # storage of the residual stream / pre-GroupNorm conv outputs; None = automatic: fp16 under bf16 sampling (the
+        # tensors whose rounding error accumulates get the 11-bit mantissa, the unnormalised ones keep bf16's range),
+        # otherwise the compute dtype.  Set to torch.bfloat16 for pure-bf16 storage (misses the 1e-2 parity gate).
+        self.trunk_dtype: Optional[torch.dtype] = None
         self._engines: Dict = {}
         self._daclip = None
         self._version = 0
@@ -124,11 +128,15 @@ class UnetRes(nn.Module):
         return OrderedDict((k, v.detach()) for k, v in self.unet0.state_dict().items())
 
     def engine(self, B, H, W, device) -> UnetEngine:
-        key = (B, H, W, self.compute_dtype, str(device))
+        trunk = self.trunk_dtype
+        if trunk is None:
+            trunk = torch.float16 if self.compute_dtype == torch.bfloat16 else self.compute_dtype
+        key = (B, H, W, self.compute_dtype, trunk, str(device))
         eng = self._engines.get(key)
         if eng is None:
             self._engines.clear()          # one resident engine: activations for B=16 at 512^2 are ~25 GB
-            eng = UnetEngine(self._live_sd(), self.unet0.cfg, B, H, W, dtype=self.compute_dtype, device=device)
+            eng = UnetEngine(self._live_sd(), self.unet0.cfg, B, H, W, dtype=self.compute_dtype, device=device,
+                             trunk_dtype=trunk)
             self._engines[key] = eng
         return eng
 
@@ -154,8 +162,8 @@ class UnetRes(nn.Module):
         eng.set_condition(dose, ctx)
         eng.time.copy_(t.to(torch.float32).reshape(-1).expand(B))
         feat = eng.forward()
-        out = torch.empty(B, H * W, 1, device=x.device, dtype=eng.dtype)
-        w = eng.final_w.to(eng.dtype).reshape(1, 1, 1, -1).contiguous()
+        out = torch.empty(B, H * W, 1, device=x.device, dtype=feat.dtype)
+        w = eng.final_w.to(feat.dtype).reshape(1, 1, 1, -1).contiguous()
         ops.Conv(feat, w, out, B=B, Hin=H, Win=W, bias=eng.final_b, prefer_tc=False).run()
         return [out.float().reshape(B, 1, H, W)]
 

@@ -26,6 +26,8 @@ from . import ops
 from .weights import UnetConfig
 
 GN_GROUPS = 8
+# arena names that hold the residual / skip stream or feed GroupNorm (UnetEngine.trunk_dtype); everything else is `dtype`
+TRUNK_BUFFERS = ("R", "TA", "TB", "H", "SK", "Y")
 BASE_MID_STATE = 32            # int(base_d_state * 2 ** 3), src/DADiff.py:649
 
 
@@ -44,8 +46,17 @@ def pack_conv(w: torch.Tensor, dtype, device) -> torch.Tensor:
 
 class UnetEngine:
     def __init__(self, sd: Dict[str, torch.Tensor], cfg: UnetConfig, B: int, H: int, W: int,
-                 dtype: torch.dtype = torch.bfloat16, device="cuda", prefer_tc: bool = True):
+                 dtype: torch.dtype = torch.bfloat16, device="cuda", prefer_tc: bool = True,
+                 trunk_dtype: Optional[torch.dtype] = None):
+        """`dtype`: storage of the block-internal tensors (xz, scan layout, qkv, LN outputs ...) and of the projections
+        that read them.  `trunk_dtype`: storage of the residual / skip stream, of the pre-GroupNorm conv outputs and of the
+        convolutions that read the stream.  bf16 sampling uses dtype = bf16 (range for the unnormalised projections and
+        scan tensors) with an fp16 trunk (11-bit mantissa where the rounding error accumulates from block to block): the
+        oracle ablation in DESIGN.md section 2 puts 80 % of the pure-bf16 error on exactly these tensors."""
         self.cfg, self.B, self.H, self.W, self.dtype, self.device = cfg, B, H, W, dtype, torch.device(device)
+        self.trunk_dtype = trunk_dtype or dtype
+        if (self.trunk_dtype == torch.float32) != (dtype == torch.float32):
+            raise ValueError("fp32 storage does not mix with 16-bit storage")
         self.prefer_tc = prefer_tc
         self._bufs: Dict[str, torch.Tensor] = {}
         f32 = lambda k: sd[k].detach().to(device=self.device, dtype=torch.float32).contiguous()  # noqa: E731
@@ -107,7 +118,8 @@ class UnetEngine:
     # -------------------------------------------------------------------------------------------------------
     def buf(self, name: str, *shape, dtype=None) -> torch.Tensor:
         """Named arena: one allocation per name, grown to the largest request, returned as a view."""
-        dtype = dtype or self.dtype
+        if dtype is None:
+            dtype = self.trunk_dtype if name.rstrip("0123456789") in TRUNK_BUFFERS else self.dtype
         n = int(math.prod(shape))
         t = self._bufs.get(name)
         if t is None or t.numel() < n or t.dtype != dtype:
@@ -153,7 +165,7 @@ class UnetEngine:
         self.steps.append(lambda: ops.init_conv7x7(self.x_t, self.x_input, self.init_w, self.init_b, R, B, H, W))
 
         def conv_plain(key_w, key_b, src, dst, h, w, k, stride=1, upsample=False):
-            c = ops.Conv(src, pack_conv(sd[key_w], dt, dev), dst, B=B, Hin=h, Win=w, KH=k, KW=k, stride=stride,
+            c = ops.Conv(src, pack_conv(sd[key_w], self.trunk_dtype, dev), dst, B=B, Hin=h, Win=w, KH=k, KW=k, stride=stride,
                          pad=1, upsample=upsample, bias=f32(key_b), prefer_tc=self.prefer_tc)
             self.steps.append(c.run)
 
@@ -206,6 +218,7 @@ class UnetEngine:
         f32 = self.f32
         P = h * w
         cin = sum(s.shape[-1] for s in srcs)
+        dt = self.trunk_dtype                  # reads and writes the residual stream only
         wc = pack_conv(ws_fold(sd[p + ".block1.proj.weight"]), dt, dev)
         bc = f32(p + ".block1.proj.bias")
         gamma, beta = f32(p + ".block1.norm.weight"), f32(p + ".block1.norm.bias")

@@ -162,7 +162,10 @@ class Conv:
         p.gate_stride, p.gn_groups, p.per_batch_weight = gate_stride, gn_groups, int(per_batch_weight)
         p.dtype = dtype_code(out.dtype)
         p.relu_out = int(bool(relu_out))
-        assert src0.dtype == out.dtype == weight.dtype and (src1 is None or src1.dtype == out.dtype)
+        # operands (src0 / src1 / weight) share one storage type; out / addend may use another 16-bit type
+        p.ab_dtype_p1 = 0 if src0.dtype == out.dtype else dtype_code(src0.dtype) + 1
+        assert src0.dtype == weight.dtype and (src1 is None or src1.dtype == src0.dtype), (src0.dtype, weight.dtype)
+        assert addend is None or addend.dtype == out.dtype
         assert weight.numel() == (B if per_batch_weight else 1) * cout * KH * KW * (c0 + c1), (weight.shape, cout, KH, KW, c0, c1)
         self.params = p
         self._keep = (src0, src1, weight, out, bias, gate, addend, gn_sums)
@@ -215,8 +218,9 @@ def init_conv7x7(x_t, x_input, weight, bias, out, B, H, W):
 
 def ln_modulate(x, out, gamma, beta, shift, scale, mod_stride, B, P, C, eps):
     with _launched("ln_modulate", f"{B}x{P}x{C}", 1):
-        check(_lib.load().fd_ln_modulate(_p(x), _p(out), _f32(gamma), _f32(beta), _f32(shift), _f32(scale), mod_stride,
-                                         B, P, C, float(eps), dtype_code(x.dtype), _stream()), "fd_ln_modulate")
+        check(_lib.load().fd_ln_modulate_io(_p(x), _p(out), _f32(gamma), _f32(beta), _f32(shift), _f32(scale), mod_stride,
+                                            B, P, C, float(eps), dtype_code(x.dtype), dtype_code(out.dtype), _stream()),
+              "fd_ln_modulate_io")
 
 
 def dwconv3x3_silu_scan(xz, ld, w, bias, xs, B, H, W, D):

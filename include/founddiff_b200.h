@@ -98,6 +98,9 @@ typedef struct {
     int per_batch_weight;
     int dtype;
     int relu_out;         /* 1: out = max(out, 0) after bias / gate / addend (the DA-CLIP ResNet blocks, src/DACLIP.py) */
+    int ab_dtype_p1;      /* 0: src0 / src1 / weight have type `dtype`; else 1 + their fd_dtype while out / addend keep `dtype`
+                             (mixed 16-bit storage: fp16 residual stream, bf16 block-internal tensors; the tensor cores
+                             need both operands in ONE 16-bit format, the output type is free) */
 } fd_conv_params;
 
 /* CUDA-core fp32-accumulate path (any dtype; the fp32 validation path and the fallback for odd shapes). */
@@ -128,6 +131,11 @@ int fd_init_conv7x7(const float* x_t, const float* x_input, const float* weight,
 int fd_ln_modulate(const void* x, void* out, const float* gamma, const float* beta, const float* shift,
                    const float* scale, int mod_stride, int B, int P, int C, float eps, int dtype,
                    cudaStream_t stream);
+
+/* Same with separate storage types for x (in_dtype) and out (out_dtype); both 16-bit or both fp32. */
+int fd_ln_modulate_io(const void* x, void* out, const float* gamma, const float* beta, const float* shift,
+                      const float* scale, int mod_stride, int B, int P, int C, float eps, int in_dtype, int out_dtype,
+                      cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * SS2D producer: depthwise 3x3 (+bias) + SiLU over the x half of `xz`, written in the 4-direction scan layout.

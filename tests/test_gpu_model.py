@@ -12,10 +12,11 @@ from oracle import founddiff_oracle as O
 pytestmark = pytest.mark.gpu
 
 # North-star gates: 1e-3 (fp32), 1e-2 (16-bit).  MEASURED on B200 (round 1, tests/golden weights): fp32 2.3e-6,
-# fp16 1.4e-3, bf16 1.15e-2 — bf16 STORAGE of every activation + bf16 weights accumulates ~50 roundings of 2^-9 and
-# lands 15 % above the 1e-2 gate (DESIGN.md "Precision").  The bf16 bound asserted here is therefore 1.5e-2, and the
-# strict 1e-2 gate for bf16 is tracked by the xfail test at the bottom of this file.
-GATE = {torch.float32: 1e-3, torch.bfloat16: 1.5e-2, torch.float16: 1e-2}
+# fp16 1.4e-3.  PURE bf16 storage of every activation + bf16 weights accumulates ~50 roundings of 2^-9 and lands at
+# 1.15e-2, 15 % above the gate (DESIGN.md "Precision"; the xfail test at the bottom keeps that visible).  The bf16
+# sampling mode therefore keeps the residual stream, the pre-GroupNorm conv outputs and the convolutions that read them
+# in fp16 (UnetRes.trunk_dtype) and is held to the strict gate here.
+GATE = {torch.float32: 1e-3, torch.bfloat16: 1e-2, torch.float16: 1e-2}
 STRICT_16BIT_GATE = 1e-2
 
 
@@ -194,12 +195,25 @@ def test_cpu_tensors_fail_loudly(model):
         model.sample([torch.rand(1, 1, 64, 64)], last=True)
 
 
-@pytest.mark.xfail(reason="bf16 storage + bf16 weights measure 1.15e-2 > 1e-2 (north-star bf16 gate); fp16 meets it", strict=False)
+@pytest.mark.xfail(reason="PURE bf16 storage (bf16 residual stream + bf16 weights) measures 1.15e-2 > 1e-2; the default "
+                          "bf16 mode (fp16 residual stream) and fp16 meet the gate", strict=False)
+def test_pure_bf16_storage_misses_strict_gate(model):
+    g = load_golden("unet_64x96.npz")
+    set_mode(model, torch.bfloat16)
+    model.model.trunk_dtype = torch.bfloat16
+    try:
+        time = g["t999.time"].cuda()
+        assert rel(model.model(g["x_in"].cuda(), [time, time])[0], g["t999.out"]) < STRICT_16BIT_GATE
+    finally:
+        model.model.trunk_dtype = None
+
+
 def test_bf16_meets_strict_north_star_gate(model):
     g = load_golden("unet_64x96.npz")
     set_mode(model, torch.bfloat16)
     time = g["t999.time"].cuda()
-    assert rel(model.model(g["x_in"].cuda(), [time, time])[0], g["t999.out"]) < STRICT_16BIT_GATE
+    r = rel(model.model(g["x_in"].cuda(), [time, time])[0], g["t999.out"])
+    assert r < 0.6 * STRICT_16BIT_GATE, r          # fp16 residual stream: expected ~3e-3
 
 
 def test_fp16_meets_strict_north_star_gate(model):

@@ -4,10 +4,12 @@
 //   SBO = HT_W*128 (not a multiple of 1024).  Tries base_offset = 0 and base_offset = (start >> 7) & 7.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -o umma_halo_probe umma_halo_probe.cu ; prints mismatch counts.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 
 #define DEVINL __device__ __forceinline__
 constexpr int HT_W = 10, HT_H = 18, NCOL = 64;
@@ -20,7 +22,7 @@ DEVINL uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off)
 __host__ __device__ inline float aval(int R, int k) { return (float)((R * 7 + k * 3) % 17 - 8); }
 __host__ __device__ inline float bval(int n, int k) { return (float)((n * 5 + k) % 13 - 6); }
 
-__global__ void __launch_bounds__(128) probe(float* out, int dy, int dx, int use_base_off) {
+__global__ void __launch_bounds__(128) probe(float* out, int dy, int dx, int use_base_off, int b_is_f16 = 0) {
     extern __shared__ __align__(1024) uint8_t raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;                      // 180 rows x 128 B
@@ -33,7 +35,8 @@ __global__ void __launch_bounds__(128) probe(float* out, int dy, int dx, int use
     }
     for (int i = threadIdx.x; i < NCOL * 64; i += 128) {
         const int n = i / 64, k = i % 64;
-        *(__nv_bfloat16*)(sB + n * 128 + (((k / 8) ^ (n % 8)) * 16) + (k % 8) * 2) = __float2bfloat16(bval(n, k));
+        if (b_is_f16) *(__half*)(sB + n * 128 + (((k / 8) ^ (n % 8)) * 16) + (k % 8) * 2) = __float2half(bval(n, k) + 0.0009765625f * (float)(k & 3));
+        else *(__nv_bfloat16*)(sB + n * 128 + (((k / 8) ^ (n % 8)) * 16) + (k % 8) * 2) = __float2bfloat16(bval(n, k));
     }
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(128) probe(float* out, int dy, int dx, int use
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *slot;
     if (threadIdx.x == 0) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | ((b_is_f16 ? 0u : 1u) << 10) | ((uint32_t)(NCOL >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t a0 = smem_u32(sA) + (uint32_t)((dy * HT_W + dx) * 128);
         const uint32_t boff = use_base_off ? ((a0 >> 7) & 7) : 0;
         for (int k = 0; k < 4; ++k) {
@@ -108,6 +111,25 @@ int main() {
                 total_bad += bad;
             }
         printf("== base_off mode %d: total mismatches %d\n", ub, total_bad);
+    }
+    // mixed operand formats: A bf16, B fp16 (values with 2^-10 fractions that bf16 could not hold)
+    {
+        probe<<<1, 128, 36 * 1024>>>(d_out, 1, 1, 0, 1);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("mixed A=bf16/B=f16: CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(h, d_out, 128 * NCOL * sizeof(float), cudaMemcpyDeviceToHost);
+        int bad = 0;
+        double maxerr = 0;
+        for (int m = 0; m < 128; ++m)
+            for (int n = 0; n < NCOL; ++n) {
+                const int R = (m / 8 + 1) * HT_W + (m % 8) + 1;
+                double ref = 0;
+                for (int k = 0; k < 64; ++k) ref += (double)aval(R, k) * ((double)bval(n, k) + 0.0009765625 * (k & 3));
+                const double err = fabs((double)h[m * NCOL + n] - ref);
+                if (err > maxerr) maxerr = err;
+                if (err > 1e-3) ++bad;
+            }
+        printf("== mixed A=bf16 / B=f16: %d mismatches, max abs err %.3e\n", bad, maxerr);
     }
     return 0;
 }
