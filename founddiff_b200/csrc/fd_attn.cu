@@ -130,7 +130,7 @@ template <typename T> FD_DEVINL void dw_st(T* p, const float (&v)[4]) {
         __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
         r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
     } else {
-        __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+        __half2 a = fd_floats2half2_sat(v[0], v[1]), b = fd_floats2half2_sat(v[2], v[3]);
         r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
     }
     *reinterpret_cast<uint2*>(p) = r;

@@ -9,6 +9,20 @@
 
 #define FD_DEVINL __device__ __forceinline__
 
+// fp16 stores saturate to +-65504 instead of producing inf (one F2FP.SATFINITE either way): the fp16-stored tensors are
+// normalisation-bounded, this only makes an out-of-range value degrade gracefully.
+FD_DEVINL __half2 fd_floats2half2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return *reinterpret_cast<__half2*>(&r);
+}
+FD_DEVINL __half fd_float2half_sat(float v) {
+    unsigned short r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return *reinterpret_cast<__half*>(&r);
+}
+
+
 // Every extern "C" entry point returns 0 or a cudaError_t value; nothing throws across the ABI.
 #define FD_LAUNCH_CHECK()                        \
     do {                                         \
@@ -27,7 +41,7 @@ template <> struct fd_type<__nv_bfloat16> {
 };
 template <> struct fd_type<__half> {
     static FD_DEVINL float ld(const __half* p) { return __half2float(*p); }
-    static FD_DEVINL void st(__half* p, float v) { *p = __float2half_rn(v); }
+    static FD_DEVINL void st(__half* p, float v) { *p = fd_float2half_sat(v); }
 };
 
 template <typename T> FD_DEVINL float fd_ld(const T* p) { return fd_type<T>::ld(p); }
@@ -68,7 +82,7 @@ template <> FD_DEVINL void fd_stv<__half, 8>(__half* p, const float (&v)[8]) {
     uint4 t;
     __half2* h = reinterpret_cast<__half2*>(&t);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) h[i] = fd_floats2half2_sat(v[2 * i], v[2 * i + 1]);
     *reinterpret_cast<uint4*>(p) = t;
 }
 

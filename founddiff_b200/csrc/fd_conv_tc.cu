@@ -200,7 +200,7 @@ template <typename T> FD_DEVINL void store16(T* dst, const float (&v)[16]) {
             __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
             w[i] = *reinterpret_cast<uint32_t*>(&h);
         } else {
-            __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            __half2 h = fd_floats2half2_sat(v[2 * i], v[2 * i + 1]);
             w[i] = *reinterpret_cast<uint32_t*>(&h);
         }
     }

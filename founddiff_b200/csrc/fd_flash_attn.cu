@@ -25,7 +25,7 @@ template <typename T> FD_DEVINL uint32_t pack2(float a, float b) {
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
         return *reinterpret_cast<uint32_t*>(&h);
     } else {
-        __half2 h = __floats2half2_rn(a, b);
+        __half2 h = fd_floats2half2_sat(a, b);
         return *reinterpret_cast<uint32_t*>(&h);
     }
 }

@@ -485,6 +485,159 @@ extern "C" int fd_selective_scan_fwd(const void* u, const void* delta, const flo
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Channel-per-lane scan for the deep levels (many short rows: batch*dim >= ~16 K rows, d_state 16 / 32).
+// A LANE owns one (batch, channel) row and walks it sequentially with its d_state states in registers — no cross-lane
+// scan at all: per (step, state) the work is FMUL, MUFU.EX2, FMUL, FFMA, FFMA (5 issue slots instead of ~15 for the
+// warp-shuffle formulation), which puts these launches on the MUFU pipe.  The 32 lanes of a warp are 32 consecutive
+// channels of one direction group, so (a) B_n[l] / C_n[l] are warp-uniform: they are staged per 64-step chunk, in the
+// time-major layout (B, 4, L, N) the x_proj kernel writes for this path, and read as broadcast LDS.128; (b) the fused
+// EfficientMerge store is naturally coalesced: a warp writes 32 consecutive channels (64 B) of one pixel per step.
+// u / delta are read straight from global memory, 16 bytes per lane per 8 steps, prefetched one octet ahead.
+constexpr int kCLChunk = 64;
+
+template <typename T, int NS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) selective_scan_cl_kernel(
+    const T* __restrict__ u, const T* __restrict__ delta, const float* __restrict__ A, const float* __restrict__ Bt,
+    const float* __restrict__ Ct, const float* __restrict__ D, const float* __restrict__ delta_bias, T* __restrict__ y,
+    int dim, int L, int softplus, int H, int W) {
+    extern __shared__ __align__(16) float s_cl[];          // [2][2][kCLChunk][NS]: buffer, B/C, step, state
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per_group = dim / 4;
+    const int blocks_per_group = per_group / (WARPS * 32);
+    const int bg = blockIdx.x / blocks_per_group;          // b * 4 + k
+    const int dloc = (blockIdx.x % blocks_per_group) * (WARPS * 32) + warp * 32 + lane;
+    const int b = bg >> 2, k = bg & 3;
+    const int d = k * per_group + dloc;
+    const long row = (long)b * dim + d;
+    const T* ur = u + row * (long)L;
+    const T* dr = delta + row * (long)L;
+    const float* Bg = Bt + (long)bg * L * NS;
+    const float* Cg = Ct + (long)bg * L * NS;
+    const float bias = delta_bias ? delta_bias[d] : 0.f;
+    const float Dd = D ? D[d] : 0.f;
+    float A2[NS], h[NS];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) { A2[n] = A[(long)d * NS + n] * 1.4426950408889634f; h[n] = 0.f; }
+
+    auto stage = [&](int c0, int buf) {                    // B and C of steps [c0, c0 + 64): two contiguous runs of 64*NS floats
+        float* dst = s_cl + (size_t)buf * 2 * kCLChunk * NS;
+        constexpr int kVec = kCLChunk * NS / 4;            // 16-byte vectors per tensor
+        for (int i = threadIdx.x; i < 2 * kVec; i += WARPS * 32) {
+            const int which = i / kVec, v = i % kVec;
+            const int l = c0 + (v * 4) / NS;
+            const float* src = (which ? Cg : Bg) + (long)c0 * NS + v * 4;
+            cp_async16(dst + which * kCLChunk * NS + v * 4, l < L ? src : Bg, l < L);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // EfficientMerge coordinates of step l, advanced incrementally (src/emamba2.py:207-210, 253-256)
+    const int mdiv = (k & 1) ? (H >> 1) : (W >> 1);
+    int mq = 0, mr = 0;
+    T* ybase = y + (long)b * H * W * per_group + dloc;
+
+    const int nchunks = (L + kCLChunk - 1) / kCLChunk;
+    stage(0, 0);
+    RawItems<T> dt_raw = load_raw<T>(dr), u_raw = load_raw<T>(ur);
+    for (int c = 0; c < nchunks; ++c) {
+        const int c0 = c * kCLChunk;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // chunk c's B/C visible; every warp is past chunk c-1
+        if (c + 1 < nchunks) stage(c0 + kCLChunk, (c + 1) & 1);
+        const float* sB = s_cl + (size_t)(c & 1) * 2 * kCLChunk * NS;
+        const float* sC = sB + kCLChunk * NS;
+        const int steps = min(kCLChunk, L - c0);           // L % 8 == 0
+        for (int s0 = 0; s0 < steps; s0 += kItems) {
+            float dtv[kItems], uv[kItems];
+            raw_to_float<T>(dt_raw, dtv);
+            raw_to_float<T>(u_raw, uv);
+            {
+                const int ln = min(c0 + s0 + kItems, L - kItems);      // next octet (clamped on the last one)
+                dt_raw = load_raw<T>(dr + ln);
+                u_raw = load_raw<T>(ur + ln);
+            }
+#pragma unroll
+            for (int i = 0; i < kItems; ++i) {
+                float t = dtv[i] + bias;
+                if (softplus) t = fast_softplus(t);
+                const float du = t * uv[i];
+                float y0 = Dd * uv[i], y1 = 0.f, y2 = 0.f, y3 = 0.f;
+                const float* pb = sB + (s0 + i) * NS;
+                const float* pc = sC + (s0 + i) * NS;
+#pragma unroll
+                for (int n = 0; n < NS; n += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(pb + n);
+                    const float4 c4 = *reinterpret_cast<const float4*>(pc + n);
+                    h[n] = fmaf(ex2_approx(t * A2[n]), h[n], du * b4.x);
+                    y0 = fmaf(h[n], c4.x, y0);
+                    h[n + 1] = fmaf(ex2_approx(t * A2[n + 1]), h[n + 1], du * b4.y);
+                    y1 = fmaf(h[n + 1], c4.y, y1);
+                    h[n + 2] = fmaf(ex2_approx(t * A2[n + 2]), h[n + 2], du * b4.z);
+                    y2 = fmaf(h[n + 2], c4.z, y2);
+                    h[n + 3] = fmaf(ex2_approx(t * A2[n + 3]), h[n + 3], du * b4.w);
+                    y3 = fmaf(h[n + 3], c4.w, y3);
+                }
+                int hh, ww;
+                if (k & 1) { ww = 2 * mq + (k >> 1); hh = 2 * mr + 1; }      // column-major sub-grids
+                else       { hh = 2 * mq; ww = 2 * mr + (k >> 1); }
+                fd_st(ybase + ((long)hh * W + ww) * per_group, (y0 + y1) + (y2 + y3));
+                if (++mr == mdiv) { mr = 0; ++mq; }
+            }
+        }
+    }
+}
+
+template <typename T, int NS>
+static int scan_cl_launch(const void* u, const void* delta, const float* A, const float* Bt, const float* Ct, const float* D,
+                          const float* delta_bias, void* y, int batch, int dim, int H, int W, int softplus, cudaStream_t st) {
+    const int L = (H / 2) * (W / 2);
+    const int per_group = dim / 4;
+    const size_t smem = (size_t)2 * 2 * kCLChunk * NS * sizeof(float);
+    // Block size (measured, B200): d_state 32 is bounded by occupancy (128 registers, 32 KB of staging per block) and runs
+    // best with 4-warp blocks; for d_state <= 16 the launch is one wave of long-running blocks and an uneven block count
+    // per SM is lost time, so the largest of 4 / 2 / 1 warps that still gives >= 6 blocks per SM is used.
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long total_warps = (long)batch * dim / 32;
+#define CL_CASE(WV)                                                                                                    \
+    if (per_group % (WV * 32) == 0 && (WV == 1 || NS >= 32 || total_warps / WV >= 6L * sms)) {                         \
+        static bool attr = false;                                                                                      \
+        if (!attr) {                                                                                                   \
+            cudaError_t e = cudaFuncSetAttribute(selective_scan_cl_kernel<T, NS, WV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                                                       \
+            attr = true;                                                                                               \
+        }                                                                                                              \
+        const unsigned grid = (unsigned)(batch * 4 * (per_group / (WV * 32)));                                         \
+        selective_scan_cl_kernel<T, NS, WV><<<grid, WV * 32, smem, st>>>((const T*)u, (const T*)delta, A, Bt, Ct, D, delta_bias, \
+                                                                         (T*)y, dim, L, softplus, H, W);               \
+        FD_LAUNCH_CHECK();                                                                                             \
+        return 0;                                                                                                      \
+    }
+    // 4-warp blocks: more blocks than SMs already at 16 K rows, and B/C staging is shared by 128 channels
+    CL_CASE(4) CL_CASE(2) CL_CASE(1)
+#undef CL_CASE
+    return FD_ERR_UNSUPPORTED;
+}
+
+extern "C" int fd_selective_scan_fwd_merge_cl(const void* u, const void* delta, const float* A, const float* Bt, const float* Ct,
+                                              const float* D, const float* delta_bias, void* y_nhwc, int batch, int dim, int H,
+                                              int W, int dstate, int delta_softplus, int io_dtype, cudaStream_t stream) {
+    if (!u || !delta || !A || !Bt || !Ct || !y_nhwc) return FD_ERR_BAD_ARGUMENT;
+    if (batch <= 0 || dim <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || dim % 4) return FD_ERR_BAD_ARGUMENT;
+    const int L = (H / 2) * (W / 2);
+    if (L % kItems || (dim / 4) % 32 || (((uintptr_t)u | (uintptr_t)delta | (uintptr_t)Bt | (uintptr_t)Ct) & 15)) return FD_ERR_UNSUPPORTED;
+#define CL_N(NSV)                                                                                                       \
+    if (dstate == NSV) {                                                                                               \
+        if (io_dtype == FD_BF16) return scan_cl_launch<__nv_bfloat16, NSV>(u, delta, A, Bt, Ct, D, delta_bias, y_nhwc, batch, dim, H, W, delta_softplus, stream); \
+        if (io_dtype == FD_F16) return scan_cl_launch<__half, NSV>(u, delta, A, Bt, Ct, D, delta_bias, y_nhwc, batch, dim, H, W, delta_softplus, stream); \
+    }
+    CL_N(8) CL_N(16) CL_N(32)
+#undef CL_N
+    return FD_ERR_UNSUPPORTED;
+}
+
 // Scan + EfficientMerge + fused dt_proj (see include/founddiff_b200.h)
 template <typename T, int NS, int RDT>
 static int scan_xdbl_launch(const void* u, const float* x_dbl, const float* dt_w, const float* A, const float* D,

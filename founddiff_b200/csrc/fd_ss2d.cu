@@ -451,8 +451,8 @@ __global__ void __launch_bounds__(256) xdt_proj_mma_kernel(const T* __restrict__
                 *reinterpret_cast<__nv_bfloat162*>(so + g * XT_XLD + col) = __floats2bfloat162_rn(o[nt][0], o[nt][1]);
                 *reinterpret_cast<__nv_bfloat162*>(so + (g + 8) * XT_XLD + col) = __floats2bfloat162_rn(o[nt][2], o[nt][3]);
             } else {
-                *reinterpret_cast<__half2*>(so + g * XT_XLD + col) = __floats2half2_rn(o[nt][0], o[nt][1]);
-                *reinterpret_cast<__half2*>(so + (g + 8) * XT_XLD + col) = __floats2half2_rn(o[nt][2], o[nt][3]);
+                *reinterpret_cast<__half2*>(so + g * XT_XLD + col) = fd_floats2half2_sat(o[nt][0], o[nt][1]);
+                *reinterpret_cast<__half2*>(so + (g + 8) * XT_XLD + col) = fd_floats2half2_sat(o[nt][2], o[nt][3]);
             }
         }
         __syncwarp();
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
                                                          float* __restrict__ xdbl, int D, int L, int CC,
                                                          const T* __restrict__ dw16 = nullptr, T* __restrict__ dts = nullptr,
                                                          float* __restrict__ Bs = nullptr, float* __restrict__ Cs = nullptr,
-                                                         int R = 0, int N = 0, int Rp = 0) {
+                                                         int R = 0, int N = 0, int Rp = 0, int bc_time_major = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_x = reinterpret_cast<T*>(smem_raw);                     // [XP_STAGES][XT_KC][XT_XLD]
     T* s_w = s_x + XP_STAGES * XT_KC * XT_XLD;                   // [XP_STAGES][MT*16][XT_WLD]
@@ -585,8 +585,15 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
                         fd_st(s_xd + c * XT_XLD + col, v0);
                         fd_st(s_xd + c * XT_XLD + col + 1, v1);
                     } else if (c < CC && l0 + col < L) {
-                        float* dst = (c < R + N ? Bs + ((long)bk * N + (c - R)) * L : Cs + ((long)bk * N + (c - R - N)) * L) + l0 + col;
-                        *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+                        if (bc_time_major) {       // (B, 4, L, N): the channel-per-lane scan reads all N states of a step at once
+                            const int n = c < R + N ? c - R : c - R - N;
+                            float* dst = (c < R + N ? Bs : Cs) + ((long)bk * L + l0 + col) * N + n;
+                            dst[0] = v0;
+                            dst[N] = v1;
+                        } else {
+                            float* dst = (c < R + N ? Bs + ((long)bk * N + (c - R)) * L : Cs + ((long)bk * N + (c - R - N)) * L) + l0 + col;
+                            *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+                        }
                     }
                 }
         __syncthreads();
@@ -625,8 +632,8 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
                     *reinterpret_cast<__nv_bfloat162*>(so + g * XT_XLD + col) = __floats2bfloat162_rn(o[nt][0], o[nt][1]);
                     *reinterpret_cast<__nv_bfloat162*>(so + (g + 8) * XT_XLD + col) = __floats2bfloat162_rn(o[nt][2], o[nt][3]);
                 } else {
-                    *reinterpret_cast<__half2*>(so + g * XT_XLD + col) = __floats2half2_rn(o[nt][0], o[nt][1]);
-                    *reinterpret_cast<__half2*>(so + (g + 8) * XT_XLD + col) = __floats2half2_rn(o[nt][2], o[nt][3]);
+                    *reinterpret_cast<__half2*>(so + g * XT_XLD + col) = fd_floats2half2_sat(o[nt][0], o[nt][1]);
+                    *reinterpret_cast<__half2*>(so + (g + 8) * XT_XLD + col) = fd_floats2half2_sat(o[nt][2], o[nt][3]);
                 }
             }
             __syncwarp();
@@ -798,7 +805,7 @@ extern "C" int fd_xdt_proj(const void* xs, const float* x_proj_w, const float* d
 
 template <typename T>
 static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, void* dts, float* Bs, float* Cs, int B, int D, int L,
-                          int R, int N, int Rp, cudaStream_t stream) {
+                          int R, int N, int Rp, int bc_layout, cudaStream_t stream) {
     const int CC = R + 2 * N;
     const int MT = (CC + 15) / 16;
     dim3 grid(fd_cdiv(L, XT_L), B * 4);
@@ -813,13 +820,14 @@ static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, vo
             attr_set = true;                                                                                                   \
         }                                                                                                                      \
         x_proj_mma_kernel<T, M, true><<<grid, 256, smem, stream>>>((const T*)xs, (const T*)xw16, nullptr, D, L, CC, (const T*)dw16, \
-                                                                   (T*)dts, Bs, Cs, R, N, Rp);                                  \
+                                                                   (T*)dts, Bs, Cs, R, N, Rp, bc_layout);                       \
         FD_LAUNCH_CHECK();                                                                                                     \
         return 0;                                                                                                              \
     }
         XDT_PIPE_CASE(1) XDT_PIPE_CASE(2) XDT_PIPE_CASE(3) XDT_PIPE_CASE(4) XDT_PIPE_CASE(5) XDT_PIPE_CASE(6)
 #undef XDT_PIPE_CASE
     }
+    if (bc_layout) return FD_ERR_UNSUPPORTED;      // the time-major B / C layout exists in the pipelined kernel only
 #define XDT_MMA_CASE(M)                                                                                                        \
     if (MT == M) {                                                                                                             \
         const size_t smem = ((size_t)XT_KC * XT_XLD + (size_t)M * 16 * XT_WLD + 32 * XT_XLD + 8 * 16 * XT_XLD) * sizeof(T);     \
@@ -840,11 +848,11 @@ static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, vo
 }
 
 extern "C" int fd_xdt_proj_tc(const void* xs, const void* xw16, const void* dw16, void* dts, float* Bs, float* Cs, int B, int D,
-                              int L, int R, int N, int Rp, int dtype, cudaStream_t stream) {
+                              int L, int R, int N, int Rp, int bc_layout, int dtype, cudaStream_t stream) {
     if (!xs || !xw16 || !dw16 || !dts || !Bs || !Cs || B <= 0 || D <= 0 || L <= 0 || R <= 0 || N <= 0) return FD_ERR_BAD_ARGUMENT;
     if ((Rp != 16 && Rp != 32) || R > Rp || D % 16 || R + 2 * N > 96) return FD_ERR_UNSUPPORTED;
-    if (dtype == FD_BF16) return xdt_mma_launch<__nv_bfloat16>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, stream);
-    if (dtype == FD_F16) return xdt_mma_launch<__half>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, stream);
+    if (dtype == FD_BF16) return xdt_mma_launch<__nv_bfloat16>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, bc_layout, stream);
+    if (dtype == FD_F16) return xdt_mma_launch<__half>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, bc_layout, stream);
     return FD_ERR_UNSUPPORTED;
 }
 

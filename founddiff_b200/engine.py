@@ -303,6 +303,11 @@ class UnetEngine:
         # levels with a small dt_rank: x_proj alone, dt_proj applied inside the scan (no (B, 4D, L) delta tensor at all)
         fuse_dt = (fuse_merge and use_xdt_tc and (N, R) in ((4, 4), (8, 8)) and D % 32 == 0
                    and os.environ.get("FD_FUSE_DT", "0") == "1")
+        # deep levels (many short rows, d_state >= 16): channel-per-lane scan, B / C time-major
+        scan_cl = (fuse_merge and use_xdt_tc and N in (16, 32) and D % 32 == 0 and B * 4 * D >= 16384
+                   and os.environ.get("FD_SCAN_CL", "1") == "1")
+        if scan_cl:
+            Bs_t, Cs_t = Bs.view(B, 4, L, N), Cs.view(B, 4, L, N)
         if fuse_dt:
             xdbl = self.buf(f"XDBL{l}", B, 4, R + 2 * N, L, dtype=torch.float32)
             dtw_flat = dtp_w.reshape(4 * D, R).contiguous()
@@ -327,7 +332,12 @@ class UnetEngine:
             ops.ln_modulate(x_in, a, n1w, n1b, sh1, sc1, MS, B, P, C, 1e-5)
             c_in.run()
             ops.dwconv3x3_silu_scan(xz, 4 * C, dw_w, dw_b, xs, B, h, w, D)
-            if fuse_dt:
+            if scan_cl:
+                ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs_t, Cs_t, B, D, L, R, N, time_major=True)
+                ops.selective_scan_fwd_merge_cl(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs_t, Cs_t, Ds, dt_bias, True,
+                                                ys.view(B, P, D), h, w)
+                ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
+            elif fuse_dt:
                 ops.x_proj_tc(xs, xw16, xdbl, B, D, L, R, N)
                 ops.selective_scan_fwd_merge_xdbl(xs.view(B, 4 * D, L), xdbl, dtw_flat, A_neg, Ds, dt_bias, True, ys.view(B, P, D), h, w)
                 ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
@@ -335,7 +345,7 @@ class UnetEngine:
                 ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N)
             else:
                 ops.xdt_proj(xs, xp_w, dtp_w, dts, Bs, Cs, B, D, L, R, N)
-            if fuse_dt:
+            if fuse_dt or scan_cl:
                 pass
             elif fuse_merge:      # scan writes channels-last directly (EfficientMerge fused), then a row-wise LN + gate
                 ops.selective_scan_fwd_merge(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs, Cs, Ds, dt_bias, True,

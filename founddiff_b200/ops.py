@@ -248,10 +248,11 @@ def pack_xdt_weights(x_proj_w: torch.Tensor, dt_w: torch.Tensor, dtype: torch.dt
     return xw.contiguous(), dw.contiguous(), Rp
 
 
-def xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N):
+def xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N, time_major=False):
+    """time_major: Bs / Cs written as (B, 4, L, N) (for selective_scan_fwd_merge_cl) instead of (B, 4, N, L)."""
     with _launched("xdt_proj_tc", f"{B}x{D}x{L} R{R} N{N}", 1):
         check(_lib.load().fd_xdt_proj_tc(_p(xs), _p(xw16), _p(dw16), _p(dts), _f32(Bs), _f32(Cs), B, D, L, R, N, Rp,
-                                         dtype_code(xs.dtype), _stream()), "fd_xdt_proj_tc")
+                                         int(bool(time_major)), dtype_code(xs.dtype), _stream()), "fd_xdt_proj_tc")
 
 
 def x_proj_tc(xs, xw16, x_dbl, B, D, L, R, N):
@@ -259,6 +260,18 @@ def x_proj_tc(xs, xw16, x_dbl, B, D, L, R, N):
     assert x_dbl.dtype == torch.float32 and x_dbl.shape == (B, 4, R + 2 * N, L)
     with _launched("x_proj_tc", f"{B}x{D}x{L} R{R} N{N}", 1):
         check(_lib.load().fd_x_proj_tc(_p(xs), _p(xw16), _f32(x_dbl), B, D, L, R, N, dtype_code(xs.dtype), _stream()), "fd_x_proj_tc")
+
+
+def selective_scan_fwd_merge_cl(u, delta, A, Bt, Ct, D, delta_bias, delta_softplus, y_nhwc, H, W):
+    """Channel-per-lane scan + EfficientMerge (deep levels): Bt, Ct time-major (b, 4, L, N) fp32."""
+    b, kd, L = u.shape
+    n = A.shape[1]
+    assert L == (H // 2) * (W // 2) and Bt.shape == (b, 4, L, n) and Ct.shape == (b, 4, L, n)
+    with _launched("selective_scan_merge", f"{b}x{kd}x{L} N{n} cl"):
+        check(_lib.load().fd_selective_scan_fwd_merge_cl(_p(u), _p(delta), _f32(A), _f32(Bt), _f32(Ct), _f32(D), _f32(delta_bias),
+                                                         _p(y_nhwc), b, kd, H, W, n, int(bool(delta_softplus)), dtype_code(u.dtype),
+                                                         _stream()), "fd_selective_scan_fwd_merge_cl")
+    return y_nhwc
 
 
 def selective_scan_fwd_merge_xdbl(u, x_dbl, dt_w, A, D, delta_bias, delta_softplus, y_nhwc, H, W):

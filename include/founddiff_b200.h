@@ -64,6 +64,13 @@ int fd_selective_scan_fwd_merge_xdbl(const void* u, const float* x_dbl, const fl
                                      const float* delta_bias, void* y_nhwc, int batch, int dim, int H, int W, int dstate,
                                      int dt_rank, int delta_softplus, int io_dtype, cudaStream_t stream);
 
+/* Scan + EfficientMerge for the deep levels (many short rows, d_state 8 / 16 / 32): one LANE per (batch, channel) row, the
+ * states in registers, no cross-lane scan.  Same arguments as fd_selective_scan_fwd_merge except that Bt, Ct are
+ * TIME-MAJOR (batch, 4, L, dstate) fp32 (fd_xdt_proj_tc with bc_layout = 1).  dim/4 % 32 == 0, L % 8 == 0; 16-bit io. */
+int fd_selective_scan_fwd_merge_cl(const void* u, const void* delta, const float* A, const float* Bt, const float* Ct,
+                                   const float* D, const float* delta_bias, void* y_nhwc, int batch, int dim, int H, int W,
+                                   int dstate, int delta_softplus, int io_dtype, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution / 1x1 GEMM with fused epilogue — replaces F.conv2d / nn.Linear call sites:
  *   WeightStandardizedConv2d 3x3 (src/DADiff.py:139-154; standardisation folded into `weight` by the host),
@@ -156,7 +163,8 @@ int fd_xdt_proj(const void* xs, const float* x_proj_w, const float* dt_w, void* 
 /* Tensor-core variant (dtype bf16 / fp16): xw16 = x_proj_w in `dtype`, rows zero-padded to a multiple of 16:
  * (4, CCp, D); dw16 = dt_w in `dtype`, columns zero-padded to Rp in {16, 32}: (4, D, Rp).  Same outputs. */
 int fd_xdt_proj_tc(const void* xs, const void* xw16, const void* dw16, void* dts, float* Bs, float* Cs, int B, int D,
-                   int L, int R, int N, int Rp, int dtype, cudaStream_t stream);
+                   int L, int R, int N, int Rp, int bc_layout, int dtype, cudaStream_t stream);
+/* bc_layout: 0 = Bs, Cs as (B,4,N,L); 1 = time-major (B,4,L,N), the layout fd_selective_scan_fwd_merge_cl reads. */
 
 /* x_proj alone on the tensor cores (levels with dt_rank <= 8): x_dbl (B, 4, R+2N, L) fp32 = einsum(xs, x_proj_weight)
  * (src/emamba2.py:334-336).  Rows [0,R) are the low-rank dt input, [R,R+N) B, [R+N,R+2N) C; fd_selective_scan_fwd_merge_xdbl

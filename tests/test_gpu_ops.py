@@ -605,3 +605,36 @@ def test_x_proj_and_scan_with_fused_dt_proj(ops, cfg, dt):
     ops.selective_scan_fwd_merge_xdbl(xs.reshape(B, 4 * D, L).to("cuda", dt), x_dbl, Wdt.reshape(4 * D, R).cuda(), A.cuda(), Dp.cuda(),
                                       bias.cuda(), True, y, H, W)
     assert rel(y.reshape(B, H, W, D), y_ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("cfg", [(16, 16, 32, 16, 16), (16, 32, 64, 32, 32), (8, 24, 96, 16, 16), (32, 16, 128, 8, 8)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_channel_per_lane_scan_with_time_major_bc(ops, cfg, dt):
+    """xdt_proj with time-major B/C + the channel-per-lane scan with EfficientMerge fused == oracle x_proj -> dt_proj ->
+    selective scan -> EfficientMerge (src/emamba2.py:334-367); also == the warp-shuffle kernel on the same inputs."""
+    H, W, D, N, R = cfg
+    B, L = 2, (H // 2) * (W // 2)
+    g = torch.Generator().manual_seed(H * W + D + N)
+    xs = q(torch.randn(B, 4, D, L, generator=g), dt)
+    Wx = torch.randn(4, R + 2 * N, D, generator=g) / math.sqrt(D)
+    Wdt = torch.randn(4, D, R, generator=g) / math.sqrt(R)
+    A = -torch.exp(torch.randn(4 * D, N, generator=g) * 0.3)
+    Dp, bias = torch.randn(4 * D, generator=g), torch.randn(4 * D, generator=g) * 0.5
+    xw16, dw16, Rp = ops.pack_xdt_weights(Wx.cuda(), Wdt.cuda(), dt)
+    xs_d = xs.to("cuda", dt)
+    dts = torch.empty(B, 4, D, L, device="cuda", dtype=dt)
+    Bs, Cs = torch.empty(B, 4, N, L, device="cuda"), torch.empty(B, 4, N, L, device="cuda")
+    Bt, Ct = torch.empty(B, 4, L, N, device="cuda"), torch.empty(B, 4, L, N, device="cuda")
+    dts_t = torch.empty_like(dts)
+    ops.xdt_proj_tc(xs_d, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N)
+    ops.xdt_proj_tc(xs_d, xw16, dw16, Rp, dts_t, Bt, Ct, B, D, L, R, N, time_major=True)
+    assert torch.equal(Bt.permute(0, 1, 3, 2), Bs) and torch.equal(Ct.permute(0, 1, 3, 2), Cs) and torch.equal(dts, dts_t)
+    # oracle scan on exactly the tensors the kernel reads
+    y_ref = scan_cpu.selective_scan_fwd(xs.reshape(B, 4 * D, L), dts.float().cpu().reshape(B, 4 * D, L), A, Bs.cpu(), Cs.cpu(), Dp, bias, True)
+    y_ref = O.efficient_merge(y_ref.view(B, 4, D, L), H, W).permute(0, 2, 3, 1)
+    y = torch.empty(B, H * W, D, device="cuda", dtype=dt)
+    ops.selective_scan_fwd_merge_cl(xs_d.view(B, 4 * D, L), dts.view(B, 4 * D, L), A.cuda(), Bt, Ct, Dp.cuda(), bias.cuda(), True, y, H, W)
+    assert rel(y.reshape(B, H, W, D), y_ref) < TOL[dt]
+    y2 = torch.empty_like(y)
+    ops.selective_scan_fwd_merge(xs_d.view(B, 4 * D, L), dts.view(B, 4 * D, L), A.cuda(), Bs, Cs, Dp.cuda(), bias.cuda(), True, y2, H, W)
+    assert rel(y, y2) < TOL[dt]
