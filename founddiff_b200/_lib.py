@@ -75,7 +75,7 @@ def load():
         "fd_ln_modulate_io": [V] * 6 + [I] * 4 + [F, I, I, V],
         "fd_dwconv3x3_silu_scan": [V, I, V, V, V, I, I, I, I, I, V],
         "fd_xdt_proj": [V] * 6 + [I] * 6 + [V],
-        "fd_xdt_proj_tc": [V] * 6 + [I] * 8 + [V],
+        "fd_xdt_proj_tc": [V] * 6 + [I] * 7 + [V, I, I, V],
         "fd_merge_ln_gate": [V, V, I, I, V, V, V, V, V, I, I, I, I, F, I, V],
         "fd_dwconv3x3_qkv_gram": [V] * 5 + [I] * 5 + [V],
         "fd_attn_weff": [V] * 5 + [I] * 3 + [V],

@@ -479,6 +479,15 @@ __global__ void __launch_bounds__(256) xdt_proj_mma_kernel(const T* __restrict__
 // itself (R FMAs per step), so the (B, 4, D, L) delta tensor is never written or read: the op becomes a single
 // streaming pass over xs.  128-step tiles, 8 warps x 16 columns, 32-channel chunks through a 3-stage cp.async ring.
 constexpr int XP_STAGES = 3;
+FD_DEVINL float xp_softplus(float x) {      // same branch-free 2-MUFU form as the scan kernel's (fd_scan.cu)
+    float y, lg;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    const float w = 1.f + y;
+    const float corr = (y < 1.f) ? (y - (w - 1.f)) * (1.f - y) : 0.f;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(w));
+    const float r = fmaf(lg, 0.6931471805599453f, corr);
+    return x > 20.f ? x : r;
+}
 FD_DEVINL void xp_cp_async16(void* smem_dst, const void* gsrc, bool valid) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     const int sz = valid ? 16 : 0;
@@ -492,7 +501,8 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
                                                          float* __restrict__ xdbl, int D, int L, int CC,
                                                          const T* __restrict__ dw16 = nullptr, T* __restrict__ dts = nullptr,
                                                          float* __restrict__ Bs = nullptr, float* __restrict__ Cs = nullptr,
-                                                         int R = 0, int N = 0, int Rp = 0, int bc_time_major = 0) {
+                                                         int R = 0, int N = 0, int Rp = 0, int bc_time_major = 0,
+                                                         const float* __restrict__ dt_bias = nullptr, int dt_softplus = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_x = reinterpret_cast<T*>(smem_raw);                     // [XP_STAGES][XT_KC][XT_XLD]
     T* s_w = s_x + XP_STAGES * XT_KC * XT_XLD;                   // [XP_STAGES][MT*16][XT_WLD]
@@ -622,6 +632,18 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
                     ldmatrix_x4_trans(bfr, s_xd + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * XT_XLD + np * 16 + 8 * (lane >> 4));
                     mma_16816<T>(o[2 * np], afr, bfr[0], bfr[1]);
                     mma_16816<T>(o[2 * np + 1], afr, bfr[2], bfr[3]);
+                }
+            }
+            if (dt_bias) {          // delta = softplus(dt_proj(...) + dt_bias) finished here: the scan (issue-bound) gets final values
+                const float b0 = dbase + g < D ? __ldg(dt_bias + (long)k * D + dbase + g) : 0.f;
+                const float b1 = dbase + g + 8 < D ? __ldg(dt_bias + (long)k * D + dbase + g + 8) : 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 16; ++nt) {
+                    o[nt][0] += b0; o[nt][1] += b0; o[nt][2] += b1; o[nt][3] += b1;
+                    if (dt_softplus) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[nt][e] = xp_softplus(o[nt][e]);
+                    }
                 }
             }
             __syncwarp();
@@ -805,7 +827,7 @@ extern "C" int fd_xdt_proj(const void* xs, const float* x_proj_w, const float* d
 
 template <typename T>
 static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, void* dts, float* Bs, float* Cs, int B, int D, int L,
-                          int R, int N, int Rp, int bc_layout, cudaStream_t stream) {
+                          int R, int N, int Rp, int bc_layout, const float* dt_bias, int dt_softplus, cudaStream_t stream) {
     const int CC = R + 2 * N;
     const int MT = (CC + 15) / 16;
     dim3 grid(fd_cdiv(L, XT_L), B * 4);
@@ -820,14 +842,14 @@ static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, vo
             attr_set = true;                                                                                                   \
         }                                                                                                                      \
         x_proj_mma_kernel<T, M, true><<<grid, 256, smem, stream>>>((const T*)xs, (const T*)xw16, nullptr, D, L, CC, (const T*)dw16, \
-                                                                   (T*)dts, Bs, Cs, R, N, Rp, bc_layout);                       \
+                                                                   (T*)dts, Bs, Cs, R, N, Rp, bc_layout, dt_bias, dt_softplus); \
         FD_LAUNCH_CHECK();                                                                                                     \
         return 0;                                                                                                              \
     }
         XDT_PIPE_CASE(1) XDT_PIPE_CASE(2) XDT_PIPE_CASE(3) XDT_PIPE_CASE(4) XDT_PIPE_CASE(5) XDT_PIPE_CASE(6)
 #undef XDT_PIPE_CASE
     }
-    if (bc_layout) return FD_ERR_UNSUPPORTED;      // the time-major B / C layout exists in the pipelined kernel only
+    if (bc_layout || dt_bias) return FD_ERR_UNSUPPORTED;      // time-major B / C and the fused bias + softplus exist in the pipelined kernel only
 #define XDT_MMA_CASE(M)                                                                                                        \
     if (MT == M) {                                                                                                             \
         const size_t smem = ((size_t)XT_KC * XT_XLD + (size_t)M * 16 * XT_WLD + 32 * XT_XLD + 8 * 16 * XT_XLD) * sizeof(T);     \
@@ -848,11 +870,12 @@ static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, vo
 }
 
 extern "C" int fd_xdt_proj_tc(const void* xs, const void* xw16, const void* dw16, void* dts, float* Bs, float* Cs, int B, int D,
-                              int L, int R, int N, int Rp, int bc_layout, int dtype, cudaStream_t stream) {
+                              int L, int R, int N, int Rp, int bc_layout, const float* dt_bias, int delta_softplus, int dtype,
+                              cudaStream_t stream) {
     if (!xs || !xw16 || !dw16 || !dts || !Bs || !Cs || B <= 0 || D <= 0 || L <= 0 || R <= 0 || N <= 0) return FD_ERR_BAD_ARGUMENT;
     if ((Rp != 16 && Rp != 32) || R > Rp || D % 16 || R + 2 * N > 96) return FD_ERR_UNSUPPORTED;
-    if (dtype == FD_BF16) return xdt_mma_launch<__nv_bfloat16>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, bc_layout, stream);
-    if (dtype == FD_F16) return xdt_mma_launch<__half>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, bc_layout, stream);
+    if (dtype == FD_BF16) return xdt_mma_launch<__nv_bfloat16>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, bc_layout, dt_bias, delta_softplus, stream);
+    if (dtype == FD_F16) return xdt_mma_launch<__half>(xs, xw16, dw16, dts, Bs, Cs, B, D, L, R, N, Rp, bc_layout, dt_bias, delta_softplus, stream);
     return FD_ERR_UNSUPPORTED;
 }
 

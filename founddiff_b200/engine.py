@@ -305,9 +305,12 @@ class UnetEngine:
                    and os.environ.get("FD_FUSE_DT", "0") == "1")
         # deep levels (many short rows, d_state >= 16): channel-per-lane scan, B / C time-major
         scan_cl = (fuse_merge and use_xdt_tc and N in (16, 32) and D % 32 == 0 and B * 4 * D >= 16384
-                   and os.environ.get("FD_SCAN_CL", "1") == "1")
+                   and os.environ.get("FD_SCAN_CL", "1") == "1")       # d_state 8 measured slower this way (too few rows)
         if scan_cl:
             Bs_t, Cs_t = Bs.view(B, 4, L, N), Cs.view(B, 4, L, N)
+        # bias + softplus finished by the x_proj/dt_proj kernel: measured neutral-to-negative for the warp-shuffle scan levels
+        # (the scan did not get faster, the producer got slower), so only the channel-per-lane levels use it
+        xdt_softplus = False
         if fuse_dt:
             xdbl = self.buf(f"XDBL{l}", B, 4, R + 2 * N, L, dtype=torch.float32)
             dtw_flat = dtp_w.reshape(4 * D, R).contiguous()
@@ -333,14 +336,16 @@ class UnetEngine:
             c_in.run()
             ops.dwconv3x3_silu_scan(xz, 4 * C, dw_w, dw_b, xs, B, h, w, D)
             if scan_cl:
-                ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs_t, Cs_t, B, D, L, R, N, time_major=True)
-                ops.selective_scan_fwd_merge_cl(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs_t, Cs_t, Ds, dt_bias, True,
+                ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs_t, Cs_t, B, D, L, R, N, time_major=True, dt_bias=dt_bias, delta_softplus=True)
+                ops.selective_scan_fwd_merge_cl(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs_t, Cs_t, Ds, None, False,
                                                 ys.view(B, P, D), h, w)
                 ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
             elif fuse_dt:
                 ops.x_proj_tc(xs, xw16, xdbl, B, D, L, R, N)
                 ops.selective_scan_fwd_merge_xdbl(xs.view(B, 4 * D, L), xdbl, dtw_flat, A_neg, Ds, dt_bias, True, ys.view(B, P, D), h, w)
                 ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
+            elif xdt_softplus:       # delta finished (bias + softplus) by the HBM-bound producer; the issue-bound scan takes it as is
+                ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N, dt_bias=dt_bias, delta_softplus=True)
             elif use_xdt_tc:
                 ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N)
             else:
@@ -348,8 +353,8 @@ class UnetEngine:
             if fuse_dt or scan_cl:
                 pass
             elif fuse_merge:      # scan writes channels-last directly (EfficientMerge fused), then a row-wise LN + gate
-                ops.selective_scan_fwd_merge(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs, Cs, Ds, dt_bias, True,
-                                             ys.view(B, P, D), h, w)
+                ops.selective_scan_fwd_merge(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs, Cs, Ds,
+                                             None if xdt_softplus else dt_bias, not xdt_softplus, ys.view(B, P, D), h, w)
                 ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
             else:
                 ops.selective_scan_fwd(xs.view(B, 4 * D, L), dts.view(B, 4 * D, L), A_neg, Bs, Cs, Ds, dt_bias, True,

@@ -248,11 +248,13 @@ def pack_xdt_weights(x_proj_w: torch.Tensor, dt_w: torch.Tensor, dtype: torch.dt
     return xw.contiguous(), dw.contiguous(), Rp
 
 
-def xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N, time_major=False):
-    """time_major: Bs / Cs written as (B, 4, L, N) (for selective_scan_fwd_merge_cl) instead of (B, 4, N, L)."""
+def xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N, time_major=False, dt_bias=None, delta_softplus=False):
+    """time_major: Bs / Cs written as (B, 4, L, N) (for selective_scan_fwd_merge_cl) instead of (B, 4, N, L).
+    dt_bias (4*D,) fp32: dts = [softplus](dt_proj(...) + dt_bias), so that the scan takes delta as is."""
     with _launched("xdt_proj_tc", f"{B}x{D}x{L} R{R} N{N}", 1):
         check(_lib.load().fd_xdt_proj_tc(_p(xs), _p(xw16), _p(dw16), _p(dts), _f32(Bs), _f32(Cs), B, D, L, R, N, Rp,
-                                         int(bool(time_major)), dtype_code(xs.dtype), _stream()), "fd_xdt_proj_tc")
+                                         int(bool(time_major)), _f32(dt_bias), int(bool(delta_softplus)), dtype_code(xs.dtype),
+                                         _stream()), "fd_xdt_proj_tc")
 
 
 def x_proj_tc(xs, xw16, x_dbl, B, D, L, R, N):

@@ -163,8 +163,12 @@ int fd_xdt_proj(const void* xs, const float* x_proj_w, const float* dt_w, void* 
 /* Tensor-core variant (dtype bf16 / fp16): xw16 = x_proj_w in `dtype`, rows zero-padded to a multiple of 16:
  * (4, CCp, D); dw16 = dt_w in `dtype`, columns zero-padded to Rp in {16, 32}: (4, D, Rp).  Same outputs. */
 int fd_xdt_proj_tc(const void* xs, const void* xw16, const void* dw16, void* dts, float* Bs, float* Cs, int B, int D,
-                   int L, int R, int N, int Rp, int bc_layout, int dtype, cudaStream_t stream);
-/* bc_layout: 0 = Bs, Cs as (B,4,N,L); 1 = time-major (B,4,L,N), the layout fd_selective_scan_fwd_merge_cl reads. */
+                   int L, int R, int N, int Rp, int bc_layout, const float* dt_bias, int delta_softplus, int dtype,
+                   cudaStream_t stream);
+/* bc_layout: 0 = Bs, Cs as (B,4,N,L); 1 = time-major (B,4,L,N), the layout fd_selective_scan_fwd_merge_cl reads.
+ * dt_bias != NULL: dts = dt_proj(...) + dt_bias[k*D + d], then softplus if delta_softplus (src/emamba2.py:344-359 applies
+ * both inside selective_scan_fn); the scan is then called with delta_bias = NULL, delta_softplus = 0.  Both options need
+ * D % 32 == 0 and L % 8 == 0 (FD_ERR_UNSUPPORTED otherwise). */
 
 /* x_proj alone on the tensor cores (levels with dt_rank <= 8): x_dbl (B, 4, R+2N, L) fp32 = einsum(xs, x_proj_weight)
  * (src/emamba2.py:334-336).  Rows [0,R) are the low-rank dt input, [R,R+N) B, [R+N,R+2N) C; fd_selective_scan_fwd_merge_xdbl

@@ -629,6 +629,12 @@ def test_channel_per_lane_scan_with_time_major_bc(ops, cfg, dt):
     ops.xdt_proj_tc(xs_d, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N)
     ops.xdt_proj_tc(xs_d, xw16, dw16, Rp, dts_t, Bt, Ct, B, D, L, R, N, time_major=True)
     assert torch.equal(Bt.permute(0, 1, 3, 2), Bs) and torch.equal(Ct.permute(0, 1, 3, 2), Cs) and torch.equal(dts, dts_t)
+    # bias + softplus finished by the producer: compare with the fp32 formula on the un-rounded projection
+    dts_sp = torch.empty_like(dts)
+    ops.xdt_proj_tc(xs_d, xw16, dw16, Rp, dts_sp, Bs, Cs, B, D, L, R, N, dt_bias=bias.cuda(), delta_softplus=True)
+    x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, q(Wx, dt))
+    dt_ref = torch.einsum("bkrl,kdr->bkdl", q(x_dbl[:, :, :R], dt), q(Wdt, dt)) + bias.view(1, 4, D, 1)
+    assert rel(dts_sp, F.softplus(dt_ref)) < TOL[dt]
     # oracle scan on exactly the tensors the kernel reads
     y_ref = scan_cpu.selective_scan_fwd(xs.reshape(B, 4 * D, L), dts.float().cpu().reshape(B, 4 * D, L), A, Bs.cpu(), Cs.cpu(), Dp, bias, True)
     y_ref = O.efficient_merge(y_ref.view(B, 4, D, L), H, W).permute(0, 2, 3, 1)
