@@ -368,6 +368,9 @@ extern "C" int fd_gn_stats(const void* y, float* sums, int B, int P, int C, int 
 }
 
 // out = silu(gn(y)) + skip     (elementwise given the statistics)
+// The grid stride is a multiple of C / VEC vectors (launcher), so a thread always lands on the same channel vector: the
+// per-channel affine map (GroupNorm statistics, gamma/beta and the optional scale/shift folded into  t = v * A + Bc) is
+// computed once per thread; the loop body is 4 independent vectors in flight, FMA + SiLU + add per element.
 template <typename T>
 __global__ void __launch_bounds__(256) gn_silu_add_kernel(const T* __restrict__ y, const float* __restrict__ sums,
                                                           const float* __restrict__ gamma,
@@ -376,28 +379,71 @@ __global__ void __launch_bounds__(256) gn_silu_add_kernel(const T* __restrict__ 
                                                           int ss_stride, const T* __restrict__ skip, T* __restrict__ out, int P,
                                                           int C, int G, float eps, long nvec_per_sample) {
     constexpr int VEC = fd_vec<T>::N;
+    constexpr int U = 4;
     const int b = blockIdx.y;
     const int cpg = C / G;
     const float inv_n = 1.f / ((float)cpg * (float)P);
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec_per_sample; i += (long)gridDim.x * blockDim.x) {
-        const int c0 = (int)((i * VEC) % C);
-        const int g = c0 / cpg;
+    const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long stride = (long)gridDim.x * blockDim.x;
+    if (i0 >= nvec_per_sample) return;
+    const int c0 = (int)((i0 * VEC) % C);
+    float ka[VEC], kb[VEC];
+    {
+        const int g = c0 / cpg;                      // a vector never straddles groups (cpg % VEC == 0)
         const float mean = sums[((long)b * G + g) * 2] * inv_n;
         const float var = fmaxf(sums[((long)b * G + g) * 2 + 1] * inv_n - mean * mean, 0.f);
         const float rstd = rsqrtf(var + eps);
-        const long off = (long)b * P * C + i * VEC;
-        float v[VEC], s[VEC];
-        fd_ldv<T, VEC>(y + off, v);
-        if (skip) fd_ldv<T, VEC>(skip + off, s);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            float t = (v[e] - mean) * rstd * __ldg(gamma + c0 + e) + __ldg(beta + c0 + e);
-            if (scale) t = t * (__ldg(scale + (long)b * ss_stride + c0 + e) + 1.f) + __ldg(shift + (long)b * ss_stride + c0 + e);
-            t = fd_silu(t);
-            v[e] = skip ? t + s[e] : t;
+            float a = rstd * __ldg(gamma + c0 + e), c = __ldg(beta + c0 + e) - mean * a;
+            if (scale) {
+                const float sc = __ldg(scale + (long)b * ss_stride + c0 + e) + 1.f;
+                a *= sc;
+                c = fmaf(c, sc, __ldg(shift + (long)b * ss_stride + c0 + e));
+            }
+            ka[e] = a; kb[e] = c;
         }
-        fd_stv<T, VEC>(out + off, v);
     }
+    const T* yb = y + (long)b * P * C;
+    const T* sb = skip ? skip + (long)b * P * C : nullptr;
+    T* ob = out + (long)b * P * C;
+    for (long i = i0; i < nvec_per_sample; i += U * stride) {
+        uint4 rv[U], rs[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long j = i + u * stride;
+            const long jj = j < nvec_per_sample ? j : i;          // clamped (valid) address, result discarded
+            rv[u] = *reinterpret_cast<const uint4*>(yb + jj * VEC);
+            if (sb) rs[u] = *reinterpret_cast<const uint4*>(sb + jj * VEC);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long j = i + u * stride;
+            float v[VEC], sk[VEC];
+            fd_raw_to_f<T>(rv[u], v);
+            if (sb) fd_raw_to_f<T>(rs[u], sk);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const float t = fd_silu(fmaf(v[e], ka[e], kb[e]));
+                v[e] = sb ? t + sk[e] : t;
+            }
+            if (j < nvec_per_sample) *reinterpret_cast<uint4*>(ob + j * VEC) = fd_f_to_raw<T>(v);
+        }
+    }
+}
+
+// grid.x such that the grid stride (grid.x * 256 vectors) is a multiple of the vectors per pixel: every thread then keeps its
+// channel vector for the whole loop.  ~4 vectors per thread per loop trip, a few trips per thread.
+static long gn_grid_x(long nvec, int vec_per_pixel) {
+    long gx = fd_cdiv(nvec, 256L * 8);
+    if (gx > 148L * 32) gx = 148L * 32;
+    if (gx < 1) gx = 1;
+    // 256 * gx % vec_per_pixel == 0  <=>  gx % (vec_per_pixel / gcd(vec_per_pixel, 256)) == 0
+    long a = vec_per_pixel, b2 = 256;
+    while (b2) { const long t = a % b2; a = b2; b2 = t; }
+    const long m = vec_per_pixel / a;
+    gx = (gx + m - 1) / m * m;
+    return gx;
 }
 
 extern "C" int fd_gn_silu_add(const void* y, const float* sums, const float* gamma, const float* beta,
@@ -408,7 +454,8 @@ extern "C" int fd_gn_silu_add(const void* y, const float* sums, const float* gam
         constexpr int VEC = fd_vec<T>::N;
         if ((C / G) % VEC) return FD_ERR_UNSUPPORTED;
         const long nvec = (long)P * C / VEC;
-        dim3 grid((unsigned)min((long)fd_cdiv(nvec, 256), 148L * 16), B);
+        if ((((uintptr_t)y | (uintptr_t)skip | (uintptr_t)out) & 15)) return FD_ERR_UNSUPPORTED;
+        dim3 grid((unsigned)gn_grid_x(nvec, C / VEC), B);
         gn_silu_add_kernel<T><<<grid, 256, 0, stream>>>((const T*)y, sums, gamma, beta, nullptr, nullptr, 0, (const T*)skip,
                                                         (T*)out, P, C, G, eps, nvec);
     });
@@ -427,7 +474,8 @@ extern "C" int fd_gn_scale_shift_silu(const void* y, const float* sums, const fl
         constexpr int VEC = fd_vec<T>::N;
         if ((C / G) % VEC) return FD_ERR_UNSUPPORTED;
         const long nvec = (long)P * C / VEC;
-        dim3 grid((unsigned)min((long)fd_cdiv(nvec, 256), 148L * 16), B);
+        if ((((uintptr_t)y | (uintptr_t)skip | (uintptr_t)out) & 15)) return FD_ERR_UNSUPPORTED;
+        dim3 grid((unsigned)gn_grid_x(nvec, C / VEC), B);
         gn_silu_add_kernel<T><<<grid, 256, 0, stream>>>((const T*)y, sums, gamma, beta, scale, shift, ss_stride, (const T*)skip,
                                                         (T*)out, P, C, G, eps, nvec);
     });
