@@ -175,7 +175,7 @@ def algorithmic(name, detail, es):
             b, d, L = map(int, dims.split("x"))
             r, n = int(r), int(n)
             return b * 4.0 * d * L * es + b * 4.0 * (r + 2 * n) * L * 4, 2.0 * b * 4 * L * d * (r + 2 * n)
-        if name == "init_conv7x7":
+        if name in ("init_conv7x7", "init_conv7x7_tc"):
             b, h, w = map(int, detail.split("x"))
             return b * h * w * (8.0 + 64 * es), 2.0 * b * h * w * 98 * 64
         if name == "final_conv_update":

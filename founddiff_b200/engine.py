@@ -162,7 +162,11 @@ class UnetEngine:
         self.x_t = torch.zeros(B, H * W, device=dev, dtype=torch.float32)
         self.x_input = torch.zeros(B, H * W, device=dev, dtype=torch.float32)
         R = self.buf("R", B, H * W, d)
-        self.steps.append(lambda: ops.init_conv7x7(self.x_t, self.x_input, self.init_w, self.init_b, R, B, H, W))
+        if R.dtype != torch.float32 and d == 64 and H % 8 == 0 and W % 16 == 0 and self.prefer_tc:
+            self.init_w16 = ops.pack_init_conv_weights(self.init_w)
+            self.steps.append(lambda: ops.init_conv7x7_tc(self.x_t, self.x_input, self.init_w16, self.init_b, R, B, H, W))
+        else:
+            self.steps.append(lambda: ops.init_conv7x7(self.x_t, self.x_input, self.init_w, self.init_b, R, B, H, W))
 
         def conv_plain(key_w, key_b, src, dst, h, w, k, stride=1, upsample=False):
             c = ops.Conv(src, pack_conv(sd[key_w], self.trunk_dtype, dev), dst, B=B, Hin=h, Win=w, KH=k, KW=k, stride=stride,

@@ -216,6 +216,22 @@ def init_conv7x7(x_t, x_input, weight, bias, out, B, H, W):
                                           out.shape[-1], dtype_code(out.dtype), _stream()), "fd_init_conv7x7")
 
 
+def pack_init_conv_weights(weight: torch.Tensor) -> torch.Tensor:
+    """(64, 2, 7, 7) fp32 -> (64, 256) fp16 for fd_init_conv7x7_tc: the 98 taps twice (hi and lo image parts), zero padded."""
+    co = weight.shape[0]
+    w = weight.detach().reshape(co, 98).to(torch.float16)
+    out = torch.zeros(co, 256, device=weight.device, dtype=torch.float16)
+    out[:, :98] = w
+    out[:, 128:226] = w
+    return out.contiguous()
+
+
+def init_conv7x7_tc(x_t, x_input, w16, bias, out, B, H, W):
+    with _launched("init_conv7x7_tc", f"{B}x{H}x{W}", 1):
+        check(_lib.load().fd_init_conv7x7_tc(_f32(x_t), _f32(x_input), _p(w16), _f32(bias), _p(out), B, H, W, out.shape[-1],
+                                             dtype_code(out.dtype), _stream()), "fd_init_conv7x7_tc")
+
+
 def ln_modulate(x, out, gamma, beta, shift, scale, mod_stride, B, P, C, eps):
     with _launched("ln_modulate", f"{B}x{P}x{C}", 1):
         check(_lib.load().fd_ln_modulate_io(_p(x), _p(out), _f32(gamma), _f32(beta), _f32(shift), _f32(scale), mod_stride,

@@ -644,3 +644,24 @@ def test_channel_per_lane_scan_with_time_major_bc(ops, cfg, dt):
     y2 = torch.empty_like(y)
     ops.selective_scan_fwd_merge(xs_d.view(B, 4 * D, L), dts.view(B, 4 * D, L), A.cuda(), Bs, Cs, Dp.cuda(), bias.cuda(), True, y2, H, W)
     assert rel(y, y2) < TOL[dt]
+
+
+@pytest.mark.parametrize("hw", [(16, 32), (64, 48), (8, 16)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_init_conv7x7_tensor_core(ops, hw, dt):
+    """init_conv on the tensor cores (fp32 images split into fp16 hi + lo, fp16 weights) == F.conv2d in fp32 up to the
+    weight rounding and the output storage type (src/DADiff.py:558, 700)."""
+    H, W = hw
+    B = 2
+    g = torch.Generator().manual_seed(H + W)
+    x_t, x_in = torch.randn(B, H * W, generator=g) * 1.5, torch.rand(B, H * W, generator=g) * 2 - 1
+    w = torch.randn(64, 2, 7, 7, generator=g) / math.sqrt(98)
+    bias = torch.randn(64, generator=g)
+    ref = F.conv2d(torch.stack([x_t.view(B, H, W), x_in.view(B, H, W)], dim=1), w.half().float(), bias, padding=3)
+    out = torch.empty(B, H * W, 64, device="cuda", dtype=dt)
+    ops.init_conv7x7_tc(x_t.cuda(), x_in.cuda(), ops.pack_init_conv_weights(w.cuda()), bias.cuda(), out, B, H, W)
+    got = out.float().cpu().view(B, H, W, 64).permute(0, 3, 1, 2)
+    assert rel(got, ref) < (3e-3 if dt == torch.bfloat16 else 4e-4), rel(got, ref)
+    # the hi/lo split keeps the inputs exact: against fp32 weights only the fp16 weight rounding (2^-12) remains
+    ref32 = F.conv2d(torch.stack([x_t.view(B, H, W), x_in.view(B, H, W)], dim=1), w, bias, padding=3)
+    assert rel(got, ref32) < (3e-3 if dt == torch.bfloat16 else 6e-4)
