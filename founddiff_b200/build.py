@@ -34,10 +34,24 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library in-tree.  Safe under concurrent callers (one process per GPU all importing the package): the
+    build runs under an exclusive file lock, late arrivals find an up-to-date library, and the .so appears atomically."""
     if not force and not needs_build():
         return LIB
+    import fcntl
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():        # another process built it while we waited
+                return LIB
+            return _build_locked(force, verbose, objdir)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool, objdir: str) -> str:
     objs = []
     procs = []
     for src in sources():
@@ -57,7 +71,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB, *objs])
+    tmp = LIB + f".tmp{os.getpid()}"
+    subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", tmp, *objs])
+    os.replace(tmp, LIB)
     return LIB
 
 
