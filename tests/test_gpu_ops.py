@@ -665,3 +665,53 @@ def test_init_conv7x7_tensor_core(ops, hw, dt):
     # the hi/lo split keeps the inputs exact: against fp32 weights only the fp16 weight rounding (2^-12) remains
     ref32 = F.conv2d(torch.stack([x_t.view(B, H, W), x_in.view(B, H, W)], dim=1), w, bias, padding=3)
     assert rel(got, ref32) < (3e-3 if dt == torch.bfloat16 else 6e-4)
+
+
+@pytest.mark.parametrize("types", [(torch.bfloat16, torch.float16), (torch.float16, torch.bfloat16)])
+def test_conv2d_mixed_operand_and_output_types(ops, types):
+    """fd_conv_params.ab_dtype_p1: operands (src / weight) in one 16-bit type, output + addend in the other, plus relu_out —
+    tcgen05 path against the CUDA-core path and against F.conv2d (the bf16 sampling mode's fp16 residual stream and the
+    DA-CLIP blocks use exactly this)."""
+    ab, od = types
+    B, C, H, W, cout = 2, 128, 16, 32, 64
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, H * W, C, generator=g).to("cuda", ab)
+    w = (torch.randn(cout, 3, 3, C, generator=g) / math.sqrt(9 * C)).to("cuda", ab)
+    bias = torch.randn(cout, generator=g).cuda()
+    add = torch.randn(B, H * W, cout, generator=g).to("cuda", od)
+    ref = F.conv2d(x.float().cpu().view(B, H, W, C).permute(0, 3, 1, 2), w.float().cpu().permute(0, 3, 1, 2), bias.cpu(), padding=1)
+    ref = F.relu(ref + add.float().cpu().view(B, H, W, cout).permute(0, 3, 1, 2))
+    res = []
+    for tc in (False, True):
+        out = torch.zeros(B, H * W, cout, device="cuda", dtype=od)
+        conv = ops.Conv(x, w, out, B=B, Hin=H, Win=W, KH=3, KW=3, pad=1, bias=bias, addend=add, relu_out=True, prefer_tc=tc)
+        assert conv.uses_tc == tc
+        conv.run()
+        res.append(out.float().cpu().view(B, H, W, cout).permute(0, 3, 1, 2))
+    tol = 1e-2 if od == torch.bfloat16 else 2e-3
+    assert rel(res[0], ref) < tol and rel(res[1], ref) < tol and rel(res[1], res[0]) < tol
+
+
+def test_ln_modulate_separate_in_out_types(ops):
+    B, P, C = 2, 96, 128
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, P, C, generator=g) * 3 + 1
+    mods = torch.randn(B, 2 * C, generator=g)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    xh = x.to(torch.float16)
+    ref = F.layer_norm(xh.float(), (C,), gamma, beta, eps=1e-5) * (1 + mods[:, None, C:]) + mods[:, None, :C]
+    out = torch.empty(B, P, C, device="cuda", dtype=torch.bfloat16)
+    from founddiff_b200.engine import _view_ptr
+    md = mods.cuda()
+    ops.ln_modulate(xh.cuda(), out, gamma.cuda(), beta.cuda(), _view_ptr(md[:, :C]), _view_ptr(md[:, C:]), 2 * C, B, P, C, 1e-5)
+    assert rel(out, ref) < TOL[torch.bfloat16]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_avgpool2x2_nhwc(ops, dt):
+    B, H, W, C = 2, 12, 20, 64
+    x = q(torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(4)), dt)
+    out = torch.empty(B, (H // 2) * (W // 2), C, device="cuda", dtype=dt)
+    ops.avgpool2x2_nhwc(x.reshape(B, H * W, C).to("cuda", dt), out, B, H, W, C)
+    ref = F.avg_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).reshape(B, -1, C)
+    assert rel(out, ref) < TOL[dt]
