@@ -222,10 +222,11 @@ template <typename T> FD_DEVINL void load16(const T* src, float (&v)[16]) {
         v[2 * i + 1] = f.y;
     }
 }
-FD_DEVINL float fast_silu(float x) {      // 5 instructions: FMUL, MUFU.EX2 (ftz: no denormal rescaling), FADD, MUFU.RCP, FMUL
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-    return __fdividef(x, 1.f + e);
+FD_DEVINL float fast_silu(float x) {      // x * sigmoid(x) = 0.5 x (1 + tanh(x / 2)): ONE MUFU op (tanh.approx, 2^-11 relative)
+    float t;                               // instead of EX2 + RCP; the result is stored in a 16-bit type (2^-9 / 2^-12) anyway
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
 }
 
 // Persistent, warp-specialised kernel.  Roles: warp 0 = TMA producer, warp 1 = MMA issuer (owns TMEM), warps 2..17 =
@@ -262,6 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fd_conv_params& p = q.p;
     const int total_tiles = q.total_tiles;
+    const uint32_t tmem_cols = 2 * BN <= 128 ? 128u : 2 * BN <= 256 ? 256u : 512u;       // two accumulators, power-of-two allocation
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -272,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     if (threadIdx.x < 16) s_gn[threadIdx.x] = 0.f;
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -549,7 +551,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols));
     }
 }
 
@@ -654,7 +656,9 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     q.taps_w = p->upsample ? 2 : p->KW;
     q.kblocks0 = p->c0 / BK;
     q.kblocks1 = p->c1 / BK;
-    q.BN = (p->Cout % 256 == 0) ? 256 : (p->Cout % 128 == 0 ? 128 : 64);
+    // N tile: 256 / 192 / 128 / 64 (tcgen05 accepts any multiple of 16 up to 256 at M = 128); 192 serves the qkv projections
+    // (Cout = 3C = 192, 384) in one or two tiles instead of three
+    q.BN = (p->Cout % 256 == 0) ? 256 : (p->Cout % 192 == 0 && !getenv("FD_CONV_NO_BN192")) ? 192 : (p->Cout % 128 == 0 ? 128 : 64);
     q.n_tiles = p->Cout / q.BN;
     const int ab_dtype = p->ab_dtype_p1 ? p->ab_dtype_p1 - 1 : p->dtype;      // operand storage (both A and B); T = output storage
     q.fmt = ab_dtype == FD_BF16 ? 1 : 0;
