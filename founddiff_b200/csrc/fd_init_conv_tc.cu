@@ -6,14 +6,15 @@
 //     (together ~22 mantissa bits) and both parts are multiplied by the same fp16 weights, K = [hi | pad | lo | pad]
 //     = 4 blocks of 64 (256), accumulated in fp32 in TMEM;
 //   * the A tile is an explicit im2col built by the CTA's threads in shared memory, directly in the canonical K-major
-//     SWIZZLE_128B layout (one warp writes one 128-byte row per instruction: conflict-free), from a 14 x 22 x 2 fp32
-//     patch of the inputs; generic-proxy writes are made visible to the tensor core with fence.proxy.async;
+//     SWIZZLE_128B layout (one warp writes one 128-byte row per instruction: conflict-free), from a 14 x 22 x 2 patch of
+//     the inputs that is split into fp16 hi / lo halves ONCE when it is loaded.  Tap rows are padded to 8 (K index
+//     = ci*56 + ky*8 + kx, zero weight at kx = 7) so that a lane's tap pair (kx, kx+1) is two adjacent patch elements:
+//     with a second copy of the patch shifted by one element every pair is one aligned LDS.32, and the im2col inner loop
+//     is LDS.32 + STS.32 per part.  Generic-proxy writes are made visible to the tensor core with fence.proxy.async;
 //   * weights (64 x 256 fp16 = 32 KB, packed by the host) stay resident in shared memory for the persistent CTA;
 //   * 16 tcgen05.mma (M128 N64 K16) per tile, issued by one thread; the 8 warps then read the accumulator
 //     (tcgen05.ld), add the bias and store 32 bytes per lane.
-// Two CTAs per SM (100 KB of shared memory each) overlap one CTA's im2col with the other's MMA / epilogue.  Measured
-// 0.55 ms per launch at 16 x 512^2 (CUDA-core kernel: 1.25 ms); ncu: the im2col build (~640 of the ~860 instructions per
-// warp and tile) is what is left — a pre-split fp16 patch with 8-tap-padded rows would turn it into LDS.32 + STS.32.
+// Two CTAs per SM (100 KB of shared memory each) overlap one CTA's im2col with the other's MMA / epilogue.
 #include <type_traits>
 
 #include "fd_common.cuh"
@@ -24,7 +25,11 @@ constexpr int IT_TH = 8, IT_TW = 16;                 // output tile (pixels)
 constexpr int IT_PH = IT_TH + 6, IT_PW = IT_TW + 6;  // input patch
 constexpr int IT_N = 64;                             // output channels
 constexpr int IT_KB = 4;                             // K blocks of 64: hi[0:64), hi[64:128), lo[0:64), lo[64:128)
-constexpr int IT_TAPS = 98;
+constexpr int IT_TAPS = 112;                         // 2 channels x 7 rows x 8 (7 taps + 1 zero-weight pad) per part
+constexpr int IT_PS = 24;                            // patch row pitch (halfwords): 12 words, so that the 28 + 4 tap pairs a warp
+constexpr int IT_CH = IT_PH * IT_PS + 24;            // reads per im2col row fall into 32 different banks (channel pitch 180 words)
+constexpr int IT_COPY = 2 * IT_CH;                   // halfwords per patch copy (2 channels)
+constexpr int IT_PF = (2 * IT_PH * IT_PW + 255) / 256;   // patch elements per thread
 
 FD_DEVINL uint32_t it_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 FD_DEVINL uint64_t it_desc(uint32_t saddr) {         // K-major SWIZZLE_128B, SBO = 1024 B (see fd_conv_tc.cu)
@@ -33,12 +38,6 @@ FD_DEVINL uint64_t it_desc(uint32_t saddr) {         // K-major SWIZZLE_128B, SB
 // explicit shared-space accesses: the 1024-byte align-up of the dynamic shared memory base goes through an integer cast,
 // after which the compiler only knows a generic pointer (ST.E / LD.E with 64-bit addresses instead of STS / LDS)
 FD_DEVINL void it_sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-FD_DEVINL void it_stsf(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
-FD_DEVINL float it_ldsf(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
-}
 FD_DEVINL uint32_t it_pack_half2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -54,8 +53,8 @@ __global__ void __launch_bounds__(256, 2) init_conv_tc_kernel(const float* __res
     uint8_t* smem = (uint8_t*)(((uintptr_t)it_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sB = smem;                                   // IT_KB x (64 rows x 128 B)
     uint8_t* sA = smem + IT_KB * IT_N * 128;              // IT_KB x (128 rows x 128 B)
-    float* s_patch = (float*)(sA + IT_KB * 128 * 128);    // [2][IT_PH][IT_PW]
-    uint64_t* bar = (uint64_t*)(s_patch + 2 * IT_PH * IT_PW);
+    __half* s_patch = (__half*)(sA + IT_KB * 128 * 128);  // [part: hi, lo][copy: 0, shifted by 1][channel][IT_CH] fp16
+    uint64_t* bar = (uint64_t*)(s_patch + 4 * IT_COPY + 4);
     uint32_t* tmem_slot = (uint32_t*)(bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sA_u = it_smem_u32(sA), sP_u = it_smem_u32(s_patch);
@@ -66,8 +65,9 @@ __global__ void __launch_bounds__(256, 2) init_conv_tc_kernel(const float* __res
         *reinterpret_cast<uint4*>(sB + kb * (IT_N * 128) + n * 128 + ((jj ^ (n & 7)) << 4)) =
             __ldg(reinterpret_cast<const uint4*>(w16) + c);
     }
-    // zero the A tile once: K positions 98..127 of both halves are never written again
+    // zero the A tile and the patch once: K positions 112..127 of both halves and the patch pad slots are never written again
     for (int c = tid; c < IT_KB * 128 * 8; c += 256) *reinterpret_cast<uint4*>(sA + c * 16) = make_uint4(0, 0, 0, 0);
+    for (int c = tid; c < 4 * IT_COPY + 4; c += 256) s_patch[c] = __float2half(0.f);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(it_smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -81,19 +81,15 @@ __global__ void __launch_bounds__(256, 2) init_conv_tc_kernel(const float* __res
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    // per-lane tap offsets inside the patch for the two K blocks of the hi half (the lo half uses the same taps)
-    int off[2][2];
-    bool ok[2][2];
+    // per-lane tap-pair offset (halfwords, even) inside a patch copy for the two K blocks of a part
+    uint32_t off[2];
 #pragma unroll
-    for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int k = kb * 64 + 2 * lane + e;
-            ok[kb][e] = k < IT_TAPS;
-            const int kk = ok[kb][e] ? k : 0;
-            const int ci = kk / 49, r = kk % 49;
-            off[kb][e] = ci * (IT_PH * IT_PW) + (r / 7) * IT_PW + (r % 7);
-        }
+    for (int kb = 0; kb < 2; ++kb) {
+        const int k = kb * 64 + 2 * lane;
+        const int kk = k < IT_TAPS ? k : 0;
+        const int ci = kk / 56, r = kk % 56;
+        off[kb] = (uint32_t)(ci * IT_CH + (r / 8) * IT_PS + (r % 8));
+    }
     // accumulator row of this thread in the epilogue: TMEM lane quarter = warp % 4, 32 columns per warp half
     const int q4 = warp & 3, ch = warp >> 2;
     const int m_epi = q4 * 32 + lane;
@@ -102,33 +98,62 @@ __global__ void __launch_bounds__(256, 2) init_conv_tc_kernel(const float* __res
 #pragma unroll
     for (int j = 0; j < 32; ++j) bv[j] = __ldg(bias + ch * 32 + j);
 
+    // the patch of the NEXT tile is fetched into registers right after this tile's MMAs are issued, so the global-load latency
+    // (three dependent-looking loads per thread were ~2 us of a 5 us tile) hides behind the MMA wait and the epilogue
+    float pv[IT_PF];
+    auto fetch_patch = [&](int tl) {
+        const int fb = tl / tiles_per_img, ft = tl - fb * tiles_per_img;
+        const int fy0 = (ft / tiles_w) * IT_TH, fx0 = (ft % tiles_w) * IT_TW;
+#pragma unroll
+        for (int u = 0; u < IT_PF; ++u) {
+            const int i = tid + u * 256;
+            const int ci = i / (IT_PH * IT_PW), r = i % (IT_PH * IT_PW);
+            const int yy = fy0 - 3 + r / IT_PW, xx = fx0 - 3 + r % IT_PW;
+            const bool ok = i < 2 * IT_PH * IT_PW && yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const float* src = (ci ? x_in : x_t) + ((long)fb * H + (ok ? yy : 0)) * W + (ok ? xx : 0);
+            const float v = __ldg(ci < 2 ? src : x_t);       // unconditional (clamped) load, masked below
+            pv[u] = ok ? v : 0.f;
+        }
+    };
+    if ((int)blockIdx.x < total_tiles) fetch_patch(blockIdx.x);
     uint32_t parity = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_img, t = tile - b * tiles_per_img;
         const int y0 = (t / tiles_w) * IT_TH, x0 = (t % tiles_w) * IT_TW;
-        // 1. input patch (zero padded)
-        for (int i = tid; i < 2 * IT_PH * IT_PW; i += 256) {
+        // 1. input patch (values prefetched during the previous tile), split into fp16 hi / lo, each stored in the plain and
+        //    the shifted copy
+#pragma unroll
+        for (int u = 0; u < IT_PF; ++u) {
+            const int i = tid + u * 256;
+            if (i >= 2 * IT_PH * IT_PW) break;
             const int ci = i / (IT_PH * IT_PW), r = i % (IT_PH * IT_PW);
-            const int yy = y0 - 3 + r / IT_PW, xx = x0 - 3 + r % IT_PW;
-            float v = 0.f;
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg((ci ? x_in : x_t) + ((long)b * H + yy) * W + xx);
-            it_stsf(sP_u + 4u * (uint32_t)i, v);
+            const float v = pv[u];
+            const uint32_t hh = it_pack_half2(v, 0.f) & 0xffffu;
+            const float hf = __half2float(*reinterpret_cast<const __half*>(&hh));
+            const uint32_t ll = it_pack_half2(v - hf, 0.f) & 0xffffu;
+            const int pr = (r / IT_PW) * IT_PS + r % IT_PW;                        // pitched index inside the channel
+            const uint32_t e0 = sP_u + 2u * (uint32_t)(ci * IT_CH + pr);           // copy 0, element pr
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(e0), "h"((unsigned short)hh) : "memory");
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(e0 + 2u * 2u * IT_COPY), "h"((unsigned short)ll) : "memory");
+            if (pr > 0) {                                                           // copy 1 holds element pr at index pr - 1
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(e0 + 2u * IT_COPY - 2u), "h"((unsigned short)hh) : "memory");
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(e0 + 2u * 3u * IT_COPY - 2u), "h"((unsigned short)ll) : "memory");
+            }
         }
         __syncthreads();
-        // 2. im2col: warp w writes rows w, w+8, ...; lane = pair of taps (4 bytes) of the 128-byte row
+        // 2. im2col: warp w writes rows w, w+8, ...; lane = pair of taps (4 bytes) of the 128-byte row.  All taps of a row have
+        //    the parity of its pixel column, which selects the patch copy in which the pair is 4-byte aligned.
 #pragma unroll 4
         for (int m = warp; m < 128; m += 8) {
-            const uint32_t pp = sP_u + 4u * (uint32_t)((m >> 4) * IT_PW + (m & 15));
+            const uint32_t px = (uint32_t)(m & 15), cpy = px & 1u;
+            const uint32_t src = sP_u + 2u * (cpy * IT_COPY + (uint32_t)(m >> 4) * IT_PS + px - cpy);
             const uint32_t row_off = (uint32_t)m * 128u + ((uint32_t)((lane >> 2) ^ (m & 7)) << 4) + ((uint32_t)(lane & 3) << 2);
 #pragma unroll
             for (int kb = 0; kb < 2; ++kb) {
-                if (kb == 1 && lane >= 17) continue;              // taps 98.. of the second block stay zero
-                const float v0 = ok[kb][0] ? it_ldsf(pp + 4u * (uint32_t)off[kb][0]) : 0.f;
-                const float v1 = ok[kb][1] ? it_ldsf(pp + 4u * (uint32_t)off[kb][1]) : 0.f;
-                const uint32_t hi = it_pack_half2(v0, v1);
-                const __half2 hh = *reinterpret_cast<const __half2*>(&hi);
-                const float2 hf = __half22float2(hh);
-                const uint32_t lo = it_pack_half2(v0 - hf.x, v1 - hf.y);
+                if (kb == 1 && lane >= (IT_TAPS - 64) / 2) continue;       // K 112.. of the second block stays zero
+                uint32_t hi, lo;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hi) : "r"(src + 2u * off[kb]));
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lo) : "r"(src + 2u * off[kb] + 2u * 2u * IT_COPY));
                 it_sts32(sA_u + (uint32_t)(kb * (128 * 128)) + row_off, hi);
                 it_sts32(sA_u + (uint32_t)((kb + 2) * (128 * 128)) + row_off, lo);
             }
@@ -161,6 +186,7 @@ __global__ void __launch_bounds__(256, 2) init_conv_tc_kernel(const float* __res
             }
             __syncwarp();
         }
+        if (tile + (int)gridDim.x < total_tiles) fetch_patch(tile + gridDim.x);
         // 4. wait for the accumulator, epilogue
         {
             uint32_t done = 0;
@@ -216,7 +242,7 @@ extern "C" int fd_init_conv7x7_tc(const float* x_t, const float* x_input, const 
     const int tiles_w = W / IT_TW, tiles_per_img = (H / IT_TH) * tiles_w;
     const long total = (long)B * tiles_per_img;
     if (total >= (1L << 31)) return FD_ERR_UNSUPPORTED;
-    const size_t smem = 1024 + (size_t)IT_KB * IT_N * 128 + (size_t)IT_KB * 128 * 128 + 2 * IT_PH * IT_PW * sizeof(float) + 64;
+    const size_t smem = 1024 + (size_t)IT_KB * IT_N * 128 + (size_t)IT_KB * 128 * 128 + (4 * IT_COPY + 4) * sizeof(__half) + 64;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

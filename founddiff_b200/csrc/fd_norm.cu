@@ -424,7 +424,8 @@ __global__ void __launch_bounds__(256) gn_silu_add_kernel(const T* __restrict__ 
             if (sb) fd_raw_to_f<T>(rs[u], sk);
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
-                const float t = fd_silu(fmaf(v[e], ka[e], kb[e]));
+                const float z = fmaf(v[e], ka[e], kb[e]);
+                const float t = sizeof(T) == 2 ? fd_silu16(z) : fd_silu(z);
                 v[e] = sb ? t + sk[e] : t;
             }
             if (j < nvec_per_sample) *reinterpret_cast<uint4*>(ob + j * VEC) = fd_f_to_raw<T>(v);

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128, 3) dwconv_scan_rw_kernel(const T* __restr
             for (int px = 0; px < 2; ++px)
 #pragma unroll
                 for (int e = 0; e < RW_V; ++e)
-                    fd_st(s_thr + e * RW_CST + px * 2 * RW_KST + off, fd_silu(acc[(S + 2) % 3][px][e]));
+                    fd_st(s_thr + e * RW_CST + px * 2 * RW_KST + off, fd_silu16(acc[(S + 2) % 3][px][e]));
         }
 #pragma unroll
         for (int px = 0; px < 2; ++px)

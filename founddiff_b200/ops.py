@@ -217,12 +217,14 @@ def init_conv7x7(x_t, x_input, weight, bias, out, B, H, W):
 
 
 def pack_init_conv_weights(weight: torch.Tensor) -> torch.Tensor:
-    """(64, 2, 7, 7) fp32 -> (64, 256) fp16 for fd_init_conv7x7_tc: the 98 taps twice (hi and lo image parts), zero padded."""
+    """(64, 2, 7, 7) fp32 -> (64, 256) fp16 for fd_init_conv7x7_tc: K index = ci*56 + ky*8 + kx (tap rows padded to 8 with a
+    zero weight), 112 of 128 used, stored twice (the hi and the lo half of the fp16-split images)."""
     co = weight.shape[0]
-    w = weight.detach().reshape(co, 98).to(torch.float16)
+    w = torch.zeros(co, 2, 7, 8, device=weight.device, dtype=torch.float16)
+    w[..., :7] = weight.detach().to(torch.float16)
     out = torch.zeros(co, 256, device=weight.device, dtype=torch.float16)
-    out[:, :98] = w
-    out[:, 128:226] = w
+    out[:, :112] = w.reshape(co, 112)
+    out[:, 128:240] = w.reshape(co, 112)
     return out.contiguous()
 
 

@@ -131,8 +131,9 @@ int fd_init_conv7x7(const float* x_t, const float* x_input, const float* weight,
                     int B, int H, int W, int Cout, int dtype, cudaStream_t stream);
 
 /* Tensor-core form of the same op (16-bit output types, Cout == 64, H % 8 == 0, W % 16 == 0).  The fp32 images are split
- * into fp16 hi + lo parts inside the kernel (no input rounding); w16: host-packed (64, 256) fp16 =
- * [weight.reshape(64, 98) | 0 (30) | the same 98 again | 0 (30)] (ops.pack_init_conv_weights). */
+ * into fp16 hi + lo parts inside the kernel (no input rounding); w16: host-packed (64, 256) fp16, K index
+ * ci*56 + ky*8 + kx with a zero weight at kx = 7 (112 of 128 used), the block stored twice for the hi and lo parts
+ * (ops.pack_init_conv_weights). */
 int fd_init_conv7x7_tc(const float* x_t, const float* x_input, const void* w16, const float* bias, void* out, int B, int H,
                        int W, int Cout, int dtype, cudaStream_t stream);
 

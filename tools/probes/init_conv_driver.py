@@ -12,3 +12,10 @@ w16 = ops.pack_init_conv_weights(w)
 for _ in range(3):
     ops.init_conv7x7_tc(x_t, x_in, w16, bias, out, B, H, W)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+e0.record()
+for _ in range(20):
+    ops.init_conv7x7_tc(x_t, x_in, w16, bias, out, B, H, W)
+e1.record()
+torch.cuda.synchronize()
+print("init_conv7x7_tc us per launch:", e0.elapsed_time(e1) / 20 * 1e3)
