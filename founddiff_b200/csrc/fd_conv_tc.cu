@@ -222,6 +222,22 @@ template <typename T> FD_DEVINL void load16(const T* src, float (&v)[16]) {
         v[2 * i + 1] = f.y;
     }
 }
+// raw 32-byte addend vector: requested early (before the accumulator is waited for), unpacked when it is added
+FD_DEVINL void load16_raw(const void* src, uint32_t (&w)[8]) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(src));
+}
+template <typename T> FD_DEVINL void add16_raw(const uint32_t (&w)[8], float (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float2 f;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        else f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] += f.x;
+        v[2 * i + 1] += f.y;
+    }
+}
 FD_DEVINL float fast_silu(float x) {      // x * sigmoid(x) = 0.5 x (1 + tanh(x / 2)): ONE MUFU op (tanh.approx, 2^-11 relative)
     float t;                               // instead of EX2 + RCP; the result is stored in a 16-bit type (2^-9 / 2^-12) anyway
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
@@ -478,6 +494,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 cur_n0 = n0;
             }
             const int buf = it & 1;
+            // residual addend of this thread's first chunk: in flight while the accumulator is still being produced; the next
+            // chunk's vector is requested while the current one is processed (the load latency was exposed once per chunk)
+            uint32_t araw[8];
+            const bool use_add = addend != nullptr && row_ok;
+            if (use_add) load16_raw(addend + orow + n0 + cg * 16, araw);
             mbar_wait_long(&tfull_bar[buf], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q4 * 32) << 16);
@@ -529,11 +550,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                             v[j] *= gv.x; v[j + 1] *= gv.y; v[j + 2] *= gv.z; v[j + 3] *= gv.w;
                         }
                     }
-                    if (addend) {
-                        float a[16];
-                        load16<T>(addend + orow + n, a);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += a[j];
+                    if (use_add) {
+                        add16_raw<T>(araw, v);
+                        if (cc + 16 < cols_per_warp) load16_raw(addend + orow + n0 + ((ci + 1) * 4 + cg) * 16, araw);
                     }
                     if (p.relu_out) {
 #pragma unroll
