@@ -75,6 +75,13 @@ def main():
             y = torch.empty_like(u)
             ms = timeit(lambda: ops.selective_scan_fwd(u, delta, A, Bm, Cm, D, bias, True, out=y), args.iters)
             report("selective_scan", f"{B}x{KD}x{L} N{N}", ms, 3.0 * B * KD * L * es + 2.0 * B * 4 * N * L * 4, 9.0 * B * KD * L * N)
+            if dt != torch.float32 and N >= 16 and B * KD >= 16384:      # deep levels: channel-per-lane kernel (+ fused merge)
+                H2 = int(round(math.sqrt(L)))
+                Bt, Ct = Bm.permute(0, 1, 3, 2).contiguous(), Cm.permute(0, 1, 3, 2).contiguous()
+                yn = torch.empty(B, 4 * L, KD // 4, device="cuda", dtype=dt)
+                ms = timeit(lambda: ops.selective_scan_fwd_merge_cl(u, delta, A, Bt, Ct, D, bias, True, yn, 2 * H2, 2 * H2), args.iters)
+                report("selective_scan_cl", f"{B}x{KD}x{L} N{N}", ms, 3.0 * B * KD * L * es + 2.0 * B * 4 * N * L * 4, 9.0 * B * KD * L * N)
+                del Bt, Ct, yn
             del u, delta, Bm, Cm, y
     if args.only in ("", "attn"):
         for C, H, _N in sel(LEVELS):
@@ -102,8 +109,14 @@ def main():
             Wx, Wd = rn(4, R + 2 * N, D, d=torch.float32), rn(4, D, R, d=torch.float32)
             dts = torch.empty_like(xs)
             Bs, Cs = torch.empty(B, 4, N, L, device="cuda"), torch.empty(B, 4, N, L, device="cuda")
-            ms = timeit(lambda: ops.xdt_proj(xs, Wx, Wd, dts, Bs, Cs, B, D, L, R, N), args.iters)
-            report("xdt_proj", f"{B}x{D}x{L} R{R} N{N}", ms, 2.0 * B * 4 * D * L * es + 2.0 * B * 4 * N * L * 4, 2.0 * B * 4 * L * D * (2 * R + 2 * N))
+            if dt == torch.float32:
+                ms = timeit(lambda: ops.xdt_proj(xs, Wx, Wd, dts, Bs, Cs, B, D, L, R, N), args.iters)
+                name = "xdt_proj"
+            else:           # the 16-bit path: tensor-core x_proj + dt_proj, cp.async ring
+                xw16, dw16, Rp = ops.pack_xdt_weights(Wx, Wd, dt)
+                ms = timeit(lambda: ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N), args.iters)
+                name = "xdt_proj_tc"
+            report(name, f"{B}x{D}x{L} R{R} N{N}", ms, 2.0 * B * 4 * D * L * es + 2.0 * B * 4 * N * L * 4, 2.0 * B * 4 * L * D * (2 * R + 2 * N))
             del xs, dts, Bs, Cs
     if args.only in ("", "ss2d"):
         for C, H, N in LEVELS[:3]:
