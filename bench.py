@@ -375,8 +375,8 @@ def run_b200(args):
                                    f"{'DDIM-' + str(S) if S < 1000 else 'ancestral-1000'}, random-init weights (seed 10, adaLN de-zeroed)",
                        "slices_per_gpu": B, "global_batch": n_global, "sampling_timesteps": S, "parallelism": f"dp{ws} (independent chains, 1 all_gather)",
                        "l2": "per-step activations (GBs) >> 126 MB L2; no explicit flush needed", "cuda_graph": True,
-                       "storage": ("bf16 block-internal tensors and projections; fp16 residual stream, pre-GroupNorm conv outputs and the "
-                                   "convolutions reading them; fp32 accumulation, sampler state and conditioning") if args.dtype == "bf16"
+                       "storage": ("bf16 block-internal tensors and projections; fp16 residual stream, pre-GroupNorm conv outputs, LayerNorm outputs and "
+                                   "the convolutions reading them; fp32 accumulation, sampler state and conditioning") if args.dtype == "bf16"
                                   else f"{args.dtype} storage, fp32 accumulation"},
             "per_slice_step_us": per_slice_step_us,
             "step_roofline": {"t_roof_us": T_ROOF_US, "frac": T_ROOF_US / per_slice_step_us,

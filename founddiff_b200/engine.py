@@ -27,7 +27,7 @@ from .weights import UnetConfig
 
 GN_GROUPS = 8
 # arena names that hold the residual / skip stream or feed GroupNorm (UnetEngine.trunk_dtype); everything else is `dtype`
-TRUNK_BUFFERS = ("R", "TA", "TB", "H", "SK", "Y")
+TRUNK_BUFFERS = ("R", "TA", "TB", "H", "SK", "Y", "A")        # "A": the adaLN-modulated LayerNorm output (normalisation-bounded)
 BASE_MID_STATE = 32            # int(base_d_state * 2 ** 3), src/DADiff.py:649
 
 
@@ -279,7 +279,8 @@ class UnetEngine:
         v = self.buf(f"V{l}", B, P, C)
         weff = self.buf(f"WEFF{l}", B, C, C)
         to_dt = lambda t: t.detach().to(device=dev, dtype=dt).contiguous()  # noqa: E731
-        in_w = to_dt(sd[p + ".mamba.in_proj.weight"])                                                  # (4C, C)
+        to_tdt = lambda t: t.detach().to(device=dev, dtype=self.trunk_dtype).contiguous()  # noqa: E731  (operands of convs reading `a`)
+        in_w = to_tdt(sd[p + ".mamba.in_proj.weight"])                                                 # (4C, C)
         out_w = to_dt(sd[p + ".mamba.out_proj.weight"])                                                # (C, 2C)
         dw_w, dw_b = f32(p + ".mamba.conv2d.weight").reshape(D, 9).contiguous(), f32(p + ".mamba.conv2d.bias")
         xp_w, dtp_w = f32(p + ".mamba.x_proj_weight"), f32(p + ".mamba.dt_projs_weight")
@@ -290,7 +291,7 @@ class UnetEngine:
         A_neg = (-torch.exp(f32(p + ".mamba.A_logs"))).contiguous()                                   # emamba2.py:344
         Ds = f32(p + ".mamba.Ds")
         on_w, on_b = f32(p + ".mamba.out_norm.weight"), f32(p + ".mamba.out_norm.bias")
-        qkv_w = to_dt(sd[p + ".attn_blk.qkv.weight"].reshape(3 * C, C))
+        qkv_w = to_tdt(sd[p + ".attn_blk.qkv.weight"].reshape(3 * C, C))
         qdw_w = f32(p + ".attn_blk.qkv_dwconv.weight").reshape(3 * C, 9).contiguous()
         qdw_wt = qdw_w.t().contiguous()                      # tap-major copy for the streaming dwconv kernel
         proj_w = f32(p + ".attn_blk.project_out.weight").reshape(C, C).contiguous()
