@@ -158,7 +158,7 @@ def p_sample_loop(sd, init: Tensor, step_noise: Callable[[int], Tensor], timeste
         x0 = _x0(sch, img, t, eps, True)
         mean = sch["posterior_mean_coef1"][t] * x0 + sch["posterior_mean_coef2"][t] * img
         if trace is not None:
-            trace.append(dict(t=t, pred_noise=eps.clone(), x_start=x0.clone()))
+            trace.append(dict(t=t, x_t=img.clone(), pred_noise=eps.clone(), x_start=x0.clone()))
         img = mean + ((0.5 * sch["posterior_log_variance_clipped"][t]).exp() * step_noise(t) if t > 0 else 0.)
     return (img + 1) * 0.5
 
@@ -179,7 +179,7 @@ def ddim_sample(sd, init: Tensor, sampling_timesteps: int, step_noise: Optional[
         eps = unet_forward(sd, img, torch.full((B,), t, dtype=torch.long))
         x0 = _x0(sch, img, t, eps, True)
         if trace is not None:
-            trace.append(dict(t=t, pred_noise=eps.clone(), x_start=x0.clone()))
+            trace.append(dict(t=t, x_t=img.clone(), pred_noise=eps.clone(), x_start=x0.clone()))
         if tn < 0:
             img = x0
             continue
