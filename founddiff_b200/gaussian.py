@@ -391,6 +391,10 @@ class GaussianDiffusion(nn.Module):
         for k, v in make_schedule(timesteps, beta_schedule).items():
             self.register_buffer(k, v)
         self._host = {k: v.double().tolist() for k, v in make_schedule(timesteps, beta_schedule).items()}
+        # optional: one CUDA graph per timestep (as the primary path does).  Off by default: linear attention still allocates
+        # its temporaries per call, and with those inside the capture the replay measured slower than eager launches
+        self.use_cuda_graph = False
+        self._graphs: Dict = {}
 
     def _plan(self):
         """[(t, coef[8])] for fd_ddpm_update: {sr, srm1, a0 (x0), a1 (x_t), a2 (eps), a3 (noise), clip, 0}."""
@@ -427,22 +431,51 @@ class GaussianDiffusion(nn.Module):
         nhwc = lambda t: t.to(dev, torch.float32).permute(0, 2, 3, 1).reshape(B, S * S, C)  # noqa: E731
         init = noise["init"] if noise is not None else torch.randn(B, C, S, S, device=dev)
         eng.x_t.copy_(nhwc(init))
-        coef = torch.zeros(8, device=dev)
-        nz = torch.zeros(B, S * S, C, device=dev)
-        x0 = torch.zeros(B, S * S, C, device=dev) if trace is not None else None
-        for t, c in self._plan():
-            eng.time.fill_(float(t))
+        bufs = eng.__dict__.setdefault("_sampler_bufs", {})
+        if "coef" not in bufs:
+            bufs.update(coef=torch.zeros(8, device=dev), nz=torch.zeros(B, S * S, C, device=dev), x0=torch.zeros(B, S * S, C, device=dev))
+        coef, nz, x0 = bufs["coef"], bufs["nz"], bufs["x0"]
+        plan = self._plan()
+        coef_host = torch.tensor([c for _, c in plan], dtype=torch.float32).pin_memory()
+        time_host = torch.tensor([[float(t)] * B for t, _ in plan], dtype=torch.float32).pin_memory()
+
+        def one_step():                                   # Unet + fused x0 / clip / posterior-or-DDIM update (+ noise)
             eng.forward()
-            coef.copy_(torch.tensor(c, dtype=torch.float32))
-            use_noise = c[5] != 0.
-            if use_noise:
+            ops.ddpm_update(eng.x_t, eng.eps, nz, coef, eng.x_t, x0)
+        step_fn = self._graphed(eng, one_step) if self.use_cuda_graph else one_step
+        for i, (t, c) in enumerate(plan):
+            coef.copy_(coef_host[i], non_blocking=True)
+            eng.time.copy_(time_host[i], non_blocking=True)
+            if c[5] != 0.:
                 nz.copy_(nhwc(noise["steps"](t)) if noise is not None else nhwc(torch.randn(B, C, S, S, device=dev)))
-            ops.ddpm_update(eng.x_t, eng.eps, nz if use_noise else None, coef, eng.x_t, x0)
+            step_fn()
             if trace is not None:
                 to_nchw = lambda v: v.view(B, S, S, C).permute(0, 3, 1, 2).clone()  # noqa: E731
                 trace.append(dict(t=t, pred_noise=to_nchw(eng.eps), x_start=to_nchw(x0)))
         img = (eng.x_t.view(B, S, S, C).permute(0, 3, 1, 2) + 1) * 0.5
         return [img.contiguous()]
+
+    def _graphed(self, eng, fn):
+        """One timestep as a CUDA graph (captured once per engine; time / coefficients / noise live in device buffers)."""
+        key = id(eng)
+        if self._graphs and next(iter(self._graphs)) != key:
+            self._graphs.clear()
+        g = self._graphs.get(key)
+        if g is None:
+            saved = eng.x_t.clone()
+            side = torch.cuda.Stream(device=eng.device)
+            side.wait_stream(torch.cuda.current_stream(eng.device))
+            with torch.cuda.stream(side):
+                fn()                                      # warm-up outside capture
+            torch.cuda.current_stream(eng.device).wait_stream(side)
+            torch.cuda.synchronize(eng.device)
+            eng.x_t.copy_(saved)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            eng.x_t.copy_(saved)
+            self._graphs[key] = g
+        return g.replay
 
     def p_sample_loop(self, shape, **kw):
         assert not self.is_ddim_sampling

@@ -103,12 +103,18 @@ def test_ancestral_sampling_vs_reference(gmodel):
     assert rel(out, a["out"]) < 0.15
 
 
-def test_default_noise_and_shapes(gmodel):
+def test_default_noise_shapes_and_graph_mode(gmodel):
     from founddiff_b200.gaussian import GaussianDiffusion
     gmodel.compute_dtype = torch.float16
     d = GaussianDiffusion(gmodel, image_size=64, timesteps=1000, sampling_timesteps=2, loss_type='l1').cuda()
     out = d.sample(batch_size=3)
     assert isinstance(out, list) and out[0].shape == (3, 3, 64, 64) and torch.isfinite(out[0]).all()
+    init = torch.randn(3, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    eager = d.sample(batch_size=3, noise={"init": init})[0]
+    d.use_cuda_graph = True
+    graphed = d.sample(batch_size=3, noise={"init": init})[0]
+    graphed2 = d.sample(batch_size=3, noise={"init": init})[0]
+    assert rel(graphed, eager.float().cpu()) < 0.15 and rel(graphed2, graphed.float().cpu()) < 0.15
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
