@@ -128,6 +128,9 @@ class UnetRes(nn.Module):
         return OrderedDict((k, v.detach()) for k, v in self.unet0.state_dict().items())
 
     def engine(self, B, H, W, device) -> UnetEngine:
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())       # 'cuda' and 'cuda:0' are one engine
         trunk = self.trunk_dtype
         if trunk is None:
             trunk = torch.float16 if self.compute_dtype == torch.bfloat16 else self.compute_dtype

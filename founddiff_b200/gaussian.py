@@ -115,6 +115,9 @@ class Unet(nn.Module):
         return res
 
     def engine(self, B, H, W, device):
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())       # 'cuda' and 'cuda:0' are one engine
         key = (B, H, W, self.compute_dtype, str(device))
         eng = self._engines.get(key)
         if eng is None:
@@ -249,9 +252,11 @@ class GaussianUnetEngine:
         bout = self.f32(p + ".fn.fn.to_out.0.bias")
         g = self.f32(p + ".fn.fn.to_out.1.g").reshape(-1).contiguous()
 
+        la = ops.LinearAttention(qkv, wout, bout, g, tmp, B, h, w, HEADS, C, prefer_tc=self.prefer_tc)
+
         def run():
             cq.run()
-            ops.linear_attention(qkv, wout, bout, g, tmp, B, h, w, HEADS, C, prefer_tc=self.prefer_tc)
+            la.run()
             x.add_(tmp)                                   # the Residual wrapper (:95-101)
         self.steps.append(run)
 
@@ -391,9 +396,7 @@ class GaussianDiffusion(nn.Module):
         for k, v in make_schedule(timesteps, beta_schedule).items():
             self.register_buffer(k, v)
         self._host = {k: v.double().tolist() for k, v in make_schedule(timesteps, beta_schedule).items()}
-        # optional: one CUDA graph per timestep (as the primary path does).  Off by default: linear attention still allocates
-        # its temporaries per call, and with those inside the capture the replay measured slower than eager launches
-        self.use_cuda_graph = False
+        self.use_cuda_graph = True                        # one CUDA graph per timestep, as the primary path
         self._graphs: Dict = {}
 
     def _plan(self):

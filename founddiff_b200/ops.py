@@ -282,6 +282,44 @@ def x_proj_tc(xs, xw16, x_dbl, B, D, L, R, N):
         check(_lib.load().fd_x_proj_tc(_p(xs), _p(xw16), _f32(x_dbl), B, D, L, R, N, dtype_code(xs.dtype), _stream()), "fd_x_proj_tc")
 
 
+class LinearAttention:
+    """lucidrains LinearAttention between to_qkv and the end of to_out (src/denoising_diffusion_pytorch.py:238-255) as a
+    call site with pre-allocated workspace and a persistent per-sample GEMM plan (graph-capturable, no allocation per call):
+    qkv (B, H*W, 3*heads*32) -> out (B, H*W, dim) = LayerNorm_c(Conv1x1(linear-attention(q, k, v)) + bias) * g."""
+
+    def __init__(self, qkv, wout, bias, g, out, B, H, W, heads, dim, scale=32 ** -0.5, prefer_tc=True):
+        N, HC, dev, dt = H * W, heads * 32, qkv.device, qkv.dtype
+        self.args = (B, N, heads, dim, float(scale), H, W)
+        self.qkv, self.wout, self.bias, self.g, self.out = qkv, wout, bias, g, out
+        self.kmax = torch.empty(B, HC, device=dev)
+        self.ksum = torch.empty(B, HC, device=dev)
+        self.ctx = torch.empty(B, heads, 32, 32, device=dev)
+        self.weff = torch.empty(B, dim, HC, device=dev, dtype=dt)
+        self.qhat = torch.empty(B, N, HC, device=dev, dtype=dt)
+        self.y = torch.empty(B, N, dim, device=dev, dtype=dt)
+        self.zb = torch.zeros_like(g)
+        self.zeros = torch.zeros(B, dim, device=dev)
+        self.conv = Conv(self.qhat, self.weff, self.y, B=B, Hin=H, Win=W, bias=bias, per_batch_weight=True, prefer_tc=prefer_tc)
+
+    def run(self):
+        lib = _lib.load()
+        B, N, heads, dim, scale, H, W = self.args
+        dt = self.qkv.dtype
+        self.kmax.fill_(float("-inf"))
+        self.ksum.zero_()
+        self.ctx.zero_()
+        with _launched("linattn_context", f"{B}x{N}x{heads}", 2):
+            check(lib.fd_linattn_context(_p(self.qkv), _f32(self.kmax), _f32(self.ksum), _f32(self.ctx), B, N, heads, dtype_code(dt),
+                                         _stream()), "fd_linattn_context")
+        with _launched("linattn_weff", f"{B}x{dim}"):
+            check(lib.fd_linattn_weff(_f32(self.ctx), _f32(self.ksum), _f32(self.wout), _p(self.weff), B, N, heads, dim, scale,
+                                      dtype_code(dt), _stream()), "fd_linattn_weff")
+        with _launched("softmax_d32", f"{B}x{N}x{heads}"):
+            check(lib.fd_softmax_d32(_p(self.qkv), _p(self.qhat), B, N, heads, dtype_code(dt), _stream()), "fd_softmax_d32")
+        self.conv.run()
+        ln_modulate(self.y, self.out, self.g, self.zb, self.zeros, self.zeros, dim, B, N, dim, 1e-5)
+
+
 def selective_scan_fwd_merge_cl(u, delta, A, Bt, Ct, D, delta_bias, delta_softplus, y_nhwc, H, W):
     """Channel-per-lane scan + EfficientMerge (deep levels): Bt, Ct time-major (b, 4, L, N) fp32."""
     b, kd, L = u.shape

@@ -16,7 +16,7 @@ diff = GaussianDiffusion(model, image_size=S, timesteps=1000, sampling_timesteps
 for _ in range(2):
     diff.sample(batch_size=B)
 torch.cuda.synchronize()
-eng = model.engine(B, S, S, torch.device("cuda"))
+eng = model.engine(B, S, S, diff.betas.device)
 e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
 n0 = ops.LAUNCHES
 e0.record()
@@ -35,3 +35,23 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 print(f"secondary path DDIM-2 sample(): {ms:.1f} ms per call, {B / ms * 1e3:.1f} images/s; peak memory "
       f"{torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+# breakdown: graph replay alone vs eager step vs full sample() in both modes
+replay = diff._graphs[id(eng)].replay if diff._graphs else None
+if replay is not None:
+    e0.record()
+    for _ in range(5):
+        replay()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"graph replay of one timestep: {e0.elapsed_time(e1) / 5:.2f} ms")
+for mode in (False, True):
+    diff.use_cuda_graph = mode
+    diff.sample(batch_size=B)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    e0.record()
+    for _ in range(3):
+        diff.sample(batch_size=B)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"sample() graph={mode}: {e0.elapsed_time(e1) / 3:.1f} ms (wall {1e3 * (time.time() - t0) / 3:.1f} ms)")
