@@ -205,6 +205,12 @@ class Conv:
             pass
 
 
+def slice_metrics(pred, target, out, B, H, W, max_val=1.0):
+    """out (B, 2) fp32: per-slice sum of squared errors and sum of the SSIM map (see metrics.py for PSNR / SSIM / RMSE)."""
+    with _launched("slice_metrics", f"{B}x{H}x{W}", 1):
+        check(_lib.load().fd_slice_metrics(_f32(pred), _f32(target), _f32(out), B, H, W, float(max_val), _stream()), "fd_slice_metrics")
+
+
 def avgpool2x2_nhwc(x, out, B, H, W, C):
     with _launched("avgpool2x2_nhwc", f"{B}x{H}x{W}x{C}", 1):
         check(_lib.load().fd_avgpool2x2_nhwc(_p(x), _p(out), B, H, W, C, dtype_code(x.dtype), _stream()), "fd_avgpool2x2_nhwc")

@@ -281,6 +281,13 @@ int fd_final_conv_update(const void* feat, const float* w, const float* bias, co
                          const float* x_t, const float* noise, const float* coef, float* x_next, float* pred_res,
                          float* pred_noise, float* x_start, long npix, int C, int dtype, cudaStream_t stream);
 int fd_unnormalize(const float* x, float* out, long n, cudaStream_t stream);
+/* Evaluation metrics of Trainer.test (src/DADiff.py:1883-1888; src/util.py:188-236 compute_psnr / compute_ssim /
+ * compute_rmse) on the device: out[2*b] = sum over the slice of (pred - target)^2, out[2*b + 1] = sum of the SSIM map
+ * (11x11 Gaussian window sigma 1.5, reflect border, C1 = (0.01 max_val)^2, C2 = (0.03 max_val)^2, map clamped to [0, 1]).
+ * pred, target: (B, H, W) fp32.  PSNR = 10 log10(max_val^2 / (sse / HW)), RMSE = sqrt(sse / HW), SSIM = sum / HW. */
+int fd_slice_metrics(const float* pred, const float* target, float* out, int B, int H, int W, float max_val,
+                     cudaStream_t stream);
+
 /* Secondary path: epsilon-prediction GaussianDiffusion update (src/denoising_diffusion_pytorch.py:547-576, 588-595,
  * 612-646), fused: x0 = sr*x_t - srm1*eps (clipped to [-1,1] if coef[6]); x_next = a0*x0 + a1*x_t + a2*eps + a3*noise;
  * coef (DEVICE fp32[8]) = {sr, srm1, a0, a1, a2, a3, clip, 0}. */

@@ -154,3 +154,50 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
              for r in range(2)]
     outs = [p.communicate(timeout=120)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_slice_io_normalise_contract_and_roundtrip(tmp_path):
+    """data/transforms.py:582-587 ((m - 1024 + 1000) / 3000 clipped to [0, 1]) and the np.save writer (src/DADiff.py:1912-1915)."""
+    import numpy as np
+    from founddiff_b200 import io
+    raw = np.array([[24.0, 1024.0, 2524.0], [3024.0, 5000.0, -500.0]], dtype=np.float32)
+    want = np.clip((raw - 1024 + 1000) / 3000, 0, 1)
+    assert np.allclose(io.normalize_hu(raw), want) and io.normalize_hu(raw).dtype == np.float32
+    paths = []
+    rng = np.random.default_rng(0)
+    for i in range(5):
+        p = str(tmp_path / f"ab-quarter-{i}.npy")
+        np.save(p, rng.uniform(0, 4000, size=(16, 24)).astype(np.float32))
+        paths.append(p)
+    batch = io.load_slices(paths[:3])
+    assert batch.shape == (3, 1, 16, 24) and float(batch.min()) >= 0 and float(batch.max()) <= 1
+    got = [(a.shape, b, len(ps)) for a, b, ps in io.SliceStream(paths, None, batch=2, device="cpu")]
+    assert [g[0][0] for g in got] == [2, 2, 1] and all(g[1] is None for g in got)
+    out = [str(tmp_path / "res" / f"{i}.npy") for i in range(3)]
+    io.save_slices(out, batch)
+    back = np.load(out[1])
+    assert back.shape == (16, 24) and np.array_equal(back, batch[1, 0].numpy())
+
+
+def test_reference_checkpoint_ingestion():
+    """Trainer.save layout (src/DADiff.py:1630-1646): {'step', 'model', 'ema', ...}; the EMA weights are the ones sampled with."""
+    import torch
+    from founddiff_b200 import weights
+    from founddiff_b200.diffusion import ResidualDiffusion, UnetRes
+    from founddiff_b200.evaluate import load_reference_checkpoint
+    sd = weights.random_state_dict(seed=3)
+    ema = {"ema_model.model.unet0." + k: v for k, v in sd.items()}
+    ema["ema_model.model.unet0.clip_model.visual.conv1.weight"] = torch.zeros(1)        # dead member, must be ignored
+    ema["initted"] = torch.tensor(True)
+    other = weights.random_state_dict(seed=4)
+    ckpt = {"step": 400, "model": {"model.unet0." + k: v for k, v in other.items()}, "ema": ema}
+    model = UnetRes(dim=64, dim_mults=(1, 2, 4, 8), num_unet=1, condition=True, input_condition=False, objective='pred_res',
+                    test_res_or_noise='res')
+    diff = ResidualDiffusion(model, image_size=64, timesteps=1000, sampling_timesteps=2, objective='pred_res', loss_type='l2',
+                             condition=True, sum_scale=0.01)
+    info = load_reference_checkpoint(diff, ckpt)
+    assert info["step"] == 400 and info["loaded"] == len(sd)
+    got = model.state_dict()
+    assert torch.equal(got["unet0.init_conv.weight"], sd["init_conv.weight"])
+    load_reference_checkpoint(diff, ckpt, prefer_ema=False)
+    assert torch.equal(model.state_dict()["unet0.init_conv.weight"], other["init_conv.weight"])

@@ -263,3 +263,32 @@ def test_daclip_tensor_core_tower_matches_library_path(state_dict):
         e_tc = float((a - c).norm() / c.norm())
         e_lib = float((b - c).norm() / c.norm())
         assert e_tc < 2e-2 and e_tc < 3 * e_lib + 2e-3, (e_tc, e_lib)
+
+
+@pytest.mark.gpu
+def test_evaluate_loop_npy_in_metrics_on_device_npy_out(model, tmp_path):
+    """Batched mirror of Trainer.test (src/DADiff.py:1817-1920): .npy slices in, sample(), device PSNR/SSIM/RMSE, .npy out."""
+    import numpy as np
+    from founddiff_b200.evaluate import evaluate
+    from oracle import metrics_oracle as MO
+    set_mode(model, torch.bfloat16, sampling_timesteps=2)
+    rng = np.random.default_rng(1)
+    ld, nd = [], []
+    for i in range(5):
+        clean = rng.uniform(200, 2800, size=(64, 64)).astype(np.float32)
+        a, b = str(tmp_path / f"ab-quarter-{i}.npy"), str(tmp_path / f"ab-full-{i}.npy")
+        np.save(a, clean + rng.normal(0, 60, size=(64, 64)).astype(np.float32))
+        np.save(b, clean)
+        ld.append(a)
+        nd.append(b)
+    res = evaluate(model, ld, nd, out_dir=str(tmp_path / "out"), batch=2, noise_seed=7)
+    assert len(res["psnr"]) == len(res["ssim"]) == len(res["rmse"]) == 5
+    from founddiff_b200 import io
+    for i in range(5):
+        out = np.load(str(tmp_path / "out" / f"ab-quarter-{i}.npy"))
+        assert out.shape == (64, 64) and out.min() >= 0 and out.max() <= 1
+        y = io.load_slices([nd[i]])
+        p = torch.from_numpy(out)[None, None]
+        assert abs(res["psnr"][i] - float(MO.compute_psnr(p, y))) < 1e-3
+        assert abs(res["ssim"][i] - float(MO.compute_ssim(p, y))) < 5e-5
+        assert abs(res["rmse"][i] - float(MO.compute_rmse(p, y))) < 1e-6

@@ -715,3 +715,24 @@ def test_avgpool2x2_nhwc(ops, dt):
     ops.avgpool2x2_nhwc(x.reshape(B, H * W, C).to("cuda", dt), out, B, H, W, C)
     ref = F.avg_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).reshape(B, -1, C)
     assert rel(out, ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("hw", [(64, 96), (33, 50), (512, 512)])
+def test_device_metrics_match_reference_formulas(ops, hw):
+    """fd_slice_metrics / founddiff_b200.metrics == compute_psnr / compute_ssim / compute_rmse (src/util.py:188-236)."""
+    from founddiff_b200 import metrics
+    from oracle import metrics_oracle as MO
+    H, W = hw
+    g = torch.Generator().manual_seed(H + W)
+    y = torch.rand(3, 1, H, W, generator=g)
+    y = F.avg_pool2d(F.pad(y, (2, 2, 2, 2), mode="reflect"), 5, stride=1)          # low-frequency content, like CT
+    p = (y + 0.05 * torch.randn(3, 1, H, W, generator=g)).clamp(0, 1)
+    yd, pd = y.cuda(), p.cuda()
+    assert abs(float(metrics.compute_psnr(pd, yd)) - float(MO.compute_psnr(p, y))) < 1e-3
+    assert abs(float(metrics.compute_rmse(pd, yd)) - float(MO.compute_rmse(p, y))) < 1e-6
+    assert abs(float(metrics.compute_ssim(pd, yd)) - float(MO.compute_ssim(p, y))) < 2e-5
+    ps, ss, rs = metrics.slice_metrics(pd, yd)
+    for i in range(3):
+        assert abs(float(ps[i]) - float(MO.compute_psnr(p[i:i + 1], y[i:i + 1]))) < 1e-3
+        assert abs(float(ss[i]) - float(MO.compute_ssim(p[i:i + 1], y[i:i + 1]))) < 2e-5
+        assert abs(float(rs[i]) - float(MO.compute_rmse(p[i:i + 1], y[i:i + 1]))) < 1e-6
