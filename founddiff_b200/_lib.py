@@ -17,7 +17,7 @@ EXPORTS = [
     "fd_version", "fd_selective_scan_fwd", "fd_selective_scan_fwd_merge", "fd_selective_scan_fwd_merge_xdbl", "fd_selective_scan_fwd_merge_cl", "fd_x_proj_tc", "fd_avgpool2x2_nhwc", "fd_slice_metrics", "fd_init_conv7x7_tc", "fd_ln_modulate_io", "fd_ln_gate", "fd_conv2d_simt", "fd_conv2d_tc_supported", "fd_conv2d_tc_plan_create",
     "fd_conv2d_tc_run", "fd_conv2d_tc_plan_destroy", "fd_init_conv7x7", "fd_ln_modulate", "fd_dwconv3x3_silu_scan",
     "fd_xdt_proj", "fd_xdt_proj_tc", "fd_merge_ln_gate", "fd_dwconv3x3_qkv_gram", "fd_dwconv3x3_nhwc", "fd_gram_qk", "fd_attn_weff", "fd_gn_stats", "fd_gn_silu_add", "fd_gn_scale_shift_silu", "fd_flash_attn_d32", "fd_linattn_context", "fd_linattn_weff", "fd_softmax_d32",
-    "fd_linear_small", "fd_time_sinusoid", "fd_sampler_init", "fd_final_conv_update", "fd_unnormalize", "fd_ddpm_update",
+    "fd_linear_small", "fd_time_sinusoid", "fd_sampler_init", "fd_final_conv_update", "fd_final_conv_update_obj", "fd_unnormalize", "fd_ddpm_update",
 ]
 
 
@@ -94,6 +94,7 @@ def load():
         "fd_time_sinusoid": [V, V, I, I, V],
         "fd_sampler_init": [V, V, F, V, V, V, L, V],
         "fd_final_conv_update": [V] * 11 + [L, I, I, V],
+        "fd_final_conv_update_obj": [V] * 14 + [L, I, I, I, V],
         "fd_unnormalize": [V, V, L, V],
         "fd_ddpm_update": [V] * 6 + [L, V],
     }

@@ -65,13 +65,22 @@ extern "C" int fd_ddpm_update(const float* x_t, const float* eps, const float* n
 }
 
 // One pixel per LPP lanes; each lane reads one 16-byte vector of the C-channel feature row.
-template <typename T>
+// MODE selects the objective branch of model_predictions (src/DADiff.py:1168-1207); feat1 / w1 / bias1 are the second
+// Unet's final_conv operands (num_unet = 2, src/DADiff.py:817-820) and are only read by the two-output modes.
+//   FD_OBJ_PRED_RES       o0 = pred_res                    (:1202-1207, also 'pred_res_noise' with test_res_or_noise = "res")
+//   FD_OBJ_PRED_NOISE     o0 = pred_noise                  (:1194-1201, also test_res_or_noise = "noise" :1180-1187)
+//   FD_OBJ_PRED_RES_NOISE o0 = pred_res, o1 = pred_noise   (:1169-1175)
+//   FD_OBJ_PRED_X0_NOISE  o0 = x_start,  o1 = pred_noise   (:1188-1192)
+// coef (DEVICE fp32[8]) = {c_xt, c_res, c_x0, c_noise, alphas_cumsum[t], betas_cumsum[t], one_minus_alphas_cumsum[t], 0}
+template <typename T, int MODE>
 __global__ void __launch_bounds__(256) final_conv_update_kernel(
     const T* __restrict__ feat, const float* __restrict__ w, const float* __restrict__ bias,
+    const T* __restrict__ feat1, const float* __restrict__ w1, const float* __restrict__ bias1,
     const float* __restrict__ x_input, const float* __restrict__ x_t, const float* __restrict__ noise,
     const float* __restrict__ coef, float* __restrict__ x_next, float* __restrict__ pred_res,
     float* __restrict__ pred_noise, float* __restrict__ x_start, long npix, int C) {
     constexpr int VEC = fd_vec<T>::N;
+    constexpr bool TWO = (MODE == FD_OBJ_PRED_RES_NOISE || MODE == FD_OBJ_PRED_X0_NOISE);
     const int lpp = C / VEC;  // lanes per pixel (power of two <= 32)
     const int lane = threadIdx.x & 31;
     const int sub = lane % lpp;
@@ -80,42 +89,97 @@ __global__ void __launch_bounds__(256) final_conv_update_kernel(
     const long pix = warp * ppw + lane / lpp;
     const bool active = pix < npix;
     float v[VEC];
-    float acc = 0.f;
+    float acc = 0.f, acc1 = 0.f;
     if (active) {
         fd_ldv<T, VEC>(feat + pix * (long)C + sub * VEC, v);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) acc += v[e] * __ldg(w + sub * VEC + e);
+        if (TWO) {
+            fd_ldv<T, VEC>(feat1 + pix * (long)C + sub * VEC, v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc1 += v[e] * __ldg(w1 + sub * VEC + e);
+        }
     }
-    for (int o = lpp / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int o = lpp / 2; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (TWO) acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+    }
     if (!active || sub != 0) return;
     const float c_xt = coef[0], c_res = coef[1], c_x0 = coef[2], c_noise = coef[3], acs = coef[4], bcs = coef[5];
     const float xi = x_input[pix], xt = x_t[pix];
-    const float pr = fminf(fmaxf(acc + bias[0], -1.f), 1.f);      // :1165-1166, 1204
-    const float x0 = fminf(fmaxf(xi - pr, -1.f), 1.f);            // :1206-1207
+    const float o0 = acc + bias[0];
+    float pr, pn, x0;
+    if (MODE == FD_OBJ_PRED_RES) {
+        pr = fminf(fmaxf(o0, -1.f), 1.f);                         // :1165-1166, 1204
+        x0 = fminf(fmaxf(xi - pr, -1.f), 1.f);                    // :1206-1207
+        pn = (xt - xi - (acs - 1.f) * pr) / bcs;                  // :1120-1124
+    } else if (MODE == FD_OBJ_PRED_NOISE) {
+        pn = o0;
+        x0 = (xt - acs * xi - bcs * pn) / coef[6];                // :1126-1130
+        x0 = fminf(fmaxf(x0, -1.f), 1.f);
+        pr = fminf(fmaxf(xi - x0, -1.f), 1.f);                    // :1199-1200
+    } else if (MODE == FD_OBJ_PRED_RES_NOISE) {
+        pr = fminf(fmaxf(o0, -1.f), 1.f);
+        pn = acc1 + bias1[0];
+        x0 = fminf(fmaxf(xt - acs * pr - bcs * pn, -1.f), 1.f);   // :1132-1136, 1175
+    } else {
+        pr = fminf(fmaxf(xi - o0, -1.f), 1.f);                    // :1189, 1191
+        pn = acc1 + bias1[0];
+        x0 = fminf(fmaxf(o0, -1.f), 1.f);                         // :1192
+    }
     if (pred_res) pred_res[pix] = pr;
     if (x_start) x_start[pix] = x0;
-    if (pred_noise) pred_noise[pix] = (xt - xi - (acs - 1.f) * pr) / bcs;   // :1120-1124
+    if (pred_noise) pred_noise[pix] = pn;
     float xn = c_xt * xt + c_res * pr + c_x0 * x0;
     if (noise) xn += c_noise * noise[pix];
     x_next[pix] = xn;
+}
+
+extern "C" int fd_final_conv_update_obj(const void* feat, const float* w, const float* bias, const void* feat1,
+                                        const float* w1, const float* bias1, const float* x_input, const float* x_t,
+                                        const float* noise, const float* coef, float* x_next, float* pred_res,
+                                        float* pred_noise, float* x_start, long npix, int C, int dtype, int objective,
+                                        cudaStream_t stream) {
+    if (!feat || !w || !bias || !x_input || !x_t || !coef || !x_next || npix <= 0 || C <= 0) return FD_ERR_BAD_ARGUMENT;
+    if (objective < FD_OBJ_PRED_RES || objective > FD_OBJ_PRED_X0_NOISE) return FD_ERR_BAD_ARGUMENT;
+    const bool two = objective == FD_OBJ_PRED_RES_NOISE || objective == FD_OBJ_PRED_X0_NOISE;
+    if (two && (!feat1 || !w1 || !bias1)) return FD_ERR_BAD_ARGUMENT;
+    FD_DISPATCH_DTYPE(dtype, T, {
+        constexpr int VEC = fd_vec<T>::N;
+        const int lpp = C / VEC;
+        if (C % VEC || lpp > 32 || (lpp & (lpp - 1))) return FD_ERR_UNSUPPORTED;
+        const long warps = (npix + (32 / lpp) - 1) / (32 / lpp);
+        const unsigned grid = (unsigned)fd_cdiv(warps, 8);
+        const T *f0 = (const T*)feat, *f1 = (const T*)feat1;
+        switch (objective) {
+            case FD_OBJ_PRED_RES:
+                final_conv_update_kernel<T, FD_OBJ_PRED_RES><<<grid, 256, 0, stream>>>(
+                    f0, w, bias, f1, w1, bias1, x_input, x_t, noise, coef, x_next, pred_res, pred_noise, x_start, npix, C);
+                break;
+            case FD_OBJ_PRED_NOISE:
+                final_conv_update_kernel<T, FD_OBJ_PRED_NOISE><<<grid, 256, 0, stream>>>(
+                    f0, w, bias, f1, w1, bias1, x_input, x_t, noise, coef, x_next, pred_res, pred_noise, x_start, npix, C);
+                break;
+            case FD_OBJ_PRED_RES_NOISE:
+                final_conv_update_kernel<T, FD_OBJ_PRED_RES_NOISE><<<grid, 256, 0, stream>>>(
+                    f0, w, bias, f1, w1, bias1, x_input, x_t, noise, coef, x_next, pred_res, pred_noise, x_start, npix, C);
+                break;
+            default:
+                final_conv_update_kernel<T, FD_OBJ_PRED_X0_NOISE><<<grid, 256, 0, stream>>>(
+                    f0, w, bias, f1, w1, bias1, x_input, x_t, noise, coef, x_next, pred_res, pred_noise, x_start, npix, C);
+                break;
+        }
+    });
+    FD_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int fd_final_conv_update(const void* feat, const float* w, const float* bias, const float* x_input,
                                     const float* x_t, const float* noise, const float* coef, float* x_next,
                                     float* pred_res, float* pred_noise, float* x_start, long npix, int C, int dtype,
                                     cudaStream_t stream) {
-    if (!feat || !w || !bias || !x_input || !x_t || !coef || !x_next || npix <= 0 || C <= 0) return FD_ERR_BAD_ARGUMENT;
-    FD_DISPATCH_DTYPE(dtype, T, {
-        constexpr int VEC = fd_vec<T>::N;
-        const int lpp = C / VEC;
-        if (C % VEC || lpp > 32 || (lpp & (lpp - 1))) return FD_ERR_UNSUPPORTED;
-        const long warps = (npix + (32 / lpp) - 1) / (32 / lpp);
-        final_conv_update_kernel<T><<<fd_cdiv(warps, 8), 256, 0, stream>>>((const T*)feat, w, bias, x_input, x_t, noise,
-                                                                          coef, x_next, pred_res, pred_noise, x_start,
-                                                                          npix, C);
-    });
-    FD_LAUNCH_CHECK();
-    return 0;
+    return fd_final_conv_update_obj(feat, w, bias, nullptr, nullptr, nullptr, x_input, x_t, noise, coef, x_next,
+                                    pred_res, pred_noise, x_start, npix, C, dtype, FD_OBJ_PRED_RES, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------

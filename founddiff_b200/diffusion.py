@@ -16,8 +16,11 @@ Additive extension: `sample(..., noise=...)` injects host-supplied noise (dict w
 ancestral sampling, "steps": (T-1,B,1,H,W) ordered t = T-1 .. 1, or a callable t -> tensor) so that runs are
 reproducible against the oracle.  Without it the same `torch.randn` calls as the reference are made on the device.
 
-Only the configuration the reference ships (train.py:78-82: num_unet=1, objective='pred_res', condition=True,
-input_condition=False) is implemented; anything else raises NotImplementedError.
+Objectives: the shipped configuration (train.py:78-82: num_unet=1, objective='pred_res') and the
+reference's other three — 'pred_noise' (num_unet=1), 'pred_res_noise' and 'pred_x0_noise' (num_unet=2, train.py:75-77; two
+Unet engines per timestep, test_res_or_noise in {"res_noise", "res", "noise"}) — all end in the same fused
+final_conv + model_predictions + update kernel (`fd_final_conv_update_obj`).  `q_sample / p_losses / forward`
+(:1382-1500) are forward-only mirrors (validation loss; no autograd).  condition=True, input_condition=False only.
 """
 from __future__ import annotations
 
@@ -80,8 +83,8 @@ class UnetRes(nn.Module):
                  random_fourier_features=False, learned_sinusoidal_dim=16, num_unet=1, condition=False,
                  input_condition=False, objective='pred_res_noise', test_res_or_noise="res_noise", seed: int = 10):
         super().__init__()
-        if num_unet != 1 or objective != 'pred_res':
-            raise NotImplementedError("only num_unet=1 / objective='pred_res' is implemented (train.py:78-82)")
+        if num_unet not in (1, 2):
+            raise ValueError("num_unet must be 1 or 2 (src/DADiff.py:775-815)")
         self.condition = condition
         self.input_condition = input_condition
         self.channels = channels
@@ -91,11 +94,14 @@ class UnetRes(nn.Module):
         self.num_unet = num_unet
         self.objective = objective
         self.test_res_or_noise = test_res_or_noise
-        self.unet0 = Unet(dim, init_dim=init_dim, out_dim=out_dim, dim_mults=dim_mults, channels=channels,
-                          self_condition=self_condition, resnet_block_groups=resnet_block_groups,
-                          learned_variance=learned_variance, learned_sinusoidal_cond=learned_sinusoidal_cond,
-                          random_fourier_features=random_fourier_features, learned_sinusoidal_dim=learned_sinusoidal_dim,
-                          condition=condition, input_condition=input_condition, seed=seed)
+        kw = dict(init_dim=init_dim, out_dim=out_dim, dim_mults=dim_mults, channels=channels,
+                  self_condition=self_condition, resnet_block_groups=resnet_block_groups,
+                  learned_variance=learned_variance, learned_sinusoidal_cond=learned_sinusoidal_cond,
+                  random_fourier_features=random_fourier_features, learned_sinusoidal_dim=learned_sinusoidal_dim,
+                  condition=condition, input_condition=input_condition)
+        self.unet0 = Unet(dim, seed=seed, **kw)
+        if num_unet == 2:
+            self.unet1 = Unet(dim, seed=seed + 1, **kw)                 # :789-801 (an independently initialised twin)
         self.compute_dtype = torch.bfloat16
         # storage of the residual stream / pre-GroupNorm conv outputs; None = automatic: fp16 under bf16 sampling (the
         # tensors whose rounding error accumulates get the 11-bit mantissa, the unnormalised ones keep bf16's range),
@@ -116,7 +122,8 @@ class UnetRes(nn.Module):
         CLIP text tower, `prompt_learner`) are ignored.  Missing live keys still raise."""
         own = super().state_dict()
         live = {k: v for k, v in state_dict.items() if k in own}
-        dead_ok = ("unet0.clip_model.", "unet0.dose_encoder.clip_model.", "unet0.dose_encoder.prompt_learner.")
+        dead_ok = tuple(f"unet{i}.{d}" for i in range(self.num_unet)
+                        for d in ("clip_model.", "dose_encoder.clip_model.", "dose_encoder.prompt_learner."))
         unexpected = [k for k in state_dict if k not in own and not k.startswith(dead_ok)]
         if strict and unexpected:
             raise RuntimeError(f"unexpected keys: {unexpected[:5]}...")
@@ -124,10 +131,13 @@ class UnetRes(nn.Module):
         self.invalidate()
         return res
 
-    def _live_sd(self):
-        return OrderedDict((k, v.detach()) for k, v in self.unet0.state_dict().items())
+    def _unet(self, idx: int) -> Unet:
+        return self.unet0 if idx == 0 else self.unet1
 
-    def engine(self, B, H, W, device) -> UnetEngine:
+    def _live_sd(self, idx: int = 0):
+        return OrderedDict((k, v.detach()) for k, v in self._unet(idx).state_dict().items())
+
+    def engine(self, B, H, W, device, idx: int = 0) -> UnetEngine:
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())       # 'cuda' and 'cuda:0' are one engine
@@ -135,40 +145,83 @@ class UnetRes(nn.Module):
         if trunk is None:
             trunk = torch.float16 if self.compute_dtype == torch.bfloat16 else self.compute_dtype
         key = (B, H, W, self.compute_dtype, trunk, str(device))
-        eng = self._engines.get(key)
+        if self._engines and next(iter(self._engines))[0] != key:
+            self._engines.clear()          # one resident shape: activations for B=16 at 512^2 are ~25 GB per Unet
+        eng = self._engines.get((key, idx))
         if eng is None:
-            self._engines.clear()          # one resident engine: activations for B=16 at 512^2 are ~25 GB
-            eng = UnetEngine(self._live_sd(), self.unet0.cfg, B, H, W, dtype=self.compute_dtype, device=device,
+            eng = UnetEngine(self._live_sd(idx), self._unet(idx).cfg, B, H, W, dtype=self.compute_dtype, device=device,
                              trunk_dtype=trunk)
-            self._engines[key] = eng
+            self._engines[(key, idx)] = eng
         return eng
 
-    def daclip(self, device) -> DAClipEncoder:
+    def daclip(self, device, idx: int = 0) -> DAClipEncoder:
+        """Each Unet owns its dose encoder (`unet{idx}.dose_encoder.*`)."""
         cdt = torch.float32 if self.compute_dtype == torch.float32 else torch.bfloat16
-        if self._daclip is None or str(self._daclip_dev) != str(device) or self._daclip.conv_dtype != cdt:
-            self._daclip = DAClipEncoder(self._live_sd(), device, conv_dtype=cdt)
-            self._daclip_dev = device
-        return self._daclip
+        if self._daclip is None:
+            self._daclip = {}
+        enc = self._daclip.get(idx)
+        if enc is None or str(enc._fd_dev) != str(device) or enc.conv_dtype != cdt:
+            enc = DAClipEncoder(self._live_sd(idx), device, conv_dtype=cdt)
+            enc._fd_dev = device
+            self._daclip[idx] = enc
+        return enc
 
-    @torch.no_grad()
-    def forward(self, x, time, x_self_cond=None):
-        """Model-call boundary (src/DADiff.py:817-836, 1161-1164): x = cat(x_t, x_input) (B,2,H,W),
-        time = [t_res, t_noise]; returns [pred (B,1,H,W)] (raw, un-clamped)."""
-        if not x.is_cuda:
-            raise RuntimeError("founddiff_b200 has no CPU path")
-        t = time[0] if isinstance(time, (list, tuple)) else time
+    def _eval_plan(self, objective: Optional[str] = None, test_res_or_noise: Optional[str] = None):
+        """Which Unets one model call evaluates, with which entry of `time`, and the FD_OBJ_* branch that consumes the
+        outputs: (kernel objective, [(unet idx, time idx), ...]).  src/DADiff.py:817-836 + :1168-1207."""
+        objective = self.objective if objective is None else objective
+        trn = self.test_res_or_noise if test_res_or_noise is None else test_res_or_noise
+        if self.num_unet == 1:
+            if objective == "pred_res":
+                return "pred_res", [(0, 0)]
+            if objective == "pred_noise":
+                return "pred_noise", [(0, 1)]
+            raise ValueError(f"objective {objective!r} needs num_unet=2 (src/DADiff.py:824-829)")
+        if objective == "pred_res_noise":
+            if trn == "res_noise":
+                return "pred_res_noise", [(0, 0), (1, 1)]
+            if trn == "res":
+                return "pred_res", [(0, 0)]
+            if trn == "noise":
+                return "pred_noise", [(1, 1)]
+            raise ValueError(f"test_res_or_noise {trn!r} (src/DADiff.py:818-823)")
+        if objective == "pred_x0_noise":
+            if trn != "res_noise":
+                raise NotImplementedError("pred_x0_noise reads both model outputs (src/DADiff.py:1188-1192)")
+            return "pred_x0_noise", [(0, 0), (1, 1)]
+        raise ValueError(f"objective {objective!r} with num_unet=2: model_output[0] would be a pair (src/DADiff.py:1194-1207)")
+
+    def _run_unet(self, idx, x, t):
         B, _, H, W = x.shape
-        eng = self.engine(B, H, W, x.device)
+        eng = self.engine(B, H, W, x.device, idx)
         eng.x_t.copy_(x[:, 0].reshape(B, -1))
         eng.x_input.copy_(x[:, 1].reshape(B, -1))
-        dose, ctx = self.daclip(x.device).embed(x[:, 1:2])
+        dose, ctx = self.daclip(x.device, idx).embed(x[:, 1:2])
         eng.set_condition(dose, ctx)
         eng.time.copy_(t.to(torch.float32).reshape(-1).expand(B))
         feat = eng.forward()
         out = torch.empty(B, H * W, 1, device=x.device, dtype=feat.dtype)
         w = eng.final_w.to(feat.dtype).reshape(1, 1, 1, -1).contiguous()
         ops.Conv(feat, w, out, B=B, Hin=H, Win=W, bias=eng.final_b, prefer_tc=False).run()
-        return [out.float().reshape(B, 1, H, W)]
+        return out.float().reshape(B, 1, H, W)
+
+    @torch.no_grad()
+    def forward(self, x, time, x_self_cond=None):
+        """Model-call boundary (src/DADiff.py:817-836, 1161-1164): x = cat(x_t, x_input) (B,2,H,W),
+        time = [t_res, t_noise].  num_unet=1: returns [pred (B,1,H,W)] (raw, un-clamped); num_unet=2: the pair
+        (unet0 output or 0, unet1 output or 0) selected by test_res_or_noise."""
+        if not x.is_cuda:
+            raise RuntimeError("founddiff_b200 has no CPU path")
+        if not isinstance(time, (list, tuple)):
+            time = [time, time]
+        if self.num_unet == 1:
+            _, evals = self._eval_plan()
+        else:                                                        # :818-823 depends on test_res_or_noise only
+            evals = {"res_noise": [(0, 0), (1, 1)], "res": [(0, 0)], "noise": [(1, 1)]}[self.test_res_or_noise]
+        outs = {idx: self._run_unet(idx, x, time[ti]) for idx, ti in evals}
+        if self.num_unet == 1:
+            return [outs[0]]
+        return outs.get(0, 0), outs.get(1, 0)
 
 
 def make_schedule(timesteps: int = 1000, variant: str = "init") -> Dict[str, torch.Tensor]:
@@ -204,14 +257,18 @@ def make_schedule(timesteps: int = 1000, variant: str = "init") -> Dict[str, tor
 
 
 class ResidualDiffusion(nn.Module):
-    """src/DADiff.py:908-1380 (sampler half).  Training members (q_sample, p_losses, forward) are out of scope."""
+    """src/DADiff.py:908-1500: the sampler, plus forward-only `q_sample / p_losses / forward` (no autograd; training
+    itself — optimiser, EMA, Trainer — is out of scope)."""
 
     def __init__(self, model, *, image_size, timesteps=1000, sampling_timesteps=None, loss_type='l1',
                  objective='pred_res_noise', ddim_sampling_eta=0., condition=False, sum_scale=None,
                  input_condition=False, input_condition_mask=False, test_res_or_noise="None"):
         super().__init__()
-        if objective != 'pred_res' or not condition or input_condition:
-            raise NotImplementedError("only objective='pred_res', condition=True, input_condition=False is implemented")
+        if not condition or input_condition:
+            raise NotImplementedError("only condition=True, input_condition=False is implemented (train.py:78-119)")
+        if objective not in ops.OBJECTIVES:
+            raise ValueError(f"unknown objective {objective}")                    # :1468
+        model._eval_plan(objective, test_res_or_noise if model.num_unet == 2 else None)   # raises on combinations the reference cannot run
         if timesteps != 1000:
             raise NotImplementedError("the reference's init() hard-codes 1000 timesteps (src/DADiff.py:1034)")
         self.model = model
@@ -233,6 +290,8 @@ class ResidualDiffusion(nn.Module):
         for k, v in make_schedule(timesteps, "ctor").items():
             self.register_buffer(k, v)
         self.use_cuda_graph = True
+        # num_unet = 2: evaluate the two Unets of a timestep on two streams (fork / join inside the step's CUDA graph)
+        self.concurrent_unets = False
         self._graphs: Dict = {}
 
     def init(self):
@@ -258,23 +317,25 @@ class ResidualDiffusion(nn.Module):
         return list(zip(times[:-1], times[1:]))
 
     def _step_plan(self):
-        """[(t, coef[6])] with coef = {c_xt, c_res, c_x0, c_noise, alphas_cumsum[t], betas_cumsum[t]}."""
+        """[(t, coef[7])] with coef = {c_xt, c_res, c_x0, c_noise, alphas_cumsum[t], betas_cumsum[t],
+        one_minus_alphas_cumsum[t]}."""
         plan = []
         if self.is_ddim_sampling:
             for t, t_next in self._ddim_pairs():
                 acs, bcs = self._sched("alphas_cumsum", t), self._sched("betas_cumsum", t)
                 if t_next < 0:
-                    plan.append((t, [0., 0., 1., 0., acs, bcs]))                                   # :1317-1321
+                    plan.append((t, [0., 0., 1., 0., acs, bcs, self._sched("one_minus_alphas_cumsum", t)]))   # :1317-1321
                 else:
                     import numpy as np
                     alpha = float(np.float32(acs) - np.float32(self._sched("alphas_cumsum", t_next)))  # :1323-1325 (fp32)
-                    plan.append((t, [1., -alpha, 0., 0., acs, bcs]))                                # :1344, sigma2 = 0
+                    plan.append((t, [1., -alpha, 0., 0., acs, bcs, self._sched("one_minus_alphas_cumsum", t)]))  # :1344, sigma2 = 0
         else:
             for t in reversed(range(self.num_timesteps)):                                           # :1254
                 acs, bcs = self._sched("alphas_cumsum", t), self._sched("betas_cumsum", t)
                 cn = float(torch.tensor(0.5 * self._sched("posterior_log_variance_clipped", t), dtype=torch.float32).exp()) if t > 0 else 0.   # :1228-1229
                 plan.append((t, [self._sched("posterior_mean_coef1", t), self._sched("posterior_mean_coef2", t),
-                                 self._sched("posterior_mean_coef3", t), cn, acs, bcs]))
+                                 self._sched("posterior_mean_coef3", t), cn, acs, bcs,
+                                 self._sched("one_minus_alphas_cumsum", t)]))
         return plan
 
     # -- sampling --------------------------------------------------------------------------------------------
@@ -291,10 +352,13 @@ class ResidualDiffusion(nn.Module):
         assert C == 1
         dev = ldct.device
         model = self.model
-        eng = model.engine(B, H, W, dev)
+        objective, evals = model._eval_plan(self.objective, self.test_res_or_noise if model.num_unet == 2 else None)
+        engs = [model.engine(B, H, W, dev, idx) for idx, _ in evals]
+        eng = engs[0]
+        for other in engs[1:]:                       # both Unets read the same images (UnetRes.forward, :817-820)
+            other.x_t, other.x_input = eng.x_t, eng.x_input
         P = H * W
         plan = self._step_plan()
-        n_noise = 0 if self.is_ddim_sampling else len(plan) - 1
 
         def get_noise(kind, idx=None, t=None):
             if noise is None:
@@ -307,31 +371,50 @@ class ResidualDiffusion(nn.Module):
         ldct32 = ldct.to(torch.float32).contiguous().view(B, P)
         first = torch.empty(B, P, device=dev, dtype=torch.float32)
         ops.sampler_init(ldct32, get_noise("init").contiguous().view(B, P), math.sqrt(self.sum_scale), eng.x_input, eng.x_t, first)
-        dose, ctx = model.daclip(dev).embed(eng.x_input.view(B, 1, H, W))       # once per slice (cached across steps)
-        eng.set_condition(dose, ctx)
+        for e, (idx, _) in zip(engs, evals):         # once per slice and per Unet (cached across timesteps)
+            dose, ctx = model.daclip(dev, idx).embed(eng.x_input.view(B, 1, H, W))
+            e.set_condition(dose, ctx)
 
         coef = self._buffer(eng, "coef", 8)
         noise_buf = self._buffer(eng, "noise", B * P).view(B, P)
         taps = None
         if trace is not None:
             taps = [self._buffer(eng, n, B * P).view(B, P) for n in ("pred_res", "pred_noise", "x_start")]
-        coef_host = torch.tensor([[*c, 0., 0.] for _, c in plan], dtype=torch.float32).pin_memory()
-        time_host = torch.tensor([self._sched("alphas_cumsum", t) for t, _ in plan], dtype=torch.float32) * self.num_timesteps  # :1162
-        time_rows = time_host[:, None].expand(-1, B).contiguous().pin_memory()
+        coef_host = torch.tensor([[*c, 0.] for _, c in plan], dtype=torch.float32).pin_memory()
+        # model time arguments (:1161-1163): [alphas_cumsum[t], betas_cumsum[t]] * num_timesteps, one row per Unet evaluated
+        time_rows = []
+        for _, ti in evals:
+            name = ("alphas_cumsum", "betas_cumsum")[ti]
+            th = torch.tensor([self._sched(name, t) for t, _ in plan], dtype=torch.float32) * self.num_timesteps
+            time_rows.append(th[:, None].expand(-1, B).contiguous().pin_memory())
+        two = len(engs) == 2
+        side = self._side_stream(dev) if (two and self.concurrent_unets) else None
 
         def one_step():
-            eng.forward()
+            if side is not None:
+                cur = torch.cuda.current_stream(dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    engs[1].forward()
+                eng.forward()
+                cur.wait_stream(side)
+            else:
+                for e in engs:
+                    e.forward()
             ops.final_conv_update(eng.feat, eng.final_w, eng.final_b, eng.x_input, eng.x_t, noise_buf, coef, eng.x_t,
-                                  *(taps if taps is not None else (None, None, None)))
+                                  *(taps if taps is not None else (None, None, None)), objective=objective,
+                                  feat1=engs[1].feat if two else None, w1=engs[1].final_w if two else None,
+                                  bias1=engs[1].final_b if two else None)
 
         step_fn = one_step
         if self.use_cuda_graph:
-            step_fn = self._graphed(eng, one_step, taps is not None)
+            step_fn = self._graphed(engs, one_step, (taps is not None, objective, side is not None))
 
         imgs = []
         for i, (t, c) in enumerate(plan):
             coef.copy_(coef_host[i], non_blocking=True)
-            eng.time.copy_(time_rows[i], non_blocking=True)
+            for e, rows in zip(engs, time_rows):
+                e.time.copy_(rows[i], non_blocking=True)
             if c[3] != 0.:
                 noise_buf.copy_(get_noise("step", i, t).contiguous().view(B, P))
             step_fn()
@@ -363,20 +446,76 @@ class ResidualDiffusion(nn.Module):
 
     @torch.no_grad()
     def model_predictions(self, x_input, x, t, x_input_condition=0, x_self_cond=None, clip_denoised=True):
-        """src/DADiff.py:1153-1209, branch 'pred_res' — the per-step parity tap.  x_input, x: (B,1,H,W) in [-1,1];
-        t: (B,) long (all equal).  Returns (pred_res, pred_noise, pred_x_start)."""
+        """src/DADiff.py:1153-1209, every objective branch — the per-step parity tap.  x_input, x: (B,1,H,W) in [-1,1];
+        t: (B,) long.  Returns (pred_res, pred_noise, pred_x_start)."""
         from collections import namedtuple
-        B, _, H, W = x.shape
-        ti = int(t.reshape(-1)[0])
-        time = (self.alphas_cumsum[ti] * self.num_timesteps).to(x.device).expand(B)
-        out = self.model(torch.cat((x, x_input), dim=1), [time, time])[0]
-        pred_res = out.clamp(-1., 1.) if clip_denoised else out
-        acs, bcs = self._sched("alphas_cumsum", ti), self._sched("betas_cumsum", ti)
-        pred_noise = (x - x_input - (acs - 1) * pred_res) / bcs
-        x_start = x_input - pred_res
-        if clip_denoised:
-            x_start = x_start.clamp(-1., 1.)
+        ex = lambda name: getattr(self, name).to(x.device)[t.reshape(-1)].view(-1, 1, 1, 1)      # noqa: E731  extract(), :841-844
+        acs, bcs, omacs = ex("alphas_cumsum"), ex("betas_cumsum"), ex("one_minus_alphas_cumsum")
+        out = self.model(torch.cat((x, x_input), dim=1),
+                         [acs.reshape(-1) * self.num_timesteps, bcs.reshape(-1) * self.num_timesteps], x_self_cond)
+        clip = (lambda v: v.clamp(-1., 1.)) if clip_denoised else (lambda v: v)
+        objective, _ = self.model._eval_plan(self.objective, self.test_res_or_noise if self.model.num_unet == 2 else None)
+        if objective == "pred_res":                                                   # :1176-1182, 1202-1207
+            pred_res = clip(out[0])
+            pred_noise = (x - x_input - (acs - 1) * pred_res) / bcs                   # :1120-1124
+            x_start = clip(x_input - pred_res)
+        elif objective == "pred_noise":                                               # :1183-1189, 1194-1201
+            pred_noise = out[1] if self.model.num_unet == 2 else out[0]
+            x_start = clip((x - acs * x_input - bcs * pred_noise) / omacs)            # :1126-1130
+            pred_res = clip(x_input - x_start)
+        elif objective == "pred_res_noise":                                           # :1169-1175
+            pred_res, pred_noise = clip(out[0]), out[1]
+            x_start = clip(x - acs * pred_res - bcs * pred_noise)                     # :1132-1136
+        else:                                                                         # pred_x0_noise :1188-1192
+            pred_res, pred_noise, x_start = clip(x_input - out[0]), out[1], clip(out[0])
         return namedtuple('ModelResPrediction', ['pred_res', 'pred_noise', 'pred_x_start'])(pred_res, pred_noise, x_start)
+
+    # -- forward-only training-side members (src/DADiff.py:1382-1500) ------------------------------------------
+    def q_sample(self, x_start, x_res, t, noise=None):
+        """:1382-1388  x_t = x_start + alphas_cumsum[t] x_res + betas_cumsum[t] noise."""
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        ex = lambda name: getattr(self, name).to(x_start.device)[t.reshape(-1)].view(-1, 1, 1, 1)  # noqa: E731
+        return x_start + ex("alphas_cumsum") * x_res + ex("betas_cumsum") * noise
+
+    @property
+    def loss_fn(self):
+        if self.loss_type == 'l1':
+            return F.l1_loss
+        if self.loss_type == 'l2':
+            return F.mse_loss
+        raise ValueError(f'invalid loss type {self.loss_type}')
+
+    @torch.no_grad()
+    def p_losses(self, imgs, t, noise=None):
+        """:1399-1482 without autograd: imgs = [x_start (gt), x_input] in [-1,1]; t (B,) long; returns the loss list
+        (one entry per model output).  The Unet evaluations run on the kernel engine."""
+        if not isinstance(imgs, (list, tuple)):
+            raise TypeError("condition=True: imgs must be the list [gt, input] (:1400-1406)")
+        x_start, x_input = imgs[0], imgs[1]
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        x_res = x_input - x_start
+        x = self.q_sample(x_start, x_res, t, noise=noise)
+        ex = lambda name: getattr(self, name).to(x.device)[t.reshape(-1)]                            # noqa: E731
+        model_out = self.model(torch.cat((x, x_input), dim=1),
+                               [ex("alphas_cumsum") * self.num_timesteps, ex("betas_cumsum") * self.num_timesteps], None)
+        target = {"pred_res_noise": [x_res, noise], "pred_x0_noise": [x_start, noise], "pred_noise": [noise],
+                  "pred_res": [x_res]}[self.objective]                                               # :1444-1466
+        losses = []
+        for out, tgt in zip(model_out, target):                                                      # :1476-1482
+            if not torch.is_tensor(out):
+                raise ValueError("p_losses needs every model output (test_res_or_noise='res_noise' with num_unet=2)")
+            loss = self.loss_fn(out, tgt, reduction='none')
+            losses.append(loss.reshape(loss.shape[0], -1).mean(dim=1).mean())
+        return losses
+
+    def forward(self, img, *args, **kwargs):
+        """:1484-1500: draws t ~ U{0..T-1} per sample, maps [gt, input] from [0,1] to [-1,1], returns p_losses."""
+        b, device = img[0].shape[0], img[0].device
+        t = torch.randint(0, self.num_timesteps, (b,), device=device).long()
+        img = [i * 2 - 1 for i in img]
+        return self.p_losses(img, t, *args, **kwargs)
 
     # -- internals -------------------------------------------------------------------------------------------
     @staticmethod
@@ -388,10 +527,17 @@ class ResidualDiffusion(nn.Module):
             store[name] = t
         return t[:n]
 
-    def _graphed(self, eng, fn, with_taps):
-        """Capture one timestep (conditioning + Unet + fused final_conv/update) as a CUDA graph; the step's scalars
+    def _side_stream(self, dev):
+        st = self.__dict__.setdefault("_side_streams", {})
+        if str(dev) not in st:
+            st[str(dev)] = torch.cuda.Stream(device=dev)
+        return st[str(dev)]
+
+    def _graphed(self, engs, fn, variant):
+        """Capture one timestep (conditioning + Unet(s) + fused final_conv/update) as a CUDA graph; the step's scalars
         (time, coefficients) and noise live in device buffers that are refreshed before each replay."""
-        key = (id(eng), with_taps)
+        eng = engs[0]
+        key = (tuple(id(e) for e in engs), variant)
         g = self._graphs.get(key)
         if g is None:
             s = torch.cuda.Stream(device=eng.device)
@@ -408,7 +554,7 @@ class ResidualDiffusion(nn.Module):
                 fn()
             eng.x_t.copy_(saved)
             self._graphs.clear()
-            self._graphs[key] = (g, eng)
+            self._graphs[key] = (g, list(engs))
         else:
             g = g[0]
         return g.replay

@@ -454,13 +454,22 @@ def sampler_init(ldct, noise, noise_scale, x_input, x_t, first):
                                           ldct.numel(), _stream()), "fd_sampler_init")
 
 
-def final_conv_update(feat, w, bias, x_input, x_t, noise, coef, x_next, pred_res=None, pred_noise=None, x_start=None):
+OBJECTIVES = {"pred_res": 0, "pred_noise": 1, "pred_res_noise": 2, "pred_x0_noise": 3}     # FD_OBJ_* (include/founddiff_b200.h)
+
+
+def final_conv_update(feat, w, bias, x_input, x_t, noise, coef, x_next, pred_res=None, pred_noise=None, x_start=None,
+                      objective: str = "pred_res", feat1=None, w1=None, bias1=None):
+    """final_conv + model_predictions (any objective, src/DADiff.py:1168-1207) + posterior / DDIM update in one kernel.
+    `feat1 / w1 / bias1`: the second Unet's final_conv operands for the two-output objectives."""
     npix = x_input.numel()
     C = feat.shape[-1]
+    if feat1 is not None and (feat1.dtype != feat.dtype or feat1.shape[-1] != C):
+        raise ValueError("both Unets must share the feature dtype and width")
     with _launched("final_conv_update", f"{npix}x{C}"):
-        check(_lib.load().fd_final_conv_update(_p(feat), _f32(w), _f32(bias), _f32(x_input), _f32(x_t), _f32(noise), _f32(coef),
-                                               _f32(x_next), _f32(pred_res), _f32(pred_noise), _f32(x_start), npix, C,
-                                               dtype_code(feat.dtype), _stream()), "fd_final_conv_update")
+        check(_lib.load().fd_final_conv_update_obj(_p(feat), _f32(w), _f32(bias), _p(feat1), _f32(w1), _f32(bias1), _f32(x_input),
+                                                   _f32(x_t), _f32(noise), _f32(coef), _f32(x_next), _f32(pred_res),
+                                                   _f32(pred_noise), _f32(x_start), npix, C, dtype_code(feat.dtype),
+                                                   OBJECTIVES[objective], _stream()), "fd_final_conv_update_obj")
 
 
 def unnormalize(x, out):

@@ -273,13 +273,32 @@ int fd_time_sinusoid(const float* time, float* out, int B, int dim, cudaStream_t
  *   with coef (DEVICE, fp32[6]) = {c_xt, c_res, c_x0, c_noise, acs = alphas_cumsum[t], bcs = betas_cumsum[t]}.
  *   DDIM (eta=0): {1, -(acs_t - acs_next), 0, 0} and {0, 0, 1, 0} for the last pair;  ancestral:
  *   {coef1[t], coef2[t], coef3[t], exp(0.5*logvar[t]) or 0 at t=0}.
+ * fd_final_conv_update_obj: the same kernel for every objective branch of model_predictions (src/DADiff.py:1168-1207),
+ *   `objective` = FD_OBJ_*; feat1 / w1 / bias1 = the second Unet's final_conv operands (num_unet = 2, UnetRes.forward
+ *   src/DADiff.py:817-820), read only by the two-output objectives (NULL otherwise); coef is fp32[8] with
+ *   coef[6] = one_minus_alphas_cumsum[t]:
+ *     FD_OBJ_PRED_RES        o0 = pred_res: as above (also 'pred_res_noise' with test_res_or_noise = "res", :1176-1182)
+ *     FD_OBJ_PRED_NOISE      o0 = pred_noise; x_start = clamp((x_t - acs x_input - bcs o0) / coef[6]);
+ *                            pred_res = clamp(x_input - x_start)          (:1194-1201; test_res_or_noise = "noise" :1183-1189)
+ *     FD_OBJ_PRED_RES_NOISE  pred_res = clamp(o0), pred_noise = o1, x_start = clamp(x_t - acs pred_res - bcs o1)  (:1169-1175)
+ *     FD_OBJ_PRED_X0_NOISE   pred_res = clamp(x_input - o0), pred_noise = o1, x_start = clamp(o0)                 (:1188-1192)
+ *   the update line (x_next) is the same for all of them: neither q_posterior (:1142-1151) nor the 'use_pred_noise'
+ *   DDIM step (:1344) reads pred_noise.
  * fd_unnormalize: out = (x + 1) / 2.
  * --------------------------------------------------------------------------------------------------------- */
+#define FD_OBJ_PRED_RES 0
+#define FD_OBJ_PRED_NOISE 1
+#define FD_OBJ_PRED_RES_NOISE 2
+#define FD_OBJ_PRED_X0_NOISE 3
 int fd_sampler_init(const float* ldct, const float* noise, float noise_scale, float* x_input, float* x_t,
                     float* first, long n, cudaStream_t stream);
 int fd_final_conv_update(const void* feat, const float* w, const float* bias, const float* x_input,
                          const float* x_t, const float* noise, const float* coef, float* x_next, float* pred_res,
                          float* pred_noise, float* x_start, long npix, int C, int dtype, cudaStream_t stream);
+int fd_final_conv_update_obj(const void* feat, const float* w, const float* bias, const void* feat1, const float* w1,
+                             const float* bias1, const float* x_input, const float* x_t, const float* noise,
+                             const float* coef, float* x_next, float* pred_res, float* pred_noise, float* x_start,
+                             long npix, int C, int dtype, int objective, cudaStream_t stream);
 int fd_unnormalize(const float* x, float* out, long n, cudaStream_t stream);
 /* Evaluation metrics of Trainer.test (src/DADiff.py:1883-1888; src/util.py:188-236 compute_psnr / compute_ssim /
  * compute_rmse) on the device: out[2*b] = sum over the slice of (pred - target)^2, out[2*b + 1] = sum of the SSIM map

@@ -298,18 +298,50 @@ def unet_forward(sd, x: Tensor, time: Tensor, dose_emb: Optional[Tensor] = None,
 
 
 # ----------------------------------------------------------------------------------------------------------
-# Sampler  (src/DADiff.py:1153-1380), objective 'pred_res', condition=True, eta forced to 0 (:940-942)
+# Sampler  (src/DADiff.py:1153-1380), condition=True, eta forced to 0 (:940-942).  Default objective 'pred_res'
+# (train.py:78-82); the other objectives take `objective=` (+ `sd1`, the second Unet's weights, for num_unet = 2).
 # ----------------------------------------------------------------------------------------------------------
+def eval_plan(objective: str, test_res_or_noise: str, num_unet: int):
+    """(branch of model_predictions, [(unet idx, time idx)]) — UnetRes.forward :817-836 + :1168-1207."""
+    if num_unet == 1:
+        return {"pred_res": ("pred_res", [(0, 0)]), "pred_noise": ("pred_noise", [(0, 1)])}[objective]
+    if objective == "pred_res_noise":
+        return {"res_noise": ("pred_res_noise", [(0, 0), (1, 1)]), "res": ("pred_res", [(0, 0)]),
+                "noise": ("pred_noise", [(1, 1)])}[test_res_or_noise]
+    assert objective == "pred_x0_noise" and test_res_or_noise == "res_noise"
+    return "pred_x0_noise", [(0, 0), (1, 1)]
+
+
 def model_predictions(sd, sched, x_input: Tensor, x_t: Tensor, t: int, emb=None, rt: Callable = _ID,
-                      num_timesteps: int = 1000):
-    """:1153-1209 branch 'pred_res' (:1202-1207). Returns (pred_res, pred_noise, x_start)."""
+                      num_timesteps: int = 1000, objective: str = "pred_res", test_res_or_noise: str = "res",
+                      sd1=None, emb1=None):
+    """:1153-1209, all objective branches. Returns (pred_res, pred_noise, x_start).  `emb` / `emb1`: cached DA-CLIP
+    embeddings of unet0 / unet1 (each Unet owns a dose encoder)."""
     B = x_t.shape[0]
-    time = (sched["alphas_cumsum"][t] * num_timesteps).expand(B)                    # :1162
-    dose, ctx = emb if emb is not None else daclip_embed(sd, x_input)
-    out = unet_forward(sd, torch.cat((x_t, x_input), dim=1), time, dose, ctx, rt=rt)
-    pred_res = out.clamp(-1., 1.)
-    pred_noise = (x_t - x_input - (sched["alphas_cumsum"][t] - 1) * pred_res) / sched["betas_cumsum"][t]   # :1120-1124
-    x_start = (x_input - pred_res).clamp(-1., 1.)
+    acs, bcs, omacs = sched["alphas_cumsum"][t], sched["betas_cumsum"][t], sched["one_minus_alphas_cumsum"][t]
+    times = [(acs * num_timesteps).expand(B), (bcs * num_timesteps).expand(B)]      # :1161-1163
+    branch, evals = eval_plan(objective, test_res_or_noise, 1 if sd1 is None else 2)
+    x_in = torch.cat((x_t, x_input), dim=1)
+    outs = {}
+    for idx, ti in evals:
+        w = sd if idx == 0 else sd1
+        e = emb if idx == 0 else emb1
+        dose, ctx = e if e is not None else daclip_embed(w, x_input)
+        outs[idx] = unet_forward(w, x_in, times[ti], dose, ctx, rt=rt)
+    clip = lambda v: v.clamp(-1., 1.)                                               # noqa: E731
+    if branch == "pred_res":                                                        # :1176-1182, 1202-1207
+        pred_res = clip(outs[0])
+        pred_noise = (x_t - x_input - (acs - 1) * pred_res) / bcs                   # :1120-1124
+        x_start = clip(x_input - pred_res)
+    elif branch == "pred_noise":                                                    # :1183-1189, 1194-1201
+        pred_noise = outs[evals[0][0]]
+        x_start = clip((x_t - acs * x_input - bcs * pred_noise) / omacs)            # :1126-1130
+        pred_res = clip(x_input - x_start)
+    elif branch == "pred_res_noise":                                                # :1169-1175
+        pred_res, pred_noise = clip(outs[0]), outs[1]
+        x_start = clip(x_t - acs * pred_res - bcs * pred_noise)                     # :1132-1136
+    else:                                                                           # pred_x0_noise :1188-1192
+        pred_res, pred_noise, x_start = clip(x_input - outs[0]), outs[1], clip(outs[0])
     return pred_res, pred_noise, x_start
 
 
@@ -320,14 +352,17 @@ def ddim_times(sampling_timesteps: int, total: int = 1000):
 
 
 def ddim_sample(sd, sched, x_input: Tensor, init_noise: Tensor, sampling_timesteps: int, sum_scale: float = 0.01,
-                last: bool = True, rt: Callable = _ID, trace: Optional[list] = None):
-    """:1275-1365 with condition=True, eta=0, type 'use_pred_noise'.  x_input in [-1,1]."""
+                last: bool = True, rt: Callable = _ID, trace: Optional[list] = None, **obj):
+    """:1275-1365 with condition=True, eta=0, type 'use_pred_noise'.  x_input in [-1,1].  `obj`: objective,
+    test_res_or_noise, sd1 (see model_predictions)."""
     img = x_input + math.sqrt(sum_scale) * init_noise                               # :1294-1295
     first = img
     emb = daclip_embed(sd, x_input)
+    if obj.get("sd1") is not None:
+        obj = dict(obj, emb1=daclip_embed(obj["sd1"], x_input))
     imgs = []
     for t, t_next in ddim_times(sampling_timesteps):
-        pred_res, pred_noise, x_start = model_predictions(sd, sched, x_input, img, t, emb, rt)
+        pred_res, pred_noise, x_start = model_predictions(sd, sched, x_input, img, t, emb, rt, **obj)
         if trace is not None:
             trace.append(dict(t=t, pred_res=pred_res, pred_noise=pred_noise, x_start=x_start))
         if t_next < 0:
@@ -342,17 +377,19 @@ def ddim_sample(sd, sched, x_input: Tensor, init_noise: Tensor, sampling_timeste
 
 def p_sample_loop(sd, sched, x_input: Tensor, init_noise: Tensor, step_noise: Callable[[int], Tensor],
                   num_timesteps: int = 1000, sum_scale: float = 0.01, last: bool = True, rt: Callable = _ID,
-                  trace: Optional[list] = None):
+                  trace: Optional[list] = None, **obj):
     """:1232-1273 + p_sample :1221-1230 + q_posterior :1142-1151.  `step_noise(t)` supplies the N(0,1) tensor
     the reference draws with randn_like at step t (t > 0)."""
     img = x_input + math.sqrt(sum_scale) * init_noise
     first = img
     emb = daclip_embed(sd, x_input)
+    if obj.get("sd1") is not None:
+        obj = dict(obj, emb1=daclip_embed(obj["sd1"], x_input))
     imgs = []
     for t in reversed(range(num_timesteps)):
         # NB the reference scales the Unet time argument by self.num_timesteps (:1162), so a fixture that
         # overrides num_timesteps (tests/golden/ancestral_32.npz) sees alphas_cumsum[t]*num_timesteps.
-        pred_res, pred_noise, x_start = model_predictions(sd, sched, x_input, img, t, emb, rt, num_timesteps)
+        pred_res, pred_noise, x_start = model_predictions(sd, sched, x_input, img, t, emb, rt, num_timesteps, **obj)
         mean = (sched["posterior_mean_coef1"][t] * img + sched["posterior_mean_coef2"][t] * pred_res
                 + sched["posterior_mean_coef3"][t] * x_start)
         if trace is not None:
@@ -368,13 +405,34 @@ def p_sample_loop(sd, sched, x_input: Tensor, init_noise: Tensor, step_noise: Ca
 
 def sample(sd, x_input01: Tensor, init_noise: Tensor, sampling_timesteps: int = 2, step_noise=None,
            schedule_variant: str = "init", last: bool = True, num_timesteps: int = 1000, rt: Callable = _ID,
-           trace: Optional[list] = None):
+           trace: Optional[list] = None, **obj):
     """ResidualDiffusion.sample (:1367-1380): x_input01 (B,1,H,W) in [0,1]; returns list in [0,1]."""
     sched = make_schedule(1000, schedule_variant)
     x_input = x_input01 * 2 - 1
     if sampling_timesteps < num_timesteps:
-        return ddim_sample(sd, sched, x_input, init_noise, sampling_timesteps, last=last, rt=rt, trace=trace)
-    return p_sample_loop(sd, sched, x_input, init_noise, step_noise, num_timesteps, last=last, rt=rt, trace=trace)
+        return ddim_sample(sd, sched, x_input, init_noise, sampling_timesteps, last=last, rt=rt, trace=trace, **obj)
+    return p_sample_loop(sd, sched, x_input, init_noise, step_noise, num_timesteps, last=last, rt=rt, trace=trace, **obj)
+
+
+def p_losses(sd, sched, x_start: Tensor, x_input: Tensor, t: Tensor, noise: Tensor, loss_type: str = "l2",
+             num_timesteps: int = 1000, objective: str = "pred_res", sd1=None):
+    """:1399-1482 (forward only), condition=True: q_sample (:1382-1388), one model call, per-output loss
+    `reduce(loss, 'b ... -> b (...)', 'mean').mean()`.  x_start / x_input in [-1,1]; t (B,) long."""
+    ex = lambda n: sched[n][t].view(-1, 1, 1, 1)                                    # noqa: E731
+    x_res = x_input - x_start
+    x = x_start + ex("alphas_cumsum") * x_res + ex("betas_cumsum") * noise
+    times = [sched["alphas_cumsum"][t] * num_timesteps, sched["betas_cumsum"][t] * num_timesteps]
+    _, evals = eval_plan(objective, "res_noise", 1 if sd1 is None else 2)
+    x_in = torch.cat((x, x_input), dim=1)
+    outs = []
+    for idx, ti in evals:
+        w = sd if idx == 0 else sd1
+        dose, ctx = daclip_embed(w, x_input)
+        outs.append(unet_forward(w, x_in, times[ti], dose, ctx))
+    target = {"pred_res_noise": [x_res, noise], "pred_x0_noise": [x_start, noise], "pred_noise": [noise],
+              "pred_res": [x_res]}[objective]
+    fn = F.l1_loss if loss_type == "l1" else F.mse_loss
+    return [fn(o, tg, reduction="none").flatten(1).mean(1).mean() for o, tg in zip(outs, target)], outs
 
 
 # ----------------------------------------------------------------------------------------------------------

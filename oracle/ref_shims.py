@@ -183,8 +183,11 @@ def install():
     return ns
 
 
-def build_reference(sampling_timesteps=2, dim=64, dim_mults=(1, 2, 4, 8), image_size=512):
-    """Construct UnetRes + ResidualDiffusion exactly as train.py:97-119 does (random init)."""
+def build_reference(sampling_timesteps=2, dim=64, dim_mults=(1, 2, 4, 8), image_size=512, num_unet=1,
+                    objective="pred_res", test_res_or_noise="res", loss_type="l2"):
+    """Construct UnetRes + ResidualDiffusion exactly as train.py:97-119 does (random init); the defaults are the shipped
+    configuration (train.py:78-82), `num_unet=2, objective='pred_res_noise', test_res_or_noise='res_noise'` the
+    commented-out one (train.py:75-77)."""
     import torch
     ns = install()
     cwd = os.getcwd()
@@ -192,12 +195,12 @@ def build_reference(sampling_timesteps=2, dim=64, dim_mults=(1, 2, 4, 8), image_
     try:
         if not os.path.exists("Dose-CLIP.pth"):
             torch.save(ns.DACLIP.CLIPIQA(model_type="clipiqa+").state_dict(), "Dose-CLIP.pth")
-        model = ns.DADiff.UnetRes(dim=dim, dim_mults=dim_mults, num_unet=1, condition=True,
-                                  input_condition=False, objective="pred_res", test_res_or_noise="res")
+        model = ns.DADiff.UnetRes(dim=dim, dim_mults=dim_mults, num_unet=num_unet, condition=True,
+                                  input_condition=False, objective=objective, test_res_or_noise=test_res_or_noise)
         diffusion = ns.DADiff.ResidualDiffusion(
             model, image_size=image_size, timesteps=1000, sampling_timesteps=sampling_timesteps,
-            objective="pred_res", loss_type="l2", condition=True, sum_scale=0.01,
-            input_condition=False, input_condition_mask=False, test_res_or_noise="res")
+            objective=objective, loss_type=loss_type, condition=True, sum_scale=0.01,
+            input_condition=False, input_condition_mask=False, test_res_or_noise=test_res_or_noise)
     finally:
         os.chdir(cwd)
     return ns, model.eval(), diffusion.eval()

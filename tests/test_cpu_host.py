@@ -38,8 +38,17 @@ def test_no_cpu_fallback():
         d.sample([torch.rand(1, 1, 64, 64)], last=True)
     with pytest.raises(RuntimeError):
         m(torch.rand(1, 2, 64, 64), [torch.zeros(1), torch.zeros(1)])
+    m2 = UnetRes(dim=64, num_unet=2, condition=True, objective='pred_res_noise', test_res_or_noise='res_noise')
+    assert m2._eval_plan() == ("pred_res_noise", [(0, 0), (1, 1)])
+    assert any(k.startswith("unet1.") for k in m2.state_dict()) and len(m2.state_dict()) == 2 * len(m.state_dict())
+    d2 = ResidualDiffusion(m2, image_size=64, sampling_timesteps=2, objective='pred_res_noise', condition=True,
+                           test_res_or_noise='res_noise')
+    with pytest.raises(RuntimeError):
+        d2.sample([torch.rand(1, 1, 64, 64)], last=True)
+    with pytest.raises(ValueError):            # the reference cannot run this combination either (src/DADiff.py:824-829)
+        ResidualDiffusion(m, image_size=64, objective='pred_res_noise', condition=True)
     with pytest.raises(NotImplementedError):
-        UnetRes(dim=64, num_unet=2, objective='pred_res_noise')
+        ResidualDiffusion(m, image_size=64, objective='pred_res', condition=False)
     # product code never imports the oracle
     for root, _, files in os.walk(os.path.join(ROOT, "founddiff_b200")):
         for f in files:

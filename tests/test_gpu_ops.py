@@ -371,6 +371,42 @@ def test_sampler_kernels(ops, dt):
     assert torch.allclose(un, (xt + 1) / 2)
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("objective", ["pred_res", "pred_noise", "pred_res_noise", "pred_x0_noise"])
+def test_final_conv_update_objectives(ops, dt, objective):
+    """fd_final_conv_update_obj: every branch of model_predictions (src/DADiff.py:1168-1207) + the shared update line."""
+    g = torch.Generator().manual_seed(19)
+    B, P, C = 2, 333, 64
+    xi, xt, nz = (torch.randn(B, P, generator=g) * 0.5 for _ in range(3))
+    f0, f1 = q(torch.randn(B, P, C, generator=g), dt), q(torch.randn(B, P, C, generator=g), dt)
+    w0, w1 = torch.randn(C, generator=g) / 6, torch.randn(C, generator=g) / 6
+    b0, b1 = torch.randn(1, generator=g) / 4, torch.randn(1, generator=g) / 4
+    coef = torch.tensor([0.7, -0.3, 0.2, 0.05, 0.72, 0.96, 0.28, 0])
+    acs, bcs, om = coef[4], coef[5], coef[6]
+    o0, o1 = f0 @ w0 + b0, f1 @ w1 + b1
+    cl = lambda v: v.clamp(-1, 1)  # noqa: E731
+    if objective == "pred_res":
+        pr = cl(o0); x0 = cl(xi - pr); pn = (xt - xi - (acs - 1) * pr) / bcs  # noqa: E702
+    elif objective == "pred_noise":
+        pn = o0; x0 = cl((xt - acs * xi - bcs * pn) / om); pr = cl(xi - x0)  # noqa: E702
+    elif objective == "pred_res_noise":
+        pr = cl(o0); pn = o1; x0 = cl(xt - acs * pr - bcs * pn)  # noqa: E702
+    else:
+        pr = cl(xi - o0); pn = o1; x0 = cl(o0)  # noqa: E702
+    xn = coef[0] * xt + coef[1] * pr + coef[2] * x0 + coef[3] * nz
+    o = [torch.empty(B, P, device="cuda") for _ in range(4)]
+    two = objective in ("pred_res_noise", "pred_x0_noise")
+    ops.final_conv_update(f0.to("cuda", dt), w0.cuda(), b0.cuda(), xi.cuda(), xt.cuda(), nz.cuda(), coef.cuda(), o[0], o[1], o[2], o[3],
+                          objective=objective, feat1=f1.to("cuda", dt) if two else None, w1=w1.cuda() if two else None,
+                          bias1=b1.cuda() if two else None)
+    for mine, ref in zip(o, (xn, pr, pn, x0)):
+        assert rel(mine, ref) < 2e-5
+    if two:
+        with pytest.raises(Exception):
+            ops.final_conv_update(f0.to("cuda", dt), w0.cuda(), b0.cuda(), xi.cuda(), xt.cuda(), None, coef.cuda(), o[0],
+                                  objective=objective)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # tcgen05 / TMEM / TMA implicit-GEMM path against the CUDA-core path (same inputs, same fused epilogue)
 TC_CASES = [
