@@ -8,8 +8,10 @@ with nn.Modules.  Every function cites the reference lines it follows.  It is PI
 reference itself: `oracle/gen_golden.py` imports the unmodified reference (under `oracle/ref_shims.py`) in the
 build container and stores small input/output fixtures in `tests/golden/`; `tests/test_oracle_golden.py` checks
 this file against them.  The one piece with no reference source is the selective scan (third-party CUDA
-extension, un-vendored and un-pinned; see oracle/selective_scan_ref.c): parity for the scan itself is
-"unpinned" — it is anchored on the published recurrence and an independent fp64 evaluation.
+extension, un-vendored, no version named; see oracle/selective_scan_ref.c).  It is pinned against a BUILD OF THE
+PUBLISHED KERNEL: vLLM 0.22 (in the image) ships the state-spaces/mamba `selective_scan_fwd` CUDA kernel;
+`oracle/gen_golden_scan_vllm.py` ran it on a B200 and `tests/golden/scan_vllm.npz` holds its outputs
+(C restatement vs those: <= 2e-7 rel-L2), next to an independent fp64 evaluation of the recurrence.
 
 The reference's floating-point arithmetic is fp32 throughout (train.py:141 amp=False), so is this.
 `rt(tensor, kind)` ("round-trip") is an optional hook applied wherever the CUDA path stores an activation to

@@ -17,7 +17,7 @@ the reference's outputs.  Fixtures:
   ddim_64x96.npz      ResidualDiffusion.sample, DDIM S=2 and S=5, last=False (all intermediates)
   ancestral_32.npz    p_sample_loop with num_timesteps overridden to 12 (t=11..0), 32x32, last=False
   scan.npz            selective scan: C restatement vs an independent fp64 sequential evaluation of the
-                      published recurrence (parity for the third-party kernel itself is unpinned)
+                      published recurrence (the published KERNEL's outputs: scan_vllm.npz, gen_golden_scan_vllm.py)
 """
 from __future__ import annotations
 

@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY — CPU restatement of the reference's evaluation metrics (src/util.py:188-236).  compute_ssim
-there calls kornia (`get_gaussian_kernel2d((11, 11), (1.5, 1.5))`, `filter2d`), which is NOT installed in this container
-and not vendored by the reference: its published semantics are restated here (normalised 1-D Gaussian outer product;
-`filter2d` = per-channel correlation with 'reflect' border, no kernel normalisation) — SSIM parity is therefore unpinned;
-PSNR / RMSE are plain formulas."""
+there takes two primitives from kornia (`get_gaussian_kernel2d((11, 11), (1.5, 1.5))`, `filter2d`), which is NOT installed in
+this container and not vendored by the reference: their published semantics are restated here (normalised 1-D Gaussian outer
+product; `filter2d` = per-channel correlation with 'reflect' border, no kernel normalisation).  Pinned by
+tests/golden/metrics.npz: the reference's OWN src/util.py functions run here with those two primitives bound to OpenCV's
+independent implementations (oracle/gen_golden_metrics.py); what stays unpinned is kornia's code for the two primitives."""
 import torch
 import torch.nn.functional as F
 

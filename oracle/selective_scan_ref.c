@@ -15,6 +15,10 @@
  * with g = d / (Dtot / G): B and C are shared by the channels of one direction group.
  * All tensors fp32, contiguous, layouts: u,delta,y (Bt, Dtot, L); A (Dtot, N); B,C (Bt, G, N, L).
  *
+ * Pinned (tests/test_oracle_golden.py::test_scan_restatement_vs_published_kernel) against the outputs of a build of the
+ * published kernel itself — vLLM 0.22's `torch.ops._C.selective_scan_fwd`, "adapted from state-spaces/mamba", run on a
+ * B200 by oracle/gen_golden_scan_vllm.py (tests/golden/scan_vllm.npz) — and against an fp64 sequential evaluation.
+ *
  * TEST INFRASTRUCTURE ONLY: used by tests/, smoke() and bench.py's cpu_baseline; never by the product.
  * `acc64 != 0` carries the state in double (used to bound the fp32 restatement's own rounding).
  */
