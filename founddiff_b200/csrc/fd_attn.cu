@@ -242,6 +242,129 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_nhwc_kernel(const T* __restr
     }
 }
 
+// v2 of the same kernel.  ncu/SASS of v1 (profiles/r1_final_ncu_dwconv_nhwc.txt): issue-bound (73 % issue slots, 120 registers) at
+// 570 instructions per 3 rows of which only 216 are FFMA — the rest was 64-bit address arithmetic redone per load (clamp,
+// multiply, LEA), the boundary SELs on every lane and the accumulator resets.  Here: (a) ONE running row pointer advanced by a
+// block-uniform stride (the row clamp becomes a uniform select of 0 / row pitch), (b) warps with no edge column (99 % at
+// W = 512) run a variant with no masks at all, row validity is a block-uniform branch, (c) a finished accumulator slot is
+// re-seeded by the first FMA of the next output row (bias as the addend) instead of being reset.
+constexpr int DW2_RY = 32;     // output rows per block segment (2 halo rows recomputed: 6 %)
+
+template <typename T, bool SILU, bool EDGE, bool BIAS>
+FD_DEVINL void dw_nhwc_rows(const T* __restrict__ in_b, T* __restrict__ out_b, const float (&wr)[9][DW_V],
+                            const float (&bs)[DW_V], int H, long rowe, int C, long fe, int y0, int y1, bool has_l,
+                            bool has_1, bool has_2) {
+    const int ymax = min(H - 1, y1);
+    int yi = y0 - 1;
+    yi -= ((yi % 3) + 3) % 3;                            // round down to a multiple of 3
+    const int offl = (!EDGE || has_l) ? C : 0, off1 = (!EDGE || has_1) ? C : 0, off2 = (!EDGE || has_2) ? 2 * C : 0;
+    const T* p = in_b + (long)min(max(yi, 0), ymax) * rowe + fe;      // row the next fetch reads (clamped into the image)
+    T* q = out_b + (long)(yi - 1) * rowe + fe;                        // output row of the current step (only dereferenced in range)
+    int yf = yi;
+    float acc[3][2][DW_V];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int e = 0; e < DW_V; ++e) acc[r][px][e] = 0.f;
+    uint2 ring[3][4];
+    auto fetch = [&](auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;
+        ring[S][0] = dw_ld_raw<T>(p - offl);
+        ring[S][1] = dw_ld_raw<T>(p);
+        ring[S][2] = dw_ld_raw<T>(p + off1);
+        ring[S][3] = dw_ld_raw<T>(p + off2);
+        p += (yf >= 0 && yf < ymax) ? rowe : 0;          // block-uniform
+        ++yf;
+    };
+    auto step = [&](int yrow, auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;       // == yrow mod 3
+        constexpr int S1 = (S + 1) % 3, S2 = (S + 2) % 3;
+        float v[4][DW_V];
+        {
+            const bool rv = yrow >= 0 && yrow < H;       // block-uniform; straight-line masking keeps the loads in flight
+            const bool ok[4] = {rv && (!EDGE || has_l), rv, rv && (!EDGE || has_1), rv && (!EDGE || has_2)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint2 r = ring[S][j];
+                r.x = ok[j] ? r.x : 0u;
+                r.y = ok[j] ? r.y : 0u;
+                dw_cvt<T>(r, v[j]);
+            }
+        }
+        fetch(slot_c);
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int e = 0; e < DW_V; ++e) {
+                float a1 = BIAS ? fmaf(v[px][e], wr[0][e], bs[e]) : v[px][e] * wr[0][e];   // output row yrow+1: first contribution
+                a1 = fmaf(v[px + 1][e], wr[1][e], a1);
+                acc[S1][px][e] = fmaf(v[px + 2][e], wr[2][e], a1);
+                float a0 = fmaf(v[px][e], wr[3][e], acc[S][px][e]);               // output row yrow
+                a0 = fmaf(v[px + 1][e], wr[4][e], a0);
+                acc[S][px][e] = fmaf(v[px + 2][e], wr[5][e], a0);
+                float a2 = fmaf(v[px][e], wr[6][e], acc[S2][px][e]);              // output row yrow-1 (complete after this)
+                a2 = fmaf(v[px + 1][e], wr[7][e], a2);
+                acc[S2][px][e] = fmaf(v[px + 2][e], wr[8][e], a2);
+            }
+        const int yo = yrow - 1;
+        if (yo >= y0 && yo < y1) {                       // block-uniform
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                if (EDGE && px == 1 && !has_1) continue;
+                float o[DW_V];
+#pragma unroll
+                for (int e = 0; e < DW_V; ++e) o[e] = SILU ? fd_silu(acc[S2][px][e]) : acc[S2][px][e];
+                dw_st<T>(q + (px ? C : 0), o);
+            }
+        }
+        q += rowe;
+    };
+    fetch(std::integral_constant<int, 0>{});
+    fetch(std::integral_constant<int, 1>{});
+    fetch(std::integral_constant<int, 2>{});
+    for (; yi <= y1; yi += 3) {
+        step(yi, std::integral_constant<int, 0>{});
+        if (yi + 1 <= y1) step(yi + 1, std::integral_constant<int, 1>{});
+        if (yi + 2 <= y1) step(yi + 2, std::integral_constant<int, 2>{});
+    }
+}
+
+template <typename T, bool SILU, bool BIAS>
+__global__ void __launch_bounds__(256, 2) dwconv3x3_nhwc_v2_kernel(const T* __restrict__ in, const float* __restrict__ w,
+                                                                   const float* __restrict__ bias, T* __restrict__ out, int H,
+                                                                   int W, int C) {
+    const int NV = C / DW_V;
+    const int W2 = (W + 1) / 2;
+    const long f2 = (long)blockIdx.x * 256 + threadIdx.x;   // index over (pixel pair, vector)
+    const bool live = f2 < (long)W2 * NV;
+    const long f2c = live ? f2 : 0;
+    const int cv = (int)(f2c % NV), x = 2 * (int)(f2c / NV);
+    const int y0 = blockIdx.y * DW2_RY, y1 = min(H, y0 + DW2_RY);
+    float wr[9][DW_V], bs[DW_V];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long)t * C + cv * DW_V));
+        wr[t][0] = wv.x; wr[t][1] = wv.y; wr[t][2] = wv.z; wr[t][3] = wv.w;
+    }
+    if (BIAS) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + cv * DW_V));
+        bs[0] = bv.x; bs[1] = bv.y; bs[2] = bv.z; bs[3] = bv.w;
+    } else {
+        bs[0] = bs[1] = bs[2] = bs[3] = 0.f;
+    }
+    const bool has_l = x > 0, has_1 = x + 1 < W, has_2 = x + 2 < W;
+    const long rowe = (long)W * C;
+    const T* in_b = in + (long)blockIdx.z * H * rowe;
+    T* out_b = out + (long)blockIdx.z * H * rowe;
+    const long fe = (long)x * C + cv * DW_V;
+    const bool edge = !(has_l && has_1 && has_2);
+    if (!live) return;                                   // whole trailing warps only matter for the vote below when partially live
+    if (__any_sync(__activemask(), edge)) dw_nhwc_rows<T, SILU, true, BIAS>(in_b, out_b, wr, bs, H, rowe, C, fe, y0, y1, has_l, has_1, has_2);
+    else dw_nhwc_rows<T, SILU, false, BIAS>(in_b, out_b, wr, bs, H, rowe, C, fe, y0, y1, true, true, true);
+}
+
 constexpr int QK_LD = 40;      // padded row (elements) of the q / k tiles: conflict-free ldmatrix
 constexpr int GR_TILE = 256;   // pixels per staged tile
 constexpr int GR_PIX = 4096;   // pixels per block
@@ -421,6 +544,16 @@ template <typename T>
 static int dwconv_nhwc_launch(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int C, int silu,
                               cudaStream_t stream) {
     const long pairs = (long)((W + 1) / 2) * (C / DW_V);
+    static const bool use_v1 = getenv("FD_DWCONV_V1") != nullptr;      // A/B switch for the measurement scripts
+    if (!use_v1) {
+        dim3 grid((unsigned)fd_cdiv(pairs, 256), (unsigned)fd_cdiv(H, DW2_RY), (unsigned)B);
+        if (silu && bias) dwconv3x3_nhwc_v2_kernel<T, true, true><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
+        else if (silu) dwconv3x3_nhwc_v2_kernel<T, true, false><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
+        else if (bias) dwconv3x3_nhwc_v2_kernel<T, false, true><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
+        else dwconv3x3_nhwc_v2_kernel<T, false, false><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
+        FD_LAUNCH_CHECK();
+        return 0;
+    }
     dim3 grid((unsigned)fd_cdiv(pairs, 256), (unsigned)fd_cdiv(H, DW_RY), (unsigned)B);
     if (silu) dwconv3x3_nhwc_kernel<T, true><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
     else dwconv3x3_nhwc_kernel<T, false><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
