@@ -129,6 +129,39 @@ template <typename T> FD_DEVINL void rw_cvt(uint2 r, float (&v)[4]) {
     }
 }
 
+// write phase of the register-window kernels: 8 lanes x 4 bytes per 16-element run; each k covers the 16 runs of one (channel, k)
+template <typename T>
+FD_DEVINL void rw_write_phase(const T* s_out, T* __restrict__ xs, int b, int c0, int ty0, int tx0, int H, int W, int D,
+                              int word_ok, int tid) {
+    const int H2 = H / 2, W2 = W / 2;
+    const long L = (long)H2 * W2;
+    const int h2_0 = ty0 / 2, w2_0 = tx0 / 2;
+    const int j = tid % 8, r = tid / 8;
+    const uint32_t* s_words = reinterpret_cast<const uint32_t*>(s_out) + r * (RW_RUN / 2) + j;
+    T* gbase = xs + ((long)b * 4 * D + c0) * L + 2 * j;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        long l;
+        int nvalid;
+        bool run_ok;
+        if (k & 1) { run_ok = (w2_0 + r) < W2; l = (long)(w2_0 + r) * H2 + h2_0; nvalid = H2 - h2_0; }
+        else       { run_ok = (h2_0 + r) < H2; l = (long)(h2_0 + r) * W2 + w2_0; nvalid = W2 - w2_0; }
+        if (!run_ok) continue;
+        T* gp = gbase + (long)k * D * L + l;
+        const uint32_t* sp = s_words + k * (RW_KST / 2);
+        if (word_ok && 2 * j + 1 < nvalid) {
+#pragma unroll 8
+            for (int c = 0; c < RW_CH; ++c) *reinterpret_cast<uint32_t*>(gp + c * L) = sp[c * (RW_CST / 2)];
+        } else {
+            for (int c = 0; c < RW_CH; ++c) {
+                const uint32_t wv = sp[c * (RW_CST / 2)];
+                if (2 * j < nvalid) *reinterpret_cast<unsigned short*>(gp + c * L) = (unsigned short)(wv & 0xffffu);
+                if (2 * j + 1 < nvalid) *reinterpret_cast<unsigned short*>(gp + c * L + 1) = (unsigned short)(wv >> 16);
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128, 3) dwconv_scan_rw_kernel(const T* __restrict__ xz, int ld, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, T* __restrict__ xs, int H,
@@ -234,34 +267,127 @@ __global__ void __launch_bounds__(128, 3) dwconv_scan_rw_kernel(const T* __restr
     }
     __syncthreads();
 
-    // write phase: 8 lanes x 4 bytes per 16-element run; iteration `it` covers the 16 runs of one (channel, k)
-    const int H2 = H / 2, W2 = W / 2;
-    const long L = (long)H2 * W2;
-    const int h2_0 = ty0 / 2, w2_0 = tx0 / 2;
-    const int j = tid % 8, r = tid / 8;
-    const uint32_t* s_words = reinterpret_cast<const uint32_t*>(s_out) + r * (RW_RUN / 2) + j;
-    T* gbase = xs + ((long)b * 4 * D + c0) * L + 2 * j;
+    rw_write_phase<T>(s_out, xs, b, c0, ty0, tx0, H, W, D, word_ok, tid);
+}
+
+// v2 of dwconv_scan_rw_kernel (same changes as dwconv3x3_nhwc_v2_kernel, fd_attn.cu): one running row pointer advanced by a
+// block-uniform stride, mask-free variant for warps without an edge column, a finished accumulator slot re-seeded by the
+// first FMA of the next output row.  The step stays straight-line (branches around the consumers made ptxas serialise the
+// prefetch ring: measured 30 % slower).
+template <typename T, bool EDGE>
+FD_DEVINL void rw_conv_phase(const T* __restrict__ base, T* s_thr, const float (&wr)[9][RW_V], const float (&bs)[RW_V], int H,
+                             int W, int ld, int xc, int y0, int y1, int pr, bool has_0, bool has_l, bool has_1, bool has_2) {
+    const int ymax = min(H - 1, y1);
+    int yi = y0 - 1;
+    yi -= ((yi % 3) + 3) % 3;
+    const long rowe = (long)W * ld;
+    const int offl = (!EDGE || has_l) ? ld : 0, off1 = (!EDGE || has_1) ? ld : 0, off2 = (!EDGE || has_2) ? 2 * ld : 0;
+    const T* p = base + (long)min(max(yi, 0), ymax) * rowe + (long)xc * ld;
+    int yf = yi;
+    float acc[3][2][RW_V];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        long l;
-        int nvalid;
-        bool run_ok;
-        if (k & 1) { run_ok = (w2_0 + r) < W2; l = (long)(w2_0 + r) * H2 + h2_0; nvalid = H2 - h2_0; }
-        else       { run_ok = (h2_0 + r) < H2; l = (long)(h2_0 + r) * W2 + w2_0; nvalid = W2 - w2_0; }
-        if (!run_ok) continue;
-        T* gp = gbase + (long)k * D * L + l;
-        const uint32_t* sp = s_words + k * (RW_KST / 2);
-        if (word_ok && 2 * j + 1 < nvalid) {
-#pragma unroll 8
-            for (int c = 0; c < RW_CH; ++c) *reinterpret_cast<uint32_t*>(gp + c * L) = sp[c * (RW_CST / 2)];
-        } else {
-            for (int c = 0; c < RW_CH; ++c) {
-                const uint32_t wv = sp[c * (RW_CST / 2)];
-                if (2 * j < nvalid) *reinterpret_cast<unsigned short*>(gp + c * L) = (unsigned short)(wv & 0xffffu);
-                if (2 * j + 1 < nvalid) *reinterpret_cast<unsigned short*>(gp + c * L + 1) = (unsigned short)(wv >> 16);
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int e = 0; e < RW_V; ++e) acc[r][px][e] = 0.f;
+    uint2 ring[3][4];
+    auto fetch = [&](auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;
+        ring[S][0] = rw_ld_raw<T>(p - offl);
+        ring[S][1] = rw_ld_raw<T>(p);
+        ring[S][2] = rw_ld_raw<T>(p + off1);
+        ring[S][3] = rw_ld_raw<T>(p + off2);
+        p += (yf >= 0 && yf < ymax) ? rowe : 0;          // block-uniform
+        ++yf;
+    };
+    auto step = [&](int yrow, auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;
+        constexpr int S1 = (S + 1) % 3, S2 = (S + 2) % 3;
+        float v[4][RW_V];
+        {
+            const bool rv = yrow >= 0 && yrow < H;
+            const bool ok[4] = {rv && (!EDGE || has_l), rv && (!EDGE || has_0), rv && (!EDGE || has_1), rv && (!EDGE || has_2)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint2 r = ring[S][j];
+                r.x = ok[j] ? r.x : 0u;
+                r.y = ok[j] ? r.y : 0u;
+                rw_cvt<T>(r, v[j]);
             }
         }
+        fetch(slot_c);
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int e = 0; e < RW_V; ++e) {
+                float a1 = fmaf(v[px][e], wr[0][e], bs[e]);                       // output row yrow+1: first contribution
+                a1 = fmaf(v[px + 1][e], wr[1][e], a1);
+                acc[S1][px][e] = fmaf(v[px + 2][e], wr[2][e], a1);
+                float a0 = fmaf(v[px][e], wr[3][e], acc[S][px][e]);               // output row yrow
+                a0 = fmaf(v[px + 1][e], wr[4][e], a0);
+                acc[S][px][e] = fmaf(v[px + 2][e], wr[5][e], a0);
+                float a2 = fmaf(v[px][e], wr[6][e], acc[S2][px][e]);              // output row yrow-1 (complete after this)
+                a2 = fmaf(v[px + 1][e], wr[7][e], a2);
+                acc[S2][px][e] = fmaf(v[px + 2][e], wr[8][e], a2);
+            }
+        const int yo = yrow - 1;
+        if (yo >= y0 && yo < y1) {
+            const int py = yo - y0;
+            // even rows: run = py/2, position = pair; odd rows (column-major directions): run = pair, position = py/2
+            const int off = (py & 1) ? (RW_KST + pr * RW_RUN + (py >> 1)) : ((py >> 1) * RW_RUN + pr);
+#pragma unroll
+            for (int px = 0; px < 2; ++px)
+#pragma unroll
+                for (int e = 0; e < RW_V; ++e)
+                    fd_st(s_thr + e * RW_CST + px * 2 * RW_KST + off, fd_silu16(acc[S2][px][e]));
+        }
+    };
+    fetch(std::integral_constant<int, 0>{});
+    fetch(std::integral_constant<int, 1>{});
+    fetch(std::integral_constant<int, 2>{});
+    for (; yi <= y1; yi += 3) {
+        step(yi, std::integral_constant<int, 0>{});
+        if (yi + 1 <= y1) step(yi + 1, std::integral_constant<int, 1>{});
+        if (yi + 2 <= y1) step(yi + 2, std::integral_constant<int, 2>{});
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128, 3) dwconv_scan_rw2_kernel(const T* __restrict__ xz, int ld, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, T* __restrict__ xs, int H,
+                                                                 int W, int D, int word_ok) {
+    static_assert(sizeof(T) == 2, "16-bit storage only");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_out = reinterpret_cast<T*>(smem_raw);                              // [RW_CH][RW_CST]
+    float* s_w = reinterpret_cast<float*>(s_out + RW_CH * RW_CST);          // [RW_CH*9] + [RW_CH]
+    const int c0 = blockIdx.x * RW_CH;
+    const int tiles_w = (W + RW_TS - 1) / RW_TS;
+    const int ty0 = (blockIdx.y / tiles_w) * RW_TS, tx0 = (blockIdx.y % tiles_w) * RW_TS;
+    const int b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int cv = tid % (RW_CH / RW_V), pr = tid / (RW_CH / RW_V);         // channel vector, pixel pair
+    const int x = tx0 + 2 * pr;
+    for (int i = tid; i < RW_CH * 10; i += 128)
+        s_w[i] = i < RW_CH * 9 ? w[(long)c0 * 9 + i] : (bias ? bias[c0 + i - RW_CH * 9] : 0.f);
+    __syncthreads();
+    float wr[9][RW_V], bs[RW_V];
+#pragma unroll
+    for (int e = 0; e < RW_V; ++e) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wr[t][e] = s_w[(cv * RW_V + e) * 9 + t];
+        bs[e] = s_w[RW_CH * 9 + cv * RW_V + e];
+    }
+    const int y0 = ty0, y1 = min(H, ty0 + RW_TS);
+    const bool has_0 = x < W, has_l = has_0 && x > 0, has_1 = x + 1 < W, has_2 = x + 2 < W;
+    const int xc = min(x, W - 1);
+    const T* base = xz + (long)b * H * W * ld + c0 + cv * RW_V;
+    T* s_thr = s_out + cv * RW_V * RW_CST;
+    const bool edge = !(has_0 && has_l && has_1 && has_2);
+    if (__any_sync(0xffffffffu, edge)) rw_conv_phase<T, true>(base, s_thr, wr, bs, H, W, ld, xc, y0, y1, pr, has_0, has_l, has_1, has_2);
+    else rw_conv_phase<T, false>(base, s_thr, wr, bs, H, W, ld, xc, y0, y1, pr, true, true, true, true);
+    __syncthreads();
+    rw_write_phase<T>(s_out, xs, b, c0, ty0, tx0, H, W, D, word_ok, tid);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -764,23 +890,23 @@ extern "C" int fd_dwconv3x3_silu_scan(const void* xz, int ld, const float* w, co
         dim3 grid(D / RW_CH, fd_cdiv(H, RW_TS) * fd_cdiv(W, RW_TS), B);
         const int word_ok = ((H / 2) % 2 == 0) && ((W / 2) % 2 == 0);
         const size_t smem = (size_t)RW_CH * RW_CST * 2 + RW_CH * 10 * sizeof(float);
+        static const bool use_v1 = getenv("FD_DWCONV_V1") != nullptr;      // A/B switch for the measurement scripts
+#define FD_RW_LAUNCH(KERNEL, TT)                                                                                      \
+    {                                                                                                                 \
+        static bool attr_set = false;                                                                                 \
+        if (!attr_set) {                                                                                              \
+            cudaError_t e = cudaFuncSetAttribute(KERNEL<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                                                      \
+            attr_set = true;                                                                                          \
+        }                                                                                                             \
+        KERNEL<TT><<<grid, 128, smem, stream>>>((const TT*)xz, ld, w, bias, (TT*)xs, H, W, D, word_ok);               \
+    }
         if (dtype == FD_BF16) {
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaError_t e = cudaFuncSetAttribute(dwconv_scan_rw_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return (int)e;
-                attr_set = true;
-            }
-            dwconv_scan_rw_kernel<__nv_bfloat16><<<grid, 128, smem, stream>>>((const __nv_bfloat16*)xz, ld, w, bias, (__nv_bfloat16*)xs, H, W, D, word_ok);
+            if (use_v1) FD_RW_LAUNCH(dwconv_scan_rw_kernel, __nv_bfloat16) else FD_RW_LAUNCH(dwconv_scan_rw2_kernel, __nv_bfloat16)
         } else {
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaError_t e = cudaFuncSetAttribute(dwconv_scan_rw_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (e != cudaSuccess) return (int)e;
-                attr_set = true;
-            }
-            dwconv_scan_rw_kernel<__half><<<grid, 128, smem, stream>>>((const __half*)xz, ld, w, bias, (__half*)xs, H, W, D, word_ok);
+            if (use_v1) FD_RW_LAUNCH(dwconv_scan_rw_kernel, __half) else FD_RW_LAUNCH(dwconv_scan_rw2_kernel, __half)
         }
+#undef FD_RW_LAUNCH
         FD_LAUNCH_CHECK();
         return 0;
     }
