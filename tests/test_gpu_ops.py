@@ -304,6 +304,36 @@ def test_xdt_proj(ops, cfg, dt):
         assert rel(dts2, dts_r) < 2 * wt and rel(Bs2, Bs_r) < wt and rel(Cs2, Cs_r) < wt
 
 
+@pytest.mark.parametrize("cfg", [(8, 64, 4, 4, 8192), (16, 32, 4, 8, 3336), (8, 128, 8, 16, 6664)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_xdt_proj_tc_long_ragged_rows(ops, cfg, dt, monkeypatch):
+    """Long rows whose length is not a multiple of the 128-step tile, with the time-major / softplus epilogues; run with the
+    optional persistent tile walk (FD_XDT_PERSIST, cp.async ring continuous across tiles) switched on."""
+    monkeypatch.setenv("FD_XDT_PERSIST", "1")
+    B, D, R, N, L = cfg
+    g = torch.Generator().manual_seed(D + L)
+    xs = q(torch.randn(B, 4, D, L, generator=g), dt)
+    Wx = torch.randn(4, R + 2 * N, D, generator=g) / math.sqrt(D)
+    Wdt = torch.randn(4, D, R, generator=g) / math.sqrt(R)
+    bias = torch.randn(4 * D, generator=g)
+    xw16, dw16, Rp = ops.pack_xdt_weights(Wx.cuda(), Wdt.cuda(), dt)
+    x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, q(Wx, dt))
+    dts_r, Bs_r, Cs_r = torch.split(x_dbl, [R, N, N], dim=2)
+    dts_r = torch.einsum("bkrl,kdr->bkdl", q(dts_r, dt), q(Wdt, dt))
+    dts = torch.zeros(B, 4, D, L, device="cuda", dtype=dt)
+    Bs, Cs = torch.zeros(B, 4, N, L, device="cuda"), torch.zeros(B, 4, N, L, device="cuda")
+    ops.xdt_proj_tc(xs.to("cuda", dt), xw16, dw16, Rp, dts, Bs, Cs, B, D, L, R, N)
+    wt = 1e-2 if dt == torch.bfloat16 else 2e-3
+    assert rel(dts, dts_r) < wt and rel(Bs, Bs_r) < 1e-4 and rel(Cs, Cs_r) < 1e-4
+    dts2 = torch.zeros_like(dts)
+    Bt, Ct = torch.zeros(B, 4, L, N, device="cuda"), torch.zeros(B, 4, L, N, device="cuda")
+    ops.xdt_proj_tc(xs.to("cuda", dt), xw16, dw16, Rp, dts2, Bt, Ct, B, D, L, R, N, time_major=True, dt_bias=bias.cuda(),
+                    delta_softplus=True)
+    assert rel(Bt.transpose(2, 3), Bs_r) < 1e-4 and rel(Ct.transpose(2, 3), Cs_r) < 1e-4
+    ref_sp = F.softplus(dts_r + bias.view(1, 4, D, 1), threshold=20.0)
+    assert rel(dts2, ref_sp) < wt
+
+
 @pytest.mark.parametrize("C", [64, 128])
 @pytest.mark.parametrize("hw", [(16, 24), (8, 40), (16, 32), (72, 64)])
 @pytest.mark.parametrize("dt", DTYPES)
