@@ -636,20 +636,14 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
     T* s_o = s_xd + 32 * XT_XLD;                                 // WITH_DT: [8 warps][16][XT_XLD] output staging
     constexpr int CCp = MT * 16;
     const int bk = blockIdx.y, k = bk & 3;
-    // The block walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... of its (batch, direction) row with the cp.async ring running
-    // continuously across them.  The launcher uses one tile per block (gridDim.x = number of tiles) — see xdt_mma_launch.
-    const int ntiles = (L + XT_L - 1) / XT_L;
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int l0 = blockIdx.x * XT_L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const T* xr = xs + (long)bk * D * L;
     const T* wx = xw16 + (long)k * CCp * D;
     const int nchunks = D / XT_KC;
 
-    const int total_chunks = my_tiles * nchunks;
-    auto stage = [&](int gc, int buf) {
-        const int ti = gc / nchunks, ch = gc - ti * nchunks;
-        const int l0 = ((int)blockIdx.x + ti * (int)gridDim.x) * XT_L;
+    auto stage = [&](int ch, int buf) {
         const int d0 = ch * XT_KC;
         T* sx = s_x + buf * XT_KC * XT_XLD;
         T* sw = s_w + buf * CCp * XT_WLD;
@@ -664,14 +658,6 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
         }
     };
 
-#pragma unroll
-    for (int s = 0; s < XP_STAGES - 1; ++s) {
-        if (s < total_chunks) stage(s, s);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    int gc = 0;
-  for (int ti = 0; ti < my_tiles; ++ti) {
-    const int l0 = ((int)blockIdx.x + ti * (int)gridDim.x) * XT_L;
     float acc[MT][2][4];
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt)
@@ -679,13 +665,19 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
-    for (int ch = 0; ch < nchunks; ++ch, ++gc) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(XP_STAGES - 2) : "memory");
-        __syncthreads();                                          // chunk gc landed; everyone is done with chunk gc-1's buffer
-        if (gc + XP_STAGES - 1 < total_chunks) stage(gc + XP_STAGES - 1, (gc + XP_STAGES - 1) % XP_STAGES);
+
+#pragma unroll
+    for (int s = 0; s < XP_STAGES - 1; ++s) {
+        if (s < nchunks) stage(s, s);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        const T* sx = s_x + (gc % XP_STAGES) * XT_KC * XT_XLD;
-        const T* sw = s_w + (gc % XP_STAGES) * CCp * XT_WLD;
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(XP_STAGES - 2) : "memory");
+        __syncthreads();                                          // chunk ch landed; everyone is done with chunk ch-1's buffer
+        if (ch + XP_STAGES - 1 < nchunks) stage(ch + XP_STAGES - 1, (ch + XP_STAGES - 1) % XP_STAGES);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const T* sx = s_x + (ch % XP_STAGES) * XT_KC * XT_XLD;
+        const T* sw = s_w + (ch % XP_STAGES) * CCp * XT_WLD;
 #pragma unroll
         for (int ks = 0; ks < XT_KC / 16; ++ks) {
             uint32_t bfr[4];
@@ -801,7 +793,6 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
             }
         }
     }
-  }   // tile loop
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -966,13 +957,6 @@ static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, vo
     const int CC = R + 2 * N;
     const int MT = (CC + 15) / 16;
     dim3 grid(fd_cdiv(L, XT_L), B * 4);
-    const dim3 grid_np = grid;
-    {   // optional (FD_XDT_PERSIST=1): persistent over l tiles, ~3 resident blocks per SM in one wave.  MEASURED SLOWER than one
-        // tile per block (702 vs 612 us at 16x128x65536): three co-resident blocks in different phases already overlap one
-        // block's epilogue with another's loads, and the hardware block scheduler balances better than a fixed tile walk.
-        const int tiles = fd_cdiv(L, XT_L), gx = (148 * 3) / (B * 4);
-        if (gx >= 1 && tiles >= 4 * gx && getenv("FD_XDT_PERSIST")) grid.x = gx;
-    }
     if (D % XT_KC == 0 && L % 8 == 0 && !getenv("FD_XDT_NO_PIPE")) {       // pipelined stage 1 (cp.async ring)
 #define XDT_PIPE_CASE(M)                                                                                                       \
     if (MT == M) {                                                                                                             \
@@ -1001,7 +985,7 @@ static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, vo
             if (e != cudaSuccess) return (int)e;                                                                               \
             attr_set = true;                                                                                                   \
         }                                                                                                                      \
-        xdt_proj_mma_kernel<T, M><<<grid_np, 256, smem, stream>>>((const T*)xs, (const T*)xw16, (const T*)dw16, (T*)dts, Bs, Cs, D, L, \
+        xdt_proj_mma_kernel<T, M><<<grid, 256, smem, stream>>>((const T*)xs, (const T*)xw16, (const T*)dw16, (T*)dts, Bs, Cs, D, L, \
                                                                 R, N, Rp);                                                      \
         FD_LAUNCH_CHECK();                                                                                                     \
         return 0;                                                                                                              \

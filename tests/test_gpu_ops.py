@@ -306,10 +306,8 @@ def test_xdt_proj(ops, cfg, dt):
 
 @pytest.mark.parametrize("cfg", [(8, 64, 4, 4, 8192), (16, 32, 4, 8, 3336), (8, 128, 8, 16, 6664)])
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
-def test_xdt_proj_tc_long_ragged_rows(ops, cfg, dt, monkeypatch):
-    """Long rows whose length is not a multiple of the 128-step tile, with the time-major / softplus epilogues; run with the
-    optional persistent tile walk (FD_XDT_PERSIST, cp.async ring continuous across tiles) switched on."""
-    monkeypatch.setenv("FD_XDT_PERSIST", "1")
+def test_xdt_proj_tc_long_ragged_rows(ops, cfg, dt):
+    """Long rows whose length is not a multiple of the 128-step tile, with the time-major / softplus epilogues."""
     B, D, R, N, L = cfg
     g = torch.Generator().manual_seed(D + L)
     xs = q(torch.randn(B, 4, D, L, generator=g), dt)
