@@ -253,7 +253,7 @@ constexpr int DW2_RY = 32;     // output rows per block segment (2 halo rows rec
 template <typename T, bool SILU, bool EDGE, bool BIAS>
 FD_DEVINL void dw_nhwc_rows(const T* __restrict__ in_b, T* __restrict__ out_b, const float (&wr)[9][DW_V],
                             const float (&bs)[DW_V], int H, long rowe, int C, long fe, int y0, int y1, bool has_l,
-                            bool has_1, bool has_2) {
+                            bool has_1, bool has_2, int pf) {
     const int ymax = min(H - 1, y1);
     int yi = y0 - 1;
     yi -= ((yi % 3) + 3) % 3;                            // round down to a multiple of 3
@@ -275,6 +275,11 @@ FD_DEVINL void dw_nhwc_rows(const T* __restrict__ in_b, T* __restrict__ out_b, c
         ring[S][1] = dw_ld_raw<T>(p);
         ring[S][2] = dw_ld_raw<T>(p + off1);
         ring[S][3] = dw_ld_raw<T>(p + off2);
+        if (pf > 0 && yf >= 0 && yf + pf <= ymax) {      // block-uniform: pull the row `pf` steps further down into L2
+            const T* pp = p + (long)pf * rowe;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + off1));
+        }
         p += (yf >= 0 && yf < ymax) ? rowe : 0;          // block-uniform
         ++yf;
     };
@@ -334,7 +339,7 @@ FD_DEVINL void dw_nhwc_rows(const T* __restrict__ in_b, T* __restrict__ out_b, c
 template <typename T, bool SILU, bool BIAS>
 __global__ void __launch_bounds__(256, 2) dwconv3x3_nhwc_v2_kernel(const T* __restrict__ in, const float* __restrict__ w,
                                                                    const float* __restrict__ bias, T* __restrict__ out, int H,
-                                                                   int W, int C) {
+                                                                   int W, int C, int pf) {
     const int NV = C / DW_V;
     const int W2 = (W + 1) / 2;
     const long f2 = (long)blockIdx.x * 256 + threadIdx.x;   // index over (pixel pair, vector)
@@ -361,8 +366,8 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_nhwc_v2_kernel(const T* __re
     const long fe = (long)x * C + cv * DW_V;
     const bool edge = !(has_l && has_1 && has_2);
     if (!live) return;                                   // whole trailing warps only matter for the vote below when partially live
-    if (__any_sync(__activemask(), edge)) dw_nhwc_rows<T, SILU, true, BIAS>(in_b, out_b, wr, bs, H, rowe, C, fe, y0, y1, has_l, has_1, has_2);
-    else dw_nhwc_rows<T, SILU, false, BIAS>(in_b, out_b, wr, bs, H, rowe, C, fe, y0, y1, true, true, true);
+    if (__any_sync(__activemask(), edge)) dw_nhwc_rows<T, SILU, true, BIAS>(in_b, out_b, wr, bs, H, rowe, C, fe, y0, y1, has_l, has_1, has_2, pf);
+    else dw_nhwc_rows<T, SILU, false, BIAS>(in_b, out_b, wr, bs, H, rowe, C, fe, y0, y1, true, true, true, pf);
 }
 
 constexpr int QK_LD = 40;      // padded row (elements) of the q / k tiles: conflict-free ldmatrix
@@ -546,11 +551,12 @@ static int dwconv_nhwc_launch(const void* in, const float* w, const float* bias,
     const long pairs = (long)((W + 1) / 2) * (C / DW_V);
     static const bool use_v1 = getenv("FD_DWCONV_V1") != nullptr;      // A/B switch for the measurement scripts
     if (!use_v1) {
+        static const int pf = getenv("FD_DWCONV_PF") ? atoi(getenv("FD_DWCONV_PF")) : 4;     // L2 prefetch distance in rows (0 = off): 700 -> 632 us
         dim3 grid((unsigned)fd_cdiv(pairs, 256), (unsigned)fd_cdiv(H, DW2_RY), (unsigned)B);
-        if (silu && bias) dwconv3x3_nhwc_v2_kernel<T, true, true><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
-        else if (silu) dwconv3x3_nhwc_v2_kernel<T, true, false><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
-        else if (bias) dwconv3x3_nhwc_v2_kernel<T, false, true><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
-        else dwconv3x3_nhwc_v2_kernel<T, false, false><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C);
+        if (silu && bias) dwconv3x3_nhwc_v2_kernel<T, true, true><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C, pf);
+        else if (silu) dwconv3x3_nhwc_v2_kernel<T, true, false><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C, pf);
+        else if (bias) dwconv3x3_nhwc_v2_kernel<T, false, true><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C, pf);
+        else dwconv3x3_nhwc_v2_kernel<T, false, false><<<grid, 256, 0, stream>>>((const T*)in, w, bias, (T*)out, H, W, C, pf);
         FD_LAUNCH_CHECK();
         return 0;
     }

@@ -276,7 +276,8 @@ __global__ void __launch_bounds__(128, 3) dwconv_scan_rw_kernel(const T* __restr
 // prefetch ring: measured 30 % slower).
 template <typename T, bool EDGE>
 FD_DEVINL void rw_conv_phase(const T* __restrict__ base, T* s_thr, const float (&wr)[9][RW_V], const float (&bs)[RW_V], int H,
-                             int W, int ld, int xc, int y0, int y1, int pr, bool has_0, bool has_l, bool has_1, bool has_2) {
+                             int W, int ld, int xc, int y0, int y1, int pr, bool has_0, bool has_l, bool has_1, bool has_2,
+                             int pf) {
     const int ymax = min(H - 1, y1);
     int yi = y0 - 1;
     yi -= ((yi % 3) + 3) % 3;
@@ -298,6 +299,11 @@ FD_DEVINL void rw_conv_phase(const T* __restrict__ base, T* s_thr, const float (
         ring[S][1] = rw_ld_raw<T>(p);
         ring[S][2] = rw_ld_raw<T>(p + off1);
         ring[S][3] = rw_ld_raw<T>(p + off2);
+        if (pf > 0 && yf >= 0 && yf + pf <= ymax) {      // block-uniform: pull the row `pf` steps further down into L2
+            const T* pp = p + (long)pf * rowe;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + off1));
+        }
         p += (yf >= 0 && yf < ymax) ? rowe : 0;          // block-uniform
         ++yf;
     };
@@ -356,7 +362,7 @@ FD_DEVINL void rw_conv_phase(const T* __restrict__ base, T* s_thr, const float (
 template <typename T>
 __global__ void __launch_bounds__(128, 3) dwconv_scan_rw2_kernel(const T* __restrict__ xz, int ld, const float* __restrict__ w,
                                                                  const float* __restrict__ bias, T* __restrict__ xs, int H,
-                                                                 int W, int D, int word_ok) {
+                                                                 int W, int D, int word_ok, int pf) {
     static_assert(sizeof(T) == 2, "16-bit storage only");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_out = reinterpret_cast<T*>(smem_raw);                              // [RW_CH][RW_CST]
@@ -384,8 +390,8 @@ __global__ void __launch_bounds__(128, 3) dwconv_scan_rw2_kernel(const T* __rest
     const T* base = xz + (long)b * H * W * ld + c0 + cv * RW_V;
     T* s_thr = s_out + cv * RW_V * RW_CST;
     const bool edge = !(has_0 && has_l && has_1 && has_2);
-    if (__any_sync(0xffffffffu, edge)) rw_conv_phase<T, true>(base, s_thr, wr, bs, H, W, ld, xc, y0, y1, pr, has_0, has_l, has_1, has_2);
-    else rw_conv_phase<T, false>(base, s_thr, wr, bs, H, W, ld, xc, y0, y1, pr, true, true, true, true);
+    if (__any_sync(0xffffffffu, edge)) rw_conv_phase<T, true>(base, s_thr, wr, bs, H, W, ld, xc, y0, y1, pr, has_0, has_l, has_1, has_2, pf);
+    else rw_conv_phase<T, false>(base, s_thr, wr, bs, H, W, ld, xc, y0, y1, pr, true, true, true, true, pf);
     __syncthreads();
     rw_write_phase<T>(s_out, xs, b, c0, ty0, tx0, H, W, D, word_ok, tid);
 }
@@ -605,6 +611,7 @@ __global__ void __launch_bounds__(256) xdt_proj_mma_kernel(const T* __restrict__
 // itself (R FMAs per step), so the (B, 4, D, L) delta tensor is never written or read: the op becomes a single
 // streaming pass over xs.  128-step tiles, 8 warps x 16 columns, 32-channel chunks through a 3-stage cp.async ring.
 constexpr int XP_STAGES = 3;
+constexpr int XO_LD = 64 + 8;      // padded row of the per-warp dt staging tile (half an l tile): 3 blocks per SM up to MT = 5
 FD_DEVINL float xp_softplus(float x) {      // same branch-free 2-MUFU form as the scan kernel's (fd_scan.cu)
     float y, lg;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
@@ -623,7 +630,7 @@ FD_DEVINL void xp_cp_async16(void* smem_dst, const void* gsrc, bool valid) {
 // WITH_DT = true is the pipelined form of xdt_proj_mma_kernel: B / C rows go to Bs / Cs, the R dt rows stay in shared
 // memory (16-bit) and the second GEMM (dt_proj, K = Rp) produces the (B, 4, D, L) delta tensor.
 template <typename T, int MT, bool WITH_DT>
-__global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ xs, const T* __restrict__ xw16,
+__global__ void __launch_bounds__(256, 3) x_proj_mma_kernel(const T* __restrict__ xs, const T* __restrict__ xw16,
                                                          float* __restrict__ xdbl, int D, int L, int CC,
                                                          const T* __restrict__ dw16 = nullptr, T* __restrict__ dts = nullptr,
                                                          float* __restrict__ Bs = nullptr, float* __restrict__ Cs = nullptr,
@@ -633,7 +640,7 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
     T* s_x = reinterpret_cast<T*>(smem_raw);                     // [XP_STAGES][XT_KC][XT_XLD]
     T* s_w = s_x + XP_STAGES * XT_KC * XT_XLD;                   // [XP_STAGES][MT*16][XT_WLD]
     T* s_xd = s_w + XP_STAGES * MT * 16 * XT_WLD;                // WITH_DT: [32][XT_XLD] first Rp rows of X_dbl
-    T* s_o = s_xd + 32 * XT_XLD;                                 // WITH_DT: [8 warps][16][XT_XLD] output staging
+    T* s_o = s_xd + 32 * XT_XLD;                                 // WITH_DT: [8 warps][16][XO_LD] output staging (one 64-l half)
     constexpr int CCp = MT * 16;
     const int bk = blockIdx.y, k = bk & 3;
     const int l0 = blockIdx.x * XT_L;
@@ -735,61 +742,70 @@ __global__ void __launch_bounds__(256) x_proj_mma_kernel(const T* __restrict__ x
         __syncthreads();
         // stage 2: each warp takes m-tiles (16 channels d) round-robin, all 128 l
         const T* wd = dw16 + (long)k * D * Rp;
-        T* so = s_o + warp * 16 * XT_XLD;
+        T* so = s_o + warp * 16 * XO_LD;
         T* dr = dts + (long)bk * D * L;
         for (int mtile = warp; mtile * 16 < D; mtile += 8) {
             const int dbase = mtile * 16;
-            float o[16][4];
-#pragma unroll
-            for (int nt = 0; nt < 16; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
-            for (int ks = 0; ks < Rp / 16; ++ks) {
-                uint32_t afr[4];
-                const T* w0 = wd + (long)(dbase + g) * Rp + ks * 16 + 2 * t4;
-                const T* w1 = wd + (long)(dbase + g + 8) * Rp + ks * 16 + 2 * t4;
-                afr[0] = *reinterpret_cast<const uint32_t*>(w0);
-                afr[1] = *reinterpret_cast<const uint32_t*>(w1);
-                afr[2] = *reinterpret_cast<const uint32_t*>(w0 + 8);
-                afr[3] = *reinterpret_cast<const uint32_t*>(w1 + 8);
-#pragma unroll
-                for (int np = 0; np < 8; ++np) {
-                    uint32_t bfr[4];
-                    ldmatrix_x4_trans(bfr, s_xd + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * XT_XLD + np * 16 + 8 * (lane >> 4));
-                    mma_16816<T>(o[2 * np], afr, bfr[0], bfr[1]);
-                    mma_16816<T>(o[2 * np + 1], afr, bfr[2], bfr[3]);
-                }
-            }
+            float b0 = 0.f, b1 = 0.f;
             if (dt_bias) {          // delta = softplus(dt_proj(...) + dt_bias) finished here: the scan (issue-bound) gets final values
-                const float b0 = dbase + g < D ? __ldg(dt_bias + (long)k * D + dbase + g) : 0.f;
-                const float b1 = dbase + g + 8 < D ? __ldg(dt_bias + (long)k * D + dbase + g + 8) : 0.f;
+                b0 = dbase + g < D ? __ldg(dt_bias + (long)k * D + dbase + g) : 0.f;
+                b1 = dbase + g + 8 < D ? __ldg(dt_bias + (long)k * D + dbase + g + 8) : 0.f;
+            }
+            __syncwarp();
+            // two halves of 64 l each: 32 accumulators live instead of 64 keeps the kernel at 3 blocks per SM (ncu: 128
+            // registers -> 2 blocks, 24 % warps active, issue 40 %, top stalls wait / long_scoreboard / barrier)
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                float o[8][4];
 #pragma unroll
-                for (int nt = 0; nt < 16; ++nt) {
-                    o[nt][0] += b0; o[nt][1] += b0; o[nt][2] += b1; o[nt][3] += b1;
-                    if (dt_softplus) {
+                for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) o[nt][e] = xp_softplus(o[nt][e]);
+                    for (int e = 0; e < 4; ++e) o[nt][e] = 0.f;
+                for (int ks = 0; ks < Rp / 16; ++ks) {
+                    uint32_t afr[4];
+                    const T* w0 = wd + (long)(dbase + g) * Rp + ks * 16 + 2 * t4;
+                    const T* w1 = wd + (long)(dbase + g + 8) * Rp + ks * 16 + 2 * t4;
+                    afr[0] = *reinterpret_cast<const uint32_t*>(w0);
+                    afr[1] = *reinterpret_cast<const uint32_t*>(w1);
+                    afr[2] = *reinterpret_cast<const uint32_t*>(w0 + 8);
+                    afr[3] = *reinterpret_cast<const uint32_t*>(w1 + 8);
+#pragma unroll
+                    for (int np = 0; np < 4; ++np) {
+                        uint32_t bfr[4];
+                        ldmatrix_x4_trans(bfr, s_xd + (ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * XT_XLD + (half * 4 + np) * 16 + 8 * (lane >> 4));
+                        mma_16816<T>(o[2 * np], afr, bfr[0], bfr[1]);
+                        mma_16816<T>(o[2 * np + 1], afr, bfr[2], bfr[3]);
                     }
                 }
-            }
-            __syncwarp();
+                if (dt_bias) {
 #pragma unroll
-            for (int nt = 0; nt < 16; ++nt) {
-                const int col = nt * 8 + 2 * t4;
-                if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-                    *reinterpret_cast<__nv_bfloat162*>(so + g * XT_XLD + col) = __floats2bfloat162_rn(o[nt][0], o[nt][1]);
-                    *reinterpret_cast<__nv_bfloat162*>(so + (g + 8) * XT_XLD + col) = __floats2bfloat162_rn(o[nt][2], o[nt][3]);
-                } else {
-                    *reinterpret_cast<__half2*>(so + g * XT_XLD + col) = fd_floats2half2_sat(o[nt][0], o[nt][1]);
-                    *reinterpret_cast<__half2*>(so + (g + 8) * XT_XLD + col) = fd_floats2half2_sat(o[nt][2], o[nt][3]);
+                    for (int nt = 0; nt < 8; ++nt) {
+                        o[nt][0] += b0; o[nt][1] += b0; o[nt][2] += b1; o[nt][3] += b1;
+                        if (dt_softplus) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) o[nt][e] = xp_softplus(o[nt][e]);
+                        }
+                    }
                 }
-            }
-            __syncwarp();
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {       // 16 rows x 256 B: lanes write 16-byte chunks, two rows per instruction
-                const int r = it * 2 + (lane >> 4), v = lane & 15;
-                if (dbase + r < D && l0 + v * 8 < L)
-                    *reinterpret_cast<uint4*>(dr + (long)(dbase + r) * L + l0 + v * 8) = *reinterpret_cast<const uint4*>(so + r * XT_XLD + v * 8);
+                for (int nt = 0; nt < 8; ++nt) {
+                    const int col = nt * 8 + 2 * t4;
+                    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                        *reinterpret_cast<__nv_bfloat162*>(so + g * XO_LD + col) = __floats2bfloat162_rn(o[nt][0], o[nt][1]);
+                        *reinterpret_cast<__nv_bfloat162*>(so + (g + 8) * XO_LD + col) = __floats2bfloat162_rn(o[nt][2], o[nt][3]);
+                    } else {
+                        *reinterpret_cast<__half2*>(so + g * XO_LD + col) = fd_floats2half2_sat(o[nt][0], o[nt][1]);
+                        *reinterpret_cast<__half2*>(so + (g + 8) * XO_LD + col) = fd_floats2half2_sat(o[nt][2], o[nt][3]);
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {   // 16 rows x 128 B: lanes write 16-byte chunks, four rows per instruction
+                    const int r = it * 4 + (lane >> 3), v = lane & 7, lc = l0 + half * 64 + v * 8;
+                    if (dbase + r < D && lc < L)
+                        *reinterpret_cast<uint4*>(dr + (long)(dbase + r) * L + lc) = *reinterpret_cast<const uint4*>(so + r * XO_LD + v * 8);
+                }
+                __syncwarp();
             }
         }
     }
@@ -891,7 +907,8 @@ extern "C" int fd_dwconv3x3_silu_scan(const void* xz, int ld, const float* w, co
         const int word_ok = ((H / 2) % 2 == 0) && ((W / 2) % 2 == 0);
         const size_t smem = (size_t)RW_CH * RW_CST * 2 + RW_CH * 10 * sizeof(float);
         static const bool use_v1 = getenv("FD_DWCONV_V1") != nullptr;      // A/B switch for the measurement scripts
-#define FD_RW_LAUNCH(KERNEL, TT)                                                                                      \
+        static const int pf = getenv("FD_DWCONV_PF") ? atoi(getenv("FD_DWCONV_PF")) : 4;     // L2 prefetch distance in rows (0 = off)
+#define FD_RW_LAUNCH(KERNEL, TT, ...)                                                                                 \
     {                                                                                                                 \
         static bool attr_set = false;                                                                                 \
         if (!attr_set) {                                                                                              \
@@ -899,12 +916,12 @@ extern "C" int fd_dwconv3x3_silu_scan(const void* xz, int ld, const float* w, co
             if (e != cudaSuccess) return (int)e;                                                                      \
             attr_set = true;                                                                                          \
         }                                                                                                             \
-        KERNEL<TT><<<grid, 128, smem, stream>>>((const TT*)xz, ld, w, bias, (TT*)xs, H, W, D, word_ok);               \
+        KERNEL<TT><<<grid, 128, smem, stream>>>((const TT*)xz, ld, w, bias, (TT*)xs, H, W, D, word_ok __VA_ARGS__);   \
     }
         if (dtype == FD_BF16) {
-            if (use_v1) FD_RW_LAUNCH(dwconv_scan_rw_kernel, __nv_bfloat16) else FD_RW_LAUNCH(dwconv_scan_rw2_kernel, __nv_bfloat16)
+            if (use_v1) FD_RW_LAUNCH(dwconv_scan_rw_kernel, __nv_bfloat16) else FD_RW_LAUNCH(dwconv_scan_rw2_kernel, __nv_bfloat16, , pf)
         } else {
-            if (use_v1) FD_RW_LAUNCH(dwconv_scan_rw_kernel, __half) else FD_RW_LAUNCH(dwconv_scan_rw2_kernel, __half)
+            if (use_v1) FD_RW_LAUNCH(dwconv_scan_rw_kernel, __half) else FD_RW_LAUNCH(dwconv_scan_rw2_kernel, __half, , pf)
         }
 #undef FD_RW_LAUNCH
         FD_LAUNCH_CHECK();
@@ -960,7 +977,7 @@ static int xdt_mma_launch(const void* xs, const void* xw16, const void* dw16, vo
     if (D % XT_KC == 0 && L % 8 == 0 && !getenv("FD_XDT_NO_PIPE")) {       // pipelined stage 1 (cp.async ring)
 #define XDT_PIPE_CASE(M)                                                                                                       \
     if (MT == M) {                                                                                                             \
-        const size_t smem = ((size_t)XP_STAGES * ((size_t)XT_KC * XT_XLD + (size_t)M * 16 * XT_WLD) + 32 * XT_XLD + 8 * 16 * XT_XLD) * sizeof(T); \
+        const size_t smem = ((size_t)XP_STAGES * ((size_t)XT_KC * XT_XLD + (size_t)M * 16 * XT_WLD) + 32 * XT_XLD + 8 * 16 * XO_LD) * sizeof(T); \
         static bool attr_set = false;                                                                                          \
         if (!attr_set) {                                                                                                       \
             cudaError_t e = cudaFuncSetAttribute(x_proj_mma_kernel<T, M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
