@@ -81,58 +81,72 @@ __global__ void __launch_bounds__(256) final_conv_update_kernel(
     float* __restrict__ pred_noise, float* __restrict__ x_start, long npix, int C) {
     constexpr int VEC = fd_vec<T>::N;
     constexpr bool TWO = (MODE == FD_OBJ_PRED_RES_NOISE || MODE == FD_OBJ_PRED_X0_NOISE);
+    constexpr int U = TWO ? 2 : 4;   // pixel groups per warp with all their loads in flight at once (one group per warp left
+                                     // the kernel latency-bound at 2.5 TB/s: a single 16-byte load, then a dependent scalar tail)
     const int lpp = C / VEC;  // lanes per pixel (power of two <= 32)
     const int lane = threadIdx.x & 31;
     const int sub = lane % lpp;
     const int ppw = 32 / lpp;
     const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long pix = warp * ppw + lane / lpp;
-    const bool active = pix < npix;
-    float v[VEC];
-    float acc = 0.f, acc1 = 0.f;
-    if (active) {
-        fd_ldv<T, VEC>(feat + pix * (long)C + sub * VEC, v);
+    const long pix0 = warp * (ppw * U) + lane / lpp;
+    float wv[VEC], wv1[TWO ? VEC : 1];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) acc += v[e] * __ldg(w + sub * VEC + e);
-        if (TWO) {
-            fd_ldv<T, VEC>(feat1 + pix * (long)C + sub * VEC, v);
+    for (int e = 0; e < VEC; ++e) {
+        wv[e] = __ldg(w + sub * VEC + e);
+        if (TWO) wv1[e] = __ldg(w1 + sub * VEC + e);
+    }
+    float v[U][VEC], v1[TWO ? U : 1][VEC], xi[U], xt[U], nz[U];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) acc1 += v[e] * __ldg(w1 + sub * VEC + e);
-        }
+    for (int u = 0; u < U; ++u) {
+        const long pix = pix0 + (long)u * ppw;
+        const long pc = pix < npix ? pix : npix - 1;             // clamped: loads stay unconditional
+        fd_ldv<T, VEC>(feat + pc * (long)C + sub * VEC, v[u]);
+        if (TWO) fd_ldv<T, VEC>(feat1 + pc * (long)C + sub * VEC, v1[u]);
+        xi[u] = x_input[pc];
+        xt[u] = x_t[pc];
+        nz[u] = noise ? noise[pc] : 0.f;
     }
-    for (int o = lpp / 2; o > 0; o >>= 1) {
-        acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (TWO) acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-    }
-    if (!active || sub != 0) return;
     const float c_xt = coef[0], c_res = coef[1], c_x0 = coef[2], c_noise = coef[3], acs = coef[4], bcs = coef[5];
-    const float xi = x_input[pix], xt = x_t[pix];
-    const float o0 = acc + bias[0];
-    float pr, pn, x0;
-    if (MODE == FD_OBJ_PRED_RES) {
-        pr = fminf(fmaxf(o0, -1.f), 1.f);                         // :1165-1166, 1204
-        x0 = fminf(fmaxf(xi - pr, -1.f), 1.f);                    // :1206-1207
-        pn = (xt - xi - (acs - 1.f) * pr) / bcs;                  // :1120-1124
-    } else if (MODE == FD_OBJ_PRED_NOISE) {
-        pn = o0;
-        x0 = (xt - acs * xi - bcs * pn) / coef[6];                // :1126-1130
-        x0 = fminf(fmaxf(x0, -1.f), 1.f);
-        pr = fminf(fmaxf(xi - x0, -1.f), 1.f);                    // :1199-1200
-    } else if (MODE == FD_OBJ_PRED_RES_NOISE) {
-        pr = fminf(fmaxf(o0, -1.f), 1.f);
-        pn = acc1 + bias1[0];
-        x0 = fminf(fmaxf(xt - acs * pr - bcs * pn, -1.f), 1.f);   // :1132-1136, 1175
-    } else {
-        pr = fminf(fmaxf(xi - o0, -1.f), 1.f);                    // :1189, 1191
-        pn = acc1 + bias1[0];
-        x0 = fminf(fmaxf(o0, -1.f), 1.f);                         // :1192
+    const float omacs = coef[6], b0 = bias[0], b1 = TWO ? bias1[0] : 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long pix = pix0 + (long)u * ppw;
+        float acc = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            acc = fmaf(v[u][e], wv[e], acc);
+            if (TWO) acc1 = fmaf(v1[u][e], wv1[e], acc1);
+        }
+        for (int o = lpp / 2; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (TWO) acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+        }
+        if (pix >= npix || sub != 0) continue;
+        const float o0 = acc + b0;
+        float pr, pn, x0;
+        if (MODE == FD_OBJ_PRED_RES) {
+            pr = fminf(fmaxf(o0, -1.f), 1.f);                         // :1165-1166, 1204
+            x0 = fminf(fmaxf(xi[u] - pr, -1.f), 1.f);                 // :1206-1207
+            pn = (xt[u] - xi[u] - (acs - 1.f) * pr) / bcs;            // :1120-1124
+        } else if (MODE == FD_OBJ_PRED_NOISE) {
+            pn = o0;
+            x0 = (xt[u] - acs * xi[u] - bcs * pn) / omacs;            // :1126-1130
+            x0 = fminf(fmaxf(x0, -1.f), 1.f);
+            pr = fminf(fmaxf(xi[u] - x0, -1.f), 1.f);                 // :1199-1200
+        } else if (MODE == FD_OBJ_PRED_RES_NOISE) {
+            pr = fminf(fmaxf(o0, -1.f), 1.f);
+            pn = acc1 + b1;
+            x0 = fminf(fmaxf(xt[u] - acs * pr - bcs * pn, -1.f), 1.f);   // :1132-1136, 1175
+        } else {
+            pr = fminf(fmaxf(xi[u] - o0, -1.f), 1.f);                 // :1189, 1191
+            pn = acc1 + b1;
+            x0 = fminf(fmaxf(o0, -1.f), 1.f);                         // :1192
+        }
+        if (pred_res) pred_res[pix] = pr;
+        if (x_start) x_start[pix] = x0;
+        if (pred_noise) pred_noise[pix] = pn;
+        x_next[pix] = c_xt * xt[u] + c_res * pr + c_x0 * x0 + c_noise * nz[u];
     }
-    if (pred_res) pred_res[pix] = pr;
-    if (x_start) x_start[pix] = x0;
-    if (pred_noise) pred_noise[pix] = pn;
-    float xn = c_xt * xt + c_res * pr + c_x0 * x0;
-    if (noise) xn += c_noise * noise[pix];
-    x_next[pix] = xn;
 }
 
 extern "C" int fd_final_conv_update_obj(const void* feat, const float* w, const float* bias, const void* feat1,
@@ -148,7 +162,9 @@ extern "C" int fd_final_conv_update_obj(const void* feat, const float* w, const 
         constexpr int VEC = fd_vec<T>::N;
         const int lpp = C / VEC;
         if (C % VEC || lpp > 32 || (lpp & (lpp - 1))) return FD_ERR_UNSUPPORTED;
-        const long warps = (npix + (32 / lpp) - 1) / (32 / lpp);
+        const bool two_k = objective == FD_OBJ_PRED_RES_NOISE || objective == FD_OBJ_PRED_X0_NOISE;
+        const long ppw_u = (long)(32 / lpp) * (two_k ? 2 : 4);       // pixels per warp (U groups, see the kernel)
+        const long warps = (npix + ppw_u - 1) / ppw_u;
         const unsigned grid = (unsigned)fd_cdiv(warps, 8);
         const T *f0 = (const T*)feat, *f1 = (const T*)feat1;
         switch (objective) {
