@@ -26,9 +26,13 @@ def load_reference_checkpoint(diffusion, checkpoint, prefer_ema: bool = True) ->
             sd = data["model"]
     if sd is None:
         sd = data
-    live = extract_live_weights(sd)
-    diffusion.model.load_state_dict({"unet0." + k: v for k, v in live.items()})
-    return {"loaded": len(live), "step": int(data.get("step", -1)) if isinstance(data, dict) else -1}
+    merged, n = {}, 0
+    for i in range(getattr(diffusion.model, "num_unet", 1)):          # num_unet = 2 checkpoints carry unet0.* and unet1.*
+        live = extract_live_weights(sd, unet=i)
+        merged.update({f"unet{i}." + k: v for k, v in live.items()})
+        n += len(live)
+    diffusion.model.load_state_dict(merged)
+    return {"loaded": n, "step": int(data.get("step", -1)) if isinstance(data, dict) else -1}
 
 
 @torch.no_grad()

@@ -245,17 +245,18 @@ def random_state_dict(seed: int = 10, cfg: UnetConfig | None = None, with_daclip
 _PREFIXES = ("ema_model.model.unet0.", "model.unet0.", "unet0.", "")
 
 
-def extract_live_weights(state_dict: Dict[str, torch.Tensor], cfg: UnetConfig | None = None) -> "OrderedDict[str, torch.Tensor]":
-    """Pick the live keys out of a reference checkpoint state dict (any of the EMA / diffusion / UnetRes / Unet
+def extract_live_weights(state_dict: Dict[str, torch.Tensor], cfg: UnetConfig | None = None, unet: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Pick the live keys of `unet{unet}` out of a reference checkpoint state dict (any of the EMA / diffusion / UnetRes / Unet
     prefixes, src/DADiff.py:1630-1636 + SURVEY Appendix B) and validate shapes.  Dead keys are dropped."""
     cfg = cfg or UnetConfig()
     out = OrderedDict()
     schema = full_schema(cfg)
-    for prefix in _PREFIXES:
+    prefixes = tuple(p.replace("unet0.", f"unet{unet}.") for p in _PREFIXES if unet == 0 or "unet0." in p)
+    for prefix in prefixes:
         if prefix + schema[0][0] in state_dict:
             break
     else:
-        raise KeyError("no FoundDiff Unet weights found (looked for 'prompt' under " + ", ".join(map(repr, _PREFIXES)) + ")")
+        raise KeyError(f"no FoundDiff unet{unet} weights found (looked for 'prompt' under " + ", ".join(map(repr, prefixes)) + ")")
     for key, shape, _ in schema:
         t = state_dict[prefix + key]
         if tuple(t.shape) != tuple(shape):

@@ -210,3 +210,36 @@ def test_reference_checkpoint_ingestion():
     assert torch.equal(got["unet0.init_conv.weight"], sd["init_conv.weight"])
     load_reference_checkpoint(diff, ckpt, prefer_ema=False)
     assert torch.equal(model.state_dict()["unet0.init_conv.weight"], other["init_conv.weight"])
+
+
+def test_two_unet_checkpoint_ingestion_and_eval_plans():
+    """num_unet = 2 (train.py:75-77): a Trainer.save checkpoint carries unet0.* and unet1.*; the objective / test_res_or_noise
+    combinations map to the Unets evaluated per step and the model-call time entry each gets (src/DADiff.py:817-836, 1161-1163)."""
+    import torch
+    from founddiff_b200 import weights
+    from founddiff_b200.diffusion import ResidualDiffusion, UnetRes
+    from founddiff_b200.evaluate import load_reference_checkpoint
+    sd0, sd1 = weights.random_state_dict(seed=5), weights.random_state_dict(seed=6)
+    ema = {"ema_model.model.unet0." + k: v for k, v in sd0.items()}
+    ema.update({"ema_model.model.unet1." + k: v for k, v in sd1.items()})
+    ema["ema_model.model.unet1.clip_model.visual.conv1.weight"] = torch.zeros(1)        # dead member of the second Unet
+    model = UnetRes(dim=64, num_unet=2, condition=True, objective='pred_res_noise', test_res_or_noise='res_noise')
+    diff = ResidualDiffusion(model, image_size=64, sampling_timesteps=2, objective='pred_res_noise', condition=True,
+                             test_res_or_noise='res_noise')
+    info = load_reference_checkpoint(diff, {"step": 7, "ema": ema})
+    assert info["loaded"] == len(sd0) + len(sd1)
+    got = model.state_dict()
+    assert torch.equal(got["unet0.init_conv.weight"], sd0["init_conv.weight"])
+    assert torch.equal(got["unet1.init_conv.weight"], sd1["init_conv.weight"])
+    assert not torch.equal(got["unet0.init_conv.weight"], got["unet1.init_conv.weight"])
+    assert model._eval_plan("pred_res_noise", "res_noise") == ("pred_res_noise", [(0, 0), (1, 1)])
+    assert model._eval_plan("pred_res_noise", "res") == ("pred_res", [(0, 0)])
+    assert model._eval_plan("pred_res_noise", "noise") == ("pred_noise", [(1, 1)])
+    assert model._eval_plan("pred_x0_noise", "res_noise") == ("pred_x0_noise", [(0, 0), (1, 1)])
+    one = UnetRes(dim=64, num_unet=1, condition=True, objective='pred_noise')
+    assert one._eval_plan() == ("pred_noise", [(0, 1)])
+    # the step plan carries one_minus_alphas_cumsum[t] for predict_start_from_xinput_noise (:1126-1130)
+    diff.init()
+    plan = diff._step_plan()
+    assert [t for t, _ in plan] == [999, 499] and len(plan[0][1]) == 7
+    assert abs(plan[0][1][6] - 1e-6) < 1e-12 and abs(plan[1][1][6] - float(diff.one_minus_alphas_cumsum[499])) < 1e-7
