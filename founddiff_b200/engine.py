@@ -313,9 +313,11 @@ class UnetEngine:
                    and os.environ.get("FD_SCAN_CL", "1") == "1")       # d_state 8 measured slower this way (too few rows)
         if scan_cl:
             Bs_t, Cs_t = Bs.view(B, 4, L, N), Cs.view(B, 4, L, N)
-        # bias + softplus finished by the x_proj/dt_proj kernel: measured neutral-to-negative for the warp-shuffle scan levels
-        # (the scan did not get faster, the producer got slower), so only the channel-per-lane levels use it
-        xdt_softplus = False
+        # bias + softplus finished by the x_proj/dt_proj kernel: measured negative for the warp-shuffle scan levels, twice (again
+        # after the producer went to 3 blocks per SM: scans 18.44 -> 18.17 ms, producer 4.02 -> 4.81 ms per call) — the scan is bound
+        # by its dependent shuffle / MUFU chains, not by issue slots — so only the channel-per-lane levels use it (FD_XDT_SOFTPLUS=1
+        # switches it on for the others)
+        xdt_softplus = fuse_merge and use_xdt_tc and not scan_cl and os.environ.get("FD_XDT_SOFTPLUS", "0") == "1"
         if fuse_dt:
             xdbl = self.buf(f"XDBL{l}", B, 4, R + 2 * N, L, dtype=torch.float32)
             dtw_flat = dtp_w.reshape(4 * D, R).contiguous()
