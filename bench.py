@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--sampling-timesteps", type=int, default=2)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--objective", default="pred_res", choices=["pred_res", "pred_noise", "pred_res_noise", "pred_x0_noise"],
+                    help="default = the shipped configuration (train.py:78-82); pred_res_noise / pred_x0_noise = two Unets per step (train.py:75-77)")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel timing pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--allow-short-warmup", action="store_true",
@@ -220,12 +222,17 @@ def run_b200(args):
     B, H, S = args.batch, args.size, args.sampling_timesteps
 
     sd = weights.random_state_dict(10)
-    model = UnetRes(dim=64, dim_mults=(1, 2, 4, 8), num_unet=1, condition=True, input_condition=False, objective='pred_res',
-                    test_res_or_noise='res')
-    model.load_state_dict({"unet0." + k: v for k, v in sd.items()})
+    num_unet = 2 if args.objective in ("pred_res_noise", "pred_x0_noise") else 1
+    trn = "res_noise" if num_unet == 2 else "res"
+    model = UnetRes(dim=64, dim_mults=(1, 2, 4, 8), num_unet=num_unet, condition=True, input_condition=False,
+                    objective=args.objective, test_res_or_noise=trn)
+    wsd = {"unet0." + k: v for k, v in sd.items()}
+    if num_unet == 2:
+        wsd.update({"unet1." + k: v for k, v in weights.random_state_dict(11).items()})
+    model.load_state_dict(wsd)
     model.compute_dtype = dt
-    diffusion = ResidualDiffusion(model, image_size=H, timesteps=1000, sampling_timesteps=S, objective='pred_res', loss_type='l2',
-                                  condition=True, sum_scale=0.01).to(dev)
+    diffusion = ResidualDiffusion(model, image_size=H, timesteps=1000, sampling_timesteps=S, objective=args.objective, loss_type='l2',
+                                  condition=True, sum_scale=0.01, test_res_or_noise=trn).to(dev)
     diffusion.init()
 
     n_global = B * ws
@@ -366,13 +373,14 @@ def run_b200(args):
         cpu_base = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     if rank == 0:
-        per_slice_step_us = (ms / args.steps) * 1e3 / (B * S)
+        per_slice_step_us = (ms / args.steps) * 1e3 / (B * S * num_unet)      # a slice-step = ONE Unet evaluation
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"FoundDiff full reverse sampling, batch {B} of {H}x{H} slices per GPU, {args.dtype}, "
-                                   f"{'DDIM-' + str(S) if S < 1000 else 'ancestral-1000'}, random-init weights (seed 10, adaLN de-zeroed)",
+                                   f"{'DDIM-' + str(S) if S < 1000 else 'ancestral-1000'}, random-init weights (seed 10, adaLN de-zeroed)"
+                                   + ("" if args.objective == "pred_res" else f", objective {args.objective} ({num_unet} Unet(s) per step)"),
                        "slices_per_gpu": B, "global_batch": n_global, "sampling_timesteps": S, "parallelism": f"dp{ws} (independent chains, 1 all_gather)",
                        "l2": "per-step activations (GBs) >> 126 MB L2; no explicit flush needed", "cuda_graph": True,
                        "storage": ("bf16 block-internal tensors and projections; fp16 residual stream, pre-GroupNorm conv outputs, LayerNorm outputs and "
