@@ -376,7 +376,7 @@ constexpr int GR_PIX = 4096;   // pixels per block
 
 template <typename T>
 __global__ void __launch_bounds__(256) gram_mma_kernel(const T* __restrict__ qkv, int ld, float* __restrict__ gram,
-                                                       float* __restrict__ qk_sq, int P, int C) {
+                                                       float* __restrict__ qk_sq, int P, int C, int pf_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_qk = reinterpret_cast<T*>(smem_raw);                      // [2 buffers][2 (q,k)][256][QK_LD]
     float* s_red = reinterpret_cast<float*>(s_qk + 2 * 2 * GR_TILE * QK_LD);   // [32*32 + 2*32]
@@ -420,6 +420,14 @@ __global__ void __launch_bounds__(256) gram_mma_kernel(const T* __restrict__ qkv
         const int buf = tile & 1;
         if (tile + 1 < ntiles) { stage(tile + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (pf_tiles > 0 && tile + 1 + pf_tiles < ntiles) {     // one 16 KB stage in flight per block bounds the kernel by latency x
+            const long p = p_begin + (long)(tile + 1 + pf_tiles) * GR_TILE + tid;   // bytes in flight: pull later tiles into L2
+            if (p < p_end) {
+                const T* src = qkv + ((long)b * P + p) * ld + head * HD;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + C));
+            }
+        }
         __syncthreads();
         const T* s_q = s_qk + (size_t)buf * 2 * GR_TILE * QK_LD;
         const T* s_k = s_q + GR_TILE * QK_LD;
@@ -586,7 +594,10 @@ static int gram_launch(const void* qkv, int ld, float* gram, float* qk_sq, int B
         attr_set = true;
     }
     dim3 grid((unsigned)(C / HD), (unsigned)fd_cdiv(P, GR_PIX), (unsigned)B);
-    gram_mma_kernel<T><<<grid, 256, smem, stream>>>((const T*)qkv, ld, gram, qk_sq, P, C);
+    // L2 prefetch distance in 256-pixel tiles.  OFF: measured 235 -> 266 us at 16x262144x64 with 2 or 4 tiles (unlike the depthwise
+    // kernels, where it gave 10 %): the q / k half-lines of the two heads are already shared through L2 by neighbouring blocks
+    static const int pf_tiles = getenv("FD_GRAM_PF") ? atoi(getenv("FD_GRAM_PF")) : 0;
+    gram_mma_kernel<T><<<grid, 256, smem, stream>>>((const T*)qkv, ld, gram, qk_sq, P, C, pf_tiles);
     FD_LAUNCH_CHECK();
     return 0;
 }
