@@ -230,8 +230,8 @@ template <typename T> FD_DEVINL void raw_to_float(const RawItems<T>& r, float (&
 // be refilled, its transposed outputs may be written out while the warps already work on chunk c).
 // RDT > 0 fuses dt_proj: `dtr` holds the rank-RDT dt input rows (fp32, same group layout as B / C with `gstride` floats
 // between direction groups), dt_w the (dim, RDT) projection; delta is formed per step in registers and `delta` is unused.
-template <typename T, int NS, int NBUF, bool MERGE, int RDT = 0>
-__global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selective_scan_smem_kernel(
+template <typename T, int NS, int NBUF, bool MERGE, int RDT = 0, int NPAR = 1>
+__global__ void __launch_bounds__(kRowsPerBlock * 32, (NPAR == 1 && NS <= 8 ? 3 : 2)) selective_scan_smem_kernel(
     const T* __restrict__ u, const T* __restrict__ delta, const float* __restrict__ A, const float* __restrict__ Bm,
     const float* __restrict__ Cm, const float* __restrict__ D, const float* __restrict__ delta_bias, T* __restrict__ y,
     int dim, int L, int G, int softplus, int H, int W, const float* __restrict__ dtr = nullptr,
@@ -365,35 +365,50 @@ __global__ void __launch_bounds__(kRowsPerBlock * 32, (NS <= 8 ? 3 : 2)) selecti
         float sdt = 0.f;
 #pragma unroll
         for (int i = 0; i < kItems; ++i) sdt += dt[i];
+        // NPAR states at a time, their five dependent shuffle rounds issued interleaved.  SASS of the NPAR = 1 kernel shows the
+        // states fully serialised (80 registers leave ptxas no room to overlap them: ~200 clk of shuffle latency per state and
+        // warp); NPAR = 2 (FD_SCAN_NPAR=2) overlaps two chains but needs 128 registers -> 2 blocks per SM instead of 3, and
+        // MEASURED SLOWER: 1694 vs 1621 us (d_state 4), 1394 vs 1299 us (d_state 8).  Occupancy hides that latency better.
 #pragma unroll
-        for (int n = 0; n < NS; ++n) {
-            const float4 b0 = *reinterpret_cast<const float4*>(sB + n * kPadChunk);
-            const float4 b1 = *reinterpret_cast<const float4*>(sB + n * kPadChunk + 4);
-            const float4 c0v = *reinterpret_cast<const float4*>(sC + n * kPadChunk);
-            const float4 c1v = *reinterpret_cast<const float4*>(sC + n * kPadChunk + 4);
-            float Bn[kItems] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            const float Cn[kItems] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
-            const float a2n = kA2InSmem ? s_a2[warp * NS + n] : A2[kA2InSmem ? 0 : n];
-            float a[kItems], bp = 0.f;
-            float ap = ex2_approx(sdt * a2n);      // product of the lane's 8 decay factors
+        for (int n0 = 0; n0 < NS; n0 += NPAR) {
+            float a[NPAR][kItems], Bn[NPAR][kItems], ap[NPAR], bp[NPAR];
 #pragma unroll
-            for (int i = 0; i < kItems; ++i) {
-                a[i] = ex2_approx(dt[i] * a2n);
-                Bn[i] = dtu[i] * Bn[i];
-                bp = fmaf(a[i], bp, Bn[i]);
+            for (int q = 0; q < NPAR; ++q) {
+                const int n = n0 + q;
+                const float4 b0 = *reinterpret_cast<const float4*>(sB + n * kPadChunk);
+                const float4 b1 = *reinterpret_cast<const float4*>(sB + n * kPadChunk + 4);
+                const float bv[kItems] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const float a2n = kA2InSmem ? s_a2[warp * NS + n] : A2[kA2InSmem ? 0 : n];
+                ap[q] = ex2_approx(sdt * a2n);      // product of the lane's 8 decay factors
+                bp[q] = 0.f;
+#pragma unroll
+                for (int i = 0; i < kItems; ++i) {
+                    a[q][i] = ex2_approx(dt[i] * a2n);
+                    Bn[q][i] = dtu[i] * bv[i];
+                    bp[q] = fmaf(a[q][i], bp[q], Bn[q][i]);
+                }
             }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) scan_round(ap, bp, o);
-            float ae, be;
-            scan_exclusive(ap, bp, ae, be);
-            float hh = fmaf(ae, h[n], be);
-            const float at = __shfl_sync(0xffffffffu, ap, 31);
-            const float bt = __shfl_sync(0xffffffffu, bp, 31);
-            h[n] = fmaf(at, h[n], bt);
+            for (int o = 1; o < 32; o <<= 1)
 #pragma unroll
-            for (int i = 0; i < kItems; ++i) {
-                hh = fmaf(a[i], hh, Bn[i]);
-                yacc[i] = fmaf(hh, Cn[i], yacc[i]);
+                for (int q = 0; q < NPAR; ++q) scan_round(ap[q], bp[q], o);
+#pragma unroll
+            for (int q = 0; q < NPAR; ++q) {
+                const int n = n0 + q;
+                float ae, be;
+                scan_exclusive(ap[q], bp[q], ae, be);
+                float hh = fmaf(ae, h[n], be);
+                const float at = __shfl_sync(0xffffffffu, ap[q], 31);
+                const float bt = __shfl_sync(0xffffffffu, bp[q], 31);
+                h[n] = fmaf(at, h[n], bt);
+                const float4 c0v = *reinterpret_cast<const float4*>(sC + n * kPadChunk);
+                const float4 c1v = *reinterpret_cast<const float4*>(sC + n * kPadChunk + 4);
+                const float Cn[kItems] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+                for (int i = 0; i < kItems; ++i) {
+                    hh = fmaf(a[q][i], hh, Bn[q][i]);
+                    yacc[i] = fmaf(hh, Cn[i], yacc[i]);
+                }
             }
         }
         if constexpr (!MERGE) {
@@ -420,9 +435,11 @@ int scan_launch(const void* u, const void* delta, const float* A, const float* B
     const int vec_ok = (L % kItems == 0) && ((((uintptr_t)u | (uintptr_t)delta | (uintptr_t)y) & 31) == 0) &&
                        ((((uintptr_t)Bm | (uintptr_t)Cm) & 31) == 0);
     // v2: rows of a block share one direction group and every access is 16/32-byte aligned
+    static const int npar_env = getenv("FD_SCAN_NPAR") ? atoi(getenv("FD_SCAN_NPAR")) : 1;
+    const int npar = (npar_env == 2 && (N == 4 || N == 8)) ? 2 : 1;       // states scanned with interleaved shuffle rounds
     if (vec_ok && L >= kItems && (N == 4 || N == 8 || N == 16 || N == 32)) {
-#define SCAN2_CASE(NSV, NB, RPWV)                                                                                   \
-    if (N == NSV && (dim / G) % (kRowsPerBlock * RPWV) == 0) {                                                      \
+#define SCAN2_CASE(NSV, NB, RPWV, NPARV)                                                                            \
+    if (N == NSV && npar == NPARV && (dim / G) % (kRowsPerBlock * RPWV) == 0) {                                                      \
         const unsigned grid2 = (unsigned)(rows / (kRowsPerBlock * RPWV));                                           \
         const size_t smem = ((size_t)NB * 2 * NSV * kPadChunk + (NSV >= 16 ? kRowsPerBlock * RPWV * NSV : 0)) * sizeof(float); \
         if (mergeH) {                                                                                               \
@@ -430,30 +447,31 @@ int scan_launch(const void* u, const void* delta, const float* A, const float* B
             static bool attr_m = false;                                                                             \
             const size_t smem_m = smem + (size_t)2 * kRowsPerBlock * RPWV * kChunk * sizeof(T);                         \
             if (!attr_m) {                                                                                          \
-                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, true>,            \
+                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, true, 0, NPARV>,            \
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);     \
                 if (e != cudaSuccess) return (int)e;                                                                \
                 attr_m = true;                                                                                      \
             }                                                                                                       \
-            selective_scan_smem_kernel<T, NSV, NB, true><<<grid2, kRowsPerBlock * 32, smem_m, st>>>(          \
+            selective_scan_smem_kernel<T, NSV, NB, true, 0, NPARV><<<grid2, kRowsPerBlock * 32, smem_m, st>>>(          \
                 (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus, mergeH, mergeW); \
           }                                                                                                         \
         } else {                                                                                                    \
             static bool attr_set = false;                                                                           \
             if (!attr_set) {                                                                                        \
-                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, false>,           \
+                cudaError_t e = cudaFuncSetAttribute(selective_scan_smem_kernel<T, NSV, NB, false, 0, NPARV>,           \
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
                 if (e != cudaSuccess) return (int)e;                                                                \
                 attr_set = true;                                                                                    \
             }                                                                                                       \
-            selective_scan_smem_kernel<T, NSV, NB, false><<<grid2, kRowsPerBlock * 32, smem, st>>>(           \
+            selective_scan_smem_kernel<T, NSV, NB, false, 0, NPARV><<<grid2, kRowsPerBlock * 32, smem, st>>>(           \
                 (const T*)u, (const T*)delta, A, Bm, Cm, D, delta_bias, (T*)y, dim, L, G, softplus, 0, 0);          \
         }                                                                                                           \
         FD_LAUNCH_CHECK();                                                                                          \
         return 0;                                                                                                   \
     }
         // RPW = 2 (16 channels per block, full-sector writes) was measured SLOWER (register spills, occupancy): not used
-        SCAN2_CASE(4, 2, 1) SCAN2_CASE(8, 2, 1) SCAN2_CASE(16, 2, 1) SCAN2_CASE(32, 1, 1)
+        SCAN2_CASE(4, 2, 1, 1) SCAN2_CASE(8, 2, 1, 1) SCAN2_CASE(16, 2, 1, 1) SCAN2_CASE(32, 1, 1, 1)
+        SCAN2_CASE(4, 2, 1, 2) SCAN2_CASE(8, 2, 1, 2)
 #undef SCAN2_CASE
     }
     if (mergeH) return FD_ERR_UNSUPPORTED;
