@@ -518,7 +518,7 @@ template <typename T, int NS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) selective_scan_cl_kernel(
     const T* __restrict__ u, const T* __restrict__ delta, const float* __restrict__ A, const float* __restrict__ Bt,
     const float* __restrict__ Ct, const float* __restrict__ D, const float* __restrict__ delta_bias, T* __restrict__ y,
-    int dim, int L, int softplus, int H, int W) {
+    int dim, int L, int softplus, int H, int W, int pf) {
     extern __shared__ __align__(16) float s_cl[];          // [2][2][kCLChunk][NS]: buffer, B/C, step, state
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per_group = dim / 4;
@@ -574,6 +574,11 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) selective_scan_cl_kern
                 const int ln = min(c0 + s0 + kItems, L - kItems);      // next octet (clamped on the last one)
                 dt_raw = load_raw<T>(dr + ln);
                 u_raw = load_raw<T>(ur + ln);
+                if (pf > 0) {                                          // every lane walks its own row: pull its next lines into L2
+                    const int lp = min(ln + pf, L - kItems);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(dr + lp));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ur + lp));
+                }
             }
 #pragma unroll
             for (int i = 0; i < kItems; ++i) {
@@ -619,6 +624,7 @@ static int scan_cl_launch(const void* u, const void* delta, const float* A, cons
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long total_warps = (long)batch * dim / 32;
+    static const int pf = getenv("FD_SCANCL_PF") ? atoi(getenv("FD_SCANCL_PF")) : 0;     // L2 prefetch distance in steps (0 = off)
 #define CL_CASE(WV)                                                                                                    \
     if (per_group % (WV * 32) == 0 && (WV == 1 || NS >= 32 || total_warps / WV >= 6L * sms)) {                         \
         static bool attr = false;                                                                                      \
@@ -629,7 +635,7 @@ static int scan_cl_launch(const void* u, const void* delta, const float* A, cons
         }                                                                                                              \
         const unsigned grid = (unsigned)(batch * 4 * (per_group / (WV * 32)));                                         \
         selective_scan_cl_kernel<T, NS, WV><<<grid, WV * 32, smem, st>>>((const T*)u, (const T*)delta, A, Bt, Ct, D, delta_bias, \
-                                                                         (T*)y, dim, L, softplus, H, W);               \
+                                                                         (T*)y, dim, L, softplus, H, W, pf);           \
         FD_LAUNCH_CHECK();                                                                                             \
         return 0;                                                                                                      \
     }
