@@ -217,6 +217,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if ws > 1:
+        # stdout carries exactly ONE JSON line: NCCL's own banner (the boxes run with NCCL_DEBUG=VERSION) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
     B, H, S = args.batch, args.size, args.sampling_timesteps
