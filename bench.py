@@ -216,9 +216,13 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    real_stdout = None
     if ws > 1:
-        # stdout carries exactly ONE JSON line: NCCL's own banner (the boxes run with NCCL_DEBUG=VERSION) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly ONE JSON line: NCCL prints its version banner straight to fd 1 (the boxes run with
+        # NCCL_DEBUG=VERSION), so fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
     B, H, S = args.batch, args.size, args.sampling_timesteps
@@ -400,7 +404,11 @@ def run_b200(args):
             line["roofline"] = roofline
         if cpu_base:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line), flush=True)
+        if real_stdout is not None:
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     if ws > 1:
         dist.destroy_process_group()
 
