@@ -543,8 +543,13 @@ __global__ void __launch_bounds__(256) xdt_proj_mma_kernel(const T* __restrict__
                     fd_st(s_xd + c * XT_XLD + col + 1, v1);
                 } else if (c < CC) {
                     float* dst = (c < R + N ? Bs + ((long)bk * N + (c - R)) * L : Cs + ((long)bk * N + (c - R - N)) * L) + l0 + col;
-                    if (l0 + col + 1 < L) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
-                    else if (l0 + col < L) dst[0] = v0;
+                    // odd L: rows of B / C start at odd float offsets, a float2 store would be misaligned (found with the 48x80
+                    // fixture: level 3 has L = 15 -> cudaErrorMisalignedAddress)
+                    if (l0 + col + 1 < L && !(L & 1)) *reinterpret_cast<float2*>(dst) = make_float2(v0, v1);
+                    else {
+                        if (l0 + col < L) dst[0] = v0;
+                        if (l0 + col + 1 < L) dst[1] = v1;
+                    }
                 }
             }
     __syncthreads();

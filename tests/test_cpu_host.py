@@ -261,3 +261,18 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert k in d
+
+
+def test_odd_deep_level_refused_in_16_bit():
+    """48x80 -> deepest level 3x5: scan length 15.  16-bit storage refuses it loudly before any kernel runs (a misaligned store in
+    the 16-bit x_proj kernel was found on this case; the fix is in, the geometry stays refused until re-validated on a GPU)."""
+    from founddiff_b200.engine import UnetEngine
+    for dt in (torch.bfloat16, torch.float16):
+        with pytest.raises(NotImplementedError):
+            UnetEngine.check_geometry(48, 80, dt)
+        UnetEngine.check_geometry(64, 96, dt)
+        UnetEngine.check_geometry(32, 48, dt)
+        UnetEngine.check_geometry(512, 512, dt)
+    UnetEngine.check_geometry(48, 80, torch.float32)
+    with pytest.raises(ValueError):
+        UnetEngine.check_geometry(40, 80, torch.float32)

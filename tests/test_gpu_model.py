@@ -292,3 +292,23 @@ def test_evaluate_loop_npy_in_metrics_on_device_npy_out(model, tmp_path):
         assert abs(res["psnr"][i] - float(MO.compute_psnr(p, y))) < 1e-3
         assert abs(res["ssim"][i] - float(MO.compute_ssim(p, y))) < 5e-5
         assert abs(res["rmse"][i] - float(MO.compute_rmse(p, y))) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [torch.float32])
+def test_ragged_geometry_vs_reference(model, dt):
+    """48x80 slices: level maps 24x40 / 12x20 / 6x10 and scan lengths 960 / 240 / 60 / 15 do not tile evenly, so the kernels run
+    the tails of their general paths; same gates as the even sizes.  Fixture from the unmodified reference:
+    tests/golden/unet_48x80.npz (oracle/gen_golden_ragged.py).  fp32 storage only: the 16-bit modes REFUSE this geometry (odd
+    deepest-level scan length, see UnetEngine.check_geometry and tests/test_cpu_host.py::test_odd_deep_level_refused_in_16_bit)."""
+    g = load_golden("unet_48x80.npz")
+    set_mode(model, dt, sampling_timesteps=2)
+    time = g["time"].cuda()
+    r = rel(model.model(g["x_in"].cuda(), [time, time])[0], g["out"])
+    print(f"48x80 {dt}: Unet rel-L2 {r:.3e}")
+    assert r < GATE[dt]
+    outs = model.sample([g["ldct"].cuda()], batch_size=1, last=False, noise={"init": g["init_noise"]})
+    assert len(outs) == g["outs"].shape[0] == 3
+    assert rel(outs[0], g["outs"][0]) < 1e-6
+    assert abs(O.psnr(outs[-1].cpu(), g["ndct"]) - O.psnr(g["outs"][-1], g["ndct"])) < 0.05
+    assert rel(outs[-1], g["outs"][-1]) < GATE[dt]
