@@ -276,3 +276,20 @@ def test_odd_deep_level_refused_in_16_bit():
     UnetEngine.check_geometry(48, 80, torch.float32)
     with pytest.raises(ValueError):
         UnetEngine.check_geometry(40, 80, torch.float32)
+
+
+def test_c_abi_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/founddiff_b200.h compiles as pedantic C99 and as C++17, and a C program (examples/c_host.c) links the library,
+    reads its version and gets FD_ERR_BAD_ARGUMENT from the argument validation — no torch, no C++ types across the boundary."""
+    import subprocess
+    from founddiff_b200 import _lib
+    inc = os.path.join(ROOT, "include")
+    src = os.path.join(ROOT, "examples", "c_host.c")
+    subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", inc, src], check=True, capture_output=True)
+    exe = str(tmp_path / "c_host")
+    libdir = os.path.dirname(_lib.lib_path())
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, src, "-o", exe, "-L", libdir,
+                        "-lfounddiff_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "sm_100a" in out.stdout, (out.returncode, out.stdout, out.stderr)
