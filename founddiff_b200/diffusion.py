@@ -26,7 +26,7 @@ from __future__ import annotations
 
 import math
 from collections import OrderedDict
-from typing import Callable, Dict, List, Optional, Union
+from typing import Dict, Optional
 
 import torch
 import torch.nn.functional as F
