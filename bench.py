@@ -145,6 +145,7 @@ def algorithmic(name, detail, es):
     try:
         if name in ("selective_scan", "selective_scan_merge"):
             fused = detail.endswith(" dt-fused")       # delta formed in-kernel from the rank-R rows of x_dbl (R == N here)
+            detail = detail[:-3] if detail.endswith(" cl") else detail       # channel-per-lane variant: same algorithmic work
             dims, n = detail.replace(" dt-fused", "").split(" N")
             b, kd, L = map(int, dims.split("x"))
             n = int(n)
