@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--allow-short-warmup", action="store_true",
                     help="full ancestral schedules only: 1 warm-up call (= 1000 Unet evaluations) instead of 3")
     ap.add_argument("--kernel-table", default="", help="write the per-kernel timing table (JSON) here")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the two extra measurement rows of SURVEY 8(d) (DDIM-10, ancestral window) that the default run appends")
+    ap.add_argument("--window", type=int, default=50, help="ancestral rows: timesteps per timed window (stated in the line)")
     return ap.parse_args()
 
 
@@ -226,7 +229,7 @@ def run_b200(args):
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[args.dtype]
-    B, H, S = args.batch, args.size, args.sampling_timesteps
+    B, H = args.batch, args.size
 
     sd = weights.random_state_dict(10)
     num_unet = 2 if args.objective in ("pred_res_noise", "pred_x0_noise") else 1
@@ -238,44 +241,16 @@ def run_b200(args):
         wsd.update({"unet1." + k: v for k, v in weights.random_state_dict(11).items()})
     model.load_state_dict(wsd)
     model.compute_dtype = dt
-    diffusion = ResidualDiffusion(model, image_size=H, timesteps=1000, sampling_timesteps=S, objective=args.objective, loss_type='l2',
-                                  condition=True, sum_scale=0.01, test_res_or_noise=trn).to(dev)
+    diffusion = ResidualDiffusion(model, image_size=H, timesteps=1000, sampling_timesteps=args.sampling_timesteps, objective=args.objective,
+                                  loss_type='l2', condition=True, sum_scale=0.01, test_res_or_noise=trn).to(dev)
     diffusion.init()
 
     n_global = B * ws
     _, ldct_g = synth_slices(n_global, H, H)
-    n_noise_steps = 0 if diffusion.is_ddim_sampling else diffusion.num_timesteps - 1
     a, b_ = fdist.shard_range(n_global, rank, ws)
-    # full ancestral schedules (999 noise tensors of B x H x W fp32 = 16.8 GB at B = 16) do not take host-supplied step
-    # noise: it is drawn on the device per step from a generator seeded by (seed, global slice range, t) instead
-    device_step_noise = n_noise_steps > 64
-    init_g, steps_g = fdist.global_noise(n_global, (1, H, H), 4321, 0 if device_step_noise else n_noise_steps)
     ldct_host = ldct_g[a:b_].contiguous().pin_memory()
-    noise_host = {"init": init_g[a:b_].contiguous().pin_memory()}
-    if steps_g is not None:
-        noise_host["steps"] = steps_g[:, a:b_].contiguous().pin_memory()
     ldct_dev = ldct_host.to(dev)
-    noise_dev = {k: v.to(dev) for k, v in noise_host.items()}
-    if device_step_noise:
-        gen = torch.Generator(device=dev)
-
-        def step_noise(t):
-            gen.manual_seed(4321 + 1000003 * a + int(t))
-            return torch.randn(b_ - a, 1, H, H, device=dev, generator=gen)
-        noise_dev["steps"] = step_noise
-
-    def step_resident():
-        out = diffusion.sample([ldct_dev], batch_size=B, last=True, noise=noise_dev)[-1]
-        return fdist.gather_slices(out, n_global)
-
-    def step_e2e():
-        x = ldct_host.to(dev, non_blocking=True)
-        nz = {k: v.to(dev, non_blocking=True) for k, v in noise_host.items()}
-        if device_step_noise:
-            nz["steps"] = noise_dev["steps"]
-        out = diffusion.sample([x], batch_size=B, last=True, noise=nz)[-1]
-        out = fdist.gather_slices(out, n_global)
-        return out.to("cpu", non_blocking=False)          # D2H read of the step's result (synchronises)
+    out_host = torch.empty(n_global if rank == 0 else b_ - a, 1, H, H).pin_memory()      # rank 0 reads the gathered batch back
 
     def barrier():
         if ws > 1:
@@ -295,29 +270,113 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    n_warm = max(args.warmup, 1 if (device_step_noise and args.allow_short_warmup) else 3)
+    class Workload:
+        """One sampler configuration (S Unet evaluations per slice; S = 1000 -> ancestral, timed over a window of timesteps).
+        Host-supplied noise (north_star), one generator per GLOBAL slice (fdist.SliceNoise): a rank draws its own shard only and
+        the numbers of a slice do not depend on the world size."""
+
+        def __init__(self, S, window):
+            self.S = S
+            diffusion.sampling_timesteps = S
+            diffusion.is_ddim_sampling = S < diffusion.num_timesteps
+            self.ancestral = not diffusion.is_ddim_sampling
+            # ancestral: a WINDOW of timesteps is timed (SURVEY 8d config 4 allows it; a full schedule is 999 x 16 MiB of step
+            # noise per rank); --window 0 runs all 1000 with the noise streamed from the host generator thread
+            self.window = (window if window > 0 else diffusion.num_timesteps) if self.ancestral else None
+            self.evals = min(self.window, diffusion.num_timesteps) if self.ancestral else S      # Unet evaluations per call
+            self.n_noise_steps = (self.evals - 1) if self.ancestral else 0
+            self.sn = fdist.SliceNoise(4321, range(a, b_), (1, H, H))
+            self.noise_host = {"init": self.sn.init()}
+            self.stream_steps = self.n_noise_steps > 64          # full schedule: produced on the fly by the host thread
+            if self.n_noise_steps and not self.stream_steps:
+                self.noise_host["steps"] = torch.stack([self.sn._draw(torch.empty(b_ - a, 1, H, H))
+                                                        for _ in range(self.n_noise_steps)]).pin_memory()
+            self.noise_dev = {k: v.to(dev) for k, v in self.noise_host.items()}
+            self.h2d = ldct_host.numel() * 4 + self.noise_host["init"].numel() * 4 + self.n_noise_steps * (b_ - a) * H * H * 4   # per rank
+            self.d2h = out_host.numel() * 4                                                                                     # rank 0
+
+        def name(self):
+            return f"DDIM-{self.S}" if not self.ancestral else (
+                "ancestral-1000" if self.evals == diffusion.num_timesteps else
+                f"ancestral p_sample, window of {self.evals} of 1000 timesteps (t = 999 .. {1000 - self.evals}; host-supplied step noise)")
+
+        def _nz(self, nz):
+            if self.stream_steps:
+                nz = dict(nz)
+                nz["steps"] = self.sn.steps(self.n_noise_steps)
+            return nz
+
+        def step_local(self):
+            return diffusion.sample([ldct_dev], batch_size=B, last=True, noise=self._nz(self.noise_dev), steps_limit=self.window)[-1]
+
+        def step_resident(self):
+            return fdist.gather_slices(self.step_local(), n_global)
+
+        def step_e2e(self):
+            x = ldct_host.to(dev, non_blocking=True)
+            nz = {"init": self.noise_host["init"].to(dev, non_blocking=True)}
+            if "steps" in self.noise_host:
+                nz["steps"] = self.noise_host["steps"]       # pinned host tensor: sample() streams one step's noise at a time
+            out = diffusion.sample([x], batch_size=B, last=True, noise=self._nz(nz), steps_limit=self.window)[-1]
+            out = fdist.gather_slices(out, n_global)
+            # D2H read of the result into pre-allocated pinned memory: rank 0 takes the whole gathered batch (what the caller of
+            # a sharded sample() consumes), every other rank only its own shard
+            out_host.copy_(out if rank == 0 else out[a:b_], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return out_host
+
+        def measure(self, steps, warmup, e2e_warmup=2):
+            for _ in range(warmup):
+                self.step_resident()
+            ms = timed(self.step_resident, steps)
+            for _ in range(e2e_warmup):
+                self.step_e2e()
+            ms_e2e = timed(self.step_e2e, steps)
+            return ms, ms_e2e
+
+    main = Workload(args.sampling_timesteps, args.window)
+    n_warm = max(args.warmup, 1 if (main.stream_steps and args.allow_short_warmup) else 3)
     for _ in range(n_warm):
-        step_resident()
+        main.step_resident()
     launches0 = ops.LAUNCHES
     diffusion.use_cuda_graph = False          # count kernels of one call in eager mode (graph replays launch the same set)
-    step_resident()
+    main.step_resident()
     launches_per_call = ops.LAUNCHES - launches0
     diffusion.use_cuda_graph = True
-    step_resident()
+    main.step_resident()
 
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms = timed(step_resident, args.steps)
+    ms = timed(main.step_resident, args.steps)
     clk = clocks.stop() if rank == 0 else None
     value = n_global * args.steps / (ms / 1e3)
 
-    for _ in range(1 if device_step_noise else 2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    for _ in range(1 if main.stream_steps else 2):
+        main.step_e2e()
+    ms_e2e = timed(main.step_e2e, args.steps)
     e2e_value = n_global * args.steps / (ms_e2e / 1e3)
-    h2d = ldct_host.numel() * 4 + sum(v.numel() * 4 for v in noise_host.values())
-    d2h = n_global * H * H * 4
+
+    # ---- the other measurement rows of SURVEY 8(d): DDIM-10 (configs 1/2 say "2 and 10") and the ancestral sampler (config 4),
+    # run by every rank so that the driver's 1/2/4/8 sweep records them too.  Fewer timed calls: they are 5x / 25x longer.
+    extras = {}
+    if not args.no_extras and args.sampling_timesteps == 2 and args.objective == "pred_res":
+        for key, S, steps in (("ddim10", 10, 3), ("ancestral", 1000, 2)):
+            wl = Workload(S, args.window)
+            m, me = wl.measure(steps, 1, 1)
+            extras[key] = {"workload": wl.name(), "steps": steps, "warmup": 1, "unet_evals_per_call": wl.evals,
+                           "ms_per_call": m / steps, "value": n_global * steps / (m / 1e3), "unit": UNIT,
+                           "per_slice_step_us": (m / steps) * 1e3 / (B * wl.evals),
+                           "step_roofline_frac": T_ROOF_US / ((m / steps) * 1e3 / (B * wl.evals)),
+                           "e2e": {"value": n_global * steps / (me / 1e3), "unit": UNIT, "ms_per_call": me / steps,
+                                   "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h}}
+            if wl.ancestral and wl.evals < diffusion.num_timesteps:
+                full = (m / steps) * diffusion.num_timesteps / wl.evals
+                extras[key]["extrapolated_full_schedule"] = {
+                    "ms_per_call": full, "value": n_global / (full / 1e3), "unit": UNIT,
+                    "note": f"window time x {diffusion.num_timesteps}/{wl.evals}: every timestep launches the same CUDA graph"}
+            del wl
+        main = Workload(args.sampling_timesteps, args.window)      # restore the sampler configuration for the profile pass
 
     # ---- per-kernel timing pass (eager, CUDA events around every launch) -> roofline of the dominant kernel ------
     roofline, table = None, []
@@ -328,11 +387,12 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
     peak_src = "measured (MEASURED_PEAKS.json; sustained bf16 figure: kernel timed inside a long step)" if peaks else "fallback"
+    S = args.sampling_timesteps
     if not args.no_profile and rank == 0:
         es = 4 if dt == torch.float32 else 2
         diffusion.use_cuda_graph = False
         ops.PROFILE = []
-        step_resident()
+        main.step_local()             # rank 0 ALONE: no collective in here (the other ranks wait at the final barrier)
         torch.cuda.synchronize(dev)
         prof, ops.PROFILE = ops.PROFILE, None
         diffusion.use_cuda_graph = True
@@ -362,17 +422,21 @@ def run_b200(args):
                         "frac": round(top["GBps"] / hbm_peak, 4), "traffic": None}
         roofline.update({"kernel": top["kernel"], "shape": top["shape"], "share_of_step": top["share"], "avg_us": top["avg_us"],
                          "peak_source": peak_src})
-        # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r1_ncu_traffic.json), if this
+        # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r*_ncu_traffic.json), if this
         # kernel/shape was captured
-        tf = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-        if os.path.exists(tf):
-            ent = json.load(open(tf)).get(f"{top['kernel']}|{top['shape']}")
-            if ent:
-                roofline["traffic"] = ent["dram_bytes"]
-                roofline["traffic_source"] = ent["source"]
+        for tf in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+            tf = os.path.join(ROOT, "profiles", tf)
+            if os.path.exists(tf):
+                ent = json.load(open(tf)).get(f"{top['kernel']}|{top['shape']}")
+                if ent:
+                    roofline["traffic"] = ent["dram_bytes"]
+                    roofline["traffic_source"] = ent["source"]
+                    break
+        # sum over launches of max(bytes / HBM, FLOPs / TC): what the step would take with every kernel at its own roof
+        roof_ms = sum(r["launches"] * max(r["alg_GB"] / hbm_peak * 1e3, r["alg_GFLOP"] / tc_peak) for r in table)
         if args.kernel_table:
             os.makedirs(os.path.dirname(os.path.abspath(args.kernel_table)), exist_ok=True)
-            json.dump({"per_call_ms_eager": total, "kernels": table}, open(args.kernel_table, "w"), indent=1)
+            json.dump({"per_call_ms_eager": total, "sum_of_launch_roofs_ms": roof_ms, "kernels": table}, open(args.kernel_table, "w"), indent=1)
 
     cpu_base = None
     if rank == 0 and ws == 1 and not args.no_cpu_baseline:
@@ -380,27 +444,31 @@ def run_b200(args):
         cpu_base = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     if rank == 0:
-        per_slice_step_us = (ms / args.steps) * 1e3 / (B * S * num_unet)      # a slice-step = ONE Unet evaluation
+        per_slice_step_us = (ms / args.steps) * 1e3 / (B * main.evals * num_unet)      # a slice-step = ONE Unet evaluation
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"FoundDiff full reverse sampling, batch {B} of {H}x{H} slices per GPU, {args.dtype}, "
-                                   f"{'DDIM-' + str(S) if S < 1000 else 'ancestral-1000'}, random-init weights (seed 10, adaLN de-zeroed)"
+                                   f"{main.name()}, random-init weights (seed 10, adaLN de-zeroed)"
                                    + ("" if args.objective == "pred_res" else f", objective {args.objective} ({num_unet} Unet(s) per step)"),
                        "slices_per_gpu": B, "global_batch": n_global, "sampling_timesteps": S, "parallelism": f"dp{ws} (independent chains, 1 all_gather)",
                        "l2": "per-step activations (GBs) >> 126 MB L2; no explicit flush needed", "cuda_graph": True,
+                       "noise": "host-supplied, one generator per global slice (world-size invariant)",
                        "storage": ("bf16 block-internal tensors and projections; fp16 residual stream, pre-GroupNorm conv outputs, LayerNorm outputs and "
                                    "the convolutions reading them; fp32 accumulation, sampler state and conditioning") if args.dtype == "bf16"
                                   else f"{args.dtype} storage, fp32 accumulation"},
             "per_slice_step_us": per_slice_step_us,
             "step_roofline": {"t_roof_us": T_ROOF_US, "frac": T_ROOF_US / per_slice_step_us,
                               "note": "BASELINE.md §3 per-slice-step roofline / measured per-slice-step time (includes DA-CLIP + sampler)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": main.h2d, "d2h_bytes_per_step": main.d2h, "ms_per_step": ms_e2e / args.steps,
+                    "note": "per rank: pinned H2D of its slices + noise; D2H into pinned memory of the gathered batch on rank 0 (own shard elsewhere)"},
             "gpu_launches": launches_per_call * args.steps,
             "gpu_launches_per_step": launches_per_call,
             "clocks": clk,
         }
+        if extras:
+            line["also"] = extras
         if roofline:
             line["roofline"] = roofline
         if cpu_base:
@@ -411,6 +479,7 @@ def run_b200(args):
         else:
             print(json.dumps(line), flush=True)
     if ws > 1:
+        dist.barrier()                # nobody tears the communicator down while rank 0 is still in its profile pass
         dist.destroy_process_group()
 
 

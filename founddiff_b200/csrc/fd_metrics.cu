@@ -17,7 +17,10 @@ struct GaussWin {
 
 FD_DEVINL int reflect(int i, int n) {          // torch 'reflect' padding (no edge repeat); n > MT_R
     i = i < 0 ? -i : i;
-    return i >= n ? 2 * n - 2 - i : i;
+    i = i >= n ? 2 * n - 2 - i : i;
+    // partial tiles load the full halo patch: far outside the image one fold is not enough (W = 16: x up to 36 -> -6).  Those
+    // patch entries only feed masked outputs; the clamp keeps the read inside the buffer.
+    return min(max(i, 0), n - 1);
 }
 
 __global__ void __launch_bounds__(MT_W * MT_H) slice_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ target,

@@ -109,27 +109,38 @@ class UnetRes(nn.Module):
         self.trunk_dtype: Optional[torch.dtype] = None
         self._engines: Dict = {}
         self._daclip = None
-        self._version = 0
+        self._built_fingerprint = None
+        # nn.Module.load_state_dict recurses with _load_from_state_dict: hooks (not a load_state_dict override) see every path
+        self._register_load_state_dict_pre_hook(self._drop_dead_keys)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
 
     # -- engine management ----------------------------------------------------------------------------------
     def invalidate(self):
-        """Call after changing weights in place; load_state_dict does it automatically."""
+        """Drops the packed engines, the DA-CLIP encoders and (through the engine identity check in
+        ResidualDiffusion._graphed) the captured CUDA graphs.  Runs automatically after load_state_dict on any path, after
+        .to() and when a parameter's version counter moved."""
         self._engines.clear()
         self._daclip = None
 
-    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        """Accepts a reference checkpoint: live keys are loaded, the reference's dead members (`clip_model.*`,
-        CLIP text tower, `prompt_learner`) are ignored.  Missing live keys still raise."""
-        own = super().state_dict()
-        live = {k: v for k, v in state_dict.items() if k in own}
-        dead_ok = tuple(f"unet{i}.{d}" for i in range(self.num_unet)
-                        for d in ("clip_model.", "dose_encoder.clip_model.", "dose_encoder.prompt_learner."))
-        unexpected = [k for k in state_dict if k not in own and not k.startswith(dead_ok)]
-        if strict and unexpected:
-            raise RuntimeError(f"unexpected keys: {unexpected[:5]}...")
-        res = super().load_state_dict(live, strict=strict, assign=assign)
+    # Dead reference members a checkpoint may carry (SURVEY §2 rows 4, 6): dropped on load, on ANY load path.
+    _DEAD = ("clip_model.", "dose_encoder.clip_model.", "dose_encoder.prompt_learner.")
+
+    def _drop_dead_keys(self, state_dict, prefix, *_):
+        """load_state_dict pre-hook: runs on the recursive path too (`Trainer.load` / EMA wrappers load through a PARENT module,
+        which never calls a child's `load_state_dict` override), before this module's children look at their keys."""
+        dead = tuple(f"{prefix}unet{i}.{d}" for i in range(self.num_unet) for d in self._DEAD)
+        own = {prefix + k for k in self.state_dict().keys()}       # `dose_encoder.clip_model.visual.*` is live
+        for k in [k for k in state_dict if k.startswith(dead) and k not in own]:
+            del state_dict[k]
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)          # .to() / .cuda() / .half(): packed engine weights would go stale
         self.invalidate()
-        return res
+        return out
+
+    def _param_fingerprint(self):
+        """Detects in-place parameter edits (optimizer / EMA steps, manual `.copy_`) between sample() calls."""
+        return sum(p._version for p in self.parameters()) + sum(b._version for b in self.buffers())
 
     def _unet(self, idx: int) -> Unet:
         return self.unet0 if idx == 0 else self.unet1
@@ -145,6 +156,10 @@ class UnetRes(nn.Module):
         if trunk is None:
             trunk = torch.float16 if self.compute_dtype == torch.bfloat16 else self.compute_dtype
         key = (B, H, W, self.compute_dtype, trunk, str(device))
+        fp = self._param_fingerprint()
+        if fp != self._built_fingerprint:              # weights changed in place since the engines were packed
+            self.invalidate()
+            self._built_fingerprint = fp
         if self._engines and next(iter(self._engines))[0] != key:
             self._engines.clear()          # one resident shape: activations for B=16 at 512^2 are ~25 GB per Unet
         eng = self._engines.get((key, idx))
@@ -340,9 +355,11 @@ class ResidualDiffusion(nn.Module):
 
     # -- sampling --------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def sample(self, x_input=0, batch_size=16, last=True, *, noise=None, trace: Optional[list] = None):
+    def sample(self, x_input=0, batch_size=16, last=True, *, noise=None, trace: Optional[list] = None,
+               steps_limit: Optional[int] = None):
         """src/DADiff.py:1367-1380.  x_input: list [ldct (B,1,H,W) in [0,1]] on a CUDA device.  Returns the list
-        [x_input_plus_noise, denoised] (or every intermediate when last=False), each (B,1,H,W) in [0,1]."""
+        [x_input_plus_noise, denoised] (or every intermediate when last=False), each (B,1,H,W) in [0,1].
+        `steps_limit` (measurement only): stop after the first n timesteps of the schedule (a window of the ancestral loop)."""
         if not isinstance(x_input, (list, tuple)):
             raise TypeError("condition=True: x_input must be a list [ldct] (src/DADiff.py:1371-1376)")
         ldct = x_input[0]
@@ -353,20 +370,49 @@ class ResidualDiffusion(nn.Module):
         dev = ldct.device
         model = self.model
         objective, evals = model._eval_plan(self.objective, self.test_res_or_noise if model.num_unet == 2 else None)
+        model._param_fingerprint() == model._built_fingerprint or model.invalidate()
+        live = {id(e) for e in model._engines.values()}
+        if any(id(e) not in live for _, es in self._graphs.values() for e in es):
+            self._graphs.clear()                     # graphs of dropped engines (and the ~23 GB of buffers they pin) go first
         engs = [model.engine(B, H, W, dev, idx) for idx, _ in evals]
         eng = engs[0]
         for other in engs[1:]:                       # both Unets read the same images (UnetRes.forward, :817-820)
             other.x_t, other.x_input = eng.x_t, eng.x_input
         P = H * W
         plan = self._step_plan()
+        if steps_limit is not None:
+            plan = plan[:max(1, int(steps_limit))]
 
         def get_noise(kind, idx=None, t=None):
             if noise is None:
                 return torch.randn(B, 1, H, W, device=dev)           # same call order as the reference (:1295, :1228)
             if kind == "init":
-                return noise["init"].to(dev, torch.float32)
+                return noise["init"].to(dev, torch.float32, non_blocking=True)
             st = noise["steps"]
-            return (st(t) if callable(st) else st[idx]).to(dev, torch.float32)
+            return st(t) if callable(st) else st[idx]
+
+        main = torch.cuda.current_stream(dev)
+        h2d = {"stream": None, "stage": None, "free": None}
+
+        def put_step_noise(src):
+            """Step noise -> the graph's noise buffer.  Host tensors (north_star: host-supplied noise) go through one device
+            staging buffer on a copy stream, so the H2D of step k+1 runs under step k's kernels; the host tensor is free for
+            its producer when this returns."""
+            if src.is_cuda:
+                noise_buf.copy_(src.to(torch.float32).reshape(B, P))
+                return
+            if h2d["stream"] is None:
+                h2d["stream"] = self._side_stream(dev, "h2d")
+                h2d["stage"] = self._buffer(eng, "noise_stage", B * P).view(B, P)
+                h2d["free"] = torch.cuda.Event()
+                h2d["free"].record(main)
+            cs = h2d["stream"]
+            cs.wait_event(h2d["free"])                   # the previous step's copy out of the staging buffer is done
+            with torch.cuda.stream(cs):
+                h2d["stage"].copy_(src.to(torch.float32).reshape(B, P), non_blocking=True)
+            cs.synchronize()
+            noise_buf.copy_(h2d["stage"])
+            h2d["free"].record(main)
 
         ldct32 = ldct.to(torch.float32).contiguous().view(B, P)
         first = torch.empty(B, P, device=dev, dtype=torch.float32)
@@ -416,7 +462,7 @@ class ResidualDiffusion(nn.Module):
             for e, rows in zip(engs, time_rows):
                 e.time.copy_(rows[i], non_blocking=True)
             if c[3] != 0.:
-                noise_buf.copy_(get_noise("step", i, t).contiguous().view(B, P))
+                put_step_noise(get_noise("step", i, t))
             step_fn()
             if trace is not None:
                 trace.append(dict(t=t, pred_res=taps[0].clone().view(B, 1, H, W), pred_noise=taps[1].clone().view(B, 1, H, W),
@@ -527,11 +573,12 @@ class ResidualDiffusion(nn.Module):
             store[name] = t
         return t[:n]
 
-    def _side_stream(self, dev):
+    def _side_stream(self, dev, name: str = "unet1"):
         st = self.__dict__.setdefault("_side_streams", {})
-        if str(dev) not in st:
-            st[str(dev)] = torch.cuda.Stream(device=dev)
-        return st[str(dev)]
+        key = (str(dev), name)
+        if key not in st:
+            st[key] = torch.cuda.Stream(device=dev)
+        return st[key]
 
     def _graphed(self, engs, fn, variant):
         """Capture one timestep (conditioning + Unet(s) + fused final_conv/update) as a CUDA graph; the step's scalars

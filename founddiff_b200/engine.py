@@ -109,6 +109,7 @@ class UnetEngine:
 
         # ---- build the layer list -----------------------------------------------------------------------
         self.steps: List = []          # list of callables executed in order by forward()
+        self.paths: Dict[str, str] = {}   # Mamba block -> kernel variant its SS2D core runs (asserted by the B = 16 parity test)
         self._acc_users = []
         self._build(sd)
         self.acc_buf = torch.zeros(max(self._acc_size, 1), device=dev, dtype=torch.float32)
@@ -350,6 +351,9 @@ class UnetEngine:
             holder["gram"] = self._acc_view(acc_g, B, heads, 32, 32)
             holder["qk"] = self._acc_view(acc_q, B, 2, C)
         self._acc_users.append(bind)
+
+        self.paths[p] = ("scan_cl time-major B/C" if scan_cl else "dt-fused warp scan" if fuse_dt else
+                         "warp scan + merge" if fuse_merge else "reference-layout" if dt == torch.float32 else "warp scan, unfused merge")
 
         def run():
             ops.ln_modulate(x_in, a, n1w, n1b, sh1, sc1, MS, B, P, C, 1e-5)

@@ -14,10 +14,13 @@ from .io import SliceStream, save_slices
 from .weights import extract_live_weights
 
 
-def load_reference_checkpoint(diffusion, checkpoint, prefer_ema: bool = True) -> Dict[str, int]:
+def load_reference_checkpoint(diffusion, checkpoint, prefer_ema: bool = True, unsafe_pickle: bool = False) -> Dict[str, int]:
     """checkpoint: path to `model-<milestone>.pt` or the loaded dict.  Loads the live denoiser + DA-CLIP weights into
-    `diffusion.model` (dead `clip_model.*` / text tower / `perceploss.*` entries are dropped)."""
-    data = torch.load(checkpoint, map_location="cpu", weights_only=False) if isinstance(checkpoint, (str, os.PathLike)) else checkpoint
+    `diffusion.model` (dead `clip_model.*` / text tower / `perceploss.*` entries are dropped).
+    `Trainer.save` files hold tensors, ints and dicts only, so the file is read with `weights_only=True`; `unsafe_pickle=True`
+    is the explicit opt-in for files that need the full unpickler (arbitrary code execution: trusted files only)."""
+    data = (torch.load(checkpoint, map_location="cpu", weights_only=not unsafe_pickle)
+            if isinstance(checkpoint, (str, os.PathLike)) else checkpoint)
     sd = None
     if isinstance(data, dict):
         if prefer_ema and "ema" in data:

@@ -108,11 +108,13 @@ class Unet(nn.Module):
         for k, v in random_gaussian_state_dict(seed, dim, dim_mults, channels).items():
             _register(self, k, v)
         self._engines: Dict = {}
+        # a post-hook (not a load_state_dict override) also runs when a parent module (GaussianDiffusion, an EMA wrapper) loads
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._engines.clear())
 
-    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
-        res = super().load_state_dict(state_dict, strict=strict, assign=assign)
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
         self._engines.clear()
-        return res
+        return out
 
     def engine(self, B, H, W, device):
         device = torch.device(device)
@@ -460,11 +462,12 @@ class GaussianDiffusion(nn.Module):
 
     def _graphed(self, eng, fn):
         """One timestep as a CUDA graph (captured once per engine; time / coefficients / noise live in device buffers)."""
-        key = id(eng)
-        if self._graphs and next(iter(self._graphs)) != key:
-            self._graphs.clear()
-        g = self._graphs.get(key)
+        # the cache entry holds the engine itself: a dropped engine's id() can be handed to its successor by CPython, and a
+        # graph replayed against freed buffers / old weights fails silently
+        ent = self._graphs.get("step")
+        g = ent[0] if ent is not None and ent[1] is eng else None
         if g is None:
+            self._graphs.clear()
             saved = eng.x_t.clone()
             side = torch.cuda.Stream(device=eng.device)
             side.wait_stream(torch.cuda.current_stream(eng.device))
@@ -477,7 +480,7 @@ class GaussianDiffusion(nn.Module):
             with torch.cuda.graph(g):
                 fn()
             eng.x_t.copy_(saved)
-            self._graphs[key] = g
+            self._graphs["step"] = (g, eng)
         return g.replay
 
     def p_sample_loop(self, shape, **kw):

@@ -146,6 +146,12 @@ assert mine.shape[0] == (3 if rank == 0 else 2)
 init, steps = fdist.global_noise(n, (1, 2, 3), seed=4321, steps=2)
 init2, _ = fdist.global_noise(n, (1, 2, 3), seed=4321, steps=2)
 assert torch.equal(init, init2) and steps.shape == (2, n, 1, 2, 3)
+# a rank draws ITS slices only and gets exactly the numbers the single-process batch holds for them (world-size invariance)
+a, b = fdist.shard_range(n, rank, ws)
+sn = fdist.SliceNoise(4321, range(a, b), (1, 2, 3), pin=False)
+assert torch.equal(sn.init(), init[a:b])
+nxt = sn.steps(2)
+assert torch.equal(nxt(999).clone(), steps[0, a:b]) and torch.equal(nxt(998).clone(), steps[1, a:b])
 out = fdist.gather_slices(mine * 2, n)
 assert torch.equal(out, full * 2), out
 even = fdist.gather_slices(torch.full((2, 1, 2, 3), float(rank)))
@@ -210,6 +216,44 @@ def test_reference_checkpoint_ingestion():
     assert torch.equal(got["unet0.init_conv.weight"], sd["init_conv.weight"])
     load_reference_checkpoint(diff, ckpt, prefer_ema=False)
     assert torch.equal(model.state_dict()["unet0.init_conv.weight"], other["init_conv.weight"])
+
+
+def test_parent_module_load_path_filters_dead_keys_and_invalidates():
+    """`Trainer.load` / EMA wrappers call load_state_dict on a PARENT module; nn.Module then recurses with _load_from_state_dict and
+    never calls a child's load_state_dict override.  The dead-key filter and the engine invalidation are hooks, so they run on that
+    path too; in-place parameter edits are caught by the version fingerprint."""
+    import torch
+    from founddiff_b200.diffusion import ResidualDiffusion, UnetRes
+    from founddiff_b200.gaussian import GaussianDiffusion, Unet as GUnet
+    m = UnetRes(dim=64, dim_mults=(1, 2, 4, 8), num_unet=1, condition=True, objective='pred_res', test_res_or_noise='res')
+    d = ResidualDiffusion(m, image_size=64, timesteps=1000, sampling_timesteps=2, objective='pred_res', condition=True, sum_scale=0.01)
+    m._engines[("stale", 0)] = object()
+    m._daclip = {0: object()}
+    sd = dict(d.state_dict())
+    sd["model.unet0.clip_model.visual.conv1.weight"] = torch.zeros(3)              # dead members of a real checkpoint
+    sd["model.unet0.dose_encoder.prompt_learner.ctx"] = torch.zeros(2, 16, 512)
+    sd["model.unet0.dose_encoder.clip_model.transformer.resblocks.0.ln_1.weight"] = torch.zeros(3)
+    sd["model.unet0.init_conv.bias"] = torch.full_like(sd["model.unet0.init_conv.bias"], 3.0)
+    res = d.load_state_dict(sd)                                                    # through the parent, strict
+    assert not res.missing_keys and not res.unexpected_keys
+    assert m._engines == {} and m._daclip is None, "engines / DA-CLIP encoder survived a parent-path load"
+    assert float(m.unet0.init_conv.bias[0]) == 3.0
+    sd["model.unet0.not_a_member"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        d.load_state_dict(sd)                                                      # real strangers still raise
+    fp = m._param_fingerprint()
+    with torch.no_grad():
+        m.unet0.init_conv.bias.mul_(2.0)
+    assert m._param_fingerprint() != fp
+    m._engines[("stale", 0)] = object()
+    m.to(torch.float32)
+    assert m._engines == {}
+    # secondary path: same hook on the lucidrains Unet, and the graph cache is keyed on the engine object itself
+    gu = GUnet(dim=64, dim_mults=(1, 2, 4, 8), channels=1)
+    gd = GaussianDiffusion(gu, image_size=32, timesteps=1000, sampling_timesteps=2)
+    gu._engines["stale"] = object()
+    gd.load_state_dict(gd.state_dict())
+    assert gu._engines == {}
 
 
 def test_two_unet_checkpoint_ingestion_and_eval_plans():

@@ -312,3 +312,51 @@ def test_ragged_geometry_vs_reference(model, dt):
     assert rel(outs[0], g["outs"][0]) < 1e-6
     assert abs(O.psnr(outs[-1].cpu(), g["ndct"]) - O.psnr(g["outs"][-1], g["ndct"])) < 0.05
     assert rel(outs[-1], g["outs"][-1]) < GATE[dt]
+
+
+def test_benchmarked_batch16_vs_oracle(model, state_dict):
+    """BASELINE config 2 exactly as bench.py runs it: B = 16 x 512x512, bf16, DDIM-2, bench.py's synthetic slices and per-slice host
+    noise.  At this batch the engine takes the many-row code paths that B <= 2 tests never reach, so the
+    composition is checked here: slices 0, 7 and 15 against the CPU oracle run on those three slices alone (slices are independent
+    chains, src/DADiff.py:1823-1825 feeds them one at a time)."""
+    import bench
+    from founddiff_b200 import distributed as fdist
+    B, H = 16, 512
+    _, ldct = bench.synth_slices(B, H, H)
+    noise = fdist.global_noise(B, (1, H, H), 4321)[0]
+    set_mode(model, torch.bfloat16, sampling_timesteps=2)
+    trace = []
+    out = model.sample([ldct.cuda()], batch_size=B, last=True, noise={"init": noise}, trace=trace)[-1]
+    eng = model.model.engine(B, H, H, "cuda")
+    print("engine paths at B=16:", eng.paths)
+    assert eng.B == 16 and len(eng.paths) == 9 and all(v != "reference-layout" for v in eng.paths.values()), eng.paths
+    pick = [0, 7, 15]
+    otrace = []
+    ref = O.sample(state_dict, ldct[pick], noise[pick], sampling_timesteps=2, trace=otrace)[-1]
+    for a, b in zip(trace, otrace):
+        assert a["t"] == b["t"]
+        for k in ("pred_res", "pred_noise"):
+            for j, i in enumerate(pick):
+                r = rel(a[k][i], b[k][j])
+                print(f"B=16 512^2 bf16 t={a['t']} slice {i} {k}: rel-L2 {r:.3e}")
+                assert r < GATE[torch.bfloat16] * (1 if k == "pred_res" else 2), (k, a["t"], i, r)
+    for j, i in enumerate(pick):
+        assert abs(O.psnr(out[i:i + 1].cpu(), ldct[i:i + 1]) - O.psnr(ref[j:j + 1], ldct[i:i + 1])) < 0.05
+
+
+def test_batch_composition_does_not_change_a_slice(model):
+    """north_star "bit-for-bit-same-noise": with the same per-slice noise a slice's result is BIT-IDENTICAL whether it is sampled
+    alone, at another position of a larger batch, or twice — every cross-pixel reduction (GroupNorm sums, Gram matrices, LayerNorm
+    rows) is accumulated in an order that depends on the slice only, never on the batch or on the thread-block schedule."""
+    from founddiff_b200 import distributed as fdist
+    H = 128
+    g = torch.Generator().manual_seed(5)
+    ldct = torch.rand(6, 1, H, H, generator=g)
+    noise = fdist.global_noise(6, (1, H, H), 99)[0]
+    for dt in (torch.float32, torch.bfloat16):
+        set_mode(model, dt, sampling_timesteps=2)
+        full = model.sample([ldct.cuda()], batch_size=6, last=True, noise={"init": noise})[-1]
+        again = model.sample([ldct.cuda()], batch_size=6, last=True, noise={"init": noise})[-1]
+        assert torch.equal(full, again), f"{dt}: two identical calls differ (max {float((full - again).abs().max()):.3e})"
+        part = model.sample([ldct[2:5].cuda()], batch_size=3, last=True, noise={"init": noise[2:5]})[-1]
+        assert torch.equal(part, full[2:5]), f"{dt}: slices 2..4 differ between B=3 and B=6 (max {float((part - full[2:5]).abs().max()):.3e})"
