@@ -284,7 +284,8 @@ def run_b200(args):
             # noise per rank); --window 0 runs all 1000 with the noise streamed from the host generator thread
             self.window = (window if window > 0 else diffusion.num_timesteps) if self.ancestral else None
             self.evals = min(self.window, diffusion.num_timesteps) if self.ancestral else S      # Unet evaluations per call
-            self.n_noise_steps = (self.evals - 1) if self.ancestral else 0
+            # every timestep with t > 0 takes a noise tensor (src/DADiff.py:1228): all of a window, all but the last of a full run
+            self.n_noise_steps = min(self.evals, diffusion.num_timesteps - 1) if self.ancestral else 0
             self.sn = fdist.SliceNoise(4321, range(a, b_), (1, H, H))
             self.noise_host = {"init": self.sn.init()}
             self.stream_steps = self.n_noise_steps > 64          # full schedule: produced on the fly by the host thread
@@ -362,8 +363,14 @@ def run_b200(args):
     extras = {}
     if not args.no_extras and args.sampling_timesteps == 2 and args.objective == "pred_res":
         for key, S, steps in (("ddim10", 10, 3), ("ancestral", 1000, 2)):
-            wl = Workload(S, args.window)
-            m, me = wl.measure(steps, 1, 1)
+            try:
+                wl = Workload(S, args.window)
+                m, me = wl.measure(steps, 1, 1)
+            except Exception as e:          # an extra row never takes the headline line down with it
+                if ws > 1:
+                    raise                   # (collectives inside: every rank must fail together)
+                extras[key] = {"error": f"{type(e).__name__}: {e}"}
+                continue
             extras[key] = {"workload": wl.name(), "steps": steps, "warmup": 1, "unet_evals_per_call": wl.evals,
                            "ms_per_call": m / steps, "value": n_global * steps / (m / 1e3), "unit": UNIT,
                            "per_slice_step_us": (m / steps) * 1e3 / (B * wl.evals),
