@@ -1,0 +1,645 @@
+// TIME-MAJOR SS2D core for the 16-bit storage modes (src/emamba2.py:295-367: EfficientScan -> x_proj / dt_proj ->
+// SelectiveScan -> EfficientMerge), laid out for a channel-per-lane scan:
+//
+//   xs_tm   (B, 4, L, D)   16-bit   scan input u: direction k, step l, D channels contiguous
+//   xdbl_tm (B, 4, L, XR)  fp32     per step: [dt low-rank input (R, only when dt_proj is fused into the scan) | B (N) | C (N)]
+//   dts_tm  (B, 4, L, D)   16-bit   delta = softplus(dt_proj + bias), only for the levels whose dt_rank is too large to fuse
+//
+// Why time-major.  In the reference's (B, 4D, L) layout a (batch, channel) row is contiguous in l, which suits a warp that
+// scans ONE row cooperatively (round 1: 5 shuffle rounds per state and chunk, ~15 issue slots per state update, 0.27 of the
+// HBM roof at the full-resolution level).  With the channel index fastest a LANE owns a channel and walks time sequentially
+// with its states in registers (FMUL, MUFU.EX2, FMUL, FFMA, FFMA per state update); a warp's 32 lanes read 64 contiguous
+// bytes per step, B / C / dt-input of the step are warp-uniform broadcasts from shared memory, the depthwise convolution
+// writes its NHWC rows unchanged (a pixel permutation, no transpose), x_proj becomes a plain K-contiguous GEMM and the
+// EfficientMerge store is 64 contiguous bytes of one pixel.
+//
+// Rows are long (L = 65536 at 512^2) and there are few of them (8192 channel rows at level 0 = 256 warps), so each row is cut
+// into S SEGMENTS that run concurrently.  The state entering a segment is obtained EXACTLY by a carry pass (pass 1): for each
+// segment but the last, h_end(from h = 0) = sum_t (prod_{s>t} a_s) b_t is accumulated walking BACKWARDS from the segment end,
+// together with P = prod a_s = 2^(A2 * sum dt).  The walk stops once the slowest state of every channel of the block has decayed
+// below 2^-30 (the remaining terms are below fp32 round-off of the sum; P is then 0 to the same accuracy); a channel that decays
+// slower than the segment is simply walked to the segment start, i.e. the result never depends on an assumed memory length.
+// Pass 2 folds the carries of the preceding segments (h = P_j h + hloc_j, a few FMAs per lane) and scans forward.
+#include <stdlib.h>
+#include <type_traits>
+
+#include "fd_common.cuh"
+
+namespace {
+
+// =========================================================================================================
+// K1: depthwise 3x3 + bias + SiLU over the x half of xz (NHWC, row pitch ld) -> xs_tm.
+// Register sliding window as dwconv3x3_nhwc_v2_kernel (fd_attn.cu): a thread owns a horizontal pixel PAIR (even x, x+1) x 4
+// channels and walks down 32 rows with a 3-row ring of raw 8-byte loads.  The two pixels of a pair belong to directions k and
+// k + 2 at the SAME step l, rows alternate between the row-major (even y) and column-major (odd y) sub-grids.
+constexpr int TM_V = 4;
+constexpr int TM_RY = 32;
+
+template <typename T> FD_DEVINL uint2 tm_ld_raw(const T* p) { return *reinterpret_cast<const uint2*>(p); }
+template <typename T> FD_DEVINL void tm_cvt(uint2 r, float (&v)[4]) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&r.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+        const float2 a = __half22float2(*reinterpret_cast<__half2*>(&r.x));
+        const float2 b = __half22float2(*reinterpret_cast<__half2*>(&r.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+}
+template <typename T> FD_DEVINL void tm_st(T* p, const float (&v)[4]) {
+    uint2 r;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+    } else {
+        __half2 a = fd_floats2half2_sat(v[0], v[1]), b = fd_floats2half2_sat(v[2], v[3]);
+        r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint2*>(p) = r;
+}
+
+template <typename T, bool EDGE>
+FD_DEVINL void dwtm_rows(const T* __restrict__ in_b, T* __restrict__ out_b, const float (&wr)[9][TM_V], const float (&bs)[TM_V],
+                         int H, int W, int ld, int D, int x, int y0, int y1, bool has_l, bool has_2, int pf) {
+    const int H2 = H >> 1, W2 = W >> 1, x2 = x >> 1;
+    const long L = (long)H2 * W2;
+    const int ymax = min(H - 1, y1);
+    int yi = y0 - 1;
+    yi -= ((yi % 3) + 3) % 3;                            // round down to a multiple of 3
+    const long rowe = (long)W * ld;
+    const int offl = (!EDGE || has_l) ? ld : 0, off1 = ld, off2 = (!EDGE || has_2) ? 2 * ld : 0;   // W is even: x + 1 < W always
+    const T* p = in_b + (long)min(max(yi, 0), ymax) * rowe + (long)x * ld;      // row the next fetch reads (clamped into the image)
+    int yf = yi;
+    float acc[3][2][TM_V];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int e = 0; e < TM_V; ++e) acc[r][px][e] = 0.f;
+    uint2 ring[3][4];
+    auto fetch = [&](auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;
+        ring[S][0] = tm_ld_raw<T>(p - offl);
+        ring[S][1] = tm_ld_raw<T>(p);
+        ring[S][2] = tm_ld_raw<T>(p + off1);
+        ring[S][3] = tm_ld_raw<T>(p + off2);
+        if (pf > 0 && yf >= 0 && yf + pf <= ymax) {      // block-uniform: pull the row `pf` steps further down into L2
+            const T* pp = p + (long)pf * rowe;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + off1));
+        }
+        p += (yf >= 0 && yf < ymax) ? rowe : 0;          // block-uniform
+        ++yf;
+    };
+    auto step = [&](int yrow, auto slot_c) {
+        constexpr int S = decltype(slot_c)::value;       // == yrow mod 3
+        constexpr int S1 = (S + 1) % 3, S2 = (S + 2) % 3;
+        float v[4][TM_V];
+        {
+            const bool rv = yrow >= 0 && yrow < H;       // block-uniform; straight-line masking keeps the loads in flight
+            const bool ok[4] = {rv && (!EDGE || has_l), rv, rv, rv && (!EDGE || has_2)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint2 r = ring[S][j];
+                r.x = ok[j] ? r.x : 0u;
+                r.y = ok[j] ? r.y : 0u;
+                tm_cvt<T>(r, v[j]);
+            }
+        }
+        fetch(slot_c);
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+            for (int e = 0; e < TM_V; ++e) {
+                float a1 = fmaf(v[px][e], wr[0][e], bs[e]);                        // output row yrow+1: first contribution
+                a1 = fmaf(v[px + 1][e], wr[1][e], a1);
+                acc[S1][px][e] = fmaf(v[px + 2][e], wr[2][e], a1);
+                float a0 = fmaf(v[px][e], wr[3][e], acc[S][px][e]);               // output row yrow
+                a0 = fmaf(v[px + 1][e], wr[4][e], a0);
+                acc[S][px][e] = fmaf(v[px + 2][e], wr[5][e], a0);
+                float a2 = fmaf(v[px][e], wr[6][e], acc[S2][px][e]);              // output row yrow-1 (complete after this)
+                a2 = fmaf(v[px + 1][e], wr[7][e], a2);
+                acc[S2][px][e] = fmaf(v[px + 2][e], wr[8][e], a2);
+            }
+        const int yo = yrow - 1;
+        if (yo >= y0 && yo < y1) {                       // block-uniform
+            const int yh = yo >> 1;
+            // even rows: directions 0 / 2, row-major l = (y/2) W2 + x/2; odd rows: directions 1 / 3, column-major l = (x/2) H2 + y/2
+            const long off = (yo & 1) ? (L + (long)x2 * H2 + yh) * D : ((long)yh * W2 + x2) * D;
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                float o[TM_V];
+#pragma unroll
+                for (int e = 0; e < TM_V; ++e) o[e] = fd_silu16(acc[S2][px][e]);
+                tm_st<T>(out_b + off + (px ? 2 * L * D : 0), o);
+            }
+        }
+    };
+    fetch(std::integral_constant<int, 0>{});
+    fetch(std::integral_constant<int, 1>{});
+    fetch(std::integral_constant<int, 2>{});
+    for (; yi <= y1; yi += 3) {
+        step(yi, std::integral_constant<int, 0>{});
+        if (yi + 1 <= y1) step(yi + 1, std::integral_constant<int, 1>{});
+        if (yi + 2 <= y1) step(yi + 2, std::integral_constant<int, 2>{});
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2) dwconv_tm_kernel(const T* __restrict__ xz, int ld, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, T* __restrict__ xs, int H, int W,
+                                                           int D, int pf) {
+    const int NV = D / TM_V;
+    const int W2 = W >> 1;
+    const long f2 = (long)blockIdx.x * 256 + threadIdx.x;   // index over (pixel pair, channel vector)
+    const bool live = f2 < (long)W2 * NV;
+    const long f2c = live ? f2 : 0;
+    const int cv = (int)(f2c % NV), x = 2 * (int)(f2c / NV);
+    const int y0 = blockIdx.y * TM_RY, y1 = min(H, y0 + TM_RY);
+    float wr[9][TM_V], bs[TM_V];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long)t * D + cv * TM_V));
+        wr[t][0] = wv.x; wr[t][1] = wv.y; wr[t][2] = wv.z; wr[t][3] = wv.w;
+    }
+    {
+        const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + cv * TM_V)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bs[0] = bv.x; bs[1] = bv.y; bs[2] = bv.z; bs[3] = bv.w;
+    }
+    const bool has_l = x > 0, has_2 = x + 2 < W;
+    const T* in_b = xz + (long)blockIdx.z * H * W * ld + cv * TM_V;
+    T* out_b = xs + (long)blockIdx.z * H * W * D + cv * TM_V;          // 4 L D == H W D elements per sample
+    if (!live) return;
+    if (__any_sync(__activemask(), !(has_l && has_2))) dwtm_rows<T, true>(in_b, out_b, wr, bs, H, W, ld, D, x, y0, y1, has_l, has_2, pf);
+    else dwtm_rows<T, false>(in_b, out_b, wr, bs, H, W, ld, D, x, y0, y1, true, true, pf);
+}
+
+// =========================================================================================================
+// K2: x_proj (+ dt_proj for the levels whose dt_rank is not fused into the scan) on time-major input.
+//   stage 1:  X_dbl[l, c] = sum_d xs_tm[l, d] Wx[k][c, d]       M = 128 steps per block (16 per warp), N = CCp, K = D
+//   stage 2:  dts[l, d]   = softplus(sum_r X_dbl[l, r] Wdt[k][d, r] + bias[d])   (WITH_DT)   M = steps, N = D, K = Rp
+// mma.sync m16n8k16, fp32 accumulate; both operands are K-contiguous, so plain (non-transposing) ldmatrix feeds them.  The
+// stage-1 accumulator fragments of the dt columns ARE the stage-2 A fragments (C layout of two adjacent n-tiles = A layout
+// of one k-tile), so X_dbl's dt part never leaves the registers.  Bound by the single read of xs_tm.
+constexpr int XM_STEPS = 128, XM_KC = 64, XM_LD = XM_KC + 8, XM_STAGES = 3;
+
+FD_DEVINL void tm_cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+FD_DEVINL float tm_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+FD_DEVINL float tm_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// log1p(exp(x)), branch-free, 2 MUFU ops (same form as fd_scan.cu's fast_softplus; threshold 20 as selective_scan_fn)
+FD_DEVINL float tm_softplus(float x) {
+    const float y = tm_ex2(x * 1.4426950408889634f);
+    const float w = 1.f + y;
+    const float corr = (y < 1.f) ? (y - (w - 1.f)) * (1.f - y) : 0.f;
+    const float r = fmaf(tm_lg2(w), 0.6931471805599453f, corr);
+    return x > 20.f ? x : r;
+}
+template <typename T> FD_DEVINL uint32_t tm_pack2(float a, float b) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __half2 h = fd_floats2half2_sat(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+
+template <typename T, int NT, bool WITH_DT>      // NT = CCp / 8 (even)
+__global__ void __launch_bounds__(256) x_proj_tm_kernel(const T* __restrict__ xs, const T* __restrict__ xw16, float* __restrict__ xdbl,
+                                                        int D, int L, int CC, int col0, int out_ld, const T* __restrict__ dw16,
+                                                        T* __restrict__ dts, const float* __restrict__ dt_bias, int Rp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int CCp = NT * 8;
+    T* s_a = reinterpret_cast<T*>(smem_raw);                     // [XM_STAGES][XM_STEPS][XM_LD]
+    T* s_w = s_a + XM_STAGES * XM_STEPS * XM_LD;                 // [XM_STAGES][CCp][XM_LD]
+    const int bk = blockIdx.y, k = bk & 3;
+    const int l0 = blockIdx.x * XM_STEPS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const T* xr = xs + (long)bk * L * D;
+    const T* wx = xw16 + (long)k * CCp * D;
+    const int nchunks = D / XM_KC;
+
+    auto stage = [&](int ch, int buf) {
+        const int d0 = ch * XM_KC;
+        T* sa = s_a + buf * XM_STEPS * XM_LD;
+        T* sw = s_w + buf * CCp * XM_LD;
+        for (int i = tid; i < XM_STEPS * (XM_KC / 8); i += 256) {
+            const int r = i / (XM_KC / 8), v = i % (XM_KC / 8);
+            const bool ok = l0 + r < L;
+            tm_cp_async16(sa + r * XM_LD + v * 8, ok ? xr + (long)(l0 + r) * D + d0 + v * 8 : xr, ok);
+        }
+        for (int i = tid; i < CCp * (XM_KC / 8); i += 256) {
+            const int r = i / (XM_KC / 8), v = i % (XM_KC / 8);
+            tm_cp_async16(sw + r * XM_LD + v * 8, wx + (long)r * D + d0 + v * 8, true);
+        }
+    };
+
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < XM_STAGES - 1; ++s) {
+        if (s < nchunks) stage(s, s);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int ch = 0; ch < nchunks; ++ch) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(XM_STAGES - 2) : "memory");
+        __syncthreads();                                          // chunk ch landed; everyone is done with chunk ch-1's buffer
+        if (ch + XM_STAGES - 1 < nchunks) stage(ch + XM_STAGES - 1, (ch + XM_STAGES - 1) % XM_STAGES);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const T* sa = s_a + (ch % XM_STAGES) * XM_STEPS * XM_LD;
+        const T* sw = s_w + (ch % XM_STAGES) * CCp * XM_LD;
+#pragma unroll
+        for (int ks = 0; ks < XM_KC / 16; ++ks) {
+            uint32_t afr[4];
+            ldmatrix_x4(afr, sa + (warp * 16 + (lane & 15)) * XM_LD + ks * 16 + 8 * (lane >> 4));
+#pragma unroll
+            for (int np = 0; np < NT / 2; ++np) {
+                uint32_t bfr[4];         // (n 0-7, k 0-7), (n 0-7, k 8-15), (n 8-15, k 0-7), (n 8-15, k 8-15)
+                ldmatrix_x4(bfr, sw + (np * 16 + (lane & 7) + 8 * (lane >> 4)) * XM_LD + ks * 16 + 8 * ((lane >> 3) & 1));
+                mma_16816<T>(acc[2 * np], afr, bfr[0], bfr[1]);
+                mma_16816<T>(acc[2 * np + 1], afr, bfr[2], bfr[3]);
+            }
+        }
+    }
+    // stage-1 epilogue: columns [col0, CC) of X_dbl, fp32, time-major rows of out_ld floats
+    const int r0 = l0 + warp * 16 + g, r1 = r0 + 8;
+    float* o0 = xdbl + ((long)bk * L + r0) * out_ld - col0;
+    float* o1 = xdbl + ((long)bk * L + r1) * out_ld - col0;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int col = nt * 8 + 2 * t4;
+        if (col >= col0 && col < CC) {
+            if (r0 < L) *reinterpret_cast<float2*>(o0 + col) = make_float2(acc[nt][0], acc[nt][1]);
+            if (r1 < L) *reinterpret_cast<float2*>(o1 + col) = make_float2(acc[nt][2], acc[nt][3]);
+        }
+    }
+    if constexpr (WITH_DT) {
+        // stage 2 straight from the accumulator fragments (dt input rounded to the storage type, as the fp32 reference's
+        // consumers see it after a 16-bit x_dbl); columns >= R meet zero rows of the padded dw16
+        uint32_t afr[2][4];
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+            if (kt * 16 < Rp && 2 * kt + 1 < NT) {
+                afr[kt][0] = tm_pack2<T>(acc[2 * kt][0], acc[2 * kt][1]);
+                afr[kt][1] = tm_pack2<T>(acc[2 * kt][2], acc[2 * kt][3]);
+                afr[kt][2] = tm_pack2<T>(acc[2 * kt + 1][0], acc[2 * kt + 1][1]);
+                afr[kt][3] = tm_pack2<T>(acc[2 * kt + 1][2], acc[2 * kt + 1][3]);
+            } else {
+                afr[kt][0] = afr[kt][1] = afr[kt][2] = afr[kt][3] = 0u;
+            }
+        }
+        const T* wd = dw16 + (long)k * D * Rp;
+        const float* bk_bias = dt_bias + (long)k * D;
+        T* d0p = dts + ((long)bk * L + r0) * D;
+        T* d1p = dts + ((long)bk * L + r1) * D;
+        for (int nd = 0; nd < D / 8; ++nd) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            const T* wrow = wd + (long)(nd * 8 + g) * Rp + 2 * t4;
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                if (kt * 16 < Rp) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + kt * 16);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + kt * 16 + 8);
+                    mma_16816<T>(o, afr[kt], b0, b1);
+                }
+            }
+            const int d = nd * 8 + 2 * t4;
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(bk_bias + d));
+            if (r0 < L) *reinterpret_cast<uint32_t*>(d0p + d) = tm_pack2<T>(tm_softplus(o[0] + bb.x), tm_softplus(o[1] + bb.y));
+            if (r1 < L) *reinterpret_cast<uint32_t*>(d1p + d) = tm_pack2<T>(tm_softplus(o[2] + bb.x), tm_softplus(o[3] + bb.y));
+        }
+    }
+}
+
+// =========================================================================================================
+// K3: segmented channel-per-lane selective scan (+ EfficientMerge store).  See the file header.
+// Block = WARPS x 32 lanes = CHB consecutive channels of one (sample, direction); grid (segments, D / CHB, B * 4).
+// Per 32-step chunk the block stages u (and delta when it is not fused) [32][CHB] 16-bit and the X_dbl rows [32][XR] fp32
+// with cp.async, double buffered, one barrier per chunk.  RDT > 0: delta = softplus(dt_w[d, :RDT] . xdbl[l, :RDT] + bias)
+// is formed in registers (RDT FMAs + 2 MUFU per step).
+constexpr int SC_T = 32;           // steps per staged chunk
+constexpr int SC_WARPS = 4;
+constexpr int SC_CHB = SC_WARPS * 32;
+constexpr float SC_DECAYED = -30.f;            // log2 of the decay below which a carry is dropped
+
+template <typename T> FD_DEVINL float tm_ld16(const T* p) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) return __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(p)) << 16);
+    else return __half2float(*p);
+}
+
+template <typename T, int NS, int RDT, bool CARRY>
+__global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
+    const T* __restrict__ u_tm, const T* __restrict__ dts_tm, const float* __restrict__ xdbl, const float* __restrict__ A,
+    const float* __restrict__ dt_w, const float* __restrict__ dt_bias, const float* __restrict__ Dskip, float* __restrict__ carry,
+    T* __restrict__ y, int D, int L, int H, int W, int S, int seg_len) {
+    constexpr int XR = RDT + 2 * NS;                    // floats per step in xdbl
+    constexpr bool HAS_DT = RDT == 0;                   // delta comes from dts_tm
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_x = reinterpret_cast<float*>(smem_raw);                              // [2][SC_T][XR]
+    T* s_u = reinterpret_cast<T*>(s_x + 2 * SC_T * XR);                           // [2][SC_T][SC_CHB]
+    T* s_d = s_u + 2 * SC_T * SC_CHB;                                             // [2][SC_T][SC_CHB]   (HAS_DT)
+    const int tid = threadIdx.x;
+    const int seg = blockIdx.x, bk = blockIdx.z, k = bk & 3, b = bk >> 2;
+    const int ch0 = blockIdx.y * SC_CHB;
+    const int dloc = ch0 + tid;                          // channel within the direction group
+    const int d = k * D + dloc;                          // row of A / dt_w / bias / D
+    const int t_begin = seg * seg_len, t_end = min(L, t_begin + seg_len);
+    const int nch = (t_end - t_begin + SC_T - 1) / SC_T;
+    const T* ug = u_tm + (long)bk * L * D + ch0;
+    const T* dg = HAS_DT ? dts_tm + (long)bk * L * D + ch0 : nullptr;
+    const float* xg = xdbl + (long)bk * L * XR;
+
+    float A2[NS], h[NS];
+    float a2max = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NS; ++n) {
+        A2[n] = A[(long)d * NS + n] * 1.4426950408889634f;
+        a2max = fmaxf(a2max, A2[n]);
+        h[n] = 0.f;
+    }
+    float wdt[RDT > 0 ? RDT : 1];
+    float bias = 0.f;
+    if constexpr (RDT > 0) {
+#pragma unroll
+        for (int r = 0; r < RDT; ++r) wdt[r] = dt_w[(long)d * RDT + r];
+        bias = dt_bias[d];
+    }
+    const float Dd = Dskip[d];
+
+    auto stage = [&](int c, int buf) {                   // chunk c of this segment: steps [t_begin + c*SC_T, +SC_T), zero-filled past t_end
+        const int t0 = t_begin + c * SC_T;
+        float* sx = s_x + buf * SC_T * XR;
+        for (int i = tid; i < SC_T * XR / 4; i += SC_CHB) {           // rows are contiguous in global memory: one flat run
+            const bool ok = t0 + (i * 4) / XR < t_end;
+            tm_cp_async16(sx + i * 4, ok ? xg + (long)t0 * XR + i * 4 : xg, ok);
+        }
+        T* su = s_u + buf * SC_T * SC_CHB;
+        T* sd = s_d + buf * SC_T * SC_CHB;
+        for (int i = tid; i < SC_T * (SC_CHB / 8); i += SC_CHB) {
+            const int r = i / (SC_CHB / 8), v = i % (SC_CHB / 8);
+            const bool ok = t0 + r < t_end;
+            tm_cp_async16(su + r * SC_CHB + v * 8, ok ? ug + (long)(t0 + r) * D + v * 8 : ug, ok);
+            if constexpr (HAS_DT) tm_cp_async16(sd + r * SC_CHB + v * 8, ok ? dg + (long)(t0 + r) * D + v * 8 : dg, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // delta and u of (chunk buffer, step s) for this lane's channel
+    auto load_step = [&](int buf, int s, float& dt, float& u) {
+        const float* xr = s_x + (buf * SC_T + s) * XR;
+        if constexpr (RDT > 0) {
+            float t = bias;
+#pragma unroll
+            for (int r = 0; r < RDT; r += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(xr + r);
+                t = fmaf(wdt[r], v.x, t); t = fmaf(wdt[r + 1], v.y, t); t = fmaf(wdt[r + 2], v.z, t); t = fmaf(wdt[r + 3], v.w, t);
+            }
+            dt = tm_softplus(t);
+        } else {
+            dt = tm_ld16<T>(s_d + (buf * SC_T + s) * SC_CHB + tid);
+        }
+        u = tm_ld16<T>(s_u + (buf * SC_T + s) * SC_CHB + tid);
+    };
+
+    if constexpr (CARRY) {
+        // ---- pass 1: backward walk from the segment end; acc_n = sum_t 2^(A2_n * cum_t) dt_t u_t B_tn, cum_t = sum_{s > t} dt_s
+        float cum = 0.f;
+        bool done = false, early = false;
+        stage(nch - 1, (nch - 1) & 1);
+        for (int c = nch - 1; c >= 0; --c) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (__syncthreads_and(done)) { early = true; break; }       // chunk c visible; every channel of the block has decayed
+            if (c > 0) stage(c - 1, (c - 1) & 1);
+            const int buf = c & 1;
+            const int ns = min(SC_T, t_end - (t_begin + c * SC_T));
+#pragma unroll 4
+            for (int s = ns - 1; s >= 0; --s) {
+                float dt, u;
+                load_step(buf, s, dt, u);
+                const float du = dt * u;
+                const float* pb = s_x + (buf * SC_T + s) * XR + RDT;
+#pragma unroll
+                for (int n = 0; n < NS; n += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(pb + n);
+                    h[n] = fmaf(tm_ex2(A2[n] * cum), du * b4.x, h[n]);
+                    h[n + 1] = fmaf(tm_ex2(A2[n + 1] * cum), du * b4.y, h[n + 1]);
+                    h[n + 2] = fmaf(tm_ex2(A2[n + 2] * cum), du * b4.z, h[n + 2]);
+                    h[n + 3] = fmaf(tm_ex2(A2[n + 3] * cum), du * b4.w, h[n + 3]);
+                }
+                cum += dt;
+            }
+            done = a2max * cum < SC_DECAYED;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        float* cb = carry + (((long)bk * S + seg) * 2) * NS * D + dloc;
+#pragma unroll
+        for (int n = 0; n < NS; ++n) {
+            cb[(long)n * D] = h[n];
+            cb[(long)(NS + n) * D] = early ? 0.f : tm_ex2(A2[n] * cum);
+        }
+    } else {
+        // ---- pass 2: fold the carries of the preceding segments, then scan forward and store through EfficientMerge
+        for (int j = 0; j < seg; ++j) {
+            const float* cb = carry + (((long)bk * S + j) * 2) * NS * D + dloc;
+#pragma unroll
+            for (int n = 0; n < NS; ++n) h[n] = fmaf(cb[(long)(NS + n) * D], h[n], cb[(long)n * D]);
+        }
+        const int H2 = H >> 1, W2 = W >> 1;
+        const int mdiv = (k & 1) ? H2 : W2;
+        int mq = t_begin / mdiv, mr = t_begin - mq * mdiv;
+        T* ybase = y + (long)b * H * W * D + dloc;
+        stage(0, 0);
+        for (int c = 0; c < nch; ++c) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                             // chunk c visible; every warp is past chunk c-1
+            if (c + 1 < nch) stage(c + 1, (c + 1) & 1);
+            const int buf = c & 1;
+            const int ns = min(SC_T, t_end - (t_begin + c * SC_T));
+#pragma unroll 4
+            for (int s = 0; s < ns; ++s) {
+                float dt, u;
+                load_step(buf, s, dt, u);
+                const float du = dt * u;
+                const float* pb = s_x + (buf * SC_T + s) * XR + RDT;
+                const float* pc = pb + NS;
+                float y0 = Dd * u, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+#pragma unroll
+                for (int n = 0; n < NS; n += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(pb + n);
+                    const float4 c4 = *reinterpret_cast<const float4*>(pc + n);
+                    h[n] = fmaf(tm_ex2(dt * A2[n]), h[n], du * b4.x);
+                    y0 = fmaf(h[n], c4.x, y0);
+                    h[n + 1] = fmaf(tm_ex2(dt * A2[n + 1]), h[n + 1], du * b4.y);
+                    y1 = fmaf(h[n + 1], c4.y, y1);
+                    h[n + 2] = fmaf(tm_ex2(dt * A2[n + 2]), h[n + 2], du * b4.z);
+                    y2 = fmaf(h[n + 2], c4.z, y2);
+                    h[n + 3] = fmaf(tm_ex2(dt * A2[n + 3]), h[n + 3], du * b4.w);
+                    y3 = fmaf(h[n + 3], c4.w, y3);
+                }
+                int hh, ww;                              // EfficientMerge coordinates of step l (src/emamba2.py:207-210, 253-256)
+                if (k & 1) { ww = 2 * mq + (k >> 1); hh = 2 * mr + 1; }
+                else       { hh = 2 * mq; ww = 2 * mr + (k >> 1); }
+                fd_st(ybase + ((long)hh * W + ww) * D, (y0 + y1) + (y2 + y3));
+                if (++mr == mdiv) { mr = 0; ++mq; }
+            }
+        }
+    }
+}
+
+int pick_segments(int B, int D, int L) {
+    // enough warps to fill the machine (>= ~16 per SM), segments not shorter than 2048 steps (the carry pass walks ~the
+    // memory length of the slowest channel of a block per segment, so short segments pay it proportionally more often)
+    static const int forced = getenv("FD_SCAN_SEGMENTS") ? atoi(getenv("FD_SCAN_SEGMENTS")) : 0;
+    if (forced > 0) return forced;
+    const long base_warps = (long)B * 4 * D / 32;
+    int S = 1;
+    while (S < 64 && base_warps * S < 148L * 24 && L / (2 * S) >= 2048) S *= 2;
+    return S;
+}
+
+template <typename T, int NS, int RDT>
+int scan_tm_launch(const void* u_tm, const void* dts_tm, const float* xdbl, const float* A, const float* dt_w, const float* dt_bias,
+                   const float* Dskip, float* carry, size_t carry_floats, void* y, int B, int D, int H, int W, int S,
+                   cudaStream_t st) {
+    const int L = (H / 2) * (W / 2);
+    constexpr int XR = RDT + 2 * NS;
+    const size_t smem = (size_t)2 * SC_T * XR * sizeof(float) + (size_t)(RDT == 0 ? 4 : 2) * SC_T * SC_CHB * sizeof(T);
+    int seg_len = ((L + S - 1) / S + SC_T - 1) / SC_T * SC_T;
+    S = (L + seg_len - 1) / seg_len;
+    if (S > 1 && (!carry || carry_floats < (size_t)B * 4 * S * 2 * NS * D)) return FD_ERR_BAD_ARGUMENT;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(scan_tm_kernel<T, NS, RDT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_tm_kernel<T, NS, RDT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    if (S > 1) {
+        scan_tm_kernel<T, NS, RDT, true><<<dim3(S - 1, D / SC_CHB, B * 4), SC_CHB, smem, st>>>(
+            (const T*)u_tm, (const T*)dts_tm, xdbl, A, dt_w, dt_bias, Dskip, carry, (T*)y, D, L, H, W, S, seg_len);
+        FD_LAUNCH_CHECK();
+    }
+    scan_tm_kernel<T, NS, RDT, false><<<dim3(S, D / SC_CHB, B * 4), SC_CHB, smem, st>>>(
+        (const T*)u_tm, (const T*)dts_tm, xdbl, A, dt_w, dt_bias, Dskip, carry, (T*)y, D, L, H, W, S, seg_len);
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int fd_dwconv3x3_silu_tm(const void* xz, int ld, const float* w_tap_major, const float* bias, void* xs_tm, int B, int H,
+                                    int W, int D, int dtype, cudaStream_t stream) {
+    if (!xz || !w_tap_major || !xs_tm || B <= 0 || H <= 0 || W <= 0 || D <= 0 || ld < D) return FD_ERR_BAD_ARGUMENT;
+    if ((H & 1) || (W & 1) || D % TM_V || ld % TM_V || ((uintptr_t)xz & 7) || ((uintptr_t)xs_tm & 7) || ((uintptr_t)w_tap_major & 15) ||
+        ((uintptr_t)bias & 15))
+        return FD_ERR_UNSUPPORTED;
+    static const int pf = getenv("FD_DWCONV_PF") ? atoi(getenv("FD_DWCONV_PF")) : 4;
+    const long pairs = (long)(W / 2) * (D / TM_V);
+    dim3 grid((unsigned)fd_cdiv(pairs, 256), (unsigned)fd_cdiv(H, TM_RY), (unsigned)B);
+    if (dtype == FD_BF16) dwconv_tm_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)xz, ld, w_tap_major, bias, (__nv_bfloat16*)xs_tm, H, W, D, pf);
+    else if (dtype == FD_F16) dwconv_tm_kernel<__half><<<grid, 256, 0, stream>>>((const __half*)xz, ld, w_tap_major, bias, (__half*)xs_tm, H, W, D, pf);
+    else return FD_ERR_UNSUPPORTED;
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T>
+static int x_proj_tm_launch(const void* xs_tm, const void* xw16, float* xdbl, const void* dw16, void* dts_tm, const float* dt_bias,
+                            int B, int D, int L, int R, int N, int Rp, int fuse_dt, cudaStream_t stream) {
+    const int CC = R + 2 * N, CCp = (CC + 15) / 16 * 16, NT = CCp / 8;
+    dim3 grid((unsigned)fd_cdiv(L, XM_STEPS), (unsigned)(B * 4));
+    const size_t smem = (size_t)XM_STAGES * (XM_STEPS + CCp) * XM_LD * sizeof(T);
+    const int col0 = fuse_dt ? 0 : R, out_ld = fuse_dt ? CC : 2 * N;
+#define XPTM_CASE(NTV)                                                                                                            \
+    if (NT == NTV) {                                                                                                              \
+        if (fuse_dt) {                                                                                                            \
+            static bool attr = false;                                                                                             \
+            if (!attr) {                                                                                                          \
+                cudaError_t e = cudaFuncSetAttribute(x_proj_tm_kernel<T, NTV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                if (e != cudaSuccess) return (int)e;                                                                              \
+                attr = true;                                                                                                      \
+            }                                                                                                                     \
+            x_proj_tm_kernel<T, NTV, false><<<grid, 256, smem, stream>>>((const T*)xs_tm, (const T*)xw16, xdbl, D, L, CC, col0, out_ld, \
+                                                                          nullptr, nullptr, nullptr, 0);                         \
+        } else {                                                                                                                  \
+            static bool attr = false;                                                                                             \
+            if (!attr) {                                                                                                          \
+                cudaError_t e = cudaFuncSetAttribute(x_proj_tm_kernel<T, NTV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                if (e != cudaSuccess) return (int)e;                                                                              \
+                attr = true;                                                                                                      \
+            }                                                                                                                     \
+            x_proj_tm_kernel<T, NTV, true><<<grid, 256, smem, stream>>>((const T*)xs_tm, (const T*)xw16, xdbl, D, L, CC, col0, out_ld, \
+                                                                         (const T*)dw16, (T*)dts_tm, dt_bias, Rp);               \
+        }                                                                                                                         \
+        FD_LAUNCH_CHECK();                                                                                                        \
+        return 0;                                                                                                                 \
+    }
+    XPTM_CASE(2) XPTM_CASE(4) XPTM_CASE(6) XPTM_CASE(8) XPTM_CASE(10) XPTM_CASE(12)
+#undef XPTM_CASE
+    return FD_ERR_UNSUPPORTED;
+}
+
+extern "C" int fd_x_proj_tm(const void* xs_tm, const void* xw16, float* xdbl_tm, const void* dw16, void* dts_tm, const float* dt_bias,
+                            int B, int D, int L, int R, int N, int Rp, int fuse_dt, int dtype, cudaStream_t stream) {
+    if (!xs_tm || !xw16 || !xdbl_tm || B <= 0 || D <= 0 || L <= 0 || R <= 0 || N <= 0) return FD_ERR_BAD_ARGUMENT;
+    if (!fuse_dt && (!dw16 || !dts_tm || !dt_bias)) return FD_ERR_BAD_ARGUMENT;
+    if (D % XM_KC || R + 2 * N > 96 || (R & 1) || (N & 1) || (((uintptr_t)xs_tm | (uintptr_t)xw16) & 15) || ((uintptr_t)xdbl_tm & 7))
+        return FD_ERR_UNSUPPORTED;
+    if (!fuse_dt && ((Rp != 16 && Rp != 32) || R > Rp || Rp > (R + 2 * N + 15) / 16 * 16 || ((uintptr_t)dw16 & 3) || ((uintptr_t)dts_tm & 3) ||
+                     ((uintptr_t)dt_bias & 7)))
+        return FD_ERR_UNSUPPORTED;
+    if (dtype == FD_BF16) return x_proj_tm_launch<__nv_bfloat16>(xs_tm, xw16, xdbl_tm, dw16, dts_tm, dt_bias, B, D, L, R, N, Rp, fuse_dt, stream);
+    if (dtype == FD_F16) return x_proj_tm_launch<__half>(xs_tm, xw16, xdbl_tm, dw16, dts_tm, dt_bias, B, D, L, R, N, Rp, fuse_dt, stream);
+    return FD_ERR_UNSUPPORTED;
+}
+
+extern "C" int fd_scan_tm_segments(int B, int D, int H, int W) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return FD_ERR_BAD_ARGUMENT;
+    const int L = (H / 2) * (W / 2);
+    int S = pick_segments(B, D, L);
+    const int seg_len = ((L + S - 1) / S + SC_T - 1) / SC_T * SC_T;
+    return (L + seg_len - 1) / seg_len;
+}
+
+extern "C" int fd_selective_scan_tm(const void* u_tm, const void* dts_tm, const float* xdbl_tm, const float* A, const float* dt_w,
+                                    const float* dt_bias, const float* D_skip, float* carry_ws, long carry_floats, void* y_nhwc,
+                                    int B, int D, int H, int W, int dstate, int dt_rank_fused, int segments, int io_dtype,
+                                    cudaStream_t stream) {
+    if (!u_tm || !xdbl_tm || !A || !D_skip || !y_nhwc || B <= 0 || D <= 0 || H <= 0 || W <= 0) return FD_ERR_BAD_ARGUMENT;
+    if ((H & 1) || (W & 1)) return FD_ERR_BAD_ARGUMENT;
+    if (dt_rank_fused ? (!dt_w || !dt_bias) : !dts_tm) return FD_ERR_BAD_ARGUMENT;
+    if (D % SC_CHB || (((uintptr_t)u_tm | (uintptr_t)dts_tm | (uintptr_t)xdbl_tm) & 15)) return FD_ERR_UNSUPPORTED;
+    const int L = (H / 2) * (W / 2);
+    int S = segments > 0 ? segments : pick_segments(B, D, L);
+#define SCTM_CASE(NSV, RV)                                                                                                         \
+    if (dstate == NSV && dt_rank_fused == RV) {                                                                                    \
+        if (io_dtype == FD_BF16)                                                                                                   \
+            return scan_tm_launch<__nv_bfloat16, NSV, RV>(u_tm, dts_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, carry_ws, (size_t)carry_floats, \
+                                                          y_nhwc, B, D, H, W, S, stream);                                          \
+        if (io_dtype == FD_F16)                                                                                                    \
+            return scan_tm_launch<__half, NSV, RV>(u_tm, dts_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, carry_ws, (size_t)carry_floats, y_nhwc, \
+                                                   B, D, H, W, S, stream);                                                         \
+        return FD_ERR_UNSUPPORTED;                                                                                                 \
+    }
+    SCTM_CASE(4, 4) SCTM_CASE(8, 4) SCTM_CASE(8, 8) SCTM_CASE(16, 8) SCTM_CASE(4, 0) SCTM_CASE(8, 0) SCTM_CASE(16, 0) SCTM_CASE(32, 0)
+#undef SCTM_CASE
+    return FD_ERR_UNSUPPORTED;
+}

@@ -332,6 +332,19 @@ class UnetEngine:
         # by its dependent shuffle / MUFU chains, not by issue slots — so only the channel-per-lane levels use it (FD_XDT_SOFTPLUS=1
         # switches it on for the others)
         xdt_softplus = fuse_merge and use_xdt_tc and not scan_cl and os.environ.get("FD_XDT_SOFTPLUS", "0") == "1"
+        # 16-bit modes: the TIME-MAJOR core (fd_ss2d_tm.cu) — channel-per-lane segmented scan, dt_proj fused where the rank is small
+        tm_fuse = (N, R) in ((4, 4), (8, 4), (8, 8), (16, 8))
+        use_tm = (dt != torch.float32 and use_xdt_tc and D % 128 == 0 and h % 2 == 0 and w % 2 == 0 and (tm_fuse or N in (4, 8, 16, 32))
+                  and os.environ.get("FD_SS2D_TM", "1") == "1")
+        if use_tm:
+            scan_cl = fuse_dt = False
+            dw_wt = dw_w.t().contiguous()                                  # tap-major (9, D)
+            xs_tm, dts_tm = xs.view(B, 4, L, D), dts.view(B, 4, L, D)
+            XR = (R + 2 * N) if tm_fuse else 2 * N
+            xdbl_tm = self.buf(f"XDBLTM.{p}", B, 4, L, XR, dtype=torch.float32)
+            S_tm = ops.scan_tm_segments(B, D, h, w)
+            carry = self.buf(f"CARRY.{p}", B * 4 * S_tm * 2 * N * D, dtype=torch.float32)
+            dtw_tm = dtp_w.reshape(4 * D, R).contiguous()
         if fuse_dt:
             xdbl = self.buf(f"XDBL{l}", B, 4, R + 2 * N, L, dtype=torch.float32)
             dtw_flat = dtp_w.reshape(4 * D, R).contiguous()
@@ -352,12 +365,30 @@ class UnetEngine:
             holder["qk"] = self._acc_view(acc_q, B, 2, C)
         self._acc_users.append(bind)
 
-        self.paths[p] = ("scan_cl time-major B/C" if scan_cl else "dt-fused warp scan" if fuse_dt else
+        self.paths[p] = (f"time-major scan, {S_tm} segment(s)" + (", dt_proj fused" if tm_fuse else "") if use_tm else
+                         "scan_cl time-major B/C" if scan_cl else "dt-fused warp scan" if fuse_dt else
                          "warp scan + merge" if fuse_merge else "reference-layout" if dt == torch.float32 else "warp scan, unfused merge")
 
         def run():
             ops.ln_modulate(x_in, a, n1w, n1b, sh1, sc1, MS, B, P, C, 1e-5)
             c_in.run()
+            if use_tm:
+                ops.dwconv3x3_silu_tm(xz, 4 * C, dw_wt, dw_b, xs_tm, B, h, w, D)
+                if tm_fuse:
+                    ops.x_proj_tm(xs_tm, xw16, xdbl_tm, None, None, None, B, D, L, R, N, Rp, True)
+                    ops.selective_scan_tm(xs_tm, None, xdbl_tm, A_neg, dtw_tm, dt_bias, Ds, carry, ys.view(B, P, D), B, D, h, w, N, R, S_tm)
+                else:
+                    ops.x_proj_tm(xs_tm, xw16, xdbl_tm, dw16, dts_tm, dt_bias, B, D, L, R, N, Rp, False)
+                    ops.selective_scan_tm(xs_tm, dts_tm, xdbl_tm, A_neg, None, None, Ds, carry, ys.view(B, P, D), B, D, h, w, N, 0, S_tm)
+                ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
+                c_out.run()
+                ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
+                c_qkv.run()
+                ops.dwconv3x3_nhwc(qkv, qdw_wt, None, qkv2, B, h, w, 3 * C)
+                ops.gram_qk(qkv2, 3 * C, holder["gram"], holder["qk"], B, P, C)
+                ops.attn_weff(holder["gram"], holder["qk"], temp, proj_w, weff, B, C)
+                c_att.run()
+                return
             ops.dwconv3x3_silu_scan(xz, 4 * C, dw_w, dw_b, xs, B, h, w, D)
             if scan_cl:
                 ops.xdt_proj_tc(xs, xw16, dw16, Rp, dts, Bs_t, Cs_t, B, D, L, R, N, time_major=True, dt_bias=dt_bias, delta_softplus=True)

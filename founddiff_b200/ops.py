@@ -288,6 +288,37 @@ def x_proj_tc(xs, xw16, x_dbl, B, D, L, R, N):
         check(_lib.load().fd_x_proj_tc(_p(xs), _p(xw16), _f32(x_dbl), B, D, L, R, N, dtype_code(xs.dtype), _stream()), "fd_x_proj_tc")
 
 
+def dwconv3x3_silu_tm(xz, ld, w_tap_major, bias, xs_tm, B, H, W, D):
+    """Depthwise 3x3 + bias + SiLU on the x half of xz -> time-major scan input (B, 4, L, D)."""
+    assert tuple(w_tap_major.shape) == (9, D)
+    with _launched("dwconv_tm", f"{B}x{H}x{W}x{D}", 1):
+        check(_lib.load().fd_dwconv3x3_silu_tm(_p(xz), ld, _f32(w_tap_major), _f32(bias), _p(xs_tm), B, H, W, D,
+                                               dtype_code(xz.dtype), _stream()), "fd_dwconv3x3_silu_tm")
+
+
+def x_proj_tm(xs_tm, xw16, xdbl, dw16, dts_tm, dt_bias, B, D, L, R, N, Rp, fuse_dt):
+    """x_proj (+ dt_proj + bias + softplus when not fused into the scan) on time-major rows; xdbl (B,4,L,R+2N | 2N) fp32."""
+    assert xdbl.dtype == torch.float32 and xdbl.shape == (B, 4, L, (R + 2 * N) if fuse_dt else 2 * N)
+    with _launched("x_proj_tm", f"{B}x{D}x{L} R{R} N{N}" + (" dt-fused" if fuse_dt else ""), 1):
+        check(_lib.load().fd_x_proj_tm(_p(xs_tm), _p(xw16), _f32(xdbl), _p(dw16), _p(dts_tm), _f32(dt_bias), B, D, L, R, N, Rp,
+                                       int(bool(fuse_dt)), dtype_code(xs_tm.dtype), _stream()), "fd_x_proj_tm")
+
+
+def scan_tm_segments(B, D, H, W) -> int:
+    return int(_lib.load().fd_scan_tm_segments(B, D, H, W))
+
+
+def selective_scan_tm(u_tm, dts_tm, xdbl, A, dt_w, dt_bias, D_skip, carry, y_nhwc, B, D, H, W, N, R_fused, segments=0):
+    """Segmented channel-per-lane scan + EfficientMerge; launches the carry pass (when > 1 segment) and the forward pass."""
+    L = (H // 2) * (W // 2)
+    S = segments or scan_tm_segments(B, D, H, W)
+    with _launched("scan_tm", f"{B}x{4 * D}x{L} N{N}" + (f" R{R_fused}" if R_fused else "") + f" S{S}", 2 if S > 1 else 1):
+        check(_lib.load().fd_selective_scan_tm(_p(u_tm), _p(dts_tm), _f32(xdbl), _f32(A), _f32(dt_w), _f32(dt_bias), _f32(D_skip),
+                                               _f32(carry), carry.numel() if carry is not None else 0, _p(y_nhwc), B, D, H, W, N,
+                                               R_fused, segments, dtype_code(u_tm.dtype), _stream()), "fd_selective_scan_tm")
+    return y_nhwc
+
+
 class LinearAttention:
     """lucidrains LinearAttention between to_qkv and the end of to_out (src/denoising_diffusion_pytorch.py:238-255) as a
     call site with pre-allocated workspace and a persistent per-sample GEMM plan (graph-capturable, no allocation per call):

@@ -184,6 +184,34 @@ int fd_xdt_proj_tc(const void* xs, const void* xw16, const void* dw16, void* dts
 int fd_x_proj_tc(const void* xs, const void* xw16, float* x_dbl, int B, int D, int L, int R, int N, int dtype,
                  cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * TIME-MAJOR SS2D core (16-bit storage): the same four reference stages — SS2D.conv2d + act + EfficientScan
+ * (src/emamba2.py:480-488, 722, 186-213), x_proj / dt_proj (:335-340), SelectiveScan.forward -> selective_scan_cuda_core.fwd
+ * (:124-157, 342-355), EfficientMerge (:238-262) — on tensors whose CHANNEL index is fastest:
+ *   xs_tm (B,4,L,D) 16-bit, xdbl_tm (B,4,L,XR) fp32, dts_tm (B,4,L,D) 16-bit; direction / step numbering as fd_dwconv3x3_silu_scan.
+ * A lane of the scan owns a channel and walks time with its states in registers; rows are cut into segments whose entry states
+ * come from an exact carry pass (founddiff_b200/csrc/fd_ss2d_tm.cu).
+ * --------------------------------------------------------------------------------------------------------- */
+/* xz: (B,H,W,ld) rows, conv channels = columns [0, D); w_tap_major: (9, D) fp32 (tap = 3*kh + kw); H, W even; D % 4 == 0. */
+int fd_dwconv3x3_silu_tm(const void* xz, int ld, const float* w_tap_major, const float* bias, void* xs_tm, int B, int H,
+                         int W, int D, int dtype, cudaStream_t stream);
+/* x_proj (+ dt_proj) on time-major rows.  xw16 / dw16: the padded 16-bit weights of fd_xdt_proj_tc ((4, ceil16(R+2N), D), (4, D, Rp)).
+ * fuse_dt = 1: xdbl_tm rows are [dt input (R) | B (N) | C (N)] (the scan applies dt_proj itself), dw16 / dts_tm / dt_bias unused.
+ * fuse_dt = 0: xdbl_tm rows are [B (N) | C (N)] and dts_tm = softplus(dt_proj(x_dbl[:R]) + dt_bias[k*D + d]) (softplus threshold
+ * 20, as selective_scan_fn with delta_softplus=True).  D % 64 == 0, R and N even, R + 2N <= 96. */
+int fd_x_proj_tm(const void* xs_tm, const void* xw16, float* xdbl_tm, const void* dw16, void* dts_tm, const float* dt_bias,
+                 int B, int D, int L, int R, int N, int Rp, int fuse_dt, int dtype, cudaStream_t stream);
+/* Number of segments fd_selective_scan_tm cuts a row into for this geometry (sizes the carry workspace: B*4*S*2*dstate*D floats). */
+int fd_scan_tm_segments(int B, int D, int H, int W);
+/* S6 scan + EfficientMerge on time-major inputs: y_nhwc (B,H,W,D) = merge(scan(u, delta, A, B, C) + D_skip * u).
+ * A: (4D, dstate) fp32 (= -exp(A_logs)); D_skip: (4D,).  dt_rank_fused > 0: delta = softplus(dt_w[d, :] . xdbl[l, :R] + dt_bias[d])
+ * with dt_w (4D, R) fp32, dts_tm unused; dt_rank_fused == 0: delta is read from dts_tm as is.  segments: 0 = automatic.
+ * carry_ws: fp32 scratch of carry_floats elements (may be NULL when one segment is used).  D % 128 == 0;
+ * (dstate, dt_rank_fused) in {(4,4), (8,4), (8,8), (16,8), (4,0), (8,0), (16,0), (32,0)}. */
+int fd_selective_scan_tm(const void* u_tm, const void* dts_tm, const float* xdbl_tm, const float* A, const float* dt_w,
+                         const float* dt_bias, const float* D_skip, float* carry_ws, long carry_floats, void* y_nhwc, int B,
+                         int D, int H, int W, int dstate, int dt_rank_fused, int segments, int io_dtype, cudaStream_t stream);
+
 /* SS2D consumer: EfficientMerge (src/emamba2.py:238-262) + out_norm LayerNorm(D) (:365) + y*z + local (:747-748).
  * ys: (B,4,D,L); z = columns [z_off, z_off+D) of xz rows (already SiLU'd); local: (B, D) fp32; out: (B,H,W,D).
  * stats_ws: caller-provided workspace of B*H*W*2 floats (per-pixel mean / rstd). */
