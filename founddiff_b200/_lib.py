@@ -14,7 +14,7 @@ from . import build as _build
 FD_F32, FD_BF16, FD_F16 = 0, 1, 2
 
 EXPORTS = [
-    "fd_version", "fd_dwconv3x3_silu_tm", "fd_x_proj_tm", "fd_scan_tm_segments", "fd_selective_scan_tm", "fd_selective_scan_fwd", "fd_selective_scan_fwd_merge", "fd_selective_scan_fwd_merge_xdbl", "fd_selective_scan_fwd_merge_cl", "fd_x_proj_tc", "fd_avgpool2x2_nhwc", "fd_slice_metrics", "fd_init_conv7x7_tc", "fd_ln_modulate_io", "fd_ln_gate", "fd_conv2d_simt", "fd_conv2d_tc_supported", "fd_conv2d_tc_plan_create",
+    "fd_version", "fd_dwconv3x3_silu_tm", "fd_x_proj_tm", "fd_scan_tm_segments", "fd_scan_tm_plan", "fd_selective_scan_tm", "fd_selective_scan_fwd", "fd_selective_scan_fwd_merge", "fd_selective_scan_fwd_merge_xdbl", "fd_selective_scan_fwd_merge_cl", "fd_x_proj_tc", "fd_avgpool2x2_nhwc", "fd_slice_metrics", "fd_init_conv7x7_tc", "fd_ln_modulate_io", "fd_ln_gate", "fd_conv2d_simt", "fd_conv2d_tc_supported", "fd_conv2d_tc_plan_create",
     "fd_conv2d_tc_run", "fd_conv2d_tc_plan_destroy", "fd_init_conv7x7", "fd_ln_modulate", "fd_dwconv3x3_silu_scan",
     "fd_xdt_proj", "fd_xdt_proj_tc", "fd_merge_ln_gate", "fd_dwconv3x3_qkv_gram", "fd_dwconv3x3_nhwc", "fd_gram_qk", "fd_attn_weff", "fd_gn_stats", "fd_gn_silu_add", "fd_gn_scale_shift_silu", "fd_flash_attn_d32", "fd_linattn_context", "fd_linattn_weff", "fd_softmax_d32",
     "fd_linear_small", "fd_time_sinusoid", "fd_sampler_init", "fd_final_conv_update", "fd_final_conv_update_obj", "fd_unnormalize", "fd_ddpm_update",
@@ -67,6 +67,7 @@ def load():
         "fd_dwconv3x3_silu_tm": [V, I, V, V, V, I, I, I, I, I, V],
         "fd_x_proj_tm": [V] * 6 + [I] * 8 + [V],
         "fd_scan_tm_segments": [I, I, I, I],
+        "fd_scan_tm_plan": [I] * 6,
         "fd_selective_scan_tm": [V] * 8 + [L, V] + [I] * 8 + [V],
         "fd_avgpool2x2_nhwc": [V, V, I, I, I, I, I, V],
         "fd_slice_metrics": [V, V, V, I, I, I, F, V],

@@ -504,12 +504,206 @@ __global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
     }
 }
 
+// =========================================================================================================
+// K3b: time-sliced cooperative scan for the levels with FEW, LONG rows (full and half resolution: 8 K - 16 K channel rows
+// of 16 K - 64 K steps).  The segmented kernel above pays for its parallelism with a second evaluation of exp(dt A) in the
+// carry pass — with the reference's dt initialisation (1e-3 .. 1e-1, A = -1 .. -N) the slowest state of some channel of every
+// warp remembers longer than a segment, so the carry pass walks whole segments and the MUFU work doubles.  Here every
+// exp(dt A) is evaluated ONCE:
+//   block = TW warps x 32 lanes; a lane is a channel, warp w owns time slice w of every chunk (chunk = TW x ST steps).
+//   phase A   each warp scans its ST steps from h = 0 and keeps, per step, y_local (registers) and the fix-up row
+//             g[n] = C[n] * prod(a[n]) (shared memory, one 16-byte vector per step and lane for N = 4);
+//             it publishes (P = prod a, h_local) of its slice.
+//   barrier   (one per chunk)
+//   fold      warp w composes the slices j < w onto the chunk's entry state: h_in = P_j h_in + h_j  (a few FMAs)
+//   fix-up    y[t] = y_local[t] + g[t] . h_in  (N FMAs per step, no MUFU), EfficientMerge store
+//   the last warp hands the chunk's exit state to the next chunk through shared memory (published by the next barrier).
+// u and the X_dbl rows of a warp's slice are staged by the warp itself (cp.async, consumed in phase A only, so the next
+// slice's copy is issued right after phase A and lands under the fold / fix-up).  The result equals the sequential
+// recurrence up to re-association.
+template <typename T, int NS, int RDT, int ST, int TW>
+__global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw_kernel(
+    const T* __restrict__ u_tm, const float* __restrict__ xdbl, const float* __restrict__ A, const float* __restrict__ dt_w,
+    const float* __restrict__ dt_bias, const float* __restrict__ Dskip, T* __restrict__ y, int D, int L, int H, int W) {
+    constexpr int XR = RDT + 2 * NS;
+    constexpr int CH = TW * ST;                          // steps per chunk
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_g = reinterpret_cast<float*>(smem_raw);     // [TW][ST][32][NS]
+    float* s_x = s_g + TW * ST * 32 * NS;                // [TW][ST][XR]
+    float* s_ph = s_x + TW * ST * XR;                    // [2][TW][2 NS][32]
+    float* s_cy = s_ph + 2 * TW * 2 * NS * 32;           // [2][NS][32]
+    T* s_u = reinterpret_cast<T*>(s_cy + 2 * NS * 32);   // [TW][ST][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bk = blockIdx.y, k = bk & 3, b = bk >> 2;
+    const int ch0 = blockIdx.x * 32;
+    const int dloc = ch0 + lane;
+    const int d = k * D + dloc;
+    const T* ug = u_tm + (long)bk * L * D + ch0;
+    const float* xg = xdbl + (long)bk * L * XR;
+    float* gw = s_g + warp * ST * 32 * NS + lane * NS;
+    float* xw = s_x + warp * ST * XR;
+    T* uw = s_u + warp * ST * 32;
+
+    float A2[NS];
+#pragma unroll
+    for (int n = 0; n < NS; ++n) A2[n] = A[(long)d * NS + n] * 1.4426950408889634f;
+    float wdt[RDT];
+#pragma unroll
+    for (int r = 0; r < RDT; ++r) wdt[r] = dt_w[(long)d * RDT + r];
+    const float bias = dt_bias[d], Dd = Dskip[d];
+    if (warp == 0) {
+#pragma unroll
+        for (int n = 0; n < NS; ++n) s_cy[n * 32 + lane] = 0.f;          // entry state of chunk 0 (published by the first barrier)
+    }
+
+    auto stage = [&](int t0) {                           // this warp's slice [t0, t0 + ST): rows past L are zero-filled
+        for (int i = lane; i < ST * XR / 4; i += 32) {   // X_dbl rows are contiguous in global memory
+            const bool ok = t0 + (i * 4) / XR < L;
+            tm_cp_async16(xw + i * 4, ok ? xg + (long)t0 * XR + i * 4 : xg, ok);
+        }
+        for (int i = lane; i < ST * 4; i += 32) {        // u: ST rows of 32 channels = 4 x 16 bytes each
+            const int r = i >> 2, v = i & 3;
+            const bool ok = t0 + r < L;
+            tm_cp_async16(uw + r * 32 + v * 8, ok ? ug + (long)(t0 + r) * D + v * 8 : ug, ok);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int H2 = H >> 1, W2 = W >> 1;
+    const int mdiv = (k & 1) ? H2 : W2;
+    T* ybase = y + (long)b * H * W * D + dloc;
+    const int nchunks = (L + CH - 1) / CH;
+    stage(warp * ST);
+    for (int c = 0; c < nchunks; ++c) {
+        const int t0 = c * CH + warp * ST;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        // ---- phase A: local scan of the slice from h = 0
+        float hl[NS], P[NS], yl[ST];
+#pragma unroll
+        for (int n = 0; n < NS; ++n) { hl[n] = 0.f; P[n] = 1.f; }
+#pragma unroll
+        for (int i = 0; i < ST; ++i) {
+            const float* xr = xw + i * XR;
+            float t = bias;
+#pragma unroll
+            for (int r = 0; r < RDT; r += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(xr + r);
+                t = fmaf(wdt[r], v.x, t); t = fmaf(wdt[r + 1], v.y, t); t = fmaf(wdt[r + 2], v.z, t); t = fmaf(wdt[r + 3], v.w, t);
+            }
+            float dt = tm_softplus(t);
+            dt = (t0 + i < L) ? dt : 0.f;                // past the end of the row: identity step (a = 1, b = 0)
+            const float u = tm_ld16<T>(uw + i * 32 + lane);
+            const float du = dt * u;
+            float y0 = Dd * u, y1 = 0.f;
+#pragma unroll
+            for (int n = 0; n < NS; n += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(xr + RDT + n);
+                const float4 c4 = *reinterpret_cast<const float4*>(xr + RDT + NS + n);
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                float gq[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = tm_ex2(dt * A2[n + j]);
+                    hl[n + j] = fmaf(a, hl[n + j], du * bb[j]);
+                    if (j & 1) y1 = fmaf(hl[n + j], cc[j], y1); else y0 = fmaf(hl[n + j], cc[j], y0);
+                    P[n + j] *= a;
+                    gq[j] = cc[j] * P[n + j];
+                }
+                *reinterpret_cast<float4*>(gw + i * 32 * NS + n) = make_float4(gq[0], gq[1], gq[2], gq[3]);
+            }
+            yl[i] = y0 + y1;
+        }
+        {
+            float* ph = s_ph + ((c & 1) * TW + warp) * 2 * NS * 32 + lane;
+#pragma unroll
+            for (int n = 0; n < NS; ++n) { ph[n * 32] = P[n]; ph[(NS + n) * 32] = hl[n]; }
+        }
+        __syncwarp();                                    // every lane is done reading the staged slice
+        if (c + 1 < nchunks) stage(t0 + CH);
+        __syncthreads();                                 // slices (and the entry state) of chunk c are published
+        // ---- fold: state entering this warp's slice
+        float hin[NS];
+        {
+            const float* cy = s_cy + (c & 1) * NS * 32 + lane;
+#pragma unroll
+            for (int n = 0; n < NS; ++n) hin[n] = cy[n * 32];
+            for (int j = 0; j < warp; ++j) {
+                const float* ph = s_ph + ((c & 1) * TW + j) * 2 * NS * 32 + lane;
+#pragma unroll
+                for (int n = 0; n < NS; ++n) hin[n] = fmaf(ph[n * 32], hin[n], ph[(NS + n) * 32]);
+            }
+        }
+        if (warp == TW - 1) {                            // exit state of the chunk = entry state of the next one
+            float* cy = s_cy + ((c + 1) & 1) * NS * 32 + lane;
+#pragma unroll
+            for (int n = 0; n < NS; ++n) cy[n * 32] = fmaf(P[n], hin[n], hl[n]);
+        }
+        // ---- fix-up + EfficientMerge store
+        int mq = t0 / mdiv, mr = t0 - mq * mdiv;
+        const int ns = min(ST, L - t0);
+#pragma unroll
+        for (int i = 0; i < ST; ++i) {
+            if (i < ns) {
+                float yv = yl[i], y2 = 0.f;
+#pragma unroll
+                for (int n = 0; n < NS; n += 4) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(gw + i * 32 * NS + n);
+                    yv = fmaf(g4.x, hin[n], yv); y2 = fmaf(g4.y, hin[n + 1], y2);
+                    yv = fmaf(g4.z, hin[n + 2], yv); y2 = fmaf(g4.w, hin[n + 3], y2);
+                }
+                int hh, ww;
+                if (k & 1) { ww = 2 * mq + (k >> 1); hh = 2 * mr + 1; }
+                else       { hh = 2 * mq; ww = 2 * mr + (k >> 1); }
+                fd_st(ybase + ((long)hh * W + ww) * D, yv + y2);
+                if (++mr == mdiv) { mr = 0; ++mq; }
+            }
+        }
+    }
+}
+
+template <typename T, int NS, int RDT, int ST, int TW>
+int scan_tw_launch(const void* u_tm, const float* xdbl, const float* A, const float* dt_w, const float* dt_bias, const float* Dskip,
+                   void* y, int B, int D, int H, int W, cudaStream_t st) {
+    const int L = (H / 2) * (W / 2);
+    constexpr int XR = RDT + 2 * NS;
+    const size_t smem = ((size_t)TW * ST * 32 * NS + (size_t)TW * ST * XR + (size_t)2 * TW * 2 * NS * 32 + 2 * NS * 32) * sizeof(float) +
+                        (size_t)TW * ST * 32 * sizeof(T);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(scan_tw_kernel<T, NS, RDT, ST, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    scan_tw_kernel<T, NS, RDT, ST, TW><<<dim3(D / 32, B * 4), TW * 32, smem, st>>>((const T*)u_tm, xdbl, A, dt_w, dt_bias, Dskip, (T*)y, D, L, H, W);
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
+// Which scan a geometry gets: 0 = segmented channel-per-lane (scan_tm_kernel), 8 / 4 = time-sliced with that many warps.
+// The time-sliced kernel needs ALL its blocks resident at once (a block walks a whole row): 2 blocks per SM with 8 warps,
+// 4 with 4 warps; it only exists for the fused-dt small-state levels.
+int pick_time_warps(int B, int D, int L, int NS, int RDT) {
+    static const int forced = getenv("FD_SCAN_TW") ? atoi(getenv("FD_SCAN_TW")) : -1;
+    if (RDT == 0 || NS > 8) return 0;
+    if (forced >= 0) return forced;
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long blocks = (long)B * 4 * (D / 32);
+    if (L < 2048) return 0;
+    if (blocks <= 2L * sms) return 8;
+    if (blocks <= 4L * sms) return 4;
+    return 0;
+}
+
 int pick_segments(int B, int D, int L) {
     // enough warps to fill the machine (>= ~16 per SM), segments not shorter than 2048 steps (the carry pass walks ~the
     // memory length of the slowest channel of a block per segment, so short segments pay it proportionally more often)
     static const int forced = getenv("FD_SCAN_SEGMENTS") ? atoi(getenv("FD_SCAN_SEGMENTS")) : 0;
     if (forced > 0) return forced;
     const long base_warps = (long)B * 4 * D / 32;
+    if (base_warps >= 148L * 4) return 1;               // >= 1 warp per scheduler: the carry pass would cost more than it buys
     int S = 1;
     while (S < 64 && base_warps * S < 148L * 24 && L / (2 * S) >= 2048) S *= 2;
     return S;
@@ -611,6 +805,16 @@ extern "C" int fd_x_proj_tm(const void* xs_tm, const void* xw16, float* xdbl_tm,
     return FD_ERR_UNSUPPORTED;
 }
 
+extern "C" int fd_scan_tm_plan(int B, int D, int H, int W, int dstate, int dt_rank_fused) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    const int L = (H / 2) * (W / 2);
+    const int tw = pick_time_warps(B, D, L, dstate, dt_rank_fused);
+    if (tw) return -tw;
+    int S = pick_segments(B, D, L);
+    const int seg_len = ((L + S - 1) / S + SC_T - 1) / SC_T * SC_T;
+    return (L + seg_len - 1) / seg_len;
+}
+
 extern "C" int fd_scan_tm_segments(int B, int D, int H, int W) {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return FD_ERR_BAD_ARGUMENT;
     const int L = (H / 2) * (W / 2);
@@ -628,6 +832,19 @@ extern "C" int fd_selective_scan_tm(const void* u_tm, const void* dts_tm, const 
     if (dt_rank_fused ? (!dt_w || !dt_bias) : !dts_tm) return FD_ERR_BAD_ARGUMENT;
     if (D % SC_CHB || (((uintptr_t)u_tm | (uintptr_t)dts_tm | (uintptr_t)xdbl_tm) & 15)) return FD_ERR_UNSUPPORTED;
     const int L = (H / 2) * (W / 2);
+    if (segments <= 0) {                                 // 0 = automatic: time-sliced kernel where rows are few and long; -8 / -4 = forced
+        const int tw = segments < 0 ? -segments : pick_time_warps(B, D, L, dstate, dt_rank_fused);
+        if (segments < 0 && tw != 8 && tw != 4) return FD_ERR_BAD_ARGUMENT;
+#define SCTW_CASE(NSV, RV, STV, TWV)                                                                                               \
+    if (tw == TWV && dstate == NSV && dt_rank_fused == RV) {                                                                       \
+        if (io_dtype == FD_BF16) return scan_tw_launch<__nv_bfloat16, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, stream); \
+        if (io_dtype == FD_F16) return scan_tw_launch<__half, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, stream); \
+        return FD_ERR_UNSUPPORTED;                                                                                                 \
+    }
+        SCTW_CASE(4, 4, 16, 8) SCTW_CASE(4, 4, 16, 4) SCTW_CASE(8, 4, 8, 8) SCTW_CASE(8, 4, 8, 4) SCTW_CASE(8, 8, 8, 8) SCTW_CASE(8, 8, 8, 4)
+#undef SCTW_CASE
+        if (segments < 0) return FD_ERR_UNSUPPORTED;
+    }
     int S = segments > 0 ? segments : pick_segments(B, D, L);
 #define SCTM_CASE(NSV, RV)                                                                                                         \
     if (dstate == NSV && dt_rank_fused == RV) {                                                                                    \

@@ -342,8 +342,8 @@ class UnetEngine:
             xs_tm, dts_tm = xs.view(B, 4, L, D), dts.view(B, 4, L, D)
             XR = (R + 2 * N) if tm_fuse else 2 * N
             xdbl_tm = self.buf(f"XDBLTM.{p}", B, 4, L, XR, dtype=torch.float32)
-            S_tm = ops.scan_tm_segments(B, D, h, w)
-            carry = self.buf(f"CARRY.{p}", B * 4 * S_tm * 2 * N * D, dtype=torch.float32)
+            S_tm = ops.scan_tm_plan(B, D, h, w, N, R if tm_fuse else 0)      # > 0 segments | -8 / -4 time-sliced kernel
+            carry = self.buf(f"CARRY.{p}", B * 4 * max(S_tm, 1) * 2 * N * D, dtype=torch.float32)
             dtw_tm = dtp_w.reshape(4 * D, R).contiguous()
         if fuse_dt:
             xdbl = self.buf(f"XDBL{l}", B, 4, R + 2 * N, L, dtype=torch.float32)
@@ -365,7 +365,8 @@ class UnetEngine:
             holder["qk"] = self._acc_view(acc_q, B, 2, C)
         self._acc_users.append(bind)
 
-        self.paths[p] = (f"time-major scan, {S_tm} segment(s)" + (", dt_proj fused" if tm_fuse else "") if use_tm else
+        self.paths[p] = ((f"time-major scan, {S_tm} segment(s)" if S_tm > 0 else f"time-major scan, time-sliced x{-S_tm}")
+                         + (", dt_proj fused" if tm_fuse else "") if use_tm else
                          "scan_cl time-major B/C" if scan_cl else "dt-fused warp scan" if fuse_dt else
                          "warp scan + merge" if fuse_merge else "reference-layout" if dt == torch.float32 else "warp scan, unfused merge")
 

@@ -308,11 +308,18 @@ def scan_tm_segments(B, D, H, W) -> int:
     return int(_lib.load().fd_scan_tm_segments(B, D, H, W))
 
 
+def scan_tm_plan(B, D, H, W, N, R_fused) -> int:
+    """> 0: segments of the segmented scan; -8 / -4: time-sliced cooperative scan with that many warps per block."""
+    return int(_lib.load().fd_scan_tm_plan(B, D, H, W, N, R_fused))
+
+
 def selective_scan_tm(u_tm, dts_tm, xdbl, A, dt_w, dt_bias, D_skip, carry, y_nhwc, B, D, H, W, N, R_fused, segments=0):
-    """Segmented channel-per-lane scan + EfficientMerge; launches the carry pass (when > 1 segment) and the forward pass."""
+    """Time-major scan + EfficientMerge.  segments: 0 = automatic, > 0 = segmented channel-per-lane scan (carry pass + forward
+    pass), -8 / -4 = time-sliced cooperative scan (one launch)."""
     L = (H // 2) * (W // 2)
-    S = segments or scan_tm_segments(B, D, H, W)
-    with _launched("scan_tm", f"{B}x{4 * D}x{L} N{N}" + (f" R{R_fused}" if R_fused else "") + f" S{S}", 2 if S > 1 else 1):
+    S = segments or scan_tm_plan(B, D, H, W, N, R_fused)
+    with _launched("scan_tm", f"{B}x{4 * D}x{L} N{N}" + (f" R{R_fused}" if R_fused else "") + (f" S{S}" if S > 0 else f" TW{-S}"),
+                   2 if S > 1 else 1):
         check(_lib.load().fd_selective_scan_tm(_p(u_tm), _p(dts_tm), _f32(xdbl), _f32(A), _f32(dt_w), _f32(dt_bias), _f32(D_skip),
                                                _f32(carry), carry.numel() if carry is not None else 0, _p(y_nhwc), B, D, H, W, N,
                                                R_fused, segments, dtype_code(u_tm.dtype), _stream()), "fd_selective_scan_tm")

@@ -203,9 +203,13 @@ int fd_x_proj_tm(const void* xs_tm, const void* xw16, float* xdbl_tm, const void
                  int B, int D, int L, int R, int N, int Rp, int fuse_dt, int dtype, cudaStream_t stream);
 /* Number of segments fd_selective_scan_tm cuts a row into for this geometry (sizes the carry workspace: B*4*S*2*dstate*D floats). */
 int fd_scan_tm_segments(int B, int D, int H, int W);
+/* The kernel `segments = 0` selects: > 0 = segmented channel-per-lane scan with that many segments; -8 / -4 = the time-sliced
+ * cooperative scan with 8 / 4 warps per 32-channel block (few, long rows; fused dt_proj, dstate <= 8; no carry workspace). */
+int fd_scan_tm_plan(int B, int D, int H, int W, int dstate, int dt_rank_fused);
 /* S6 scan + EfficientMerge on time-major inputs: y_nhwc (B,H,W,D) = merge(scan(u, delta, A, B, C) + D_skip * u).
  * A: (4D, dstate) fp32 (= -exp(A_logs)); D_skip: (4D,).  dt_rank_fused > 0: delta = softplus(dt_w[d, :] . xdbl[l, :R] + dt_bias[d])
- * with dt_w (4D, R) fp32, dts_tm unused; dt_rank_fused == 0: delta is read from dts_tm as is.  segments: 0 = automatic.
+ * with dt_w (4D, R) fp32, dts_tm unused; dt_rank_fused == 0: delta is read from dts_tm as is.  segments: 0 = automatic
+ * (fd_scan_tm_plan), > 0 = that many segments, -8 / -4 = time-sliced kernel.
  * carry_ws: fp32 scratch of carry_floats elements (may be NULL when one segment is used).  D % 128 == 0;
  * (dstate, dt_rank_fused) in {(4,4), (8,4), (8,8), (16,8), (4,0), (8,0), (16,0), (32,0)}. */
 int fd_selective_scan_tm(const void* u_tm, const void* dts_tm, const float* xdbl_tm, const float* A, const float* dt_w,

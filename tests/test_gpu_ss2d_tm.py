@@ -88,7 +88,7 @@ def _scan_case(ops, H, W, D, N, R, fuse, dt, segments, slow=False, B=2, seed=0):
     Dp, bias = torch.randn(4 * D, generator=g), torch.randn(4 * D, generator=g) * 0.5 - (3.0 if slow else 0.0)
     Bm, Cm = torch.randn(B, 4, L, N, generator=g), torch.randn(B, 4, L, N, generator=g)
     Wdt = torch.randn(4, D, R, generator=g) / math.sqrt(R)
-    S = segments or ops.scan_tm_segments(B, D, H, W)
+    S = segments if segments > 0 else ops.scan_tm_segments(B, D, H, W)
     carry = torch.full((B * 4 * max(S, 1) * 2 * N * D,), float("nan"), device="cuda")
     y = torch.full((B, H * W, D), float("nan"), device="cuda", dtype=dt)
     if fuse:
@@ -115,16 +115,18 @@ def _scan_case(ops, H, W, D, N, R, fuse, dt, segments, slow=False, B=2, seed=0):
 @pytest.mark.parametrize("cfg", [(16, 24, 128, 4, 4, True), (64, 64, 128, 8, 4, True), (32, 48, 256, 8, 8, True), (24, 40, 256, 16, 8, True),
                                  (16, 16, 512, 16, 16, False), (8, 12, 1024, 32, 32, False), (6, 10, 128, 4, 4, True),
                                  (32, 32, 128, 8, 8, False), (2, 2, 128, 4, 4, True)])
-@pytest.mark.parametrize("segments", [1, 3, 0])
+@pytest.mark.parametrize("segments", [1, 3, 0, -8, -4])
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 def test_scan_time_major_vs_oracle(ops, cfg, segments, dt):
     H, W, D, N, R, fuse = cfg
+    if segments < 0 and (not fuse or N > 8):
+        pytest.skip("the time-sliced kernel exists for the fused-dt, d_state <= 8 levels")
     r = _scan_case(ops, H, W, D, N, R, fuse, dt, segments)
     assert r < TOL[dt], r
 
 
 @pytest.mark.parametrize("slow", [False, True])
-@pytest.mark.parametrize("segments", [1, 2, 8, 16])
+@pytest.mark.parametrize("segments", [1, 2, 8, 16, -8, -4, 0])
 def test_scan_time_major_segments_are_exact(ops, segments, slow):
     """Long rows (L = 16384) cut into 1 / 2 / 8 / 16 segments give the same answer as the sequential recurrence — including
     channels whose memory is far longer than a segment (A scaled by 1e-3, small delta), where the carry pass cannot stop early
