@@ -200,13 +200,16 @@ FD_DEVINL float tm_lg2(float x) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// log1p(exp(x)), branch-free, 2 MUFU ops (same form as fd_scan.cu's fast_softplus; threshold 20 as selective_scan_fn)
+// log1p(exp(x)), branch-free, 2 MUFU ops + 9 FP32 ops.  w = 1 + y rounds; for y < 1 the lost part d = y - (w - 1) is exact and
+// log1p(y) = log(w) + log1p(d / w) ~ log(w) + d (1 - y) (the factor only has to be right to O(1): the term is <= half an ulp of
+// w); for y >= 1 the factor (1 - min(y, 1)) switches the correction off.  Large x: log2(1 + 2^(x log2 e)) ln 2 = x to fp32
+// precision (selective_scan_fn switches to the identity above 20: same value within 3e-7 relative); the clamp keeps y finite.
 FD_DEVINL float tm_softplus(float x) {
+    x = fminf(x, 80.f);
     const float y = tm_ex2(x * 1.4426950408889634f);
     const float w = 1.f + y;
-    const float corr = (y < 1.f) ? (y - (w - 1.f)) * (1.f - y) : 0.f;
-    const float r = fmaf(tm_lg2(w), 0.6931471805599453f, corr);
-    return x > 20.f ? x : r;
+    const float corr = (y - (w - 1.f)) * (1.f - fminf(y, 1.f));
+    return fmaf(tm_lg2(w), 0.6931471805599453f, corr);
 }
 template <typename T> FD_DEVINL uint32_t tm_pack2(float a, float b) {
     if constexpr (std::is_same<T, __nv_bfloat16>::value) {
@@ -311,22 +314,98 @@ __global__ void __launch_bounds__(256) x_proj_tm_kernel(const T* __restrict__ xs
         const float* bk_bias = dt_bias + (long)k * D;
         T* d0p = dts + ((long)bk * L + r0) * D;
         T* d1p = dts + ((long)bk * L + r1) * D;
-        for (int nd = 0; nd < D / 8; ++nd) {
-            float o[4] = {0.f, 0.f, 0.f, 0.f};
+        // B fragments (dt_proj weights, K-contiguous rows of dw16) come straight from global memory / L1: they are the same for
+        // every block of a direction.  The loads of n-tile nd + 1 are issued before the MMAs and the softplus epilogue of n-tile
+        // nd, so their latency sits under ~60 instructions of work instead of in front of every MMA.
+        const int nk = Rp / 16;
+        uint32_t bcur[2][2], bnxt[2][2];
+        float2 bbc, bbn;
+        auto load_b = [&](int nd, uint32_t (&bf)[2][2], float2& bb) {
             const T* wrow = wd + (long)(nd * 8 + g) * Rp + 2 * t4;
 #pragma unroll
             for (int kt = 0; kt < 2; ++kt) {
-                if (kt * 16 < Rp) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wrow + kt * 16);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wrow + kt * 16 + 8);
-                    mma_16816<T>(o, afr[kt], b0, b1);
+                if (kt < nk) {
+                    bf[kt][0] = *reinterpret_cast<const uint32_t*>(wrow + kt * 16);
+                    bf[kt][1] = *reinterpret_cast<const uint32_t*>(wrow + kt * 16 + 8);
+                } else {
+                    bf[kt][0] = bf[kt][1] = 0u;
                 }
             }
+            bb = __ldg(reinterpret_cast<const float2*>(bk_bias + nd * 8 + 2 * t4));
+        };
+        load_b(0, bcur, bbc);
+        const int nnd = D / 8;
+        for (int nd = 0; nd < nnd; ++nd) {
+            if (nd + 1 < nnd) load_b(nd + 1, bnxt, bbn);
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt)
+                if (kt < nk) mma_16816<T>(o, afr[kt], bcur[kt][0], bcur[kt][1]);
             const int d = nd * 8 + 2 * t4;
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(bk_bias + d));
-            if (r0 < L) *reinterpret_cast<uint32_t*>(d0p + d) = tm_pack2<T>(tm_softplus(o[0] + bb.x), tm_softplus(o[1] + bb.y));
-            if (r1 < L) *reinterpret_cast<uint32_t*>(d1p + d) = tm_pack2<T>(tm_softplus(o[2] + bb.x), tm_softplus(o[3] + bb.y));
+            if (r0 < L) *reinterpret_cast<uint32_t*>(d0p + d) = tm_pack2<T>(tm_softplus(o[0] + bbc.x), tm_softplus(o[1] + bbc.y));
+            if (r1 < L) *reinterpret_cast<uint32_t*>(d1p + d) = tm_pack2<T>(tm_softplus(o[2] + bbc.x), tm_softplus(o[3] + bbc.y));
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) { bcur[kt][0] = bnxt[kt][0]; bcur[kt][1] = bnxt[kt][1]; }
+            bbc = bbn;
         }
+    }
+}
+
+template <typename T> FD_DEVINL float tm_ld16(const T* p) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) return __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(p)) << 16);
+    else return __half2float(*p);
+}
+
+// EfficientMerge (src/emamba2.py:238-262) as a running ELEMENT offset into one sample's (H, W, D) tensor: direction k, step l
+// -> pixel (2 (l / W2), 2 (l % W2) + kx) for the row-major directions, (2 (l % H2) + 1, 2 (l / H2) + kx) for the column-major
+// ones.  One add per step, one compare; no multiply in the loop.  H * W * D < 2^31 (checked by the launcher).
+struct MergeWalk {
+    int off, mr, mdiv, inc, wrap;
+    FD_DEVINL void init(int k, int l, int H, int W, int D) {
+        const int col = k & 1, kx = k >> 1;
+        mdiv = col ? (H >> 1) : (W >> 1);
+        const int mq = l / mdiv;
+        mr = l - mq * mdiv;
+        const int hh = col ? 2 * mr + 1 : 2 * mq, ww = col ? 2 * mq + kx : 2 * mr + kx;
+        off = (hh * W + ww) * D;
+        inc = col ? 2 * W * D : 2 * D;
+        wrap = col ? (2 - H * W) * D : W * D;            // extra offset when the fast index wraps
+    }
+    FD_DEVINL void next() {
+        off += inc;
+        if (++mr == mdiv) { mr = 0; off += wrap; }
+    }
+};
+
+// Four consecutive steps of one channel, software-pipelined by hand: the four delta chains (dt_proj FMAs, softplus = 2 MUFU)
+// and then the 4 N decay factors are independent of each other and of the recurrence, so they are issued back to back;
+// only h = a h + b is sequential.  Left to itself ptxas keeps each step's chain in program order and a warp then sits out
+// ~150 clk of dependent latency per step.
+template <typename T, int NS, int RDT, int XR, int USTRIDE, bool MASK>
+FD_DEVINL void load_steps4(const float* __restrict__ xr, const T* __restrict__ ur, const T* __restrict__ dr, const float (&wdt)[RDT > 0 ? RDT : 1],
+                           float bias, int nvalid, float (&dt)[4], float (&u)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if constexpr (RDT > 0) {
+            float t = bias;
+#pragma unroll
+            for (int r = 0; r < RDT; r += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(xr + q * XR + r);
+                t = fmaf(wdt[r], v.x, t); t = fmaf(wdt[r + 1], v.y, t); t = fmaf(wdt[r + 2], v.z, t); t = fmaf(wdt[r + 3], v.w, t);
+            }
+            dt[q] = t;
+        } else {
+            dt[q] = tm_ld16<T>(dr + q * USTRIDE);
+        }
+        u[q] = tm_ld16<T>(ur + q * USTRIDE);
+    }
+    if constexpr (RDT > 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dt[q] = tm_softplus(dt[q]);
+    }
+    if constexpr (MASK) {                                // steps past the end of the row / segment: identity (a = 1, b = 0)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dt[q] = q < nvalid ? dt[q] : 0.f;
     }
 }
 
@@ -341,10 +420,6 @@ constexpr int SC_WARPS = 4;
 constexpr int SC_CHB = SC_WARPS * 32;
 constexpr float SC_DECAYED = -30.f;            // log2 of the decay below which a carry is dropped
 
-template <typename T> FD_DEVINL float tm_ld16(const T* p) {
-    if constexpr (std::is_same<T, __nv_bfloat16>::value) return __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(p)) << 16);
-    else return __half2float(*p);
-}
 
 template <typename T, int NS, int RDT, bool CARRY>
 __global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
@@ -353,6 +428,7 @@ __global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
     T* __restrict__ y, int D, int L, int H, int W, int S, int seg_len) {
     constexpr int XR = RDT + 2 * NS;                    // floats per step in xdbl
     constexpr bool HAS_DT = RDT == 0;                   // delta comes from dts_tm
+    constexpr bool PRE_A = NS <= 8;                     // decay factors of a 4-step block computed ahead of the recurrence
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_x = reinterpret_cast<float*>(smem_raw);                              // [2][SC_T][XR]
     T* s_u = reinterpret_cast<T*>(s_x + 2 * SC_T * XR);                           // [2][SC_T][SC_CHB]
@@ -378,6 +454,7 @@ __global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
     }
     float wdt[RDT > 0 ? RDT : 1];
     float bias = 0.f;
+    wdt[0] = 0.f;
     if constexpr (RDT > 0) {
 #pragma unroll
         for (int r = 0; r < RDT; ++r) wdt[r] = dt_w[(long)d * RDT + r];
@@ -402,22 +479,6 @@ __global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // delta and u of (chunk buffer, step s) for this lane's channel
-    auto load_step = [&](int buf, int s, float& dt, float& u) {
-        const float* xr = s_x + (buf * SC_T + s) * XR;
-        if constexpr (RDT > 0) {
-            float t = bias;
-#pragma unroll
-            for (int r = 0; r < RDT; r += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(xr + r);
-                t = fmaf(wdt[r], v.x, t); t = fmaf(wdt[r + 1], v.y, t); t = fmaf(wdt[r + 2], v.z, t); t = fmaf(wdt[r + 3], v.w, t);
-            }
-            dt = tm_softplus(t);
-        } else {
-            dt = tm_ld16<T>(s_d + (buf * SC_T + s) * SC_CHB + tid);
-        }
-        u = tm_ld16<T>(s_u + (buf * SC_T + s) * SC_CHB + tid);
-    };
 
     if constexpr (CARRY) {
         // ---- pass 1: backward walk from the segment end; acc_n = sum_t 2^(A2_n * cum_t) dt_t u_t B_tn, cum_t = sum_{s > t} dt_s
@@ -430,21 +491,29 @@ __global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
             if (c > 0) stage(c - 1, (c - 1) & 1);
             const int buf = c & 1;
             const int ns = min(SC_T, t_end - (t_begin + c * SC_T));
-#pragma unroll 4
-            for (int s = ns - 1; s >= 0; --s) {
-                float dt, u;
-                load_step(buf, s, dt, u);
-                const float du = dt * u;
-                const float* pb = s_x + (buf * SC_T + s) * XR + RDT;
+            const float* sx = s_x + buf * SC_T * XR;
+            const T* su = s_u + buf * SC_T * SC_CHB + tid;
+            const T* sd = s_d + buf * SC_T * SC_CHB + tid;
+#pragma unroll 2
+            for (int s0 = SC_T - 4; s0 >= 0; s0 -= 4) {
+                if (s0 >= ns) continue;                  // block-uniform (only the segment's last chunk can be short)
+                float dt[4], u[4], cq[4];
+                load_steps4<T, NS, RDT, XR, SC_CHB, true>(sx + s0 * XR, su + s0 * SC_CHB, sd + s0 * SC_CHB, wdt, bias, ns - s0, dt, u);
+                cq[3] = cum; cq[2] = cq[3] + dt[3]; cq[1] = cq[2] + dt[2]; cq[0] = cq[1] + dt[1];
+                cum = cq[0] + dt[0];
 #pragma unroll
-                for (int n = 0; n < NS; n += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(pb + n);
-                    h[n] = fmaf(tm_ex2(A2[n] * cum), du * b4.x, h[n]);
-                    h[n + 1] = fmaf(tm_ex2(A2[n + 1] * cum), du * b4.y, h[n + 1]);
-                    h[n + 2] = fmaf(tm_ex2(A2[n + 2] * cum), du * b4.z, h[n + 2]);
-                    h[n + 3] = fmaf(tm_ex2(A2[n + 3] * cum), du * b4.w, h[n + 3]);
+                for (int q = 3; q >= 0; --q) {
+                    const float du = dt[q] * u[q];
+                    const float* pb = sx + (s0 + q) * XR + RDT;
+#pragma unroll
+                    for (int n = 0; n < NS; n += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(pb + n);
+                        h[n] = fmaf(tm_ex2(A2[n] * cq[q]), du * b4.x, h[n]);
+                        h[n + 1] = fmaf(tm_ex2(A2[n + 1] * cq[q]), du * b4.y, h[n + 1]);
+                        h[n + 2] = fmaf(tm_ex2(A2[n + 2] * cq[q]), du * b4.z, h[n + 2]);
+                        h[n + 3] = fmaf(tm_ex2(A2[n + 3] * cq[q]), du * b4.w, h[n + 3]);
+                    }
                 }
-                cum += dt;
             }
             done = a2max * cum < SC_DECAYED;
         }
@@ -462,9 +531,8 @@ __global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
 #pragma unroll
             for (int n = 0; n < NS; ++n) h[n] = fmaf(cb[(long)(NS + n) * D], h[n], cb[(long)n * D]);
         }
-        const int H2 = H >> 1, W2 = W >> 1;
-        const int mdiv = (k & 1) ? H2 : W2;
-        int mq = t_begin / mdiv, mr = t_begin - mq * mdiv;
+        MergeWalk mw;
+        mw.init(k, t_begin, H, W, D);
         T* ybase = y + (long)b * H * W * D + dloc;
         stage(0, 0);
         for (int c = 0; c < nch; ++c) {
@@ -473,33 +541,50 @@ __global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
             if (c + 1 < nch) stage(c + 1, (c + 1) & 1);
             const int buf = c & 1;
             const int ns = min(SC_T, t_end - (t_begin + c * SC_T));
-#pragma unroll 4
-            for (int s = 0; s < ns; ++s) {
-                float dt, u;
-                load_step(buf, s, dt, u);
-                const float du = dt * u;
-                const float* pb = s_x + (buf * SC_T + s) * XR + RDT;
-                const float* pc = pb + NS;
-                float y0 = Dd * u, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+            const float* sx = s_x + buf * SC_T * XR;
+            const T* su = s_u + buf * SC_T * SC_CHB + tid;
+            const T* sd = s_d + buf * SC_T * SC_CHB + tid;
+            auto run = [&](auto mask_c) {
+                constexpr bool MASK = decltype(mask_c)::value;
+#pragma unroll 2
+                for (int s0 = 0; s0 < SC_T; s0 += 4) {
+                    if (MASK && s0 >= ns) break;
+                    float dt[4], u[4];
+                    load_steps4<T, NS, RDT, XR, SC_CHB, MASK>(sx + s0 * XR, su + s0 * SC_CHB, sd + s0 * SC_CHB, wdt, bias, ns - s0, dt, u);
+                    float a[PRE_A ? 4 : 1][PRE_A ? NS : 1];
+                    if constexpr (PRE_A) {
 #pragma unroll
-                for (int n = 0; n < NS; n += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(pb + n);
-                    const float4 c4 = *reinterpret_cast<const float4*>(pc + n);
-                    h[n] = fmaf(tm_ex2(dt * A2[n]), h[n], du * b4.x);
-                    y0 = fmaf(h[n], c4.x, y0);
-                    h[n + 1] = fmaf(tm_ex2(dt * A2[n + 1]), h[n + 1], du * b4.y);
-                    y1 = fmaf(h[n + 1], c4.y, y1);
-                    h[n + 2] = fmaf(tm_ex2(dt * A2[n + 2]), h[n + 2], du * b4.z);
-                    y2 = fmaf(h[n + 2], c4.z, y2);
-                    h[n + 3] = fmaf(tm_ex2(dt * A2[n + 3]), h[n + 3], du * b4.w);
-                    y3 = fmaf(h[n + 3], c4.w, y3);
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int n = 0; n < NS; ++n) a[q][n] = tm_ex2(dt[q] * A2[n]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float du = dt[q] * u[q];
+                        const float* pb = sx + (s0 + q) * XR + RDT;
+                        const float* pc = pb + NS;
+                        float y0 = Dd * u[q], y1 = 0.f, y2 = 0.f, y3 = 0.f;
+#pragma unroll
+                        for (int n = 0; n < NS; n += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(pb + n);
+                            const float4 c4 = *reinterpret_cast<const float4*>(pc + n);
+                            h[n] = fmaf(PRE_A ? a[PRE_A ? q : 0][PRE_A ? n : 0] : tm_ex2(dt[q] * A2[n]), h[n], du * b4.x);
+                            y0 = fmaf(h[n], c4.x, y0);
+                            h[n + 1] = fmaf(PRE_A ? a[PRE_A ? q : 0][PRE_A ? n + 1 : 0] : tm_ex2(dt[q] * A2[n + 1]), h[n + 1], du * b4.y);
+                            y1 = fmaf(h[n + 1], c4.y, y1);
+                            h[n + 2] = fmaf(PRE_A ? a[PRE_A ? q : 0][PRE_A ? n + 2 : 0] : tm_ex2(dt[q] * A2[n + 2]), h[n + 2], du * b4.z);
+                            y2 = fmaf(h[n + 2], c4.z, y2);
+                            h[n + 3] = fmaf(PRE_A ? a[PRE_A ? q : 0][PRE_A ? n + 3 : 0] : tm_ex2(dt[q] * A2[n + 3]), h[n + 3], du * b4.w);
+                            y3 = fmaf(h[n + 3], c4.w, y3);
+                        }
+                        if (!MASK || s0 + q < ns) {
+                            fd_st(ybase + mw.off, (y0 + y1) + (y2 + y3));
+                            mw.next();
+                        }
+                    }
                 }
-                int hh, ww;                              // EfficientMerge coordinates of step l (src/emamba2.py:207-210, 253-256)
-                if (k & 1) { ww = 2 * mq + (k >> 1); hh = 2 * mr + 1; }
-                else       { hh = 2 * mq; ww = 2 * mr + (k >> 1); }
-                fd_st(ybase + ((long)hh * W + ww) * D, (y0 + y1) + (y2 + y3));
-                if (++mr == mdiv) { mr = 0; ++mq; }
-            }
+            };
+            if (ns == SC_T) run(std::false_type{}); else run(std::true_type{});
         }
     }
 }
@@ -527,6 +612,7 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw_kernel(
     const float* __restrict__ dt_bias, const float* __restrict__ Dskip, T* __restrict__ y, int D, int L, int H, int W) {
     constexpr int XR = RDT + 2 * NS;
     constexpr int CH = TW * ST;                          // steps per chunk
+    static_assert(ST % 4 == 0 && NS % 4 == 0 && RDT % 4 == 0 && RDT > 0, "4-step blocks, float4 rows");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_g = reinterpret_cast<float*>(smem_raw);     // [TW][ST][32][NS]
     float* s_x = s_g + TW * ST * 32 * NS;                // [TW][ST][XR]
@@ -569,51 +655,53 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw_kernel(
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    const int H2 = H >> 1, W2 = W >> 1;
-    const int mdiv = (k & 1) ? H2 : W2;
     T* ybase = y + (long)b * H * W * D + dloc;
     const int nchunks = (L + CH - 1) / CH;
     stage(warp * ST);
     for (int c = 0; c < nchunks; ++c) {
         const int t0 = c * CH + warp * ST;
+        const int ns = min(ST, L - t0);                  // live steps of this slice (<= 0: the slice is past the end of the row)
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         // ---- phase A: local scan of the slice from h = 0
         float hl[NS], P[NS], yl[ST];
 #pragma unroll
         for (int n = 0; n < NS; ++n) { hl[n] = 0.f; P[n] = 1.f; }
+        auto phase_a = [&](auto mask_c) {
+            constexpr bool MASK = decltype(mask_c)::value;
 #pragma unroll
-        for (int i = 0; i < ST; ++i) {
-            const float* xr = xw + i * XR;
-            float t = bias;
+            for (int i0 = 0; i0 < ST; i0 += 4) {
+                float dt[4], u[4], a[4][NS];
+                load_steps4<T, NS, RDT, XR, 32, MASK>(xw + i0 * XR, uw + i0 * 32 + lane, nullptr, wdt, bias, ns - i0, dt, u);
 #pragma unroll
-            for (int r = 0; r < RDT; r += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(xr + r);
-                t = fmaf(wdt[r], v.x, t); t = fmaf(wdt[r + 1], v.y, t); t = fmaf(wdt[r + 2], v.z, t); t = fmaf(wdt[r + 3], v.w, t);
-            }
-            float dt = tm_softplus(t);
-            dt = (t0 + i < L) ? dt : 0.f;                // past the end of the row: identity step (a = 1, b = 0)
-            const float u = tm_ld16<T>(uw + i * 32 + lane);
-            const float du = dt * u;
-            float y0 = Dd * u, y1 = 0.f;
+                for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int n = 0; n < NS; n += 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(xr + RDT + n);
-                const float4 c4 = *reinterpret_cast<const float4*>(xr + RDT + NS + n);
-                const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
-                float gq[4];
+                    for (int n = 0; n < NS; ++n) a[q][n] = tm_ex2(dt[q] * A2[n]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float a = tm_ex2(dt * A2[n + j]);
-                    hl[n + j] = fmaf(a, hl[n + j], du * bb[j]);
-                    if (j & 1) y1 = fmaf(hl[n + j], cc[j], y1); else y0 = fmaf(hl[n + j], cc[j], y0);
-                    P[n + j] *= a;
-                    gq[j] = cc[j] * P[n + j];
+                for (int q = 0; q < 4; ++q) {
+                    const float* xr = xw + (i0 + q) * XR + RDT;
+                    const float du = dt[q] * u[q];
+                    float y0 = Dd * u[q], y1 = 0.f;
+#pragma unroll
+                    for (int n = 0; n < NS; n += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(xr + n);
+                        const float4 c4 = *reinterpret_cast<const float4*>(xr + NS + n);
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                        float gq[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            hl[n + j] = fmaf(a[q][n + j], hl[n + j], du * bb[j]);
+                            if (j & 1) y1 = fmaf(hl[n + j], cc[j], y1); else y0 = fmaf(hl[n + j], cc[j], y0);
+                            P[n + j] *= a[q][n + j];
+                            gq[j] = cc[j] * P[n + j];
+                        }
+                        *reinterpret_cast<float4*>(gw + (i0 + q) * 32 * NS + n) = make_float4(gq[0], gq[1], gq[2], gq[3]);
+                    }
+                    yl[i0 + q] = y0 + y1;
                 }
-                *reinterpret_cast<float4*>(gw + i * 32 * NS + n) = make_float4(gq[0], gq[1], gq[2], gq[3]);
             }
-            yl[i] = y0 + y1;
-        }
+        };
+        if (ns >= ST) phase_a(std::false_type{}); else phase_a(std::true_type{});
         {
             float* ph = s_ph + ((c & 1) * TW + warp) * 2 * NS * 32 + lane;
 #pragma unroll
@@ -640,24 +728,27 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw_kernel(
             for (int n = 0; n < NS; ++n) cy[n * 32] = fmaf(P[n], hin[n], hl[n]);
         }
         // ---- fix-up + EfficientMerge store
-        int mq = t0 / mdiv, mr = t0 - mq * mdiv;
-        const int ns = min(ST, L - t0);
+        if (ns > 0) {
+            MergeWalk mw;
+            mw.init(k, t0, H, W, D);
+            auto fixup = [&](auto mask_c) {
+                constexpr bool MASK = decltype(mask_c)::value;
 #pragma unroll
-        for (int i = 0; i < ST; ++i) {
-            if (i < ns) {
-                float yv = yl[i], y2 = 0.f;
+                for (int i = 0; i < ST; ++i) {
+                    if (!MASK || i < ns) {
+                        float yv = yl[i], y2 = 0.f;
 #pragma unroll
-                for (int n = 0; n < NS; n += 4) {
-                    const float4 g4 = *reinterpret_cast<const float4*>(gw + i * 32 * NS + n);
-                    yv = fmaf(g4.x, hin[n], yv); y2 = fmaf(g4.y, hin[n + 1], y2);
-                    yv = fmaf(g4.z, hin[n + 2], yv); y2 = fmaf(g4.w, hin[n + 3], y2);
+                        for (int n = 0; n < NS; n += 4) {
+                            const float4 g4 = *reinterpret_cast<const float4*>(gw + i * 32 * NS + n);
+                            yv = fmaf(g4.x, hin[n], yv); y2 = fmaf(g4.y, hin[n + 1], y2);
+                            yv = fmaf(g4.z, hin[n + 2], yv); y2 = fmaf(g4.w, hin[n + 3], y2);
+                        }
+                        fd_st(ybase + mw.off, yv + y2);
+                        mw.next();
+                    }
                 }
-                int hh, ww;
-                if (k & 1) { ww = 2 * mq + (k >> 1); hh = 2 * mr + 1; }
-                else       { hh = 2 * mq; ww = 2 * mr + (k >> 1); }
-                fd_st(ybase + ((long)hh * W + ww) * D, yv + y2);
-                if (++mr == mdiv) { mr = 0; ++mq; }
-            }
+            };
+            if (ns >= ST) fixup(std::false_type{}); else fixup(std::true_type{});
         }
     }
 }

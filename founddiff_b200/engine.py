@@ -335,7 +335,14 @@ class UnetEngine:
         # 16-bit modes: the TIME-MAJOR core (fd_ss2d_tm.cu) — channel-per-lane segmented scan, dt_proj fused where the rank is small
         tm_fuse = (N, R) in ((4, 4), (8, 4), (8, 8), (16, 8))
         use_tm = (dt != torch.float32 and use_xdt_tc and D % 128 == 0 and h % 2 == 0 and w % 2 == 0 and (tm_fuse or N in (4, 8, 16, 32))
-                  and os.environ.get("FD_SS2D_TM", "1") == "1")
+                  and os.environ.get("FD_SS2D_TM", "1") != "0")
+        if use_tm and os.environ.get("FD_SS2D_TM", "1") != "all":
+            # Measured per level at B = 16 (profiles/r2_scan_tm_variants.json, whole dwconv + x_proj + scan chain): the time-major
+            # chain wins wherever a lane has >= 16 states or the rows are many (one segment), and at the full-resolution d_state-4
+            # level (time-sliced scan, dt_proj fused: 2.91 vs 3.10 ms); at d_state 8 with few long rows the round-1 warp-shuffle
+            # chain is still 6 % ahead (1.09 vs 1.16 ms), so that one geometry keeps it.
+            if N == 8 and ops.scan_tm_plan(B, D, h, w, N, R if tm_fuse else 0) < 0 and D == 128:
+                use_tm = False
         if use_tm:
             scan_cl = fuse_dt = False
             dw_wt = dw_w.t().contiguous()                                  # tap-major (9, D)
