@@ -9,12 +9,40 @@ namespace {
 
 constexpr int HD = 32;            // channels per head (heads = C/32, src/DADiff.py:468)
 constexpr int TPH = 8, TPW = 32;  // pixel tile: 8 rows x 32 cols = 256 pixels
+constexpr int GRAM_REC = HD * HD + 2 * HD;   // one block's partial: 32x32 Gram + the squared norms of q and k
+
+// Reproducible reduction of the per-block Gram partials (no floating-point atomics): every block has stored its record in
+// ws[(b, head), chunk]; the block that arrives last for (b, head) adds the records in CHUNK ORDER and writes gram / qk_sq.
+// The grouping of pixels into chunks depends on the sample's geometry only, so a slice gets bit-identical attention in any
+// batch.  Counters live behind the records (ws must be zero on entry).  Called by all 256 threads of the block.
+__device__ __forceinline__ void gram_finish(float* __restrict__ ws, float* __restrict__ gram, float* __restrict__ qk_sq, int b, int head,
+                                            int C, int nchunks, int chunk, int B) {
+    __shared__ int s_last;
+    const int heads = C / HD, tid = threadIdx.x;
+    (void)chunk;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        int* counters = reinterpret_cast<int*>(ws + (long)B * heads * nchunks * GRAM_REC);
+        s_last = atomicAdd(counters + b * heads + head, 1) == nchunks - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* rec = ws + ((long)b * heads + head) * nchunks * GRAM_REC;
+    for (int i = tid; i < GRAM_REC; i += 256) {
+        float t = 0.f;
+        for (int k = 0; k < nchunks; ++k) t += __ldcg(rec + (long)k * GRAM_REC + i);
+        if (i < HD * HD) gram[((long)b * heads + head) * HD * HD + i] = t;
+        else qk_sq[((long)b * 2 + (i - HD * HD) / HD) * C + head * HD + (i - HD * HD) % HD] = t;
+    }
+}
 
 // grid: (C/32 heads, tiles, B).  Each block: dwconv for the head's q, k, v channels on a 8x32 pixel tile.
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_qkv_gram_kernel(const T* __restrict__ qkv, const float* __restrict__ w,
                                                               T* __restrict__ v_out, float* __restrict__ gram,
-                                                              float* __restrict__ qk_sq, int H, int W, int C) {
+                                                              float* __restrict__ qk_sq, float* __restrict__ ws, int H, int W, int C) {
     constexpr int VEC = fd_vec<T>::N;
     constexpr int NVH = HD / VEC;                    // vectors per 32-channel segment
     constexpr int HP = (TPH + 2) * (TPW + 2);        // halo pixels
@@ -86,16 +114,17 @@ __global__ void __launch_bounds__(256) dwconv_qkv_gram_kernel(const T* __restric
 #pragma unroll
             for (int j = 0; j < 4; ++j) g[j] = fmaf(qv, kp[j], g[j]);
         }
-        float* gg = gram + (((long)b * (C / HD) + head) * HD + gi) * HD + gj;
+        float* part = ws + (((long)b * (C / HD) + head) * gridDim.y + blockIdx.y) * GRAM_REC;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) atomicAdd(gg + j, g[j]);
+        for (int j = 0; j < 4; ++j) __stcg(part + gi * HD + gj + j, g[j]);
     }
     if (tid < 2 * HD) {
         const float* s = (tid < HD ? s_q : s_k) + (tid % HD);
         float acc = 0.f;
         for (int p = 0; p < TPH * TPW; ++p) { const float v = s[p * (HD + 1)]; acc = fmaf(v, v, acc); }
-        atomicAdd(qk_sq + ((long)b * 2 + tid / HD) * C + head * HD + tid % HD, acc);
+        __stcg(ws + (((long)b * (C / HD) + head) * gridDim.y + blockIdx.y) * GRAM_REC + HD * HD + tid, acc);
     }
+    gram_finish(ws, gram, qk_sq, b, head, C, (int)gridDim.y, (int)blockIdx.y, (int)gridDim.z);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -376,7 +405,7 @@ constexpr int GR_PIX = 4096;   // pixels per block
 
 template <typename T>
 __global__ void __launch_bounds__(256) gram_mma_kernel(const T* __restrict__ qkv, int ld, float* __restrict__ gram,
-                                                       float* __restrict__ qk_sq, int P, int C, int pf_tiles) {
+                                                       float* __restrict__ qk_sq, float* __restrict__ ws, int P, int C, int pf_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* s_qk = reinterpret_cast<T*>(smem_raw);                      // [2 buffers][2 (q,k)][256][QK_LD]
     float* s_red = reinterpret_cast<float*>(s_qk + 2 * 2 * GR_TILE * QK_LD);   // [32*32 + 2*32]
@@ -461,35 +490,38 @@ __global__ void __launch_bounds__(256) gram_mma_kernel(const T* __restrict__ qkv
         }
         __syncthreads();                                 // buffer `buf` may be refilled by the next-but-one stage
     }
-    {
-        const int g = lane >> 2, t4 = lane & 3;
+    // the 8 warps add their accumulators into s_red one after the other (warp order = pixel order): no shared-memory atomics
+    for (int wsel = 0; wsel < 8; ++wsel) {
+        if (warp == wsel) {
+            const int g = lane >> 2, t4 = lane & 3;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
+            for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const int row = mt * 16 + g, col = nt * 8 + 2 * t4;
-                atomicAdd(&s_red[row * HD + col], acc[mt][nt][0]);
-                atomicAdd(&s_red[row * HD + col + 1], acc[mt][nt][1]);
-                atomicAdd(&s_red[(row + 8) * HD + col], acc[mt][nt][2]);
-                atomicAdd(&s_red[(row + 8) * HD + col + 1], acc[mt][nt][3]);
-            }
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int ns = 0; ns < 2; ++ns) {
-                    float* r = s_red + HD * HD + a * HD;
-                    const int row = mt * 16 + g, col = mt * 16 + ns * 8 + 2 * t4;
-                    if (row == col) atomicAdd(&r[row], accd[a][mt][ns][0]);
-                    if (row == col + 1) atomicAdd(&r[row], accd[a][mt][ns][1]);
-                    if (row + 8 == col) atomicAdd(&r[row + 8], accd[a][mt][ns][2]);
-                    if (row + 8 == col + 1) atomicAdd(&r[row + 8], accd[a][mt][ns][3]);
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int row = mt * 16 + g, col = nt * 8 + 2 * t4;
+                    s_red[row * HD + col] += acc[mt][nt][0];
+                    s_red[row * HD + col + 1] += acc[mt][nt][1];
+                    s_red[(row + 8) * HD + col] += acc[mt][nt][2];
+                    s_red[(row + 8) * HD + col + 1] += acc[mt][nt][3];
                 }
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int ns = 0; ns < 2; ++ns) {
+                        float* r = s_red + HD * HD + a * HD;
+                        const int row = mt * 16 + g, col = mt * 16 + ns * 8 + 2 * t4;
+                        if (row == col) r[row] += accd[a][mt][ns][0];
+                        if (row == col + 1) r[row] += accd[a][mt][ns][1];
+                        if (row + 8 == col) r[row + 8] += accd[a][mt][ns][2];
+                        if (row + 8 == col + 1) r[row + 8] += accd[a][mt][ns][3];
+                    }
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
-    float* gg = gram + ((long)b * (C / HD) + head) * HD * HD;
-    for (int i = tid; i < HD * HD; i += 256) atomicAdd(gg + i, s_red[i]);
-    if (tid < 2 * HD) atomicAdd(qk_sq + ((long)b * 2 + tid / HD) * C + head * HD + tid % HD, s_red[HD * HD + tid]);
+    float* part = ws + (((long)b * (C / HD) + head) * gridDim.y + blockIdx.y) * GRAM_REC;
+    for (int i = tid; i < GRAM_REC; i += 256) __stcg(part + i, s_red[i]);
+    gram_finish(ws, gram, qk_sq, b, head, C, (int)gridDim.y, (int)blockIdx.y, (int)gridDim.z);
 }
 
 // grid: (heads, B); block 256.  attn in shared memory, then weff rows.
@@ -530,9 +562,15 @@ __global__ void __launch_bounds__(256) attn_weff_kernel(const float* __restrict_
 
 }  // namespace
 
-extern "C" int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, float* gram, float* qk_sq, int B, int H, int W,
-                                     int C, int dtype, cudaStream_t stream) {
-    if (!qkv || !w || !v || !gram || !qk_sq || B <= 0 || H <= 0 || W <= 0 || C <= 0) return FD_ERR_BAD_ARGUMENT;
+extern "C" long fd_gram_ws_floats(int B, int H, int W, int C, int dtype) {
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % HD) return 0;
+    const long chunks = dtype == FD_F32 ? (long)fd_cdiv(H, TPH) * fd_cdiv(W, TPW) : fd_cdiv((long)H * W, GR_PIX);
+    return (long)B * (C / HD) * chunks * GRAM_REC + (long)B * (C / HD);
+}
+
+extern "C" int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, float* gram, float* qk_sq, float* ws, int B, int H,
+                                     int W, int C, int dtype, cudaStream_t stream) {
+    if (!qkv || !w || !v || !gram || !qk_sq || !ws || B <= 0 || H <= 0 || W <= 0 || C <= 0) return FD_ERR_BAD_ARGUMENT;
     if (C % HD) return FD_ERR_UNSUPPORTED;
     const int ntiles = fd_cdiv(H, TPH) * fd_cdiv(W, TPW);
     if (dtype == FD_F32) {
@@ -546,7 +584,7 @@ extern "C" int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, f
             if (e != cudaSuccess) return (int)e;
             attr_set = true;
         }
-        dwconv_qkv_gram_kernel<T><<<grid, 256, smem, stream>>>((const T*)qkv, w, (T*)v, gram, qk_sq, H, W, C);
+        dwconv_qkv_gram_kernel<T><<<grid, 256, smem, stream>>>((const T*)qkv, w, (T*)v, gram, qk_sq, ws, H, W, C);
         FD_LAUNCH_CHECK();
         return 0;
     }
@@ -585,7 +623,7 @@ extern "C" int fd_dwconv3x3_nhwc(const void* in, const float* w, const float* bi
 }
 
 template <typename T>
-static int gram_launch(const void* qkv, int ld, float* gram, float* qk_sq, int B, int P, int C, cudaStream_t stream) {
+static int gram_launch(const void* qkv, int ld, float* gram, float* qk_sq, float* ws, int B, int P, int C, cudaStream_t stream) {
     const size_t smem = (size_t)2 * 2 * GR_TILE * QK_LD * sizeof(T) + (size_t)(HD * HD + 2 * HD) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -597,17 +635,17 @@ static int gram_launch(const void* qkv, int ld, float* gram, float* qk_sq, int B
     // L2 prefetch distance in 256-pixel tiles.  OFF: measured 235 -> 266 us at 16x262144x64 with 2 or 4 tiles (unlike the depthwise
     // kernels, where it gave 10 %): the q / k half-lines of the two heads are already shared through L2 by neighbouring blocks
     static const int pf_tiles = getenv("FD_GRAM_PF") ? atoi(getenv("FD_GRAM_PF")) : 0;
-    gram_mma_kernel<T><<<grid, 256, smem, stream>>>((const T*)qkv, ld, gram, qk_sq, P, C, pf_tiles);
+    gram_mma_kernel<T><<<grid, 256, smem, stream>>>((const T*)qkv, ld, gram, qk_sq, ws, P, C, pf_tiles);
     FD_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int fd_gram_qk(const void* qkv, int ld, float* gram, float* qk_sq, int B, int P, int C, int dtype,
+extern "C" int fd_gram_qk(const void* qkv, int ld, float* gram, float* qk_sq, float* ws, int B, int P, int C, int dtype,
                           cudaStream_t stream) {
-    if (!qkv || !gram || !qk_sq || B <= 0 || P <= 0 || C <= 0 || ld < 2 * C) return FD_ERR_BAD_ARGUMENT;
+    if (!qkv || !gram || !qk_sq || !ws || B <= 0 || P <= 0 || C <= 0 || ld < 2 * C) return FD_ERR_BAD_ARGUMENT;
     if (C % HD || ld % 8) return FD_ERR_UNSUPPORTED;
-    if (dtype == FD_BF16) return gram_launch<__nv_bfloat16>(qkv, ld, gram, qk_sq, B, P, C, stream);
-    if (dtype == FD_F16) return gram_launch<__half>(qkv, ld, gram, qk_sq, B, P, C, stream);
+    if (dtype == FD_BF16) return gram_launch<__nv_bfloat16>(qkv, ld, gram, qk_sq, ws, B, P, C, stream);
+    if (dtype == FD_F16) return gram_launch<__half>(qkv, ld, gram, qk_sq, ws, B, P, C, stream);
     return FD_ERR_UNSUPPORTED;
 }
 

@@ -274,7 +274,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint64_t* tfull_bar = wfull_bar + 1;              // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
-    float* s_gn = (float*)(tmem_slot + 2);            // [2][8] GroupNorm partial sums of the current sample
+    float* s_gn = (float*)(tmem_slot + 2);            // [16 epilogue warps][2][8] GroupNorm partial sums of the current sample
+    int* s_gn_last = (int*)(s_gn + NUM_EPI_WARPS * 16);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fd_conv_params& p = q.p;
@@ -288,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 16) s_gn[threadIdx.x] = 0.f;
+    if (threadIdx.x < NUM_EPI_WARPS * 16) s_gn[threadIdx.x] = 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -451,7 +452,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 4; ++i) { gacc_s[i][0] = gacc_s[i][1] = gacc_q[i][0] = gacc_q[i][1] = 0.f; }
         int cur_b = -1, cur_n0 = 0;
-        auto gn_reduce_to_smem = [&]() {               // warp-reduce the lane accumulators into the block's s_gn
+        // Every epilogue warp owns a row of s_gn: no shared-memory atomics, the order of additions is the program order.
+        float* my_gn = s_gn + (warp - 2) * 16;
+        auto gn_reduce_to_smem = [&]() {               // warp-reduce the lane accumulators into this warp's row of s_gn
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
                 if (ci * 16 < cols_per_warp) {
@@ -460,23 +463,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                         const float sv = fd_warp_sum(gacc_s[ci][hf]), qv = fd_warp_sum(gacc_q[ci][hf]);
                         if (lane == 0) {
                             const int g = (cur_n0 + (ci * 4 + cg) * 16 + hf * 8) >> q.cpg_shift;
-                            atomicAdd(&s_gn[g], sv);
-                            atomicAdd(&s_gn[8 + g], qv);
+                            my_gn[g] += sv;
+                            my_gn[8 + g] += qv;
                         }
                         gacc_s[ci][hf] = gacc_q[ci][hf] = 0.f;
                     }
                 }
             }
         };
-        auto gn_flush_sample = [&]() {                 // all 16 epilogue warps: block sums of sample cur_b -> global
+        // All 16 epilogue warps: the block's sums of sample cur_b leave the block.
+        //   gn_ws given: stored into the slot of this block's residue class (tile index within the sample mod grid size) — the set
+        //   of tiles behind a slot and their order depend on the sample's geometry only; the block that completes the sample
+        //   (arrival counter) adds the slots in index order and writes gn_sums.  Reproducible bit for bit.
+        //   no gn_ws: floating-point atomics straight into gn_sums (order = block timing).
+        const int tps = total_tiles / p.B;             // tiles per sample
+        const int nslots = (int)gridDim.x;
+        auto gn_flush_sample = [&]() {
             asm volatile("bar.sync 1, 512;" ::: "memory");
             const int et = threadIdx.x - 64;
-            if (cur_b >= 0 && et < 2 * p.gn_groups) {
-                const int which = et / p.gn_groups, g = et % p.gn_groups;
-                atomicAdd(&p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which], s_gn[which * 8 + g]);
-                s_gn[which * 8 + g] = 0.f;
+            float tot = 0.f;
+            if (cur_b >= 0 && et < 16) {
+#pragma unroll
+                for (int w = 0; w < NUM_EPI_WARPS; ++w) { tot += s_gn[w * 16 + et]; s_gn[w * 16 + et] = 0.f; }
+                const int which = et >> 3, g = et & 7;
+                if (p.gn_ws) {
+                    const int slot = ((int)blockIdx.x + nslots - (int)(((long)cur_b * tps) % nslots)) % nslots;
+                    __stcg(p.gn_ws + ((long)cur_b * nslots + slot) * 16 + et, tot);
+                    __threadfence();
+                } else if (g < p.gn_groups) {
+                    atomicAdd(&p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which], tot);
+                }
             }
             asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (p.gn_ws && cur_b >= 0) {
+                if (et == 0) {
+                    int* counters = reinterpret_cast<int*>(p.gn_ws + (long)p.B * nslots * 16);
+                    const int expected = tps < nslots ? tps : nslots;
+                    *s_gn_last = atomicAdd(counters + cur_b, 1) == expected - 1;
+                }
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (*s_gn_last && et < 16) {
+                    __threadfence();
+                    float t = 0.f;
+                    for (int r = 0; r < nslots; ++r) t += __ldcg(p.gn_ws + ((long)cur_b * nslots + r) * 16 + et);
+                    const int which = et >> 3, g = et & 7;
+                    if (g < p.gn_groups) p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which] = t;
+                }
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+            }
         };
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -631,6 +665,13 @@ static int conv_dims(const fd_conv_params* p, int* Hout, int* Wout) {
 
 extern "C" int fd_conv_check_params(const fd_conv_params* p);
 
+extern "C" long fd_conv_gn_ws_floats(int B) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;   // no device: the B200 count
+    return B > 0 ? (long)B * (sms * 16 + 1) : 0;
+}
+
 extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
     if (fd_conv_check_params(p)) return 0;
     if (p->dtype != FD_BF16 && p->dtype != FD_F16) return 0;
@@ -748,12 +789,13 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     }
     const size_t data_bytes = q.halo ? (size_t)(q.b_stationary ? num_kb : q.stages_b) * b_tile + (size_t)q.stages * q.a_stage_bytes
                                      : (size_t)q.stages * stage_bytes;
-    plan->smem = data_bytes + 1024 /*align slack*/ + 512 /*barriers, gn*/;
-    if (plan->smem > 220 * 1024) { free(plan); return FD_ERR_UNSUPPORTED; }
+    plan->smem = data_bytes + 1024 /*align slack*/ + 2048 /*barriers, per-warp GroupNorm rows*/;
+    if (plan->smem > 222 * 1024) { free(plan); return FD_ERR_UNSUPPORTED; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    plan->grid = dim3((unsigned)(q.total_tiles < sms ? q.total_tiles : sms));
+    // with gn_ws the slot classes are residues modulo the grid size: always one block per SM, whatever the batch
+    plan->grid = dim3((unsigned)((q.total_tiles < sms && !(p->gn_sums && p->gn_ws)) ? q.total_tiles : sms));
     *out_plan = plan;
     return 0;
 }
@@ -763,14 +805,14 @@ extern "C" int fd_conv2d_tc_run(const fd_gemm_plan* plan, cudaStream_t stream) {
     static bool attr_bf16 = false, attr_f16 = false;
     if (plan->q.p.dtype == FD_BF16) {
         if (!attr_bf16) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr_bf16 = true;
         }
         conv_tc_kernel<__nv_bfloat16><<<plan->grid, NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
     } else {
         if (!attr_f16) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr_f16 = true;
         }

@@ -326,17 +326,16 @@ extern "C" int fd_ln_gate(const void* y, const void* xz, int ld, int z_off, cons
 // sample; thread t owns vector column (t % VR) so its group is fixed; smem + atomics finish the reduction.
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ y, float* __restrict__ sums, int P,
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ y, float* __restrict__ sums, float* __restrict__ ws, int P,
                                                        int C, int G, int pix_per_block) {
     constexpr int VEC = fd_vec<T>::N;
-    extern __shared__ float sm[];  // [G][2]
+    __shared__ float s_s[256], s_q[256];
+    __shared__ int s_last;
     const int b = blockIdx.y;
     const int vr = C / VEC;
     const int col = threadIdx.x % vr;
     const int rstep = blockDim.x / vr;
     const int r0 = threadIdx.x / vr;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
     const int p0 = blockIdx.x * pix_per_block;
     const int p1 = min(P, p0 + pix_per_block);
     float s = 0.f, q = 0.f;
@@ -346,22 +345,50 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ y, 
 #pragma unroll
         for (int e = 0; e < VEC; ++e) { s += v[e]; q += v[e] * v[e]; }
     }
-    const int g = (col * VEC) / (C / G);
-    atomicAdd(&sm[2 * g], s);
-    atomicAdd(&sm[2 * g + 1], q);
+    s_s[threadIdx.x] = s;
+    s_q[threadIdx.x] = q;
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&sums[(long)b * 2 * G + i], sm[i]);
+    // Block sums per group in THREAD ORDER, block partials in BLOCK ORDER by the last block to arrive: the result depends on the
+    // sample's data only (no floating-point atomics), so a slice gets the same statistics in any batch and on any run.
+    const int nblk = gridDim.x;
+    float* part = ws + ((long)b * nblk + blockIdx.x) * 2 * G;
+    if (threadIdx.x < 2 * G) {
+        const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+        const float* src = which ? s_q : s_s;
+        const int cpg_v = vr / G;                       // vector columns per group
+        float t = 0.f;
+        for (int r = 0; r < rstep; ++r)
+            for (int c = g * cpg_v; c < (g + 1) * cpg_v; ++c) t += src[r * vr + c];
+        __stcg(part + threadIdx.x, t);
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* counters = reinterpret_cast<int*>(ws + (long)gridDim.y * nblk * 2 * G);
+        s_last = atomicAdd(counters + b, 1) == nblk - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 2 * G) {
+        __threadfence();
+        float t = 0.f;
+        for (int k = 0; k < nblk; ++k) t += __ldcg(ws + ((long)b * nblk + k) * 2 * G + threadIdx.x);
+        sums[(long)b * 2 * G + threadIdx.x] = t;
+    }
 }
 
-extern "C" int fd_gn_stats(const void* y, float* sums, int B, int P, int C, int G, int dtype, cudaStream_t stream) {
-    if (!y || !sums || B <= 0 || P <= 0 || C <= 0 || G <= 0 || C % G) return FD_ERR_BAD_ARGUMENT;
+extern "C" long fd_gn_stats_ws_floats(int B, int P, int G) {
+    return (B > 0 && P > 0 && G > 0) ? (long)B * fd_cdiv(P, 256) * 2 * G + B : 0;
+}
+
+extern "C" int fd_gn_stats(const void* y, float* sums, float* ws, int B, int P, int C, int G, int dtype, cudaStream_t stream) {
+    if (!y || !sums || !ws || B <= 0 || P <= 0 || C <= 0 || G <= 0 || C % G) return FD_ERR_BAD_ARGUMENT;
     FD_DISPATCH_DTYPE(dtype, T, {
         constexpr int VEC = fd_vec<T>::N;
         const int vr = C / VEC;
-        if (C % VEC || (C / G) % VEC || vr > 256 || 256 % vr) return FD_ERR_UNSUPPORTED;
+        if (C % VEC || (C / G) % VEC || vr > 256 || 256 % vr || G > 64) return FD_ERR_UNSUPPORTED;
         const int ppb = 256;  // pixels per block
         dim3 grid(fd_cdiv(P, ppb), B);
-        gn_stats_kernel<T><<<grid, 256, 2 * G * sizeof(float), stream>>>((const T*)y, sums, P, C, G, ppb);
+        gn_stats_kernel<T><<<grid, 256, 0, stream>>>((const T*)y, sums, ws, P, C, G, ppb);
     });
     FD_LAUNCH_CHECK();
     return 0;

@@ -783,8 +783,9 @@ int pick_time_warps(int B, int D, int L, int NS, int RDT) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long blocks = (long)B * 4 * (D / 32);
     if (L < 2048) return 0;
+    // measured (profiles/r2_scan_tm_variants.json): with >= 512 channel-warps one unsegmented pass is faster than either
+    // form of time parallelism (16x256x16384 N8: 1.57 ms vs 1.95 time-sliced x4 vs 1.73 with 4 segments)
     if (blocks <= 2L * sms) return 8;
-    if (blocks <= 4L * sms) return 4;
     return 0;
 }
 
@@ -794,7 +795,7 @@ int pick_segments(int B, int D, int L) {
     static const int forced = getenv("FD_SCAN_SEGMENTS") ? atoi(getenv("FD_SCAN_SEGMENTS")) : 0;
     if (forced > 0) return forced;
     const long base_warps = (long)B * 4 * D / 32;
-    if (base_warps >= 148L * 4) return 1;               // >= 1 warp per scheduler: the carry pass would cost more than it buys
+    if (base_warps >= 512) return 1;                    // ~1 warp per scheduler: the carry pass would cost more than it buys
     int S = 1;
     while (S < 64 && base_warps * S < 148L * 24 && L / (2 * S) >= 2048) S *= 2;
     return S;

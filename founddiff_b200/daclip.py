@@ -159,53 +159,89 @@ class DAClipEncoder:
             fn()
         return tw["out"].view(B, tw["h"], tw["w"], tw["c"]).permute(0, 3, 1, 2)
 
+    # Library kernels (cuDNN stem, cuBLAS attention pool / heads) are launched on FIXED-size groups of slices, the last group
+    # zero-padded: cuDNN / cuBLAS choose algorithms (tilings, split-K) from the problem size, so a slice's embedding could change
+    # in the last bits with the batch it is in.  With a fixed group size every launch has the same shape, and within one launch a
+    # slice's result does not depend on its position or on the other slices.  The tcgen05 tower is per-sample by construction.
+    LIB_GROUP = 4
+
+    def _groups(self, x: torch.Tensor):
+        n, g = x.shape[0], self.LIB_GROUP
+        for a in range(0, n, g):
+            c = x[a:a + g]
+            if c.shape[0] < g:
+                c = torch.cat([c, c.new_zeros((g - c.shape[0],) + tuple(c.shape[1:]))], dim=0)
+            yield min(g, n - a), c
+
+    def _stem(self, x_input: torch.Tensor) -> torch.Tensor:
+        v = PREFIX + "clip_model.visual."
+        outs = []
+        for n, c in self._groups(x_input):
+            x = c.to(self.conv_dtype).repeat(1, 3, 1, 1).contiguous(memory_format=torch.channels_last)   # src/DADiff.py:692
+            x = F.relu(self._conv_bn(x, v + "conv1", v + "bn1", stride=2, padding=1))
+            x = F.relu(self._conv_bn(x, v + "conv2", v + "bn2", padding=1))
+            x = F.relu(self._conv_bn(x, v + "conv3", v + "bn3", padding=1))
+            outs.append(x[:n])
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    def _tower_lib(self, x: torch.Tensor) -> torch.Tensor:
+        v = PREFIX + "clip_model.visual."
+        outs = []
+        for n, c in self._groups(x):
+            c = F.avg_pool2d(c, 2)
+            for li, blocks in enumerate(self.layers):
+                for bi in range(blocks):
+                    c = self._bottleneck(f"{v}layer{li + 1}.{bi}.", c, 2 if (li > 0 and bi == 0) else 1)
+            outs.append(c[:n])
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    def _pool_heads(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        sd = self.sd
+        a = PREFIX + "clip_model.visual.attnpool."
+        B, C, H, W = x.shape
+        tok = x.reshape(B, C, H * W).permute(2, 0, 1)
+        tok = torch.cat([tok.mean(dim=0, keepdim=True), tok], dim=0)          # (HW+1, B, C)
+        # AttentionPool2d (src/DACLIP.py:168-211) with ONE query (the mean token).  k_proj / v_proj are linear, so they
+        # are applied to the query / to the attention-weighted token sum instead of to all HW+1 tokens (softmax weights
+        # sum to 1, so the v bias passes through): identical result, ~70x fewer FLOPs than projecting every token —
+        # as fp32 SIMT GEMMs (TF32 off) those two projections were 1.3 ms of the 4.6 ms embedding.
+        hd = C // self.heads
+        q = F.linear(tok[0], sd[a + "q_proj.weight"], sd[a + "q_proj.bias"]).reshape(B, self.heads, hd) * (hd ** -0.5)
+        wk = sd[a + "k_proj.weight"].reshape(self.heads, hd, C)
+        wv = sd[a + "v_proj.weight"].reshape(self.heads, hd, C)
+        qk = torch.einsum("bhd,hdc->bhc", q, wk)                               # W_k^T q per head
+        qb = torch.einsum("bhd,hd->bh", q, sd[a + "k_proj.bias"].reshape(self.heads, hd))
+        att = (torch.einsum("bhc,tbc->bht", qk, tok) + qb[..., None]).softmax(dim=-1)
+        xbar = torch.einsum("bht,tbc->bhc", att, tok)                          # attention-weighted token sum per head
+        o = (torch.einsum("bhc,hdc->bhd", xbar, wv) + sd[a + "v_proj.bias"].reshape(self.heads, hd)).reshape(1, B, C)
+        feat = F.linear(o, sd[a + "c_proj.weight"], sd[a + "c_proj.bias"])[0]
+        h1 = F.linear(F.relu(F.linear(feat, sd[PREFIX + "head1.0.weight"], sd[PREFIX + "head1.0.bias"])),
+                      sd[PREFIX + "head1.2.weight"], sd[PREFIX + "head1.2.bias"])
+        h2 = F.linear(F.relu(F.linear(feat, sd[PREFIX + "head2.0.weight"], sd[PREFIX + "head2.0.bias"])),
+                      sd[PREFIX + "head2.2.weight"], sd[PREFIX + "head2.2.bias"])
+        dose = h1 / h1.norm(dim=-1, keepdim=True).clamp_min(1e-30)             # src/DACLIP.py:1210 (the clamp only guards zero padding)
+        ctx = F.normalize(h2, dim=1)                                           # src/DACLIP.py:1207
+        return dose, ctx
+
     @torch.no_grad()
     def embed(self, x_input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        sd = self.sd
-        v = PREFIX + "clip_model.visual."
         prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
         try:
-            x = x_input.to(self.conv_dtype).repeat(1, 3, 1, 1).contiguous(memory_format=torch.channels_last)   # src/DADiff.py:692
-            x = F.relu(self._conv_bn(x, v + "conv1", v + "bn1", stride=2, padding=1))
-            x = F.relu(self._conv_bn(x, v + "conv2", v + "bn2", padding=1))
-            x = F.relu(self._conv_bn(x, v + "conv3", v + "bn3", padding=1))
+            x = self._stem(x_input)
             y = None
             if self.use_tc and x.shape[2] % 16 == 0 and x.shape[3] % 16 == 0:
                 y = self._tower_tc(x)                     # pools the (channels-last) stem output itself
-            if y is not None:
-                x = y
-            else:
-                x = F.avg_pool2d(x, 2)
-                for li, blocks in enumerate(self.layers):
-                    for bi in range(blocks):
-                        x = self._bottleneck(f"{v}layer{li + 1}.{bi}.", x, 2 if (li > 0 and bi == 0) else 1)
-            a = v + "attnpool."
+            x = y if y is not None else self._tower_lib(x)
             x = x.float()
-            B, C, H, W = x.shape
-            tok = x.reshape(B, C, H * W).permute(2, 0, 1)
-            tok = torch.cat([tok.mean(dim=0, keepdim=True), tok], dim=0)          # (HW+1, B, C)
-            # AttentionPool2d (src/DACLIP.py:168-211) with ONE query (the mean token).  k_proj / v_proj are linear, so they
-            # are applied to the query / to the attention-weighted token sum instead of to all HW+1 tokens (softmax weights
-            # sum to 1, so the v bias passes through): identical result, ~70x fewer FLOPs than projecting every token —
-            # as fp32 SIMT GEMMs (TF32 off) those two projections were 1.3 ms of the 4.6 ms embedding.
-            hd = C // self.heads
-            q = F.linear(tok[0], sd[a + "q_proj.weight"], sd[a + "q_proj.bias"]).reshape(B, self.heads, hd) * (hd ** -0.5)
-            wk = sd[a + "k_proj.weight"].reshape(self.heads, hd, C)
-            wv = sd[a + "v_proj.weight"].reshape(self.heads, hd, C)
-            qk = torch.einsum("bhd,hdc->bhc", q, wk)                               # W_k^T q per head
-            qb = torch.einsum("bhd,hd->bh", q, sd[a + "k_proj.bias"].reshape(self.heads, hd))
-            att = (torch.einsum("bhc,tbc->bht", qk, tok) + qb[..., None]).softmax(dim=-1)
-            xbar = torch.einsum("bht,tbc->bhc", att, tok)                          # attention-weighted token sum per head
-            o = (torch.einsum("bhc,hdc->bhd", xbar, wv) + sd[a + "v_proj.bias"].reshape(self.heads, hd)).reshape(1, B, C)
-            feat = F.linear(o, sd[a + "c_proj.weight"], sd[a + "c_proj.bias"])[0]
-            h1 = F.linear(F.relu(F.linear(feat, sd[PREFIX + "head1.0.weight"], sd[PREFIX + "head1.0.bias"])),
-                          sd[PREFIX + "head1.2.weight"], sd[PREFIX + "head1.2.bias"])
-            h2 = F.linear(F.relu(F.linear(feat, sd[PREFIX + "head2.0.weight"], sd[PREFIX + "head2.0.bias"])),
-                          sd[PREFIX + "head2.2.weight"], sd[PREFIX + "head2.2.bias"])
-            dose = h1 / h1.norm(dim=-1, keepdim=True)                              # src/DACLIP.py:1210
-            ctx = F.normalize(h2, dim=1)                                           # src/DACLIP.py:1207
+            dose, ctx = [], []
+            for n, c in self._groups(x):
+                d, cx = self._pool_heads(c)
+                dose.append(d[:n])
+                ctx.append(cx[:n])
+            dose = dose[0] if len(dose) == 1 else torch.cat(dose, dim=0)
+            ctx = ctx[0] if len(ctx) == 1 else torch.cat(ctx, dim=0)
         finally:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
         return dose.contiguous(), ctx.contiguous()

@@ -243,6 +243,8 @@ class UnetEngine:
         y = self.buf(f"Y{l}", B, P, cout)
         src1 = srcs[1] if len(srcs) > 1 else None
         acc = self._acc(B * GN_GROUPS * 2)
+        # zeroed every forward with the other accumulators: slots + arrival counters of the reproducible GroupNorm sums
+        acc_ws = self._acc(max(ops.conv_gn_ws_floats(B), ops.gn_stats_ws_floats(B, P, GN_GROUPS)))
         has_res = (p + ".res_conv.weight") in sd
         if has_res:
             sk = self.buf(f"SK{l}", B, P, cout)
@@ -258,7 +260,8 @@ class UnetEngine:
             sums = self._acc_view(acc, B, GN_GROUPS, 2)
             holder["sums"] = sums
             holder["conv"] = ops.Conv(srcs[0], wc, y, B=B, Hin=h, Win=w, KH=3, KW=3, pad=1, src1=src1, bias=bc,
-                                      gn_sums=sums, gn_groups=GN_GROUPS, prefer_tc=self.prefer_tc)
+                                      gn_sums=sums, gn_groups=GN_GROUPS, prefer_tc=self.prefer_tc,
+                                      gn_ws=self._acc_view(acc_ws, self._acc_slices[acc_ws][1]))
             if has_res:
                 holder["rconv"] = ops.Conv(srcs[0], wr, sk, B=B, Hin=h, Win=w, src1=src1, bias=br, prefer_tc=self.prefer_tc)
         self._acc_users.append(bind)
@@ -312,6 +315,7 @@ class UnetEngine:
         temp = f32(p + ".attn_blk.temperature").reshape(-1).contiguous()
         acc_g = self._acc(B * heads * 32 * 32)
         acc_q = self._acc(B * 2 * C)
+        acc_gw = self._acc(ops.gram_ws_floats(B, h, w, C, dt))      # per-chunk Gram records + arrival counters (zeroed per forward)
         tc = self.prefer_tc
         holder = {}
         c_in = ops.Conv(a, in_w, xz, B=B, Hin=h, Win=w, silu_from=2 * C, prefer_tc=tc)
@@ -370,6 +374,7 @@ class UnetEngine:
         def bind():
             holder["gram"] = self._acc_view(acc_g, B, heads, 32, 32)
             holder["qk"] = self._acc_view(acc_q, B, 2, C)
+            holder["gws"] = self._acc_view(acc_gw, self._acc_slices[acc_gw][1])
         self._acc_users.append(bind)
 
         self.paths[p] = ((f"time-major scan, {S_tm} segment(s)" if S_tm > 0 else f"time-major scan, time-sliced x{-S_tm}")
@@ -393,7 +398,7 @@ class UnetEngine:
                 ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
                 c_qkv.run()
                 ops.dwconv3x3_nhwc(qkv, qdw_wt, None, qkv2, B, h, w, 3 * C)
-                ops.gram_qk(qkv2, 3 * C, holder["gram"], holder["qk"], B, P, C)
+                ops.gram_qk(qkv2, 3 * C, holder["gram"], holder["qk"], B, P, C, ws=holder["gws"])
                 ops.attn_weff(holder["gram"], holder["qk"], temp, proj_w, weff, B, C)
                 c_att.run()
                 return
@@ -428,9 +433,9 @@ class UnetEngine:
             c_qkv.run()
             if split_attn:
                 ops.dwconv3x3_nhwc(qkv, qdw_wt, None, qkv2, B, h, w, 3 * C)
-                ops.gram_qk(qkv2, 3 * C, holder["gram"], holder["qk"], B, P, C)
+                ops.gram_qk(qkv2, 3 * C, holder["gram"], holder["qk"], B, P, C, ws=holder["gws"])
             else:
-                ops.dwconv3x3_qkv_gram(qkv, qdw_w, v, holder["gram"], holder["qk"], B, h, w, C)
+                ops.dwconv3x3_qkv_gram(qkv, qdw_w, v, holder["gram"], holder["qk"], B, h, w, C, ws=holder["gws"])
             ops.attn_weff(holder["gram"], holder["qk"], temp, proj_w, weff, B, C)
             c_att.run()
         self.steps.append(run)

@@ -140,9 +140,13 @@ class Conv:
 
     def __init__(self, src0, weight, out, *, B, Hin, Win, KH=1, KW=1, stride=1, pad=0, upsample=False, src1=None,
                  bias=None, gate=None, gate_stride=0, addend=None, silu_from=None, gn_sums=None, gn_groups=0,
-                 per_batch_weight=False, prefer_tc=True, c0=None, ld0=0, relu_out=False):
+                 per_batch_weight=False, prefer_tc=True, c0=None, ld0=0, relu_out=False, gn_ws=None):
         """`c0` / `ld0`: read only the first c0 channels of rows of pitch ld0 starting at src0's data pointer (src0 may
-        be a strided channel-slice view)."""
+        be a strided channel-slice view).
+        `gn_sums` (B, G, 2): GroupNorm statistics of the output.  With `gn_ws` (zeroed before every run: conv_gn_ws_floats(B) for
+        the tcgen05 kernel, gn_stats_ws_floats(B, P, G) otherwise — pass max of the two) they are reproducible: the tcgen05 kernel
+        reduces fixed per-sample slots in order; any other shape runs the convolution without statistics and a separate
+        reproducible fd_gn_stats pass over its output.  Without gn_ws: float atomics (gn_sums zeroed by the caller)."""
         lib = _lib.load()
         c0 = src0.shape[-1] if c0 is None else c0
         c1 = src1.shape[-1] if src1 is not None else 0
@@ -151,6 +155,8 @@ class Conv:
         p.src0 = c_void_p(src0.data_ptr()) if ld0 else _p(src0)
         p.src1, p.weight, p.out = _p(src1), _p(weight), _p(out)
         p.bias, p.gate, p.addend, p.gn_sums = _f32(bias), _f32(gate), _p(addend), _f32(gn_sums)
+        p.gn_ws = _f32(gn_ws)
+        self._gn = None
         p.c0, p.c1, p.B, p.Hin, p.Win, p.Cout = c0, c1, B, Hin, Win, cout
         p.ld0 = ld0
         p.KH, p.KW, p.stride, p.pad, p.upsample = KH, KW, stride, pad, int(upsample)
@@ -168,13 +174,20 @@ class Conv:
         assert addend is None or addend.dtype == out.dtype
         assert weight.numel() == (B if per_batch_weight else 1) * cout * KH * KW * (c0 + c1), (weight.shape, cout, KH, KW, c0, c1)
         self.params = p
-        self._keep = (src0, src1, weight, out, bias, gate, addend, gn_sums)
+        self._keep = (src0, src1, weight, out, bias, gate, addend, gn_sums, gn_ws)
         self._lib = lib
         self._plan = c_void_p()
         self.uses_tc = False
         if prefer_tc and lib.fd_conv2d_tc_supported(byref(p)):
             check(lib.fd_conv2d_tc_plan_create(byref(p), byref(self._plan)), "fd_conv2d_tc_plan_create")
             self.uses_tc = True
+        elif gn_sums is not None and gn_ws is not None:
+            # CUDA-core path: statistics by a separate reproducible pass over the stored output (the kernel's own epilogue sums
+            # use float atomics)
+            Pout = out.shape[-2] if out.dim() >= 2 else 0
+            assert gn_ws.numel() >= gn_stats_ws_floats(B, Pout, gn_groups), "gn_ws too small for the CUDA-core path"
+            p.gn_sums, p.gn_ws = None, None
+            self._gn = (out, gn_sums, gn_ws, B, Pout, cout, gn_groups)
 
     def describe(self) -> str:
         p = self.params
@@ -196,6 +209,9 @@ class Conv:
                 check(self._lib.fd_conv2d_tc_run(self._plan, _stream()), "fd_conv2d_tc_run")
             else:
                 check(self._lib.fd_conv2d_simt(byref(self.params), _stream()), "fd_conv2d_simt")
+        if self._gn is not None:
+            o, sums, ws, B, P, C, G = self._gn
+            gn_stats(o, sums, B, P, C, G, ws=ws)
 
     def __del__(self):
         try:
@@ -395,9 +411,16 @@ def merge_ln_gate(ys, xz, ld, z_off, gamma, beta, local, stats_ws, out, B, H, W,
               "fd_merge_ln_gate")
 
 
-def dwconv3x3_qkv_gram(qkv, w, v, gram, qk_sq, B, H, W, C):
+def gram_ws_floats(B, H, W, C, dtype) -> int:
+    """Size of the zeroed fp32 workspace of dwconv3x3_qkv_gram (fp32 storage) / gram_qk (16-bit storage)."""
+    return int(_lib.load().fd_gram_ws_floats(B, H, W, C, dtype_code(dtype)))
+
+
+def dwconv3x3_qkv_gram(qkv, w, v, gram, qk_sq, B, H, W, C, ws=None):
+    if ws is None:
+        ws = torch.zeros(gram_ws_floats(B, H, W, C, qkv.dtype), device=qkv.device)
     with _launched("dwconv_qkv_gram", f"{B}x{H}x{W}x{C}", 1):
-        check(_lib.load().fd_dwconv3x3_qkv_gram(_p(qkv), _f32(w), _p(v), _f32(gram), _f32(qk_sq), B, H, W, C,
+        check(_lib.load().fd_dwconv3x3_qkv_gram(_p(qkv), _f32(w), _p(v), _f32(gram), _f32(qk_sq), _f32(ws), B, H, W, C,
                                                 dtype_code(qkv.dtype), _stream()), "fd_dwconv3x3_qkv_gram")
 
 
@@ -409,9 +432,12 @@ def dwconv3x3_nhwc(x, w, bias, out, B, H, W, C, silu=False):
                                             _stream()), "fd_dwconv3x3_nhwc")
 
 
-def gram_qk(qkv, ld, gram, qk_sq, B, P, C):
+def gram_qk(qkv, ld, gram, qk_sq, B, P, C, ws=None):
+    """ws: zeroed fp32 scratch of gram_ws_floats(B, 1, P, C, dtype) elements (allocated here when omitted)."""
+    if ws is None:
+        ws = torch.zeros(gram_ws_floats(B, 1, P, C, qkv.dtype), device=qkv.device)
     with _launched("gram_qk", f"{B}x{P}x{C}", 1):
-        check(_lib.load().fd_gram_qk(_p(qkv), ld, _f32(gram), _f32(qk_sq), B, P, C, dtype_code(qkv.dtype), _stream()),
+        check(_lib.load().fd_gram_qk(_p(qkv), ld, _f32(gram), _f32(qk_sq), _f32(ws), B, P, C, dtype_code(qkv.dtype), _stream()),
               "fd_gram_qk")
 
 
@@ -421,9 +447,22 @@ def attn_weff(gram, qk_sq, temperature, proj_w, weff, B, C):
                                        dtype_code(weff.dtype), _stream()), "fd_attn_weff")
 
 
-def gn_stats(y, sums, B, P, C, G):
+def gn_stats_ws_floats(B, P, G) -> int:
+    return int(_lib.load().fd_gn_stats_ws_floats(B, P, G))
+
+
+def conv_gn_ws_floats(B) -> int:
+    """Size of the `gn_ws` workspace of a Conv with gn_sums (reproducible GroupNorm statistics)."""
+    return int(_lib.load().fd_conv_gn_ws_floats(B))
+
+
+def gn_stats(y, sums, B, P, C, G, ws=None):
+    """sums (B, G, 2) = per-group (sum, sum of squares) of y (B, P, C); reproducible (no float atomics).  ws: ZEROED fp32 scratch of
+    gn_stats_ws_floats(B, P, G) elements (allocated here when omitted)."""
+    if ws is None:
+        ws = torch.zeros(gn_stats_ws_floats(B, P, G), device=y.device, dtype=torch.float32)
     with _launched("gn_stats", f"{B}x{P}x{C}", 1):
-        check(_lib.load().fd_gn_stats(_p(y), _f32(sums), B, P, C, G, dtype_code(y.dtype), _stream()), "fd_gn_stats")
+        check(_lib.load().fd_gn_stats(_p(y), _f32(sums), _f32(ws), B, P, C, G, dtype_code(y.dtype), _stream()), "fd_gn_stats")
 
 
 def gn_silu_add(y, sums, gamma, beta, skip, out, B, P, C, G, eps=1e-5):

@@ -81,7 +81,12 @@ int fd_selective_scan_fwd_merge_cl(const void* u, const void* delta, const float
  *   acc[m, n]  = sum_{kh,kw,ci} in[b, ho*stride-pad+kh, wo*stride-pad+kw, ci] * weight[(b,) n, kh, kw, ci]
  *   v          = acc + bias[n];  if (n >= silu_from) v = silu(v)
  *   out[m, n]  = (addend ? addend[m, n] : 0) + (gate ? gate[b*gate_stride + n] : 1) * v
- *   gn_sums[b, n / (Cout/gn_groups), 0:2] += (sum v, sum v^2)          (optional GroupNorm partial statistics)
+ *   gn_sums[b, n / (Cout/gn_groups), 0:2]  = (sum v, sum v^2)          (optional GroupNorm statistics of the output)
+ * GroupNorm statistics are REPRODUCIBLE when `gn_ws` is given (tcgen05 path): every thread block stores the partial sums of the
+ * tiles it owns of a sample into its own slot — the slot is the residue class of the sample's tile index modulo the (fixed)
+ * grid size, so the grouping and the order of additions depend on the sample only, not on the batch it sits in or on block
+ * timing — and the last block to finish a sample adds the slots in index order.  Without gn_ws the sums are accumulated with
+ * floating-point atomics (gn_sums must then be zero on entry, and the last bits depend on the block schedule).
  * `in` is the channel concatenation of src0 (c0 channels) and src1 (c1 channels, may be NULL/0).
  * weight: (Cout, KH, KW, c0+c1) in `dtype`, or (B, Cout, KH, KW, c0+c1) when per_batch_weight.
  * --------------------------------------------------------------------------------------------------------- */
@@ -95,6 +100,7 @@ typedef struct {
     void* out;
     float* gn_sums;
     const void* weight_up4; /* upsample only (tcgen05 path): (4, Cout, 2, 2, c0) phase-summed weights, see fd_conv_tc.cu */
+    float* gn_ws;         /* optional: fd_conv_gn_ws_floats(B) floats, ZERO on entry (slots + per-sample arrival counters) */
     int c0, c1;
     int ld0;              /* row pitch (elements) of src0; 0 = dense (c0).  Lets a GEMM read a channel slice of a wider tensor */
     int B, Hin, Win, Cout;
@@ -109,6 +115,9 @@ typedef struct {
                              (mixed 16-bit storage: fp16 residual stream, bf16 block-internal tensors; the tensor cores
                              need both operands in ONE 16-bit format, the output type is free) */
 } fd_conv_params;
+
+/* Size (floats) of fd_conv_params.gn_ws for a batch of B samples on the current device. */
+long fd_conv_gn_ws_floats(int B);
 
 /* CUDA-core fp32-accumulate path (any dtype; the fp32 validation path and the fallback for odd shapes). */
 int fd_conv2d_simt(const fd_conv_params* p, cudaStream_t stream);
@@ -230,32 +239,37 @@ int fd_ln_gate(const void* y, const void* xz, int ld, int z_off, const float* ga
 
 /* ---------------------------------------------------------------------------------------------------------
  * TransposedAttention (src/DADiff.py:263-285), C/32 heads of 32 channels.
- * fd_dwconv3x3_qkv_gram: depthwise 3x3 over qkv (B,H,W,3C); writes v (B,H,W,C) and ACCUMULATES (atomics; zero
- *   the buffers first) gram[b, head, i, j] = sum_p q_i k_j  and  qk_sq[b, 0:2, c] = sum_p q_c^2, k_c^2.
+ * fd_dwconv3x3_qkv_gram: depthwise 3x3 over qkv (B,H,W,3C); writes v (B,H,W,C), gram[b, head, i, j] = sum_p q_i k_j and
+ *   qk_sq[b, 0:2, c] = sum_p q_c^2, k_c^2.  REPRODUCIBLE: every block stores the partial of its pixel chunk into `ws`
+ *   (fd_gram_ws_floats floats, ZERO on entry) and the last block of a (sample, head) adds the chunks in order — no
+ *   floating-point atomics, the same bits for a slice in any batch.
  * fd_attn_weff: attn = softmax(gram / (max(|q_i|,1e-12) max(|k_j|,1e-12)) * temperature[head]) and folds it
  *   into the output projection: weff[b, o, h*32+j] = sum_i proj_w[o, h*32+i] * attn[b,h,i,j]   (dtype),
  *   so that project_out(attn @ v) == v @ weff[b]^T, a per-sample 1x1 GEMM (fd_conv2d_*, per_batch_weight).
  * --------------------------------------------------------------------------------------------------------- */
-int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, float* gram, float* qk_sq, int B, int H,
+long fd_gram_ws_floats(int B, int H, int W, int C, int dtype);
+int fd_dwconv3x3_qkv_gram(const void* qkv, const float* w, void* v, float* gram, float* qk_sq, float* ws, int B, int H,
                           int W, int C, int dtype, cudaStream_t stream);
 /* 16-bit storage types (bf16 / fp16) split the first step into two streaming kernels:
  *   fd_dwconv3x3_nhwc: depthwise 3x3 (+bias, +SiLU) over a channels-last (B,H,W,C) tensor, register sliding window;
  *                      NB its weights are TAP-MAJOR: w is (9, C) fp32 (the other dwconv entry points take (C, 9));
- *   fd_gram_qk:        gram / qk_sq (same meaning as above, ACCUMULATED) from q = columns [0,C), k = columns [C,2C) of
+ *   fd_gram_qk:        gram / qk_sq (same meaning and the same `ws` contract as above) from q = columns [0,C), k = columns [C,2C) of
  *                      rows of pitch `ld` — q.k^T and the norms run on the tensor cores (mma.sync, fp32 accumulate).
  * v is then read in place (columns [2C,3C), ld0 = 3C) by the per-sample W_eff GEMM. */
 int fd_dwconv3x3_nhwc(const void* in, const float* w, const float* bias, void* out, int B, int H, int W, int C, int silu,
                       int dtype, cudaStream_t stream);
-int fd_gram_qk(const void* qkv, int ld, float* gram, float* qk_sq, int B, int P, int C, int dtype, cudaStream_t stream);
+int fd_gram_qk(const void* qkv, int ld, float* gram, float* qk_sq, float* ws, int B, int P, int C, int dtype, cudaStream_t stream);
 int fd_attn_weff(const float* gram, const float* qk_sq, const float* temperature, const float* proj_w,
                  void* weff, int B, int C, int dtype, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * GroupNorm(G) + SiLU + skip add (src/DADiff.py:213-229, 426-430):
- *   fd_gn_stats:     sums[b, g, 0:2] += (sum, sum of squares) over the group (zero the buffer first)
+ *   fd_gn_stats:     sums[b, g, 0:2] = (sum, sum of squares) over the group.  Reproducible: block partials go to `ws`
+ *                    (fd_gn_stats_ws_floats(B, P, G) floats, ZERO on entry) and are added in block order by the last block.
  *   fd_gn_silu_add:  out = silu((y - mean) * rstd * gamma + beta) + (skip ? skip : 0)
  * --------------------------------------------------------------------------------------------------------- */
-int fd_gn_stats(const void* y, float* sums, int B, int P, int C, int G, int dtype, cudaStream_t stream);
+long fd_gn_stats_ws_floats(int B, int P, int G);
+int fd_gn_stats(const void* y, float* sums, float* ws, int B, int P, int C, int G, int dtype, cudaStream_t stream);
 int fd_gn_silu_add(const void* y, const float* sums, const float* gamma, const float* beta, const void* skip,
                    void* out, int B, int P, int C, int G, float eps, int dtype, cudaStream_t stream);
 
