@@ -163,10 +163,14 @@ class DAClipEncoder:
     # zero-padded: cuDNN / cuBLAS choose algorithms (tilings, split-K) from the problem size, so a slice's embedding could change
     # in the last bits with the batch it is in.  With a fixed group size every launch has the same shape, and within one launch a
     # slice's result does not depend on its position or on the other slices.  The tcgen05 tower is per-sample by construction.
+    # Measured on B200 (tools/probes/batch_invariance.py): the bf16 stem + the fp32 pool / heads are position-independent inside a
+    # group of 4; the fp32 cuDNN tower of the validation mode is not (4e-8 on the embeddings), so fp32 mode runs slice by slice.
     LIB_GROUP = 4
 
     def _groups(self, x: torch.Tensor):
-        n, g = x.shape[0], self.LIB_GROUP
+        import os
+        n = x.shape[0]
+        g = int(os.environ.get("FD_DACLIP_GROUP", "0")) or (1 if self.conv_dtype == torch.float32 else self.LIB_GROUP)
         for a in range(0, n, g):
             c = x[a:a + g]
             if c.shape[0] < g:
