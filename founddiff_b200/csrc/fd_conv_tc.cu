@@ -274,8 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint64_t* tfull_bar = wfull_bar + 1;              // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
-    float* s_gn = (float*)(tmem_slot + 2);            // [16 epilogue warps][2][8] GroupNorm partial sums of the current sample
-    int* s_gn_last = (int*)(s_gn + NUM_EPI_WARPS * 16);
+    float* s_gn = (float*)(tmem_slot + 2);            // [2 flush parities][16 epilogue warps][2][8] GroupNorm partial sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fd_conv_params& p = q.p;
@@ -289,7 +288,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < NUM_EPI_WARPS * 16) s_gn[threadIdx.x] = 0.f;
+    if (threadIdx.x < 2 * NUM_EPI_WARPS * 16) s_gn[threadIdx.x] = 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -452,9 +451,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 4; ++i) { gacc_s[i][0] = gacc_s[i][1] = gacc_q[i][0] = gacc_q[i][1] = 0.f; }
         int cur_b = -1, cur_n0 = 0;
-        // Every epilogue warp owns a row of s_gn: no shared-memory atomics, the order of additions is the program order.
-        float* my_gn = s_gn + (warp - 2) * 16;
+        // Every epilogue warp owns a row of s_gn (no shared-memory atomics: the order of additions is the program order); the rows
+        // are double-buffered by flush parity so that ONE barrier per flush is enough — while the first epilogue warp sums and
+        // clears the rows of flush k, the other warps may already be adding into the rows of flush k + 1.
+        int gn_par = 0;
         auto gn_reduce_to_smem = [&]() {               // warp-reduce the lane accumulators into this warp's row of s_gn
+            float* my_gn = s_gn + (gn_par * NUM_EPI_WARPS + (warp - 2)) * 16;
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
                 if (ci * 16 < cols_per_warp) {
@@ -471,45 +473,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 }
             }
         };
-        // All 16 epilogue warps: the block's sums of sample cur_b leave the block.
+        // The block's sums of sample cur_b leave the block (all 16 epilogue warps call this; only the first one works).
         //   gn_ws given: stored into the slot of this block's residue class (tile index within the sample mod grid size) — the set
         //   of tiles behind a slot and their order depend on the sample's geometry only; the block that completes the sample
-        //   (arrival counter) adds the slots in index order and writes gn_sums.  Reproducible bit for bit.
+        //   (arrival counter, release / acquire through one fence on either side) adds the slots in index order and writes
+        //   gn_sums.  Reproducible bit for bit.
         //   no gn_ws: floating-point atomics straight into gn_sums (order = block timing).
         const int tps = total_tiles / p.B;             // tiles per sample
         const int nslots = (int)gridDim.x;
         auto gn_flush_sample = [&]() {
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            const int et = threadIdx.x - 64;
+            asm volatile("bar.sync 1, 512;" ::: "memory");          // every warp's row of this parity is complete
+            const int par = gn_par;
+            gn_par ^= 1;
+            if (warp != 2 || cur_b < 0) return;
             float tot = 0.f;
-            if (cur_b >= 0 && et < 16) {
+            if (lane < 16) {
+                float* rows = s_gn + par * NUM_EPI_WARPS * 16 + lane;
 #pragma unroll
-                for (int w = 0; w < NUM_EPI_WARPS; ++w) { tot += s_gn[w * 16 + et]; s_gn[w * 16 + et] = 0.f; }
-                const int which = et >> 3, g = et & 7;
-                if (p.gn_ws) {
-                    const int slot = ((int)blockIdx.x + nslots - (int)(((long)cur_b * tps) % nslots)) % nslots;
-                    __stcg(p.gn_ws + ((long)cur_b * nslots + slot) * 16 + et, tot);
-                    __threadfence();
-                } else if (g < p.gn_groups) {
-                    atomicAdd(&p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which], tot);
-                }
+                for (int w = 0; w < NUM_EPI_WARPS; ++w) { tot += rows[w * 16]; rows[w * 16] = 0.f; }
             }
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            if (p.gn_ws && cur_b >= 0) {
-                if (et == 0) {
-                    int* counters = reinterpret_cast<int*>(p.gn_ws + (long)p.B * nslots * 16);
-                    const int expected = tps < nslots ? tps : nslots;
-                    *s_gn_last = atomicAdd(counters + cur_b, 1) == expected - 1;
-                }
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                if (*s_gn_last && et < 16) {
-                    __threadfence();
-                    float t = 0.f;
-                    for (int r = 0; r < nslots; ++r) t += __ldcg(p.gn_ws + ((long)cur_b * nslots + r) * 16 + et);
-                    const int which = et >> 3, g = et & 7;
-                    if (g < p.gn_groups) p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which] = t;
-                }
-                asm volatile("bar.sync 1, 512;" ::: "memory");
+            const int which = lane >> 3, g = lane & 7;
+            if (!p.gn_ws) {
+                if (lane < 16 && g < p.gn_groups) atomicAdd(&p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which], tot);
+                return;
+            }
+            const int slot = ((int)blockIdx.x + nslots - (int)(((long)cur_b * tps) % nslots)) % nslots;
+            if (lane < 16) __stcg(p.gn_ws + ((long)cur_b * nslots + slot) * 16 + lane, tot);
+            __syncwarp();
+            int last = 0;
+            if (lane == 0) {
+                __threadfence();                                   // release: the 16 stores above (ordered by __syncwarp) before the arrival
+                int* counters = reinterpret_cast<int*>(p.gn_ws + (long)p.B * nslots * 16);
+                const int expected = tps < nslots ? tps : nslots;
+                last = atomicAdd(counters + cur_b, 1) == expected - 1;
+                if (last) __threadfence();                         // acquire: the other blocks' slots
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            __syncwarp();                                          // orders lane 0's acquire fence before the other lanes' loads
+            if (last && lane < 16) {
+                float t = 0.f;
+                for (int r = 0; r < nslots; ++r) t += __ldcg(p.gn_ws + ((long)cur_b * nslots + r) * 16 + lane);
+                if (g < p.gn_groups) p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which] = t;
             }
         };
         int it = 0;
@@ -789,8 +793,8 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     }
     const size_t data_bytes = q.halo ? (size_t)(q.b_stationary ? num_kb : q.stages_b) * b_tile + (size_t)q.stages * q.a_stage_bytes
                                      : (size_t)q.stages * stage_bytes;
-    plan->smem = data_bytes + 1024 /*align slack*/ + 2048 /*barriers, per-warp GroupNorm rows*/;
-    if (plan->smem > 222 * 1024) { free(plan); return FD_ERR_UNSUPPORTED; }
+    plan->smem = data_bytes + 1024 /*align slack*/ + 3072 /*barriers, per-warp GroupNorm rows (two parities)*/;
+    if (plan->smem > 223 * 1024) { free(plan); return FD_ERR_UNSUPPORTED; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -805,14 +809,14 @@ extern "C" int fd_conv2d_tc_run(const fd_gemm_plan* plan, cudaStream_t stream) {
     static bool attr_bf16 = false, attr_f16 = false;
     if (plan->q.p.dtype == FD_BF16) {
         if (!attr_bf16) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr_bf16 = true;
         }
         conv_tc_kernel<__nv_bfloat16><<<plan->grid, NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
     } else {
         if (!attr_f16) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr_f16 = true;
         }
