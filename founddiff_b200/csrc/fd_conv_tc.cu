@@ -475,9 +475,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         };
         // The block's sums of sample cur_b leave the block (all 16 epilogue warps call this; only the first one works).
         //   gn_ws given: stored into the slot of this block's residue class (tile index within the sample mod grid size) — the set
-        //   of tiles behind a slot and their order depend on the sample's geometry only; the block that completes the sample
-        //   (arrival counter, release / acquire through one fence on either side) adds the slots in index order and writes
-        //   gn_sums.  Reproducible bit for bit.
+        //   of tiles behind a slot and their order depend on the sample's geometry only; fd_conv2d_tc_run then launches a
+        //   32-thread-per-sample kernel that adds the slots in index order into gn_sums.  Reproducible bit for bit.  (A "last
+        //   block finishes" variant inside this kernel cost 30 - 200 % on the GroupNorm convolutions: the fence in front of the
+        //   arrival counter waits for the warp's own output stores.)
         //   no gn_ws: floating-point atomics straight into gn_sums (order = block timing).
         const int tps = total_tiles / p.B;             // tiles per sample
         const int nslots = (int)gridDim.x;
@@ -498,23 +499,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 return;
             }
             const int slot = ((int)blockIdx.x + nslots - (int)(((long)cur_b * tps) % nslots)) % nslots;
-            if (lane < 16) __stcg(p.gn_ws + ((long)cur_b * nslots + slot) * 16 + lane, tot);
-            __syncwarp();
-            int last = 0;
-            if (lane == 0) {
-                __threadfence();                                   // release: the 16 stores above (ordered by __syncwarp) before the arrival
-                int* counters = reinterpret_cast<int*>(p.gn_ws + (long)p.B * nslots * 16);
-                const int expected = tps < nslots ? tps : nslots;
-                last = atomicAdd(counters + cur_b, 1) == expected - 1;
-                if (last) __threadfence();                         // acquire: the other blocks' slots
-            }
-            last = __shfl_sync(0xffffffffu, last, 0);
-            __syncwarp();                                          // orders lane 0's acquire fence before the other lanes' loads
-            if (last && lane < 16) {
-                float t = 0.f;
-                for (int r = 0; r < nslots; ++r) t += __ldcg(p.gn_ws + ((long)cur_b * nslots + r) * 16 + lane);
-                if (g < p.gn_groups) p.gn_sums[((long)cur_b * p.gn_groups + g) * 2 + which] = t;
-            }
+            if (lane < 16) p.gn_ws[((long)cur_b * nslots + slot) * 16 + lane] = tot;
         };
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -612,6 +597,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
 }
 
+// gn_sums[b, g, which] = sum over the slots, in slot order (one warp per sample; slots of blocks that own no tile of the sample
+// hold the zeros the caller put there)
+__global__ void __launch_bounds__(32) gn_finalize_kernel(const float* __restrict__ ws, float* __restrict__ sums, int nslots, int groups) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (lane >= 16) return;
+    float t = 0.f;
+    for (int r = 0; r < nslots; ++r) t += ws[((long)b * nslots + r) * 16 + lane];
+    const int which = lane >> 3, g = lane & 7;
+    if (g < groups) sums[((long)b * groups + g) * 2 + which] = t;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -673,7 +669,7 @@ extern "C" long fd_conv_gn_ws_floats(int B) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;   // no device: the B200 count
-    return B > 0 ? (long)B * (sms * 16 + 1) : 0;
+    return B > 0 ? (long)B * sms * 16 : 0;
 }
 
 extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
@@ -823,6 +819,10 @@ extern "C" int fd_conv2d_tc_run(const fd_gemm_plan* plan, cudaStream_t stream) {
         conv_tc_kernel<__half><<<plan->grid, NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
     }
     FD_LAUNCH_CHECK();
+    if (plan->q.p.gn_sums && plan->q.p.gn_ws) {
+        gn_finalize_kernel<<<plan->q.p.B, 32, 0, stream>>>(plan->q.p.gn_ws, plan->q.p.gn_sums, (int)plan->grid.x, plan->q.p.gn_groups);
+        FD_LAUNCH_CHECK();
+    }
     return 0;
 }
 

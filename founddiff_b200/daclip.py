@@ -42,8 +42,11 @@ class DAClipEncoder:
         # by the 16-bit sampling modes: it perturbs the embeddings by ~6e-3 and the Unet output by ~1.6e-4 rel-L2
         # (measured with the oracle, DESIGN.md "Precision"), far below the 16-bit path's own rounding.
         self.conv_dtype = conv_dtype
-        self.sd = {k: v.detach().to(device=device, dtype=torch.float32 if v.is_floating_point() else v.dtype)
-                   for k, v in state_dict.items() if k.startswith(PREFIX)}
+        self.device = torch.device(device)
+        # BatchNorm folding, layout permutes and 16-bit conversion run on HOST copies (one upload per finished tensor)
+        self.sd_host = {k: v.detach().to("cpu", torch.float32) for k, v in state_dict.items()
+                        if k.startswith(PREFIX) and v.is_floating_point()}
+        self.sd = {k: v.to(self.device) for k, v in self.sd_host.items() if ".visual.attnpool." in k or ".head" in k}
         self.layers, self.heads = tuple(layers), heads
         # BatchNorm (eval) folded into the preceding bias-free convolution once, at load time
         self._folded = {}
@@ -53,11 +56,11 @@ class DAClipEncoder:
     def _conv_bn(self, x, conv, bn, stride=1, padding=0):
         key = conv
         if key not in self._folded:
-            sd = self.sd
+            sd = self.sd_host
             w = sd[conv + ".weight"]
             s = sd[bn + ".weight"] * torch.rsqrt(sd[bn + ".running_var"] + 1e-5)
-            wf = (w * s[:, None, None, None]).to(self.conv_dtype).contiguous(memory_format=torch.channels_last)
-            self._folded[key] = (wf, (sd[bn + ".bias"] - sd[bn + ".running_mean"] * s).to(self.conv_dtype).contiguous())
+            wf = (w * s[:, None, None, None]).to(self.conv_dtype).to(self.device).contiguous(memory_format=torch.channels_last)
+            self._folded[key] = (wf, (sd[bn + ".bias"] - sd[bn + ".running_mean"] * s).to(self.conv_dtype).contiguous().to(self.device))
         w, b = self._folded[key]
         return F.conv2d(x, w, b, stride=stride, padding=padding)
 
@@ -67,7 +70,7 @@ class DAClipEncoder:
         if stride > 1:
             out = F.avg_pool2d(out, stride)
         out = self._conv_bn(out, p + "conv3", p + "bn3")
-        if (p + "downsample.0.weight") in self.sd:
+        if (p + "downsample.0.weight") in self.sd_host:
             idt = F.avg_pool2d(x, stride) if stride > 1 else x
             idt = self._conv_bn(idt, p + "downsample.0", p + "downsample.1")
         else:
@@ -80,11 +83,11 @@ class DAClipEncoder:
         """BN-folded weight as (Cout, KH, KW, Cin) 16-bit + fp32 bias, the layout fd_conv_params takes."""
         key = "nhwc:" + conv
         if key not in self._folded:
-            sd = self.sd
+            sd = self.sd_host
             w = sd[conv + ".weight"]
             s = sd[bn + ".weight"] * torch.rsqrt(sd[bn + ".running_var"] + 1e-5)
-            wf = (w * s[:, None, None, None]).permute(0, 2, 3, 1).to(self.conv_dtype).contiguous()
-            self._folded[key] = (wf, (sd[bn + ".bias"] - sd[bn + ".running_mean"] * s).float().contiguous())
+            wf = (w * s[:, None, None, None]).permute(0, 2, 3, 1).to(self.conv_dtype).contiguous().to(self.device)
+            self._folded[key] = (wf, (sd[bn + ".bias"] - sd[bn + ".running_mean"] * s).float().contiguous().to(self.device))
         return self._folded[key]
 
     def _build_tower(self, B: int, H: int, W: int, dev):
@@ -115,7 +118,7 @@ class DAClipEncoder:
                     t2p = new(ho, wo, planes)
                     seq.append(lambda a=t2, o=t2p, hh=h, ww=w, c=planes: ops.avgpool2x2_nhwc(a, o, B, hh, ww, c))
                 idt = x
-                if (p + "downsample.0.weight") in self.sd:
+                if (p + "downsample.0.weight") in self.sd_host:
                     wd, bd = self._folded_nhwc(p + "downsample.0", p + "downsample.1")
                     src = x
                     if stride > 1:

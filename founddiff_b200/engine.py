@@ -39,9 +39,18 @@ def ws_fold(w: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     return (w - mean) * (var + eps).rsqrt()
 
 
+def upload(t: torch.Tensor, device, dtype=None) -> torch.Tensor:
+    """Host tensor -> device, converted and made contiguous ON THE HOST: weight packing launches no device kernel (one memcpy per
+    packed tensor), so an engine build is a few hundred copies instead of ~1000 elementwise launches."""
+    t = t.detach()
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous().to(device)
+
+
 def pack_conv(w: torch.Tensor, dtype, device) -> torch.Tensor:
-    """(Cout, Cin, KH, KW) -> (Cout, KH, KW, Cin) contiguous in the activation dtype."""
-    return w.float().permute(0, 2, 3, 1).contiguous().to(device=device, dtype=dtype)
+    """(Cout, Cin, KH, KW) -> (Cout, KH, KW, Cin) contiguous in the activation dtype (packed on the host)."""
+    return upload(w.detach().float().cpu().permute(0, 2, 3, 1), device, dtype)
 
 
 class UnetEngine:
@@ -59,7 +68,10 @@ class UnetEngine:
             raise ValueError("fp32 storage does not mix with 16-bit storage")
         self.prefer_tc = prefer_tc
         self._bufs: Dict[str, torch.Tensor] = {}
-        f32 = lambda k: sd[k].detach().to(device=self.device, dtype=torch.float32).contiguous()  # noqa: E731
+        # every weight transformation below (fp32 casts, weight standardisation, permutes, concatenations, -exp(A_logs), 16-bit
+        # conversion, zero padding) runs on HOST copies; the device only ever receives finished tensors
+        sd = {k: v.detach().to("cpu", torch.float32) for k, v in sd.items() if v.is_floating_point()}
+        f32 = lambda k: upload(sd[k], self.device)  # noqa: E731
         self.f32 = f32
         self.sd = sd
         d, td = cfg.dim, cfg.time_dim
@@ -74,9 +86,9 @@ class UnetEngine:
         self.pm_w, self.pm_b = f32("prompt_mlp.weight"), f32("prompt_mlp.bias")
         blocks = cfg.mamba_blocks()
         self.mod_total = sum(6 * C for _, C, _ in blocks)
-        self.adaln_w = torch.cat([f32(f"{p}.adaLN_modulation.1.weight") for p, _, _ in blocks], dim=0).contiguous()
-        self.adaln_b = torch.cat([f32(f"{p}.adaLN_modulation.1.bias") for p, _, _ in blocks], dim=0).contiguous()
-        self.local_w = torch.cat([f32(f"{p}.mamba.attn.0.weight") for p, _, _ in blocks], dim=0).contiguous()
+        self.adaln_w = upload(torch.cat([sd[f"{p}.adaLN_modulation.1.weight"] for p, _, _ in blocks], dim=0), self.device)
+        self.adaln_b = upload(torch.cat([sd[f"{p}.adaLN_modulation.1.bias"] for p, _, _ in blocks], dim=0), self.device)
+        self.local_w = upload(torch.cat([sd[f"{p}.mamba.attn.0.weight"] for p, _, _ in blocks], dim=0), self.device)
         self.local_total = sum(2 * C for _, C, _ in blocks)
 
         # ---- per-step conditioning buffers ---------------------------------------------------------------
@@ -173,18 +185,23 @@ class UnetEngine:
 
         # init conv (fp32 images -> level-0 trunk); `r = x.clone()` (src/DADiff.py:701) lives in its own buffer R
         self.init_w, self.init_b = f32("init_conv.weight"), f32("init_conv.bias")
+        init_w_host = sd["init_conv.weight"]
         self.x_t = torch.zeros(B, H * W, device=dev, dtype=torch.float32)
         self.x_input = torch.zeros(B, H * W, device=dev, dtype=torch.float32)
         R = self.buf("R", B, H * W, d)
         if R.dtype != torch.float32 and d == 64 and H % 8 == 0 and W % 16 == 0 and self.prefer_tc:
-            self.init_w16 = ops.pack_init_conv_weights(self.init_w)
+            self.init_w16 = upload(ops.pack_init_conv_weights(init_w_host), dev)
             self.steps.append(lambda: ops.init_conv7x7_tc(self.x_t, self.x_input, self.init_w16, self.init_b, R, B, H, W))
         else:
             self.steps.append(lambda: ops.init_conv7x7(self.x_t, self.x_input, self.init_w, self.init_b, R, B, H, W))
 
         def conv_plain(key_w, key_b, src, dst, h, w, k, stride=1, upsample=False):
-            c = ops.Conv(src, pack_conv(sd[key_w], self.trunk_dtype, dev), dst, B=B, Hin=h, Win=w, KH=k, KW=k, stride=stride,
-                         pad=1, upsample=upsample, bias=f32(key_b), prefer_tc=self.prefer_tc)
+            w_host = sd[key_w].permute(0, 2, 3, 1).contiguous()                   # (Cout, KH, KW, Cin)
+            up4 = None
+            if upsample and self.prefer_tc and dst.dtype != torch.float32:        # phase-summed 2x2 kernels, packed on the host
+                up4 = upload(ops.pack_upsample_phases(w_host.to(self.trunk_dtype), w_host.shape[0], w_host.shape[-1]), dev)
+            c = ops.Conv(src, upload(w_host, dev, self.trunk_dtype), dst, B=B, Hin=h, Win=w, KH=k, KW=k, stride=stride,
+                         pad=1, upsample=upsample, bias=f32(key_b), prefer_tc=self.prefer_tc, weight_up4=up4)
             self.steps.append(c.run)
 
         cur = R
@@ -226,7 +243,7 @@ class UnetEngine:
         h, w = sizes[0]
         self.feat = self.buf("TB0", B, h * w, d)
         self._resblock("final_res_block", 0, [cur, R], self.feat, d, h, w)         # :733-735
-        self.final_w = f32("final_conv.weight").reshape(-1).contiguous()
+        self.final_w = upload(sd["final_conv.weight"].reshape(-1), dev)
         self.final_b = f32("final_conv.bias")
 
     # -------------------------------------------------------------------------------------------------------
@@ -295,24 +312,27 @@ class UnetEngine:
         qkv = self.buf(f"QKV{l}", B, P, 3 * C)
         v = self.buf(f"V{l}", B, P, C)
         weff = self.buf(f"WEFF{l}", B, C, C)
-        to_dt = lambda t: t.detach().to(device=dev, dtype=dt).contiguous()  # noqa: E731
-        to_tdt = lambda t: t.detach().to(device=dev, dtype=self.trunk_dtype).contiguous()  # noqa: E731  (operands of convs reading `a`)
+        to_dt = lambda t: upload(t, dev, dt)  # noqa: E731
+        to_tdt = lambda t: upload(t, dev, self.trunk_dtype)  # noqa: E731  (operands of convs reading `a`)
         in_w = to_tdt(sd[p + ".mamba.in_proj.weight"])                                                 # (4C, C)
         out_w = to_dt(sd[p + ".mamba.out_proj.weight"])                                                # (C, 2C)
-        dw_w, dw_b = f32(p + ".mamba.conv2d.weight").reshape(D, 9).contiguous(), f32(p + ".mamba.conv2d.bias")
+        dw_host = sd[p + ".mamba.conv2d.weight"].reshape(D, 9)
+        dw_w, dw_b = upload(dw_host, dev), f32(p + ".mamba.conv2d.bias")
         xp_w, dtp_w = f32(p + ".mamba.x_proj_weight"), f32(p + ".mamba.dt_projs_weight")
         use_xdt_tc = dt != torch.float32 and R <= 32 and R + 2 * N <= 96
         if use_xdt_tc:
-            xw16, dw16, Rp = ops.pack_xdt_weights(xp_w, dtp_w, dt)
-        dt_bias = f32(p + ".mamba.dt_projs_bias").reshape(-1).contiguous()
-        A_neg = (-torch.exp(f32(p + ".mamba.A_logs"))).contiguous()                                   # emamba2.py:344
+            xw16, dw16, Rp = ops.pack_xdt_weights(sd[p + ".mamba.x_proj_weight"], sd[p + ".mamba.dt_projs_weight"], dt)
+            xw16, dw16 = upload(xw16, dev), upload(dw16, dev)
+        dt_bias = upload(sd[p + ".mamba.dt_projs_bias"].reshape(-1), dev)
+        A_neg = upload(-torch.exp(sd[p + ".mamba.A_logs"]), dev)                                      # emamba2.py:344
         Ds = f32(p + ".mamba.Ds")
         on_w, on_b = f32(p + ".mamba.out_norm.weight"), f32(p + ".mamba.out_norm.bias")
         qkv_w = to_tdt(sd[p + ".attn_blk.qkv.weight"].reshape(3 * C, C))
-        qdw_w = f32(p + ".attn_blk.qkv_dwconv.weight").reshape(3 * C, 9).contiguous()
-        qdw_wt = qdw_w.t().contiguous()                      # tap-major copy for the streaming dwconv kernel
-        proj_w = f32(p + ".attn_blk.project_out.weight").reshape(C, C).contiguous()
-        temp = f32(p + ".attn_blk.temperature").reshape(-1).contiguous()
+        qdw_host = sd[p + ".attn_blk.qkv_dwconv.weight"].reshape(3 * C, 9)
+        qdw_w = upload(qdw_host, dev)
+        qdw_wt = upload(qdw_host.t(), dev)                   # tap-major copy for the streaming dwconv kernel
+        proj_w = upload(sd[p + ".attn_blk.project_out.weight"].reshape(C, C), dev)
+        temp = upload(sd[p + ".attn_blk.temperature"].reshape(-1), dev)
         acc_g = self._acc(B * heads * 32 * 32)
         acc_q = self._acc(B * 2 * C)
         acc_gw = self._acc(ops.gram_ws_floats(B, h, w, C, dt))      # per-chunk Gram records + arrival counters (zeroed per forward)
@@ -349,16 +369,16 @@ class UnetEngine:
                 use_tm = False
         if use_tm:
             scan_cl = fuse_dt = False
-            dw_wt = dw_w.t().contiguous()                                  # tap-major (9, D)
+            dw_wt = upload(dw_host.t(), dev)                               # tap-major (9, D)
             xs_tm, dts_tm = xs.view(B, 4, L, D), dts.view(B, 4, L, D)
             XR = (R + 2 * N) if tm_fuse else 2 * N
             xdbl_tm = self.buf(f"XDBLTM.{p}", B, 4, L, XR, dtype=torch.float32)
             S_tm = ops.scan_tm_plan(B, D, h, w, N, R if tm_fuse else 0)      # > 0 segments | -8 / -4 time-sliced kernel
             carry = self.buf(f"CARRY.{p}", B * 4 * max(S_tm, 1) * 2 * N * D, dtype=torch.float32)
-            dtw_tm = dtp_w.reshape(4 * D, R).contiguous()
+            dtw_tm = upload(sd[p + ".mamba.dt_projs_weight"].reshape(4 * D, R), dev)
         if fuse_dt:
             xdbl = self.buf(f"XDBL{l}", B, 4, R + 2 * N, L, dtype=torch.float32)
-            dtw_flat = dtp_w.reshape(4 * D, R).contiguous()
+            dtw_flat = upload(sd[p + ".mamba.dt_projs_weight"].reshape(4 * D, R), dev)
         split_attn = dt != torch.float32            # 16-bit modes: streaming dwconv + tensor-core Gram, v read in place
         if split_attn:
             qkv2 = self.buf(f"QKV2{l}", B, P, 3 * C)

@@ -140,7 +140,7 @@ class Conv:
 
     def __init__(self, src0, weight, out, *, B, Hin, Win, KH=1, KW=1, stride=1, pad=0, upsample=False, src1=None,
                  bias=None, gate=None, gate_stride=0, addend=None, silu_from=None, gn_sums=None, gn_groups=0,
-                 per_batch_weight=False, prefer_tc=True, c0=None, ld0=0, relu_out=False, gn_ws=None):
+                 per_batch_weight=False, prefer_tc=True, c0=None, ld0=0, relu_out=False, gn_ws=None, weight_up4=None):
         """`c0` / `ld0`: read only the first c0 channels of rows of pitch ld0 starting at src0's data pointer (src0 may
         be a strided channel-slice view).
         `gn_sums` (B, G, 2): GroupNorm statistics of the output.  With `gn_ws` (zeroed before every run: conv_gn_ws_floats(B) for
@@ -160,9 +160,10 @@ class Conv:
         p.c0, p.c1, p.B, p.Hin, p.Win, p.Cout = c0, c1, B, Hin, Win, cout
         p.ld0 = ld0
         p.KH, p.KW, p.stride, p.pad, p.upsample = KH, KW, stride, pad, int(upsample)
-        self._w4 = None
+        self._w4 = weight_up4                    # (4, Cout, 2, 2, Cin) phase-summed kernels; packed here unless the caller did (on the host)
         if upsample and prefer_tc and out.dtype != torch.float32:
-            self._w4 = pack_upsample_phases(weight, cout, c0 + c1)
+            if self._w4 is None:
+                self._w4 = pack_upsample_phases(weight, cout, c0 + c1)
             p.weight_up4 = _p(self._w4)
         p.silu_from = cout if silu_from is None else silu_from
         p.gate_stride, p.gn_groups, p.per_batch_weight = gate_stride, gn_groups, int(per_batch_weight)
@@ -204,7 +205,8 @@ class Conv:
         return 2.0 * p.B * ho * wo * p.Cout * p.KH * p.KW * (p.c0 + p.c1)
 
     def run(self):
-        with _launched("conv_tc" if self.uses_tc else "conv_simt", self.describe()):
+        with _launched("conv_tc" if self.uses_tc else "conv_simt", self.describe(),
+                       2 if (self.uses_tc and self.params.gn_sums and self.params.gn_ws) else 1):
             if self.uses_tc:
                 check(self._lib.fd_conv2d_tc_run(self._plan, _stream()), "fd_conv2d_tc_run")
             else:

@@ -85,7 +85,7 @@ int fd_selective_scan_fwd_merge_cl(const void* u, const void* delta, const float
  * GroupNorm statistics are REPRODUCIBLE when `gn_ws` is given (tcgen05 path): every thread block stores the partial sums of the
  * tiles it owns of a sample into its own slot — the slot is the residue class of the sample's tile index modulo the (fixed)
  * grid size, so the grouping and the order of additions depend on the sample only, not on the batch it sits in or on block
- * timing — and the last block to finish a sample adds the slots in index order.  Without gn_ws the sums are accumulated with
+ * timing — and a second, tiny launch adds the slots in index order.  Without gn_ws the sums are accumulated with
  * floating-point atomics (gn_sums must then be zero on entry, and the last bits depend on the block schedule).
  * `in` is the channel concatenation of src0 (c0 channels) and src1 (c1 channels, may be NULL/0).
  * weight: (Cout, KH, KW, c0+c1) in `dtype`, or (B, Cout, KH, KW, c0+c1) when per_batch_weight.
@@ -100,7 +100,7 @@ typedef struct {
     void* out;
     float* gn_sums;
     const void* weight_up4; /* upsample only (tcgen05 path): (4, Cout, 2, 2, c0) phase-summed weights, see fd_conv_tc.cu */
-    float* gn_ws;         /* optional: fd_conv_gn_ws_floats(B) floats, ZERO on entry (slots + per-sample arrival counters) */
+    float* gn_ws;         /* optional: fd_conv_gn_ws_floats(B) floats, ZERO on entry (one 16-float slot per sample and thread block) */
     int c0, c1;
     int ld0;              /* row pitch (elements) of src0; 0 = dense (c0).  Lets a GEMM read a channel slice of a wider tensor */
     int B, Hin, Win, Cout;
