@@ -307,19 +307,16 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert k in d
 
 
-def test_odd_deep_level_refused_in_16_bit():
-    """48x80 -> deepest level 3x5: scan length 15.  16-bit storage refuses it loudly before any kernel runs (a misaligned store in
-    the 16-bit x_proj kernel was found on this case; the fix is in, the geometry stays refused until re-validated on a GPU)."""
+def test_geometry_check():
+    """H, W must be multiples of 16 (three 2x downsamplings + the stride-2 scan sub-grids); odd deepest-level scan lengths
+    (48x80 -> 3x5) are accepted in every storage mode since round 2 (validated under compute-sanitizer, GPU test
+    test_ragged_geometry_vs_reference)."""
     from founddiff_b200.engine import UnetEngine
-    for dt in (torch.bfloat16, torch.float16):
-        with pytest.raises(NotImplementedError):
-            UnetEngine.check_geometry(48, 80, dt)
-        UnetEngine.check_geometry(64, 96, dt)
-        UnetEngine.check_geometry(32, 48, dt)
-        UnetEngine.check_geometry(512, 512, dt)
-    UnetEngine.check_geometry(48, 80, torch.float32)
-    with pytest.raises(ValueError):
-        UnetEngine.check_geometry(40, 80, torch.float32)
+    for dt in (torch.bfloat16, torch.float16, torch.float32):
+        for hw in ((48, 80), (64, 96), (32, 48), (512, 512)):
+            UnetEngine.check_geometry(*hw, dt)
+        with pytest.raises(ValueError):
+            UnetEngine.check_geometry(40, 80, dt)
 
 
 def test_c_abi_header_is_plain_c_and_links_from_c(tmp_path):

@@ -295,12 +295,12 @@ def test_evaluate_loop_npy_in_metrics_on_device_npy_out(model, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dt", [torch.float32])
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
 def test_ragged_geometry_vs_reference(model, dt):
     """48x80 slices: level maps 24x40 / 12x20 / 6x10 and scan lengths 960 / 240 / 60 / 15 do not tile evenly, so the kernels run
     the tails of their general paths; same gates as the even sizes.  Fixture from the unmodified reference:
-    tests/golden/unet_48x80.npz (oracle/gen_golden_ragged.py).  fp32 storage only: the 16-bit modes REFUSE this geometry (odd
-    deepest-level scan length, see UnetEngine.check_geometry and tests/test_cpu_host.py::test_odd_deep_level_refused_in_16_bit)."""
+    tests/golden/unet_48x80.npz (oracle/gen_golden_ragged.py).  All storage modes: the odd deepest-level scan length (15) that
+    the 16-bit modes refused in round 1 was validated under compute-sanitizer in round 2 (tools/sanitize.sh)."""
     g = load_golden("unet_48x80.npz")
     set_mode(model, dt, sampling_timesteps=2)
     time = g["time"].cuda()
