@@ -39,7 +39,9 @@ constexpr int BK = 64;           // K block = one 128-byte swizzle atom of 16-bi
 constexpr int UMMA_K = 16;
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_EPI_WARPS = 16;
-constexpr int NTHREADS = (2 + NUM_EPI_WARPS) * 32;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, 16 epilogue warps
+constexpr int NUM_STAT_WARPS = 2;                     // LayerNorm row statistics of the staged A tile (ln_u != NULL), 2 rows per lane
+constexpr int NTHREADS = (2 + NUM_EPI_WARPS + NUM_STAT_WARPS) * 32;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner,
+                                                      // 16 epilogue warps, 2 statistics warps
 
 // n / d for 0 <= n with n * d < 2^32 as one multiply-high (host-precomputed ceil(2^32 / d); d == 1 handled apart)
 struct FastDiv {
@@ -273,19 +275,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint64_t* wfull_bar = bempty_bar + MAX_STAGES;    // halo mode, stationary weights: all tiles landed
     uint64_t* tfull_bar = wfull_bar + 1;              // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator drained
-    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    uint64_t* sfull_bar = tempty_bar + 2;             // [2] LayerNorm row statistics of the tile written (ln fold)
+    uint32_t* tmem_slot = (uint32_t*)(sfull_bar + 2);
     float* s_gn = (float*)(tmem_slot + 2);            // [2 flush parities][16 epilogue warps][2][8] GroupNorm partial sums
+    float2* s_ln = (float2*)(s_gn + 2 * NUM_EPI_WARPS * 16);   // [2 accumulator buffers][128 rows] (mean, rstd) of the input rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fd_conv_params& p = q.p;
+    const bool ln_fold = p.ln_u != nullptr;           // LayerNorm of the input rows folded into this GEMM (box mode, 1x1)
     const int total_tiles = q.total_tiles;
     const uint32_t tmem_cols = 2 * BN <= 128 ? 128u : 2 * BN <= 256 ? 256u : 512u;       // two accumulators, power-of-two allocation
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        // with the LayerNorm fold a stage is released by the MMA commit AND by the statistics warps that read its A tile
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ln_fold ? 1 + NUM_STAT_WARPS : 1); }
         for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
         mbar_init(wfull_bar, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], NUM_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], NUM_EPI_WARPS); mbar_init(&sfull_bar[s], NUM_STAT_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 2 * NUM_EPI_WARPS * 16) s_gn[threadIdx.x] = 0.f;
@@ -435,6 +441,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 __syncwarp();
             }
         }
+    } else if (warp >= 2 + NUM_EPI_WARPS) {
+        // ================================ LayerNorm row statistics (ln fold): 2 warps ================================
+        // mean / rstd over the c0 input channels of each of the tile's 128 pixels, read from the SAME staged A tiles the MMA
+        // consumes (no extra global traffic, no separate normalisation pass).  A row of a K block is 128 bytes = 8 swizzled
+        // 16-byte chunks; sums do not care about the chunk order, so lane r reads chunk (j + r) & 7 at step j: the eight
+        // rows a quarter-warp touches per LDS.128 phase hit eight different bank groups.
+        if (ln_fold) {
+            const int r0 = (warp - 2 - NUM_EPI_WARPS) * 64 + lane, r1 = r0 + 32;
+            const float inv_c = 1.f / (float)p.c0;
+            int stage = 0, it = 0;
+            uint32_t ph = 0;
+            auto acc8 = [&](const uint4& v, float& sum, float& sq) {
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 f;
+                    if (q.fmt) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                    else f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                    sum += f.x; sq = fmaf(f.x, f.x, sq);
+                    sum += f.y; sq = fmaf(f.y, f.y, sq);
+                }
+            };
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                float sa0 = 0.f, qa0 = 0.f, sa1 = 0.f, qa1 = 0.f;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], ph);
+                    const uint8_t* sa = smem + (size_t)stage * stage_bytes;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 va = *reinterpret_cast<const uint4*>(sa + r0 * 128 + (((j + r0) & 7) << 4));
+                        const uint4 vb = *reinterpret_cast<const uint4*>(sa + r1 * 128 + (((j + r1) & 7) << 4));
+                        acc8(va, sa0, qa0);
+                        acc8(vb, sa1, qa1);
+                    }
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[stage])) : "memory");
+                    if (++stage == stages) { stage = 0; ph ^= 1; }
+                }
+                mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);     // the epilogue has read the statistics of tile it - 2
+                const float m0 = sa0 * inv_c, m1 = sa1 * inv_c;
+                s_ln[buf * BM + r0] = make_float2(m0, rsqrtf(fmaxf(qa0 * inv_c - m0 * m0, 0.f) + p.ln_eps));
+                s_ln[buf * BM + r1] = make_float2(m1, rsqrtf(fmaxf(qa1 * inv_c - m1 * m1, 0.f) + p.ln_eps));
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sfull_bar[buf])) : "memory");
+            }
+        }
     } else {
         // ================================ epilogue: 16 warps ================================
         const int q4 = warp & 3;                       // TMEM lane quarter this warp may access
@@ -524,6 +577,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (use_add) load16_raw(addend + orow + n0 + cg * 16, araw);
             mbar_wait_long(&tfull_bar[buf], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float ln_mean = 0.f, ln_rstd = 1.f;
+            if (ln_fold) {                             // statistics of this thread's pixel (written by the statistics warps)
+                mbar_wait(&sfull_bar[buf], (it >> 1) & 1);
+                const float2 st = s_ln[buf * BM + m];
+                ln_mean = st.x;
+                ln_rstd = st.y;
+            }
             const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q4 * 32) << 16);
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
@@ -543,6 +603,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 const int n = n0 + c;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                if (ln_fold) {                         // W LN(x) = rstd (W' x - mean u) + v   (fd_ln_fold made W', u, v)
+                    const float* up = p.ln_u + (long)b * p.Cout + n;
+                    const float* vp = p.ln_v + (long)b * p.Cout + n;
+                    const float nm = -ln_mean;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 uu = __ldg(reinterpret_cast<const float4*>(up + j));
+                        const float4 vv = __ldg(reinterpret_cast<const float4*>(vp + j));
+                        v[j] = fmaf(ln_rstd, fmaf(nm, uu.x, v[j]), vv.x);
+                        v[j + 1] = fmaf(ln_rstd, fmaf(nm, uu.y, v[j + 1]), vv.y);
+                        v[j + 2] = fmaf(ln_rstd, fmaf(nm, uu.z, v[j + 2]), vv.z);
+                        v[j + 3] = fmaf(ln_rstd, fmaf(nm, uu.w, v[j + 3]), vv.w);
+                    }
+                }
                 if (p.bias) {                          // warp-uniform branches, 16-byte parameter loads
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -694,6 +768,10 @@ extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
         const int cpg = p->Cout / p->gn_groups;
         if (cpg < 8 || cpg % 8 || (cpg & (cpg - 1)) || p->gn_groups > 8) return 0;
     }
+    if (p->ln_u || p->ln_v) {     // LayerNorm fold: plain 1x1 GEMM over one input tensor (box mode), 16-byte aligned vectors
+        if (!p->ln_u || !p->ln_v || p->KH != 1 || p->KW != 1 || p->stride != 1 || p->pad != 0 || p->upsample || p->c1) return 0;
+        if (((uintptr_t)p->ln_u | (uintptr_t)p->ln_v) & 15 || p->Cout % 4) return 0;
+    }
     const uintptr_t al = (uintptr_t)p->src0 | (uintptr_t)p->src1 | (uintptr_t)p->weight | (uintptr_t)p->out |
                          (uintptr_t)p->addend | (uintptr_t)p->weight_up4;
     if (al & 15) return 0;
@@ -789,8 +867,8 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     }
     const size_t data_bytes = q.halo ? (size_t)(q.b_stationary ? num_kb : q.stages_b) * b_tile + (size_t)q.stages * q.a_stage_bytes
                                      : (size_t)q.stages * stage_bytes;
-    plan->smem = data_bytes + 1024 /*align slack*/ + 3072 /*barriers, per-warp GroupNorm rows (two parities)*/;
-    if (plan->smem > 223 * 1024) { free(plan); return FD_ERR_UNSUPPORTED; }
+    plan->smem = data_bytes + 1024 /*align slack*/ + 5120 /*barriers, per-warp GroupNorm rows (two parities), LayerNorm row statistics*/;
+    if (plan->smem > 225 * 1024) { free(plan); return FD_ERR_UNSUPPORTED; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -805,14 +883,14 @@ extern "C" int fd_conv2d_tc_run(const fd_gemm_plan* plan, cudaStream_t stream) {
     static bool attr_bf16 = false, attr_f16 = false;
     if (plan->q.p.dtype == FD_BF16) {
         if (!attr_bf16) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr_bf16 = true;
         }
         conv_tc_kernel<__nv_bfloat16><<<plan->grid, NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
     } else {
         if (!attr_f16) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr_f16 = true;
         }

@@ -333,9 +333,43 @@ class UnetEngine:
         acc_gw = self._acc(ops.gram_ws_floats(B, h, w, C, dt))      # per-chunk Gram records + arrival counters (zeroed per forward)
         tc = self.prefer_tc
         holder = {}
-        c_in = ops.Conv(a, in_w, xz, B=B, Hin=h, Win=w, silu_from=2 * C, prefer_tc=tc)
+        # LayerNorm + adaLN modulate folded into the 1x1 GEMM that reads it (fd_ln_fold + the statistics warps of conv_tc): the
+        # GEMM reads the residual stream itself, the `a` tensor and both ln_modulate passes disappear.  The folded weights are
+        # per sample and per step (B x Cout x C), so the fold only pays where a level has many more pixels than output channels.
+        use_fold = (dt != torch.float32 and tc and P >= 8 * 4 * C and os.environ.get("FD_LN_FOLD", "1") == "1")
+        c_in = c_qkv = None
+        if use_fold:
+            tdt = self.trunk_dtype
+            in_w32 = upload(sd[p + ".mamba.in_proj.weight"], dev)
+            qkv_w32 = upload(sd[p + ".attn_blk.qkv.weight"].reshape(3 * C, C), dev)
+            wf_in = self.buf(f"WFIN.{p}", B, 4 * C, C, dtype=tdt)
+            wf_qkv = self.buf(f"WFQKV.{p}", B, 3 * C, C, dtype=tdt)
+            u_in, v_in = (torch.zeros(B, 4 * C, device=dev, dtype=torch.float32) for _ in range(2))
+            u_q, v_q = (torch.zeros(B, 3 * C, device=dev, dtype=torch.float32) for _ in range(2))
+            try:
+                c_in = ops.Conv(x_in, wf_in, xz, B=B, Hin=h, Win=w, silu_from=2 * C, per_batch_weight=True, prefer_tc=True,
+                                ln_u=u_in, ln_v=v_in, ln_eps=1e-5)
+                c_qkv = ops.Conv(x, wf_qkv, qkv, B=B, Hin=h, Win=w, per_batch_weight=True, prefer_tc=True, ln_u=u_q, ln_v=v_q, ln_eps=1e-6)
+            except Exception:                           # geometry does not tile for the tensor-core kernel: separate passes
+                use_fold = False
+        if not use_fold:
+            c_in = ops.Conv(a, in_w, xz, B=B, Hin=h, Win=w, silu_from=2 * C, prefer_tc=tc)
+            c_qkv = ops.Conv(a, qkv_w, qkv, B=B, Hin=h, Win=w, prefer_tc=tc)
         c_out = ops.Conv(g, out_w, x, B=B, Hin=h, Win=w, gate=g1, gate_stride=MS, addend=x_in, prefer_tc=tc)
-        c_qkv = ops.Conv(a, qkv_w, qkv, B=B, Hin=h, Win=w, prefer_tc=tc)
+
+        def ln1_in_proj():
+            if use_fold:
+                ops.ln_fold(in_w32, n1w, n1b, sh1, sc1, MS, wf_in, u_in, v_in, B, 4 * C, C)
+            else:
+                ops.ln_modulate(x_in, a, n1w, n1b, sh1, sc1, MS, B, P, C, 1e-5)
+            c_in.run()
+
+        def ln2_qkv():
+            if use_fold:
+                ops.ln_fold(qkv_w32, None, None, sh2, sc2, MS, wf_qkv, u_q, v_q, B, 3 * C, C)
+            else:
+                ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
+            c_qkv.run()
         # fused scan+merge needs 16-bit io, 16/32-byte aligned rows (L % 8 == 0) and d_state in {4, 8, 16, 32}
         fuse_merge = dt != torch.float32 and L % 8 == 0 and N in (4, 8, 16, 32) and D % 8 == 0
         # levels with a small dt_rank: x_proj alone, dt_proj applied inside the scan (no (B, 4D, L) delta tensor at all)
@@ -393,13 +427,12 @@ class UnetEngine:
         self._acc_users.append(bind)
 
         self.paths[p] = ((f"time-major scan, {S_tm} segment(s)" if S_tm > 0 else f"time-major scan, time-sliced x{-S_tm}")
-                         + (", dt_proj fused" if tm_fuse else "") if use_tm else
+                         + (", dt_proj fused" if tm_fuse else "") + (", LayerNorm folded into in_proj / qkv" if use_fold else "") if use_tm else
                          "scan_cl time-major B/C" if scan_cl else "dt-fused warp scan" if fuse_dt else
                          "warp scan + merge" if fuse_merge else "reference-layout" if dt == torch.float32 else "warp scan, unfused merge")
 
         def run():
-            ops.ln_modulate(x_in, a, n1w, n1b, sh1, sc1, MS, B, P, C, 1e-5)
-            c_in.run()
+            ln1_in_proj()
             if use_tm:
                 ops.dwconv3x3_silu_tm(xz, 4 * C, dw_wt, dw_b, xs_tm, B, h, w, D)
                 if tm_fuse:
@@ -410,8 +443,7 @@ class UnetEngine:
                     ops.selective_scan_tm(xs_tm, dts_tm, xdbl_tm, A_neg, None, None, Ds, carry, ys.view(B, P, D), B, D, h, w, N, 0, S_tm)
                 ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
                 c_out.run()
-                ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
-                c_qkv.run()
+                ln2_qkv()
                 ops.dwconv3x3_nhwc(qkv, qdw_wt, None, qkv2, B, h, w, 3 * C)
                 ops.gram_qk(qkv2, 3 * C, holder["gram"], holder["qk"], B, P, C, ws=holder["gws"])
                 ops.attn_weff(holder["gram"], holder["qk"], temp, proj_w, weff, B, C)
@@ -444,8 +476,7 @@ class UnetEngine:
                                        out=ys.view(B, 4 * D, L))
                 ops.merge_ln_gate(ys, xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), stat, g, B, h, w, D)
             c_out.run()
-            ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
-            c_qkv.run()
+            ln2_qkv()
             if split_attn:
                 ops.dwconv3x3_nhwc(qkv, qdw_wt, None, qkv2, B, h, w, 3 * C)
                 ops.gram_qk(qkv2, 3 * C, holder["gram"], holder["qk"], B, P, C, ws=holder["gws"])

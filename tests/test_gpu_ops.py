@@ -856,3 +856,51 @@ def test_device_metrics_vs_reference_util_fixture(ops):
             assert abs(float(ss[i]) - float(g[f"{tag}.{i}.ssim"])) < 2e-5, tag
             assert abs(float(ps[i]) - float(g[f"{tag}.{i}.psnr"])) < 1e-3, tag
             assert abs(float(rs[i]) - float(g[f"{tag}.{i}.rmse"])) < 1e-6, tag
+
+
+@pytest.mark.parametrize("cfg", [(16, 32, 64, 256, True, 128), (16, 16, 128, 384, False, None), (8, 32, 256, 1024, True, 512), (24, 48, 64, 192, False, None),
+                                 (16, 16, 512, 2048, True, 1024)])
+@pytest.mark.parametrize("types", [(torch.float16, torch.bfloat16), (torch.bfloat16, torch.bfloat16), (torch.float16, torch.float16)])
+def test_layernorm_folded_into_1x1_gemm(ops, cfg, types):
+    """LayerNorm (+ affine) + adaLN modulate + 1x1 projection (src/DADiff.py:486-487 -> src/emamba2.py:717 in_proj with SiLU on the
+    z half, src/DADiff.py:258 qkv) as ONE tcgen05 GEMM on the raw residual stream: fd_ln_fold makes the per-sample weights, the
+    kernel's statistics warps take mean / rstd from the staged operand tile.  Against torch: F.layer_norm -> modulate -> F.linear."""
+    H, W, C, Cout, affine, silu_from = cfg
+    in_dt, out_dt = types
+    B, P = 3, H * W
+    g = torch.Generator().manual_seed(C + Cout)
+    x = q(torch.randn(B, P, C, generator=g) * 1.5 + 0.7, in_dt)                       # non-zero mean: the mean term must cancel
+    Wt = torch.randn(Cout, C, generator=g) / math.sqrt(C)
+    gamma = 1 + 0.2 * torch.randn(C, generator=g) if affine else None
+    beta = 0.2 * torch.randn(C, generator=g) if affine else None
+    mods = torch.randn(B, 2 * C + 5, generator=g) * 0.3                                # strided modulation rows, as in the engine
+    shift, scale = mods[:, :C], mods[:, C:2 * C]
+    eps = 1e-5 if affine else 1e-6
+    xn = F.layer_norm(x, (C,), gamma, beta, eps) * (1 + scale[:, None]) + shift[:, None]
+    ref = torch.einsum("bpc,oc->bpo", xn, Wt)
+    if silu_from is not None:
+        ref = torch.cat([ref[..., :silu_from], F.silu(ref[..., silu_from:])], dim=-1)
+
+    class V:                                    # strided fp32 view handed over as (pointer, row stride), like engine._view_ptr
+        def __init__(self, t):
+            self.t, self.dtype, self.is_cuda = t, torch.float32, True
+
+        def is_contiguous(self):
+            return True
+
+        def data_ptr(self):
+            return self.t.data_ptr()
+    md = mods.cuda()
+    wf = torch.empty(B, Cout, C, device="cuda", dtype=in_dt)
+    u, v = torch.empty(B, Cout, device="cuda"), torch.empty(B, Cout, device="cuda")
+    ops.ln_fold(Wt.cuda(), gamma.cuda() if affine else None, beta.cuda() if affine else None, V(md[:, :C]), V(md[:, C:2 * C]),
+                mods.shape[1], wf, u, v, B, Cout, C)
+    out = torch.full((B, P, Cout), float("nan"), device="cuda", dtype=out_dt)
+    conv = ops.Conv(x.to("cuda", in_dt), wf, out, B=B, Hin=H, Win=W, per_batch_weight=True, ln_u=u, ln_v=v, ln_eps=eps,
+                    silu_from=silu_from)
+    assert conv.uses_tc
+    conv.run()
+    conv.run()                                  # second run: barrier phases / buffers are reusable
+    r = rel(out, ref)
+    print(f"ln-folded 1x1 {cfg} {types}: rel-L2 {r:.3e}")
+    assert torch.isfinite(out.float()).all() and r < TOL[out_dt] * (1.5 if in_dt == torch.bfloat16 else 1.0), r
