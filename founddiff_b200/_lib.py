@@ -26,7 +26,7 @@ class ConvParams(Structure):
     _fields_ = [
         ("src0", c_void_p), ("src1", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("gate", c_void_p),
         ("addend", c_void_p), ("out", c_void_p), ("gn_sums", c_void_p), ("weight_up4", c_void_p), ("gn_ws", c_void_p),
-        ("ln_u", c_void_p), ("ln_v", c_void_p),
+        ("ln_v", c_void_p),
         ("c0", c_int), ("c1", c_int), ("ld0", c_int), ("B", c_int), ("Hin", c_int), ("Win", c_int), ("Cout", c_int),
         ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int), ("upsample", c_int),
         ("silu_from", c_int), ("gate_stride", c_int), ("gn_groups", c_int), ("per_batch_weight", c_int),
@@ -80,7 +80,7 @@ def load():
         "fd_init_conv7x7": [V] * 5 + [I] * 5 + [V],
         "fd_init_conv7x7_tc": [V] * 5 + [I] * 5 + [V],
         "fd_ln_modulate": [V] * 6 + [I] * 4 + [F, I, V],
-        "fd_ln_fold": [V] * 5 + [I] + [V] * 3 + [I] * 4 + [V],
+        "fd_ln_fold": [V] * 5 + [I] + [V] * 2 + [I] * 4 + [V],
         "fd_ln_modulate_io": [V] * 6 + [I] * 4 + [F, I, I, V],
         "fd_dwconv3x3_silu_scan": [V, I, V, V, V, I, I, I, I, I, V],
         "fd_xdt_proj": [V] * 6 + [I] * 6 + [V],

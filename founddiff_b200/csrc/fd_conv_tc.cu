@@ -39,9 +39,10 @@ constexpr int BK = 64;           // K block = one 128-byte swizzle atom of 16-bi
 constexpr int UMMA_K = 16;
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_EPI_WARPS = 16;
-constexpr int NUM_STAT_WARPS = 2;                     // LayerNorm row statistics of the staged A tile (ln_u != NULL), 2 rows per lane
-constexpr int NTHREADS = (2 + NUM_EPI_WARPS + NUM_STAT_WARPS) * 32;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner,
-                                                      // 16 epilogue warps, 2 statistics warps
+constexpr int NUM_STAT_WARPS = 1;                     // LayerNorm row statistics of the staged A tile (ln_v != NULL), 4 rows per lane
+                                                      // (a second warp would cap the kernel at 96 registers and spill the epilogue)
+constexpr int NTHREADS = (2 + NUM_EPI_WARPS) * 32;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, 16 epilogue warps
+constexpr int NTHREADS_LN = NTHREADS + NUM_STAT_WARPS * 32;   // + the statistics warp of the LayerNorm-fold instantiation
 
 // n / d for 0 <= n with n * d < 2^32 as one multiply-high (host-precomputed ceil(2^32 / d); d == 1 handled apart)
 struct FastDiv {
@@ -251,8 +252,10 @@ FD_DEVINL float fast_silu(float x) {      // x * sigmoid(x) = 0.5 x (1 + tanh(x 
 // epilogue (lane quarter = warp % 4, column group = (warp - 2) / 4).  Two TMEM accumulator buffers let the epilogue of
 // tile i overlap the loads + MMAs of tile i+1; every role walks the same static tile sequence
 // tile = blockIdx.x + i * gridDim.x (N tile fastest, so neighbouring CTAs share the A tile in L2).
-template <typename T>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// LNFOLD is a template parameter so that the plain instantiation keeps the register allocation and schedule it was tuned
+// with (as a run-time flag the fold cost every other 64-wide GEMM 13 - 15 %).
+template <typename T, bool LNFOLD>
+__global__ void __launch_bounds__(LNFOLD ? NTHREADS_LN : NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -282,7 +285,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fd_conv_params& p = q.p;
-    const bool ln_fold = p.ln_u != nullptr;           // LayerNorm of the input rows folded into this GEMM (box mode, 1x1)
+    constexpr bool ln_fold = LNFOLD;                  // LayerNorm of the input rows folded into this GEMM (box mode, 1x1)
     const int total_tiles = q.total_tiles;
     const uint32_t tmem_cols = 2 * BN <= 128 ? 128u : 2 * BN <= 256 ? 256u : 512u;       // two accumulators, power-of-two allocation
 
@@ -441,14 +444,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 __syncwarp();
             }
         }
-    } else if (warp >= 2 + NUM_EPI_WARPS) {
-        // ================================ LayerNorm row statistics (ln fold): 2 warps ================================
-        // mean / rstd over the c0 input channels of each of the tile's 128 pixels, read from the SAME staged A tiles the MMA
-        // consumes (no extra global traffic, no separate normalisation pass).  A row of a K block is 128 bytes = 8 swizzled
-        // 16-byte chunks; sums do not care about the chunk order, so lane r reads chunk (j + r) & 7 at step j: the eight
-        // rows a quarter-warp touches per LDS.128 phase hit eight different bank groups.
+    } else if (LNFOLD && warp >= 2 + NUM_EPI_WARPS) {
+        // ================================ LayerNorm row statistics (ln fold): 1 warp ================================
+        // rstd over the c0 input channels of each of the tile's 128 pixels, read from the SAME staged A tiles the MMA consumes
+        // (no extra global traffic, no separate normalisation pass).  A row of a K block is 128 bytes = 8 swizzled 16-byte
+        // chunks; sums do not care about the chunk order, so the lane owning row r reads chunk (j + r) & 7 at step j: the
+        // eight rows a quarter-warp touches per LDS.128 phase hit eight different bank groups.  The mean itself is not needed
+        // downstream: fd_ln_fold gives every weight row a zero sum, so W'(x - mean 1) = W'x.
         if (ln_fold) {
-            const int r0 = (warp - 2 - NUM_EPI_WARPS) * 64 + lane, r1 = r0 + 32;
             const float inv_c = 1.f / (float)p.c0;
             int stage = 0, it = 0;
             uint32_t ph = 0;
@@ -459,31 +462,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     float2 f;
                     if (q.fmt) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
                     else f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-                    sum += f.x; sq = fmaf(f.x, f.x, sq);
-                    sum += f.y; sq = fmaf(f.y, f.y, sq);
+                    sum += f.x + f.y;
+                    sq = fmaf(f.x, f.x, fmaf(f.y, f.y, sq));
                 }
             };
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
-                float sa0 = 0.f, qa0 = 0.f, sa1 = 0.f, qa1 = 0.f;
+                float sm[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], ph);
-                    const uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    const uint8_t* sa = smem + (size_t)stage * stage_bytes + lane * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const uint4 va = *reinterpret_cast<const uint4*>(sa + r0 * 128 + (((j + r0) & 7) << 4));
-                        const uint4 vb = *reinterpret_cast<const uint4*>(sa + r1 * 128 + (((j + r1) & 7) << 4));
-                        acc8(va, sa0, qa0);
-                        acc8(vb, sa1, qa1);
+                        const int off = ((j + lane) & 7) << 4;           // rows lane, lane + 32, ...: same (row & 7)
+                        uint4 v4[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) v4[r] = *reinterpret_cast<const uint4*>(sa + r * 32 * 128 + off);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc8(v4[r], sm[r], sq[r]);
                     }
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[stage])) : "memory");
                     if (++stage == stages) { stage = 0; ph ^= 1; }
                 }
                 mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);     // the epilogue has read the statistics of tile it - 2
-                const float m0 = sa0 * inv_c, m1 = sa1 * inv_c;
-                s_ln[buf * BM + r0] = make_float2(m0, rsqrtf(fmaxf(qa0 * inv_c - m0 * m0, 0.f) + p.ln_eps));
-                s_ln[buf * BM + r1] = make_float2(m1, rsqrtf(fmaxf(qa1 * inv_c - m1 * m1, 0.f) + p.ln_eps));
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float mean = sm[r] * inv_c;
+                    s_ln[buf * BM + r * 32 + lane] = make_float2(mean, rsqrtf(fmaxf(sq[r] * inv_c - mean * mean, 0.f) + p.ln_eps));
+                }
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sfull_bar[buf])) : "memory");
             }
@@ -577,12 +584,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (use_add) load16_raw(addend + orow + n0 + cg * 16, araw);
             mbar_wait_long(&tfull_bar[buf], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float ln_mean = 0.f, ln_rstd = 1.f;
-            if (ln_fold) {                             // statistics of this thread's pixel (written by the statistics warps)
+            float ln_rstd = 1.f;
+            if (ln_fold) {                             // statistics of this thread's pixel (written by the statistics warp)
                 mbar_wait(&sfull_bar[buf], (it >> 1) & 1);
-                const float2 st = s_ln[buf * BM + m];
-                ln_mean = st.x;
-                ln_rstd = st.y;
+                ln_rstd = s_ln[buf * BM + m].y;
             }
             const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q4 * 32) << 16);
 #pragma unroll
@@ -603,18 +608,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 const int n = n0 + c;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-                if (ln_fold) {                         // W LN(x) = rstd (W' x - mean u) + v   (fd_ln_fold made W', u, v)
-                    const float* up = p.ln_u + (long)b * p.Cout + n;
+                if (ln_fold) {                         // W LN(x) = rstd W' x + v   (fd_ln_fold made W' with zero row sums, and v)
                     const float* vp = p.ln_v + (long)b * p.Cout + n;
-                    const float nm = -ln_mean;
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
-                        const float4 uu = __ldg(reinterpret_cast<const float4*>(up + j));
                         const float4 vv = __ldg(reinterpret_cast<const float4*>(vp + j));
-                        v[j] = fmaf(ln_rstd, fmaf(nm, uu.x, v[j]), vv.x);
-                        v[j + 1] = fmaf(ln_rstd, fmaf(nm, uu.y, v[j + 1]), vv.y);
-                        v[j + 2] = fmaf(ln_rstd, fmaf(nm, uu.z, v[j + 2]), vv.z);
-                        v[j + 3] = fmaf(ln_rstd, fmaf(nm, uu.w, v[j + 3]), vv.w);
+                        v[j] = fmaf(ln_rstd, v[j], vv.x);
+                        v[j + 1] = fmaf(ln_rstd, v[j + 1], vv.y);
+                        v[j + 2] = fmaf(ln_rstd, v[j + 2], vv.z);
+                        v[j + 3] = fmaf(ln_rstd, v[j + 3], vv.w);
                     }
                 }
                 if (p.bias) {                          // warp-uniform branches, 16-byte parameter loads
@@ -768,9 +770,9 @@ extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
         const int cpg = p->Cout / p->gn_groups;
         if (cpg < 8 || cpg % 8 || (cpg & (cpg - 1)) || p->gn_groups > 8) return 0;
     }
-    if (p->ln_u || p->ln_v) {     // LayerNorm fold: plain 1x1 GEMM over one input tensor (box mode), 16-byte aligned vectors
-        if (!p->ln_u || !p->ln_v || p->KH != 1 || p->KW != 1 || p->stride != 1 || p->pad != 0 || p->upsample || p->c1) return 0;
-        if (((uintptr_t)p->ln_u | (uintptr_t)p->ln_v) & 15 || p->Cout % 4) return 0;
+    if (p->ln_v) {                // LayerNorm fold: plain 1x1 GEMM over one input tensor (box mode), 16-byte aligned vector
+        if (p->KH != 1 || p->KW != 1 || p->stride != 1 || p->pad != 0 || p->upsample || p->c1) return 0;
+        if (((uintptr_t)p->ln_v & 15) || p->Cout % 4) return 0;
     }
     const uintptr_t al = (uintptr_t)p->src0 | (uintptr_t)p->src1 | (uintptr_t)p->weight | (uintptr_t)p->out |
                          (uintptr_t)p->addend | (uintptr_t)p->weight_up4;
@@ -878,24 +880,25 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     return 0;
 }
 
+template <typename T, bool LNFOLD>
+static int conv_tc_launch(const fd_gemm_plan* plan, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<T, LNFOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    conv_tc_kernel<T, LNFOLD><<<plan->grid, LNFOLD ? NTHREADS_LN : NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
+    return 0;
+}
+
 extern "C" int fd_conv2d_tc_run(const fd_gemm_plan* plan, cudaStream_t stream) {
     if (!plan) return FD_ERR_BAD_ARGUMENT;
-    static bool attr_bf16 = false, attr_f16 = false;
-    if (plan->q.p.dtype == FD_BF16) {
-        if (!attr_bf16) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-            if (e != cudaSuccess) return (int)e;
-            attr_bf16 = true;
-        }
-        conv_tc_kernel<__nv_bfloat16><<<plan->grid, NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
-    } else {
-        if (!attr_f16) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
-            if (e != cudaSuccess) return (int)e;
-            attr_f16 = true;
-        }
-        conv_tc_kernel<__half><<<plan->grid, NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
-    }
+    const bool fold = plan->q.p.ln_v != nullptr;
+    int rc;
+    if (plan->q.p.dtype == FD_BF16) rc = fold ? conv_tc_launch<__nv_bfloat16, true>(plan, stream) : conv_tc_launch<__nv_bfloat16, false>(plan, stream);
+    else rc = fold ? conv_tc_launch<__half, true>(plan, stream) : conv_tc_launch<__half, false>(plan, stream);
+    if (rc) return rc;
     FD_LAUNCH_CHECK();
     if (plan->q.p.gn_sums && plan->q.p.gn_ws) {
         gn_finalize_kernel<<<plan->q.p.B, 32, 0, stream>>>(plan->q.p.gn_ws, plan->q.p.gn_sums, (int)plan->grid.x, plan->q.p.gn_groups);

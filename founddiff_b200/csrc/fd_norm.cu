@@ -323,40 +323,44 @@ extern "C" int fd_ln_gate(const void* y, const void* xz, int ld, int z_off, cons
 
 // ------------------------------------------------------------------------------------------------------
 // LayerNorm + adaLN modulation folded into the weights of the 1x1 GEMM that consumes it (see fd_ln_fold in the header).
-// One warp per (sample, output row): Wf = round(W g), u = sum of the ROUNDED row, v = W h; fixed shuffle tree -> reproducible.
+// One warp per (sample, output row): Wf = round(W g - rowmean(W g)), v = W h; fixed shuffle tree -> reproducible.
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, const float* __restrict__ shift,
                                                       const float* __restrict__ scale, int mod_stride, T* __restrict__ Wf,
-                                                      float* __restrict__ u, float* __restrict__ v, int Cout, int C) {
+                                                      float* __restrict__ v, int Cout, int C) {
     const int lane = threadIdx.x & 31, o = blockIdx.x * 8 + (threadIdx.x >> 5), b = blockIdx.y;
     if (o >= Cout) return;
     const float* wr = W + (long)o * C;
     const float* sc = scale + (long)b * mod_stride;
     const float* sh = shift + (long)b * mod_stride;
     T* out = Wf + ((long)b * Cout + o) * C;
-    float us = 0.f, vs = 0.f;
+    float gs = 0.f, vs = 0.f;
     for (int c = lane; c < C; c += 32) {
         const float s1 = 1.f + sc[c];
         const float g = gamma ? gamma[c] * s1 : s1;
         const float h = (beta ? beta[c] * s1 : 0.f) + sh[c];
         const float w = wr[c];
-        fd_st(out + c, w * g);
-        us += fd_ld(out + c);                 // the value the tensor cores will see
+        gs = fmaf(w, g, gs);
         vs = fmaf(w, h, vs);
     }
-    us = fd_warp_sum(us);
+    gs = fd_warp_sum(gs) / (float)C;          // row mean of W g: subtracting it makes the row blind to the input's mean
     vs = fd_warp_sum(vs);
-    if (lane == 0) { u[(long)b * Cout + o] = us; v[(long)b * Cout + o] = vs; }
+    for (int c = lane; c < C; c += 32) {
+        const float s1 = 1.f + sc[c];
+        const float g = gamma ? gamma[c] * s1 : s1;
+        fd_st(out + c, fmaf(wr[c], g, -gs));
+    }
+    if (lane == 0) v[(long)b * Cout + o] = vs;
 }
 
 extern "C" int fd_ln_fold(const float* W, const float* gamma, const float* beta, const float* shift, const float* scale, int mod_stride,
-                          void* Wf, float* u, float* v, int B, int Cout, int C, int dtype, cudaStream_t stream) {
-    if (!W || !shift || !scale || !Wf || !u || !v || B <= 0 || Cout <= 0 || C <= 0 || mod_stride < C) return FD_ERR_BAD_ARGUMENT;
+                          void* Wf, float* v, int B, int Cout, int C, int dtype, cudaStream_t stream) {
+    if (!W || !shift || !scale || !Wf || !v || B <= 0 || Cout <= 0 || C <= 0 || mod_stride < C) return FD_ERR_BAD_ARGUMENT;
     if ((gamma == nullptr) != (beta == nullptr)) return FD_ERR_BAD_ARGUMENT;
     dim3 grid((unsigned)fd_cdiv(Cout, 8), (unsigned)B);
-    FD_DISPATCH_DTYPE(dtype, T, (ln_fold_kernel<T><<<grid, 256, 0, stream>>>(W, gamma, beta, shift, scale, mod_stride, (T*)Wf, u, v, Cout, C)));
+    FD_DISPATCH_DTYPE(dtype, T, (ln_fold_kernel<T><<<grid, 256, 0, stream>>>(W, gamma, beta, shift, scale, mod_stride, (T*)Wf, v, Cout, C)));
     FD_LAUNCH_CHECK();
     return 0;
 }

@@ -344,12 +344,12 @@ class UnetEngine:
             qkv_w32 = upload(sd[p + ".attn_blk.qkv.weight"].reshape(3 * C, C), dev)
             wf_in = self.buf(f"WFIN.{p}", B, 4 * C, C, dtype=tdt)
             wf_qkv = self.buf(f"WFQKV.{p}", B, 3 * C, C, dtype=tdt)
-            u_in, v_in = (torch.zeros(B, 4 * C, device=dev, dtype=torch.float32) for _ in range(2))
-            u_q, v_q = (torch.zeros(B, 3 * C, device=dev, dtype=torch.float32) for _ in range(2))
+            v_in = torch.zeros(B, 4 * C, device=dev, dtype=torch.float32)
+            v_q = torch.zeros(B, 3 * C, device=dev, dtype=torch.float32)
             try:
                 c_in = ops.Conv(x_in, wf_in, xz, B=B, Hin=h, Win=w, silu_from=2 * C, per_batch_weight=True, prefer_tc=True,
-                                ln_u=u_in, ln_v=v_in, ln_eps=1e-5)
-                c_qkv = ops.Conv(x, wf_qkv, qkv, B=B, Hin=h, Win=w, per_batch_weight=True, prefer_tc=True, ln_u=u_q, ln_v=v_q, ln_eps=1e-6)
+                                ln_v=v_in, ln_eps=1e-5)
+                c_qkv = ops.Conv(x, wf_qkv, qkv, B=B, Hin=h, Win=w, per_batch_weight=True, prefer_tc=True, ln_v=v_q, ln_eps=1e-6)
             except Exception:                           # geometry does not tile for the tensor-core kernel: separate passes
                 use_fold = False
         if not use_fold:
@@ -359,14 +359,14 @@ class UnetEngine:
 
         def ln1_in_proj():
             if use_fold:
-                ops.ln_fold(in_w32, n1w, n1b, sh1, sc1, MS, wf_in, u_in, v_in, B, 4 * C, C)
+                ops.ln_fold(in_w32, n1w, n1b, sh1, sc1, MS, wf_in, v_in, B, 4 * C, C)
             else:
                 ops.ln_modulate(x_in, a, n1w, n1b, sh1, sc1, MS, B, P, C, 1e-5)
             c_in.run()
 
         def ln2_qkv():
             if use_fold:
-                ops.ln_fold(qkv_w32, None, None, sh2, sc2, MS, wf_qkv, u_q, v_q, B, 3 * C, C)
+                ops.ln_fold(qkv_w32, None, None, sh2, sc2, MS, wf_qkv, v_q, B, 3 * C, C)
             else:
                 ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
             c_qkv.run()

@@ -141,7 +141,7 @@ class Conv:
     def __init__(self, src0, weight, out, *, B, Hin, Win, KH=1, KW=1, stride=1, pad=0, upsample=False, src1=None,
                  bias=None, gate=None, gate_stride=0, addend=None, silu_from=None, gn_sums=None, gn_groups=0,
                  per_batch_weight=False, prefer_tc=True, c0=None, ld0=0, relu_out=False, gn_ws=None, weight_up4=None,
-                 ln_u=None, ln_v=None, ln_eps=1e-5):
+                 ln_v=None, ln_eps=1e-5):
         """`c0` / `ld0`: read only the first c0 channels of rows of pitch ld0 starting at src0's data pointer (src0 may
         be a strided channel-slice view).
         `gn_sums` (B, G, 2): GroupNorm statistics of the output.  With `gn_ws` (zeroed before every run: conv_gn_ws_floats(B) for
@@ -158,7 +158,7 @@ class Conv:
         p.bias, p.gate, p.addend, p.gn_sums = _f32(bias), _f32(gate), _p(addend), _f32(gn_sums)
         p.gn_ws = _f32(gn_ws)
         # LayerNorm of the input rows folded into this GEMM (tcgen05 path only): weight = ln_fold()'s per-sample W', see the header
-        p.ln_u, p.ln_v, p.ln_eps = _f32(ln_u), _f32(ln_v), float(ln_eps)
+        p.ln_v, p.ln_eps = _f32(ln_v), float(ln_eps)
         self._gn = None
         p.c0, p.c1, p.B, p.Hin, p.Win, p.Cout = c0, c1, B, Hin, Win, cout
         p.ld0 = ld0
@@ -178,14 +178,14 @@ class Conv:
         assert addend is None or addend.dtype == out.dtype
         assert weight.numel() == (B if per_batch_weight else 1) * cout * KH * KW * (c0 + c1), (weight.shape, cout, KH, KW, c0, c1)
         self.params = p
-        self._keep = (src0, src1, weight, out, bias, gate, addend, gn_sums, gn_ws, ln_u, ln_v)
+        self._keep = (src0, src1, weight, out, bias, gate, addend, gn_sums, gn_ws, ln_v)
         self._lib = lib
         self._plan = c_void_p()
         self.uses_tc = False
         if prefer_tc and lib.fd_conv2d_tc_supported(byref(p)):
             check(lib.fd_conv2d_tc_plan_create(byref(p), byref(self._plan)), "fd_conv2d_tc_plan_create")
             self.uses_tc = True
-        elif ln_u is not None:
+        elif ln_v is not None:
             raise _lib.FdError("Conv: the LayerNorm fold needs the tcgen05 path (1x1, stride 1, tiling geometry): " + self.describe())
         elif gn_sums is not None and gn_ws is not None:
             # CUDA-core path: statistics by a separate reproducible pass over the stored output (the kernel's own epilogue sums
@@ -270,10 +270,10 @@ def ln_modulate(x, out, gamma, beta, shift, scale, mod_stride, B, P, C, eps):
               "fd_ln_modulate_io")
 
 
-def ln_fold(W, gamma, beta, shift, scale, mod_stride, Wf, u, v, B, Cout, C):
-    """Per-sample folded weights of LayerNorm + adaLN modulate + 1x1 GEMM: Wf (B, Cout, C) 16-bit, u, v (B, Cout) fp32."""
+def ln_fold(W, gamma, beta, shift, scale, mod_stride, Wf, v, B, Cout, C):
+    """Per-sample folded weights of LayerNorm + adaLN modulate + 1x1 GEMM: Wf (B, Cout, C) 16-bit (zero row sums), v (B, Cout) fp32."""
     with _launched("ln_fold", f"{B}x{Cout}x{C}", 1):
-        check(_lib.load().fd_ln_fold(_f32(W), _f32(gamma), _f32(beta), _f32(shift), _f32(scale), mod_stride, _p(Wf), _f32(u), _f32(v),
+        check(_lib.load().fd_ln_fold(_f32(W), _f32(gamma), _f32(beta), _f32(shift), _f32(scale), mod_stride, _p(Wf), _f32(v),
                                      B, Cout, C, dtype_code(Wf.dtype), _stream()), "fd_ln_fold")
 
 

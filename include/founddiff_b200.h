@@ -101,10 +101,10 @@ typedef struct {
     float* gn_sums;
     const void* weight_up4; /* upsample only (tcgen05 path): (4, Cout, 2, 2, c0) phase-summed weights, see fd_conv_tc.cu */
     float* gn_ws;         /* optional: fd_conv_gn_ws_floats(B) floats, ZERO on entry (one 16-float slot per sample and thread block) */
-    const float* ln_u;    /* optional (tcgen05 path, 1x1 stride 1, c1 == 0): LayerNorm over the c0 input channels of every pixel FOLDED */
-    const float* ln_v;    /*   into this GEMM: out = rstd_p * (acc - mean_p * ln_u[b, n]) + ln_v[b, n] with acc = W'_b x_p on the RAW input.   */
-                          /*   W'_b = W diag(g_b), ln_u = row sums of W'_b, ln_v = W h_b come from fd_ln_fold (g, h: the LayerNorm affine */
-                          /*   and adaLN modulation); mean_p / rstd_p are computed inside the kernel from the staged operand tile.  (B, Cout) fp32 each. */
+    const float* ln_v;    /* optional (tcgen05 path, 1x1 stride 1, c1 == 0): LayerNorm over the c0 input channels of every pixel FOLDED */
+                          /*   into this GEMM: out = rstd_p * acc + ln_v[b, n] with acc = W'_b x_p on the RAW input.  W'_b (zero row  */
+                          /*   sums) and ln_v (B, Cout) fp32 come from fd_ln_fold; rstd_p is computed inside the kernel from the staged */
+                          /*   operand tile. */
     int c0, c1;
     int ld0;              /* row pitch (elements) of src0; 0 = dense (c0).  Lets a GEMM read a channel slice of a wider tensor */
     int B, Hin, Win, Cout;
@@ -161,13 +161,14 @@ int fd_ln_modulate(const void* x, void* out, const float* gamma, const float* be
                    cudaStream_t stream);
 
 /* LayerNorm + adaLN modulate folded into the 1x1 GEMM that follows it (src/DADiff.py:486-487 -> src/emamba2.py:717 in_proj,
- * src/DADiff.py:258 qkv).  With xhat = (x - mean) rstd:  W ((xhat gamma + beta)(1 + scale) + shift) = rstd (W' x - mean u) + v,
- *   g = gamma (1 + scale_b), h = beta (1 + scale_b) + shift_b (gamma / beta NULL: 1 / 0),
- *   Wf[b, o, c] = W[o, c] g[c] rounded to `dtype`;  u[b, o] = sum_c Wf[b, o, c] (of the ROUNDED values, so the mean cancels
- *   exactly);  v[b, o] = sum_c W[o, c] h[c].   W: (Cout, C) fp32; shift / scale: rows of mod_stride floats per sample.
- * The consumer is fd_conv2d_tc with per_batch_weight = 1, weight = Wf, ln_u = u, ln_v = v. */
+ * src/DADiff.py:258 qkv).  With xhat = (x - mean) rstd,  g = gamma (1 + scale_b),  h = beta (1 + scale_b) + shift_b
+ * (gamma / beta NULL: 1 / 0):   W ((xhat gamma + beta)(1 + scale) + shift) = rstd (W g)(x - mean 1) + W h.
+ *   Wf[b, o, c] = W[o, c] g[c] - rowmean_c(W[o, :] g), rounded to `dtype`: every row sums to zero, so Wf (x - mean 1) = Wf x
+ *   and the GEMM runs on the RAW activations;  v[b, o] = sum_c W[o, c] h[c].
+ *   W: (Cout, C) fp32; shift / scale: rows of mod_stride floats per sample.
+ * The consumer is fd_conv2d_tc with per_batch_weight = 1, weight = Wf, ln_v = v: out = rstd_p (Wf x_p) + v. */
 int fd_ln_fold(const float* W, const float* gamma, const float* beta, const float* shift, const float* scale, int mod_stride,
-               void* Wf, float* u, float* v, int B, int Cout, int C, int dtype, cudaStream_t stream);
+               void* Wf, float* v, int B, int Cout, int C, int dtype, cudaStream_t stream);
 
 /* Same with separate storage types for x (in_dtype) and out (out_dtype); both 16-bit or both fp32. */
 int fd_ln_modulate_io(const void* x, void* out, const float* gamma, const float* beta, const float* shift,

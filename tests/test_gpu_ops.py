@@ -892,11 +892,12 @@ def test_layernorm_folded_into_1x1_gemm(ops, cfg, types):
             return self.t.data_ptr()
     md = mods.cuda()
     wf = torch.empty(B, Cout, C, device="cuda", dtype=in_dt)
-    u, v = torch.empty(B, Cout, device="cuda"), torch.empty(B, Cout, device="cuda")
+    v = torch.empty(B, Cout, device="cuda")
     ops.ln_fold(Wt.cuda(), gamma.cuda() if affine else None, beta.cuda() if affine else None, V(md[:, :C]), V(md[:, C:2 * C]),
-                mods.shape[1], wf, u, v, B, Cout, C)
+                mods.shape[1], wf, v, B, Cout, C)
+    assert float(wf.float().sum(dim=-1).abs().max()) < 0.05         # rows sum to zero up to the 16-bit rounding of the entries
     out = torch.full((B, P, Cout), float("nan"), device="cuda", dtype=out_dt)
-    conv = ops.Conv(x.to("cuda", in_dt), wf, out, B=B, Hin=H, Win=W, per_batch_weight=True, ln_u=u, ln_v=v, ln_eps=eps,
+    conv = ops.Conv(x.to("cuda", in_dt), wf, out, B=B, Hin=H, Win=W, per_batch_weight=True, ln_v=v, ln_eps=eps,
                     silu_from=silu_from)
     assert conv.uses_tc
     conv.run()
