@@ -39,8 +39,7 @@ constexpr int BK = 64;           // K block = one 128-byte swizzle atom of 16-bi
 constexpr int UMMA_K = 16;
 constexpr int MAX_STAGES = 8;
 constexpr int NUM_EPI_WARPS = 16;
-constexpr int NUM_STAT_WARPS = 1;                     // LayerNorm row statistics of the staged A tile (ln_v != NULL), 4 rows per lane
-                                                      // (a second warp would cap the kernel at 96 registers and spill the epilogue)
+constexpr int NUM_STAT_WARPS = 2;                     // LayerNorm row statistics of the staged A tile (ln_v != NULL), 2 rows per lane
 constexpr int NTHREADS = (2 + NUM_EPI_WARPS) * 32;    // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, 16 epilogue warps
 constexpr int NTHREADS_LN = NTHREADS + NUM_STAT_WARPS * 32;   // + the statistics warp of the LayerNorm-fold instantiation
 
@@ -282,6 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint32_t* tmem_slot = (uint32_t*)(sfull_bar + 2);
     float* s_gn = (float*)(tmem_slot + 2);            // [2 flush parities][16 epilogue warps][2][8] GroupNorm partial sums
     float2* s_ln = (float2*)(s_gn + 2 * NUM_EPI_WARPS * 16);   // [2 accumulator buffers][128 rows] (mean, rstd) of the input rows
+    float* s_lnv = (float*)(s_ln + 2 * BM);           // [Cout <= 1024] ln_v of the sample the block is working on (ln fold)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fd_conv_params& p = q.p;
@@ -445,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             }
         }
     } else if (LNFOLD && warp >= 2 + NUM_EPI_WARPS) {
-        // ================================ LayerNorm row statistics (ln fold): 1 warp ================================
+        // ================================ LayerNorm row statistics (ln fold): 2 warps ================================
         // rstd over the c0 input channels of each of the tile's 128 pixels, read from the SAME staged A tiles the MMA consumes
         // (no extra global traffic, no separate normalisation pass).  A row of a K block is 128 bytes = 8 swizzled 16-byte
         // chunks; sums do not care about the chunk order, so the lane owning row r reads chunk (j + r) & 7 at step j: the
@@ -466,30 +466,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                     sq = fmaf(f.x, f.x, fmaf(f.y, f.y, sq));
                 }
             };
+            const int row0 = (warp - 2 - NUM_EPI_WARPS) * 64 + lane;            // this lane's rows: row0 and row0 + 32 (same row & 7)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
-                float sm[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+                float sm[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], ph);
-                    const uint8_t* sa = smem + (size_t)stage * stage_bytes + lane * 128;
+                    const uint8_t* sa = smem + (size_t)stage * stage_bytes + row0 * 128;
+                    // the whole 2 x 128 bytes go to registers first and the stage is handed back at once: holding it for the
+                    // ~1000 clk of the accumulation below kept the TMA producer from running ahead (ncu: 955 vs 585 us,
+                    // long-scoreboard stalls doubled) — the ring is only 2 - 3 stages deep for the wide-N GEMMs this serves
+                    uint4 v4[2][8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int off = ((j + lane) & 7) << 4;           // rows lane, lane + 32, ...: same (row & 7)
-                        uint4 v4[4];
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) v4[r] = *reinterpret_cast<const uint4*>(sa + r * 32 * 128 + off);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) acc8(v4[r], sm[r], sq[r]);
+                        const int off = ((j + lane) & 7) << 4;
+                        v4[0][j] = *reinterpret_cast<const uint4*>(sa + off);
+                        v4[1][j] = *reinterpret_cast<const uint4*>(sa + 32 * 128 + off);
                     }
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[stage])) : "memory");
                     if (++stage == stages) { stage = 0; ph ^= 1; }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        acc8(v4[0][j], sm[0], sq[0]);
+                        acc8(v4[1][j], sm[1], sq[1]);
+                    }
                 }
                 mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);     // the epilogue has read the statistics of tile it - 2
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < 2; ++r) {
                     const float mean = sm[r] * inv_c;
-                    s_ln[buf * BM + r * 32 + lane] = make_float2(mean, rsqrtf(fmaxf(sq[r] * inv_c - mean * mean, 0.f) + p.ln_eps));
+                    s_ln[buf * BM + row0 + r * 32] = make_float2(mean, rsqrtf(fmaxf(sq[r] * inv_c - mean * mean, 0.f) + p.ln_eps));
                 }
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sfull_bar[buf])) : "memory");
@@ -511,6 +518,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 4; ++i) { gacc_s[i][0] = gacc_s[i][1] = gacc_q[i][0] = gacc_q[i][1] = 0.f; }
         int cur_b = -1, cur_n0 = 0;
+        int cur_lnb = -1;
         // Every epilogue warp owns a row of s_gn (no shared-memory atomics: the order of additions is the program order); the rows
         // are double-buffered by flush parity so that ONE barrier per flush is enough — while the first epilogue warp sums and
         // clears the rows of flush k, the other warps may already be adding into the rows of flush k + 1.
@@ -576,6 +584,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 if (b != cur_b) { gn_flush_sample(); cur_b = b; }
                 cur_n0 = n0;
             }
+            if (ln_fold && b != cur_lnb) {              // uniform over the 16 warps: the sample's ln_v row moves to shared memory
+                // (read per 16-column chunk straight from global memory it cost 20 % of the kernel's stall samples: every chunk
+                // waited out an L1 round trip in front of its FMAs)
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                for (int i = threadIdx.x - 64; i < p.Cout; i += NUM_EPI_WARPS * 32) s_lnv[i] = __ldg(p.ln_v + (long)b * p.Cout + i);
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                cur_lnb = b;
+            }
             const int buf = it & 1;
             // residual addend of this thread's first chunk: in flight while the accumulator is still being produced; the next
             // chunk's vector is requested while the current one is processed (the load latency was exposed once per chunk)
@@ -590,6 +606,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 ln_rstd = s_ln[buf * BM + m].y;
             }
             const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q4 * 32) << 16);
+            // (Software-pipelining the TMEM reads — tcgen05.ld of chunk ci + 1 in flight under chunk ci's math — needs a second
+            // 16-register set; at the 96-register cap of an 18-warp block it spilled 190 bytes per thread.  Not done.)
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
                 const int cc = ci * 16;
@@ -609,10 +627,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
                 if (ln_fold) {                         // W LN(x) = rstd W' x + v   (fd_ln_fold made W' with zero row sums, and v)
-                    const float* vp = p.ln_v + (long)b * p.Cout + n;
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
-                        const float4 vv = __ldg(reinterpret_cast<const float4*>(vp + j));
+                        const float4 vv = *reinterpret_cast<const float4*>(s_lnv + n + j);
                         v[j] = fmaf(ln_rstd, v[j], vv.x);
                         v[j + 1] = fmaf(ln_rstd, v[j + 1], vv.y);
                         v[j + 2] = fmaf(ln_rstd, v[j + 2], vv.z);
@@ -772,7 +789,7 @@ extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
     }
     if (p->ln_v) {                // LayerNorm fold: plain 1x1 GEMM over one input tensor (box mode), 16-byte aligned vector
         if (p->KH != 1 || p->KW != 1 || p->stride != 1 || p->pad != 0 || p->upsample || p->c1) return 0;
-        if (((uintptr_t)p->ln_v & 15) || p->Cout % 4) return 0;
+        if (((uintptr_t)p->ln_v & 15) || p->Cout % 4 || p->Cout > 1024) return 0;
     }
     const uintptr_t al = (uintptr_t)p->src0 | (uintptr_t)p->src1 | (uintptr_t)p->weight | (uintptr_t)p->out |
                          (uintptr_t)p->addend | (uintptr_t)p->weight_up4;
@@ -854,6 +871,7 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
         q.stages = (int)((190 * 1024) / stage_bytes);
         if (q.stages > MAX_STAGES) q.stages = MAX_STAGES;
         if (q.stages > 2 * num_kb) q.stages = 2 * num_kb < 2 ? 2 : 2 * num_kb;     // enough to prefetch the next tile
+        if (p->ln_v && q.stages < 3 && 3 * stage_bytes <= 190 * 1024) q.stages = 3;   // a stage also waits for the statistics warps
     }
     q.total_tiles = p->B * q.phases * q.tiles_h * q.tiles_w * q.n_tiles;
     {
@@ -869,7 +887,8 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     }
     const size_t data_bytes = q.halo ? (size_t)(q.b_stationary ? num_kb : q.stages_b) * b_tile + (size_t)q.stages * q.a_stage_bytes
                                      : (size_t)q.stages * stage_bytes;
-    plan->smem = data_bytes + 1024 /*align slack*/ + 5120 /*barriers, per-warp GroupNorm rows (two parities), LayerNorm row statistics*/;
+    plan->smem = data_bytes + 1024 /*align slack*/ + 5120 /*barriers, per-warp GroupNorm rows (two parities), LayerNorm row statistics*/
+                 + (p->ln_v ? 4096 : 0) /*ln_v of the current sample*/;
     if (plan->smem > 225 * 1024) { free(plan); return FD_ERR_UNSUPPORTED; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
