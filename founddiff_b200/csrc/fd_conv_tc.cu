@@ -473,9 +473,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], ph);
                     const uint8_t* sa = smem + (size_t)stage * stage_bytes + row0 * 128;
-                    // the whole 2 x 128 bytes go to registers first and the stage is handed back at once: holding it for the
-                    // ~1000 clk of the accumulation below kept the TMA producer from running ahead (ncu: 955 vs 585 us,
-                    // long-scoreboard stalls doubled) — the ring is only 2 - 3 stages deep for the wide-N GEMMs this serves
+                    // The stage is handed back only AFTER its rows have been accumulated.  Releasing it right after the loads
+                    // (the values sit in registers) was 15 % faster but NOT reproducible for GEMMs with two K blocks and two N
+                    // tiles (tools/probes/ln_fold_repro.py: rows normalised with wrong statistics in most launches at 16x256^2,
+                    // 128 -> 512; never with the late release, never for one K block or one N tile).  The cause was not found
+                    // in the barrier protocol; until it is, correctness wins.
                     uint4 v4[2][8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -483,14 +485,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                         v4[0][j] = *reinterpret_cast<const uint4*>(sa + off);
                         v4[1][j] = *reinterpret_cast<const uint4*>(sa + 32 * 128 + off);
                     }
-                    __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[stage])) : "memory");
-                    if (++stage == stages) { stage = 0; ph ^= 1; }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         acc8(v4[0][j], sm[0], sq[0]);
                         acc8(v4[1][j], sm[1], sq[1]);
                     }
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty_bar[stage])) : "memory");
+                    if (++stage == stages) { stage = 0; ph ^= 1; }
                 }
                 mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);     // the epilogue has read the statistics of tile it - 2
 #pragma unroll
@@ -874,6 +876,7 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
         if (p->ln_v && q.stages < 3 && 3 * stage_bytes <= 190 * 1024) q.stages = 3;   // a stage also waits for the statistics warps
     }
     q.total_tiles = p->B * q.phases * q.tiles_h * q.tiles_w * q.n_tiles;
+
     {
         auto mk = [](int d) { FastDiv f; f.d = (uint32_t)d; f.mul = d > 1 ? (uint32_t)((((uint64_t)1 << 32) + d - 1) / d) : 0u; return f; };
         q.dv_n = mk(q.n_tiles); q.dv_w = mk(q.tiles_w); q.dv_h = mk(q.tiles_h); q.dv_p = mk(q.phases);
