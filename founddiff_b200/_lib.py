@@ -14,7 +14,7 @@ from . import build as _build
 FD_F32, FD_BF16, FD_F16 = 0, 1, 2
 
 EXPORTS = [
-    "fd_version", "fd_ln_fold", "fd_gram_ws_floats", "fd_conv_gn_ws_floats", "fd_gn_stats_ws_floats", "fd_dwconv3x3_silu_tm", "fd_x_proj_tm", "fd_scan_tm_segments", "fd_scan_tm_plan", "fd_selective_scan_tm", "fd_selective_scan_fwd", "fd_selective_scan_fwd_merge", "fd_selective_scan_fwd_merge_xdbl", "fd_selective_scan_fwd_merge_cl", "fd_x_proj_tc", "fd_avgpool2x2_nhwc", "fd_slice_metrics", "fd_init_conv7x7_tc", "fd_ln_modulate_io", "fd_ln_gate", "fd_conv2d_simt", "fd_conv2d_tc_supported", "fd_conv2d_tc_plan_create",
+    "fd_version", "fd_program_arena_bytes", "fd_program_load", "fd_program_buffer", "fd_program_num_launches", "fd_unet_step", "fd_sample_step", "fd_program_destroy", "fd_ln_fold", "fd_gram_ws_floats", "fd_conv_gn_ws_floats", "fd_gn_stats_ws_floats", "fd_dwconv3x3_silu_tm", "fd_x_proj_tm", "fd_scan_tm_segments", "fd_scan_tm_plan", "fd_selective_scan_tm", "fd_selective_scan_fwd", "fd_selective_scan_fwd_merge", "fd_selective_scan_fwd_merge_xdbl", "fd_selective_scan_fwd_merge_cl", "fd_x_proj_tc", "fd_avgpool2x2_nhwc", "fd_slice_metrics", "fd_init_conv7x7_tc", "fd_ln_modulate_io", "fd_ln_gate", "fd_conv2d_simt", "fd_conv2d_tc_supported", "fd_conv2d_tc_plan_create",
     "fd_conv2d_tc_run", "fd_conv2d_tc_plan_destroy", "fd_init_conv7x7", "fd_ln_modulate", "fd_dwconv3x3_silu_scan",
     "fd_xdt_proj", "fd_xdt_proj_tc", "fd_merge_ln_gate", "fd_dwconv3x3_qkv_gram", "fd_dwconv3x3_nhwc", "fd_gram_qk", "fd_attn_weff", "fd_gn_stats", "fd_gn_silu_add", "fd_gn_scale_shift_silu", "fd_flash_attn_d32", "fd_linattn_context", "fd_linattn_weff", "fd_softmax_d32",
     "fd_linear_small", "fd_time_sinusoid", "fd_sampler_init", "fd_final_conv_update", "fd_final_conv_update_obj", "fd_unnormalize", "fd_ddpm_update",
@@ -45,11 +45,14 @@ def lib_path() -> str:
     return _build.LIB
 
 
+PROXY = None          # set by program.Recorder: a wrapper around the loaded library that records every launch it forwards
+
+
 def load():
     """Load (building first if needed) the CUDA library.  Raises if it cannot be had — no fallback."""
     global _lib
     if _lib is not None:
-        return _lib
+        return PROXY if PROXY is not None else _lib
     path = _build.LIB
     if _build.needs_build():
         try:
@@ -111,6 +114,20 @@ def load():
         fn.restype = c_int
     lib.fd_conv_gn_ws_floats.argtypes = [c_int]
     lib.fd_conv_gn_ws_floats.restype = c_long
+    lib.fd_program_arena_bytes.argtypes = [c_char_p]
+    lib.fd_program_arena_bytes.restype = c_long
+    lib.fd_program_load.argtypes = [c_char_p, c_void_p, c_long, POINTER(c_void_p)]
+    lib.fd_program_load.restype = c_int
+    lib.fd_program_buffer.argtypes = [c_void_p, c_char_p, POINTER(c_long)]
+    lib.fd_program_buffer.restype = c_void_p
+    lib.fd_program_num_launches.argtypes = [c_void_p]
+    lib.fd_program_num_launches.restype = c_int
+    lib.fd_unet_step.argtypes = [c_void_p, c_void_p]
+    lib.fd_unet_step.restype = c_int
+    lib.fd_sample_step.argtypes = [c_void_p, c_void_p]
+    lib.fd_sample_step.restype = c_int
+    lib.fd_program_destroy.argtypes = [c_void_p]
+    lib.fd_program_destroy.restype = None
     lib.fd_gram_ws_floats.argtypes = [c_int] * 5
     lib.fd_gram_ws_floats.restype = c_long
     lib.fd_gn_stats_ws_floats.argtypes = [c_int, c_int, c_int]
@@ -120,7 +137,7 @@ def load():
     lib.fd_conv2d_tc_plan_destroy.argtypes = [c_void_p]
     lib.fd_conv2d_tc_plan_destroy.restype = None
     _lib = lib
-    return lib
+    return PROXY if PROXY is not None else lib
 
 
 def check(rc: int, what: str):

@@ -29,7 +29,8 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "founddiff_b200.h")]
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc")) + [
+        os.path.join(HERE, "..", "include", "founddiff_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -52,6 +53,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def _build_locked(force: bool, verbose: bool, objdir: str) -> str:
+    from . import gen_dispatch
+    gen_dispatch.write()                       # csrc/fd_program_dispatch.inc from the header (step programs)
     objs = []
     procs = []
     for src in sources():

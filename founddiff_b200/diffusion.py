@@ -356,7 +356,7 @@ class ResidualDiffusion(nn.Module):
     # -- sampling --------------------------------------------------------------------------------------------
     @torch.no_grad()
     def sample(self, x_input=0, batch_size=16, last=True, *, noise=None, trace: Optional[list] = None,
-               steps_limit: Optional[int] = None):
+               steps_limit: Optional[int] = None, _record=None):
         """src/DADiff.py:1367-1380.  x_input: list [ldct (B,1,H,W) in [0,1]] on a CUDA device.  Returns the list
         [x_input_plus_noise, denoised] (or every intermediate when last=False), each (B,1,H,W) in [0,1].
         `steps_limit` (measurement only): stop after the first n timesteps of the schedule (a window of the ancestral loop)."""
@@ -453,8 +453,25 @@ class ResidualDiffusion(nn.Module):
                                   bias1=engs[1].final_b if two else None)
 
         step_fn = one_step
-        if self.use_cuda_graph:
+        if self.use_cuda_graph and _record is None:
             step_fn = self._graphed(engs, one_step, (taps is not None, objective, side is not None))
+        if _record is not None:                      # program.export_step_program: the first timestep runs eagerly under the recorder
+            if two or taps is not None:
+                raise NotImplementedError("step programs are recorded for the one-Unet objectives without taps")
+            for t_, n_ in ((eng.x_t, "x_t"), (eng.x_input, "x_input"), (eng.time, "time"), (coef, "coef"), (noise_buf, "noise"),
+                           (eng.prompt_emb, "prompt_emb"), (eng.feat, "feat")):
+                _record.name(t_, n_)
+            for j, lv in enumerate(eng._local_views):
+                _record.name(lv.dense(), f"local.{j}")
+
+            def step_fn():
+                if _record.calls:
+                    return one_step()
+                with _record:
+                    eng.forward()
+                    _record.mark_unet_done()
+                    ops.final_conv_update(eng.feat, eng.final_w, eng.final_b, eng.x_input, eng.x_t, noise_buf, coef, eng.x_t,
+                                          None, None, None, objective=objective)
 
         imgs = []
         for i, (t, c) in enumerate(plan):

@@ -45,7 +45,10 @@ def upload(t: torch.Tensor, device, dtype=None) -> torch.Tensor:
     t = t.detach()
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
-    return t.contiguous().to(device)
+    out = t.contiguous().to(device)
+    if out.is_cuda:
+        ops.CONST_STORAGES.add(out.untyped_storage().data_ptr())      # a plan file stores these with their bytes (program.py)
+    return out
 
 
 def pack_conv(w: torch.Tensor, dtype, device) -> torch.Tensor:
@@ -511,7 +514,7 @@ class UnetEngine:
     def forward(self):
         """One Unet evaluation on (self.x_t, self.x_input, self.time); the result is `self.feat`, the input of
         final_conv, which the sampler fuses with the update (ops.final_conv_update)."""
-        self.acc_buf.zero_()
+        ops.zero_(self.acc_buf)
         self.conditioning()
         for fn in self.steps:
             fn()

@@ -22,9 +22,15 @@ def dtype_code(dt: torch.dtype) -> int:
         raise TypeError(f"unsupported activation dtype {dt}") from None
 
 
+_REC = None                      # program.Recorder while a step is being recorded
+CONST_STORAGES = set()           # storage pointers of packed weights (engine.upload): stored with their bytes in a plan file
+
+
 def _p(t: Optional[torch.Tensor]):
     if t is None:
         return None
+    if _REC is not None:
+        _REC.note(t)
     if not t.is_cuda:
         raise _lib.FdError("founddiff_b200 ops need CUDA tensors (there is no CPU fallback)")
     if not t.is_contiguous():
@@ -210,6 +216,8 @@ class Conv:
         return 2.0 * p.B * ho * wo * p.Cout * p.KH * p.KW * (p.c0 + p.c1)
 
     def run(self):
+        if _REC is not None:
+            _REC.conv(self)
         with _launched("conv_tc" if self.uses_tc else "conv_simt", self.describe(),
                        2 if (self.uses_tc and self.params.gn_sums and self.params.gn_ws) else 1):
             if self.uses_tc:
@@ -522,6 +530,13 @@ def linear_attention(qkv, wout, bias, g, out, B, H, W, heads, dim, scale=32 ** -
     zeros = torch.zeros(B, dim, device=dev)
     ln_modulate(y, out, g, torch.zeros_like(g), zeros, zeros, dim, B, N, dim, 1e-5)
     return out
+
+
+def zero_(t: torch.Tensor):
+    """t.zero_() that a step recording sees (cudaMemsetAsync in the replayed program)."""
+    if _REC is not None:
+        _REC.memset(t)
+    t.zero_()
 
 
 def linear_small(x, W, bias, out, *, add=None, act_in=0, act_out=0):

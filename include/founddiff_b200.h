@@ -23,8 +23,8 @@
 extern "C" {
 #endif
 
-#ifndef __CUDA_RUNTIME_H__
-typedef struct CUstream_st* cudaStream_t;
+#if !defined(__CUDA_RUNTIME_H__) && !defined(__CUDA_RUNTIME_API_H__) && !defined(__DRIVER_TYPES_H__)
+typedef struct CUstream_st* cudaStream_t;      /* include the CUDA runtime headers first if the host uses them */
 #endif
 
 typedef enum { FD_F32 = 0, FD_BF16 = 1, FD_F16 = 2 } fd_dtype;
@@ -373,6 +373,28 @@ int fd_slice_metrics(const float* pred, const float* target, float* out, int B, 
  * coef (DEVICE fp32[8]) = {sr, srm1, a0, a1, a2, a3, clip, 0}. */
 int fd_ddpm_update(const float* x_t, const float* eps, const float* noise, const float* coef, float* x_next, float* x_start,
                    long n, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Step programs — `unet_step` of SURVEY 8(b): one C call launches a whole timestep on caller-owned memory.
+ * Replaces, per timestep, `Unet.forward` (src/DADiff.py:685-740; fd_unet_step) and additionally `model_predictions` + the
+ * DDIM / posterior update (src/DADiff.py:1153-1209, 1221-1230, 1323-1344; fd_sample_step).  A plan file is recorded once by the
+ * host module for a fixed (batch, H, W, storage type): founddiff_b200/program.py::export_step_program.  It holds the packed
+ * weights, the launch list and the buffer layout; loading it resolves every pointer into the caller's arena and builds the
+ * TMA descriptors of the convolutions.  Steps are stream-ordered, allocation-free and CUDA-graph capturable.
+ *   per step the caller writes (device memory, fp32): "time" (B) = alphas_cumsum[t] * 1000 (src/DADiff.py:1161-1163),
+ *   "coef" (8) = {c_xt, c_res, c_x0, c_noise, alphas_cumsum[t], betas_cumsum[t], one_minus_alphas_cumsum[t], 0}, "noise" (B, H*W)
+ *   when c_noise != 0; per slice batch: "x_input" and "x_t" (B, H*W, in [-1, 1]) and the conditioning vectors "prompt_emb" /
+ *   "local.<block>" (from the DA-CLIP embeddings; the plan file carries the values of the slices it was recorded with).
+ *   After fd_sample_step "x_t" holds x_{t-1}.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct fd_program fd_program;
+long fd_program_arena_bytes(const char* path);                        /* < 0: not a plan file */
+int fd_program_load(const char* path, void* arena, long arena_bytes, fd_program** prog);
+void* fd_program_buffer(const fd_program* prog, const char* name, long* nbytes);   /* NULL: no such buffer */
+int fd_program_num_launches(const fd_program* prog);
+int fd_unet_step(const fd_program* prog, cudaStream_t stream);
+int fd_sample_step(const fd_program* prog, cudaStream_t stream);
+void fd_program_destroy(fd_program* prog);
 
 #ifdef __cplusplus
 }
