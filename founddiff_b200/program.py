@@ -61,7 +61,8 @@ class Recorder:
 
     # -- hooks used by ops ---------------------------------------------------------------------------------
     def note(self, t):
-        t = getattr(t, "t", t)                            # engine._view_ptr
+        if not isinstance(t, torch.Tensor):
+            t = getattr(t, "t", None)                     # engine._view_ptr wraps a strided view
         if isinstance(t, torch.Tensor) and t.is_cuda:
             self.tensors[t.data_ptr()] = t
 
