@@ -418,8 +418,9 @@ class ResidualDiffusion(nn.Module):
         first = torch.empty(B, P, device=dev, dtype=torch.float32)
         ops.sampler_init(ldct32, get_noise("init").contiguous().view(B, P), math.sqrt(self.sum_scale), eng.x_input, eng.x_t, first)
         for e, (idx, _) in zip(engs, evals):         # once per slice and per Unet (cached across timesteps)
-            dose, ctx = model.daclip(dev, idx).embed(eng.x_input.view(B, 1, H, W))
-            e.set_condition(dose, ctx)
+            with ops.nvtx_range("fd.sample.daclip (once per slice)"):
+                dose, ctx = model.daclip(dev, idx).embed(eng.x_input.view(B, 1, H, W))
+                e.set_condition(dose, ctx)
 
         coef = self._buffer(eng, "coef", 8)
         noise_buf = self._buffer(eng, "noise", B * P).view(B, P)
@@ -480,7 +481,8 @@ class ResidualDiffusion(nn.Module):
                 e.time.copy_(rows[i], non_blocking=True)
             if c[3] != 0.:
                 put_step_noise(get_noise("step", i, t))
-            step_fn()
+            with ops.nvtx_range(f"fd.sample.step t={t}"):
+                step_fn()
             if trace is not None:
                 trace.append(dict(t=t, pred_res=taps[0].clone().view(B, 1, H, W), pred_noise=taps[1].clone().view(B, 1, H, W),
                                   x_start=taps[2].clone().view(B, 1, H, W)))

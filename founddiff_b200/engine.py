@@ -124,9 +124,11 @@ class UnetEngine:
 
         # ---- build the layer list -----------------------------------------------------------------------
         self.steps: List = []          # list of callables executed in order by forward()
+        self.step_names: List[str] = []   # NVTX label of each entry (filled after the build from the block prefixes)
         self.paths: Dict[str, str] = {}   # Mamba block -> kernel variant its SS2D core runs (asserted by the B = 16 parity test)
         self._acc_users = []
         self._build(sd)
+        self.step_names = [getattr(fn, "_fd_name", f"fd.unet.step{i}") for i, fn in enumerate(self.steps)]
         self.acc_buf = torch.zeros(max(self._acc_size, 1), device=dev, dtype=torch.float32)
         for fn in self._acc_users:
             fn()
@@ -286,6 +288,7 @@ class UnetEngine:
             if has_res:
                 holder["rconv"].run()
             ops.gn_silu_add(y, holder["sums"], gamma, beta, sk, out, B, P, cout, GN_GROUPS)
+        run._fd_name = f"fd.unet.{p} ResnetBlock {cin}->{cout} @{h}x{w}"
         self.steps.append(run)
 
     # -------------------------------------------------------------------------------------------------------
@@ -487,6 +490,7 @@ class UnetEngine:
                 ops.dwconv3x3_qkv_gram(qkv, qdw_w, v, holder["gram"], holder["qk"], B, h, w, C, ws=holder["gws"])
             ops.attn_weff(holder["gram"], holder["qk"], temp, proj_w, weff, B, C)
             c_att.run()
+        run._fd_name = f"fd.unet.{p} Mamba_block C{C} N{N} @{h}x{w}"
         self.steps.append(run)
         return x
 
@@ -515,9 +519,15 @@ class UnetEngine:
         """One Unet evaluation on (self.x_t, self.x_input, self.time); the result is `self.feat`, the input of
         final_conv, which the sampler fuses with the update (ops.final_conv_update)."""
         ops.zero_(self.acc_buf)
-        self.conditioning()
-        for fn in self.steps:
-            fn()
+        with ops.nvtx_range("fd.unet.conditioning"):
+            self.conditioning()
+        if ops.NVTX:
+            for name, fn in zip(self.step_names, self.steps):
+                with ops.nvtx_range(name):
+                    fn()
+        else:
+            for fn in self.steps:
+                fn()
         return self.feat
 
 

@@ -53,6 +53,31 @@ def version() -> str:
 
 
 # ---------------------------------------------------------------------------------------------------------
+# NVTX ranges: FD_NVTX=1 brackets sample() / DA-CLIP / every timestep / every Unet block, so that a
+# timeline (ncu --nvtx, nsys where available) is labelled with the reference's own structure.  Off by default: a push / pop
+# pair per block is ~1 us of host time per launch group.
+import os as _os
+NVTX = _os.environ.get("FD_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    __slots__ = ("name",)
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+# ---------------------------------------------------------------------------------------------------------
 # Launch accounting / per-kernel timing (bench.py).  LAUNCHES counts kernels launched through this module;
 # when PROFILE is a list every op is bracketed by CUDA events on the launching stream and appended as
 # (name, detail, start_event, end_event).
