@@ -136,6 +136,39 @@ def main():
             report("ln_gate", f"{B}x{H * H}x{D}", ms, 3.0 * B * H * H * D * es)
             del ynhwc
             del xz, xs, out
+    if args.only in ("", "tm") and dt != torch.float32:
+        # the time-major SS2D chain the 16-bit engine runs (fd_ss2d_tm.cu): depthwise conv -> x_proj (-> dt_proj) -> scan + merge, with
+        # the reference's parameter initialisation (dt in [1e-3, 1e-1], A = -1 .. -N: src/emamba2.py:548-574), which decides how far
+        # a carry has to be walked.  Bytes: SURVEY 8(d) stage figures.
+        for C, H, N in sel(LEVELS):
+            D, L, R = 2 * C, H * H // 4, math.ceil(C / 16)
+            fuse = (N, R) in ((4, 4), (8, 4), (8, 8), (16, 8))
+            xz = rn(B, H * H, 4 * C)
+            w9, bcv = rn(9, D, d=torch.float32) * 0.3, rn(D, d=torch.float32) * 0.1
+            xs = torch.empty(B, 4, L, D, device="cuda", dtype=dt)
+            ms = timeit(lambda: ops.dwconv3x3_silu_tm(xz, 4 * C, w9, bcv, xs, B, H, H, D), args.iters)
+            report("dwconv_tm", f"{B}x{H}x{H}x{D}", ms, 2.0 * B * H * H * D * es, 18.0 * B * H * H * D)
+            Wx, Wd = rn(4, R + 2 * N, D, d=torch.float32) / math.sqrt(D), (torch.rand(4, D, R, device="cuda", generator=g) * 2 - 1) * R ** -0.5
+            xw16, dw16, Rp = ops.pack_xdt_weights(Wx, Wd, dt)
+            dtv = torch.exp(torch.rand(4 * D, device="cuda", generator=g) * (math.log(0.1) - math.log(0.001)) + math.log(0.001))
+            bias = (dtv + torch.log(-torch.expm1(-dtv))).contiguous()
+            A = -torch.arange(1, N + 1, device="cuda", dtype=torch.float32).repeat(4 * D, 1).contiguous()
+            Dp = torch.ones(4 * D, device="cuda")
+            xdbl = torch.empty(B, 4, L, (R + 2 * N) if fuse else 2 * N, device="cuda")
+            dts = None if fuse else torch.empty(B, 4, L, D, device="cuda", dtype=dt)
+            ms = timeit(lambda: ops.x_proj_tm(xs, xw16, xdbl, None if fuse else dw16, dts, None if fuse else bias, B, D, L, R, N, Rp, fuse), args.iters)
+            report("x_proj_tm" + ("" if fuse else "+dt"), f"{B}x{D}x{L} R{R} N{N}", ms,
+                   (B * 4.0 * D * L * es + B * 4.0 * (R + 2 * N) * L * 4) if fuse else (2.0 * B * 4 * D * L * es + 2.0 * B * 4 * N * L * 4),
+                   2.0 * B * 4 * L * D * ((R + 2 * N) if fuse else (2 * R + 2 * N)))
+            plan = ops.scan_tm_plan(B, D, H, H, N, R if fuse else 0)
+            carry = torch.empty(B * 4 * max(plan, 1) * 2 * N * D, device="cuda")
+            y = torch.empty(B, H * H, D, device="cuda", dtype=dt)
+            dtw = Wd.reshape(4 * D, R).contiguous()
+            ms = timeit(lambda: ops.selective_scan_tm(xs, dts, xdbl, A, dtw if fuse else None, bias if fuse else None, Dp, carry, y, B, D, H, H,
+                                                      N, R if fuse else 0, plan), args.iters)
+            report(f"scan_tm {'TW' + str(-plan) if plan < 0 else 'S' + str(plan)}", f"{B}x{4 * D}x{L} N{N}", ms,
+                   3.0 * B * 4 * D * L * es + 2.0 * B * 4 * N * L * 4, 9.0 * B * 4 * D * L * N)
+            del xz, xs, xdbl, dts, carry, y
     if args.only in ("", "norm"):
         from founddiff_b200.engine import _view_ptr
         for C, H, _ in LEVELS[:3]:
@@ -147,8 +180,10 @@ def main():
             report("ln_modulate", f"{B}x{P}x{C}", ms, 2.0 * B * P * C * es)
             sums = torch.zeros(B, 8, 2, device="cuda")
             ops.gn_stats(x, sums, B, P, C, 8)
-            ms = timeit(lambda: ops.gn_silu_add(x, sums, gm, bt, x, out, B, P, C, 8), args.iters)
+            skip = rn(B, P, C)               # its own tensor: with skip == x the kernel moved 2 tensors while 3 were counted
+            ms = timeit(lambda: ops.gn_silu_add(x, sums, gm, bt, skip, out, B, P, C, 8), args.iters)
             report("gn_silu_add", f"{B}x{P}x{C}", ms, 3.0 * B * P * C * es)
+            del skip
     if args.only in ("", "conv"):
         # (c0, c1, cout, k, stride, up, H, epilogue) of representative call sites of one Unet evaluation
         CONVS = [(64, 0, 256, 1, 1, False, 512, "silu_half"), (64, 0, 192, 1, 1, False, 512, "plain"),
