@@ -771,10 +771,283 @@ int scan_tw_launch(const void* u_tm, const float* xdbl, const float* A, const fl
     return 0;
 }
 
+// =========================================================================================================
+// K3c: the time-sliced scan rewritten around PACKED fp32 arithmetic (fma / mul .f32x2 = FFMA2 / FMUL2 on sm_100a).
+// Measured on B200 (tools/probes/pipe_rates.cu): a warp-wide FFMA2 occupies the FMA pipe for 2 clk but ONE issue slot,
+// MUFU.EX2 runs at 16 lanes / clk / SM (one warp instruction per 8 clk and scheduler) — so a state update
+// (FMUL, EX2, FMUL, FFMA, FFMA [+ FMUL, FMUL, FFMA of the time-slice fix-up]) is MUFU-bound as soon as it costs fewer than
+// 8 issue slots, and K3b (ncu: 96 instructions per channel-step, 69 % of the issue slots busy) was bound by issue.  Here the
+// states of a lane live as pairs (n, n + 1) in 64-bit registers: decay argument, input term, recurrence, output dot product,
+// running product and fix-up row are one packed instruction per PAIR, the softplus of two steps shares its non-MUFU
+// arithmetic the same way, B / C / dt-input rows arrive as LDS.128 = two ready-made pairs, and (P, h) of a slice travel
+// through shared memory as 64-bit words.  Same algorithm, same association order as K3b (results agree to the last
+// re-association), and only for geometries where no slice is ragged or straddles an EfficientMerge row: L % (TW ST) == 0
+// and the merge row length (W/2 resp. H/2) a multiple of ST — everything else takes K3b.
+typedef unsigned long long u64;
+FD_DEVINL u64 f2_pack(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+FD_DEVINL void f2_unpack(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+FD_DEVINL u64 f2_fma(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+FD_DEVINL u64 f2_mul(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+FD_DEVINL u64 f2_add(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// tm_softplus on two values at once: 4 MUFU + 2 FMNMX clamps + 2 FMNMX + 7 packed ops (15 issue slots for two, 11 each before)
+FD_DEVINL void tm_softplus2(float x0, float x1, float& d0, float& d1) {
+    const u64 xa = f2_mul(f2_pack(fminf(x0, 80.f), fminf(x1, 80.f)), f2_pack(1.4426950408889634f, 1.4426950408889634f));
+    float a0, a1;
+    f2_unpack(xa, a0, a1);
+    const float y0 = tm_ex2(a0), y1 = tm_ex2(a1);
+    const u64 y = f2_pack(y0, y1);
+    const u64 w = f2_add(y, f2_pack(1.f, 1.f));
+    const u64 wm1 = f2_add(w, f2_pack(-1.f, -1.f));
+    const u64 lost = f2_fma(wm1, f2_pack(-1.f, -1.f), y);                              // y - (w - 1), exact for y < 1
+    const u64 fac = f2_fma(f2_pack(fminf(y0, 1.f), fminf(y1, 1.f)), f2_pack(-1.f, -1.f), f2_pack(1.f, 1.f));
+    const u64 corr = f2_mul(lost, fac);
+    float w0, w1;
+    f2_unpack(w, w0, w1);
+    const u64 r = f2_fma(f2_pack(tm_lg2(w0), tm_lg2(w1)), f2_pack(0.6931471805599453f, 0.6931471805599453f), corr);
+    f2_unpack(r, d0, d1);
+}
+
+// VAR bit 0: y_local kept in shared memory instead of ST registers; bit 1: delta of the whole slice formed ahead of the recurrence
+// (ST / 2 independent softplus chains in flight instead of SB / 2); bit 2: two half-slices per warp scanned in lockstep
+template <typename T, int NS, int RDT, int ST, int TW, int VAR>
+__global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
+    const T* __restrict__ u_tm, const float* __restrict__ xdbl, const float* __restrict__ A, const float* __restrict__ dt_w,
+    const float* __restrict__ dt_bias, const float* __restrict__ Dskip, T* __restrict__ y, int D, int L, int H, int W) {
+    constexpr int XR = RDT + 2 * NS;
+    constexpr int CH = TW * ST;                          // steps per chunk
+    constexpr int NP = NS / 2, RP = RDT / 2, NQ = NS / 4;
+    constexpr int SB = NS <= 4 ? 4 : 2;                  // steps whose decay factors are issued ahead of the recurrence
+    constexpr bool YL_SMEM = VAR & 1, DT_AHEAD = (VAR & 2) != 0;
+    constexpr int NSL = (VAR & 4) ? 2 : 1, STS = ST / NSL;  // half-slices scanned in lockstep by one warp
+    constexpr int GS = NQ * 128 + (YL_SMEM ? 32 : 0);    // floats per step in s_g: NQ planes of one float4 per lane [+ one y_local per lane]
+    static_assert(ST % SB == 0 && SB % NSL == 0 && NS % 4 == 0 && RDT % 4 == 0 && RDT > 0, "step blocks, float4 rows");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_g = reinterpret_cast<float*>(smem_raw);     // [TW][ST][GS]   fix-up rows C * prod(a)
+    float* s_x = s_g + TW * ST * GS;                // [TW][ST][XR]
+    u64* s_ph = reinterpret_cast<u64*>(s_x + TW * ST * XR);   // [2][TW][2 NP][32]  (P pairs | h pairs) of a slice
+    u64* s_cy = s_ph + 2 * TW * 2 * NP * 32;             // [2][NP][32]           state entering a chunk
+    T* s_u = reinterpret_cast<T*>(s_cy + 2 * NP * 32);   // [TW][ST][32]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bk = blockIdx.y, k = bk & 3, b = bk >> 2;
+    const int ch0 = blockIdx.x * 32;
+    const int dloc = ch0 + lane;
+    const int d = k * D + dloc;
+    const T* ug = u_tm + (long)bk * L * D + ch0;
+    const float* xg = xdbl + (long)bk * L * XR;
+    float* gw = s_g + warp * ST * GS + lane * 4;
+    float* ylw = s_g + warp * ST * GS + NQ * 128 + lane;
+    float* xw = s_x + warp * ST * XR;
+    T* uw = s_u + warp * ST * 32;
+
+    u64 A2[NP], wdt[RP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) A2[j] = f2_pack(A[(long)d * NS + 2 * j] * 1.4426950408889634f, A[(long)d * NS + 2 * j + 1] * 1.4426950408889634f);
+#pragma unroll
+    for (int r = 0; r < RP; ++r) wdt[r] = f2_pack(dt_w[(long)d * RDT + 2 * r], dt_w[(long)d * RDT + 2 * r + 1]);
+    const u64 bias2 = f2_pack(dt_bias[d], 0.f);
+    const float Dd = Dskip[d];
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) s_cy[j * 32 + lane] = 0ull;          // entry state of chunk 0 (published by the first barrier)
+    }
+
+    auto stage = [&](int t0) {                           // this warp's slice [t0, t0 + ST)
+        for (int i = lane; i < ST * XR / 4; i += 32) tm_cp_async16(xw + i * 4, xg + (long)t0 * XR + i * 4, true);
+        for (int i = lane; i < ST * 4; i += 32) {        // u: ST rows of 32 channels = 4 x 16 bytes each
+            const int r = i >> 2, v = i & 3;
+            tm_cp_async16(uw + r * 32 + v * 8, ug + (long)(t0 + r) * D + v * 8, true);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto dt_raw = [&](int i) {                           // dt_proj of step i of the staged slice (+ bias), before the softplus
+        u64 p = bias2;
+#pragma unroll
+        for (int r = 0; r < RP; r += 2) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(xw + i * XR + 2 * r);
+            p = f2_fma(wdt[r], v.x, p);
+            p = f2_fma(wdt[r + 1], v.y, p);
+        }
+        float plo, phi;
+        f2_unpack(p, plo, phi);
+        return plo + phi;
+    };
+
+    // EfficientMerge position of this warp's slice, advanced by CH steps per chunk (no division in the loop): slices never
+    // straddle a merge row here, so inside a slice the store address moves by a constant stride.
+    const int col = k & 1, kx = k >> 1;
+    const int mdiv = col ? (H >> 1) : (W >> 1);
+    int mq = (warp * ST) / mdiv, mr = (warp * ST) - mq * mdiv;
+    const int inc = col ? 2 * W * D : 2 * D;
+    T* ybase = y + (long)b * H * W * D + dloc;
+    const int nchunks = L / CH;
+    stage(warp * ST);
+    for (int c = 0; c < nchunks; ++c) {
+        const int t0 = c * CH + warp * ST;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        // ---- phase A: local scan(s) of the slice from h = 0.  NSL = 2: the slice is two half-slices scanned in lockstep (two
+        // independent recurrences per lane: twice the instruction-level parallelism for 2 NS more registers)
+        u64 hl[NSL][NP], P[NSL][NP];
+        float yl[YL_SMEM ? 1 : ST];
+        float dta[DT_AHEAD ? ST : 1];
+#pragma unroll
+        for (int s = 0; s < NSL; ++s)
+#pragma unroll
+            for (int j = 0; j < NP; ++j) { hl[s][j] = 0ull; P[s][j] = f2_pack(1.f, 1.f); }
+        if constexpr (DT_AHEAD) {
+#pragma unroll
+            for (int i = 0; i < ST; ++i) dta[i] = dt_raw(i);
+#pragma unroll
+            for (int i = 0; i < ST; i += 2) tm_softplus2(dta[i], dta[i + 1], dta[i], dta[i + 1]);
+        }
+#pragma unroll
+        for (int i0 = 0; i0 < STS; i0 += SB / NSL) {
+            float dt[SB], u[SB];
+#pragma unroll
+            for (int q = 0; q < SB; ++q) {               // in-flight step q: half-slice q % NSL, step i0 + q / NSL of it
+                const int st = (q % NSL) * STS + i0 + q / NSL;
+                dt[q] = DT_AHEAD ? dta[DT_AHEAD ? st : 0] : dt_raw(st);
+                u[q] = tm_ld16<T>(uw + st * 32 + lane);
+            }
+            if constexpr (!DT_AHEAD) {
+#pragma unroll
+                for (int q = 0; q < SB; q += 2) tm_softplus2(dt[q], dt[q + 1], dt[q], dt[q + 1]);
+            }
+            u64 a[SB][NP];
+#pragma unroll
+            for (int q = 0; q < SB; ++q) {
+                const u64 dt2 = f2_pack(dt[q], dt[q]);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {
+                    float e0, e1;
+                    f2_unpack(f2_mul(dt2, A2[j]), e0, e1);
+                    a[q][j] = f2_pack(tm_ex2(e0), tm_ex2(e1));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < SB; ++q) {
+                const int sl = q % NSL, st = sl * STS + i0 + q / NSL;
+                const float* xr = xw + st * XR + RDT;
+                const float du = dt[q] * u[q];
+                const u64 du2 = f2_pack(du, du);
+                u64 ya = 0ull;
+#pragma unroll
+                for (int jq = 0; jq < NQ; ++jq) {
+                    const ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(xr + 4 * jq);
+                    const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(xr + NS + 4 * jq);
+                    const int j = 2 * jq;
+                    hl[sl][j] = f2_fma(a[q][j], hl[sl][j], f2_mul(du2, b2.x));
+                    hl[sl][j + 1] = f2_fma(a[q][j + 1], hl[sl][j + 1], f2_mul(du2, b2.y));
+                    ya = jq == 0 ? f2_mul(hl[sl][j], c2.x) : f2_fma(hl[sl][j], c2.x, ya);
+                    ya = f2_fma(hl[sl][j + 1], c2.y, ya);
+                    P[sl][j] = f2_mul(P[sl][j], a[q][j]);
+                    P[sl][j + 1] = f2_mul(P[sl][j + 1], a[q][j + 1]);
+                    ulonglong2 g2;
+                    g2.x = f2_mul(c2.x, P[sl][j]);
+                    g2.y = f2_mul(c2.y, P[sl][j + 1]);
+                    *reinterpret_cast<ulonglong2*>(gw + st * GS + jq * 128) = g2;
+                }
+                float ylo, yhi;
+                f2_unpack(ya, ylo, yhi);
+                const float yv = fmaf(Dd, u[q], ylo) + yhi;
+                if constexpr (YL_SMEM) ylw[st * GS] = yv;
+                else yl[YL_SMEM ? 0 : st] = yv;
+            }
+        }
+        {                                                // (P, h) of the whole slice: the half-slices composed
+            u64* ph = s_ph + ((c & 1) * TW + warp) * 2 * NP * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                ph[j * 32] = NSL == 2 ? f2_mul(P[0][j], P[NSL - 1][j]) : P[0][j];
+                ph[(NP + j) * 32] = NSL == 2 ? f2_fma(P[NSL - 1][j], hl[0][j], hl[NSL - 1][j]) : hl[0][j];
+            }
+        }
+        __syncwarp();                                    // every lane is done reading the staged slice
+        if (c + 1 < nchunks) stage(t0 + CH);
+        __syncthreads();                                 // slices (and the entry state) of chunk c are published
+        // ---- fold: state entering this warp's slice (and its second half)
+        u64 hin[NSL][NP];
+        {
+            const u64* cy = s_cy + (c & 1) * NP * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) hin[0][j] = cy[j * 32];
+            for (int jw = 0; jw < warp; ++jw) {
+                const u64* ph = s_ph + ((c & 1) * TW + jw) * 2 * NP * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) hin[0][j] = f2_fma(ph[j * 32], hin[0][j], ph[(NP + j) * 32]);
+            }
+            if constexpr (NSL == 2) {
+#pragma unroll
+                for (int j = 0; j < NP; ++j) hin[NSL - 1][j] = f2_fma(P[0][j], hin[0][j], hl[0][j]);
+            }
+        }
+        if (warp == TW - 1) {                            // exit state of the chunk = entry state of the next one
+            u64* cy = s_cy + ((c + 1) & 1) * NP * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) cy[j * 32] = f2_fma(P[NSL - 1][j], hin[NSL - 1][j], hl[NSL - 1][j]);
+        }
+        // ---- fix-up + EfficientMerge store
+        {
+            T* yp = ybase + (col ? ((long)(2 * mr + 1) * W + 2 * mq + kx) * D : ((long)(2 * mq) * W + 2 * mr + kx) * D);
+#pragma unroll
+            for (int i = 0; i < ST; ++i) {
+                const int sl = i / STS;
+                u64 f = 0ull;
+#pragma unroll
+                for (int jq = 0; jq < NQ; ++jq) {
+                    const ulonglong2 g2 = *reinterpret_cast<const ulonglong2*>(gw + i * GS + jq * 128);
+                    f = jq == 0 ? f2_mul(g2.x, hin[sl][0]) : f2_fma(g2.x, hin[sl][2 * jq], f);
+                    f = f2_fma(g2.y, hin[sl][2 * jq + 1], f);
+                }
+                float flo, fhi;
+                f2_unpack(f, flo, fhi);
+                const float y0 = YL_SMEM ? ylw[i * GS] : yl[YL_SMEM ? 0 : i];
+                fd_st(yp + (long)i * inc, (y0 + flo) + fhi);
+            }
+            mr += CH;
+            while (mr >= mdiv) { mr -= mdiv; ++mq; }
+        }
+    }
+}
+
+template <typename T, int NS, int RDT, int ST, int TW, int VAR>
+int scan_tw2_launch_v(const void* u_tm, const float* xdbl, const float* A, const float* dt_w, const float* dt_bias, const float* Dskip,
+                      void* y, int B, int D, int H, int W, cudaStream_t st) {
+    const int L = (H / 2) * (W / 2);
+    constexpr int XR = RDT + 2 * NS, GS = NS * 32 + ((VAR & 1) ? 32 : 0);
+    const size_t smem = ((size_t)TW * ST * GS + (size_t)TW * ST * XR) * sizeof(float) +
+                        ((size_t)2 * TW * NS * 32 + NS * 32) * sizeof(u64) + (size_t)TW * ST * 32 * sizeof(T);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(scan_tw2_kernel<T, NS, RDT, ST, TW, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    scan_tw2_kernel<T, NS, RDT, ST, TW, VAR><<<dim3(D / 32, B * 4), TW * 32, smem, st>>>((const T*)u_tm, xdbl, A, dt_w, dt_bias, Dskip, (T*)y, D, L, H, W);
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+template <typename T, int NS, int RDT, int ST, int TW>
+int scan_tw2_launch(const void* u_tm, const float* xdbl, const float* A, const float* dt_w, const float* dt_bias, const float* Dskip,
+                    void* y, int B, int D, int H, int W, cudaStream_t st) {
+    // measured at B = 16 (profiles/r2_scan_tw2_notes.txt): delta formed ahead (VAR 2) 1705 us vs 1730 at the level-0 shape; y_local in
+    // shared memory (bit 0) 1838 and two half-slices in lockstep (bit 2) 1738 — the kernel is bound by the shared-memory data pipe
+    // (19 wavefronts per warp-step), not by registers or by the recurrence's latency, so neither helps
+    return scan_tw2_launch_v<T, NS, RDT, ST, TW, 2>(u_tm, xdbl, A, dt_w, dt_bias, Dskip, y, B, D, H, W, st);
+}
+
+// K3c applies when no slice is ragged and no slice straddles an EfficientMerge row
+static bool tw2_ok(int H, int W, int ST, int TW) {
+    static const int off = getenv("FD_SCAN_TW2") ? atoi(getenv("FD_SCAN_TW2")) == 0 : 0;
+    const int L = (H / 2) * (W / 2);
+    return !off && L % (TW * ST) == 0 && (W / 2) % ST == 0 && (H / 2) % ST == 0;
+}
+
 // Which scan a geometry gets: 0 = segmented channel-per-lane (scan_tm_kernel), 8 / 4 = time-sliced with that many warps.
 // The time-sliced kernel needs ALL its blocks resident at once (a block walks a whole row): 2 blocks per SM with 8 warps,
 // 4 with 4 warps; it only exists for the fused-dt small-state levels.
-int pick_time_warps(int B, int D, int L, int NS, int RDT) {
+int pick_time_warps(int B, int D, int H2, int W2, int NS, int RDT) {
+    const int L = H2 * W2;
     static const int forced = getenv("FD_SCAN_TW") ? atoi(getenv("FD_SCAN_TW")) : -1;
     if (RDT == 0 || NS > 8) return 0;
     if (forced >= 0) return forced;
@@ -786,6 +1059,8 @@ int pick_time_warps(int B, int D, int L, int NS, int RDT) {
     // measured (profiles/r2_scan_tm_variants.json): with >= 512 channel-warps one unsegmented pass is faster than either
     // form of time parallelism (16x256x16384 N8: 1.57 ms vs 1.95 time-sliced x4 vs 1.73 with 4 segments)
     if (blocks <= 2L * sms) return 8;
+    // 16x256x16384 N8 R8 (512 blocks): the packed time-sliced kernel with 4 warps per block (4 blocks per SM) 1.49 ms vs 1.57 unsegmented
+    if (NS == 8 && blocks <= 4L * sms && tw2_ok(2 * H2, 2 * W2, 8, 4)) return 4;
     return 0;
 }
 
@@ -900,7 +1175,7 @@ extern "C" int fd_x_proj_tm(const void* xs_tm, const void* xw16, float* xdbl_tm,
 extern "C" int fd_scan_tm_plan(int B, int D, int H, int W, int dstate, int dt_rank_fused) {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
     const int L = (H / 2) * (W / 2);
-    const int tw = pick_time_warps(B, D, L, dstate, dt_rank_fused);
+    const int tw = pick_time_warps(B, D, H / 2, W / 2, dstate, dt_rank_fused);
     if (tw) return -tw;
     int S = pick_segments(B, D, L);
     const int seg_len = ((L + S - 1) / S + SC_T - 1) / SC_T * SC_T;
@@ -925,8 +1200,18 @@ extern "C" int fd_selective_scan_tm(const void* u_tm, const void* dts_tm, const 
     if (D % SC_CHB || (((uintptr_t)u_tm | (uintptr_t)dts_tm | (uintptr_t)xdbl_tm) & 15)) return FD_ERR_UNSUPPORTED;
     const int L = (H / 2) * (W / 2);
     if (segments <= 0) {                                 // 0 = automatic: time-sliced kernel where rows are few and long; -8 / -4 = forced
-        const int tw = segments < 0 ? -segments : pick_time_warps(B, D, L, dstate, dt_rank_fused);
+        // -8 / -4: time-sliced kernel, packed form (K3c) where the geometry allows; -1008 / -1004: K3b forced
+        const bool force_b = segments <= -1000;
+        const int tw = segments < 0 ? -(segments % 1000) : pick_time_warps(B, D, H / 2, W / 2, dstate, dt_rank_fused);
         if (segments < 0 && tw != 8 && tw != 4) return FD_ERR_BAD_ARGUMENT;
+#define SCTW2_CASE(NSV, RV, STV, TWV)                                                                                              \
+    if (!force_b && tw == TWV && dstate == NSV && dt_rank_fused == RV && tw2_ok(H, W, STV, TWV)) {                                 \
+        if (io_dtype == FD_BF16) return scan_tw2_launch<__nv_bfloat16, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, stream); \
+        if (io_dtype == FD_F16) return scan_tw2_launch<__half, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, stream); \
+        return FD_ERR_UNSUPPORTED;                                                                                                 \
+    }
+        SCTW2_CASE(4, 4, 16, 8) SCTW2_CASE(4, 4, 16, 4) SCTW2_CASE(8, 4, 8, 8) SCTW2_CASE(8, 4, 8, 4) SCTW2_CASE(8, 8, 8, 8) SCTW2_CASE(8, 8, 8, 4)
+#undef SCTW2_CASE
 #define SCTW_CASE(NSV, RV, STV, TWV)                                                                                               \
     if (tw == TWV && dstate == NSV && dt_rank_fused == RV) {                                                                       \
         if (io_dtype == FD_BF16) return scan_tw_launch<__nv_bfloat16, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, stream); \

@@ -115,7 +115,7 @@ def _scan_case(ops, H, W, D, N, R, fuse, dt, segments, slow=False, B=2, seed=0):
 @pytest.mark.parametrize("cfg", [(16, 24, 128, 4, 4, True), (64, 64, 128, 8, 4, True), (32, 48, 256, 8, 8, True), (24, 40, 256, 16, 8, True),
                                  (16, 16, 512, 16, 16, False), (8, 12, 1024, 32, 32, False), (6, 10, 128, 4, 4, True),
                                  (32, 32, 128, 8, 8, False), (2, 2, 128, 4, 4, True)])
-@pytest.mark.parametrize("segments", [1, 3, 0, -8, -4])
+@pytest.mark.parametrize("segments", [1, 3, 0, -8, -4, -1008, -1004])
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 def test_scan_time_major_vs_oracle(ops, cfg, segments, dt):
     H, W, D, N, R, fuse = cfg
@@ -126,7 +126,7 @@ def test_scan_time_major_vs_oracle(ops, cfg, segments, dt):
 
 
 @pytest.mark.parametrize("slow", [False, True])
-@pytest.mark.parametrize("segments", [1, 2, 8, 16, -8, -4, 0])
+@pytest.mark.parametrize("segments", [1, 2, 8, 16, -8, -4, -1008, 0])
 def test_scan_time_major_segments_are_exact(ops, segments, slow):
     """Long rows (L = 16384) cut into 1 / 2 / 8 / 16 segments give the same answer as the sequential recurrence — including
     channels whose memory is far longer than a segment (A scaled by 1e-3, small delta), where the carry pass cannot stop early
