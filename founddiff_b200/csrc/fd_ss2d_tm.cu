@@ -351,6 +351,14 @@ __global__ void __launch_bounds__(256) x_proj_tm_kernel(const T* __restrict__ xs
     }
 }
 
+// packed fp32 pairs in 64-bit registers (fma / mul / add .f32x2 = FFMA2 / FMUL2 / FADD2 on sm_100a: one issue slot, two results)
+typedef unsigned long long u64;
+FD_DEVINL u64 f2_pack(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+FD_DEVINL void f2_unpack(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+FD_DEVINL u64 f2_fma(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+FD_DEVINL u64 f2_mul(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+FD_DEVINL u64 f2_add(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 template <typename T> FD_DEVINL float tm_ld16(const T* p) {
     if constexpr (std::is_same<T, __nv_bfloat16>::value) return __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(p)) << 16);
     else return __half2float(*p);
@@ -531,6 +539,9 @@ __global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
 #pragma unroll
             for (int n = 0; n < NS; ++n) h[n] = fmaf(cb[(long)(NS + n) * D], h[n], cb[(long)n * D]);
         }
+        u64 hp[NS / 2], A2p[NS / 2];
+#pragma unroll
+        for (int j = 0; j < NS / 2; ++j) { hp[j] = f2_pack(h[2 * j], h[2 * j + 1]); A2p[j] = f2_pack(A2[2 * j], A2[2 * j + 1]); }
         MergeWalk mw;
         mw.init(k, t_begin, H, W, D);
         T* ybase = y + (long)b * H * W * D + dloc;
@@ -546,39 +557,58 @@ __global__ void __launch_bounds__(SC_CHB, (NS >= 16 ? 4 : 6)) scan_tm_kernel(
             const T* sd = s_d + buf * SC_T * SC_CHB + tid;
             auto run = [&](auto mask_c) {
                 constexpr bool MASK = decltype(mask_c)::value;
-#pragma unroll 2
+#pragma unroll(NS >= 32 ? 1 : 2)
                 for (int s0 = 0; s0 < SC_T; s0 += 4) {
                     if (MASK && s0 >= ns) break;
                     float dt[4], u[4];
                     load_steps4<T, NS, RDT, XR, SC_CHB, MASK>(sx + s0 * XR, su + s0 * SC_CHB, sd + s0 * SC_CHB, wdt, bias, ns - s0, dt, u);
-                    float a[PRE_A ? 4 : 1][PRE_A ? NS : 1];
+                    // states as pairs (n, n + 1): decay argument, input term, recurrence and output dot product are one packed
+                    // instruction per pair (3 issue slots per state update instead of 5; the update is then bound by MUFU.EX2
+                    // alone: tools/probes/pipe_rates.cu)
+                    u64 a[PRE_A ? 4 : 1][PRE_A ? NS / 2 : 1];
                     if constexpr (PRE_A) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
+                        for (int q = 0; q < 4; ++q) {
+                            const u64 dt2 = f2_pack(dt[q], dt[q]);
 #pragma unroll
-                            for (int n = 0; n < NS; ++n) a[q][n] = tm_ex2(dt[q] * A2[n]);
+                            for (int j = 0; j < NS / 2; ++j) {
+                                float e0, e1;
+                                f2_unpack(f2_mul(dt2, A2p[j]), e0, e1);
+                                a[q][j] = f2_pack(tm_ex2(e0), tm_ex2(e1));
+                            }
+                        }
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float du = dt[q] * u[q];
+                        const u64 du2 = f2_pack(du, du), dt2 = f2_pack(dt[q], dt[q]);
                         const float* pb = sx + (s0 + q) * XR + RDT;
                         const float* pc = pb + NS;
-                        float y0 = Dd * u[q], y1 = 0.f, y2 = 0.f, y3 = 0.f;
+                        u64 ya = 0ull, yb = 0ull;
 #pragma unroll
                         for (int n = 0; n < NS; n += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(pb + n);
-                            const float4 c4 = *reinterpret_cast<const float4*>(pc + n);
-                            h[n] = fmaf(PRE_A ? a[PRE_A ? q : 0][PRE_A ? n : 0] : tm_ex2(dt[q] * A2[n]), h[n], du * b4.x);
-                            y0 = fmaf(h[n], c4.x, y0);
-                            h[n + 1] = fmaf(PRE_A ? a[PRE_A ? q : 0][PRE_A ? n + 1 : 0] : tm_ex2(dt[q] * A2[n + 1]), h[n + 1], du * b4.y);
-                            y1 = fmaf(h[n + 1], c4.y, y1);
-                            h[n + 2] = fmaf(PRE_A ? a[PRE_A ? q : 0][PRE_A ? n + 2 : 0] : tm_ex2(dt[q] * A2[n + 2]), h[n + 2], du * b4.z);
-                            y2 = fmaf(h[n + 2], c4.z, y2);
-                            h[n + 3] = fmaf(PRE_A ? a[PRE_A ? q : 0][PRE_A ? n + 3 : 0] : tm_ex2(dt[q] * A2[n + 3]), h[n + 3], du * b4.w);
-                            y3 = fmaf(h[n + 3], c4.w, y3);
+                            const ulonglong2 b2 = *reinterpret_cast<const ulonglong2*>(pb + n);
+                            const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(pc + n);
+                            u64 a0, a1;
+                            if constexpr (PRE_A) {
+                                a0 = a[PRE_A ? q : 0][PRE_A ? n / 2 : 0];
+                                a1 = a[PRE_A ? q : 0][PRE_A ? n / 2 + 1 : 0];
+                            } else {
+                                float e0, e1, e2, e3;
+                                f2_unpack(f2_mul(dt2, A2p[n / 2]), e0, e1);
+                                f2_unpack(f2_mul(dt2, A2p[n / 2 + 1]), e2, e3);
+                                a0 = f2_pack(tm_ex2(e0), tm_ex2(e1));
+                                a1 = f2_pack(tm_ex2(e2), tm_ex2(e3));
+                            }
+                            hp[n / 2] = f2_fma(a0, hp[n / 2], f2_mul(du2, b2.x));
+                            hp[n / 2 + 1] = f2_fma(a1, hp[n / 2 + 1], f2_mul(du2, b2.y));
+                            ya = n == 0 ? f2_mul(hp[0], c2.x) : f2_fma(hp[n / 2], c2.x, ya);
+                            yb = n == 0 ? f2_mul(hp[1], c2.y) : f2_fma(hp[n / 2 + 1], c2.y, yb);
                         }
                         if (!MASK || s0 + q < ns) {
-                            fd_st(ybase + mw.off, (y0 + y1) + (y2 + y3));
+                            float y0, y1;
+                            f2_unpack(f2_add(ya, yb), y0, y1);
+                            fd_st(ybase + mw.off, fmaf(Dd, u[q], y0) + y1);
                             mw.next();
                         }
                     }
@@ -783,12 +813,6 @@ int scan_tw_launch(const void* u_tm, const float* xdbl, const float* A, const fl
 // through shared memory as 64-bit words.  Same algorithm, same association order as K3b (results agree to the last
 // re-association), and only for geometries where no slice is ragged or straddles an EfficientMerge row: L % (TW ST) == 0
 // and the merge row length (W/2 resp. H/2) a multiple of ST — everything else takes K3b.
-typedef unsigned long long u64;
-FD_DEVINL u64 f2_pack(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-FD_DEVINL void f2_unpack(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-FD_DEVINL u64 f2_fma(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-FD_DEVINL u64 f2_mul(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-FD_DEVINL u64 f2_add(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 // tm_softplus on two values at once: 4 MUFU + 2 FMNMX clamps + 2 FMNMX + 7 packed ops (15 issue slots for two, 11 each before)
 FD_DEVINL void tm_softplus2(float x0, float x1, float& d0, float& d1) {
     const u64 xa = f2_mul(f2_pack(fminf(x0, 80.f), fminf(x1, 80.f)), f2_pack(1.4426950408889634f, 1.4426950408889634f));
@@ -819,7 +843,10 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
     constexpr int SB = NS <= 4 ? 4 : 2;                  // steps whose decay factors are issued ahead of the recurrence
     constexpr bool YL_SMEM = VAR & 1, DT_AHEAD = (VAR & 2) != 0;
     constexpr int NSL = (VAR & 4) ? 2 : 1, STS = ST / NSL;  // half-slices scanned in lockstep by one warp
-    constexpr int GS = NQ * 128 + (YL_SMEM ? 32 : 0);    // floats per step in s_g: NQ planes of one float4 per lane [+ one y_local per lane]
+    constexpr bool G_TMEM = (VAR & 8) != 0;              // fix-up rows in tensor memory instead of shared memory
+    constexpr int TCOLS = (TW / 4) * ST * NS;            // TMEM columns of the block: per lane quarter, TW / 4 warps x ST steps x NS
+    static_assert(!G_TMEM || (NSL == 1 && !YL_SMEM && (SB * NS == 16) && TCOLS >= 32 && (TCOLS & (TCOLS - 1)) == 0), "TMEM rows: 16 registers per step block");
+    constexpr int GS = G_TMEM ? 0 : NQ * 128 + (YL_SMEM ? 32 : 0);   // floats per step in s_g: NQ planes of one float4 per lane [+ one y_local per lane]
     static_assert(ST % SB == 0 && SB % NSL == 0 && NS % 4 == 0 && RDT % 4 == 0 && RDT > 0, "step blocks, float4 rows");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_g = reinterpret_cast<float*>(smem_raw);     // [TW][ST][GS]   fix-up rows C * prod(a)
@@ -827,6 +854,7 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
     u64* s_ph = reinterpret_cast<u64*>(s_x + TW * ST * XR);   // [2][TW][2 NP][32]  (P pairs | h pairs) of a slice
     u64* s_cy = s_ph + 2 * TW * 2 * NP * 32;             // [2][NP][32]           state entering a chunk
     T* s_u = reinterpret_cast<T*>(s_cy + 2 * NP * 32);   // [TW][ST][32]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_u + TW * ST * 32);   // TMEM base address of the block's allocation
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bk = blockIdx.y, k = bk & 3, b = bk >> 2;
     const int ch0 = blockIdx.x * 32;
@@ -834,6 +862,22 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
     const int d = k * D + dloc;
     const T* ug = u_tm + (long)bk * L * D + ch0;
     const float* xg = xdbl + (long)bk * L * XR;
+    uint32_t tg = 0;                                     // this warp's TMEM window: its lane quarter, ST * NS columns
+    if constexpr (G_TMEM) {
+        // Tensor memory as a per-lane scratchpad.  The fix-up rows are lane-private (written in phase A, read back by the same
+        // lane after the barrier): through shared memory they were 8 of the kernel's 19 wavefronts per warp-step on the one
+        // shared-memory data pipe (profiles/r2_ncu_scan_tw2.txt); tcgen05.st / tcgen05.ld move 16 registers per instruction
+        // on TMEM's own path.  A warp may touch the 32 TMEM lanes of its quarter (warp % 4); warps w and w + 4 share a quarter
+        // and take different columns.
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(s_tmem)), "r"(TCOLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tg = *s_tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)((warp >> 2) * ST * NS);
+    }
     float* gw = s_g + warp * ST * GS + lane * 4;
     float* ylw = s_g + warp * ST * GS + NQ * 128 + lane;
     float* xw = s_x + warp * ST * XR;
@@ -924,6 +968,7 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
                     a[q][j] = f2_pack(tm_ex2(e0), tm_ex2(e1));
                 }
             }
+            float gt[G_TMEM ? 16 : 1];
 #pragma unroll
             for (int q = 0; q < SB; ++q) {
                 const int sl = q % NSL, st = sl * STS + i0 + q / NSL;
@@ -945,7 +990,12 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
                     ulonglong2 g2;
                     g2.x = f2_mul(c2.x, P[sl][j]);
                     g2.y = f2_mul(c2.y, P[sl][j + 1]);
-                    *reinterpret_cast<ulonglong2*>(gw + st * GS + jq * 128) = g2;
+                    if constexpr (G_TMEM) {
+                        f2_unpack(g2.x, gt[q * NS + 4 * jq], gt[q * NS + 4 * jq + 1]);
+                        f2_unpack(g2.y, gt[q * NS + 4 * jq + 2], gt[q * NS + 4 * jq + 3]);
+                    } else {
+                        *reinterpret_cast<ulonglong2*>(gw + st * GS + jq * 128) = g2;
+                    }
                 }
                 float ylo, yhi;
                 f2_unpack(ya, ylo, yhi);
@@ -953,7 +1003,13 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
                 if constexpr (YL_SMEM) ylw[st * GS] = yv;
                 else yl[YL_SMEM ? 0 : st] = yv;
             }
+            if constexpr (G_TMEM) {                      // the SB steps' rows (16 registers) in one tcgen05.st: columns [i0 NS, +16)
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(tg + (uint32_t)(i0 * NS)),
+                             "f"(gt[0]), "f"(gt[1]), "f"(gt[2]), "f"(gt[3]), "f"(gt[4]), "f"(gt[5]), "f"(gt[6]), "f"(gt[7]), "f"(gt[8]), "f"(gt[9]),
+                             "f"(gt[10]), "f"(gt[11]), "f"(gt[12]), "f"(gt[13]), "f"(gt[14]), "f"(gt[15]) : "memory");
+            }
         }
+        if constexpr (G_TMEM) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         {                                                // (P, h) of the whole slice: the half-slices composed
             u64* ph = s_ph + ((c & 1) * TW + warp) * 2 * NP * 32 + lane;
 #pragma unroll
@@ -989,13 +1045,29 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
         // ---- fix-up + EfficientMerge store
         {
             T* yp = ybase + (col ? ((long)(2 * mr + 1) * W + 2 * mq + kx) * D : ((long)(2 * mq) * W + 2 * mr + kx) * D);
+            float gl[G_TMEM ? 16 : 1];
 #pragma unroll
             for (int i = 0; i < ST; ++i) {
                 const int sl = i / STS;
+                if constexpr (G_TMEM) {
+                    if (i % SB == 0) {
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                     : "=f"(gl[0]), "=f"(gl[1]), "=f"(gl[2]), "=f"(gl[3]), "=f"(gl[4]), "=f"(gl[5]), "=f"(gl[6]), "=f"(gl[7]), "=f"(gl[8]),
+                                       "=f"(gl[9]), "=f"(gl[10]), "=f"(gl[11]), "=f"(gl[12]), "=f"(gl[13]), "=f"(gl[14]), "=f"(gl[15])
+                                     : "r"(tg + (uint32_t)(i * NS)));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
+                }
                 u64 f = 0ull;
 #pragma unroll
                 for (int jq = 0; jq < NQ; ++jq) {
-                    const ulonglong2 g2 = *reinterpret_cast<const ulonglong2*>(gw + i * GS + jq * 128);
+                    ulonglong2 g2;
+                    if constexpr (G_TMEM) {
+                        g2.x = f2_pack(gl[(i % SB) * NS + 4 * jq], gl[(i % SB) * NS + 4 * jq + 1]);
+                        g2.y = f2_pack(gl[(i % SB) * NS + 4 * jq + 2], gl[(i % SB) * NS + 4 * jq + 3]);
+                    } else {
+                        g2 = *reinterpret_cast<const ulonglong2*>(gw + i * GS + jq * 128);
+                    }
                     f = jq == 0 ? f2_mul(g2.x, hin[sl][0]) : f2_fma(g2.x, hin[sl][2 * jq], f);
                     f = f2_fma(g2.y, hin[sl][2 * jq + 1], f);
                 }
@@ -1008,15 +1080,20 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
             while (mr >= mdiv) { mr -= mdiv; ++mq; }
         }
     }
+    if constexpr (G_TMEM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*s_tmem), "r"(TCOLS));
+    }
 }
 
 template <typename T, int NS, int RDT, int ST, int TW, int VAR>
 int scan_tw2_launch_v(const void* u_tm, const float* xdbl, const float* A, const float* dt_w, const float* dt_bias, const float* Dskip,
                       void* y, int B, int D, int H, int W, cudaStream_t st) {
     const int L = (H / 2) * (W / 2);
-    constexpr int XR = RDT + 2 * NS, GS = NS * 32 + ((VAR & 1) ? 32 : 0);
+    constexpr int XR = RDT + 2 * NS, GS = (VAR & 8) ? 0 : NS * 32 + ((VAR & 1) ? 32 : 0);
     const size_t smem = ((size_t)TW * ST * GS + (size_t)TW * ST * XR) * sizeof(float) +
-                        ((size_t)2 * TW * NS * 32 + NS * 32) * sizeof(u64) + (size_t)TW * ST * 32 * sizeof(T);
+                        ((size_t)2 * TW * NS * 32 + NS * 32) * sizeof(u64) + (size_t)TW * ST * 32 * sizeof(T) + 16;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(scan_tw2_kernel<T, NS, RDT, ST, TW, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1033,7 +1110,9 @@ int scan_tw2_launch(const void* u_tm, const float* xdbl, const float* A, const f
     // measured at B = 16 (profiles/r2_scan_tw2_notes.txt): delta formed ahead (VAR 2) 1705 us vs 1730 at the level-0 shape; y_local in
     // shared memory (bit 0) 1838 and two half-slices in lockstep (bit 2) 1738 — the kernel is bound by the shared-memory data pipe
     // (19 wavefronts per warp-step), not by registers or by the recurrence's latency, so neither helps
-    return scan_tw2_launch_v<T, NS, RDT, ST, TW, 2>(u_tm, xdbl, A, dt_w, dt_bias, Dskip, y, B, D, H, W, st);
+    static const bool smem_rows = getenv("FD_SCAN_TW2_TMEM") && atoi(getenv("FD_SCAN_TW2_TMEM")) == 0;
+    if (smem_rows) return scan_tw2_launch_v<T, NS, RDT, ST, TW, 2>(u_tm, xdbl, A, dt_w, dt_bias, Dskip, y, B, D, H, W, st);
+    return scan_tw2_launch_v<T, NS, RDT, ST, TW, 10>(u_tm, xdbl, A, dt_w, dt_bias, Dskip, y, B, D, H, W, st);
 }
 
 // K3c applies when no slice is ragged and no slice straddles an EfficientMerge row

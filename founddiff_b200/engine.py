@@ -395,13 +395,9 @@ class UnetEngine:
         tm_fuse = (N, R) in ((4, 4), (8, 4), (8, 8), (16, 8))
         use_tm = (dt != torch.float32 and use_xdt_tc and D % 128 == 0 and h % 2 == 0 and w % 2 == 0 and (tm_fuse or N in (4, 8, 16, 32))
                   and os.environ.get("FD_SS2D_TM", "1") != "0")
-        if use_tm and os.environ.get("FD_SS2D_TM", "1") != "all":
-            # Measured per level at B = 16 (profiles/r2_scan_tm_variants.json, whole dwconv + x_proj + scan chain): the time-major
-            # chain wins wherever a lane has >= 16 states or the rows are many (one segment), and at the full-resolution d_state-4
-            # level (time-sliced scan, dt_proj fused: 2.91 vs 3.10 ms); at d_state 8 with few long rows the round-1 warp-shuffle
-            # chain is still 6 % ahead (1.09 vs 1.16 ms), so that one geometry keeps it.
-            if N == 8 and ops.scan_tm_plan(B, D, h, w, N, R if tm_fuse else 0) < 0 and D == 128:
-                use_tm = False
+        # Measured per level at B = 16 (profiles/r2_scan_tm_variants.json, profiles/r2_scan_tw2_notes.txt): the time-major chain wins at
+        # every level since the time-sliced scan moved to packed arithmetic with its fix-up rows in tensor memory (the d_state-8,
+        # D = 128 level was the last one on the round-1 warp-shuffle chain: 743 us against 705 now, and a cheaper dwconv / x_proj).
         if use_tm:
             scan_cl = fuse_dt = False
             dw_wt = upload(dw_host.t(), dev)                               # tap-major (9, D)
