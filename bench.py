@@ -173,6 +173,14 @@ def algorithmic(name, detail, es):
             if fused:
                 return b * 4.0 * d * L * es + b * 4.0 * (r + 2 * n) * L * 4, 2.0 * b * 4 * L * d * (r + 2 * n)
             return 2.0 * b * 4 * d * L * es + 2.0 * b * 4 * n * L * 4, 2.0 * b * 4 * L * d * (2 * r + 2 * n)
+        if name == "row_rstd":
+            r, c = map(int, detail.split("x"))
+            return r * (c * es + 4.0), 0.0
+        if name == "ln_gate_out_proj":       # y, z in; addend in, out: (2 D + 2 Cout) elements per pixel
+            bp, dc = detail.split("->")
+            b, p, d = map(int, bp.split("x"))
+            co = int(dc)
+            return b * p * (2.0 * d + 2.0 * co) * es, 2.0 * b * p * d * co
         if name in ("ln_modulate", "gn_silu_add", "ln_gate"):
             b, p, c = map(int, detail.split("x"))
             return (2.0 if name == "ln_modulate" else 3.0) * b * p * c * es, 0.0

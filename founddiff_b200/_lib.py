@@ -14,7 +14,7 @@ from . import build as _build
 FD_F32, FD_BF16, FD_F16 = 0, 1, 2
 
 EXPORTS = [
-    "fd_version", "fd_program_arena_bytes", "fd_program_load", "fd_program_buffer", "fd_program_num_launches", "fd_unet_step", "fd_sample_step", "fd_program_destroy", "fd_ln_fold", "fd_gram_ws_floats", "fd_conv_gn_ws_floats", "fd_gn_stats_ws_floats", "fd_dwconv3x3_silu_tm", "fd_x_proj_tm", "fd_scan_tm_segments", "fd_scan_tm_plan", "fd_selective_scan_tm", "fd_selective_scan_fwd", "fd_selective_scan_fwd_merge", "fd_selective_scan_fwd_merge_xdbl", "fd_selective_scan_fwd_merge_cl", "fd_x_proj_tc", "fd_avgpool2x2_nhwc", "fd_slice_metrics", "fd_init_conv7x7_tc", "fd_ln_modulate_io", "fd_ln_gate", "fd_conv2d_simt", "fd_conv2d_tc_supported", "fd_conv2d_tc_plan_create",
+    "fd_version", "fd_program_arena_bytes", "fd_program_load", "fd_program_buffer", "fd_program_num_launches", "fd_unet_step", "fd_sample_step", "fd_program_destroy", "fd_ln_fold", "fd_gram_ws_floats", "fd_conv_gn_ws_floats", "fd_gn_stats_ws_floats", "fd_dwconv3x3_silu_tm", "fd_x_proj_tm", "fd_scan_tm_segments", "fd_scan_tm_plan", "fd_selective_scan_tm", "fd_selective_scan_fwd", "fd_selective_scan_fwd_merge", "fd_selective_scan_fwd_merge_xdbl", "fd_selective_scan_fwd_merge_cl", "fd_x_proj_tc", "fd_avgpool2x2_nhwc", "fd_slice_metrics", "fd_init_conv7x7_tc", "fd_ln_modulate_io", "fd_row_rstd", "fd_ln_gate", "fd_ln_gate_out_proj", "fd_ln_gate_out_proj_supported", "fd_conv2d_simt", "fd_conv2d_tc_supported", "fd_conv2d_tc_plan_create",
     "fd_conv2d_tc_run", "fd_conv2d_tc_plan_destroy", "fd_init_conv7x7", "fd_ln_modulate", "fd_dwconv3x3_silu_scan",
     "fd_xdt_proj", "fd_xdt_proj_tc", "fd_merge_ln_gate", "fd_dwconv3x3_qkv_gram", "fd_dwconv3x3_nhwc", "fd_gram_qk", "fd_attn_weff", "fd_gn_stats", "fd_gn_silu_add", "fd_gn_scale_shift_silu", "fd_flash_attn_d32", "fd_linattn_context", "fd_linattn_weff", "fd_softmax_d32",
     "fd_linear_small", "fd_time_sinusoid", "fd_sampler_init", "fd_final_conv_update", "fd_final_conv_update_obj", "fd_unnormalize", "fd_ddpm_update",
@@ -26,7 +26,7 @@ class ConvParams(Structure):
     _fields_ = [
         ("src0", c_void_p), ("src1", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("gate", c_void_p),
         ("addend", c_void_p), ("out", c_void_p), ("gn_sums", c_void_p), ("weight_up4", c_void_p), ("gn_ws", c_void_p),
-        ("ln_v", c_void_p),
+        ("ln_v", c_void_p), ("ln_rstd", c_void_p),
         ("c0", c_int), ("c1", c_int), ("ld0", c_int), ("B", c_int), ("Hin", c_int), ("Win", c_int), ("Cout", c_int),
         ("KH", c_int), ("KW", c_int), ("stride", c_int), ("pad", c_int), ("upsample", c_int),
         ("silu_from", c_int), ("gate_stride", c_int), ("gn_groups", c_int), ("per_batch_weight", c_int),
@@ -76,6 +76,9 @@ def load():
         "fd_avgpool2x2_nhwc": [V, V, I, I, I, I, I, V],
         "fd_slice_metrics": [V, V, V, I, I, I, F, V],
         "fd_ln_gate": [V, V, I, I, V, V, V, V, I, I, I, F, I, V],
+        "fd_row_rstd": [V, V, L, I, F, I, V],
+        "fd_ln_gate_out_proj": [V, V, I, I, V, V, V, V, V, I, V, V, I, I, I, I, F, I, I, V],
+        "fd_ln_gate_out_proj_supported": [I] * 7,
         "fd_conv2d_simt": [POINTER(ConvParams), V],
         "fd_conv2d_tc_supported": [POINTER(ConvParams)],
         "fd_conv2d_tc_plan_create": [POINTER(ConvParams), POINTER(c_void_p)],

@@ -113,6 +113,14 @@ FD_DEVINL float fd_warp_max(float v) {
     return v;
 }
 
+// packed fp32 pairs in 64-bit registers (fma / mul / add .f32x2 = FFMA2 / FMUL2 / FADD2 on sm_100a: one issue slot, two results)
+typedef unsigned long long u64;
+FD_DEVINL u64 f2_pack(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+FD_DEVINL void f2_unpack(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+FD_DEVINL u64 f2_fma(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+FD_DEVINL u64 f2_mul(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+FD_DEVINL u64 f2_add(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // ---- warp-level tensor-core helpers (mma.sync m16n8k16, fp32 accumulate) for the small, memory-bound GEMMs that sit
 // inside fused kernels (Gram matrices, x_proj/dt_proj); the large convolutions / projections use tcgen05 (fd_conv_tc.cu).
 FD_DEVINL void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {

@@ -251,10 +251,12 @@ FD_DEVINL float fast_silu(float x) {      // x * sigmoid(x) = 0.5 x (1 + tanh(x 
 // epilogue (lane quarter = warp % 4, column group = (warp - 2) / 4).  Two TMEM accumulator buffers let the epilogue of
 // tile i overlap the loads + MMAs of tile i+1; every role walks the same static tile sequence
 // tile = blockIdx.x + i * gridDim.x (N tile fastest, so neighbouring CTAs share the A tile in L2).
-// LNFOLD is a template parameter so that the plain instantiation keeps the register allocation and schedule it was tuned
-// with (as a run-time flag the fold cost every other 64-wide GEMM 13 - 15 %).
-template <typename T, bool LNFOLD>
-__global__ void __launch_bounds__(LNFOLD ? NTHREADS_LN : NTHREADS, 1)
+// LNMODE is a template parameter so that the plain instantiation keeps the register allocation and schedule it was tuned
+// with (as a run-time flag the fold cost every other 64-wide GEMM 13 - 15 %).  0: no fold; 1: fold, row statistics by the two
+// statistics warps from the staged operand tile; 2: fold, per-pixel rstd read from p.ln_rstd (fd_row_rstd) — no statistics warps,
+// the stage protocol of the plain kernel (measured: 64 -> 256 at 16 x 512^2 715 us with the statistics warps, 561 us plain).
+template <typename T, int LNMODE>
+__global__ void __launch_bounds__(LNMODE == 1 ? NTHREADS_LN : NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -285,13 +287,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const fd_conv_params& p = q.p;
-    constexpr bool ln_fold = LNFOLD;                  // LayerNorm of the input rows folded into this GEMM (box mode, 1x1)
+    constexpr bool ln_fold = LNMODE != 0;             // LayerNorm of the input rows folded into this GEMM (box mode, 1x1)
+    constexpr bool ln_stats = LNMODE == 1;            // statistics warps in this block
     const int total_tiles = q.total_tiles;
     const uint32_t tmem_cols = 2 * BN <= 128 ? 128u : 2 * BN <= 256 ? 256u : 512u;       // two accumulators, power-of-two allocation
 
     if (threadIdx.x == 0) {
         // with the LayerNorm fold a stage is released by the MMA commit AND by the statistics warps that read its A tile
-        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ln_fold ? 1 + NUM_STAT_WARPS : 1); }
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], ln_stats ? 1 + NUM_STAT_WARPS : 1); }
         for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
         mbar_init(wfull_bar, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], NUM_EPI_WARPS); mbar_init(&sfull_bar[s], NUM_STAT_WARPS); }
@@ -444,14 +447,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 __syncwarp();
             }
         }
-    } else if (LNFOLD && warp >= 2 + NUM_EPI_WARPS) {
+    } else if (LNMODE == 1 && warp >= 2 + NUM_EPI_WARPS) {
         // ================================ LayerNorm row statistics (ln fold): 2 warps ================================
         // rstd over the c0 input channels of each of the tile's 128 pixels, read from the SAME staged A tiles the MMA consumes
         // (no extra global traffic, no separate normalisation pass).  A row of a K block is 128 bytes = 8 swizzled 16-byte
         // chunks; sums do not care about the chunk order, so the lane owning row r reads chunk (j + r) & 7 at step j: the
         // eight rows a quarter-warp touches per LDS.128 phase hit eight different bank groups.  The mean itself is not needed
         // downstream: fd_ln_fold gives every weight row a zero sum, so W'(x - mean 1) = W'x.
-        if (ln_fold) {
+        if (ln_stats) {
             const float inv_c = 1.f / (float)p.c0;
             int stage = 0, it = 0;
             uint32_t ph = 0;
@@ -600,12 +603,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             uint32_t araw[8];
             const bool use_add = addend != nullptr && row_ok;
             if (use_add) load16_raw(addend + orow + n0 + cg * 16, araw);
+            float ln_rstd_g = 1.f;                      // external statistics: requested before the accumulator is waited for
+            if (LNMODE == 2 && row_ok) ln_rstd_g = __ldg(p.ln_rstd + ((long)b * q.Hout + oh) * q.Wout + ow);
             mbar_wait_long(&tfull_bar[buf], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float ln_rstd = 1.f;
-            if (ln_fold) {                             // statistics of this thread's pixel (written by the statistics warp)
+            if (ln_stats) {                            // statistics of this thread's pixel (written by the statistics warp)
                 mbar_wait(&sfull_bar[buf], (it >> 1) & 1);
                 ln_rstd = s_ln[buf * BM + m].y;
+            } else if (ln_fold) {
+                ln_rstd = ln_rstd_g;
             }
             const uint32_t tacc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q4 * 32) << 16);
             // (Software-pipelining the TMEM reads — tcgen05.ld of chunk ci + 1 in flight under chunk ci's math — needs a second
@@ -791,7 +798,9 @@ extern "C" int fd_conv2d_tc_supported(const fd_conv_params* p) {
     }
     if (p->ln_v) {                // LayerNorm fold: plain 1x1 GEMM over one input tensor (box mode), 16-byte aligned vector
         if (p->KH != 1 || p->KW != 1 || p->stride != 1 || p->pad != 0 || p->upsample || p->c1) return 0;
-        if (((uintptr_t)p->ln_v & 15) || p->Cout % 4 || p->Cout > 1024) return 0;
+        if (((uintptr_t)p->ln_v & 15) || ((uintptr_t)p->ln_rstd & 3) || p->Cout % 4 || p->Cout > 1024) return 0;
+    } else if (p->ln_rstd) {
+        return 0;
     }
     const uintptr_t al = (uintptr_t)p->src0 | (uintptr_t)p->src1 | (uintptr_t)p->weight | (uintptr_t)p->out |
                          (uintptr_t)p->addend | (uintptr_t)p->weight_up4;
@@ -873,7 +882,7 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
         q.stages = (int)((190 * 1024) / stage_bytes);
         if (q.stages > MAX_STAGES) q.stages = MAX_STAGES;
         if (q.stages > 2 * num_kb) q.stages = 2 * num_kb < 2 ? 2 : 2 * num_kb;     // enough to prefetch the next tile
-        if (p->ln_v && q.stages < 3 && 3 * stage_bytes <= 190 * 1024) q.stages = 3;   // a stage also waits for the statistics warps
+        if (p->ln_v && !p->ln_rstd && q.stages < 3 && 3 * stage_bytes <= 190 * 1024) q.stages = 3;   // a stage also waits for the statistics warps
     }
     q.total_tiles = p->B * q.phases * q.tiles_h * q.tiles_w * q.n_tiles;
 
@@ -902,24 +911,26 @@ extern "C" int fd_conv2d_tc_plan_create(const fd_conv_params* p, fd_gemm_plan** 
     return 0;
 }
 
-template <typename T, bool LNFOLD>
+template <typename T, int LNMODE>
 static int conv_tc_launch(const fd_gemm_plan* plan, cudaStream_t stream) {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<T, LNFOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<T, LNMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    conv_tc_kernel<T, LNFOLD><<<plan->grid, LNFOLD ? NTHREADS_LN : NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
+    conv_tc_kernel<T, LNMODE><<<plan->grid, LNMODE == 1 ? NTHREADS_LN : NTHREADS, plan->smem, stream>>>(plan->map_a0, plan->map_a1, plan->map_w, plan->q);
     return 0;
 }
 
 extern "C" int fd_conv2d_tc_run(const fd_gemm_plan* plan, cudaStream_t stream) {
     if (!plan) return FD_ERR_BAD_ARGUMENT;
-    const bool fold = plan->q.p.ln_v != nullptr;
+    const int mode = plan->q.p.ln_v == nullptr ? 0 : plan->q.p.ln_rstd ? 2 : 1;
     int rc;
-    if (plan->q.p.dtype == FD_BF16) rc = fold ? conv_tc_launch<__nv_bfloat16, true>(plan, stream) : conv_tc_launch<__nv_bfloat16, false>(plan, stream);
-    else rc = fold ? conv_tc_launch<__half, true>(plan, stream) : conv_tc_launch<__half, false>(plan, stream);
+    if (plan->q.p.dtype == FD_BF16)
+        rc = mode == 2 ? conv_tc_launch<__nv_bfloat16, 2>(plan, stream) : mode ? conv_tc_launch<__nv_bfloat16, 1>(plan, stream) : conv_tc_launch<__nv_bfloat16, 0>(plan, stream);
+    else
+        rc = mode == 2 ? conv_tc_launch<__half, 2>(plan, stream) : mode ? conv_tc_launch<__half, 1>(plan, stream) : conv_tc_launch<__half, 0>(plan, stream);
     if (rc) return rc;
     FD_LAUNCH_CHECK();
     if (plan->q.p.gn_sums && plan->q.p.gn_ws) {

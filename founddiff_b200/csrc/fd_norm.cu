@@ -322,6 +322,53 @@ extern "C" int fd_ln_gate(const void* y, const void* xz, int ld, int z_off, cons
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Per-row LayerNorm statistic for a folded GEMM (fd_conv_params.ln_rstd): rstd = 1 / sqrt(var + eps), two-pass in registers as
+// every other LayerNorm here.  LPR lanes share a row (one 16-byte vector each, NV vectors per lane), U row groups per warp in flight.
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int LPR, int NV, int U>
+__global__ void __launch_bounds__(256) row_rstd_kernel(const T* __restrict__ x, float* __restrict__ rstd, long rows, int C, float eps) {
+    constexpr int VEC = fd_vec<T>::N;
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, sub = lane % LPR;
+    const long warp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long row0 = warp * (RPW * U) + lane / LPR;
+    uint4 raw[U][NV];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long row = row0 + u * RPW;
+        const T* xr = x + (row < rows ? row : 0) * C;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) raw[u][j] = *reinterpret_cast<const uint4*>(xr + (sub + j * LPR) * VEC);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long row = row0 + u * RPW;
+        float v[NV][VEC];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) fd_raw_to_f<T>(raw[u][j], v[j]);
+        float mean, rs;
+        fd_row_stats<LPR, NV, VEC>(v, C, eps, mean, rs);
+        if (sub == 0 && row < rows) rstd[row] = rs;
+    }
+}
+
+extern "C" int fd_row_rstd(const void* x, float* rstd, long rows, int C, float eps, int dtype, cudaStream_t stream) {
+    if (!x || !rstd || rows <= 0 || C <= 0) return FD_ERR_BAD_ARGUMENT;
+    if ((dtype != FD_BF16 && dtype != FD_F16) || ((uintptr_t)x & 15)) return FD_ERR_UNSUPPORTED;
+#define RR_CASE(CV, L, N, UU)                                                                                         \
+    if (C == CV) {                                                                                                    \
+        const int grid = fd_cdiv(rows, (long)(32 / L) * 8 * UU);                                                      \
+        if (dtype == FD_BF16) row_rstd_kernel<__nv_bfloat16, L, N, UU><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, rstd, rows, C, eps); \
+        else row_rstd_kernel<__half, L, N, UU><<<grid, 256, 0, stream>>>((const __half*)x, rstd, rows, C, eps);      \
+        FD_LAUNCH_CHECK();                                                                                            \
+        return 0;                                                                                                     \
+    }
+    RR_CASE(64, 8, 1, 4) RR_CASE(128, 16, 1, 4) RR_CASE(256, 32, 1, 4) RR_CASE(512, 32, 2, 2)
+#undef RR_CASE
+    return FD_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // LayerNorm + adaLN modulation folded into the weights of the 1x1 GEMM that consumes it (see fd_ln_fold in the header).
 // One warp per (sample, output row): Wf = round(W g - rowmean(W g)), v = W h; fixed shuffle tree -> reproducible.
 // ------------------------------------------------------------------------------------------------------

@@ -96,19 +96,19 @@ extern "C" void fd_program_destroy(fd_program* prog) {
     delete prog;
 }
 
-// fd_conv_params as the recorder serialises it: 11 pointers (src0, src1, weight, bias, gate, addend, out, gn_sums, weight_up4,
-// gn_ws, ln_v), then the integer fields in struct order, ln_eps as the only float
+// fd_conv_params as the recorder serialises it: 12 pointers (src0, src1, weight, bias, gate, addend, out, gn_sums, weight_up4,
+// gn_ws, ln_v, ln_rstd), then the integer fields in struct order, ln_eps as the only float
 static int unpack_conv(const FileOp& fo, const std::vector<void*>& ptr, fd_conv_params* p) {
-    if (fo.nargs != 11 + 20) return FD_ERR_BAD_ARGUMENT;
+    if (fo.nargs != 12 + 20) return FD_ERR_BAD_ARGUMENT;
     memset(p, 0, sizeof(*p));
-    const void** pp[11] = {&p->src0, &p->src1, &p->weight, (const void**)&p->bias, (const void**)&p->gate, &p->addend,
+    const void** pp[12] = {&p->src0, &p->src1, &p->weight, (const void**)&p->bias, (const void**)&p->gate, &p->addend,
                            (const void**)&p->out, (const void**)&p->gn_sums, &p->weight_up4, (const void**)&p->gn_ws,
-                           (const void**)&p->ln_v};
-    for (int i = 0; i < 11; ++i) *pp[i] = ptr[i];
+                           (const void**)&p->ln_v, (const void**)&p->ln_rstd};
+    for (int i = 0; i < 12; ++i) *pp[i] = ptr[i];
     int* ip[19] = {&p->c0, &p->c1, &p->ld0, &p->B, &p->Hin, &p->Win, &p->Cout, &p->KH, &p->KW, &p->stride, &p->pad, &p->upsample,
                    &p->silu_from, &p->gate_stride, &p->gn_groups, &p->per_batch_weight, &p->dtype, &p->relu_out, &p->ab_dtype_p1};
-    for (int i = 0; i < 19; ++i) *ip[i] = (int)(int64_t)fo.args[11 + i].value;
-    uint32_t bits = (uint32_t)fo.args[11 + 19].value;
+    for (int i = 0; i < 19; ++i) *ip[i] = (int)(int64_t)fo.args[12 + i].value;
+    uint32_t bits = (uint32_t)fo.args[12 + 19].value;
     memcpy(&p->ln_eps, &bits, 4);
     return 0;
 }

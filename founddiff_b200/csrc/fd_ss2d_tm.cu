@@ -351,14 +351,6 @@ __global__ void __launch_bounds__(256) x_proj_tm_kernel(const T* __restrict__ xs
     }
 }
 
-// packed fp32 pairs in 64-bit registers (fma / mul / add .f32x2 = FFMA2 / FMUL2 / FADD2 on sm_100a: one issue slot, two results)
-typedef unsigned long long u64;
-FD_DEVINL u64 f2_pack(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-FD_DEVINL void f2_unpack(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-FD_DEVINL u64 f2_fma(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-FD_DEVINL u64 f2_mul(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-FD_DEVINL u64 f2_add(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-
 template <typename T> FD_DEVINL float tm_ld16(const T* p) {
     if constexpr (std::is_same<T, __nv_bfloat16>::value) return __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(p)) << 16);
     else return __half2float(*p);

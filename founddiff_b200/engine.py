@@ -344,6 +344,7 @@ class UnetEngine:
         # per sample and per step (B x Cout x C), so the fold only pays where a level has many more pixels than output channels.
         use_fold = (dt != torch.float32 and tc and P >= 8 * 4 * C and os.environ.get("FD_LN_FOLD", "1") == "1")
         c_in = c_qkv = None
+        ext_rstd = False
         if use_fold:
             tdt = self.trunk_dtype
             in_w32 = upload(sd[p + ".mamba.in_proj.weight"], dev)
@@ -352,10 +353,15 @@ class UnetEngine:
             wf_qkv = self.buf(f"WFQKV.{p}", B, 3 * C, C, dtype=tdt)
             v_in = torch.zeros(B, 4 * C, device=dev, dtype=torch.float32)
             v_q = torch.zeros(B, 3 * C, device=dev, dtype=torch.float32)
+            # row statistics by a separate one-read pass (fd_row_rstd, 4 bytes written per pixel) instead of the GEMM's statistics
+            # warps: the folded GEMMs then run at the plain kernel's speed (64 -> 256 at 16 x 512^2: 715 -> 561 us for a 90 us pass)
+            ext_rstd = os.environ.get("FD_LN_RSTD", "1") == "1" and C in (64, 128, 256, 512)
+            rstd = self.buf(f"RSTD{l}", B, P, dtype=torch.float32) if ext_rstd else None
             try:
                 c_in = ops.Conv(x_in, wf_in, xz, B=B, Hin=h, Win=w, silu_from=2 * C, per_batch_weight=True, prefer_tc=True,
-                                ln_v=v_in, ln_eps=1e-5)
-                c_qkv = ops.Conv(x, wf_qkv, qkv, B=B, Hin=h, Win=w, per_batch_weight=True, prefer_tc=True, ln_v=v_q, ln_eps=1e-6)
+                                ln_v=v_in, ln_eps=1e-5, ln_rstd=rstd)
+                c_qkv = ops.Conv(x, wf_qkv, qkv, B=B, Hin=h, Win=w, per_batch_weight=True, prefer_tc=True, ln_v=v_q, ln_eps=1e-6,
+                                 ln_rstd=rstd)
             except Exception:                           # geometry does not tile for the tensor-core kernel: separate passes
                 use_fold = False
         if not use_fold:
@@ -366,6 +372,8 @@ class UnetEngine:
         def ln1_in_proj():
             if use_fold:
                 ops.ln_fold(in_w32, n1w, n1b, sh1, sc1, MS, wf_in, v_in, B, 4 * C, C)
+                if ext_rstd:
+                    ops.row_rstd(x_in, rstd, B * P, C, 1e-5)
             else:
                 ops.ln_modulate(x_in, a, n1w, n1b, sh1, sc1, MS, B, P, C, 1e-5)
             c_in.run()
@@ -373,6 +381,8 @@ class UnetEngine:
         def ln2_qkv():
             if use_fold:
                 ops.ln_fold(qkv_w32, None, None, sh2, sc2, MS, wf_qkv, v_q, B, 3 * C, C)
+                if ext_rstd:
+                    ops.row_rstd(x, rstd, B * P, C, 1e-6)
             else:
                 ops.ln_modulate(x, a, None, None, sh2, sc2, MS, B, P, C, 1e-6)
             c_qkv.run()
@@ -398,6 +408,10 @@ class UnetEngine:
         # Measured per level at B = 16 (profiles/r2_scan_tm_variants.json, profiles/r2_scan_tw2_notes.txt): the time-major chain wins at
         # every level since the time-sliced scan moved to packed arithmetic with its fix-up rows in tensor memory (the d_state-8,
         # D = 128 level was the last one on the round-1 warp-shuffle chain: 743 us against 705 now, and a cheaper dwconv / x_proj).
+        # out_norm + gate + local + out_proj + gated residual in one pass (fd_ln_gate_gemm.cu) where the level is large and the
+        # kernel exists (D = 128 -> C = 64: the full-resolution level, 4 of the 9 Mamba blocks and 2/3 of their tail traffic)
+        fuse_tail = (use_tm and os.environ.get("FD_FUSE_TAIL", "1") == "1" and out_w.dtype == dt
+                     and ops.ln_gate_out_proj_supported(P, D, C, 4 * C, 2 * C, dt, x.dtype))
         if use_tm:
             scan_cl = fuse_dt = False
             dw_wt = upload(dw_host.t(), dev)                               # tap-major (9, D)
@@ -429,7 +443,7 @@ class UnetEngine:
         self._acc_users.append(bind)
 
         self.paths[p] = ((f"time-major scan, {S_tm} segment(s)" if S_tm > 0 else f"time-major scan, time-sliced x{-S_tm}")
-                         + (", dt_proj fused" if tm_fuse else "") + (", LayerNorm folded into in_proj / qkv" if use_fold else "") if use_tm else
+                         + (", dt_proj fused" if tm_fuse else "") + (", LayerNorm folded into in_proj / qkv" if use_fold else "") + (", fused out_norm / out_proj tail" if fuse_tail else "") if use_tm else
                          "scan_cl time-major B/C" if scan_cl else "dt-fused warp scan" if fuse_dt else
                          "warp scan + merge" if fuse_merge else "reference-layout" if dt == torch.float32 else "warp scan, unfused merge")
 
@@ -443,8 +457,12 @@ class UnetEngine:
                 else:
                     ops.x_proj_tm(xs_tm, xw16, xdbl_tm, dw16, dts_tm, dt_bias, B, D, L, R, N, Rp, False)
                     ops.selective_scan_tm(xs_tm, dts_tm, xdbl_tm, A_neg, None, None, Ds, carry, ys.view(B, P, D), B, D, h, w, N, 0, S_tm)
-                ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
-                c_out.run()
+                if fuse_tail:
+                    ops.ln_gate_out_proj(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), out_w, g1, MS, x_in, x,
+                                         B, P, D, C)
+                else:
+                    ops.ln_gate(ys.view(B, P, D), xz, 4 * C, 2 * C, on_w, on_b, local_c.dense(), g, B, P, D)
+                    c_out.run()
                 ln2_qkv()
                 ops.dwconv3x3_nhwc(qkv, qdw_wt, None, qkv2, B, h, w, 3 * C)
                 ops.gram_qk(qkv2, 3 * C, holder["gram"], holder["qk"], B, P, C, ws=holder["gws"])

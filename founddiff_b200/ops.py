@@ -139,10 +139,30 @@ def selective_scan_fwd_merge(u, delta, A, B, C, D, delta_bias, delta_softplus, y
     return y_nhwc
 
 
+def row_rstd(x, rstd, rows, C, eps):
+    """rstd[row] = 1 / sqrt(var(x[row, :C]) + eps): the statistics of a LayerNorm folded into the GEMM that reads x (Conv(ln_rstd=...))."""
+    with _launched("row_rstd", f"{rows}x{C}"):
+        check(_lib.load().fd_row_rstd(_p(x), _f32(rstd), rows, C, float(eps), dtype_code(x.dtype), _stream()), "fd_row_rstd")
+
+
 def ln_gate(y, xz, ld, z_off, gamma, beta, local, out, B, P, C, eps=1e-5):
     with _launched("ln_gate", f"{B}x{P}x{C}"):
         check(_lib.load().fd_ln_gate(_p(y), _p(xz), ld, z_off, _f32(gamma), _f32(beta), _f32(local), _p(out), B, P, C,
                                      float(eps), dtype_code(y.dtype), _stream()), "fd_ln_gate")
+
+
+def ln_gate_out_proj_supported(P, D, Cout, ld, z_off, io_dtype, out_dtype) -> bool:
+    if io_dtype == torch.float32 or out_dtype == torch.float32:
+        return False
+    return bool(_lib.load().fd_ln_gate_out_proj_supported(P, D, Cout, ld, z_off, dtype_code(io_dtype), dtype_code(out_dtype)))
+
+
+def ln_gate_out_proj(y, xz, ld, z_off, gamma, beta, local, w, gate, gate_stride, addend, out, B, P, D, Cout, eps=1e-5):
+    """out = addend + gate * (w . ((LN(y) * gamma + beta) * z + local)): fd_ln_gate + out_proj + gated residual in one pass."""
+    with _launched("ln_gate_out_proj", f"{B}x{P}x{D}->{Cout}"):
+        check(_lib.load().fd_ln_gate_out_proj(_p(y), _p(xz), ld, z_off, _f32(gamma), _f32(beta), _f32(local), _p(w), _f32(gate), gate_stride,
+                                              _p(addend), _p(out), B, P, D, Cout, float(eps), dtype_code(y.dtype), dtype_code(out.dtype),
+                                              _stream()), "fd_ln_gate_out_proj")
 
 
 def pack_upsample_phases(weight: torch.Tensor, cout: int, cin: int) -> torch.Tensor:
@@ -172,7 +192,7 @@ class Conv:
     def __init__(self, src0, weight, out, *, B, Hin, Win, KH=1, KW=1, stride=1, pad=0, upsample=False, src1=None,
                  bias=None, gate=None, gate_stride=0, addend=None, silu_from=None, gn_sums=None, gn_groups=0,
                  per_batch_weight=False, prefer_tc=True, c0=None, ld0=0, relu_out=False, gn_ws=None, weight_up4=None,
-                 ln_v=None, ln_eps=1e-5):
+                 ln_v=None, ln_eps=1e-5, ln_rstd=None):
         """`c0` / `ld0`: read only the first c0 channels of rows of pitch ld0 starting at src0's data pointer (src0 may
         be a strided channel-slice view).
         `gn_sums` (B, G, 2): GroupNorm statistics of the output.  With `gn_ws` (zeroed before every run: conv_gn_ws_floats(B) for
@@ -190,6 +210,7 @@ class Conv:
         p.gn_ws = _f32(gn_ws)
         # LayerNorm of the input rows folded into this GEMM (tcgen05 path only): weight = ln_fold()'s per-sample W', see the header
         p.ln_v, p.ln_eps = _f32(ln_v), float(ln_eps)
+        p.ln_rstd = _f32(ln_rstd)           # per-pixel rstd from row_rstd(): the GEMM then needs no statistics warps
         self._gn = None
         p.c0, p.c1, p.B, p.Hin, p.Win, p.Cout = c0, c1, B, Hin, Win, cout
         p.ld0 = ld0
@@ -209,7 +230,7 @@ class Conv:
         assert addend is None or addend.dtype == out.dtype
         assert weight.numel() == (B if per_batch_weight else 1) * cout * KH * KW * (c0 + c1), (weight.shape, cout, KH, KW, c0, c1)
         self.params = p
-        self._keep = (src0, src1, weight, out, bias, gate, addend, gn_sums, gn_ws, ln_v)
+        self._keep = (src0, src1, weight, out, bias, gate, addend, gn_sums, gn_ws, ln_v, ln_rstd)
         self._lib = lib
         self._plan = c_void_p()
         self.uses_tc = False

@@ -153,7 +153,7 @@ class Recorder:
                         args.append(arg(A_LONG if k == "l" else A_INT, 0, int(getattr(v, "value", v))))
             elif kind == OP_CONV:
                 p = payload
-                for f in ("src0", "src1", "weight", "bias", "gate", "addend", "out", "gn_sums", "weight_up4", "gn_ws", "ln_v"):
+                for f in ("src0", "src1", "weight", "bias", "gate", "addend", "out", "gn_sums", "weight_up4", "gn_ws", "ln_v", "ln_rstd"):
                     args.append(ptr_arg(getattr(p, f)))
                 for f in ("c0", "c1", "ld0", "B", "Hin", "Win", "Cout", "KH", "KW", "stride", "pad", "upsample", "silu_from",
                           "gate_stride", "gn_groups", "per_batch_weight", "dtype", "relu_out", "ab_dtype_p1"):

@@ -105,6 +105,9 @@ typedef struct {
                           /*   into this GEMM: out = rstd_p * acc + ln_v[b, n] with acc = W'_b x_p on the RAW input.  W'_b (zero row  */
                           /*   sums) and ln_v (B, Cout) fp32 come from fd_ln_fold; rstd_p is computed inside the kernel from the staged */
                           /*   operand tile. */
+    const float* ln_rstd; /* optional with ln_v: (B, Hin*Win) fp32 per-pixel 1/sqrt(var + eps) of the input rows from fd_row_rstd (or from */
+                          /*   the kernel that produced the rows).  The GEMM then runs without its statistics warps, at the speed of */
+                          /*   the plain 1x1 kernel; ln_eps is not used. */
     int c0, c1;
     int ld0;              /* row pitch (elements) of src0; 0 = dense (c0).  Lets a GEMM read a channel slice of a wider tensor */
     int B, Hin, Win, Cout;
@@ -249,8 +252,24 @@ int fd_merge_ln_gate(const void* ys, const void* xz, int ld, int z_off, const fl
 
 /* Row-wise tail of SS2D on channels-last data: out = (LN_C(y) * gamma + beta) * z + local[b]  (src/emamba2.py:365,
  * 747-748); z = columns [z_off, z_off+C) of xz rows of pitch ld; local: (B, C) fp32. */
+/* rstd[b, p] = 1 / sqrt(var_C(x[b, p, :]) + eps) (biased variance, two-pass in registers), x: (B*P, C) rows of a 16-bit type.
+ * The LayerNorm statistics a folded GEMM needs (fd_conv_params.ln_rstd): one read of the rows, 4 bytes written per row.
+ * C in {64, 128, 256, 512}. */
+int fd_row_rstd(const void* x, float* rstd, long rows, int C, float eps, int dtype, cudaStream_t stream);
+
 int fd_ln_gate(const void* y, const void* xz, int ld, int z_off, const float* gamma, const float* beta, const float* local,
                void* out, int B, int P, int C, float eps, int dtype, cudaStream_t stream);
+
+/* fd_ln_gate fused with out_proj and the Mamba block's gated residual (src/emamba2.py:365, 747-748 -> src/DADiff.py:486):
+ *   out[p, :] = addend[p, :] + gate[b, :] * (w . ((LN_D(y[p, :]) * gamma + beta) * z[p, :] + local[b, :]))
+ * one pass over the pixels instead of fd_ln_gate + a 1x1 convolution: the gated row never touches HBM.  w: (Cout, D) row-major in
+ * io_dtype (= storage of y / xz and operand type of the product); gate: (B, Cout) fp32 rows of pitch gate_stride; addend / out:
+ * (B, P, Cout) in out_dtype.  Built for the full-resolution level, D = 128, Cout = 64, P % 16 == 0, 16-bit types
+ * (fd_ln_gate_out_proj_supported says whether a geometry is taken; otherwise use the two calls). */
+int fd_ln_gate_out_proj_supported(int P, int D, int Cout, int ld, int z_off, int io_dtype, int out_dtype);
+int fd_ln_gate_out_proj(const void* y, const void* xz, int ld, int z_off, const float* gamma, const float* beta, const float* local,
+                        const void* w, const float* gate, int gate_stride, const void* addend, void* out, int B, int P, int D, int Cout,
+                        float eps, int io_dtype, int out_dtype, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * TransposedAttention (src/DADiff.py:263-285), C/32 heads of 32 channels.

@@ -905,3 +905,67 @@ def test_layernorm_folded_into_1x1_gemm(ops, cfg, types):
     r = rel(out, ref)
     print(f"ln-folded 1x1 {cfg} {types}: rel-L2 {r:.3e}")
     assert torch.isfinite(out.float()).all() and r < TOL[out_dt] * (1.5 if in_dt == torch.bfloat16 else 1.0), r
+    # the same GEMM with the row statistics from fd_row_rstd (no statistics warps in the kernel): the engine's form
+    rstd = torch.full((B, P), float("nan"), device="cuda")
+    ops.row_rstd(x.to("cuda", in_dt), rstd, B * P, C, eps)
+    assert rel(rstd, 1.0 / torch.sqrt(x.var(dim=-1, unbiased=False) + eps)) < 1e-5
+    out2 = torch.full((B, P, Cout), float("nan"), device="cuda", dtype=out_dt)
+    conv2 = ops.Conv(x.to("cuda", in_dt), wf, out2, B=B, Hin=H, Win=W, per_batch_weight=True, ln_v=v, ln_eps=eps, silu_from=silu_from,
+                     ln_rstd=rstd)
+    assert conv2.uses_tc
+    conv2.run()
+    conv2.run()
+    r2 = rel(out2, ref)
+    assert torch.isfinite(out2.float()).all() and r2 < TOL[out_dt] * (1.5 if in_dt == torch.bfloat16 else 1.0), r2
+    assert rel(out2, out.float().cpu()) < 2e-3          # both forms: same GEMM, statistics one-pass (in kernel) vs two-pass
+
+
+@pytest.mark.parametrize("dts", [(torch.bfloat16, torch.float16), (torch.bfloat16, torch.bfloat16), (torch.float16, torch.float16)])
+@pytest.mark.parametrize("BP", [(2, 48), (3, 4096), (1, 16)])
+def test_ln_gate_out_proj_fused_tail(dts, BP):
+    """fd_ln_gate_out_proj (out_norm -> * silu(z) + local -> out_proj -> gated residual, src/emamba2.py:365, 747-748 and
+    src/DADiff.py:486) against the same chain in fp32 torch, and against the two-launch form it replaces (fd_ln_gate + 1x1
+    conv with gate / addend epilogue): same roundings (the gated row is rounded to the operand type in both), so they agree
+    to accumulation order."""
+    from founddiff_b200 import ops
+    dti, dto = dts
+    B, P = BP
+    D, C = 128, 64
+    g = torch.Generator().manual_seed(B * P)
+    y = (torch.randn(B, P, D, generator=g) * 3 + 0.5).to(dti)
+    xz = torch.randn(B, P, 4 * C, generator=g).to(dti)
+    gamma, beta = torch.randn(D, generator=g) * 0.3 + 1, torch.randn(D, generator=g) * 0.1
+    local = torch.randn(B, D, generator=g) * 0.2
+    w = (torch.randn(C, D, generator=g) / D ** 0.5).to(dti)
+    mods = torch.randn(B, 6 * C, generator=g) * 0.5
+    addend = torch.randn(B, P, C, generator=g).to(dto)
+    assert ops.ln_gate_out_proj_supported(P, D, C, 4 * C, 2 * C, dti, dto)
+    yf, zf = y.float(), xz.float()[..., 2 * C:]
+    row = (F.layer_norm(yf, (D,), gamma, beta, 1e-5) * zf + local[:, None, :]).to(dti).float()
+    gate = mods[:, C:2 * C]
+    ref = addend.float() + gate[:, None, :] * (row @ w.float().t())
+    out = torch.full((B, P, C), float("nan"), device="cuda", dtype=dto)
+    mods_d = mods.cuda()
+
+    class View:                          # a column block of the modulation table, as the engine passes it (pointer + pitch)
+        dtype, is_cuda = torch.float32, True
+
+        def is_contiguous(self):
+            return True
+
+        def data_ptr(self):
+            return mods_d.data_ptr() + C * 4
+    ops.ln_gate_out_proj(y.cuda(), xz.cuda(), 4 * C, 2 * C, gamma.cuda(), beta.cuda(), local.cuda(), w.cuda(), View(), 6 * C,
+                         addend.cuda(), out, B, P, D, C)
+    assert torch.isfinite(out.float()).all()
+    tol = 6e-3 if dto == torch.bfloat16 else 1.5e-3
+    assert rel(out, ref) < tol, rel(out, ref)
+    # two-launch form
+    gbuf = torch.empty(B, P, D, device="cuda", dtype=dti)
+    ops.ln_gate(y.cuda(), xz.cuda(), 4 * C, 2 * C, gamma.cuda(), beta.cuda(), local.cuda(), gbuf, B, P, D)
+    two = addend.float() + gate[:, None, :] * (gbuf.float().cpu() @ w.float().t())
+    assert rel(out, two) < tol
+    # in place (the engine's trunk may alias: out == addend)
+    io = addend.cuda().clone()
+    ops.ln_gate_out_proj(y.cuda(), xz.cuda(), 4 * C, 2 * C, gamma.cuda(), beta.cuda(), local.cuda(), w.cuda(), View(), 6 * C, io, io, B, P, D, C)
+    assert torch.equal(io, out)
