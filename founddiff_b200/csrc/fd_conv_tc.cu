@@ -638,6 +638,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 if (ln_fold) {                         // W LN(x) = rstd W' x + v   (fd_ln_fold made W' with zero row sums, and v)
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
+                        // (an explicit ld.shared here instead of the generic load the compiler emits — the shared-memory carve-up
+                        // goes through an integer round-up — measured SLOWER, 715 -> 750 us at 64 -> 256: the volatile asm pins the
+                        // load in front of its FMAs)
                         const float4 vv = *reinterpret_cast<const float4*>(s_lnv + n + j);
                         v[j] = fmaf(ln_rstd, v[j], vv.x);
                         v[j + 1] = fmaf(ln_rstd, v[j + 1], vv.y);

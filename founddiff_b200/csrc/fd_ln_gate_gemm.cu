@@ -9,10 +9,12 @@
 // The GEMM is small (K = D = 128, N = C = 64: 16 KFLOP per 640 bytes of traffic) and the kernel stays HBM-bound, so it runs on
 // warp-level mma.sync (m16n8k16, fp32 accumulate) with the A operand built IN REGISTERS from the rows the warp has just
 // normalised — no shared-memory round trip for A at all:
-//   * a warp owns 16 consecutive pixels; lane (g = lane / 4, t = lane % 4) holds channels [32 t, 32 t + 32) of pixels g and
-//     g + 8 (4 x LDG.128 per row and tensor), so a row's LayerNorm statistics are two shuffles inside the quad;
+//   * a warp owns 16 consecutive pixels; lane (g = lane / 4, t = lane % 4) holds the 16-byte pieces t, t + 4, t + 8, t + 12 of
+//     the rows of pixels g and g + 8 (4 x LDG.128 per row and tensor: the four lanes of a quad read 64 contiguous bytes per
+//     instruction — with 64 contiguous bytes per LANE instead, every warp load touched 16 cache lines half a sector at a time and
+//     the kernel sat at 3.2 TB/s on the L1 tag stage), so a row's LayerNorm statistics are two shuffles inside the quad;
 //   * the K index of a GEMM may be permuted freely as long as A and B agree: k-tile j takes, from thread t, the four channels
-//     32 t + 4 j + {0, 1, 2, 3} as the fragment's (k = 2t, 2t+1, 2t+8, 2t+9) — exactly what the thread already holds;
+//     32 (j / 2) + 8 t + 4 (j % 2) + {0, 1, 2, 3} as the fragment's (k = 2t, 2t+1, 2t+8, 2t+9) — exactly what the thread holds;
 //   * the weight is re-laid once per block into fragment order in shared memory (one conflict-free LDS.64 per MMA).
 // The row g is rounded to the operand type before the product, as the two-launch form did when it stored it.
 #include <type_traits>
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(LG_WARPS * 32, 2) ln_gate_out_proj_kernel(
     const int g = lane >> 2, t = lane & 3;
     for (int i = threadIdx.x; i < LG_NT * LG_KT * 32; i += LG_WARPS * 32) {
         const int ln = i & 31, j = (i >> 5) % LG_KT, nn = i / (32 * LG_KT);
-        s_w[i] = *reinterpret_cast<const unsigned long long*>(w + (long)(8 * nn + (ln >> 2)) * LG_D + 32 * (ln & 3) + 4 * j);
+        s_w[i] = *reinterpret_cast<const unsigned long long*>(w + (long)(8 * nn + (ln >> 2)) * LG_D + 32 * (j >> 1) + 8 * (ln & 3) + 4 * (j & 1));
     }
     for (int i = threadIdx.x; i < LG_D; i += LG_WARPS * 32) { s_gamma[i] = gamma[i]; s_beta[i] = beta[i]; }
     __syncthreads();
@@ -67,12 +69,12 @@ __global__ void __launch_bounds__(LG_WARPS * 32, 2) ln_gate_out_proj_kernel(
         uint4 ry[2][4], rz[2][4];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const TI* yr = y + (long)(row0 + 8 * r) * LG_D + 32 * t;
-            const TI* zr = xz + (long)(row0 + 8 * r) * ld + z_off + 32 * t;
+            const TI* yr = y + (long)(row0 + 8 * r) * LG_D + 8 * t;
+            const TI* zr = xz + (long)(row0 + 8 * r) * ld + z_off + 8 * t;
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                ry[r][v] = *reinterpret_cast<const uint4*>(yr + 8 * v);
-                rz[r][v] = *reinterpret_cast<const uint4*>(zr + 8 * v);
+                ry[r][v] = *reinterpret_cast<const uint4*>(yr + 32 * v);
+                rz[r][v] = *reinterpret_cast<const uint4*>(zr + 32 * v);
             }
         }
         // LayerNorm statistics: sum and sum of squares in one pass over the raw registers, as packed fp32 pairs (one FADD2 + one
@@ -106,14 +108,14 @@ __global__ void __launch_bounds__(LG_WARPS * 32, 2) ln_gate_out_proj_kernel(
             nrm_a[r] = f2_pack(rstd, rstd);
             nrm_c[r] = f2_pack(-mean * rstd, -mean * rstd);
         }
-        // A fragments: k-tile j = channels 32 t + 4 j .. + 3 of both rows; three packed FMAs per channel pair
+        // A fragments: k-tiles 2 v, 2 v + 1 = the two halves of the thread's v-th 16-byte piece, both rows; three packed FMAs per pair
         uint32_t afr[LG_KT][4];
-        const float* lb = local + (long)b * LG_D + 32 * t;
+        const float* lb = local + (long)b * LG_D + 8 * t;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {                          // 8 channels per 16-byte vector = k-tiles 2 v and 2 v + 1
-            const ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(s_gamma + 32 * t + 8 * v), g1 = *reinterpret_cast<const ulonglong2*>(s_gamma + 32 * t + 8 * v + 4);
-            const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(s_beta + 32 * t + 8 * v), b1 = *reinterpret_cast<const ulonglong2*>(s_beta + 32 * t + 8 * v + 4);
-            const ulonglong2 l0 = __ldg(reinterpret_cast<const ulonglong2*>(lb + 8 * v)), l1 = __ldg(reinterpret_cast<const ulonglong2*>(lb + 8 * v + 4));
+            const ulonglong2 g0 = *reinterpret_cast<const ulonglong2*>(s_gamma + 32 * v + 8 * t), g1 = *reinterpret_cast<const ulonglong2*>(s_gamma + 32 * v + 8 * t + 4);
+            const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(s_beta + 32 * v + 8 * t), b1 = *reinterpret_cast<const ulonglong2*>(s_beta + 32 * v + 8 * t + 4);
+            const ulonglong2 l0 = __ldg(reinterpret_cast<const ulonglong2*>(lb + 32 * v)), l1 = __ldg(reinterpret_cast<const ulonglong2*>(lb + 32 * v + 4));
             const u64 gm[4] = {g0.x, g0.y, g1.x, g1.y}, bt[4] = {b0.x, b0.y, b1.x, b1.y}, lc[4] = {l0.x, l0.y, l1.x, l1.y};
 #pragma unroll
             for (int r = 0; r < 2; ++r) {

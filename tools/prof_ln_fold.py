@@ -32,7 +32,10 @@ ops.ln_fold(W, None, None, V(mods[:, :C]), V(mods[:, C:]), 2 * C, wf, v, B, Co, 
 plain = ops.Conv(a, W.to(torch.float16), out, B=B, Hin=H, Win=H, silu_from=Co // 2)
 pbw = ops.Conv(a, wf, out, B=B, Hin=H, Win=H, silu_from=Co // 2, per_batch_weight=True)
 fold = ops.Conv(x, wf, out, B=B, Hin=H, Win=H, silu_from=Co // 2, per_batch_weight=True, ln_v=v, ln_eps=1e-5)
-for name, c in (("plain", plain), ("per-batch weight", pbw), ("ln fold", fold)):
+rstd = torch.empty(B, P, device="cuda")
+ops.row_rstd(x, rstd, B * P, C, 1e-5)
+fold2 = ops.Conv(x, wf, out, B=B, Hin=H, Win=H, silu_from=Co // 2, per_batch_weight=True, ln_v=v, ln_eps=1e-5, ln_rstd=rstd)
+for name, c in (("plain", plain), ("per-batch weight", pbw), ("ln fold", fold), ("ln fold, external rstd", fold2)):
     for _ in range(2):
         c.run()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
