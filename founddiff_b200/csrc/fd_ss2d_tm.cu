@@ -59,9 +59,20 @@ template <typename T> FD_DEVINL void tm_st(T* p, const float (&v)[4]) {
     *reinterpret_cast<uint2*>(p) = r;
 }
 
+// 16-bit pair -> packed fp32 pair (FFMA2 operand)
+template <typename T> FD_DEVINL u64 tm_cvt2(uint32_t w) {
+    float2 f;
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w));
+    else f = __half22float2(*reinterpret_cast<__half2*>(&w));
+    return f2_pack(f.x, f.y);
+}
+
+// The 9-tap accumulation runs on packed fp32 pairs (two adjacent channels per FFMA2): the kernel is bound by issue slots (240 of
+// the 710 instructions of a 3-row iteration were FFMA; 607 with 108 FFMA2), and a packed FMA takes one slot for two results.
 template <typename T, bool EDGE>
-FD_DEVINL void dwtm_rows(const T* __restrict__ in_b, T* __restrict__ out_b, const float (&wr)[9][TM_V], const float (&bs)[TM_V],
+FD_DEVINL void dwtm_rows(const T* __restrict__ in_b, T* __restrict__ out_b, const u64 (&wr)[9][TM_V / 2], const u64 (&bs)[TM_V / 2],
                          int H, int W, int ld, int D, int x, int y0, int y1, bool has_l, bool has_2, int pf) {
+    constexpr int NP = TM_V / 2;
     const int H2 = H >> 1, W2 = W >> 1, x2 = x >> 1;
     const long L = (long)H2 * W2;
     const int ymax = min(H - 1, y1);
@@ -71,13 +82,13 @@ FD_DEVINL void dwtm_rows(const T* __restrict__ in_b, T* __restrict__ out_b, cons
     const int offl = (!EDGE || has_l) ? ld : 0, off1 = ld, off2 = (!EDGE || has_2) ? 2 * ld : 0;   // W is even: x + 1 < W always
     const T* p = in_b + (long)min(max(yi, 0), ymax) * rowe + (long)x * ld;      // row the next fetch reads (clamped into the image)
     int yf = yi;
-    float acc[3][2][TM_V];
+    u64 acc[3][2][NP];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int px = 0; px < 2; ++px)
 #pragma unroll
-            for (int e = 0; e < TM_V; ++e) acc[r][px][e] = 0.f;
+            for (int e = 0; e < NP; ++e) acc[r][px][e] = 0ull;
     uint2 ring[3][4];
     auto fetch = [&](auto slot_c) {
         constexpr int S = decltype(slot_c)::value;
@@ -96,7 +107,7 @@ FD_DEVINL void dwtm_rows(const T* __restrict__ in_b, T* __restrict__ out_b, cons
     auto step = [&](int yrow, auto slot_c) {
         constexpr int S = decltype(slot_c)::value;       // == yrow mod 3
         constexpr int S1 = (S + 1) % 3, S2 = (S + 2) % 3;
-        float v[4][TM_V];
+        u64 v[4][NP];
         {
             const bool rv = yrow >= 0 && yrow < H;       // block-uniform; straight-line masking keeps the loads in flight
             const bool ok[4] = {rv && (!EDGE || has_l), rv, rv, rv && (!EDGE || has_2)};
@@ -105,23 +116,24 @@ FD_DEVINL void dwtm_rows(const T* __restrict__ in_b, T* __restrict__ out_b, cons
                 uint2 r = ring[S][j];
                 r.x = ok[j] ? r.x : 0u;
                 r.y = ok[j] ? r.y : 0u;
-                tm_cvt<T>(r, v[j]);
+                v[j][0] = tm_cvt2<T>(r.x);
+                v[j][1] = tm_cvt2<T>(r.y);
             }
         }
         fetch(slot_c);
 #pragma unroll
         for (int px = 0; px < 2; ++px)
 #pragma unroll
-            for (int e = 0; e < TM_V; ++e) {
-                float a1 = fmaf(v[px][e], wr[0][e], bs[e]);                        // output row yrow+1: first contribution
-                a1 = fmaf(v[px + 1][e], wr[1][e], a1);
-                acc[S1][px][e] = fmaf(v[px + 2][e], wr[2][e], a1);
-                float a0 = fmaf(v[px][e], wr[3][e], acc[S][px][e]);               // output row yrow
-                a0 = fmaf(v[px + 1][e], wr[4][e], a0);
-                acc[S][px][e] = fmaf(v[px + 2][e], wr[5][e], a0);
-                float a2 = fmaf(v[px][e], wr[6][e], acc[S2][px][e]);              // output row yrow-1 (complete after this)
-                a2 = fmaf(v[px + 1][e], wr[7][e], a2);
-                acc[S2][px][e] = fmaf(v[px + 2][e], wr[8][e], a2);
+            for (int e = 0; e < NP; ++e) {
+                u64 a1 = f2_fma(v[px][e], wr[0][e], bs[e]);                        // output row yrow+1: first contribution
+                a1 = f2_fma(v[px + 1][e], wr[1][e], a1);
+                acc[S1][px][e] = f2_fma(v[px + 2][e], wr[2][e], a1);
+                u64 a0 = f2_fma(v[px][e], wr[3][e], acc[S][px][e]);               // output row yrow
+                a0 = f2_fma(v[px + 1][e], wr[4][e], a0);
+                acc[S][px][e] = f2_fma(v[px + 2][e], wr[5][e], a0);
+                u64 a2 = f2_fma(v[px][e], wr[6][e], acc[S2][px][e]);              // output row yrow-1 (complete after this)
+                a2 = f2_fma(v[px + 1][e], wr[7][e], a2);
+                acc[S2][px][e] = f2_fma(v[px + 2][e], wr[8][e], a2);
             }
         const int yo = yrow - 1;
         if (yo >= y0 && yo < y1) {                       // block-uniform
@@ -132,7 +144,12 @@ FD_DEVINL void dwtm_rows(const T* __restrict__ in_b, T* __restrict__ out_b, cons
             for (int px = 0; px < 2; ++px) {
                 float o[TM_V];
 #pragma unroll
-                for (int e = 0; e < TM_V; ++e) o[e] = fd_silu16(acc[S2][px][e]);
+                for (int e = 0; e < NP; ++e) {
+                    float a, b;
+                    f2_unpack(acc[S2][px][e], a, b);
+                    o[2 * e] = fd_silu16(a);
+                    o[2 * e + 1] = fd_silu16(b);
+                }
                 tm_st<T>(out_b + off + (px ? 2 * L * D : 0), o);
             }
         }
@@ -158,15 +175,15 @@ __global__ void __launch_bounds__(256, 2) dwconv_tm_kernel(const T* __restrict__
     const long f2c = live ? f2 : 0;
     const int cv = (int)(f2c % NV), x = 2 * (int)(f2c / NV);
     const int y0 = blockIdx.y * TM_RY, y1 = min(H, y0 + TM_RY);
-    float wr[9][TM_V], bs[TM_V];
+    u64 wr[9][TM_V / 2], bs[TM_V / 2];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
         const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (long)t * D + cv * TM_V));
-        wr[t][0] = wv.x; wr[t][1] = wv.y; wr[t][2] = wv.z; wr[t][3] = wv.w;
+        wr[t][0] = f2_pack(wv.x, wv.y); wr[t][1] = f2_pack(wv.z, wv.w);
     }
     {
         const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + cv * TM_V)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        bs[0] = bv.x; bs[1] = bv.y; bs[2] = bv.z; bs[3] = bv.w;
+        bs[0] = f2_pack(bv.x, bv.y); bs[1] = f2_pack(bv.z, bv.w);
     }
     const bool has_l = x > 0, has_2 = x + 2 < W;
     const T* in_b = xz + (long)blockIdx.z * H * W * ld + cv * TM_V;
