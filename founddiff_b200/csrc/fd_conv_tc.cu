@@ -260,7 +260,10 @@ __global__ void __launch_bounds__(LNMODE == 1 ? NTHREADS_LN : NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by POINTER arithmetic on the shared array: rounding the address up through an integer cast made every
+    // later access of this memory a generic load / store (long-scoreboard latency: the LayerNorm-fold epilogue's ln_v reads alone
+    // cost the 64 -> 256 GEMM 130 us of its 690)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int BN = q.BN;
     const uint32_t a_bytes = BM * BK * 2, b_bytes = (uint32_t)BN * BK * 2;
     const uint32_t stage_bytes = a_bytes + b_bytes;
@@ -575,6 +578,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (lane < 16) p.gn_ws[((long)cur_b * nslots + slot) * 16 + lane] = tot;
         };
         int it = 0;
+        auto rstd_of = [&](int tl) -> float {          // ln_rstd of this thread's pixel in tile tl (fold: 1x1, no upsampling)
+            const TileCoord tn = decode_tile(q, tl);
+            const int ri = tn.th * q.tile_h + (m >> q.tile_w_shift), rj = tn.tw * q.tile_w + (m & (q.tile_w - 1));
+            return (ri < q.Hout && rj < q.Wout) ? __ldg(p.ln_rstd + ((long)tn.b * q.Hout + ri) * q.Wout + rj) : 1.f;
+        };
+        float rstd_next = 1.f;
+        if (LNMODE == 2 && (int)blockIdx.x < total_tiles) rstd_next = rstd_of((int)blockIdx.x);
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc = decode_tile(q, tile);
             const int phase = tc.phase, b = tc.b;
@@ -603,8 +613,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             uint32_t araw[8];
             const bool use_add = addend != nullptr && row_ok;
             if (use_add) load16_raw(addend + orow + n0 + cg * 16, araw);
-            float ln_rstd_g = 1.f;                      // external statistics: requested before the accumulator is waited for
-            if (LNMODE == 2 && row_ok) ln_rstd_g = __ldg(p.ln_rstd + ((long)b * q.Hout + oh) * q.Wout + ow);
+            // external statistics: this tile's value was requested one tile ago (the accumulator is normally ready when the
+            // epilogue gets to it, so a load issued here had its whole latency in front of the first FMA: 15 % of the kernel's
+            // stall samples); now the next tile's
+            const float ln_rstd_g = rstd_next;
+            if (LNMODE == 2 && tile + (int)gridDim.x < total_tiles) rstd_next = rstd_of(tile + (int)gridDim.x);
             mbar_wait_long(&tfull_bar[buf], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float ln_rstd = 1.f;
