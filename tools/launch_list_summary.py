@@ -18,7 +18,7 @@ for r in rd:
     unit = r[iu]
     us = v / 1e3 if unit in ("ns", "nsecond") else v * 1e3 if unit in ("ms", "msecond") else v
     rows.append((r[ik], us))
-OURS = ("conv_tc", "selective_scan", "dwconv", "ln_", "gn_", "x_proj", "xdt_proj", "init_conv", "gram_mma", "attn_weff", "final_conv",
+OURS = ("conv_tc", "selective_scan", "scan_tw", "scan_tm", "row_rstd", "dwconv", "ln_", "gn_", "x_proj", "xdt_proj", "init_conv", "gram_mma", "attn_weff", "final_conv",
         "linear_small", "avgpool2x2_nhwc", "sampler_init", "time_sinusoid", "unnormalize", "conv_simt", "merge_", "flash", "linattn")
 
 

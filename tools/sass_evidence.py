@@ -13,7 +13,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "founddiff_b200",
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 KEYS = [("UTC*MMA", r"UTC\w*MMA"), ("LDTM", r"LDTM"), ("STTM", r"STTM"), ("UTMALDG", r"UTMALDG"), ("UTMASTG", r"UTMASTG"),
         ("SYNCS", r"SYNCS"), ("HMMA", r"\bHMMA"), ("LDGSTS", r"LDGSTS"), ("LDSM", r"LDSM"), ("MUFU", r"MUFU"), ("SHFL", r"SHFL"),
-        ("FFMA", r"\bFFMA")]
+        ("FFMA", r"\bFFMA(?!2)"), ("F*2 f32x2", r"\bF(?:FMA|MUL|ADD)2")]
 cur, rows = None, collections.OrderedDict()
 ins = re.compile(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\w+\s+)?([A-Z][A-Z0-9_.]*)")
 for line in sass.splitlines():
