@@ -228,6 +228,24 @@ FD_DEVINL float tm_softplus(float x) {
     const float corr = (y - (w - 1.f)) * (1.f - fminf(y, 1.f));
     return fmaf(tm_lg2(w), 0.6931471805599453f, corr);
 }
+// tm_softplus on two values at once: 4 MUFU + 2 FMNMX clamps + 2 FMNMX + 7 packed ops (15 issue slots for two, 11 each before)
+FD_DEVINL void tm_softplus2(float x0, float x1, float& d0, float& d1) {
+    const u64 xa = f2_mul(f2_pack(fminf(x0, 80.f), fminf(x1, 80.f)), f2_pack(1.4426950408889634f, 1.4426950408889634f));
+    float a0, a1;
+    f2_unpack(xa, a0, a1);
+    const float y0 = tm_ex2(a0), y1 = tm_ex2(a1);
+    const u64 y = f2_pack(y0, y1);
+    const u64 w = f2_add(y, f2_pack(1.f, 1.f));
+    const u64 wm1 = f2_add(w, f2_pack(-1.f, -1.f));
+    const u64 lost = f2_fma(wm1, f2_pack(-1.f, -1.f), y);                              // y - (w - 1), exact for y < 1
+    const u64 fac = f2_fma(f2_pack(fminf(y0, 1.f), fminf(y1, 1.f)), f2_pack(-1.f, -1.f), f2_pack(1.f, 1.f));
+    const u64 corr = f2_mul(lost, fac);
+    float w0, w1;
+    f2_unpack(w, w0, w1);
+    const u64 r = f2_fma(f2_pack(tm_lg2(w0), tm_lg2(w1)), f2_pack(0.6931471805599453f, 0.6931471805599453f), corr);
+    f2_unpack(r, d0, d1);
+}
+
 template <typename T> FD_DEVINL uint32_t tm_pack2(float a, float b) {
     if constexpr (std::is_same<T, __nv_bfloat16>::value) {
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -329,8 +347,6 @@ __global__ void __launch_bounds__(256) x_proj_tm_kernel(const T* __restrict__ xs
         }
         const T* wd = dw16 + (long)k * D * Rp;
         const float* bk_bias = dt_bias + (long)k * D;
-        T* d0p = dts + ((long)bk * L + r0) * D;
-        T* d1p = dts + ((long)bk * L + r1) * D;
         // B fragments (dt_proj weights, K-contiguous rows of dw16) come straight from global memory / L1: they are the same for
         // every block of a direction.  The loads of n-tile nd + 1 are issued before the MMAs and the softplus epilogue of n-tile
         // nd, so their latency sits under ~60 instructions of work instead of in front of every MMA.
@@ -352,15 +368,37 @@ __global__ void __launch_bounds__(256) x_proj_tm_kernel(const T* __restrict__ xs
         };
         load_b(0, bcur, bbc);
         const int nnd = D / 8;
+        // delta leaves through a per-warp shared-memory tile (16 steps x 64 channels, the pipeline's buffers are free by now): a C
+        // fragment holds 2 adjacent channels per lane, so storing from it a warp instruction wrote eight 16-byte pieces in eight
+        // cache lines (the deep levels, D = 512 / 1024, ran at 1.3 - 2.1 TB/s on it); read back by rows, a lane writes 16 bytes
+        // and a warp instruction four complete 128-byte row segments.
+        __syncthreads();                                  // every warp is out of the stage-1 loop: s_a is reusable
+        constexpr int OT = 64 + 8;                        // tile row pitch (elements): the 8 rows of a fragment store hit 32 banks
+        T* ot = s_a + warp * 16 * OT;
         for (int nd = 0; nd < nnd; ++nd) {
             if (nd + 1 < nnd) load_b(nd + 1, bnxt, bbn);
             float o[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int kt = 0; kt < 2; ++kt)
                 if (kt < nk) mma_16816<T>(o, afr[kt], bcur[kt][0], bcur[kt][1]);
-            const int d = nd * 8 + 2 * t4;
-            if (r0 < L) *reinterpret_cast<uint32_t*>(d0p + d) = tm_pack2<T>(tm_softplus(o[0] + bbc.x), tm_softplus(o[1] + bbc.y));
-            if (r1 < L) *reinterpret_cast<uint32_t*>(d1p + d) = tm_pack2<T>(tm_softplus(o[2] + bbc.x), tm_softplus(o[3] + bbc.y));
+            const int dc = (nd & 7) * 8 + 2 * t4;         // column inside the 64-channel group
+            float s0, s1, s2, s3;                         // softplus on packed pairs: the deep levels (D = 512 / 1024 softplus per step) are
+            tm_softplus2(o[0] + bbc.x, o[1] + bbc.y, s0, s1);     // bound by this epilogue's issue slots and MUFU ops, not by HBM
+            tm_softplus2(o[2] + bbc.x, o[3] + bbc.y, s2, s3);
+            *reinterpret_cast<uint32_t*>(ot + g * OT + dc) = tm_pack2<T>(s0, s1);
+            *reinterpret_cast<uint32_t*>(ot + (g + 8) * OT + dc) = tm_pack2<T>(s2, s3);
+            if ((nd & 7) == 7) {                          // D % 64 == 0: a group is always complete
+                __syncwarp();
+                const int d0 = (nd & ~7) * 8 + (lane & 7) * 8;
+#pragma unroll
+                for (int ps = 0; ps < 4; ++ps) {
+                    const int rr = ps * 4 + (lane >> 3);
+                    const int row = l0 + warp * 16 + rr;
+                    const uint4 v = *reinterpret_cast<const uint4*>(ot + rr * OT + (lane & 7) * 8);
+                    if (row < L) *reinterpret_cast<uint4*>(dts + ((long)bk * L + row) * D + d0) = v;
+                }
+                __syncwarp();
+            }
 #pragma unroll
             for (int kt = 0; kt < 2; ++kt) { bcur[kt][0] = bnxt[kt][0]; bcur[kt][1] = bnxt[kt][1]; }
             bbc = bbn;
@@ -822,24 +860,6 @@ int scan_tw_launch(const void* u_tm, const float* xdbl, const float* A, const fl
 // through shared memory as 64-bit words.  Same algorithm, same association order as K3b (results agree to the last
 // re-association), and only for geometries where no slice is ragged or straddles an EfficientMerge row: L % (TW ST) == 0
 // and the merge row length (W/2 resp. H/2) a multiple of ST — everything else takes K3b.
-// tm_softplus on two values at once: 4 MUFU + 2 FMNMX clamps + 2 FMNMX + 7 packed ops (15 issue slots for two, 11 each before)
-FD_DEVINL void tm_softplus2(float x0, float x1, float& d0, float& d1) {
-    const u64 xa = f2_mul(f2_pack(fminf(x0, 80.f), fminf(x1, 80.f)), f2_pack(1.4426950408889634f, 1.4426950408889634f));
-    float a0, a1;
-    f2_unpack(xa, a0, a1);
-    const float y0 = tm_ex2(a0), y1 = tm_ex2(a1);
-    const u64 y = f2_pack(y0, y1);
-    const u64 w = f2_add(y, f2_pack(1.f, 1.f));
-    const u64 wm1 = f2_add(w, f2_pack(-1.f, -1.f));
-    const u64 lost = f2_fma(wm1, f2_pack(-1.f, -1.f), y);                              // y - (w - 1), exact for y < 1
-    const u64 fac = f2_fma(f2_pack(fminf(y0, 1.f), fminf(y1, 1.f)), f2_pack(-1.f, -1.f), f2_pack(1.f, 1.f));
-    const u64 corr = f2_mul(lost, fac);
-    float w0, w1;
-    f2_unpack(w, w0, w1);
-    const u64 r = f2_fma(f2_pack(tm_lg2(w0), tm_lg2(w1)), f2_pack(0.6931471805599453f, 0.6931471805599453f), corr);
-    f2_unpack(r, d0, d1);
-}
-
 // VAR bit 0: y_local kept in shared memory instead of ST registers; bit 1: delta of the whole slice formed ahead of the recurrence
 // (ST / 2 independent softplus chains in flight instead of SB / 2); bit 2: two half-slices per warp scanned in lockstep
 template <typename T, int NS, int RDT, int ST, int TW, int VAR>
@@ -1252,7 +1272,7 @@ extern "C" int fd_x_proj_tm(const void* xs_tm, const void* xw16, float* xdbl_tm,
     if (!fuse_dt && (!dw16 || !dts_tm || !dt_bias)) return FD_ERR_BAD_ARGUMENT;
     if (D % XM_KC || R + 2 * N > 96 || (R & 1) || (N & 1) || (((uintptr_t)xs_tm | (uintptr_t)xw16) & 15) || ((uintptr_t)xdbl_tm & 7))
         return FD_ERR_UNSUPPORTED;
-    if (!fuse_dt && ((Rp != 16 && Rp != 32) || R > Rp || Rp > (R + 2 * N + 15) / 16 * 16 || ((uintptr_t)dw16 & 3) || ((uintptr_t)dts_tm & 3) ||
+    if (!fuse_dt && ((Rp != 16 && Rp != 32) || R > Rp || Rp > (R + 2 * N + 15) / 16 * 16 || ((uintptr_t)dw16 & 3) || ((uintptr_t)dts_tm & 15) ||
                      ((uintptr_t)dt_bias & 7)))
         return FD_ERR_UNSUPPORTED;
     if (dtype == FD_BF16) return x_proj_tm_launch<__nv_bfloat16>(xs_tm, xw16, xdbl_tm, dw16, dts_tm, dt_bias, B, D, L, R, N, Rp, fuse_dt, stream);
