@@ -461,21 +461,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const float inv_c = 1.f / (float)p.c0;
             int stage = 0, it = 0;
             uint32_t ph = 0;
-            auto acc8 = [&](const uint4& v, float& sum, float& sq) {
+            // sums as packed fp32 pairs (one FADD2 + one FFMA2 per two channels): an ablation showed the statistics ARITHMETIC, not
+            // their loads or the barrier protocol, bounding this instantiation (64 -> 256: 759 us; 577 us with the accumulation
+            // skipped, against 558 us for the plain GEMM), i.e. the two statistics warps are the critical path of the block
+            auto acc8 = [&](const uint4& v, u64& sum, u64& sq) {
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float2 f;
                     if (q.fmt) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
                     else f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-                    sum += f.x + f.y;
-                    sq = fmaf(f.x, f.x, fmaf(f.y, f.y, sq));
+                    const u64 f2 = f2_pack(f.x, f.y);
+                    sum = f2_add(sum, f2);
+                    sq = f2_fma(f2, f2, sq);
                 }
             };
             const int row0 = (warp - 2 - NUM_EPI_WARPS) * 64 + lane;            // this lane's rows: row0 and row0 + 32 (same row & 7)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
-                float sm[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
+                u64 sm[2] = {0ull, 0ull}, sq[2] = {0ull, 0ull};
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], ph);
                     const uint8_t* sa = smem + (size_t)stage * stage_bytes + row0 * 128;
@@ -503,8 +507,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);     // the epilogue has read the statistics of tile it - 2
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                    const float mean = sm[r] * inv_c;
-                    s_ln[buf * BM + row0 + r * 32] = make_float2(mean, rsqrtf(fmaxf(sq[r] * inv_c - mean * mean, 0.f) + p.ln_eps));
+                    float s0, s1, q0, q1;
+                    f2_unpack(sm[r], s0, s1);
+                    f2_unpack(sq[r], q0, q1);
+                    const float mean = (s0 + s1) * inv_c;
+                    s_ln[buf * BM + row0 + r * 32] = make_float2(mean, rsqrtf(fmaxf((q0 + q1) * inv_c - mean * mean, 0.f) + p.ln_eps));
                 }
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&sfull_bar[buf])) : "memory");

@@ -353,12 +353,11 @@ class UnetEngine:
             wf_qkv = self.buf(f"WFQKV.{p}", B, 3 * C, C, dtype=tdt)
             v_in = torch.zeros(B, 4 * C, device=dev, dtype=torch.float32)
             v_q = torch.zeros(B, 3 * C, device=dev, dtype=torch.float32)
-            # row statistics by a separate one-read pass (fd_row_rstd, 4 bytes written per pixel) instead of the GEMM's statistics
-            # warps: the folded GEMMs then run at the plain kernel's speed (64 -> 256 at 16 x 512^2: 715 -> 561 us for a 90 us pass)
-            # Measured per level (B = 16, kernel table of bench.py): at C >= 128 the GEMM has two or more K blocks and N tiles and
-            # gains more (128 -> 512: 519 -> 360 us, 128 -> 384: 470 -> 278) than the pass costs (61 us); at C = 64 the epilogue, not
-            # the statistics, bounds the GEMM (727 us either way) and the pass (110 us) is a loss.  FD_LN_RSTD=0 / =all override.
-            ext_rstd = {"0": False, "all": C in (64, 128, 256, 512)}.get(os.environ.get("FD_LN_RSTD", "1"), C in (128, 256, 512))
+            # Row statistics: the GEMM's own statistics warps (default) or a separate one-read pass (fd_row_rstd, 4 bytes per pixel,
+            # FD_LN_RSTD=1: at C >= 128, =all: everywhere).  The pass won while the statistics warps accumulated in scalar fp32 and
+            # were the critical path of the block (64 -> 256: 759 us against 665 + a 110 us pass); on packed fp32 pairs they are not
+            # (627 us), and per level the two forms now measure equal or better for the in-kernel one, which needs no extra launch.
+            ext_rstd = {"1": C in (128, 256, 512), "all": C in (64, 128, 256, 512)}.get(os.environ.get("FD_LN_RSTD", "0"), False)
             rstd = self.buf(f"RSTD{l}", B, P, dtype=torch.float32) if ext_rstd else None
             try:
                 c_in = ops.Conv(x_in, wf_in, xz, B=B, Hin=h, Win=w, silu_from=2 * C, per_batch_weight=True, prefer_tc=True,
