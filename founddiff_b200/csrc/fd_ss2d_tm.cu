@@ -347,61 +347,60 @@ __global__ void __launch_bounds__(256) x_proj_tm_kernel(const T* __restrict__ xs
         }
         const T* wd = dw16 + (long)k * D * Rp;
         const float* bk_bias = dt_bias + (long)k * D;
-        // B fragments (dt_proj weights, K-contiguous rows of dw16) come straight from global memory / L1: they are the same for
-        // every block of a direction.  The loads of n-tile nd + 1 are issued before the MMAs and the softplus epilogue of n-tile
-        // nd, so their latency sits under ~60 instructions of work instead of in front of every MMA.
+        // B fragments (dt_proj weights, K-contiguous rows of dw16) come straight from global memory (L1 / L2: the same for every
+        // block of a direction).  One 64-channel GROUP at a time: the loads of all 8 n-tiles of the group are issued together,
+        // then 8 independent (MMA -> softplus -> tile store) chains follow, fully unrolled — as a one-n-tile loop with a
+        // one-deep prefetch a warp sat out an L2 round trip and a 150-cycle dependent softplus chain per n-tile (D = 1024:
+        // 128 of them per block, 0.36 instructions per clock and SM).
         const int nk = Rp / 16;
-        uint32_t bcur[2][2], bnxt[2][2];
-        float2 bbc, bbn;
-        auto load_b = [&](int nd, uint32_t (&bf)[2][2], float2& bb) {
-            const T* wrow = wd + (long)(nd * 8 + g) * Rp + 2 * t4;
-#pragma unroll
-            for (int kt = 0; kt < 2; ++kt) {
-                if (kt < nk) {
-                    bf[kt][0] = *reinterpret_cast<const uint32_t*>(wrow + kt * 16);
-                    bf[kt][1] = *reinterpret_cast<const uint32_t*>(wrow + kt * 16 + 8);
-                } else {
-                    bf[kt][0] = bf[kt][1] = 0u;
-                }
-            }
-            bb = __ldg(reinterpret_cast<const float2*>(bk_bias + nd * 8 + 2 * t4));
-        };
-        load_b(0, bcur, bbc);
-        const int nnd = D / 8;
+        const int ngroups = D / 64;
         // delta leaves through a per-warp shared-memory tile (16 steps x 64 channels, the pipeline's buffers are free by now): a C
         // fragment holds 2 adjacent channels per lane, so storing from it a warp instruction wrote eight 16-byte pieces in eight
-        // cache lines (the deep levels, D = 512 / 1024, ran at 1.3 - 2.1 TB/s on it); read back by rows, a lane writes 16 bytes
-        // and a warp instruction four complete 128-byte row segments.
+        // cache lines; read back by rows, a lane writes 16 bytes and a warp instruction four complete 128-byte row segments.
         __syncthreads();                                  // every warp is out of the stage-1 loop: s_a is reusable
         constexpr int OT = 64 + 8;                        // tile row pitch (elements): the 8 rows of a fragment store hit 32 banks
         T* ot = s_a + warp * 16 * OT;
-        for (int nd = 0; nd < nnd; ++nd) {
-            if (nd + 1 < nnd) load_b(nd + 1, bnxt, bbn);
-            float o[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int gr = 0; gr < ngroups; ++gr) {
+            uint32_t bf[8][2][2];
+            float2 bb[8];
 #pragma unroll
-            for (int kt = 0; kt < 2; ++kt)
-                if (kt < nk) mma_16816<T>(o, afr[kt], bcur[kt][0], bcur[kt][1]);
-            const int dc = (nd & 7) * 8 + 2 * t4;         // column inside the 64-channel group
-            float s0, s1, s2, s3;                         // softplus on packed pairs: the deep levels (D = 512 / 1024 softplus per step) are
-            tm_softplus2(o[0] + bbc.x, o[1] + bbc.y, s0, s1);     // bound by this epilogue's issue slots and MUFU ops, not by HBM
-            tm_softplus2(o[2] + bbc.x, o[3] + bbc.y, s2, s3);
-            *reinterpret_cast<uint32_t*>(ot + g * OT + dc) = tm_pack2<T>(s0, s1);
-            *reinterpret_cast<uint32_t*>(ot + (g + 8) * OT + dc) = tm_pack2<T>(s2, s3);
-            if ((nd & 7) == 7) {                          // D % 64 == 0: a group is always complete
-                __syncwarp();
-                const int d0 = (nd & ~7) * 8 + (lane & 7) * 8;
+            for (int i = 0; i < 8; ++i) {
+                const int nd = gr * 8 + i;
+                const T* wrow = wd + (long)(nd * 8 + g) * Rp + 2 * t4;
 #pragma unroll
-                for (int ps = 0; ps < 4; ++ps) {
-                    const int rr = ps * 4 + (lane >> 3);
-                    const int row = l0 + warp * 16 + rr;
-                    const uint4 v = *reinterpret_cast<const uint4*>(ot + rr * OT + (lane & 7) * 8);
-                    if (row < L) *reinterpret_cast<uint4*>(dts + ((long)bk * L + row) * D + d0) = v;
+                for (int kt = 0; kt < 2; ++kt) {
+                    if (kt < nk) {
+                        bf[i][kt][0] = *reinterpret_cast<const uint32_t*>(wrow + kt * 16);
+                        bf[i][kt][1] = *reinterpret_cast<const uint32_t*>(wrow + kt * 16 + 8);
+                    } else {
+                        bf[i][kt][0] = bf[i][kt][1] = 0u;
+                    }
                 }
-                __syncwarp();
+                bb[i] = __ldg(reinterpret_cast<const float2*>(bk_bias + nd * 8 + 2 * t4));
             }
 #pragma unroll
-            for (int kt = 0; kt < 2; ++kt) { bcur[kt][0] = bnxt[kt][0]; bcur[kt][1] = bnxt[kt][1]; }
-            bbc = bbn;
+            for (int i = 0; i < 8; ++i) {
+                float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt)
+                    if (kt < nk) mma_16816<T>(o, afr[kt], bf[i][kt][0], bf[i][kt][1]);
+                const int dc = i * 8 + 2 * t4;            // column inside the 64-channel group
+                float s0, s1, s2, s3;                     // softplus on packed pairs
+                tm_softplus2(o[0] + bb[i].x, o[1] + bb[i].y, s0, s1);
+                tm_softplus2(o[2] + bb[i].x, o[3] + bb[i].y, s2, s3);
+                *reinterpret_cast<uint32_t*>(ot + g * OT + dc) = tm_pack2<T>(s0, s1);
+                *reinterpret_cast<uint32_t*>(ot + (g + 8) * OT + dc) = tm_pack2<T>(s2, s3);
+            }
+            __syncwarp();
+            const int d0 = gr * 64 + (lane & 7) * 8;
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                const int rr = ps * 4 + (lane >> 3);
+                const int row = l0 + warp * 16 + rr;
+                const uint4 v = *reinterpret_cast<const uint4*>(ot + rr * OT + (lane & 7) * 8);
+                if (row < L) *reinterpret_cast<uint4*>(dts + ((long)bk * L + row) * D + d0) = v;
+            }
+            __syncwarp();
         }
     }
 }
