@@ -400,15 +400,17 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_nhwc_v2_kernel(const T* __re
 }
 
 constexpr int QK_LD = 40;      // padded row (elements) of the q / k tiles: conflict-free ldmatrix
-constexpr int GR_TILE = 256;   // pixels per staged tile
+constexpr int GR_TILE = 128;   // pixels per staged tile
+constexpr int GR_STAGES = 4;   // cp.async ring: 3 tiles (24 KB per block, 2 blocks per SM) in flight — with two 256-pixel buffers (one
+                               // tile in flight per block) the kernel was bound by latency x bytes in flight at 0.57 of the HBM roof
 constexpr int GR_PIX = 4096;   // pixels per block
 
 template <typename T>
 __global__ void __launch_bounds__(256) gram_mma_kernel(const T* __restrict__ qkv, int ld, float* __restrict__ gram,
                                                        float* __restrict__ qk_sq, float* __restrict__ ws, int P, int C, int pf_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_qk = reinterpret_cast<T*>(smem_raw);                      // [2 buffers][2 (q,k)][256][QK_LD]
-    float* s_red = reinterpret_cast<float*>(s_qk + 2 * 2 * GR_TILE * QK_LD);   // [32*32 + 2*32]
+    T* s_qk = reinterpret_cast<T*>(smem_raw);                      // [GR_STAGES][2 (q,k)][GR_TILE][QK_LD]
+    float* s_red = reinterpret_cast<float*>(s_qk + GR_STAGES * 2 * GR_TILE * QK_LD);   // [32*32 + 2*32]
     const int head = blockIdx.x, b = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long p_begin = (long)blockIdx.y * GR_PIX;
@@ -444,25 +446,22 @@ __global__ void __launch_bounds__(256) gram_mma_kernel(const T* __restrict__ qkv
 #pragma unroll
                 for (int e = 0; e < 4; ++e) accd[a][mt][ns][e] = 0.f;
     }
-    stage(0, 0);
+#pragma unroll
+    for (int st = 0; st < GR_STAGES - 1; ++st) {
+        if (st < ntiles) stage(st, st);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int tile = 0; tile < ntiles; ++tile) {
-        const int buf = tile & 1;
-        if (tile + 1 < ntiles) { stage(tile + 1, buf ^ 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (pf_tiles > 0 && tile + 1 + pf_tiles < ntiles) {     // one 16 KB stage in flight per block bounds the kernel by latency x
-            const long p = p_begin + (long)(tile + 1 + pf_tiles) * GR_TILE + tid;   // bytes in flight: pull later tiles into L2
-            if (p < p_end) {
-                const T* src = qkv + ((long)b * P + p) * ld + head * HD;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(src + C));
-            }
-        }
-        __syncthreads();
+        const int buf = tile % GR_STAGES;
+        asm volatile("cp.async.wait_group %0;" ::"n"(GR_STAGES - 2) : "memory");          // tile `tile` has landed (this thread's part)
+        __syncthreads();                                 // ... for everybody, and every warp is done with tile - 1: its buffer is refilled
+        if (tile + GR_STAGES - 1 < ntiles) stage(tile + GR_STAGES - 1, (tile + GR_STAGES - 1) % GR_STAGES);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
         const T* s_q = s_qk + (size_t)buf * 2 * GR_TILE * QK_LD;
         const T* s_k = s_q + GR_TILE * QK_LD;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {                 // each warp owns 32 pixels of the tile
-            const int p0 = warp * 32 + ks * 16;
+        for (int ks = 0; ks < GR_TILE / 128; ++ks) {     // each warp owns GR_TILE / 8 pixels of the tile
+            const int p0 = warp * (GR_TILE / 8) + ks * 16;
             uint32_t aq[2][4], ak[2][4], bq[2][4], bk[2][4];
             const int ar = p0 + (lane & 7) + 8 * (lane >> 4), ac = 8 * ((lane >> 3) & 1);
 #pragma unroll
@@ -488,8 +487,8 @@ __global__ void __launch_bounds__(256) gram_mma_kernel(const T* __restrict__ qkv
                 }
             }
         }
-        __syncthreads();                                 // buffer `buf` may be refilled by the next-but-one stage
     }
+    __syncthreads();
     // the 8 warps add their accumulators into s_red one after the other (warp order = pixel order): no shared-memory atomics
     for (int wsel = 0; wsel < 8; ++wsel) {
         if (warp == wsel) {
@@ -624,7 +623,7 @@ extern "C" int fd_dwconv3x3_nhwc(const void* in, const float* w, const float* bi
 
 template <typename T>
 static int gram_launch(const void* qkv, int ld, float* gram, float* qk_sq, float* ws, int B, int P, int C, cudaStream_t stream) {
-    const size_t smem = (size_t)2 * 2 * GR_TILE * QK_LD * sizeof(T) + (size_t)(HD * HD + 2 * HD) * sizeof(float);
+    const size_t smem = (size_t)GR_STAGES * 2 * GR_TILE * QK_LD * sizeof(T) + (size_t)(HD * HD + 2 * HD) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(gram_mma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
