@@ -864,7 +864,8 @@ int scan_tw_launch(const void* u_tm, const float* xdbl, const float* A, const fl
 template <typename T, int NS, int RDT, int ST, int TW, int VAR>
 __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
     const T* __restrict__ u_tm, const float* __restrict__ xdbl, const float* __restrict__ A, const float* __restrict__ dt_w,
-    const float* __restrict__ dt_bias, const float* __restrict__ Dskip, T* __restrict__ y, int D, int L, int H, int W) {
+    const float* __restrict__ dt_bias, const float* __restrict__ Dskip, T* __restrict__ y, int D, int L, int H, int W, int nseg,
+    uint32_t* __restrict__ chain_ws) {
     constexpr int XR = RDT + 2 * NS;
     constexpr int CH = TW * ST;                          // steps per chunk
     constexpr int NP = NS / 2, RP = RDT / 2, NQ = NS / 4;
@@ -884,8 +885,33 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
     T* s_u = reinterpret_cast<T*>(s_cy + 2 * NP * 32);   // [TW][ST][32]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_u + TW * ST * 32);   // TMEM base address of the block's allocation
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int bk = blockIdx.y, k = bk & 3, b = bk >> 2;
-    const int ch0 = blockIdx.x * 32;
+    // Chained segments (nseg > 1, grid.z = nseg): a row of L steps is cut into nseg segments that are separate blocks; the state
+    // leaving a segment travels to its successor through global memory behind a release / acquire flag.  256 rows on 2 x 148
+    // block slots left 40 SMs with one block (done at 0.59 of the kernel's time, ncu: l1tex__cycles_active min / max); with short
+    // blocks the hardware scheduler refills the slots and every SM works until the last segments.  Which (segment, row) a block
+    // takes comes from a ticket drawn in START order, segment-major — the predecessor of a block holds a smaller ticket, so it is
+    // resident or finished whenever its successor waits for it: no deadlock whatever order the blocks are dispatched in.
+    // Arithmetic is untouched (the carried state is the fp32 s_cy row of the unchained kernel): results are bit-identical.
+    int bx = (int)blockIdx.x, bk = (int)blockIdx.y, seg = 0, link = 0;
+    if (nseg > 1) {
+        if (threadIdx.x == 0) {
+            const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
+            const uint32_t t = atomicAdd(chain_ws, 1u);
+            if (t == total - 1) atomicExch(chain_ws, 0u);          // every ticket of this launch is drawn: ready for the next launch
+            s_tmem[1] = t;
+        }
+        __syncthreads();
+        const uint32_t t = s_tmem[1], units = gridDim.x * gridDim.y;
+        seg = (int)(t / units);
+        const uint32_t un = t - (uint32_t)seg * units;
+        bk = (int)(un / gridDim.x);
+        bx = (int)(un - (uint32_t)bk * gridDim.x);
+        link = (int)un * (nseg - 1) + seg;                          // link seg -> seg + 1 of this row (seg - 1 -> seg is link - 1)
+    }
+    uint32_t* const chain_flag = chain_ws + 1;
+    u64* const chain_carry = reinterpret_cast<u64*>(chain_ws + ((1 + gridDim.x * gridDim.y * (uint32_t)(nseg - 1) + 3u) & ~3u));
+    const int k = bk & 3, b = bk >> 2;
+    const int ch0 = bx * 32;
     const int dloc = ch0 + lane;
     const int d = k * D + dloc;
     const T* ug = u_tm + (long)bk * L * D + ch0;
@@ -918,7 +944,7 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
     for (int r = 0; r < RP; ++r) wdt[r] = f2_pack(dt_w[(long)d * RDT + 2 * r], dt_w[(long)d * RDT + 2 * r + 1]);
     const u64 bias2 = f2_pack(dt_bias[d], 0.f);
     const float Dd = Dskip[d];
-    if (warp == 0) {
+    if (warp == 0 && seg == 0) {
 #pragma unroll
         for (int j = 0; j < NP; ++j) s_cy[j * 32 + lane] = 0ull;          // entry state of chunk 0 (published by the first barrier)
     }
@@ -948,13 +974,14 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
     // straddle a merge row here, so inside a slice the store address moves by a constant stride.
     const int col = k & 1, kx = k >> 1;
     const int mdiv = col ? (H >> 1) : (W >> 1);
-    int mq = (warp * ST) / mdiv, mr = (warp * ST) - mq * mdiv;
+    const int nchunks = (L / CH) / nseg;                 // chunks of this block's segment
+    const int step0 = seg * nchunks * CH;                // first step of the segment
+    int mq = (step0 + warp * ST) / mdiv, mr = (step0 + warp * ST) - mq * mdiv;
     const int inc = col ? 2 * W * D : 2 * D;
     T* ybase = y + (long)b * H * W * D + dloc;
-    const int nchunks = L / CH;
-    stage(warp * ST);
+    stage(step0 + warp * ST);
     for (int c = 0; c < nchunks; ++c) {
-        const int t0 = c * CH + warp * ST;
+        const int t0 = step0 + c * CH + warp * ST;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         // ---- phase A: local scan(s) of the slice from h = 0.  NSL = 2: the slice is two half-slices scanned in lockstep (two
@@ -1048,6 +1075,22 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
         }
         __syncwarp();                                    // every lane is done reading the staged slice
         if (c + 1 < nchunks) stage(t0 + CH);
+        if (seg > 0 && c == 0 && warp == 0) {            // entry state of the segment: wait for the predecessor (phase A is done already)
+            uint32_t* flag = chain_flag + (link - 1);
+            uint32_t ready, polls = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ready) : "l"(flag) : "memory");
+                if (!ready) {
+                    __nanosleep(100);
+                    if (++polls > (1u << 24)) __trap();  // > 1.5 s for a hand-over that takes microseconds: a workspace that was not
+                }                                        // zero-filled (or is shared by two launches) — fail loudly instead of hanging
+            } while (!ready);
+            const u64* cg = chain_carry + (size_t)(link - 1) * NP * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) s_cy[j * 32 + lane] = __ldcg(cg + j * 32);
+            __syncwarp();
+            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(flag) = 0u;      // one consumer per flag: clean for the next launch
+        }
         __syncthreads();                                 // slices (and the entry state) of chunk c are published
         // ---- fold: state entering this warp's slice (and its second half)
         u64 hin[NSL][NP];
@@ -1067,8 +1110,19 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
         }
         if (warp == TW - 1) {                            // exit state of the chunk = entry state of the next one
             u64* cy = s_cy + ((c + 1) & 1) * NP * 32 + lane;
+            const bool hand_over = c == nchunks - 1 && seg + 1 < nseg;         // the successor segment is another block
+            u64* cg = chain_carry + (size_t)link * NP * 32 + lane;
 #pragma unroll
-            for (int j = 0; j < NP; ++j) cy[j * 32] = f2_fma(P[NSL - 1][j], hin[NSL - 1][j], hl[NSL - 1][j]);
+            for (int j = 0; j < NP; ++j) {
+                const u64 hx = f2_fma(P[NSL - 1][j], hin[NSL - 1][j], hl[NSL - 1][j]);
+                cy[j * 32] = hx;
+                if (hand_over) __stcg(cg + j * 32, hx);
+            }
+            if (hand_over) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(chain_flag + link), "r"(1u) : "memory");
+            }
         }
         // ---- fix-up + EfficientMerge store
         {
@@ -1117,7 +1171,7 @@ __global__ void __launch_bounds__(TW * 32, (TW == 8 ? 2 : 4)) scan_tw2_kernel(
 
 template <typename T, int NS, int RDT, int ST, int TW, int VAR>
 int scan_tw2_launch_v(const void* u_tm, const float* xdbl, const float* A, const float* dt_w, const float* dt_bias, const float* Dskip,
-                      void* y, int B, int D, int H, int W, cudaStream_t st) {
+                      void* y, int B, int D, int H, int W, int nseg, uint32_t* chain_ws, cudaStream_t st) {
     const int L = (H / 2) * (W / 2);
     constexpr int XR = RDT + 2 * NS, GS = (VAR & 8) ? 0 : NS * 32 + ((VAR & 1) ? 32 : 0);
     const size_t smem = ((size_t)TW * ST * GS + (size_t)TW * ST * XR) * sizeof(float) +
@@ -1128,19 +1182,20 @@ int scan_tw2_launch_v(const void* u_tm, const float* xdbl, const float* A, const
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    scan_tw2_kernel<T, NS, RDT, ST, TW, VAR><<<dim3(D / 32, B * 4), TW * 32, smem, st>>>((const T*)u_tm, xdbl, A, dt_w, dt_bias, Dskip, (T*)y, D, L, H, W);
+    scan_tw2_kernel<T, NS, RDT, ST, TW, VAR><<<dim3(D / 32, B * 4, nseg), TW * 32, smem, st>>>((const T*)u_tm, xdbl, A, dt_w, dt_bias, Dskip, (T*)y, D, L, H, W,
+                                                                                              nseg, chain_ws);
     FD_LAUNCH_CHECK();
     return 0;
 }
 template <typename T, int NS, int RDT, int ST, int TW>
 int scan_tw2_launch(const void* u_tm, const float* xdbl, const float* A, const float* dt_w, const float* dt_bias, const float* Dskip,
-                    void* y, int B, int D, int H, int W, cudaStream_t st) {
+                    void* y, int B, int D, int H, int W, int nseg, uint32_t* chain_ws, cudaStream_t st) {
     // measured at B = 16 (profiles/r2_scan_tw2_notes.txt): delta formed ahead (VAR 2) 1705 us vs 1730 at the level-0 shape; y_local in
     // shared memory (bit 0) 1838 and two half-slices in lockstep (bit 2) 1738 — the kernel is bound by the shared-memory data pipe
     // (19 wavefronts per warp-step), not by registers or by the recurrence's latency, so neither helps
     static const bool smem_rows = getenv("FD_SCAN_TW2_TMEM") && atoi(getenv("FD_SCAN_TW2_TMEM")) == 0;
-    if (smem_rows) return scan_tw2_launch_v<T, NS, RDT, ST, TW, 2>(u_tm, xdbl, A, dt_w, dt_bias, Dskip, y, B, D, H, W, st);
-    return scan_tw2_launch_v<T, NS, RDT, ST, TW, 10>(u_tm, xdbl, A, dt_w, dt_bias, Dskip, y, B, D, H, W, st);
+    if (smem_rows) return scan_tw2_launch_v<T, NS, RDT, ST, TW, 2>(u_tm, xdbl, A, dt_w, dt_bias, Dskip, y, B, D, H, W, nseg, chain_ws, st);
+    return scan_tw2_launch_v<T, NS, RDT, ST, TW, 10>(u_tm, xdbl, A, dt_w, dt_bias, Dskip, y, B, D, H, W, nseg, chain_ws, st);
 }
 
 // K3c applies when no slice is ragged and no slice straddles an EfficientMerge row
@@ -1149,6 +1204,27 @@ static bool tw2_ok(int H, int W, int ST, int TW) {
     const int L = (H / 2) * (W / 2);
     return !off && L % (TW * ST) == 0 && (W / 2) % ST == 0 && (H / 2) % ST == 0;
 }
+
+// Chained segments of the packed time-sliced kernel (see scan_tw2_kernel): how many blocks a row is cut into.  Measured at B = 16
+// (gpurun_out/chain_sweep.log -> profiles/r2_scan_chain_sweep.txt): segments of 16 chunks are the optimum at all three time-sliced
+// shapes (level 0 N4: 1637 us unchained, 1441 with 32 segments; N8 R4: 714 -> 649 with 16; N8 R8 x4 warps: 1357 -> 1160 with 32);
+// 2 segments are slower than none (the waiting successor holds a block slot), 8-chunk segments pay the block prologue too often.
+// FD_SCAN_CHAIN = 0 / 1 switches chaining off, any other value is the segment count.  0 = the geometry is not chained.
+static int chain_segments(int H, int W, int ST, int TW) {
+    const char* env = getenv("FD_SCAN_CHAIN");           // read per call (plan time and launch, never inside a graph replay): sweepable
+    if (!tw2_ok(H, W, ST, TW)) return 0;
+    const int nchunks = (H / 2) * (W / 2) / (TW * ST);
+    int n = env ? atoi(env) : nchunks / 16;
+    if (n <= 1) return 0;
+    while (n & (n - 1)) n &= n - 1;                      // power of two (nchunks is one for the image sizes of interest; else halve)
+    while (n > 1 && (nchunks % n || nchunks / n < 4)) n >>= 1;
+    return n >= (env ? 2 : 4) ? n : 0;
+}
+static long chain_ws_floats(int B, int D, int dstate, int nseg) {       // ticket counter | flags (16-byte padded) | carried states
+    const long links = (long)B * 4 * (D / 32) * (nseg - 1);
+    return ((1 + links + 3) & ~3L) + links * dstate * 32;
+}
+static int tw_steps(int dstate) { return dstate == 4 ? 16 : 8; }        // ST of the SCTW2_CASE table below
 
 // Which scan a geometry gets: 0 = segmented channel-per-lane (scan_tm_kernel), 8 / 4 = time-sliced with that many warps.
 // The time-sliced kernel needs ALL its blocks resident at once (a block walks a whole row): 2 blocks per SM with 8 warps,
@@ -1313,8 +1389,8 @@ extern "C" int fd_selective_scan_tm(const void* u_tm, const void* dts_tm, const 
         if (segments < 0 && tw != 8 && tw != 4) return FD_ERR_BAD_ARGUMENT;
 #define SCTW2_CASE(NSV, RV, STV, TWV)                                                                                              \
     if (!force_b && tw == TWV && dstate == NSV && dt_rank_fused == RV && tw2_ok(H, W, STV, TWV)) {                                 \
-        if (io_dtype == FD_BF16) return scan_tw2_launch<__nv_bfloat16, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, stream); \
-        if (io_dtype == FD_F16) return scan_tw2_launch<__half, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, stream); \
+        if (io_dtype == FD_BF16) return scan_tw2_launch<__nv_bfloat16, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, 1, nullptr, stream); \
+        if (io_dtype == FD_F16) return scan_tw2_launch<__half, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, 1, nullptr, stream); \
         return FD_ERR_UNSUPPORTED;                                                                                                 \
     }
         SCTW2_CASE(4, 4, 16, 8) SCTW2_CASE(4, 4, 16, 4) SCTW2_CASE(8, 4, 8, 8) SCTW2_CASE(8, 4, 8, 4) SCTW2_CASE(8, 8, 8, 8) SCTW2_CASE(8, 8, 8, 4)
@@ -1342,5 +1418,36 @@ extern "C" int fd_selective_scan_tm(const void* u_tm, const void* dts_tm, const 
     }
     SCTM_CASE(4, 4) SCTM_CASE(8, 4) SCTM_CASE(8, 8) SCTM_CASE(16, 8) SCTM_CASE(4, 0) SCTM_CASE(8, 0) SCTM_CASE(16, 0) SCTM_CASE(32, 0)
 #undef SCTM_CASE
+    return FD_ERR_UNSUPPORTED;
+}
+
+extern "C" int fd_scan_tm_chain_plan(int B, int D, int H, int W, int dstate, int dt_rank_fused, int* ws_floats) {
+    if (ws_floats) *ws_floats = 0;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1) || D % 32) return 0;
+    const int tw = pick_time_warps(B, D, H / 2, W / 2, dstate, dt_rank_fused);
+    if (tw != 8 && tw != 4) return 0;
+    if (!((dstate == 4 && dt_rank_fused == 4) || (dstate == 8 && (dt_rank_fused == 4 || dt_rank_fused == 8)))) return 0;
+    const int nseg = chain_segments(H, W, tw_steps(dstate), tw);
+    if (nseg && ws_floats) *ws_floats = (int)chain_ws_floats(B, D, dstate, nseg);
+    return nseg;
+}
+
+extern "C" int fd_selective_scan_tm_chained(const void* u_tm, const float* xdbl_tm, const float* A, const float* dt_w, const float* dt_bias,
+                                            const float* D_skip, float* chain_ws, long chain_floats, void* y_nhwc, int B, int D, int H,
+                                            int W, int dstate, int dt_rank_fused, int io_dtype, cudaStream_t stream) {
+    if (!u_tm || !xdbl_tm || !A || !dt_w || !dt_bias || !D_skip || !chain_ws || !y_nhwc) return FD_ERR_BAD_ARGUMENT;
+    int need = 0;
+    const int nseg = fd_scan_tm_chain_plan(B, D, H, W, dstate, dt_rank_fused, &need);
+    if (nseg <= 1) return FD_ERR_UNSUPPORTED;
+    if (chain_floats < need || ((uintptr_t)chain_ws & 15) || (((uintptr_t)u_tm | (uintptr_t)xdbl_tm) & 15)) return FD_ERR_BAD_ARGUMENT;
+    const int tw = pick_time_warps(B, D, H / 2, W / 2, dstate, dt_rank_fused);
+#define SCCH_CASE(NSV, RV, STV, TWV)                                                                                               \
+    if (tw == TWV && dstate == NSV && dt_rank_fused == RV) {                                                                       \
+        if (io_dtype == FD_BF16) return scan_tw2_launch<__nv_bfloat16, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, nseg, (uint32_t*)chain_ws, stream); \
+        if (io_dtype == FD_F16) return scan_tw2_launch<__half, NSV, RV, STV, TWV>(u_tm, xdbl_tm, A, dt_w, dt_bias, D_skip, y_nhwc, B, D, H, W, nseg, (uint32_t*)chain_ws, stream); \
+        return FD_ERR_UNSUPPORTED;                                                                                                 \
+    }
+    SCCH_CASE(4, 4, 16, 8) SCCH_CASE(4, 4, 16, 4) SCCH_CASE(8, 4, 8, 8) SCCH_CASE(8, 4, 8, 4) SCCH_CASE(8, 8, 8, 8) SCCH_CASE(8, 8, 8, 4)
+#undef SCCH_CASE
     return FD_ERR_UNSUPPORTED;
 }

@@ -422,6 +422,10 @@ class UnetEngine:
             xdbl_tm = self.buf(f"XDBLTM.{p}", B, 4, L, XR, dtype=torch.float32)
             S_tm = ops.scan_tm_plan(B, D, h, w, N, R if tm_fuse else 0)      # > 0 segments | -8 / -4 time-sliced kernel
             carry = self.buf(f"CARRY.{p}", B * 4 * max(S_tm, 1) * 2 * N * D, dtype=torch.float32)
+            # time-sliced levels: rows cut into chained segments (short blocks refill the SMs; bit-identical results).  The workspace
+            # holds the ticket counter, the hand-over flags and the carried states: zero-filled here once, every launch leaves it zeroed
+            chain_n, chain_floats = ops.scan_tm_chain_plan(B, D, h, w, N, R) if (tm_fuse and S_tm < 0) else (0, 0)
+            chain_ws = torch.zeros(chain_floats, device=dev, dtype=torch.float32) if chain_n > 1 else None
             dtw_tm = upload(sd[p + ".mamba.dt_projs_weight"].reshape(4 * D, R), dev)
         if fuse_dt:
             xdbl = self.buf(f"XDBL{l}", B, 4, R + 2 * N, L, dtype=torch.float32)
@@ -444,7 +448,7 @@ class UnetEngine:
             holder["gws"] = self._acc_view(acc_gw, self._acc_slices[acc_gw][1])
         self._acc_users.append(bind)
 
-        self.paths[p] = ((f"time-major scan, {S_tm} segment(s)" if S_tm > 0 else f"time-major scan, time-sliced x{-S_tm}")
+        self.paths[p] = (((f"time-major scan, {S_tm} segment(s)" if S_tm > 0 else f"time-major scan, time-sliced x{-S_tm}") + (f", {chain_n} chained segments" if chain_n > 1 else ""))
                          + (", dt_proj fused" if tm_fuse else "") + (", LayerNorm folded into in_proj / qkv" if use_fold else "") + (", fused out_norm / out_proj tail" if fuse_tail else "") if use_tm else
                          "scan_cl time-major B/C" if scan_cl else "dt-fused warp scan" if fuse_dt else
                          "warp scan + merge" if fuse_merge else "reference-layout" if dt == torch.float32 else "warp scan, unfused merge")
@@ -455,7 +459,10 @@ class UnetEngine:
                 ops.dwconv3x3_silu_tm(xz, 4 * C, dw_wt, dw_b, xs_tm, B, h, w, D)
                 if tm_fuse:
                     ops.x_proj_tm(xs_tm, xw16, xdbl_tm, None, None, None, B, D, L, R, N, Rp, True)
-                    ops.selective_scan_tm(xs_tm, None, xdbl_tm, A_neg, dtw_tm, dt_bias, Ds, carry, ys.view(B, P, D), B, D, h, w, N, R, S_tm)
+                    if chain_ws is not None:
+                        ops.selective_scan_tm_chained(xs_tm, xdbl_tm, A_neg, dtw_tm, dt_bias, Ds, chain_ws, ys.view(B, P, D), B, D, h, w, N, R)
+                    else:
+                        ops.selective_scan_tm(xs_tm, None, xdbl_tm, A_neg, dtw_tm, dt_bias, Ds, carry, ys.view(B, P, D), B, D, h, w, N, R, S_tm)
                 else:
                     ops.x_proj_tm(xs_tm, xw16, xdbl_tm, dw16, dts_tm, dt_bias, B, D, L, R, N, Rp, False)
                     ops.selective_scan_tm(xs_tm, dts_tm, xdbl_tm, A_neg, None, None, Ds, carry, ys.view(B, P, D), B, D, h, w, N, 0, S_tm)

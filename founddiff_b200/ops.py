@@ -410,6 +410,25 @@ def selective_scan_tm(u_tm, dts_tm, xdbl, A, dt_w, dt_bias, D_skip, carry, y_nhw
     return y_nhwc
 
 
+def scan_tm_chain_plan(B, D, H, W, N, R_fused):
+    """(segments, workspace floats) of the chained time-sliced scan for this geometry; (0, 0) where it does not apply."""
+    n = ctypes.c_int(0)
+    nseg = int(_lib.load().fd_scan_tm_chain_plan(B, D, H, W, N, R_fused, ctypes.byref(n)))
+    return nseg, int(n.value)
+
+
+def selective_scan_tm_chained(u_tm, xdbl, A, dt_w, dt_bias, D_skip, chain_ws, y_nhwc, B, D, H, W, N, R_fused):
+    """Time-sliced scan + EfficientMerge with chained segments (fd_selective_scan_tm_chained).  chain_ws: fp32 workspace of
+    scan_tm_chain_plan(...)[1] floats, zero-filled once by the caller; same bits as selective_scan_tm."""
+    L = (H // 2) * (W // 2)
+    tw, (nseg, _) = -scan_tm_plan(B, D, H, W, N, R_fused), scan_tm_chain_plan(B, D, H, W, N, R_fused)
+    with _launched("scan_tm", f"{B}x{4 * D}x{L} N{N} R{R_fused} TW{tw} x{nseg}", 1):
+        check(_lib.load().fd_selective_scan_tm_chained(_p(u_tm), _f32(xdbl), _f32(A), _f32(dt_w), _f32(dt_bias), _f32(D_skip),
+                                                       _f32(chain_ws), chain_ws.numel(), _p(y_nhwc), B, D, H, W, N, R_fused,
+                                                       dtype_code(u_tm.dtype), _stream()), "fd_selective_scan_tm_chained")
+    return y_nhwc
+
+
 class LinearAttention:
     """lucidrains LinearAttention between to_qkv and the end of to_out (src/denoising_diffusion_pytorch.py:238-255) as a
     call site with pre-allocated workspace and a persistent per-sample GEMM plan (graph-capturable, no allocation per call):

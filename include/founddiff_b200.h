@@ -242,6 +242,19 @@ int fd_scan_tm_plan(int B, int D, int H, int W, int dstate, int dt_rank_fused);
 int fd_selective_scan_tm(const void* u_tm, const void* dts_tm, const float* xdbl_tm, const float* A, const float* dt_w,
                          const float* dt_bias, const float* D_skip, float* carry_ws, long carry_floats, void* y_nhwc, int B,
                          int D, int H, int W, int dstate, int dt_rank_fused, int segments, int io_dtype, cudaStream_t stream);
+/* The time-sliced scan with CHAINED SEGMENTS (same op, same bits: src/emamba2.py:124-157 + EfficientMerge :238-262).  A row is cut
+ * into fd_scan_tm_chain_plan(...) segments that run as separate short blocks; the state leaving a segment reaches its successor
+ * through chain_ws behind a release / acquire flag, and blocks draw (segment, row) tickets in start order (a predecessor is
+ * always resident or finished: no deadlock).  No exp(dt A) is evaluated twice.  What it buys is balance: 64 x D/32 whole-row
+ * blocks on 2 x 148 slots leave the SMs that hold one block idle for the second half of the launch; short blocks refill the
+ * slots (level 0 at B = 16: 1.57 -> 1.48 ms inside the step).  fd_scan_tm_chain_plan returns the segment count (0: not chained for
+ * this geometry — call fd_selective_scan_tm) and the workspace size in floats.  chain_ws must be ZERO-FILLED ONCE by the caller
+ * before its first use and left alone afterwards (every launch leaves its counter and flags zeroed again); one workspace per
+ * concurrently running launch.  Other arguments as fd_selective_scan_tm with dt_rank_fused > 0. */
+int fd_scan_tm_chain_plan(int B, int D, int H, int W, int dstate, int dt_rank_fused, int* ws_floats);
+int fd_selective_scan_tm_chained(const void* u_tm, const float* xdbl_tm, const float* A, const float* dt_w, const float* dt_bias,
+                                 const float* D_skip, float* chain_ws, long chain_floats, void* y_nhwc, int B, int D, int H,
+                                 int W, int dstate, int dt_rank_fused, int io_dtype, cudaStream_t stream);
 
 /* SS2D consumer: EfficientMerge (src/emamba2.py:238-262) + out_norm LayerNorm(D) (:365) + y*z + local (:747-748).
  * ys: (B,4,D,L); z = columns [z_off, z_off+D) of xz rows (already SiLU'd); local: (B, D) fp32; out: (B,H,W,D).

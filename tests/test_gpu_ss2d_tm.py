@@ -136,6 +136,51 @@ def test_scan_time_major_segments_are_exact(ops, segments, slow):
     assert r < 1.5e-3, r                        # fp16 output rounding alone is ~3e-4
 
 
+@pytest.mark.parametrize("cfg", [(128, 128, 128, 4, 4, 2), (256, 256, 128, 4, 4, 1), (128, 128, 128, 8, 4, 2), (128, 128, 256, 8, 8, 2),
+                                 (256, 128, 256, 8, 8, 4)])
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_chained_time_sliced_scan_is_bit_identical(ops, cfg, dt, monkeypatch):
+    """fd_selective_scan_tm_chained (rows cut into segments that run as separate blocks, the state handed over through global
+    memory) against the one-block-per-row kernel on the same inputs: the SAME bits, launch after launch on one workspace (every
+    launch must leave the ticket counter and the hand-over flags zeroed), with channels whose memory spans many segments; and
+    against the fp32 recurrence of the oracle.  Reference op: src/emamba2.py:124-157, merge :238-262."""
+    H, W, D, N, R, B = cfg
+    L = (H // 2) * (W // 2)
+    nseg, ws_floats = ops.scan_tm_chain_plan(B, D, H, W, N, R)
+    if nseg <= 1:                               # short rows are not chained by default: force it (the variable is read per call)
+        monkeypatch.setenv("FD_SCAN_CHAIN", "4")
+        nseg, ws_floats = ops.scan_tm_chain_plan(B, D, H, W, N, R)
+    if nseg <= 1:
+        pytest.skip(f"geometry {cfg} is not chained on this device (plan {ops.scan_tm_plan(B, D, H, W, N, R)})")
+    g = torch.Generator().manual_seed(H + W + D + N)
+    u_tm = q(torch.randn(B, 4, L, D, generator=g), dt).to("cuda", dt)
+    A = -torch.exp(torch.randn(4 * D, N, generator=g) * 0.3)
+    A[::5] *= 1e-3                              # memory far longer than a segment
+    Dp, bias = torch.randn(4 * D, generator=g), torch.randn(4 * D, generator=g) * 0.5 - 1.0
+    xdbl = torch.randn(B, 4, L, R + 2 * N, generator=g)
+    Wdt = (torch.randn(4, D, R, generator=g) / math.sqrt(R)).reshape(4 * D, R).contiguous()
+    args = (xdbl.cuda(), A.cuda(), Wdt.cuda(), bias.cuda(), Dp.cuda())
+    y0 = torch.full((B, H * W, D), float("nan"), device="cuda", dtype=dt)
+    ops.selective_scan_tm(u_tm, None, args[0], args[1], args[2], args[3], args[4], None, y0, B, D, H, W, N, R,
+                          ops.scan_tm_plan(B, D, H, W, N, R))
+    ws = torch.zeros(ws_floats, device="cuda")
+    links = B * 4 * (D // 32) * (nseg - 1)
+    for it in range(3):
+        y1 = torch.full((B, H * W, D), float("nan"), device="cuda", dtype=dt)
+        ops.selective_scan_tm_chained(u_tm, *args, ws, y1, B, D, H, W, N, R)
+        torch.cuda.synchronize()
+        assert torch.equal(y0.view(torch.int16), y1.view(torch.int16)), f"launch {it}: chained scan differs from the unchained kernel"
+        assert int(ws[: 1 + links].view(torch.int32).abs().sum()) == 0, f"launch {it}: ticket counter / flags not left zeroed"
+    delta_raw = torch.einsum("bklr,kdr->bkdl", xdbl[..., :R], Wdt.view(4, D, R)).reshape(B, 4 * D, L)
+    y_ref = scan_cpu.selective_scan_fwd(u_tm.float().cpu().permute(0, 1, 3, 2).reshape(B, 4 * D, L).contiguous(), delta_raw.contiguous(), A,
+                                        xdbl[..., R:R + N].permute(0, 1, 3, 2).contiguous(), xdbl[..., R + N:].permute(0, 1, 3, 2).contiguous(),
+                                        Dp, bias, True)
+    y_ref = O.efficient_merge(y_ref.view(B, 4, D, L), H, W).permute(0, 2, 3, 1)
+    r = rel(y1.reshape(B, H, W, D), y_ref)
+    print(f"chained scan {cfg} {dt}: {nseg} segments, rel-L2 vs oracle {r:.3e}")
+    assert r < TOL[dt], r
+
+
 @pytest.mark.parametrize("cfg", [(32, 48, 64, 4, 4), (64, 32, 64, 8, 4), (32, 32, 128, 8, 8), (16, 48, 128, 16, 8), (16, 16, 256, 16, 16),
                                  (16, 16, 512, 32, 32), (12, 20, 64, 4, 4)])
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])

@@ -8,7 +8,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 2600 -c
     python bench.py --steps 1 --warmup 3 --no-profile --no-cpu-baseline --no-extras > gpurun_out/final_launches.log 2>&1
 # 2. full captures
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:scan_tw2 -c 1 -o gpurun_out/final_scan_tw2 -f \
-    python tools/prof_scan_tm.py -8 > /dev/null 2>&1
+    python tools/prof_scan_tm.py chain > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 1 -o gpurun_out/final_conv_3x3 -f \
     python bench_micro.py --only conv --pick 3 --iters 1 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 1 -o gpurun_out/final_conv_inproj -f \
