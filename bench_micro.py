@@ -216,8 +216,10 @@ def main():
         for N in sel([1024, 4096]):
             qkv = rn(B, N, 3 * 128)
             out = torch.empty(B, N, 128, device="cuda", dtype=dt)
-            ms = timeit(lambda: ops.flash_attn_d32(qkv, out, B, N, 4, 32 ** -0.5), args.iters)
-            report("flash_attn_d32", f"{B}x{N}x4x32", ms, 4.0 * B * N * 128 * es, 4.0 * B * 4 * N * N * 32)
+            for impl in ("tc", "mma"):
+                ms = timeit(lambda: ops.flash_attn_d32(qkv, out, B, N, 4, 32 ** -0.5, impl=impl), args.iters)
+                report("flash_attn_d32" + ("_tc (tcgen05)" if impl == "tc" else " (mma.sync)"), f"{B}x{N}x4x32", ms, 4.0 * B * N * 128 * es,
+                       4.0 * B * 4 * N * N * 32)
     if args.only in ("", "linattn"):
         # lucidrains LinearAttention (4 heads x 32) at the 256^2 and 512^2 feature maps of the first level (dim 64)
         for H in sel([256, 512]):

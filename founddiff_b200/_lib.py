@@ -16,7 +16,7 @@ FD_F32, FD_BF16, FD_F16 = 0, 1, 2
 EXPORTS = [
     "fd_version", "fd_program_arena_bytes", "fd_program_load", "fd_program_buffer", "fd_program_num_launches", "fd_unet_step", "fd_sample_step", "fd_program_destroy", "fd_ln_fold", "fd_gram_ws_floats", "fd_conv_gn_ws_floats", "fd_gn_stats_ws_floats", "fd_dwconv3x3_silu_tm", "fd_x_proj_tm", "fd_scan_tm_segments", "fd_scan_tm_plan", "fd_selective_scan_tm", "fd_scan_tm_chain_plan", "fd_selective_scan_tm_chained", "fd_selective_scan_fwd", "fd_selective_scan_fwd_merge", "fd_selective_scan_fwd_merge_xdbl", "fd_selective_scan_fwd_merge_cl", "fd_x_proj_tc", "fd_avgpool2x2_nhwc", "fd_slice_metrics", "fd_init_conv7x7_tc", "fd_ln_modulate_io", "fd_row_rstd", "fd_ln_gate", "fd_ln_gate_out_proj", "fd_ln_gate_out_proj_supported", "fd_conv2d_simt", "fd_conv2d_tc_supported", "fd_conv2d_tc_plan_create",
     "fd_conv2d_tc_run", "fd_conv2d_tc_plan_destroy", "fd_init_conv7x7", "fd_ln_modulate", "fd_dwconv3x3_silu_scan",
-    "fd_xdt_proj", "fd_xdt_proj_tc", "fd_merge_ln_gate", "fd_dwconv3x3_qkv_gram", "fd_dwconv3x3_nhwc", "fd_gram_qk", "fd_attn_weff", "fd_gn_stats", "fd_gn_silu_add", "fd_gn_scale_shift_silu", "fd_flash_attn_d32", "fd_linattn_context", "fd_linattn_weff", "fd_softmax_d32",
+    "fd_xdt_proj", "fd_xdt_proj_tc", "fd_merge_ln_gate", "fd_dwconv3x3_qkv_gram", "fd_dwconv3x3_nhwc", "fd_gram_qk", "fd_attn_weff", "fd_gn_stats", "fd_gn_silu_add", "fd_gn_scale_shift_silu", "fd_flash_attn_d32", "fd_flash_attn_d32_tc", "fd_linattn_context", "fd_linattn_weff", "fd_softmax_d32",
     "fd_linear_small", "fd_time_sinusoid", "fd_sampler_init", "fd_final_conv_update", "fd_final_conv_update_obj", "fd_unnormalize", "fd_ddpm_update",
 ]
 
@@ -103,6 +103,7 @@ def load():
         "fd_linear_small": [V] * 5 + [I] * 5 + [V],
         "fd_gn_scale_shift_silu": [V] * 6 + [I, V, V] + [I] * 4 + [F, I, V],
         "fd_flash_attn_d32": [V, V, I, I, I, F, I, V],
+        "fd_flash_attn_d32_tc": [V, V, I, I, I, F, I, V],
         "fd_linattn_context": [V, V, V, V, I, I, I, I, V],
         "fd_linattn_weff": [V, V, V, V, I, I, I, I, F, I, V],
         "fd_softmax_d32": [V, V, I, I, I, I, V],

@@ -1,0 +1,356 @@
+// Bottleneck self-attention of the lucidrains Unet (src/denoising_diffusion_pytorch.py:257-279) on the 5th-generation tensor
+// cores: heads of d = 32 over N = H*W tokens, out = softmax(q k^T * scale) v, flash style.
+//
+// One CTA = 128 queries of one (sample, head); key tiles of 128.  Both contractions are tcgen05.mma (kind::f16, M = 128,
+// cta_group::1) with fp32 accumulators in tensor memory:
+//   S   = Q K_j^T      A = Q   [128 q   x 32 d ],  B = K_j   [128 keys x 32 d ]  -> TMEM columns [0, 128)     2 MMAs (K = 16)
+//   O_j = P_j V_j      A = P_j [128 q   x 128 k],  B = V_j^T [48 rows  x 128 k]  -> TMEM columns [128, 176)   8 MMAs
+// All operands are K-major SWIZZLE_128B tiles written by the CTA's own threads (same canonical layout and descriptors as
+// fd_conv_tc.cu / fd_init_conv_tc.cu: rows of 128 bytes, 16-byte chunk c of row r at ((c ^ (r & 7)) << 4), 8-row groups of
+// 1024 B): Q and K rows carry 32 channels = the first 64 bytes of a 128-byte row (only the two K = 16 steps that exist are
+// issued), K_j arrives by cp.async straight from the qkv tensor, V_j is transposed on the way in (a thread owns a key, loads
+// its 64 bytes one tile ahead and scatters 32 halfwords), P_j is written by the softmax threads.  A thread owns a query row =
+// a TMEM lane: it reads its 128 scores with four tcgen05.ld.32x32b.x32 in flight (one wait), takes the row maximum, writes
+// p = 2^(s scale - m) in the storage type.  Generic-proxy writes are published to the tensor core with fence.proxy.async.
+// O_j is a FRESH accumulator per tile; the running output lives in registers (o = o * corr + O_j), so tensor memory is never
+// read-modify-written.  Per tile one block barrier; behind it one thread issues S_{j+1} FIRST and then the 8 MMAs of O_j, and
+// O_j is only collected in the next iteration after the score load and the maximum — the P V product runs under them.  Two
+// CTAs per SM (79 KB of shared memory, 256 TMEM columns, 244 registers each) overlap one CTA's softmax with the other's MMAs.
+// Roof of the op at d = 32: MUFU.EX2, one per score (128 FLOPs per exp; 16 / clk / SM = ~560 TFLOP/s), not the tensor pipe.
+// The row sums come from the tensor core as well: V^T carries a row of ones, so column 32 of O_j is sum_k P_j[q, k] over the
+// SAME rounded P that multiplies V.
+#include <stdlib.h>
+#include <type_traits>
+
+#include "fd_common.cuh"
+
+namespace {
+
+constexpr int FT_BQ = 128, FT_BK = 128, FT_D = 32;
+constexpr int FT_TILE = 128 * 128;                   // bytes of a [128 rows][128 B] operand tile
+constexpr int FT_VROWS = 48;                         // rows of V^T: 32 channels, a row of ones (-> row sums of P), zero padding to N % 16 == 0
+constexpr int FT_VT = FT_VROWS * 128;                // bytes of one 64-key atom of V^T [48 rows][128 B]
+
+FD_DEVINL uint32_t ft_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FD_DEVINL uint64_t ft_desc(uint32_t saddr) {         // K-major SWIZZLE_128B, SBO = 1024 B, version 1 (see fd_conv_tc.cu)
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+FD_DEVINL uint32_t ft_idesc(int fmt, int n) {        // f32 accumulate, a / b format, K-major both, N >> 3, M = 128
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+FD_DEVINL void ft_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+FD_DEVINL void ft_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ft_smem_u32(bar)) : "memory");
+}
+FD_DEVINL void ft_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(ft_smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+}
+FD_DEVINL void ft_ld32(uint32_t taddr, float (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]),
+          "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]), "=f"(r[17]), "=f"(r[18]),
+          "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]),
+          "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+FD_DEVINL float ft_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <typename T> FD_DEVINL uint32_t ft_pack2(float a, float b) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __half2 h = fd_floats2half2_sat(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+FD_DEVINL void ft_cp16(uint32_t dst, const void* src, bool ok) {
+    const int sz = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+FD_DEVINL float ft_ld1(uint32_t taddr) {
+    float r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(r) : "r"(taddr));
+    return r;
+}
+// 32 TMEM columns into r[0..32) WITHOUT the wait: several of these are issued back to back, then one tcgen05.wait::ld
+FD_DEVINL void ft_ld32_nowait(uint32_t taddr, float* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]), "=f"(r[8]), "=f"(r[9]),
+          "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15]), "=f"(r[16]), "=f"(r[17]), "=f"(r[18]),
+          "=f"(r[19]), "=f"(r[20]), "=f"(r[21]), "=f"(r[22]), "=f"(r[23]), "=f"(r[24]), "=f"(r[25]), "=f"(r[26]), "=f"(r[27]),
+          "=f"(r[28]), "=f"(r[29]), "=f"(r[30]), "=f"(r[31])
+        : "r"(taddr));
+}
+// P pair in the storage type.  PACKED: the exponent pair is rounded to the 16-bit type FIRST and one MUFU op evaluates both
+// (ex2.approx.ftz.bf16x2 / ex2.approx.f16x2): P is stored in that type anyway, the kernel is bound by MUFU.EX2, and the row sum
+// comes from the SAME rounded values (ones row of V^T), so numerator and denominator stay consistent.
+template <typename T, bool PACKED> FD_DEVINL uint32_t ft_p2(float x0, float x1) {
+    if constexpr (PACKED) {
+        uint32_t xin, r;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(xin) : "f"(x1), "f"(x0));
+            asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(xin));
+        } else {
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xin) : "f"(x1), "f"(x0));
+            asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(xin));
+        }
+        return r;
+    } else {
+        return ft_pack2<T>(ft_ex2(x0), ft_ex2(x1));
+    }
+}
+
+template <typename T, bool PACKED>
+__global__ void __launch_bounds__(128, 2) flash_attn_d32_tc_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int heads,
+                                                                   float scale_log2e) {
+    extern __shared__ __align__(1024) uint8_t ft_raw[];
+    uint8_t* smem = ft_raw + ((1024u - (ft_smem_u32(ft_raw) & 1023u)) & 1023u);
+    uint8_t* sQ = smem;                               // [128 q][128 B]     (first 64 B of a row used)
+    uint8_t* sK = sQ + FT_TILE;                       // [128 keys][128 B]
+    uint8_t* sP = sK + FT_TILE;                       // [2 atoms of 64 keys][128 q][128 B]
+    uint8_t* sV = sP + 2 * FT_TILE;                   // [2 atoms][48 rows: 32 d, a row of ones, 15 rows of zeros][128 B]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sV + 2 * FT_VT);      // [0]: S ready, [1]: O_j ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int HC = heads * FT_D, ld = 3 * HC;
+    const int head = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * FT_BQ;
+    const T* base = qkv + (long)b * N * ld + head * FT_D;
+    const uint32_t sQ_u = ft_smem_u32(sQ), sK_u = ft_smem_u32(sK), sP_u = ft_smem_u32(sP), sV_u = ft_smem_u32(sV);
+    constexpr int fmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ft_smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ft_smem_u32(&bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ft_smem_u32(tmem_slot)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {   // rows 32 .. 47 of both V^T atoms, written once: row 32 = ones (O column 32 = row sum of P), the rest zero
+        const uint32_t one2 = fmt ? 0x3F803F80u : 0x3C003C00u;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = tid + u * 128, a = i >> 7, r = 32 + ((i & 127) >> 3), c = i & 7;
+            const uint32_t v = r == 32 ? one2 : 0u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(sV_u + (uint32_t)a * FT_VT + (uint32_t)r * 128u + (uint32_t)(c << 4)), "r"(v) : "memory");
+        }
+    }
+
+    // row r of a [rows][64 B used of 128 B] tile: 4 chunks of 16 bytes, swizzled
+    auto load_rows = [&](uint32_t dst, int col_off, int row0) {      // 128 rows x 4 chunks = 512 copies, 4 per thread
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = tid + u * 128, r = i >> 2, c = i & 3;
+            const bool ok = row0 + r < N;
+            ft_cp16(dst + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4), base + (long)(ok ? row0 + r : 0) * ld + col_off + c * 8, ok);
+        }
+    };
+    // V of key (k0 + tid): 64 bytes into registers (zero past N), scattered later as V^T[d][key]
+    uint4 vreg[4];
+    auto load_v = [&](int k0) {
+        const int key = k0 + tid;
+        const bool ok = key < N;
+        const uint4* src = reinterpret_cast<const uint4*>(base + (long)(ok ? key : 0) * ld + 2 * HC);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vreg[c] = ok ? __ldg(src + c) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    auto store_vt = [&]() {
+        const uint32_t dst = sV_u + (uint32_t)(tid >> 6) * FT_VT;       // atom of this key
+        const uint32_t kc = (uint32_t)((tid & 63) >> 3), kb = (uint32_t)(tid & 7) * 2u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t w[4] = {vreg[c].x, vreg[c].y, vreg[c].z, vreg[c].w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t d = (uint32_t)(c * 8 + e);
+                const unsigned short hv = (unsigned short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + d * 128u + ((kc ^ (d & 7u)) << 4) + kb), "h"(hv) : "memory");
+            }
+        }
+    };
+
+    const int ntiles = (N + FT_BK - 1) / FT_BK;
+    load_rows(sQ_u, 0, q0);
+    load_rows(sK_u, HC, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    load_v(0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tO = tmem + 128u;
+    const uint32_t lane_sel = ((uint32_t)(warp * 32)) << 16;             // this warp's TMEM lane quarter; thread = query row
+    const uint32_t idesc_s = ft_idesc(fmt, 128), idesc_o = ft_idesc(fmt, FT_VROWS);
+    const uint64_t dQ = ft_desc(sQ_u), dK = ft_desc(sK_u), dP = ft_desc(sP_u), dV = ft_desc(sV_u);
+
+    auto issue_s = [&]() {                                               // S = Q K^T: two K = 16 steps (32 B each)
+        ft_mma(tS, dQ, dK, idesc_s, 0u);
+        ft_mma(tS, dQ + 2, dK + 2, idesc_s, 1u);
+        ft_commit(&bar[0]);
+    };
+    if (tid == 0) issue_s();
+
+    float o[FT_D];
+#pragma unroll
+    for (int e = 0; e < FT_D; ++e) o[e] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, corr_prev = 0.f;
+    const int row = tid;                                                 // query row of the tile
+    const uint32_t p_row = sP_u + (uint32_t)row * 128u;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    // o <- o * corr + O_j, l <- l * corr + rowsum_j (column 32 of the accumulator: P_j times the ones row)
+    auto take_o = [&](uint32_t par, float corr) {
+        ft_wait(&bar[1], par);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float oj[32];
+        ft_ld32_nowait(tO + lane_sel, oj);
+        const float lj = ft_ld1(tO + lane_sel + 32u);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < FT_D; ++e) o[e] = fmaf(o[e], corr, oj[e]);
+        l_run = fmaf(l_run, corr, lj);
+    };
+
+    for (int j = 0; j < ntiles; ++j) {
+        const uint32_t par = (uint32_t)(j & 1);
+        ft_wait(&bar[0], par);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // the whole score row in registers: four loads in flight, one wait
+        float s[FT_BK];
+        ft_ld32_nowait(tS + lane_sel, s);
+        ft_ld32_nowait(tS + lane_sel + 32u, s + 32);
+        ft_ld32_nowait(tS + lane_sel + 64u, s + 64);
+        ft_ld32_nowait(tS + lane_sel + 96u, s + 96);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // K_{j+1} into the tile S_j has just finished reading
+        if (j + 1 < ntiles) {
+            load_rows(sK_u, HC, (j + 1) * FT_BK);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        const int kbase = j * FT_BK;
+        if (kbase + FT_BK > N) {                          // ragged last tile: keys past N out of the maximum and of P
+#pragma unroll
+            for (int e = 0; e < FT_BK; ++e) s[e] = kbase + e < N ? s[e] : -INFINITY;
+        }
+        float mx8[8];                                    // eight independent chains (a single one is 128 dependent FMNMX per tile)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx8[i] = s[i];
+#pragma unroll
+        for (int e = 8; e < FT_BK; ++e) mx8[e & 7] = fmaxf(mx8[e & 7], s[e]);
+        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+        const float m_new = fmaxf(m_run, mx * scale_log2e);              // scale > 0
+        const float corr = ft_ex2(m_run - m_new);
+        m_run = m_new;
+        // O_{j-1} is taken only now: its 8 MMAs ran under the score load and the maximum above
+        if (j > 0) take_o(par ^ 1u, corr_prev);
+        corr_prev = corr;
+        // p = 2^(s scale - m) in the storage type -> shared memory (A operand of P V); P's buffer is free: O_{j-1} is complete
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            const uint32_t dst = p_row + (uint32_t)(cb >> 1) * FT_TILE;  // keys [cb*32, +32): atom cb / 2, chunks (cb & 1) * 4 .. + 3
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = cb * 32 + c * 8 + 2 * i;
+                    w[i] = ft_p2<T, PACKED>(fmaf(s[e], scale_log2e, -m_new), fmaf(s[e + 1], scale_log2e, -m_new));
+                }
+                const uint32_t chunk = (uint32_t)((cb & 1) * 4 + c);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + ((chunk ^ rsw) << 4)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3])
+                             : "memory");
+            }
+        }
+        store_vt();                                      // V_j^T (registers loaded during tile j - 1); its buffer is free: O_{j-1} is complete
+        if (j + 1 < ntiles) asm volatile("cp.async.wait_group 0;" ::: "memory");      // this thread's part of K_{j+1}
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                 // P_j, V_j^T, K_{j+1} complete; every thread has S_j and O_{j-1} in registers
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (j + 1 < ntiles) issue_s();               // first: the next tile's softmax starts while O_j is still being multiplied
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ft_mma(tO, dP + (uint64_t)(a * (FT_TILE >> 4) + 2 * k), dV + (uint64_t)(a * (FT_VT >> 4) + 2 * k), idesc_o, (uint32_t)(a | k));
+            ft_commit(&bar[1]);
+        }
+        __syncwarp();
+        if (j + 1 < ntiles) load_v((j + 1) * FT_BK);     // V_{j+1} into registers: in flight under the next tile's score load
+    }
+    take_o((uint32_t)((ntiles - 1) & 1), corr_prev);
+    if (q0 + row < N) {
+        const float inv = 1.f / l_run;
+        T* orow = out + ((long)b * N + q0 + row) * HC + head * FT_D;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint4 v;
+            v.x = ft_pack2<T>(o[8 * c] * inv, o[8 * c + 1] * inv);
+            v.y = ft_pack2<T>(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+            v.z = ft_pack2<T>(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+            v.w = ft_pack2<T>(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+            *reinterpret_cast<uint4*>(orow + 8 * c) = v;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
+}  // namespace
+
+template <typename T, bool PACKED>
+static int ft_launch(const void* qkv, void* out, int B, int N, int heads, float sl, cudaStream_t stream) {
+    const size_t smem = 1024 + (size_t)4 * FT_TILE + (size_t)2 * FT_VT + 64;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(flash_attn_d32_tc_kernel<T, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    dim3 grid((unsigned)fd_cdiv(N, FT_BQ), (unsigned)heads, (unsigned)B);
+    flash_attn_d32_tc_kernel<T, PACKED><<<grid, 128, smem, stream>>>((const T*)qkv, (T*)out, N, heads, sl);
+    FD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fd_flash_attn_d32_tc(const void* qkv, void* out, int B, int N, int heads, float scale, int dtype, cudaStream_t stream) {
+    if (!qkv || !out || B <= 0 || N <= 0 || heads <= 0 || !(scale > 0.f)) return FD_ERR_BAD_ARGUMENT;
+    if ((((uintptr_t)qkv | (uintptr_t)out) & 15)) return FD_ERR_UNSUPPORTED;
+    // Exponentials in fp32, rounded to the storage type afterwards.  FD_FLASH_PACKED=1: one MUFU op per PAIR on 16-bit operands
+    // (ex2.approx.ftz.bf16x2 / .f16x2) — measured 476 us against 456 at 16 x 4096 tokens x 4 heads and 1.5x the rounding error:
+    // with 8 warps per SM the kernel waits on its serial per-tile chain (score load -> maximum -> exponentials -> store -> barrier),
+    // not on the MUFU pipe, so halving the MUFU work buys nothing.  Kept as a switch for the measurement.
+    const char* env = getenv("FD_FLASH_PACKED");
+    const bool packed = env && atoi(env) == 1;
+    const float sl = scale * 1.4426950408889634f;
+    if (dtype == FD_BF16) return packed ? ft_launch<__nv_bfloat16, true>(qkv, out, B, N, heads, sl, stream) : ft_launch<__nv_bfloat16, false>(qkv, out, B, N, heads, sl, stream);
+    if (dtype == FD_F16) return packed ? ft_launch<__half, true>(qkv, out, B, N, heads, sl, stream) : ft_launch<__half, false>(qkv, out, B, N, heads, sl, stream);
+    return FD_ERR_UNSUPPORTED;
+}

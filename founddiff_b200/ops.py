@@ -566,11 +566,15 @@ def gn_scale_shift_silu(y, sums, gamma, beta, scale, shift, ss_stride, skip, out
               "fd_gn_scale_shift_silu")
 
 
-def flash_attn_d32(qkv, out, B, N, heads, scale):
-    """lucidrains bottleneck Attention (src/denoising_diffusion_pytorch.py:257-279); qkv (B,N,3*heads*32), out (B,N,heads*32)."""
-    with _launched("flash_attn_d32", f"{B}x{N}x{heads}"):
-        check(_lib.load().fd_flash_attn_d32(_p(qkv), _p(out), B, N, heads, float(scale), dtype_code(qkv.dtype), _stream()),
-              "fd_flash_attn_d32")
+def flash_attn_d32(qkv, out, B, N, heads, scale, impl=None):
+    """lucidrains bottleneck Attention (src/denoising_diffusion_pytorch.py:257-279); qkv (B,N,3*heads*32), out (B,N,heads*32).
+    impl: "tc" = tcgen05 / tensor-memory kernel (default), "mma" = the mma.sync kernel of round 1 (FD_FLASH_TC=0 selects it)."""
+    if impl is None:
+        impl = "mma" if _os.environ.get("FD_FLASH_TC", "1") == "0" else "tc"
+    lib = _lib.load()
+    fn, name = (lib.fd_flash_attn_d32_tc, "fd_flash_attn_d32_tc") if impl == "tc" else (lib.fd_flash_attn_d32, "fd_flash_attn_d32")
+    with _launched("flash_attn_d32" + ("_tc" if impl == "tc" else ""), f"{B}x{N}x{heads}"):
+        check(fn(_p(qkv), _p(out), B, N, heads, float(scale), dtype_code(qkv.dtype), _stream()), name)
 
 
 def linear_attention(qkv, wout, bias, g, out, B, H, W, heads, dim, scale=32 ** -0.5, prefer_tc=True):

@@ -329,6 +329,9 @@ int fd_gn_scale_shift_silu(const void* y, const float* sums, const float* gamma,
  * out[b, i, h*32 + d] = sum_j softmax_j(scale * q_i . k_j) v_j[d];  qkv (B, N, 3*heads*32) = [q | k | v] channels-last
  * ('b (h c)' order, as produced by the to_qkv 1x1 GEMM); out (B, N, heads*32).  dtype bf16 / fp16. */
 int fd_flash_attn_d32(const void* qkv, void* out, int B, int N, int heads, float scale, int dtype, cudaStream_t stream);
+/* The same op on tcgen05 / tensor memory (fd_flash_attn_tc.cu): 128-query CTAs, S = Q K^T and O_j = P_j V_j as tcgen05.mma with
+ * TMEM accumulators, softmax by the thread that owns the TMEM lane of its query row.  Any N; 16-byte aligned pointers. */
+int fd_flash_attn_d32_tc(const void* qkv, void* out, int B, int N, int heads, float scale, int dtype, cudaStream_t stream);
 
 /* Secondary path: LinearAttention (:227-255) between to_qkv and to_out, same qkv layout as above.
  *   fd_linattn_context: ctx_raw[b,h,d,e] += sum_n exp(k[n,d] - kmax[d]) v[n,e];  ksum[b,hd] += sum_n exp(k - kmax)

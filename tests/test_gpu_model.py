@@ -330,6 +330,9 @@ def test_benchmarked_batch16_vs_oracle(model, state_dict):
     eng = model.model.engine(B, H, H, "cuda")
     print("engine paths at B=16:", eng.paths)
     assert eng.B == 16 and len(eng.paths) == 9 and all(v != "reference-layout" for v in eng.paths.values()), eng.paths
+    # the full- and half-resolution levels take the time-sliced scan with chained segments at this batch (hand-over of the state
+    # between blocks through global memory): this test is the model-level check of that path
+    assert sum("chained segments" in v for v in eng.paths.values()) >= 4, eng.paths
     pick = [0, 7, 15]
     otrace = []
     ref = O.sample(state_dict, ldct[pick], noise[pick], sampling_timesteps=2, trace=otrace)[-1]
