@@ -168,6 +168,12 @@ def main():
                                                       N, R if fuse else 0, plan), args.iters)
             report(f"scan_tm {'TW' + str(-plan) if plan < 0 else 'S' + str(plan)}", f"{B}x{4 * D}x{L} N{N}", ms,
                    3.0 * B * 4 * D * L * es + 2.0 * B * 4 * N * L * 4, 9.0 * B * 4 * D * L * N)
+            nseg, ws_floats = ops.scan_tm_chain_plan(B, D, H, H, N, R) if fuse else (0, 0)
+            if nseg > 1:                     # what the engine launches at this level: the same kernel with chained segments
+                ws = torch.zeros(ws_floats, device="cuda")
+                ms = timeit(lambda: ops.selective_scan_tm_chained(xs, xdbl, A, dtw, bias, Dp, ws, y, B, D, H, H, N, R), args.iters)
+                report(f"scan_tm TW{-plan} x{nseg} chained", f"{B}x{4 * D}x{L} N{N}", ms,
+                       3.0 * B * 4 * D * L * es + 2.0 * B * 4 * N * L * 4, 9.0 * B * 4 * D * L * N)
             del xz, xs, xdbl, dts, carry, y
     if args.only in ("", "norm"):
         from founddiff_b200.engine import _view_ptr

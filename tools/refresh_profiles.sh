@@ -18,3 +18,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:ln_g
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:dwconv_tm -c 1 -o gpurun_out/final_dwconv_tm -f \
     python bench_micro.py --only tm --iters 1 > /dev/null 2>&1
 ls -la gpurun_out/final_* | head -20
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:flash_attn_d32_tc -c 1 -o gpurun_out/final_flash_tc -f \
+    python bench_micro.py --only flash --pick 1 --iters 1 > /dev/null 2>&1
+ls -la gpurun_out/final_* | head -20
