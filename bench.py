@@ -230,7 +230,10 @@ def conv_algorithmic(detail, es):
     k, s = int(parts[2][1:]), int(parts[3][1:])
     up = 2 if "up2" in parts else 1
     ho, wo = h * up // s, w * up // s
-    flops = 2.0 * b * ho * wo * cout * k * k * (c0 + c1)
+    # nearest x2 upsample + 3x3 runs as 4 output phases of a 2x2 convolution over the low-resolution input (pre-summed weights):
+    # 4 taps per output pixel are EXECUTED, not 9 — counting the reference's 9 gave "TFLOP/s" above the hardware peak
+    taps = 4 if up == 2 else k * k
+    flops = 2.0 * b * ho * wo * cout * taps * (c0 + c1)
     byts = (b * h * w * (c0 + c1) + b * ho * wo * cout) * es
     return byts, flops
 

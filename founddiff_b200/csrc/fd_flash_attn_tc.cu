@@ -19,6 +19,15 @@
 // Roof of the op at d = 32: MUFU.EX2, one per score (128 FLOPs per exp; 16 / clk / SM = ~560 TFLOP/s), not the tensor pipe.
 // The row sums come from the tensor core as well: V^T carries a row of ones, so column 32 of O_j is sum_k P_j[q, k] over the
 // SAME rounded P that multiplies V.
+// Measured at 16 x 4096 tokens x 4 heads (B200, bench_micro.py --only flash): 455 us = 302 TFLOP/s, MUFU pipe 56 % busy
+// (profiles/r2_final_ncu_flash_tc.txt; the mma.sync kernel of round 1: 633 us).  Three restructurings were built, verified against
+// the same tests and measured SLOWER, then removed: (a) exponentials as 16-bit pairs, one MUFU op per two (FD_FLASH_PACKED=1 keeps
+// this one as a switch): 476 us; (b) two threads per query row (256 threads, 123 registers, row maxima exchanged behind 64-thread
+// named barriers): 521 us; (c) key tiles of 64 with the score accumulator double-buffered in tensor memory so that S_{j+1} is ready a
+// whole tile ahead: 511 us.  None of MUFU throughput, warps per scheduler or the S latency is what limits this form; what is left
+// is the one block barrier per tile with a single issuing thread behind it (12 % of the stall samples sit on that barrier) and the
+// fixed-latency waits between dependent MUFU / FFMA / F2FP of a thread's own row — the next step is a warp-specialised pipeline
+// (dedicated MMA / load warps, two softmax groups on different query tiles, mbarriers instead of the block barrier).
 #include <stdlib.h>
 #include <type_traits>
 
