@@ -319,6 +319,31 @@ def test_geometry_check():
             UnetEngine.check_geometry(40, 80, dt)
 
 
+def test_chained_scan_plan_is_host_logic(monkeypatch):
+    """fd_scan_tm_chain_plan (no launch, runs without a GPU: the SM count falls back to 148): the benchmark's time-sliced levels are
+    cut into segments of 16 chunks, the workspace is ticket counter + one flag and one carried state (dstate x 32 floats) per link,
+    short rows and the channel-per-lane levels are not chained, and FD_SCAN_CHAIN overrides per call."""
+    from founddiff_b200 import ops
+    monkeypatch.delenv("FD_SCAN_CHAIN", raising=False)
+
+    def ws(B, D, N, nseg):
+        links = B * 4 * (D // 32) * (nseg - 1)
+        return ((1 + links + 3) // 4) * 4 + links * N * 32
+
+    for B, D, H, N, R, tw, st in ((16, 128, 512, 4, 4, 8, 16), (16, 128, 256, 8, 4, 8, 8), (16, 256, 256, 8, 8, 4, 8)):
+        assert ops.scan_tm_plan(B, D, H, H, N, R) == -tw
+        nseg, floats = ops.scan_tm_chain_plan(B, D, H, H, N, R)
+        nchunks = (H // 2) ** 2 // (tw * st)
+        assert nseg == nchunks // 16 and nchunks % nseg == 0 and floats == ws(B, D, N, nseg), (B, D, H, N, R, nseg, floats)
+    assert ops.scan_tm_chain_plan(16, 1024, 64, 64, 32, 0) == (0, 0)          # channel-per-lane level
+    assert ops.scan_tm_chain_plan(2, 128, 48, 80, 4, 4) == (0, 0)             # short ragged rows: segmented kernel
+    assert ops.scan_tm_chain_plan(2, 128, 128, 128, 4, 4) == (0, 0)           # 32 chunks: fewer than 4 segments of 16
+    monkeypatch.setenv("FD_SCAN_CHAIN", "4")
+    assert ops.scan_tm_chain_plan(2, 128, 128, 128, 4, 4) == (4, ws(2, 128, 4, 4))
+    monkeypatch.setenv("FD_SCAN_CHAIN", "0")
+    assert ops.scan_tm_chain_plan(16, 128, 512, 512, 4, 4) == (0, 0)
+
+
 def test_c_abi_header_is_plain_c_and_links_from_c(tmp_path):
     """include/founddiff_b200.h compiles as pedantic C99 and as C++17, and a C program (examples/c_host.c) links the library,
     reads its version and gets FD_ERR_BAD_ARGUMENT from the argument validation — no torch, no C++ types across the boundary."""
