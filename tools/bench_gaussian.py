@@ -36,7 +36,8 @@ ms = e0.elapsed_time(e1) / 3
 print(f"secondary path DDIM-2 sample(): {ms:.1f} ms per call, {B / ms * 1e3:.1f} images/s; peak memory "
       f"{torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
 # breakdown: graph replay alone vs eager step vs full sample() in both modes
-replay = diff._graphs[id(eng)].replay if diff._graphs else None
+entry = diff._graphs.get("step") if diff._graphs else None          # (graph, engine) since the round-1 review's fix
+replay = entry[0].replay if entry else None
 if replay is not None:
     e0.record()
     for _ in range(5):
